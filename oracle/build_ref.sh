@@ -1,0 +1,44 @@
+#!/usr/bin/env bash
+# Builds the UNMODIFIED reference C path (hartallo) into oracle/_ref/ from the sources where they lie under
+# $HL_REFERENCE (default /root/reference).  Nothing from the reference is copied into the repository: the two
+# one-line, non-algorithmic patches (decoder bit-reader inline asm; rdtsc timer) are applied with sed to temporary
+# copies that are deleted when the build ends.  Recipe = SURVEY.md Appendix A.
+#
+# TEST INFRASTRUCTURE ONLY: the product (hartallo_b200/) never links or executes anything produced here.
+set -euo pipefail
+REF="${HL_REFERENCE:-/root/reference}"
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+JOBS="${JOBS:-$(nproc)}"
+if [ ! -d "$REF/source/h264" ]; then
+  echo "build_ref: reference tree not found at $REF (GPU box uses the prebuilt oracle/_ref)" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+TMP="$(mktemp -d)"
+trap 'rm -rf "$TMP"' EXIT
+mkdir -p "$TMP/inc/hartallo/h264" "$TMP/shim" "$TMP/obj" "$TMP/src"
+# patch 1: decoder-only bit reader uses malformed GNU inline asm -> force the portable branch
+sed '203s/#if defined(__GNUC__)/#if 0/' "$REF/include/hartallo/h264/hl_codec_264_bits.h" > "$TMP/inc/hartallo/h264/hl_codec_264_bits.h"
+# patch 2: timing helper only ('#error "Not implemented: use rdtsc inline asm"')
+sed '376s/.*/    return __builtin_ia32_rdtsc();/' "$REF/source/hl_cpu.c" > "$TMP/src/hl_cpu.c"
+# workaround 1: C files include <cfloat>
+printf '#include <float.h>\n#include <limits.h>\n' > "$TMP/shim/cfloat"
+# workaround 2: struct tags first declared inside prototypes + missing <limits.h>
+{ printf '#include <limits.h>\n#include <float.h>\n'; \
+  grep -rhoE 'struct +hl_[a-z0-9_]+' "$REF/include" "$REF/source" | sed -E 's/struct +/struct /' | sort -u | sed 's/$/;/'; } > "$TMP/fwd.h"
+CF="-std=gnu99 -O2 -w -fPIC -fcommon -D_GNU_SOURCE -DHL_DISABLE_INTRIN=1 -DHL_DISABLE_ASM=1 -include $TMP/fwd.h -I$TMP/inc -I$REF/include -I$TMP/shim"
+SRCS=$(ls "$REF"/source/*.c "$REF"/source/h264/*.c | grep -v /test | grep -v hl_codec_264_me.c | grep -v hl_x86_globals.c | grep -v '/hl_cpu.c$')
+SRCS="$SRCS $TMP/src/hl_cpu.c"
+echo "$SRCS" | tr ' ' '\n' | grep -v '^$' | xargs -P "$JOBS" -I{} sh -c 'gcc '"$CF"' -c "$1" -o '"$TMP"'/obj/$(basename "${1%.c}").o' _ {}
+rm -f "$OUT/libhartallo_ref.a"
+ar rcs "$OUT/libhartallo_ref.a" "$TMP"/obj/*.o
+# shared object with every reference symbol visible: lets tests call the *_cpp kernels directly (ctypes)
+gcc -shared -o "$OUT/libhartallo_ref.so" -Wl,--whole-archive "$OUT/libhartallo_ref.a" -Wl,--no-whole-archive -lpthread -lm -ldl
+# driver (our code, reference public API + link-time wrappers that record per-MB decisions / per-candidate traces)
+WRAPS="-Wl,--wrap=hl_codec_264_interpol_luma -Wl,--wrap=hl_codec_264_residual_write_block_cavlc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc -Wl,--wrap=hl_codec_264_me_ds_mb_find_best_cost -Wl,--wrap=hl_codec_264_nal_slice_data_encode"
+if [ -f "$HERE/ref_driver.c" ]; then
+  gcc $CF -c "$HERE/ref_driver.c" -o "$TMP/obj_driver.o"
+  gcc "$TMP/obj_driver.o" $WRAPS "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_ref_driver"
+fi
+echo "build_ref: built $(ls "$OUT")"
