@@ -41,4 +41,9 @@ if [ -f "$HERE/ref_driver.c" ]; then
   gcc $CF -c "$HERE/ref_driver.c" -o "$TMP/obj_driver.o"
   gcc "$TMP/obj_driver.o" $WRAPS "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_ref_driver"
 fi
+# kernel-level harness: reference kernels behind plain-pointer entry points (ctypes)
+if [ -f "$HERE/ref_kernels.c" ]; then
+  gcc $CF -c "$HERE/ref_kernels.c" -o "$TMP/obj_kernels.o"
+  gcc -shared -o "$OUT/libref_kernels.so" "$TMP/obj_kernels.o" -Wl,--whole-archive "$OUT/libhartallo_ref.a" -Wl,--no-whole-archive -lpthread -lm -ldl
+fi
 echo "build_ref: built $(ls "$OUT")"

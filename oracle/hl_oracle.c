@@ -1,0 +1,327 @@
+/*
+ * hl_oracle.c -- CPU restatement (plain C, scalar loops) of the reference's arithmetic for the encoder pixel hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this.
+ * The product (hartallo_b200/) never links, imports or executes it.
+ *
+ * PINNED: every function below is checked bit-for-bit against the reference's own function (called through
+ * oracle/_ref/libref_kernels.so, built from /root/reference by oracle/build_ref.sh) by tests/test_oracle_pinned.py,
+ * and against golden vectors generated from the reference and committed under tests/golden/.
+ *
+ * Each function cites the reference file:line it restates.  Written independently of the CUDA code (per-sample
+ * formulas straight from the structure of the reference / H.264 clauses, no shared source).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define HLO_API __attribute__((visibility("default")))
+
+static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static int clip1(int v) { return clip3(0, 255, v); }
+
+/* --- luma sample fetch ------------------------------------------------------------------------------------------
+ * source/h264/hl_codec_264_pred_inter.c:384-396 + source/h264/hl_codec_264_interpol.c:74-131:
+ * the partition ORIGIN is clipped to [-17, W+17] x [-17, H+17] (not each sample), then every sample is fetched through
+ * an index table that clamps its coordinates to the picture. */
+typedef struct { const uint8_t* p; int W, H, X, Y; } luma_src_t;
+static int L(const luma_src_t* s, int dx, int dy)
+{
+    int x = clip3(0, s->W - 1, s->X + dx), y = clip3(0, s->H - 1, s->Y + dy);
+    return s->p[y * s->W + x];
+}
+/* include/hartallo/h264/hl_codec_264_macros.h:73 Tap6Filter */
+static int tap6(int E, int F, int G, int H, int I, int J) { return E - 5 * (F + I) + 20 * (G + H) + J; }
+static int b1(const luma_src_t* s, int x, int y) { return tap6(L(s, x - 2, y), L(s, x - 1, y), L(s, x, y), L(s, x + 1, y), L(s, x + 2, y), L(s, x + 3, y)); }
+static int h1(const luma_src_t* s, int x, int y) { return tap6(L(s, x, y - 2), L(s, x, y - 1), L(s, x, y), L(s, x, y + 1), L(s, x, y + 2), L(s, x, y + 3)); }
+static int half_b(const luma_src_t* s, int x, int y) { return clip1((b1(s, x, y) + 16) >> 5); }
+static int half_h(const luma_src_t* s, int x, int y) { return clip1((h1(s, x, y) + 16) >> 5); }
+static int half_j(const luma_src_t* s, int x, int y)
+{
+    int j1 = tap6(b1(s, x, y - 2), b1(s, x, y - 1), b1(s, x, y), b1(s, x, y + 1), b1(s, x, y + 2), b1(s, x, y + 3));
+    return clip1((j1 + 512) >> 10);
+}
+
+/* hl_codec_264_interpol_luma, pred_inter.c:339-885 (dispatch :401-845; kernels include/hartallo/h264/hl_codec_264_interpol.h:162-923).
+ * Table 8-12 of the standard.  out is a 16x16 u8 array (stride 16); only partW x partH is written. */
+HLO_API void hlo_interp_luma(const uint8_t* ref, int W, int H, int xL, int yL, int partW, int partH, int mvx, int mvy, uint8_t* out)
+{
+    luma_src_t s;
+    int xf = mvx & 3, yf = mvy & 3, x, y;
+    s.p = ref; s.W = W; s.H = H;
+    s.X = clip3(-17, W + 17, xL + (mvx >> 2));
+    s.Y = clip3(-17, H + 17, yL + (mvy >> 2));
+    for (y = 0; y < partH; ++y) for (x = 0; x < partW; ++x) {
+        int G = L(&s, x, y), v;
+        switch (xf + 4 * yf) {
+        case 0: v = G; break;
+        case 1: v = (G + half_b(&s, x, y) + 1) >> 1; break;                              /* a */
+        case 2: v = half_b(&s, x, y); break;                                               /* b */
+        case 3: v = (L(&s, x + 1, y) + half_b(&s, x, y) + 1) >> 1; break;                  /* c */
+        case 4: v = (G + half_h(&s, x, y) + 1) >> 1; break;                              /* d */
+        case 5: v = (half_b(&s, x, y) + half_h(&s, x, y) + 1) >> 1; break;                 /* e */
+        case 6: v = (half_b(&s, x, y) + half_j(&s, x, y) + 1) >> 1; break;                 /* f */
+        case 7: v = (half_b(&s, x, y) + half_h(&s, x + 1, y) + 1) >> 1; break;             /* g */
+        case 8: v = half_h(&s, x, y); break;                                               /* h */
+        case 9: v = (half_h(&s, x, y) + half_j(&s, x, y) + 1) >> 1; break;                 /* i */
+        case 10: v = half_j(&s, x, y); break;                                              /* j */
+        case 11: v = (half_j(&s, x, y) + half_h(&s, x + 1, y) + 1) >> 1; break;            /* k */
+        case 12: v = (L(&s, x, y + 1) + half_h(&s, x, y) + 1) >> 1; break;                 /* n */
+        case 13: v = (half_h(&s, x, y) + half_b(&s, x, y + 1) + 1) >> 1; break;            /* p */
+        case 14: v = (half_j(&s, x, y) + half_b(&s, x, y + 1) + 1) >> 1; break;            /* q */
+        default: v = (half_h(&s, x + 1, y) + half_b(&s, x, y + 1) + 1) >> 1; break;        /* r */
+        }
+        out[y * 16 + x] = (uint8_t)v;
+    }
+}
+
+/* hl_codec_264_interpol_chroma_cpp, pred_inter.c:888-940 -> hl_codec_264_interpol_chroma_cat1_u8_cpp, interpol.c:337-385
+ * (sample loader interpol.c:250-334: per-sample clamp).  One plane; out is 8x8 (stride 8).  xL,yL = LUMA origin of
+ * the partition, mv = chroma mv (= luma mv for 4:2:0 frame MBs, utils.c:834-851). */
+HLO_API void hlo_interp_chroma(const uint8_t* refc, int Wc, int Hc, int xL, int yL, int partWc, int partHc, int mvx, int mvy, uint8_t* out)
+{
+    int x0 = (xL >> 1) + (mvx >> 3), y0 = (yL >> 1) + (mvy >> 3), xf = mvx & 7, yf = mvy & 7, x, y;
+    for (y = 0; y < partHc; ++y) for (x = 0; x < partWc; ++x) {
+        int xa = clip3(0, Wc - 1, x0 + x), xb = clip3(0, Wc - 1, x0 + x + 1);
+        int ya = clip3(0, Hc - 1, y0 + y), yc = clip3(0, Hc - 1, y0 + y + 1);
+        int A = refc[ya * Wc + xa], B = refc[ya * Wc + xb], C = refc[yc * Wc + xa], D = refc[yc * Wc + xb];
+        out[y * 8 + x] = (uint8_t)(((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6);
+    }
+}
+
+/* hl_codec_264_transf_frw_residual4x4_cpp, transf.c:716-768: W = Cf . X . Cf^T */
+HLO_API void hlo_fwd4x4(const int32_t* in, int32_t* out)
+{
+    static const int Cf[4][4] = {{1, 1, 1, 1}, {2, 1, -1, -2}, {1, -1, -1, 1}, {1, -2, 2, -1}};
+    int t[4][4], i, j, k;
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { t[i][j] = 0; for (k = 0; k < 4; ++k) t[i][j] += Cf[i][k] * in[k * 4 + j]; }
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { int a = 0; for (k = 0; k < 4; ++k) a += t[i][k] * Cf[j][k]; out[i * 4 + j] = a; }
+}
+
+/* HL_CODEC_264_QUANT_MF, source/h264/hl_codec_264_tables.c:10-17 (spec values) */
+static int quant_mf(int qp, int i, int j)
+{
+    static const int a[6][3] = {{13107, 5243, 8066}, {11916, 4660, 7490}, {10082, 4194, 6554}, {9362, 3647, 5825}, {8192, 3355, 5243}, {7282, 2893, 4559}};
+    int k = (i % 2 == 0 && j % 2 == 0) ? 0 : ((i % 2 == 1 && j % 2 == 1) ? 1 : 2);
+    return a[qp % 6][k];
+}
+/* normAdjust4x4, include/hartallo/h264/hl_codec_264_macros.h:69; LevelScale4x4 = flat16 * normAdjust, pps.c:38-80 */
+static int level_scale(int qp, int i, int j)
+{
+    static const int v[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+    int k = (i % 2 == 0 && j % 2 == 0) ? 0 : ((i % 2 == 1 && j % 2 == 1) ? 1 : 2);
+    return 16 * v[qp % 6][k];
+}
+
+/* hl_codec_264_quant_frw4x4_scale_ac_cpp, quant.c:116-137; tables.c:19-45 (qbits, f) */
+HLO_API void hlo_quant4x4(int qp, int intra, const int32_t* in, int32_t* out)
+{
+    int qbits = 15 + qp / 6, f = (1 << qbits) / (intra ? 3 : 6), i, j;
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) {
+        int w = in[i * 4 + j], z = (abs(w) * quant_mf(qp, i, j) + f) >> qbits;
+        out[i * 4 + j] = w >= 0 ? z : -z;
+    }
+}
+/* hl_codec_264_quant_frw4x4_scale_dc_luma_cpp quant.c:141-165 (n=16), hl_codec_264_quant_frw2x2_scale_dc_chroma_cpp quant.c:168-189 (n=4) */
+HLO_API void hlo_quant_dc(int qp, int intra, const int32_t* in, int32_t* out, int n)
+{
+    int qbits = 15 + qp / 6, f = (1 << qbits) / (intra ? 3 : 6), i;
+    for (i = 0; i < n; ++i) { int w = in[i], z = (abs(w) * quant_mf(qp, 0, 0) + 2 * f) >> (qbits + 1); out[i] = w >= 0 ? z : -z; }
+}
+
+/* hl_codec_264_quant_scale_residual4x4_cpp, quant.c:68-111 */
+HLO_API void hlo_dequant4x4(int qp, int keep_dc, const int32_t* c, int32_t* d)
+{
+    int i, j;
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) {
+        int v = c[i * 4 + j] * level_scale(qp, i, j);
+        d[i * 4 + j] = qp >= 24 ? v << (qp / 6 - 4) : (v + (1 << (3 - qp / 6))) >> (4 - qp / 6);
+    }
+    if (keep_dc) d[0] = c[0];
+}
+/* hl_codec_264_transf_inverse_residual4x4_cpp, transf.c:420-456 */
+HLO_API void hlo_inv4x4(const int32_t* d, int32_t* r)
+{
+    int e[4][4], f[4][4], g[4][4], h[4][4], i, j;
+    for (i = 0; i < 4; ++i) {
+        e[i][0] = d[i * 4] + d[i * 4 + 2]; e[i][1] = d[i * 4] - d[i * 4 + 2];
+        e[i][2] = (d[i * 4 + 1] >> 1) - d[i * 4 + 3]; e[i][3] = d[i * 4 + 1] + (d[i * 4 + 3] >> 1);
+        f[i][0] = e[i][0] + e[i][3]; f[i][1] = e[i][1] + e[i][2]; f[i][2] = e[i][1] - e[i][2]; f[i][3] = e[i][0] - e[i][3];
+    }
+    for (j = 0; j < 4; ++j) {
+        g[0][j] = f[0][j] + f[2][j]; g[1][j] = f[0][j] - f[2][j]; g[2][j] = (f[1][j] >> 1) - f[3][j]; g[3][j] = f[1][j] + (f[3][j] >> 1);
+        h[0][j] = g[0][j] + g[3][j]; h[1][j] = g[1][j] + g[2][j]; h[2][j] = g[1][j] - g[2][j]; h[3][j] = g[0][j] - g[3][j];
+    }
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) r[i * 4 + j] = (h[i][j] + 32) >> 6;
+}
+/* hl_codec_264_transf_scale_residual4x4, transf.c:376-417 = dequant + inverse */
+HLO_API void hlo_dequant_inv4x4(int qp, int keep_dc, const int32_t* c, int32_t* r)
+{
+    int32_t d[16];
+    hlo_dequant4x4(qp, keep_dc, c, d);
+    hlo_inv4x4(d, r);
+}
+
+static void hadamard4(const int32_t* in, int32_t* out)
+{
+    static const int Hm[4][4] = {{1, 1, 1, 1}, {1, 1, -1, -1}, {1, -1, -1, 1}, {1, -1, 1, -1}};
+    int t[4][4], i, j, k;
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { t[i][j] = 0; for (k = 0; k < 4; ++k) t[i][j] += Hm[i][k] * in[k * 4 + j]; }
+    for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { int a = 0; for (k = 0; k < 4; ++k) a += t[i][k] * Hm[j][k]; out[i * 4 + j] = a; }
+}
+/* hl_codec_264_transf_frw_hadamard4x4_dc_luma_cpp, transf.c:774-841: H.X.H then >>1 */
+HLO_API void hlo_hadamard4x4_dc_luma(const int32_t* in, int32_t* out)
+{
+    int i;
+    hadamard4(in, out);
+    for (i = 0; i < 16; ++i) out[i] >>= 1;
+}
+/* hl_codec_264_transf_scale_luma_dc_coeff_intra16x16_cpp, transf.c:498-608 */
+HLO_API void hlo_scale_luma_dc(int qp, const int32_t* c, int32_t* dcY)
+{
+    int32_t f[16];
+    int i, scale = level_scale(qp, 0, 0);
+    hadamard4(c, f);
+    for (i = 0; i < 16; ++i) dcY[i] = qp >= 36 ? (f[i] * scale) << (qp / 6 - 6) : (f[i] * scale + (1 << (5 - qp / 6))) >> (6 - qp / 6);
+}
+/* hl_codec_264_transf_frw_hadamard2x2_dc_chroma, transf.c:843-868 */
+HLO_API void hlo_hadamard2x2(const int32_t* in, int32_t* out)
+{
+    int a = in[0] + in[2], b = in[1] + in[3], c = in[0] - in[2], d = in[1] - in[3];
+    out[0] = a + b; out[1] = a - b; out[2] = c + d; out[3] = c - d;
+}
+/* hl_codec_264_transf_scale_chroma_dc_coeff (ChromaArrayType 1), transf.c:612-700 */
+HLO_API void hlo_scale_chroma_dc(int qpc, const int32_t* c, int32_t* dc)
+{
+    int32_t f[4];
+    int i, scale = level_scale(qpc, 0, 0);
+    hlo_hadamard2x2(c, f);
+    for (i = 0; i < 4; ++i) dc[i] = ((f[i] * scale) << (qpc / 6)) >> 5;
+}
+
+/* hl_math_sad4x4_u8_cpp, source/hl_math.c:239-257 */
+HLO_API int hlo_sad4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
+{
+    int s = 0, x, y;
+    for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) s += abs((int)a[y * sa + x] - (int)b[y * sb + x]);
+    return s;
+}
+/* hl_math_satd4x4_u8_cpp, source/hl_math.c:283-357: sum |H.D.H| >> 1 */
+HLO_API int hlo_satd4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
+{
+    int32_t d[16], t[16];
+    int s = 0, x, y;
+    for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) d[y * 4 + x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+    hadamard4(d, t);
+    for (x = 0; x < 16; ++x) s += abs(t[x]);
+    return s >> 1;
+}
+/* hl_math_addclip_4x4_u8xi32_cpp, include/hartallo/hl_math.h:261,303-323: the sum is stored to a uint8_t BEFORE the
+ * clip, so it wraps modulo 256. */
+HLO_API void hlo_addclip_u8xi32(const uint8_t* pred, const int32_t* res, uint8_t* out)
+{
+    int i;
+    for (i = 0; i < 16; ++i) out[i] = (uint8_t)((int)pred[i] + res[i]);
+}
+/* hl_math_addclip_4x4_cpp, hl_math.h:278-300: Clip3(0,255, pred + res) */
+HLO_API void hlo_addclip_i32(const int32_t* pred, const int32_t* res, int32_t* out)
+{
+    int i;
+    for (i = 0; i < 16; ++i) out[i] = clip1(pred[i] + res[i]);
+}
+
+/* zig-zag: Scan4x4_L / InverseScan4x4, include/hartallo/h264/hl_codec_264_utils.h:146-180 */
+static const int kZZ[16][2] = {{0, 0}, {0, 1}, {1, 0}, {2, 0}, {1, 1}, {0, 2}, {0, 3}, {1, 2}, {2, 1}, {3, 0}, {3, 1}, {2, 2}, {1, 3}, {2, 3}, {3, 2}, {3, 3}};
+HLO_API void hlo_zigzag(const int32_t* m, int32_t* lv) { int k; for (k = 0; k < 16; ++k) lv[k] = m[kZZ[k][0] * 4 + kZZ[k][1]]; }
+HLO_API void hlo_inv_zigzag(const int32_t* lv, int32_t* m) { int k; for (k = 0; k < 16; ++k) m[kZZ[k][0] * 4 + kZZ[k][1]] = lv[k]; }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * CAVLC bit length of a residual block in RDO mode: hl_codec_264_residual_write_block_cavlc, residual.c:757-898,
+ * writers cavlc.c:652-836 (tables = H.264 Tables 9-5, 9-7..9-10), level table cavlc.c:59-104.
+ * nC is given by the caller (residual.c:698-755 computes it from neighbour state).
+ * Returns total bits; *single_ctr per residual.c:881-897; *total_coeff as stored at residual.c:797-805. */
+static const uint8_t kCT[3][4][17] = {
+    {{1, 6, 8, 9, 10, 11, 13, 13, 13, 14, 14, 15, 15, 16, 16, 16, 16}, {0, 2, 6, 8, 9, 10, 11, 13, 13, 14, 14, 15, 15, 15, 16, 16, 16},
+     {0, 0, 3, 7, 8, 9, 10, 11, 13, 13, 14, 14, 15, 15, 16, 16, 16}, {0, 0, 0, 5, 6, 7, 8, 9, 10, 11, 13, 14, 14, 15, 15, 16, 16}},
+    {{2, 6, 6, 7, 8, 8, 9, 11, 11, 12, 12, 12, 13, 13, 13, 14, 14}, {0, 2, 5, 6, 6, 7, 8, 9, 11, 11, 12, 12, 13, 13, 14, 14, 14},
+     {0, 0, 3, 6, 6, 7, 8, 9, 11, 11, 12, 12, 13, 13, 13, 14, 14}, {0, 0, 0, 4, 4, 5, 6, 6, 7, 9, 11, 11, 12, 13, 13, 13, 14}},
+    {{4, 6, 6, 6, 7, 7, 7, 7, 8, 8, 9, 9, 9, 10, 10, 10, 10}, {0, 4, 5, 5, 5, 5, 6, 6, 7, 8, 8, 9, 9, 9, 10, 10, 10},
+     {0, 0, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10}, {0, 0, 0, 4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 9, 10, 10, 10}}};
+static const uint8_t kTZ[15][16] = {
+    {1, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 9}, {3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 6, 6}, {4, 3, 3, 3, 4, 4, 3, 3, 4, 5, 5, 6, 5, 6},
+    {5, 3, 4, 4, 3, 3, 3, 4, 3, 4, 5, 5, 5}, {4, 4, 4, 3, 3, 3, 3, 3, 4, 5, 4, 5}, {6, 5, 3, 3, 3, 3, 3, 3, 4, 3, 6}, {6, 5, 3, 3, 3, 2, 3, 4, 3, 6},
+    {6, 4, 5, 3, 2, 2, 3, 3, 6}, {6, 6, 4, 2, 2, 3, 2, 5}, {5, 5, 3, 2, 2, 2, 4}, {4, 4, 3, 3, 1, 3}, {4, 4, 2, 1, 3}, {3, 3, 1, 2}, {2, 2, 1}, {1, 1}};
+static const uint8_t kRB[7][15] = {{1, 1}, {1, 2, 2}, {2, 2, 2, 2}, {2, 2, 2, 3, 3}, {2, 2, 3, 3, 3, 3}, {2, 3, 3, 3, 3, 3, 3}, {3, 3, 3, 3, 3, 3, 3, 4, 5, 6, 7, 8, 9, 10, 11}};
+
+HLO_API int hlo_cavlc_bits(const int32_t* lv, int max_num_coeff, int nC, int32_t* single_ctr, int32_t* total_coeff)
+{
+    int nz[16], run[16] = {0}, tc = 0, t1 = 0, tz = 0, k = -1, j, bits = 0, cnt_t1 = 1, seen = 0, sl, zl = 0;
+    for (j = 0; j < max_num_coeff; ++j) {          /* residual.c:761-784 (reverse scan) */
+        int c = lv[max_num_coeff - 1 - j];
+        if (c) {
+            nz[tc++] = c; seen = 1; ++k;
+            if (cnt_t1) { if (c == 1 || c == -1) { ++t1; cnt_t1 = t1 < 3; } else cnt_t1 = 0; }
+        } else if (seen) { ++run[k]; ++tz; }
+    }
+    bits += nC >= 8 ? 6 : kCT[nC < 2 ? 0 : (nC < 4 ? 1 : 2)][t1][tc];     /* cavlc.c:652-706 */
+    *total_coeff = tc;
+    *single_ctr = 9;                                /* residual.c:883 (only meaningful when tc > 0) */
+    if (tc > 0) {
+        static const int thr[7] = {0, 3, 6, 12, 24, 48, 1 << 15};
+        sl = (tc > 10 && t1 < 3) ? 1 : 0;
+        for (j = 0; j < tc; ++j) {                  /* residual.c:819-859 */
+            int lc, prefix, ssz;
+            if (j < t1) { bits += 1; continue; }
+            lc = nz[j] > 0 ? (nz[j] << 1) - 2 : -(nz[j] << 1) - 1;
+            if (j == t1 && t1 < 3 && lc >= 2) lc -= 2;
+            /* cavlc.c:59-104: prefix/suffix sizes */
+            if (sl == 0) { if (lc < 14) { prefix = lc; ssz = 0; } else if (lc < 30) { prefix = 14; ssz = 4; } else { prefix = 15; ssz = 12; } }
+            else { prefix = lc >> sl; if (prefix < 15) ssz = sl; else { prefix = 15; ssz = 12; } }
+            bits += prefix + 1 + ssz;
+            if (sl == 0) sl = 1;
+            if (abs(nz[j]) > thr[sl]) ++sl;
+        }
+        if (tc < max_num_coeff) { bits += kTZ[tc - 1][tz]; zl = tz; }        /* residual.c:862-873 */
+        for (j = 0; j < tc - 1 && zl > 0; ++j) { bits += kRB[(zl > 7 ? 7 : zl) - 1][run[j]]; zl -= run[j]; }
+        if (tc == 1 && abs(nz[0]) == 1) {           /* residual.c:884-896 */
+            static const int T[6] = {3, 2, 2, 1, 1, 1};
+            int rn = zl > 0 ? run[0] : 0;
+            *single_ctr = rn < 6 ? T[rn] : 0;
+        }
+    }
+    return bits;
+}
+
+/* nC from neighbour counts (residual.c:742-754); nA/nB < 0 = not available */
+HLO_API int hlo_nC(int nA, int nB)
+{
+    if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1;
+    if (nA >= 0) return nA;
+    if (nB >= 0) return nB;
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One luma 4x4 trial encode as done for every ME candidate: hl_codec_264_me_ds_mb_compute_cost_mode, me_ds.c:607-670
+ * -> hl_codec_264_rdo_mb_compute_inter_luma4x4, rdo.c:2784-2830.
+ * src/pred: 4x4 u8 with strides.  Returns distortion (SAD); *nonzero, levels[16] (zig-zag) filled when nonzero. */
+HLO_API int hlo_trial_luma4x4(const uint8_t* src, int ss, const uint8_t* pred, int ps, int qp, int32_t* levels, int32_t* nonzero)
+{
+    int32_t res[16], w[16], z[16], c[16], r[16];
+    uint8_t p4[16], rec[16];
+    int x, y, all0 = 1;
+    for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) { res[y * 4 + x] = (int)src[y * ss + x] - (int)pred[y * ps + x]; p4[y * 4 + x] = pred[y * ps + x]; if (res[y * 4 + x]) all0 = 0; }
+    if (!all0) {
+        hlo_fwd4x4(res, w);
+        hlo_quant4x4(qp, 0, w, z);
+        hlo_zigzag(z, levels);
+        all0 = 1;
+        for (x = 0; x < 16; ++x) if (levels[x]) all0 = 0;
+    }
+    *nonzero = !all0;
+    if (all0) return hlo_sad4x4(src, ss, pred, ps);
+    hlo_inv_zigzag(levels, c);
+    hlo_dequant_inv4x4(qp, 0, c, r);
+    hlo_addclip_u8xi32(p4, r, rec);                /* wraps: me_ds.c:636-639 */
+    return hlo_sad4x4(src, ss, rec, 4);
+}
