@@ -1,0 +1,242 @@
+// hlb_api.cu -- C-ABI plumbing of libhl_b200.so: device selection, stream contexts, frame-store slots, host-buffer
+// wrappers around the batch kernels.  No CPU fallback anywhere: a failing CUDA call is reported as an HL_ERROR_T value.
+#include <string.h>
+
+#include "hlb_common.cuh"
+
+namespace hlb {
+static thread_local char g_err[512] = "";
+void set_last_error(const char* what, cudaError_t e, const char* file, int line)
+{
+    snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    cudaGetLastError();  // clear the sticky-less error state
+}
+int launch_me_cost(const uint8_t* d_src, const uint8_t* d_ref, int W, int H, int qp, const hlb200_me_cand_t* d_cands, int n, hlb200_me_cost_t* d_out, cudaStream_t st);
+size_t mbstate_bytes(int nmb);
+int slice_reset_state(hlb200_ctx* ctx);
+}  // namespace hlb
+using namespace hlb;
+
+static int ensure_scratch(hlb200_ctx* c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return HLB200_OK;
+    if (c->d_scratch) HLB_CUDA(cudaFree(c->d_scratch));
+    c->d_scratch = nullptr; c->scratch_bytes = 0;
+    HLB_CUDA(cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return HLB200_OK;
+}
+static size_t plane_bytes(const hlb200_ctx* c, int p) { return p == 0 ? (size_t)c->width * c->height : (size_t)(c->width >> 1) * (c->height >> 1); }
+
+// host -> device through the pinned staging buffer (so the copy is truly asynchronous and ordered on the stream)
+static int h2d(hlb200_ctx* c, void* d, const void* h, size_t bytes)
+{
+    HLB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return HLB200_OK;
+}
+static int d2h(hlb200_ctx* c, void* h, const void* d, size_t bytes)
+{
+    HLB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return HLB200_OK;
+}
+
+extern "C" {
+
+int hlb200_version(void) { return 100; }
+const char* hlb200_last_error(void) { return g_err; }
+
+int hlb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hlb200_init(int device)
+{
+    int n = 0;
+    HLB_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0 || device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "no CUDA device %d (count %d): this library has no CPU fallback", device, n); return HLB200_ERR_SYSTEM; }
+    HLB_CUDA(cudaSetDevice(device));
+    HLB_CUDA(cudaFree(0));
+    return HLB200_OK;
+}
+
+int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out)
+{
+    if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || max_refs < 1 || max_refs > HLB200_MAX_REFS) return HLB200_ERR_INVALID_PARAMETER;
+    hlb200_ctx* c = new hlb200_ctx();
+    memset(c, 0, sizeof(*c));
+    c->width = width; c->height = height; c->mbw = width >> 4; c->mbh = height >> 4; c->nmb = c->mbw * c->mbh;
+    c->max_refs = max_refs; c->nslots = max_refs + 1;
+    *out = c;
+    HLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (int p = 0; p < 3; ++p) {
+        HLB_CUDA(cudaMalloc(&c->d_src[p], plane_bytes(c, p)));
+        HLB_CUDA(cudaMalloc(&c->d_pred[p], plane_bytes(c, p)));
+        HLB_CUDA(cudaMalloc(&c->d_tmp[p], plane_bytes(c, p)));
+        for (int s = 0; s < c->nslots; ++s) {
+            HLB_CUDA(cudaMalloc(&c->d_slot[s][p], plane_bytes(c, p)));
+            HLB_CUDA(cudaMemsetAsync(c->d_slot[s][p], 0, plane_bytes(c, p), c->stream));
+        }
+    }
+    HLB_CUDA(cudaMalloc(&c->d_records, sizeof(hlb200_mb_record_t) * c->nmb));
+    HLB_CUDA(cudaMalloc(&c->d_mbstate, mbstate_bytes(c->nmb)));
+    HLB_CUDA(cudaMalloc(&c->d_sched, sizeof(int) * (64 + c->nmb)));
+    int rc = slice_reset_state(c);
+    if (rc) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_stream_destroy(hlb200_ctx_t* c)
+{
+    if (!c) return HLB200_ERR_INVALID_PARAMETER;
+    cudaStreamSynchronize(c->stream);
+    for (int p = 0; p < 3; ++p) {
+        cudaFree(c->d_src[p]); cudaFree(c->d_pred[p]); cudaFree(c->d_tmp[p]);
+        for (int s = 0; s < c->nslots; ++s) cudaFree(c->d_slot[s][p]);
+    }
+    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_sched); cudaFree(c->d_scratch);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+    return HLB200_OK;
+}
+
+int hlb200_stream_set_cuda_stream(hlb200_ctx_t* c, void* cuda_stream)
+{
+    if (!c) return HLB200_ERR_INVALID_PARAMETER;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) HLB_CUDA(cudaStreamDestroy(c->stream));
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return HLB200_OK;
+}
+
+int hlb200_stream_sync(hlb200_ctx_t* c)
+{
+    if (!c) return HLB200_ERR_INVALID_PARAMETER;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_frame_upload(hlb200_ctx_t* c, const uint8_t* y, const uint8_t* u, const uint8_t* v, int stride_y, int stride_c)
+{
+    if (!c || !y || !u || !v || stride_y < c->width || stride_c < (c->width >> 1)) return HLB200_ERR_INVALID_PARAMETER;
+    const uint8_t* h[3] = {y, u, v};
+    for (int p = 0; p < 3; ++p) {
+        const int w = p ? c->width >> 1 : c->width, hh = p ? c->height >> 1 : c->height, st = p ? stride_c : stride_y;
+        HLB_CUDA(cudaMemcpy2DAsync(c->d_src[p], w, h[p], st, w, hh, cudaMemcpyHostToDevice, c->stream));
+    }
+    return HLB200_OK;
+}
+
+int hlb200_slot_upload(hlb200_ctx_t* c, int slot, const uint8_t* y, const uint8_t* u, const uint8_t* v)
+{
+    if (!c || slot < 0 || slot >= c->nslots || !y || !u || !v) return HLB200_ERR_INVALID_PARAMETER;
+    const uint8_t* h[3] = {y, u, v};
+    for (int p = 0; p < 3; ++p) { int rc = h2d(c, c->d_slot[slot][p], h[p], plane_bytes(c, p)); if (rc) return rc; }
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_slot_download(hlb200_ctx_t* c, int slot, uint8_t* y, uint8_t* u, uint8_t* v)
+{
+    if (!c || slot < 0 || slot >= c->nslots || !y || !u || !v) return HLB200_ERR_INVALID_PARAMETER;
+    uint8_t* h[3] = {y, u, v};
+    for (int p = 0; p < 3; ++p) { int rc = d2h(c, h[p], c->d_slot[slot][p], plane_bytes(c, p)); if (rc) return rc; }
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_state_reset(hlb200_ctx_t* c)
+{
+    if (!c) return HLB200_ERR_INVALID_PARAMETER;
+    return slice_reset_state(c);
+}
+
+// ---- host-buffer batch wrappers -----------------------------------------------------------------------------------
+int hlb200_interp_luma(hlb200_ctx_t* c, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y)
+{
+    if (!c || ref_slot < 0 || ref_slot >= c->nslots || !motion || !pred_y) return HLB200_ERR_INVALID_PARAMETER;
+    int rc = ensure_scratch(c, sizeof(hlb200_mb_motion_t) * c->nmb);
+    if (rc) return rc;
+    if ((rc = h2d(c, c->d_scratch, motion, sizeof(hlb200_mb_motion_t) * c->nmb))) return rc;
+    if ((rc = hlb200_dev_interp_luma(c->d_slot[ref_slot][0], c->width, c->height, (const hlb200_mb_motion_t*)c->d_scratch, c->d_pred[0], c->stream))) return rc;
+    if ((rc = d2h(c, pred_y, c->d_pred[0], plane_bytes(c, 0)))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_interp_chroma(hlb200_ctx_t* c, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_u, uint8_t* pred_v)
+{
+    if (!c || ref_slot < 0 || ref_slot >= c->nslots || !motion || !pred_u || !pred_v) return HLB200_ERR_INVALID_PARAMETER;
+    int rc = ensure_scratch(c, sizeof(hlb200_mb_motion_t) * c->nmb);
+    if (rc) return rc;
+    if ((rc = h2d(c, c->d_scratch, motion, sizeof(hlb200_mb_motion_t) * c->nmb))) return rc;
+    if ((rc = hlb200_dev_interp_chroma(c->d_slot[ref_slot][1], c->d_slot[ref_slot][2], c->width, c->height, (const hlb200_mb_motion_t*)c->d_scratch, c->d_pred[1],
+                                       c->d_pred[2], c->stream)))
+        return rc;
+    if ((rc = d2h(c, pred_u, c->d_pred[1], plane_bytes(c, 1)))) return rc;
+    if ((rc = d2h(c, pred_v, c->d_pred[2], plane_bytes(c, 2)))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_tq_recon(hlb200_ctx_t* c, int qp, int chroma_qp_index_offset, const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v,
+                    hlb200_mb_coeffs_t* coeffs, uint8_t* recon_y, uint8_t* recon_u, uint8_t* recon_v)
+{
+    if (!c || !pred_y || !pred_u || !pred_v || !coeffs || !recon_y || !recon_u || !recon_v) return HLB200_ERR_INVALID_PARAMETER;
+    int rc = ensure_scratch(c, sizeof(hlb200_mb_coeffs_t) * c->nmb);
+    if (rc) return rc;
+    const uint8_t* hp[3] = {pred_y, pred_u, pred_v};
+    uint8_t* hr[3] = {recon_y, recon_u, recon_v};
+    for (int p = 0; p < 3; ++p) if ((rc = h2d(c, c->d_pred[p], hp[p], plane_bytes(c, p)))) return rc;
+    if ((rc = hlb200_dev_tq_recon(c->d_src[0], c->d_src[1], c->d_src[2], c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, qp, chroma_qp_index_offset,
+                                  (hlb200_mb_coeffs_t*)c->d_scratch, c->d_tmp[0], c->d_tmp[1], c->d_tmp[2], c->stream)))
+        return rc;
+    if ((rc = d2h(c, coeffs, c->d_scratch, sizeof(hlb200_mb_coeffs_t) * c->nmb))) return rc;
+    for (int p = 0; p < 3; ++p) if ((rc = d2h(c, hr[p], c->d_tmp[p], plane_bytes(c, p)))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_sad4x4(hlb200_ctx_t* c, const uint8_t* pred_y, int use_satd, int32_t* out_per_blk)
+{
+    if (!c || !pred_y || !out_per_blk) return HLB200_ERR_INVALID_PARAMETER;
+    const size_t nb = (size_t)(c->width >> 2) * (c->height >> 2);
+    int rc = ensure_scratch(c, nb * sizeof(int32_t));
+    if (rc) return rc;
+    if ((rc = h2d(c, c->d_pred[0], pred_y, plane_bytes(c, 0)))) return rc;
+    if ((rc = hlb200_dev_sad4x4(c->d_src[0], c->d_pred[0], c->width, c->height, use_satd, (int32_t*)c->d_scratch, c->stream))) return rc;
+    if ((rc = d2h(c, out_per_blk, c->d_scratch, nb * sizeof(int32_t)))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+int hlb200_me_cost(hlb200_ctx_t* c, int ref_slot, int qp, const hlb200_me_cand_t* cands, int n, hlb200_me_cost_t* out)
+{
+    if (!c || ref_slot < 0 || ref_slot >= c->nslots || !cands || !out || n < 0 || qp < 0 || qp > 51) return HLB200_ERR_INVALID_PARAMETER;
+    if (n == 0) return HLB200_OK;
+    for (int i = 0; i < n; ++i) {
+        const hlb200_me_cand_t& d = cands[i];
+        if (d.mb_x < 0 || d.mb_x >= c->mbw || d.mb_y < 0 || d.mb_y >= c->mbh || (d.part_w != 4 && d.part_w != 8 && d.part_w != 16) ||
+            (d.part_h != 4 && d.part_h != 8 && d.part_h != 16) || d.part_x + d.part_w > 16 || d.part_y + d.part_h > 16 || (d.part_x & 3) || (d.part_y & 3))
+            return HLB200_ERR_INVALID_PARAMETER;
+    }
+    const size_t in_b = sizeof(hlb200_me_cand_t) * (size_t)n, in_pad = (in_b + 255) & ~(size_t)255, out_b = sizeof(hlb200_me_cost_t) * (size_t)n;
+    int rc = ensure_scratch(c, in_pad + out_b);
+    if (rc) return rc;
+    hlb200_me_cand_t* d_c = (hlb200_me_cand_t*)c->d_scratch;
+    hlb200_me_cost_t* d_o = (hlb200_me_cost_t*)((char*)c->d_scratch + in_pad);
+    if ((rc = h2d(c, d_c, cands, in_b))) return rc;
+    if ((rc = launch_me_cost(c->d_src[0], c->d_slot[ref_slot][0], c->width, c->height, qp, d_c, n, d_o, c->stream))) return rc;
+    if ((rc = d2h(c, out, d_o, out_b))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+// hlb_batch.cu -- whole-frame batch kernels of the stateless part of the hot path:
+// luma/chroma fractional interpolation, residual -> T -> Q -> Q^-1 -> T^-1 -> reconstruction, SAD/SATD and the
+// independent ME candidate cost.  All are HBM-bound integer/byte kernels (no tensor cores: 4x4 butterflies are not
+// a dense contraction); one thread owns one 4x4 block in registers, one warp owns one (or two) macroblocks.
+#include "hlb_common.cuh"
+
+namespace hlb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// 9x9 window around a 4x4 block (rows/cols -2..+6), fetched with the per-sample clamp of the reference's index
+// table (source/h264/hl_codec_264_interpol.c:108-131).  (X,Y) = position of output pixel (0,0) AFTER the partition
+// origin clip of pred_inter.c:395-396.  Fully unrolled: the window lives in registers.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_win9(const uint8_t* __restrict__ plane, int W, int H, int X, int Y, uint8_t t[81])
+{
+    if (X >= 2 && Y >= 2 && X + 7 <= W && Y + 7 <= H) {
+        const uint8_t* p = plane + (Y - 2) * W + (X - 2);
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) t[r * 9 + c] = __ldg(p + r * W + c);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int y = clip3(0, H - 1, Y - 2 + r);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) t[r * 9 + c] = __ldg(plane + y * W + clip3(0, W - 1, X - 2 + c));
+        }
+    }
+}
+
+// ---------------- luma interpolation: one thread per 4x4 block, raster block order inside the MB -------------------
+__global__ void __launch_bounds__(128) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
+                                                     const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int mb = t >> 4;
+    if (mb >= nmb) return;
+    const int k = t & 15, bx = (k & 3) * 4, by = (k >> 2) * 4;
+    const int mbx = mb % mbw, mby = mb / mbw;
+    const hlb200_mb_motion_t* m = motion + mb;
+    const PartGeom g = part_of(m->part_mode, m->sub_mode, bx, by);
+    const int mvx = m->mv[g.part][g.sub][0], mvy = m->mv[g.part][g.sub][1];
+    // origin clip applies to the PARTITION origin
+    const int X = clip3(-17, W + 17, mbx * 16 + g.ox + (mvx >> 2)) + (bx - g.ox);
+    const int Y = clip3(-17, H + 17, mby * 16 + g.oy + (mvy >> 2)) + (by - g.oy);
+    uint8_t win[81];
+    load_win9(ref, W, H, X, Y, win);
+    uint8_t out[16];
+    interp_luma_4x4(win + 2 * 9 + 2, 9, mvx & 3, mvy & 3, out);
+    uint8_t* o = pred + (mby * 16 + by) * W + mbx * 16 + bx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<uint32_t*>(o + r * W) = out[r * 4] | (out[r * 4 + 1] << 8) | (out[r * 4 + 2] << 16) | ((uint32_t)out[r * 4 + 3] << 24);
+}
+
+// ---------------- chroma interpolation: one thread per chroma sample pair (Cb, Cr) ---------------------------------
+__global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
+                                                       const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int mb = t >> 6;
+    if (mb >= nmb) return;
+    const int px = t & 7, py = (t >> 3) & 7;
+    const int mbx = mb % mbw, mby = mb / mbw;
+    const int Wc = W >> 1, Hc = H >> 1;
+    const hlb200_mb_motion_t* m = motion + mb;
+    const PartGeom g = part_of(m->part_mode, m->sub_mode, px * 2, py * 2);
+    const int mvx = m->mv[g.part][g.sub][0], mvy = m->mv[g.part][g.sub][1];
+    const int x0 = mbx * 8 + px + (mvx >> 3), y0 = mby * 8 + py + (mvy >> 3), xf = mvx & 7, yf = mvy & 7;
+    const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
+    const int o = (mby * 8 + py) * Wc + mbx * 8 + px;
+    pred_u[o] = (uint8_t)interp_chroma_px(__ldg(ref_u + ya + xa), __ldg(ref_u + ya + xb), __ldg(ref_u + yc + xa), __ldg(ref_u + yc + xb), xf, yf);
+    pred_v[o] = (uint8_t)interp_chroma_px(__ldg(ref_v + ya + xa), __ldg(ref_v + ya + xb), __ldg(ref_v + yc + xa), __ldg(ref_v + yc + xb), xf, yf);
+}
+
+// ---------------- residual coding + reconstruction: one warp per macroblock ----------------------------------------
+// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks 0..3; lanes 20..23: Cr blocks 0..3 (raster); lanes 24..31 idle.
+__device__ __forceinline__ void load4x4(const uint8_t* __restrict__ p, int pitch, uint8_t v[16])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + r * pitch));
+        v[r * 4] = w & 255; v[r * 4 + 1] = (w >> 8) & 255; v[r * 4 + 2] = (w >> 16) & 255; v[r * 4 + 3] = w >> 24;
+    }
+}
+__device__ __forceinline__ void store4x4(uint8_t* __restrict__ p, int pitch, const int v[16])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<uint32_t*>(p + r * pitch) = (uint32_t)v[r * 4] | ((uint32_t)v[r * 4 + 1] << 8) | ((uint32_t)v[r * 4 + 2] << 16) | ((uint32_t)v[r * 4 + 3] << 24);
+}
+
+__global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
+                                                  const uint8_t* __restrict__ pred_y, const uint8_t* __restrict__ pred_u, const uint8_t* __restrict__ pred_v,
+                                                  int W, int H, int mbw, int nmb, int qp, int qpc, hlb200_mb_coeffs_t* __restrict__ coeffs,
+                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nmb) return;  // warp-uniform
+    const int mb = warp, mbx = mb % mbw, mby = mb / mbw;
+    hlb200_mb_coeffs_t* out = coeffs + mb;
+    const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
+    const int plane = is_luma ? 0 : ((lane - 16) >> 2) + 1, cblk = (lane - 16) & 3;
+    const int pitch = is_luma ? W : (W >> 1);
+    const int bx = is_luma ? blk_x(lane) : (cblk & 1) * 4, by = is_luma ? blk_y(lane) : (cblk >> 1) * 4;
+    const int off = is_luma ? (mby * 16 + by) * W + mbx * 16 + bx : (mby * 8 + by) * pitch + mbx * 8 + bx;
+    const uint8_t* s = plane == 0 ? src_y : (plane == 1 ? src_u : src_v);
+    const uint8_t* p = plane == 0 ? pred_y : (plane == 1 ? pred_u : pred_v);
+    uint8_t* r = plane == 0 ? rec_y : (plane == 1 ? rec_u : rec_v);
+
+    uint8_t sv[16], pv[16];
+    int m[16], lv[16];
+    bool res_nz = false;
+    if (is_luma || is_chroma) {
+        load4x4(s + off, pitch, sv);
+        load4x4(p + off, pitch, pv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; res_nz |= (m[i] != 0); }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { m[i] = 0; pv[i] = 0; }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lv[i] = 0;
+
+    int dc_coef = 0;     // chroma: pre-quant W00 (rdo.c:2591)
+    bool coded = false;  // luma: CBP4x4 bit; chroma: AC bit
+    if (res_nz) {
+        fwd_transform4x4(m);
+        dc_coef = m[0];
+        quant4x4_ac(m, is_luma ? qp : qpc, /*intra f*/ !is_luma);  // chroma AC always uses the intra offset (rdo.c:2588)
+        zigzag4x4(m, lv);
+        if (is_luma) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) coded |= (lv[i] != 0);
+        } else {
+#pragma unroll
+            for (int i = 1; i < 16; ++i) coded |= (lv[i] != 0);
+        }
+    }
+    if (!is_chroma) dc_coef = 0;
+
+    // ---- chroma: single-coefficient elimination + 2x2 DC (rdo.c:2599-2672) ----
+    int nnz_ac = 0, big = 0;
+    if (is_chroma) {
+#pragma unroll
+        for (int i = 1; i < 16; ++i) { nnz_ac += (lv[i] != 0); big |= (iabs(lv[i]) > 1); }
+    }
+    const unsigned full = 0xffffffffu;
+    const int base = 16 + ((lane >= 20) ? 4 : 0);  // first lane of my chroma plane (for lanes >= 16)
+    int tot = 0, anybig = 0, dcs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int src_lane = is_chroma ? base + k : lane;
+        tot += __shfl_sync(full, nnz_ac, src_lane);
+        anybig |= __shfl_sync(full, big, src_lane);
+        dcs[k] = __shfl_sync(full, dc_coef, src_lane);
+    }
+    const unsigned ac_ballot = __ballot_sync(full, is_chroma && coded);
+    unsigned ac_mask = is_chroma ? ((ac_ballot >> base) & 15u) : 0u;  // CodedBlockPatternChromaAC4x4 of my plane
+    if (is_chroma && tot == 1 && !anybig) ac_mask = 0;                // exactly one +-1 AC coefficient in the plane
+    const bool dc_tent = is_chroma && (dcs[0] | dcs[1] | dcs[2] | dcs[3]) != 0;
+    int dcl[4] = {0, 0, 0, 0};
+    unsigned dc_mask = 0;
+    int dcr[4] = {0, 0, 0, 0};
+    if (dc_tent) {
+        dcl[0] = dcs[0]; dcl[1] = dcs[1]; dcl[2] = dcs[2]; dcl[3] = dcs[3];
+        hadamard2x2(dcl);
+        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ false);  // DC uses the MB's own intra flag: inter here (rdo.c:2660)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dc_mask |= (dcl[k] != 0) << k;
+        if (dc_mask) {  // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dcr[k] = dcl[k];
+            hadamard2x2(dcr);
+            const int ls = 16 * kNormAdjust[qpc % 6][0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dcr[k] = ((dcr[k] * ls) << (qpc / 6)) >> 5;
+        }
+    }
+
+    // ---- reconstruction ----
+    int rec[16];
+    bool use_res;
+    int c[16];
+    if (is_luma) {
+        use_res = coded;
+        inv_zigzag4x4(lv, c);
+    } else {
+        const int mydc = dcr[cblk];
+        use_res = is_chroma && (mydc != 0 || ((ac_mask >> cblk) & 1));  // transf.c:236: AC levels are used whenever the DC is non-zero
+        int l2[16];
+        l2[0] = mydc;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) l2[i] = lv[i];
+        inv_zigzag4x4(l2, c);
+    }
+    if (use_res) {
+        dequant4x4(c, is_luma ? qp : qpc, /*keep_dc*/ !is_luma);
+        inv_transform4x4(c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[i] = clip255((int)pv[i] + c[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[i] = pv[i];
+    }
+    if (is_luma || is_chroma) store4x4(r + off, pitch, rec);
+
+    // ---- outputs ----
+    if (is_luma) {
+        int16_t* o = out->luma_level[lane];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) *reinterpret_cast<uint32_t*>(o + i) = (uint32_t)(uint16_t)(coded ? lv[i] : 0) | ((uint32_t)(uint16_t)(coded ? lv[i + 1] : 0) << 16);
+    } else if (is_chroma) {
+        int16_t* o = out->chroma_ac_level[plane - 1][cblk];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) o[i] = (int16_t)lv[i + 1];
+        o[15] = 0;
+        if (cblk == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out->chroma_dc_level[plane - 1][k] = (int16_t)dcl[k];
+            out->cbp_chroma_dc4x4[plane - 1] = (uint8_t)dc_mask;
+            out->cbp_chroma_ac4x4[plane - 1] = (uint8_t)ac_mask;
+        }
+    }
+    const unsigned lb = __ballot_sync(full, is_luma && coded);
+    if (lane == 0) out->cbp_luma4x4 = (uint16_t)(lb & 0xffffu);
+}
+
+// ---------------- SAD / SATD of every 4x4 block of two planes -------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sad4x4(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int W, int H, int use_satd, int32_t* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bw = W >> 2, nb = bw * (H >> 2);
+    if (t >= nb) return;
+    const int bx = (t % bw) * 4, by = (t / bw) * 4;
+    uint8_t x[16], y[16];
+    load4x4(a + by * W + bx, W, x);
+    load4x4(b + by * W + bx, W, y);
+    out[t] = use_satd ? satd16(x, y) : sad16(x, y);
+}
+
+// ---------------- independent ME candidate cost (me_ds.c:527-688): 16 lanes per candidate ---------------------------
+__global__ void __launch_bounds__(128) k_me_cost(const uint8_t* __restrict__ src, const uint8_t* __restrict__ ref, int W, int H, int qp,
+                                                 const hlb200_me_cand_t* __restrict__ cands, int n, hlb200_me_cost_t* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci = t >> 4, k = t & 15;
+    const bool valid = ci < n;
+    const hlb200_me_cand_t cd = cands[valid ? ci : 0];
+    const int bw = cd.part_w >> 2, bh = cd.part_h >> 2;
+    const bool active = valid && k < bw * bh;
+    const int bx = cd.part_x + (k % bw) * 4, by = cd.part_y + (k / bw) * 4;  // raster inside the partition
+    int dist = 0, bits = 0, sctr = 0, tc = 0, t1 = 0, nzb = 0;
+    if (active) {
+        const int X = clip3(-17, W + 17, cd.mb_x * 16 + cd.part_x + (cd.mv_x >> 2)) + (bx - cd.part_x);
+        const int Y = clip3(-17, H + 17, cd.mb_y * 16 + cd.part_y + (cd.mv_y >> 2)) + (by - cd.part_y);
+        uint8_t win[81], pv[16], sv[16];
+        load_win9(ref, W, H, X, Y, win);
+        interp_luma_4x4(win + 20, 9, cd.mv_x & 3, cd.mv_y & 3, pv);
+        load4x4(src + (cd.mb_y * 16 + by) * W + cd.mb_x * 16 + bx, W, sv);
+        int m[16], lv[16];
+        bool nz = false;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; nz |= (m[i] != 0); }
+        if (nz) {
+            fwd_transform4x4(m);
+            quant4x4_ac(m, qp, false);
+            zigzag4x4(m, lv);
+            nz = false;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) nz |= (lv[i] != 0);
+        }
+        if (nz) {
+            const CavlcInfo ci2 = cavlc_block_info(lv, 16, false);
+            bits = ci2.bits_rest; sctr = ci2.single_ctr; tc = ci2.total_coeff; t1 = ci2.trailing_ones; nzb = 1;
+            int c[16];
+            inv_zigzag4x4(lv, c);
+            dequant4x4(c, qp, false);
+            inv_transform4x4(c);
+            uint8_t rec[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rec[i] = (uint8_t)((int)pv[i] + c[i]);  // wraps (hl_math.h:261)
+            dist = sad16(sv, rec);
+        } else {
+            dist = sad16(sv, pv);
+        }
+    }
+    const int blk = active ? blk_idx_from_xy(bx, by) : 0;
+    unsigned cbp = nzb ? (1u << blk) : 0u;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        dist += __shfl_xor_sync(0xffffffffu, dist, o, 16);
+        bits += __shfl_xor_sync(0xffffffffu, bits, o, 16);
+        sctr += __shfl_xor_sync(0xffffffffu, sctr, o, 16);
+        cbp |= __shfl_xor_sync(0xffffffffu, cbp, o, 16);
+    }
+    if (valid) {
+        hlb200_me_cost_t* o = out + ci;
+        if (k == 0) { o->dist = dist; o->bits_rest = bits; o->single_ctr = sctr; o->cbp_luma4x4 = (uint16_t)cbp; o->pad = 0; }
+    }
+    // per-block counts: every lane of the candidate clears its slot, then active non-zero lanes write theirs
+    if (valid) { out[ci].total_coeff[k] = 0; out[ci].trailing_ones[k] = 0; }
+    __syncwarp();
+    if (active && nzb) { out[ci].total_coeff[blk] = (uint8_t)tc; out[ci].trailing_ones[blk] = (uint8_t)t1; }
+}
+
+}  // namespace hlb
+
+using namespace hlb;
+
+extern "C" {
+
+int hlb200_dev_interp_luma(const uint8_t* d_ref_y, int width, int height, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_y, void* cuda_stream)
+{
+    if (!d_ref_y || !d_motion || !d_pred_y || (width & 15) || (height & 15)) return HLB200_ERR_INVALID_PARAMETER;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4);
+    k_interp_luma<<<(nmb * 16 + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, width, height, mbw, nmb, d_motion, d_pred_y);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+
+int hlb200_dev_interp_chroma(const uint8_t* d_ref_u, const uint8_t* d_ref_v, int width, int height, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_u,
+                             uint8_t* d_pred_v, void* cuda_stream)
+{
+    if (!d_ref_u || !d_ref_v || !d_motion || !d_pred_u || !d_pred_v || (width & 15) || (height & 15)) return HLB200_ERR_INVALID_PARAMETER;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4);
+    k_interp_chroma<<<(nmb * 64 + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+
+int hlb200_dev_tq_recon(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
+                        const uint8_t* d_pred_v, int width, int height, int qp, int chroma_qp_index_offset, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y,
+                        uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream)
+{
+    if (!d_src_y || !d_pred_y || !d_coeffs || !d_recon_y || (width & 15) || (height & 15) || qp < 0 || qp > 51) return HLB200_ERR_INVALID_PARAMETER;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4);
+    k_tq_recon<<<(nmb * 32 + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, mbw, nmb, qp,
+                                                                            host_chroma_qp(qp, chroma_qp_index_offset), d_coeffs, d_recon_y, d_recon_u, d_recon_v);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+
+int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream)
+{
+    if (!d_a || !d_b || !d_out || (width & 3) || (height & 3)) return HLB200_ERR_INVALID_PARAMETER;
+    const int nb = (width >> 2) * (height >> 2);
+    k_sad4x4<<<(nb + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_a, d_b, width, height, use_satd, d_out);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+
+}  // extern "C"
+
+namespace hlb {
+int launch_me_cost(const uint8_t* d_src, const uint8_t* d_ref, int W, int H, int qp, const hlb200_me_cand_t* d_cands, int n, hlb200_me_cost_t* d_out, cudaStream_t st)
+{
+    if (n <= 0) return HLB200_OK;
+    k_me_cost<<<(n * 16 + 127) / 128, 128, 0, st>>>(d_src, d_ref, W, H, qp, d_cands, n, d_out);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+}  // namespace hlb

@@ -1,6 +1,6 @@
 // hlb_prims.cuh -- per-4x4-block integer primitives of the H.264 pixel hot path, written for one CUDA thread per
 // 4x4 block with the whole block in registers (the natural unit of the reference, see below), bit-exact with the
-// reference's C path.  Every function is `HLB_HD` so that the same source also compiles as plain C++ for the CPU
+// reference's C path.  Every function is `HLB_HD` (device-only under nvcc) and the same source also compiles as plain C++ for the CPU
 // emulation harness under tests/emu (a debugging aid -- never part of the shipped library).
 //
 // Reference behaviour followed (file:line under the reference tree):
@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define HLB_HD __host__ __device__ __forceinline__
+#define HLB_HD __device__ __forceinline__
 #define HLB_TABLE __device__
 #else
 #define HLB_HD inline

@@ -1,0 +1,157 @@
+"""ctypes binding of libhl_b200.so (include/hlb200.h).  Fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libhl_b200.so")
+
+
+class Hlb200Error(RuntimeError):
+    pass
+
+
+# ---- numpy dtypes mirroring the C structs of include/hlb200.h ----
+MB_MOTION = np.dtype([("part_mode", "u1"), ("sub_mode", "u1", (4,)), ("ref_idx", "i1", (4,)), ("pad", "u1", (3,)), ("mv", "<i2", (4, 4, 2))])
+MB_COEFFS = np.dtype([("luma_level", "<i2", (16, 16)), ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16)),
+                      ("cbp_luma4x4", "<u2"), ("cbp_chroma_dc4x4", "u1", (2,)), ("cbp_chroma_ac4x4", "u1", (2,)), ("pad", "u1", (2,))])
+ME_CAND = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("part_x", "u1"), ("part_y", "u1"), ("part_w", "u1"), ("part_h", "u1"), ("mv_x", "<i2"), ("mv_y", "<i2")])
+ME_COST = np.dtype([("dist", "<i4"), ("bits_rest", "<i4"), ("single_ctr", "<i4"), ("cbp_luma4x4", "<u2"), ("total_coeff", "u1", (16,)),
+                    ("trailing_ones", "u1", (16,)), ("pad", "<u2")])
+MB_RECORD = np.dtype([
+    ("mb_class", "u1"), ("mb_type", "u1"), ("part_mode", "u1"), ("sub_mode", "u1", (4,)), ("i16_pred_mode", "u1"), ("intra_chroma_pred_mode", "u1"),
+    ("coded_block_pattern", "u1"), ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("cbp_chroma_dc4x4", "u1", (2,)), ("cbp_chroma_ac4x4", "u1", (2,)),
+    ("cbp_luma4x4", "<u2"), ("mb_qp_delta", "i1"), ("qp_y", "u1"), ("qp_c", "u1", (2,)), ("ref_idx", "i1", (4,)), ("i4_pred_mode", "u1", (16,)),
+    ("prev_intra4x4_pred_mode_flag", "u1", (16,)), ("rem_intra4x4_pred_mode", "u1", (16,)), ("pad", "u1", (3,)),
+    ("mv", "<i2", (4, 4, 2)), ("mvd", "<i2", (4, 4, 2)), ("mad", "<i4"),
+    ("luma_level", "<i2", (16, 16)), ("i16_dc_level", "<i2", (16,)), ("i16_ac_level", "<i2", (16, 16)),
+    ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16))], align=True)
+
+
+class SliceParams(C.Structure):
+    _fields_ = [("slice_type", C.c_int32), ("qp", C.c_int32), ("me_range", C.c_int32), ("num_refs", C.c_int32), ("chroma_qp_index_offset", C.c_int32),
+                ("cur_slot", C.c_int32), ("ref_slot", C.c_int32 * 16)]
+
+
+_lib = None
+
+
+def load():
+    """Loads libhl_b200.so; raises Hlb200Error when it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise Hlb200Error("libhl_b200.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; g.build()'`; there is no CPU fallback" % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    vp, ip = C.c_void_p, C.c_int
+    sig = {
+        "hlb200_init": [ip], "hlb200_device_count": [], "hlb200_version": [],
+        "hlb200_stream_create": [ip, ip, ip, C.POINTER(vp)], "hlb200_stream_destroy": [vp], "hlb200_stream_set_cuda_stream": [vp, vp],
+        "hlb200_stream_sync": [vp], "hlb200_frame_upload": [vp, vp, vp, vp, ip, ip], "hlb200_slot_upload": [vp, ip, vp, vp, vp],
+        "hlb200_slot_download": [vp, ip, vp, vp, vp], "hlb200_state_reset": [vp],
+        "hlb200_slice_encode": [vp, C.POINTER(SliceParams), vp], "hlb200_slice_encode_async": [vp, C.POINTER(SliceParams)], "hlb200_records_download": [vp, vp],
+        "hlb200_interp_luma": [vp, ip, vp, vp], "hlb200_interp_chroma": [vp, ip, vp, vp, vp],
+        "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
+        "hlb200_dev_interp_luma": [vp, ip, ip, vp, vp, vp], "hlb200_dev_interp_chroma": [vp, vp, ip, ip, vp, vp, vp, vp],
+        "hlb200_dev_tq_recon": [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp], "hlb200_dev_sad4x4": [vp, vp, ip, ip, ip, vp, vp],
+    }
+    for name, args in sig.items():
+        f = getattr(lib, name)
+        f.argtypes, f.restype = args, ip
+    lib.hlb200_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise Hlb200Error("%s failed with HL_ERROR %d: %s" % (what, rc, load().hlb200_last_error().decode()))
+
+
+def ptr(a):
+    """host pointer of a C-contiguous numpy array"""
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+class Stream:
+    """One encoder stream context (hlb200_ctx_t)."""
+
+    def __init__(self, width, height, max_refs=1, device=0):
+        self.lib = load()
+        check(self.lib.hlb200_init(device), "hlb200_init")
+        self.w, self.h = width, height
+        self.nmb = (width // 16) * (height // 16)
+        self.ctx = C.c_void_p()
+        check(self.lib.hlb200_stream_create(width, height, max_refs, C.byref(self.ctx)), "hlb200_stream_create")
+
+    def close(self):
+        if self.ctx:
+            self.lib.hlb200_stream_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _planes(self, yuv):
+        w, h = self.w, self.h
+        yuv = np.ascontiguousarray(yuv, np.uint8).reshape(-1)
+        y, u, v = yuv[:w * h], yuv[w * h:w * h * 5 // 4], yuv[w * h * 5 // 4:w * h * 3 // 2]
+        return y, u, v
+
+    def upload_frame(self, yuv):
+        y, u, v = self._planes(yuv)
+        check(self.lib.hlb200_frame_upload(self.ctx, ptr(y), ptr(u), ptr(v), self.w, self.w // 2), "frame_upload")
+        check(self.lib.hlb200_stream_sync(self.ctx), "sync")
+
+    def upload_slot(self, slot, yuv):
+        y, u, v = self._planes(yuv)
+        check(self.lib.hlb200_slot_upload(self.ctx, slot, ptr(y), ptr(u), ptr(v)), "slot_upload")
+
+    def download_slot(self, slot):
+        w, h = self.w, self.h
+        out = np.zeros(w * h * 3 // 2, np.uint8)
+        y, u, v = out[:w * h], out[w * h:w * h * 5 // 4], out[w * h * 5 // 4:]
+        check(self.lib.hlb200_slot_download(self.ctx, slot, ptr(y), ptr(u), ptr(v)), "slot_download")
+        return out
+
+    def interp_luma(self, ref_slot, motion):
+        out = np.zeros((self.h, self.w), np.uint8)
+        check(self.lib.hlb200_interp_luma(self.ctx, ref_slot, ptr(motion), ptr(out)), "interp_luma")
+        return out
+
+    def interp_chroma(self, ref_slot, motion):
+        u = np.zeros((self.h // 2, self.w // 2), np.uint8)
+        v = np.zeros_like(u)
+        check(self.lib.hlb200_interp_chroma(self.ctx, ref_slot, ptr(motion), ptr(u), ptr(v)), "interp_chroma")
+        return u, v
+
+    def tq_recon(self, qp, pred_yuv, chroma_qp_index_offset=0):
+        py, pu, pv = self._planes(pred_yuv)
+        coeffs = np.zeros(self.nmb, MB_COEFFS)
+        rec = np.zeros(self.w * self.h * 3 // 2, np.uint8)
+        w, h = self.w, self.h
+        ry, ru, rv = rec[:w * h], rec[w * h:w * h * 5 // 4], rec[w * h * 5 // 4:]
+        check(self.lib.hlb200_tq_recon(self.ctx, qp, chroma_qp_index_offset, ptr(py), ptr(pu), ptr(pv), ptr(coeffs), ptr(ry), ptr(ru), ptr(rv)), "tq_recon")
+        return coeffs, rec
+
+    def sad4x4(self, pred_y, satd=False):
+        out = np.zeros((self.h // 4, self.w // 4), np.int32)
+        p = np.ascontiguousarray(pred_y, np.uint8)
+        check(self.lib.hlb200_sad4x4(self.ctx, ptr(p), 1 if satd else 0, ptr(out)), "sad4x4")
+        return out
+
+    def me_cost(self, ref_slot, qp, cands):
+        out = np.zeros(len(cands), ME_COST)
+        check(self.lib.hlb200_me_cost(self.ctx, ref_slot, qp, ptr(cands), len(cands), ptr(out)), "me_cost")
+        return out
+
+    def slice_encode(self, params):
+        rec = np.zeros(self.nmb, MB_RECORD)
+        check(self.lib.hlb200_slice_encode(self.ctx, C.byref(params), ptr(rec)), "slice_encode")
+        return rec

@@ -1,0 +1,180 @@
+/*
+ * hlb200.h -- C-ABI of libhl_b200.so: the B200 (sm_100a) implementation of hartallo's H.264 encoder pixel hot path.
+ *
+ * This is the drop-in boundary.  Host code stays C (the reference's own host code, unchanged) and reaches CUDA only
+ * through these entry points: plain pointers and sizes, no C++/torch types.  Every function returns an `int` that
+ * maps 1:1 onto the reference's HL_ERROR_T (include/hartallo/hl_types.h:101-122); 0 = HL_ERROR_SUCCESS.
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns HLB200_ERR_SYSTEM.
+ *
+ * What each group replaces in the reference (file:line under the reference tree):
+ *
+ *   hlb200_slice_encode        hl_codec_264_nal_slice_data_encode            source/h264/hl_codec_264_slice.c:1701
+ *                              (the per-MB decide+reconstruct part of its loop :1786-1894, i.e.
+ *                               hl_codec_264_rdo_mb_guess_best_inter_pred_avc source/h264/hl_codec_264_rdo.c:678,
+ *                               hl_codec_264_rdo_mb_guess_best_intra_pred_avc rdo.c:99,
+ *                               hl_codec_264_me_ds_mb_find_best_cost          source/h264/hl_codec_264_me_ds.c:104);
+ *                              the CAVLC serialisation (_hl_codec_264_mb_write_no_pcm, source/h264/hl_codec_264_mb.c:543)
+ *                              stays on the host and consumes hlb200_mb_record_t.
+ *   hlb200_interp_luma/chroma  hl_codec_264_interpol_luma  source/h264/hl_codec_264_pred_inter.c:339,
+ *                              hl_codec_264_interpol_chroma_cpp pred_inter.c:888 (whole-frame batch, one MV set per MB)
+ *   hlb200_tq_recon            _hl_codec_264_rdo_mb_reconstruct_inter rdo.c:2274 (residual part :2428-2478) and
+ *                              _hl_codec_264_rdo_mb_reconstruct_chroma rdo.c:2502 (whole-frame batch)
+ *   hlb200_sad4x4/satd4x4      hl_math_sad4x4_u8 source/hl_math.c:239, hl_math_satd4x4_u8 hl_math.c:283 (whole-frame batch)
+ *   hlb200_me_cost             hl_codec_264_me_ds_mb_compute_cost_mode me_ds.c:527 (batch of independent candidates)
+ *
+ * Ownership: device memory belongs to the stream context; host buffers are caller-owned.  One CUDA stream per
+ * context; no global mutable state, so -- unlike the reference (rdo.c:97 `static double last_best_intra_cost`) --
+ * many contexts may live in one process.
+ */
+#ifndef HLB200_H_
+#define HLB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HLB200_API __attribute__((visibility("default")))
+#else
+#define HLB200_API
+#endif
+
+/* same numeric values as HL_ERROR_T */
+enum {
+    HLB200_OK = 0,
+    HLB200_ERR_INVALID_PARAMETER = 1,
+    HLB200_ERR_INVALID_STATE = 3,
+    HLB200_ERR_NOT_IMPLEMENTED = 7,
+    HLB200_ERR_OUTOFMEMORY = 8,
+    HLB200_ERR_SYSTEM = 13
+};
+
+#define HLB200_MAX_REFS 16
+
+typedef struct hlb200_ctx hlb200_ctx_t; /* one per encoded stream (or SVC layer) */
+
+/* Partition layout + motion of one macroblock: mirrors NumMbPart / sub_mb_type / mvL0[4][4] / refIdxL0[4] of
+ * hl_codec_264_mb_t (include/hartallo/h264/hl_codec_264_mb.h:98-269). */
+typedef struct hlb200_mb_motion {
+    uint8_t part_mode;   /* 0: 16x16, 1: 16x8, 2: 8x16, 3: 8x8 */
+    uint8_t sub_mode[4]; /* for 8x8: 0: 8x8, 1: 8x4, 2: 4x8, 3: 4x4 */
+    int8_t ref_idx[4];   /* per mbPartIdx */
+    uint8_t pad[3];
+    int16_t mv[4][4][2]; /* [mbPartIdx][subMbPartIdx][x,y], quarter-pel */
+} hlb200_mb_motion_t;
+
+enum { HLB200_MB_P_SKIP = 0, HLB200_MB_P_INTER = 1, HLB200_MB_I16x16 = 2, HLB200_MB_I4x4 = 3 };
+
+/* Per-macroblock decision record: exactly the fields the reference's writer reads (mb.c:584-860, residual.c:987-1094). */
+typedef struct hlb200_mb_record {
+    uint8_t mb_class;                 /* HLB200_MB_* */
+    uint8_t mb_type;                  /* syntax element value, Table 7-11/7-13 (P slices: already +5 for intra) */
+    uint8_t part_mode;                /* as hlb200_mb_motion_t */
+    uint8_t sub_mode[4];
+    uint8_t i16_pred_mode;            /* Intra16x16PredMode */
+    uint8_t intra_chroma_pred_mode;
+    uint8_t coded_block_pattern;      /* coded_block_pattern (after the ">47 => -16" quirk, rdo.c:2776) */
+    uint8_t cbp_luma, cbp_chroma;     /* CodedBlockPatternLuma / Chroma */
+    uint8_t cbp_chroma_dc4x4[2], cbp_chroma_ac4x4[2];
+    uint16_t cbp_luma4x4;             /* CodedBlockPatternLuma4x4 */
+    int8_t mb_qp_delta;
+    uint8_t qp_y, qp_c[2];
+    int8_t ref_idx[4];
+    uint8_t i4_pred_mode[16];         /* Intra4x4PredMode */
+    uint8_t prev_intra4x4_pred_mode_flag[16];
+    uint8_t rem_intra4x4_pred_mode[16];
+    uint8_t pad[3];
+    int16_t mv[4][4][2];              /* mvL0 */
+    int16_t mvd[4][4][2];             /* mvd_l0 */
+    int32_t mad;                      /* best distortion (rate-control hook, rdo.c:1265) */
+    int16_t luma_level[16][16];       /* LumaLevel (zig-zag) */
+    int16_t i16_dc_level[16];         /* Intra16x16DCLevel */
+    int16_t i16_ac_level[16][16];     /* Intra16x16ACLevel (15 used) */
+    int16_t chroma_dc_level[2][4];    /* ChromaDCLevel */
+    int16_t chroma_ac_level[2][4][16];/* ChromaACLevel (15 used) */
+} hlb200_mb_record_t;
+
+typedef struct hlb200_slice_params {
+    int32_t slice_type;  /* 0: I (intra only), 1: P */
+    int32_t qp;          /* SliceQPY; fixed QP (rate control stays on the host, rc_bitrate < 0) */
+    int32_t me_range;    /* codec->me_range, clipped to [1,64] as rdo.c:847 */
+    int32_t num_refs;    /* num_ref_idx_l0_active_minus1 + 1 */
+    int32_t chroma_qp_index_offset;
+    int32_t cur_slot;    /* frame-store slot receiving the reconstruction */
+    int32_t ref_slot[HLB200_MAX_REFS]; /* RefPicList0[i] -> frame-store slot */
+} hlb200_slice_params_t;
+
+/* Levels / flags produced by the batch transform-quant-reconstruct kernel, per macroblock */
+typedef struct hlb200_mb_coeffs {
+    int16_t luma_level[16][16];
+    int16_t chroma_dc_level[2][4];
+    int16_t chroma_ac_level[2][4][16];
+    uint16_t cbp_luma4x4;
+    uint8_t cbp_chroma_dc4x4[2], cbp_chroma_ac4x4[2];
+    uint8_t pad[2];
+} hlb200_mb_coeffs_t;
+
+/* One independent ME candidate for hlb200_me_cost (me_ds.c:527): partition rectangle inside MB (mb_x, mb_y) */
+typedef struct hlb200_me_cand {
+    int16_t mb_x, mb_y;     /* macroblock coordinates */
+    uint8_t part_x, part_y; /* partition origin inside the MB (luma samples) */
+    uint8_t part_w, part_h; /* 16,8,4 */
+    int16_t mv_x, mv_y;     /* quarter-pel */
+} hlb200_me_cand_t;
+typedef struct hlb200_me_cost {
+    int32_t dist;               /* SAD of the trial reconstruction */
+    int32_t bits_rest;          /* residual bits without coeff_token */
+    int32_t single_ctr;         /* sum over non-zero blocks */
+    uint16_t cbp_luma4x4;       /* non-zero 4x4 blocks (bit = luma4x4BlkIdx) */
+    uint8_t total_coeff[16];    /* per luma4x4BlkIdx of the partition (0 where zero / outside) */
+    uint8_t trailing_ones[16];
+    uint16_t pad;
+} hlb200_me_cost_t;
+
+/* ---- library / device ---- */
+HLB200_API int hlb200_init(int device);            /* cudaSetDevice + sanity; HLB200_ERR_SYSTEM when no GPU */
+HLB200_API int hlb200_device_count(void);
+HLB200_API const char* hlb200_last_error(void);    /* thread-local text of the last CUDA failure */
+HLB200_API int hlb200_version(void);
+
+/* ---- stream context ---- */
+HLB200_API int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out);
+HLB200_API int hlb200_stream_destroy(hlb200_ctx_t* ctx);
+HLB200_API int hlb200_stream_set_cuda_stream(hlb200_ctx_t* ctx, void* cuda_stream); /* run on a caller-owned cudaStream_t */
+HLB200_API int hlb200_stream_sync(hlb200_ctx_t* ctx);
+/* source frame (hl_frame_video_t::data_ptr[0..2], include/hartallo/hl_frame.h:28-41) -> device */
+HLB200_API int hlb200_frame_upload(hlb200_ctx_t* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v, int stride_y, int stride_c);
+/* frame-store planes (DPB layout source/h264/hl_codec_264_dpb.c:88-166: tight Y|U|V, stride = width) */
+HLB200_API int hlb200_slot_upload(hlb200_ctx_t* ctx, int slot, const uint8_t* y, const uint8_t* u, const uint8_t* v);
+HLB200_API int hlb200_slot_download(hlb200_ctx_t* ctx, int slot, uint8_t* y, uint8_t* u, uint8_t* v);
+HLB200_API int hlb200_state_reset(hlb200_ctx_t* ctx); /* forget the per-MB state carried across frames (new stream) */
+
+/* ---- the hot path: one slice (= one picture) ---- */
+HLB200_API int hlb200_slice_encode(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params, hlb200_mb_record_t* out_records /* PicSizeInMbs, host */);
+/* asynchronous form: records stay on the device until fetched */
+HLB200_API int hlb200_slice_encode_async(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params);
+HLB200_API int hlb200_records_download(hlb200_ctx_t* ctx, hlb200_mb_record_t* out_records);
+
+/* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
+HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);
+HLB200_API int hlb200_interp_chroma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_u, uint8_t* pred_v);
+HLB200_API int hlb200_tq_recon(hlb200_ctx_t* ctx, int qp, int chroma_qp_index_offset, const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v,
+                               hlb200_mb_coeffs_t* coeffs, uint8_t* recon_y, uint8_t* recon_u, uint8_t* recon_v);
+HLB200_API int hlb200_sad4x4(hlb200_ctx_t* ctx, const uint8_t* pred_y, int use_satd, int32_t* out_per_blk /* (H/4)*(W/4) */);
+HLB200_API int hlb200_me_cost(hlb200_ctx_t* ctx, int ref_slot, int qp, const hlb200_me_cand_t* cands, int n, hlb200_me_cost_t* out);
+
+/* ---- the same kernels on device pointers (inputs already resident in HBM; asynchronous on `cuda_stream`) ---- */
+HLB200_API int hlb200_dev_interp_luma(const uint8_t* d_ref_y, int width, int height, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_y, void* cuda_stream);
+HLB200_API int hlb200_dev_interp_chroma(const uint8_t* d_ref_u, const uint8_t* d_ref_v, int width, int height, const hlb200_mb_motion_t* d_motion,
+                                        uint8_t* d_pred_u, uint8_t* d_pred_v, void* cuda_stream);
+HLB200_API int hlb200_dev_tq_recon(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
+                                   const uint8_t* d_pred_v, int width, int height, int qp, int chroma_qp_index_offset, hlb200_mb_coeffs_t* d_coeffs,
+                                   uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
+HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLB200_H_ */

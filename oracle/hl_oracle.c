@@ -325,3 +325,138 @@ HLO_API int hlo_trial_luma4x4(const uint8_t* src, int ss, const uint8_t* pred, i
     hlo_addclip_u8xi32(p4, r, rec);                /* wraps: me_ds.c:636-639 */
     return hlo_sad4x4(src, ss, rec, 4);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Residual coding + reconstruction of one INTER macroblock given its prediction:
+ *   luma   _hl_codec_264_rdo_mb_reconstruct_inter, rdo.c:2428-2478 (the "Single_ctr_luma >= 6" branch)
+ *   chroma _hl_codec_264_rdo_mb_reconstruct_chroma, rdo.c:2502-2700 and hl_codec_264_transf_decode_chroma, transf.c:161-296
+ * Planes are tight (pitch W for luma, W/2 for chroma).  chroma_ac is IN/OUT: it is the persistent ChromaACLevel of
+ * the macroblock object (the reference does not clear it for blocks whose residual is all zero, and uses it whenever
+ * the de-quantised DC of the block is non-zero -- transf.c:236-245).  Pass zeros for a stateless call. */
+HLO_API void hlo_recon_inter_mb(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
+                                const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int mb_is_intra, int16_t* luma_level /*[16][16]*/,
+                                int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,
+                                int32_t* cbp_ac /*[2]*/, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v)
+{
+    int b, i, x, y, c, Wc = W >> 1;
+    *cbp_luma4x4 = 0;
+    for (b = 0; b < 16; ++b) {                                        /* rdo.c:2428 */
+        int xo = ((b >> 2) & 1) * 8 + (b & 1) * 4, yo = (b >> 3) * 8 + ((b >> 1) & 1) * 4;
+        const uint8_t* s = src_y + (mby * 16 + yo) * W + mbx * 16 + xo;
+        const uint8_t* p = pred_y + (mby * 16 + yo) * W + mbx * 16 + xo;
+        uint8_t* r = rec_y + (mby * 16 + yo) * W + mbx * 16 + xo;
+        int32_t res[16], w[16], z[16], lv[16], cc[16], rr[16];
+        int all0 = 1;
+        for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) { res[y * 4 + x] = (int)s[y * W + x] - (int)p[y * W + x]; if (res[y * 4 + x]) all0 = 0; }
+        if (!all0) {
+            hlo_fwd4x4(res, w);
+            hlo_quant4x4(qp, 0, w, z);
+            all0 = 1;
+            for (i = 0; i < 16; ++i) if (z[i]) all0 = 0;
+            if (!all0) { hlo_zigzag(z, lv); *cbp_luma4x4 |= 1 << b; }
+        }
+        if (all0) for (i = 0; i < 16; ++i) lv[i] = 0;
+        for (i = 0; i < 16; ++i) luma_level[b * 16 + i] = (int16_t)lv[i];
+        if (*cbp_luma4x4 & (1 << b)) {
+            hlo_inv_zigzag(lv, cc);
+            hlo_dequant_inv4x4(qp, 0, cc, rr);
+            for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) r[y * W + x] = (uint8_t)clip1((int)p[y * W + x] + rr[y * 4 + x]);
+        } else {
+            for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) r[y * W + x] = p[y * W + x];
+        }
+    }
+    /* chroma, rdo.c:2561-2672 */
+    {
+        int32_t dccoef[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, single[2] = {0, 0}, totc[2] = {0, 0};
+        cbp_ac[0] = cbp_ac[1] = cbp_dc[0] = cbp_dc[1] = 0;
+        for (b = 0; b < 4; ++b) {
+            int xo = (b & 1) * 4, yo = (b >> 1) * 4;
+            for (c = 0; c < 2; ++c) {
+                const uint8_t* s = (c ? src_v : src_u) + (mby * 8 + yo) * Wc + mbx * 8 + xo;
+                const uint8_t* p = (c ? pred_v : pred_u) + (mby * 8 + yo) * Wc + mbx * 8 + xo;
+                int16_t* ac = chroma_ac + (c * 4 + b) * 16;
+                int32_t res[16], w[16], z[16], lv[16];
+                int all0 = 1;
+                for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) { res[y * 4 + x] = (int)s[y * Wc + x] - (int)p[y * Wc + x]; if (res[y * 4 + x]) all0 = 0; }
+                if (!all0) {
+                    hlo_fwd4x4(res, w);
+                    hlo_quant4x4(qpc, 1, w, z);                      /* always the intra offset: rdo.c:2588,2618 */
+                    hlo_zigzag(z, lv);
+                    for (i = 1; i < 16; ++i) ac[i - 1] = (int16_t)lv[i];   /* Scan4x4_AC_C, utils.h:183 */
+                    all0 = 1;
+                    for (i = 0; i < 16; ++i) if (ac[i]) all0 = 0;    /* allzero16 over [0..15]; [15] is never written */
+                    dccoef[c][b] = w[0];
+                    cbp_ac[c] |= all0 ? 0 : (1 << b);
+                    cbp_dc[c] |= w[0] ? (1 << b) : 0;
+                } else dccoef[c][b] = 0;
+                if (single[c] < 7 && (cbp_ac[c] & (1 << b))) {      /* rdo.c:2599-2607 */
+                    int32_t l16[16], sc, tc;
+                    for (i = 0; i < 16; ++i) l16[i] = ac[i];
+                    hlo_cavlc_bits(l16, 16, 0, &sc, &tc);
+                    single[c] += sc; totc[c] += tc;
+                }
+            }
+        }
+        for (c = 0; c < 2; ++c) if (single[c] < 7 && totc[c] == 1) cbp_ac[c] = 0;   /* rdo.c:2641-2649 */
+        if (cbp_dc[0] || cbp_dc[1]) {
+            for (c = 0; c < 2; ++c) if (cbp_dc[c]) {
+                int32_t h4[4], q4[4];
+                hlo_hadamard2x2(dccoef[c], h4);
+                hlo_quant_dc(qpc, mb_is_intra, h4, q4, 4);           /* rdo.c:2660: isIntra of the MB */
+                for (i = 0; i < 4; ++i) chroma_dc[c * 4 + i] = (int16_t)q4[i];
+                cbp_dc[c] = (q4[0] ? 1 : 0) | (q4[1] ? 2 : 0) | (q4[2] ? 4 : 0) | (q4[3] ? 8 : 0);
+            }
+        }
+        /* transf.c:161-296 */
+        for (c = 0; c < 2; ++c) {
+            const uint8_t* pp = (c ? pred_v : pred_u);
+            uint8_t* rp = (c ? rec_v : rec_u);
+            int32_t dcC[4] = {0, 0, 0, 0};
+            if (cbp_dc[c]) { int32_t l4[4]; for (i = 0; i < 4; ++i) l4[i] = chroma_dc[c * 4 + i]; hlo_scale_chroma_dc(qpc, l4, dcC); }
+            for (b = 0; b < 4; ++b) {
+                int xo = (b & 1) * 4, yo = (b >> 1) * 4;
+                const uint8_t* p = pp + (mby * 8 + yo) * Wc + mbx * 8 + xo;
+                uint8_t* r = rp + (mby * 8 + yo) * Wc + mbx * 8 + xo;
+                int use = (cbp_dc[c] || cbp_ac[c]) && (dcC[b] || (cbp_ac[c] & (1 << b)));
+                if (use) {
+                    int32_t l16[16], cc[16], rr[16];
+                    l16[0] = dcC[b];
+                    for (i = 1; i < 16; ++i) l16[i] = chroma_ac[(c * 4 + b) * 16 + i - 1];
+                    hlo_inv_zigzag(l16, cc);
+                    hlo_dequant_inv4x4(qpc, 1, cc, rr);
+                    for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) r[y * Wc + x] = (uint8_t)clip1((int)p[y * Wc + x] + rr[y * 4 + x]);
+                } else {
+                    for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) r[y * Wc + x] = p[y * Wc + x];
+                }
+            }
+        }
+    }
+}
+
+/* Whole ME candidate (one partition at one MV): hl_codec_264_me_ds_mb_compute_cost_mode, me_ds.c:527-688, without the
+ * coeff_token bits (they depend on encoder history).  Outputs: dist, bits_rest, single_ctr, cbp4x4 and
+ * per-block TotalCoeff / TrailingOnes indexed by luma4x4BlkIdx. */
+HLO_API void hlo_me_cost(const uint8_t* src, const uint8_t* ref, int W, int H, int qp, int mbx, int mby, int px, int py, int pw, int ph, int mvx, int mvy,
+                         int32_t* dist, int32_t* bits_rest, int32_t* single_ctr, int32_t* cbp, uint8_t* total_coeff /*16*/, uint8_t* trailing_ones /*16*/)
+{
+    uint8_t pred[256];
+    int bx, by, i;
+    *dist = *bits_rest = *single_ctr = *cbp = 0;
+    for (i = 0; i < 16; ++i) total_coeff[i] = trailing_ones[i] = 0;
+    hlo_interp_luma(ref, W, H, mbx * 16 + px, mby * 16 + py, pw, ph, mvx, mvy, pred);
+    for (by = 0; by < ph; by += 4) for (bx = 0; bx < pw; bx += 4) {
+        int32_t lv[16], nz, sc, tc, x = px + bx, y = py + by;
+        int blk = ((y >> 3) << 3) | ((x >> 3) << 2) | (((y >> 2) & 1) << 1) | ((x >> 2) & 1);
+        *dist += hlo_trial_luma4x4(src + (mby * 16 + y) * W + mbx * 16 + x, W, pred + by * 16 + bx, 16, qp, lv, &nz);
+        if (nz) {
+            int t1 = 0, k;
+            int full = hlo_cavlc_bits(lv, 16, 0, &sc, &tc);
+            /* trailing ones, residual.c:768-776 */
+            for (k = 15; k >= 0; --k) { if (!lv[k]) continue; if ((lv[k] == 1 || lv[k] == -1) && t1 < 3) ++t1; else break; }
+            *bits_rest += full - kCT[0][t1][tc];
+            *single_ctr += sc;
+            *cbp |= 1 << blk;
+            total_coeff[blk] = (uint8_t)tc; trailing_ones[blk] = (uint8_t)t1;
+        }
+    }
+}
