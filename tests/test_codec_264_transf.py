@@ -62,7 +62,7 @@ def test_tq_recon_parity(qp, kind):
         sel = oc["cbp_chroma_dc4x4"][:, c] != 0
         assert np.array_equal(gc["chroma_dc_level"][sel, c], oc["chroma_dc_level"][sel, c])
     assert np.array_equal(gc["chroma_ac_level"][..., :15], oc["chroma_ac_level"][..., :15])
-    if kind == "near":
+    if kind == "near" and qp >= 31:  # the content must exercise the all-zero / eliminated paths
         assert (oc["cbp_chroma_ac4x4"] == 0).any() and (oc["cbp_luma4x4"] == 0).any()
     st.close()
 
