@@ -308,6 +308,9 @@ __global__ void __launch_bounds__(128) k_me_cost(const uint8_t* __restrict__ src
 
 }  // namespace hlb
 
+namespace hlb {
+int launch_me_cost(const uint8_t* d_src, const uint8_t* d_ref, int W, int H, int qp, const hlb200_me_cand_t* d_cands, int n, hlb200_me_cost_t* d_out, cudaStream_t st);
+}
 using namespace hlb;
 
 extern "C" {
@@ -350,6 +353,37 @@ int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int hei
     k_sad4x4<<<(nb + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_a, d_b, width, height, use_satd, d_out);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
+}
+
+// dependency-free integer work: 8 independent accumulator chains x 4 ops (IADD3 + LOP3 pairs), fully unrolled
+__global__ void __launch_bounds__(256) k_int_alu_probe(int iters, uint32_t* __restrict__ sink)
+{
+    uint32_t a0 = threadIdx.x, a1 = blockIdx.x, a2 = 3, a3 = 5, a4 = 7, a5 = 11, a6 = 13, a7 = 17;
+    const uint32_t k = blockDim.x + 1u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            a0 = (a0 + k) ^ a4; a1 = (a1 + k) ^ a5; a2 = (a2 + k) ^ a6; a3 = (a3 + k) ^ a7;
+            a4 = (a4 + k) ^ a0; a5 = (a5 + k) ^ a1; a6 = (a6 + k) ^ a2; a7 = (a7 + k) ^ a3;
+        }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink, void* cuda_stream, uint64_t* ops_out)
+{
+    if (blocks <= 0 || iters <= 0 || !d_sink) return HLB200_ERR_INVALID_PARAMETER;
+    k_int_alu_probe<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(iters, d_sink);
+    HLB_CUDA(cudaGetLastError());
+    if (ops_out) *ops_out = (uint64_t)blocks * 256u * (uint64_t)iters * 32u;  // 16 adds + 16 xors per iteration
+    return HLB200_OK;
+}
+
+int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n, hlb200_me_cost_t* d_out,
+                       void* cuda_stream)
+{
+    if (!d_src_y || !d_ref_y || !d_cands || !d_out || n < 0 || (width & 15) || (height & 15) || qp < 0 || qp > 51) return HLB200_ERR_INVALID_PARAMETER;
+    return launch_me_cost(d_src_y, d_ref_y, width, height, qp, d_cands, n, d_out, (cudaStream_t)cuda_stream);
 }
 
 }  // extern "C"

@@ -173,6 +173,13 @@ HLB200_API int hlb200_dev_tq_recon(const uint8_t* d_src_y, const uint8_t* d_src_
                                    const uint8_t* d_pred_v, int width, int height, int qp, int chroma_qp_index_offset, hlb200_mb_coeffs_t* d_coeffs,
                                    uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
 HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
+HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n,
+                                  hlb200_me_cost_t* d_out, void* cuda_stream);
+
+/* ---- measurement aid: dependency-free 32-bit integer-ALU micro-kernel (the "measured integer peak" the ME roofline is quoted against).
+ * Launches `blocks` x 256 threads, each doing `iters` x 32 independent IADD3/LOP3; writes one word per thread to d_sink; *ops_out = integer
+ * operations executed. */
+HLB200_API int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink, void* cuda_stream, uint64_t* ops_out);
 
 #ifdef __cplusplus
 }

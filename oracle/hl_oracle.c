@@ -460,3 +460,52 @@ HLO_API void hlo_me_cost(const uint8_t* src, const uint8_t* ref, int W, int H, i
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batch drivers used by bench.py's cpu_baseline leg ("port") and by the parity tests at larger sizes: plain loops over
+ * the functions above, no new arithmetic. */
+/* cands: n x 8 int32 {mb_x, mb_y, part_x, part_y, part_w, part_h, mv_x, mv_y}; out: n x 4 int32 {dist, bits_rest, single_ctr, cbp} */
+HLO_API void hlo_me_cost_batch(const uint8_t* src, const uint8_t* ref, int W, int H, int qp, const int32_t* cands, int n, int32_t* out)
+{
+    int i;
+    uint8_t tc[16], t1[16];
+    for (i = 0; i < n; ++i) {
+        const int32_t* c = cands + 8 * i;
+        hlo_me_cost(src, ref, W, H, qp, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], out + 4 * i, out + 4 * i + 1, out + 4 * i + 2, out + 4 * i + 3, tc, t1);
+    }
+}
+/* Prediction (luma + chroma) and residual coding / reconstruction of macroblocks [mb_begin, mb_end) of a frame.
+ * parts: per MB 16 entries x 7 int32 {valid, ox, oy, w, h, mvx, mvy} (list of the MB's partitions, valid=0 terminates).
+ * Writes pred and rec planes (tight, Y|U|V) and returns the number of non-zero luma 4x4 blocks (a checksum for callers). */
+HLO_API int hlo_predict_recon_mbs(const uint8_t* src_yuv, const uint8_t* ref_yuv, int W, int H, int qp, int qpc, const int32_t* parts, int mb_begin, int mb_end,
+                                  uint8_t* pred_yuv, uint8_t* rec_yuv)
+{
+    const int Wc = W >> 1, Hc = H >> 1, mbw = W >> 4;
+    const uint8_t *sy = src_yuv, *su = sy + W * H, *sv = su + Wc * Hc, *ry = ref_yuv, *ru = ry + W * H, *rv = ru + Wc * Hc;
+    uint8_t *py = pred_yuv, *pu = py + W * H, *pv = pu + Wc * Hc, *oy = rec_yuv, *ou = oy + W * H, *ov = ou + Wc * Hc;
+    int mb, k, x, y, nz = 0;
+    for (mb = mb_begin; mb < mb_end; ++mb) {
+        const int mbx = mb % mbw, mby = mb / mbw;
+        int16_t ll[256], dc[8], ac[128];
+        int32_t c4, cdc[2], cac[2];
+        memset(ac, 0, sizeof(ac));
+        for (k = 0; k < 16; ++k) {
+            const int32_t* p = parts + ((size_t)mb * 16 + k) * 7;
+            uint8_t tmp[256], tcu[64], tcv[64];
+            int xl, yl;
+            if (!p[0]) break;
+            xl = mbx * 16 + p[1]; yl = mby * 16 + p[2];
+            hlo_interp_luma(ry, W, H, xl, yl, p[3], p[4], p[5], p[6], tmp);
+            for (y = 0; y < p[4]; ++y) for (x = 0; x < p[3]; ++x) py[(yl + y) * W + xl + x] = tmp[y * 16 + x];
+            hlo_interp_chroma(ru, Wc, Hc, xl, yl, p[3] >> 1, p[4] >> 1, p[5], p[6], tcu);
+            hlo_interp_chroma(rv, Wc, Hc, xl, yl, p[3] >> 1, p[4] >> 1, p[5], p[6], tcv);
+            for (y = 0; y < (p[4] >> 1); ++y) for (x = 0; x < (p[3] >> 1); ++x) {
+                pu[((yl >> 1) + y) * Wc + (xl >> 1) + x] = tcu[y * 8 + x];
+                pv[((yl >> 1) + y) * Wc + (xl >> 1) + x] = tcv[y * 8 + x];
+            }
+        }
+        hlo_recon_inter_mb(sy, su, sv, py, pu, pv, W, mbx, mby, qp, qpc, 0, ll, dc, ac, &c4, cdc, cac, oy, ou, ov);
+        for (k = 0; k < 16; ++k) nz += (c4 >> k) & 1;
+    }
+    return nz;
+}
