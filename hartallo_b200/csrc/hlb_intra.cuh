@@ -179,7 +179,12 @@ HLB_HD int ic_pred_px(int mode, const int* p, const ICParams& q, int x, int y)
     case 0: return q.dc[((y >> 2) << 1) | (x >> 2)];
     case 1: return p[1 + y];
     case 2: return p[9 + x];
-    default: return clip255((q.a + q.b * (x - 3) + q.c * (y - 3) + 16) >> 5);
+    default: {
+        // the reference iterates with UNSIGNED x,y (pred_intra.c:1194,1214): the sum is formed modulo 2^32 and shifted LOGICALLY, so a
+        // negative plane value becomes a large positive one and clips to 255 instead of 0
+        const uint32_t v = ((uint32_t)q.a + (uint32_t)q.b * (uint32_t)(x - 3) + (uint32_t)q.c * (uint32_t)(y - 3) + 16u) >> 5;
+        return clip255((int)v);
+    }
     }
 }
 

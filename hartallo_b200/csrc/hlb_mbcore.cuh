@@ -1,0 +1,1006 @@
+// hlb_mbcore.cuh -- per-macroblock decide + reconstruct of a P (or I) picture: the device-side counterpart of the loop body of
+// hl_codec_264_nal_slice_data_encode (source/h264/hl_codec_264_slice.c:1786-1894), i.e.
+//   hl_codec_264_rdo_mb_guess_best_inter_pred_avc   source/h264/hl_codec_264_rdo.c:678
+//   hl_codec_264_me_ds_mb_find_best_cost            source/h264/hl_codec_264_me_ds.c:104   (+ compute_cost_mode :527)
+//   mvp / PSkip mv / neighbour partitions           source/h264/hl_codec_264_utils.c:709-963, source/h264/hl_codec_264_mb.c:426
+//   nC of the CAVLC rate term                       source/h264/hl_codec_264_residual.c:624-755
+//   reconstruction, chroma, CBP                     rdo.c:2140-2780, source/h264/hl_codec_264_transf.c:161
+//   intra decision (I pictures and inside P)        rdo.c:99-300, 1526-2137  (hlb_mbintra.cuh)
+//
+// Execution model ("master / lanes"): the serial control flow of one macroblock (search trajectory, mode loop, commits) is
+// written once as ordinary sequential code; every data-parallel piece (<= 9 candidates x 16 4x4 blocks of trial encodes, the
+// 24 blocks of a reconstruction, intra mode x block trials) is a *command* made of phases, each phase a function of (work, lane).
+// On the GPU one CTA owns one macroblock: thread 0 runs the control flow, posts a command in shared memory and all threads
+// run its phases with a CTA barrier between phases.  The same source compiles as plain C++ (lanes become loops) for the CPU
+// emulation harness under tools/emu, which exists to debug the control flow against traces of the reference -- it is never
+// part of the shipped library.
+#pragma once
+#include <float.h>
+#include <limits.h>
+
+#include "../../include/hlb200.h"
+#include "hlb_prims.cuh"
+#include "hlb_intra.cuh"
+
+#ifdef HLB_EMU_DEBUG
+#include <stdio.h>
+extern int g_emu_dbg;   // set by the emulation harness for the macroblock under investigation
+#define HLB_DBG(...) do { if (g_emu_dbg) fprintf(stderr, __VA_ARGS__); } while (0)
+#else
+#define HLB_DBG(...) do { } while (0)
+#endif
+
+namespace hlb {
+
+enum { MBK_PSKIP = HLB200_MB_P_SKIP, MBK_INTER = HLB200_MB_P_INTER, MBK_I16 = HLB200_MB_I16x16, MBK_I4 = HLB200_MB_I4x4 };
+
+// State of one macroblock address that outlives the macroblock (read by later MBs of the picture and, for the fields the
+// reference never resets, by the same address in the next picture -- SURVEY Appendix C).
+struct MbState {
+    uint8_t kind;          // MBK_*
+    uint8_t part_mode;     // 0 16x16, 1 16x8, 2 8x16, 3 8x8 (final geometry; 0 for PSkip)
+    uint8_t sub_mode[4];   // 0 8x8, 1 8x4, 2 4x8, 3 4x4
+    uint8_t cbp_luma;      // CodedBlockPatternLuma (8x8 bits)
+    uint8_t cbp_chroma;    // CodedBlockPatternChroma
+    uint8_t tc_luma[16];   // TotalCoeffsLuma[] exactly as the reference leaves it (trial leftovers included)
+    uint8_t tc_cac[2][4];  // TotalCoeffsChromaACCbCr
+    int8_t ref_idx[4];     // RefIdxL0
+    uint8_t i4_mode[16];   // Intra4x4PredMode
+    uint8_t last_sctr;     // pc_esd->rdo.Single_ctr after this macroblock (a chain through raster order, residual.c:882)
+    uint8_t pad[3];
+    int16_t mv[4][4][2];       // MvL0
+    int16_t chroma_ac[2][4][16];  // ChromaACLevel (persistent: only rewritten for blocks with a non-zero residual, rdo.c:2577)
+    int16_t chroma_dc[2][4];      // ChromaDCLevel
+};
+
+struct FrameCtx {
+    int W, H, mbw, mbh;
+    int qp, qpc;
+    int is_p, me_range, num_refs;
+    double lambda;                       // lambda_mode = 0.852 * (1 << ((QP-12)/3)), slice.c:1766
+    const uint8_t* src[3];
+    uint8_t* cur[3];                     // reconstruction of the current picture (frame-store planes, pitch = W / W/2)
+    const uint8_t* ref[HLB200_MAX_REFS][3];
+    MbState* st;
+    hlb200_mb_record_t* rec;
+};
+
+// ---- partition geometry of the 7 search modes (rdo.c:711-809): 0 16x16, 1 16x8, 2 8x16, 3 8x8, 4 8x4, 5 4x8, 6 4x4 ----
+HLB_HD int mode_nparts(int m) { return m == 0 ? 1 : (m < 3 ? 2 : 4); }
+HLB_HD int mode_nsub(int m) { return m <= 3 ? 1 : (m == 6 ? 4 : 2); }
+HLB_HD int mode_part_w(int m) { return (m == 0 || m == 1) ? 16 : 8; }
+HLB_HD int mode_part_h(int m) { return (m == 0 || m == 2) ? 16 : 8; }
+HLB_HD int mode_sub_w(int m) { return m <= 3 ? mode_part_w(m) : ((m == 4) ? 8 : 4); }
+HLB_HD int mode_sub_h(int m) { return m <= 3 ? mode_part_h(m) : ((m == 5) ? 8 : 4); }
+HLB_HD void mode_rect(int m, int part, int sub, int& ox, int& oy, int& w, int& h)
+{
+    const int pw = mode_part_w(m), ph = mode_part_h(m);
+    w = mode_sub_w(m); h = mode_sub_h(m);
+    ox = (part % (16 / pw)) * pw; oy = (part / (16 / pw)) * ph;
+    if (m > 3) { ox += (sub % (8 / w)) * w; oy += (sub / (8 / w)) * h; }
+}
+// (mbPartIdx, subMbPartIdx) covering luma position (x,y) for a geometry given as part_mode + sub_mode[] (6.4.12.4, mb.h:313)
+HLB_HD void part_at(int part_mode, const uint8_t* sub_mode, int x, int y, int& part, int& sub)
+{
+    sub = 0;
+    switch (part_mode) {
+    case 0: part = 0; break;
+    case 1: part = y >> 3; break;
+    case 2: part = x >> 3; break;
+    default: {
+        part = ((y >> 3) << 1) | (x >> 3);
+        const int lx = x & 7, ly = y & 7;
+        switch (sub_mode[part]) {
+        case 0: sub = 0; break;
+        case 1: sub = ly >> 2; break;
+        case 2: sub = lx >> 2; break;
+        default: sub = ((ly >> 2) << 1) | (lx >> 2); break;
+        }
+    }
+    }
+}
+
+#define HLB_MAXC 9
+enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_LUMA, CMD_CHROMA, CMD_STORE, CMD_I16_EVAL, CMD_I16_RATE, CMD_I16_RECON, CMD_I4_EVAL, CMD_I4_COMMIT, CMD_PRED_CHROMA_INTRA };
+
+// Scratch of the macroblock being encoded (shared memory on the GPU)
+struct MbWork {
+    // command mailbox
+    int cmd, arg0, arg1;
+    // identity / neighbourhood
+    int mb, mbx, mby;
+    int availA, availB, availC, availD;
+    // source samples
+    uint8_t src_y[256];
+    uint8_t src_c[2][64];
+    // evolving state of the current macroblock
+    uint8_t tc[16];        // TotalCoeffsLuma
+    uint8_t tc_cac[2][4];
+    uint8_t cbp_gate;      // CodedBlockPatternLuma as left by the previous picture (gate of in-MB neighbours, utils.h:10-20)
+    int8_t extA[16], extB[16];   // nA / nB contributed by the neighbouring macroblocks (-1 = not available), per luma4x4BlkIdx on the MB edge
+    int last_sctr;         // rdo.Single_ctr chain; -1 = not yet written by this macroblock
+    int need_prev_sctr;    // set when the chain value of the raster predecessor was consumed
+    int16_t chroma_ac[2][4][16];
+    int16_t chroma_dc[2][4];
+    // ---- ME ----
+    int mode, ref;
+    const uint8_t* ref_y;
+    int16_t mv_cur[4][4][2];   // (*MvL0) of the current macroblock during the search
+    int8_t ref_cur[4];         // RefIdxL0 of the current macroblock (stale during the search)
+    int16_t mvp[4][4][2];
+    int16_t best_mv[4][4][2];
+    double best_cost[4][4];
+    int best_dist[4][4], best_sctr[4][4], best_cbp[4][4];
+    int probably_pskip;
+    // one evaluation step
+    int part_ox, part_oy, part_w, part_h, ncand;
+    int16_t cmvx[HLB_MAXC], cmvy[HLB_MAXC];
+    int32_t r_dist[HLB_MAXC][16];
+    uint16_t r_bits[HLB_MAXC][16];
+    uint8_t r_tc[HLB_MAXC][16], r_t1[HLB_MAXC][16], r_sctr[HLB_MAXC][16], r_nz[HLB_MAXC][16], eff[HLB_MAXC][16];
+    int32_t c_dist[HLB_MAXC], c_rbc[HLB_MAXC], c_sctr[HLB_MAXC], c_cbp[HLB_MAXC], c_last[HLB_MAXC];
+    // ---- reconstruction ----
+    int fin_mode, fin_sub[4];          // committed geometry (part_mode, sub_mode[])
+    int16_t fin_mv[4][4][2];
+    int8_t fin_ref[4];
+    uint8_t pred_y[256];
+    uint8_t pred_c[2][64];
+    uint8_t rec_y[256];
+    uint8_t rec_c[2][64];
+    int16_t luma_level[16][16];
+    int luma_skip_residual;            // Single_ctr_luma < 6 (rdo.c:2419)
+    int cbp_luma4x4;
+    int cbp_ac[2], cbp_dc[2];
+    int mb_is_intra;
+    int32_t c_dccoef[2][4];
+    uint8_t c_acnz[2][4], c_sc[2][4], c_tc[2][4], c_resnz[2][4];
+    // ---- intra ----
+    int i16_mode, i16_cbp4x4, i4_cbp4x4, intra_chroma_mode;
+    int16_t i16_dc[16];
+    int16_t i16_ac[16][16];
+    uint8_t i4_mode[16], prev_i4[16], rem_i4[16];
+    int32_t p33[33];
+    int32_t p17[2][17];
+    int32_t p13[13];
+    // scratch of the intra trials
+    int16_t t_ac[4][16][16];
+    int32_t t_dcw[4][16];
+    int16_t t_dc[4][16];
+    uint8_t t_nz[4][16], t_tc[4][16], t_t1[4][16], t_sc[4][16];
+    uint16_t t_bits[4][16];
+    int32_t t_dist[4][16];
+    int t_mode_ok[4], t_cbp[4], t_rate[4], t_sctr[4], t_dcbits[4];
+    uint8_t t_pred[4][256];
+    int i4_blk;
+    int32_t q_dist[9];
+    uint16_t q_bits[9];
+    uint8_t q_nz[9], q_tc[9], q_t1[9], q_sc[9], q_ok[9], q_res0[9];
+    int16_t q_lv[9][16];
+    uint8_t q_pred[9][16];
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Neighbour derivation for motion data (6.4.10.7 + 8.4.1.3.2; mb.c:426-541, utils.c:854-963)
+// ------------------------------------------------------------------------------------------------------------------
+struct NbMotion { int avail; int ref; int mvx, mvy; };
+
+HLB_HD NbMotion nb_motion_at(const MbWork& w, const FrameCtx& f, int xN, int yN, int cur_part, int cur_sub)
+{
+    NbMotion r;
+    r.avail = 0; r.ref = -1; r.mvx = 0; r.mvy = 0;
+    if (xN >= 0 && xN <= 15 && yN >= 0 && yN <= 15) {  // inside the current macroblock: geometry of the mode being searched
+        uint8_t sm[4];
+        const int s = w.mode <= 3 ? 0 : w.mode - 3;
+        sm[0] = sm[1] = sm[2] = sm[3] = (uint8_t)s;
+        int p, q;
+        part_at(w.mode < 3 ? w.mode : 3, sm, xN, yN, p, q);
+        if (p > cur_part || (p == cur_part && q > cur_sub)) return r;  // not yet searched
+        r.avail = 1; r.ref = w.ref_cur[p]; r.mvx = w.mv_cur[p][q][0]; r.mvy = w.mv_cur[p][q][1];
+        return r;
+    }
+    int addr;
+    if (yN < 0 && xN >= 0 && xN <= 15) { if (!w.availB) return r; addr = w.mb - f.mbw; }
+    else if (yN < 0 && xN > 15) { if (!w.availC) return r; addr = w.mb - f.mbw + 1; }
+    else if (yN < 0 && xN < 0) { if (!w.availD) return r; addr = w.mb - f.mbw - 1; }
+    else if (xN < 0 && yN >= 0 && yN <= 15) { if (!w.availA) return r; addr = w.mb - 1; }
+    else return r;
+    const MbState& s = f.st[addr];
+    r.avail = 1;
+    if (s.kind == MBK_I16 || s.kind == MBK_I4) return r;  // intra: ref -1, mv 0
+    int p, q;
+    part_at(s.part_mode, s.sub_mode, (xN + 16) & 15, (yN + 16) & 15, p, q);
+    r.ref = s.ref_idx[p]; r.mvx = s.mv[p][q][0]; r.mvy = s.mv[p][q][1];
+    return r;
+}
+
+HLB_HD int median3(int a, int b, int c)
+{
+    const int mn = a < b ? (a < c ? a : c) : (b < c ? b : c), mx = a > b ? (a > c ? a : c) : (b > c ? b : c);
+    return a + b + c - mn - mx;
+}
+
+// 8.4.1.3 (utils.c:751-798).  (ox,oy,pw) = origin and predPartWidth of the partition under the current search mode
+HLB_HD void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, int ref, int& mx, int& my)
+{
+    int ox, oy, pw, ph;
+    mode_rect(w.mode, part, sub, ox, oy, pw, ph);
+    NbMotion A = nb_motion_at(w, f, ox - 1, oy, part, sub);
+    NbMotion B = nb_motion_at(w, f, ox, oy - 1, part, sub);
+    NbMotion C = nb_motion_at(w, f, ox + pw, oy - 1, part, sub);
+    if (!C.avail) C = nb_motion_at(w, f, ox - 1, oy - 1, part, sub);
+    const int mw = mode_part_w(w.mode), mh = mode_part_h(w.mode);
+    if (mw == 16 && mh == 8 && part == 0 && B.ref == ref) { mx = B.mvx; my = B.mvy; return; }
+    if (mw == 16 && mh == 8 && part == 1 && A.ref == ref) { mx = A.mvx; my = A.mvy; return; }
+    if (mw == 8 && mh == 16 && part == 0 && A.ref == ref) { mx = A.mvx; my = A.mvy; return; }
+    if (mw == 8 && mh == 16 && part == 1 && C.ref == ref) { mx = C.mvx; my = C.mvy; return; }
+    if (!B.avail && !C.avail && A.avail) { B = A; C = A; }
+    if (A.ref == ref && B.ref != ref && C.ref != ref) { mx = A.mvx; my = A.mvy; }
+    else if (B.ref == ref && C.ref != ref && A.ref != ref) { mx = B.mvx; my = B.mvy; }
+    else if (C.ref == ref && B.ref != ref && A.ref != ref) { mx = C.mvx; my = C.mvy; }
+    else { mx = median3(A.mvx, B.mvx, C.mvx); my = median3(A.mvy, B.mvy, C.mvy); }
+}
+
+// 8.4.1.1 (utils.c:709-748); only ever called with the 16x16 geometry
+HLB_HD void derive_pskip_mv(const MbWork& w, const FrameCtx& f, int& mx, int& my)
+{
+    NbMotion A = nb_motion_at(w, f, -1, 0, 0, 0);
+    NbMotion B = nb_motion_at(w, f, 0, -1, 0, 0);
+    if (!A.avail || !B.avail || (A.ref == 0 && A.mvx == 0 && A.mvy == 0) || (B.ref == 0 && B.mvx == 0 && B.mvy == 0)) { mx = my = 0; return; }
+    derive_mvp(w, f, 0, 0, 0, mx, my);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// nC inputs coming from the neighbouring macroblocks (residual.c:698-741)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD int nb_count(const MbState& s, int blk)
+{
+    if (s.kind == MBK_PSKIP) return 0;
+    if (((s.cbp_luma >> (blk >> 2)) & 1) == 0) return 0;
+    return s.tc_luma[blk];
+}
+HLB_HD int nc_from(int nA, int nB)
+{
+    if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1;
+    if (nA >= 0) return nA;
+    if (nB >= 0) return nB;
+    return 0;
+}
+// nC of luma block `blk` of the current macroblock given per-block counts `cnt` (TotalCoeffsLuma view to use for in-MB neighbours)
+HLB_HD int luma_nc(const MbWork& w, const uint8_t* cnt, int blk)
+{
+    const int x = blk_x(blk), y = blk_y(blk);
+    int nA, nB;
+    if (x > 0) { const int a = blk_idx_from_xy(x - 4, y); nA = ((w.cbp_gate >> (a >> 2)) & 1) ? cnt[a] : 0; }
+    else nA = w.extA[blk];
+    if (y > 0) { const int b = blk_idx_from_xy(x, y - 4); nB = ((w.cbp_gate >> (b >> 2)) & 1) ? cnt[b] : 0; }
+    else nB = w.extB[blk];
+    return nc_from(nA, nB);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sample access
+// ------------------------------------------------------------------------------------------------------------------
+// 9x9 window (rows/cols -2..+6 around a 4x4 block whose pixel (0,0) sits at (X,Y)), per-sample clamp (interpol.c:108-131)
+HLB_HD void ref_window9(const uint8_t* plane, int W, int H, int X, int Y, uint8_t t[81])
+{
+    if (X >= 2 && Y >= 2 && X + 7 <= W && Y + 7 <= H) {
+        const uint8_t* p = plane + (Y - 2) * W + (X - 2);
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) t[r * 9 + c] = p[r * W + c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int y = clip3(0, H - 1, Y - 2 + r);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) t[r * 9 + c] = plane[y * W + clip3(0, W - 1, X - 2 + c)];
+        }
+    }
+}
+
+// luma prediction of the 4x4 block at (bx,by) (MB coordinates) belonging to a partition with origin (ox,oy) and motion (mvx,mvy)
+HLB_HD void pred_luma_4x4(const FrameCtx& f, const uint8_t* ref_y, int mbx, int mby, int ox, int oy, int bx, int by, int mvx, int mvy, uint8_t out[16])
+{
+    const int X = clip3(-17, f.W + 17, mbx * 16 + ox + (mvx >> 2)) + (bx - ox);   // origin clip of pred_inter.c:395 applies to the partition
+    const int Y = clip3(-17, f.H + 17, mby * 16 + oy + (mvy >> 2)) + (by - oy);
+    uint8_t win[81];
+    ref_window9(ref_y, f.W, f.H, X, Y, win);
+    interp_luma_4x4(win + 20, 9, mvx & 3, mvy & 3, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CMD_ME_EVAL: the trial encodes of one search step (me_ds.c:527-688 for every candidate of the step)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
+{
+    const int bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
+    const int c = lane / nblk, k = lane - c * nblk;
+    if (c >= w.ncand) return;
+    const int bx = w.part_ox + (k % bw) * 4, by = w.part_oy + (k / bw) * 4;
+    const int blk = blk_idx_from_xy(bx, by);
+    uint8_t pv[16], sv[16];
+    pred_luma_4x4(f, w.ref_y, w.mbx, w.mby, w.part_ox, w.part_oy, bx, by, w.cmvx[c], w.cmvy[c], pv);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sv[r * 4 + q] = w.src_y[(by + r) * 16 + bx + q];
+    int m[16], lv[16];
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; nz |= (m[i] != 0); }
+    if (nz) {
+        fwd_transform4x4(m);
+        quant4x4_ac(m, f.qp, false);
+        zigzag4x4(m, lv);
+        nz = false;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nz |= (lv[i] != 0);
+    }
+    int dist, bits = 0, tc = 0, t1 = 0, sc = 0;
+    if (nz) {
+        const CavlcInfo ci = cavlc_block_info(lv, 16, false);
+        bits = ci.bits_rest; tc = ci.total_coeff; t1 = ci.trailing_ones; sc = ci.single_ctr;
+        int cc[16];
+        inv_zigzag4x4(lv, cc);
+        dequant4x4(cc, f.qp, false);
+        inv_transform4x4(cc);
+        uint8_t rec[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[i] = (uint8_t)((int)pv[i] + cc[i]);  // wraps mod 256 (hl_math.h:261)
+        dist = sad16(sv, rec);
+    } else dist = sad16(sv, pv);
+    w.r_dist[c][blk] = dist; w.r_bits[c][blk] = (uint16_t)bits; w.r_tc[c][blk] = (uint8_t)tc; w.r_t1[c][blk] = (uint8_t)t1;
+    w.r_sctr[c][blk] = (uint8_t)sc; w.r_nz[c][blk] = nz ? 1 : 0;
+}
+HLB_HD bool blk_in_part(const MbWork& w, int blk)
+{
+    const int x = blk_x(blk), y = blk_y(blk);
+    return x >= w.part_ox && x < w.part_ox + w.part_w && y >= w.part_oy && y < w.part_oy + w.part_h;
+}
+// per block: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806)
+HLB_HD void me_phase_scan(MbWork& w, int lane)
+{
+    if (lane >= 16) return;
+    int e = w.tc[lane];
+    const bool in = blk_in_part(w, lane);
+    for (int c = 0; c < w.ncand; ++c) {
+        if (in && w.r_nz[c][lane]) e = w.r_tc[c][lane];
+        w.eff[c][lane] = (uint8_t)e;
+    }
+    w.tc[lane] = (uint8_t)e;
+}
+HLB_HD void me_phase_token(MbWork& w, int lane)
+{
+    const int bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
+    const int c = lane / nblk, k = lane - c * nblk;
+    if (c >= w.ncand) return;
+    const int blk = blk_idx_from_xy(w.part_ox + (k % bw) * 4, w.part_oy + (k / bw) * 4);
+    if (!w.r_nz[c][blk]) return;
+    const int nC = luma_nc(w, w.eff[c], blk);
+    HLB_DBG("      token c%d blk %d: nC %d tc %d t1 %d gate %x eff[4]=%d eff[1]=%d extA %d extB %d\n", c, blk, nC, w.r_tc[c][blk], w.r_t1[c][blk], w.cbp_gate, w.eff[c][4], w.eff[c][1], w.extA[blk], w.extB[blk]);
+    w.r_bits[c][blk] = (uint16_t)(w.r_bits[c][blk] + coeff_token_len(nC, w.r_tc[c][blk], w.r_t1[c][blk]));
+}
+HLB_HD void me_phase_sum(MbWork& w, int lane)
+{
+    if (lane >= w.ncand) return;
+    const int c = lane, bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
+    int dist = 0, rbc = 0, sc = 0, cbp = 0, last = -1;
+    for (int k = 0; k < nblk; ++k) {
+        const int blk = blk_idx_from_xy(w.part_ox + (k % bw) * 4, w.part_oy + (k / bw) * 4);
+        dist += w.r_dist[c][blk];
+        if (w.r_nz[c][blk]) { rbc += w.r_bits[c][blk]; sc += w.r_sctr[c][blk]; cbp |= 1 << blk; last = w.r_sctr[c][blk]; }
+    }
+    w.c_dist[c] = dist; w.c_rbc[c] = rbc; w.c_sctr[c] = sc; w.c_cbp[c] = cbp; w.c_last[c] = last;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Search of one mode (me_ds.c:104-477)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_TABLE static const int8_t kDspInt[9][2] = {{0, 2}, {-1, 1}, {1, 1}, {-2, 0}, {0, 0}, {2, 0}, {-1, -1}, {1, -1}, {0, -2}};
+HLB_TABLE static const int8_t kDspHalf[5][2] = {{0, 1}, {-1, 0}, {0, -1}, {1, 0}, {0, 0}};
+HLB_TABLE static const int8_t kDspQuarter[9][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {0, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+// points skipped in the next iteration after the best point `idx` (me_ds.c:384-465), as bit masks over pattern indices
+HLB_TABLE static const uint16_t kPruneInt[9] = {0x1D0, 0x130, 0x1DA, 0x0B4, 0x000, 0x05A, 0x0B7, 0x05F, 0x017};
+HLB_TABLE static const uint16_t kPruneHalf[5] = {0x014, 0x018, 0x011, 0x012, 0x000};
+HLB_TABLE static const uint16_t kPruneQuarter[9] = {0x1B0, 0x1F8, 0x03F, 0x1B6, 0x000, 0x0DB, 0x036, 0x03F, 0x01B};
+HLB_TABLE static const uint8_t kHeaderBits[7] = {3, 5, 5, 11, 19, 19, 27};
+
+template <class X>
+HLB_HD void me_eval(X& x, MbWork& w)
+{
+    const int nblk = (w.part_w >> 2) * (w.part_h >> 2);
+    x.run(CMD_ME_EVAL, w.ncand * nblk < 16 ? 16 : w.ncand * nblk);  // the scan phase needs one lane per luma block
+    for (int c = 0; c < w.ncand; ++c)
+        if (w.c_last[c] >= 0) w.last_sctr = w.c_last[c];
+}
+
+HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
+{
+    w.best_cost[p][s] = cost; w.best_sctr[p][s] = w.c_sctr[c]; w.best_dist[p][s] = w.c_dist[c]; w.best_cbp[p][s] = w.c_cbp[c];
+    w.best_mv[p][s][0] = w.cmvx[c]; w.best_mv[p][s][1] = w.cmvy[c];
+}
+
+template <class X>
+HLB_HD void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
+{
+    w.mode = mode;
+    const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
+    for (int p = 0; p < nparts; ++p)
+        for (int s = 0; s < nsub; ++s) { w.best_sctr[p][s] = 9; w.best_dist[p][s] = INT_MAX; w.best_cost[p][s] = DBL_MAX; }
+    w.probably_pskip = 0;
+    if (mode == 0 && w.ref == 0) {  // PSkip probe (me_ds.c:229-261)
+        int sx, sy, px, py;
+        derive_pskip_mv(w, f, sx, sy);
+        derive_mvp(w, f, 0, 0, w.ref, px, py);
+        if (px == sx && py == sy) {
+            mode_rect(mode, 0, 0, w.part_ox, w.part_oy, w.part_w, w.part_h);
+            w.ncand = 1; w.cmvx[0] = (int16_t)px; w.cmvy[0] = (int16_t)py;
+            me_eval(x, w);
+            if (w.c_rbc[0] == 0 || w.c_sctr[0] < 6) { w.probably_pskip = 1; set_best(w, 0, 0, 0.0, 0); }
+        }
+    }
+    for (int p = 0; p < nparts; ++p) {
+        for (int s = 0; s < nsub; ++s) {
+            int shift = 2, flags = 0xFFFFFF, px, py;
+            derive_mvp(w, f, p, s, w.ref, px, py);
+            w.mvp[p][s][0] = (int16_t)px; w.mvp[p][s][1] = (int16_t)py;
+            mode_rect(mode, p, s, w.part_ox, w.part_oy, w.part_w, w.part_h);
+            // cost at the predictor, then at (0,0) (me_ds.c:283-299)
+            w.ncand = 1; w.cmvx[0] = (int16_t)px; w.cmvy[0] = (int16_t)py;
+            if (px != 0 || py != 0) { w.ncand = 2; w.cmvx[1] = 0; w.cmvy[1] = 0; }
+            me_eval(x, w);
+            for (int c = 0; c < w.ncand; ++c) {
+                const int rbc_mv = se_len(w.cmvx[c] - px) + se_len(w.cmvy[c] - py);
+                const double cost = w.c_dist[c] + ((w.c_rbc[c] + rbc_mv) * f.lambda);
+                HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f [init]\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], cost);
+                if (cost < w.best_cost[p][s]) set_best(w, p, s, cost, c);
+            }
+            int cx = w.best_mv[p][s][0] >> 2, cy = w.best_mv[p][s][1] >> 2;
+            int wl = cx - f.me_range, wr = cx + f.me_range, wt = cy - f.me_range, wb = cy + f.me_range;
+            for (;;) {
+                int best_idx = -1;
+                const int count = shift == 1 ? 5 : 9;
+                uint8_t idxs[HLB_MAXC];
+                w.ncand = 0;
+                for (int i = 0; i < count; ++i) {
+                    if (!(flags & (1 << i))) continue;
+                    const int8_t* o = shift == 2 ? kDspInt[i] : (shift == 1 ? kDspHalf[i] : kDspQuarter[i]);
+                    const int mx = cx + o[0], my = cy + o[1];
+                    if (mx < wl || mx > wr || my < wt || my > wb) continue;
+                    idxs[w.ncand] = (uint8_t)i;
+                    w.cmvx[w.ncand] = (int16_t)(mx * (1 << shift)); w.cmvy[w.ncand] = (int16_t)(my * (1 << shift));
+                    ++w.ncand;
+                }
+                if (w.ncand > 0) {
+                    me_eval(x, w);
+                    for (int c = 0; c < w.ncand; ++c) {
+                        const int rbc_mv = se_len(w.cmvx[c] - px) + se_len(w.cmvy[c] - py);
+                        const double cost = w.c_dist[c] + ((w.c_rbc[c] + rbc_mv) * f.lambda);
+                        HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], cost);
+                        if (cost < w.best_cost[p][s]) { best_idx = idxs[c]; set_best(w, p, s, cost, c); }
+                    }
+                }
+                flags = 0xFFFFFF;
+                if (shift == 2 && best_idx == -1) {
+                    shift = 1;
+                    cx = w.best_mv[p][s][0] >> 2; cy = w.best_mv[p][s][1] >> 2;  // integer-pel value used as a half-pel centre
+                    wl = cx - f.me_range; wr = cx + f.me_range; wt = cy - f.me_range; wb = cy + f.me_range;
+                } else if (best_idx == -1) {
+                    if (shift == 1) {
+                        shift = 0;
+                        cx = w.best_mv[p][s][0]; cy = w.best_mv[p][s][1];
+                        wl = cx - f.me_range; wr = cx + f.me_range; wt = cy - f.me_range; wb = cy + f.me_range;
+                    } else break;
+                } else {
+                    cx = w.best_mv[p][s][0] >> shift; cy = w.best_mv[p][s][1] >> shift;
+                    flags &= ~(int)(shift == 2 ? kPruneInt[best_idx] : (shift == 1 ? kPruneHalf[best_idx] : kPruneQuarter[best_idx]));
+                }
+            }
+            w.mv_cur[p][s][0] = w.best_mv[p][s][0]; w.mv_cur[p][s][1] = w.best_mv[p][s][1];
+            HLB_DBG("   part m%d p%d s%d: mv (%d,%d) mvp (%d,%d) cost %.4f dist %d sctr %d\n", mode, p, s, w.best_mv[p][s][0], w.best_mv[p][s][1], px, py, w.best_cost[p][s], w.best_dist[p][s], w.best_sctr[p][s]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Inter prediction of the whole macroblock with the committed geometry (rdo.c:2331-2416) -> w.pred_y / w.pred_c
+// lanes 0..15 luma blocks (raster), 16..23 chroma 4x4 blocks (Cb 0..3, Cr 0..3)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void fin_rect(const MbWork& w, int x, int y, int& part, int& sub, int& ox, int& oy)
+{
+    uint8_t sm[4] = {(uint8_t)w.fin_sub[0], (uint8_t)w.fin_sub[1], (uint8_t)w.fin_sub[2], (uint8_t)w.fin_sub[3]};
+    part_at(w.fin_mode, sm, x, y, part, sub);
+    int m = w.fin_mode < 3 ? w.fin_mode : 3 + w.fin_sub[part], pw, ph;
+    mode_rect(m, part, sub, ox, oy, pw, ph);
+}
+HLB_HD void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane < 16) {
+        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
+        int p, s, ox, oy;
+        fin_rect(w, bx, by, p, s, ox, oy);
+        uint8_t pv[16];
+        pred_luma_4x4(f, f.ref[w.fin_ref[p]][0], w.mbx, w.mby, ox, oy, bx, by, w.fin_mv[p][s][0], w.fin_mv[p][s][1], pv);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w.pred_y[(by + r) * 16 + bx + q] = pv[r * 4 + q];
+    } else if (lane < 24) {
+        const int c = (lane - 16) >> 2, b = (lane - 16) & 3, cx0 = (b & 1) * 4, cy0 = (b >> 1) * 4;
+        const int Wc = f.W >> 1, Hc = f.H >> 1;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) {
+                const int px = cx0 + q, py = cy0 + r;
+                int p, s, ox, oy;
+                fin_rect(w, px * 2, py * 2, p, s, ox, oy);
+                const uint8_t* rp = f.ref[w.fin_ref[p]][1 + c];
+                const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
+                const int x0 = w.mbx * 8 + px + (mvx >> 3), y0 = w.mby * 8 + py + (mvy >> 3);
+                const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
+                w.pred_c[c][py * 8 + px] = (uint8_t)interp_chroma_px(rp[ya + xa], rp[ya + xb], rp[yc + xa], rp[yc + xb], mvx & 7, mvy & 7);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Luma residual coding + reconstruction of an inter macroblock (rdo.c:2418-2478): lanes 0..15 = luma4x4BlkIdx
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane >= 16) return;
+    const int bx = blk_x(lane), by = blk_y(lane);
+    uint8_t sv[16], pv[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sv[r * 4 + q] = w.src_y[(by + r) * 16 + bx + q]; pv[r * 4 + q] = w.pred_y[(by + r) * 16 + bx + q]; }
+    int rec[16];
+    bool coded = false;
+    if (!w.luma_skip_residual) {
+        int m[16], lv[16];
+        bool nz = false;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; nz |= (m[i] != 0); }
+        if (nz) {
+            fwd_transform4x4(m);
+            quant4x4_ac(m, f.qp, false);
+            zigzag4x4(m, lv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) coded |= (lv[i] != 0);
+        }
+        if (coded) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w.luma_level[lane][i] = (int16_t)lv[i];
+            int c[16];
+            inv_zigzag4x4(lv, c);
+            dequant4x4(c, f.qp, false);
+            inv_transform4x4(c);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rec[i] = clip255((int)pv[i] + c[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w.luma_level[lane][i] = 0;
+        }
+    }
+    if (!coded) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[i] = pv[i];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w.rec_y[(by + r) * 16 + bx + q] = (uint8_t)rec[r * 4 + q];
+    w.r_nz[0][lane] = coded ? 1 : 0;   // gathered into cbp_luma4x4 by the master
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Chroma residual coding + reconstruction (rdo.c:2502-2700, transf.c:161-296) from w.pred_c.
+// phase 0: lanes 0..7 = (plane, block): residual, transform, AC quantisation (intra offset, always), CAVLC info
+// phase 1: lane 0: the serial bookkeeping (single-coefficient elimination, DC Hadamard + quantisation)
+// phase 2: lanes 0..7: reconstruction
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane >= 8) return;
+    const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+    int m[16], lv[16];
+    bool nz = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { m[r * 4 + q] = (int)w.src_c[c][(y0 + r) * 8 + x0 + q] - (int)w.pred_c[c][(y0 + r) * 8 + x0 + q]; nz |= (m[r * 4 + q] != 0); }
+    w.c_resnz[c][b] = nz ? 1 : 0;
+    w.c_dccoef[c][b] = 0; w.c_acnz[c][b] = 0; w.c_sc[c][b] = 9; w.c_tc[c][b] = 0;
+    if (!nz) return;
+    fwd_transform4x4(m);
+    w.c_dccoef[c][b] = m[0];
+    quant4x4_ac(m, f.qpc, true);
+    zigzag4x4(m, lv);
+    bool acnz = false;
+#pragma unroll
+    for (int i = 1; i < 16; ++i) { w.chroma_ac[c][b][i - 1] = (int16_t)lv[i]; acnz |= (lv[i] != 0); }
+    w.c_acnz[c][b] = acnz ? 1 : 0;
+    if (acnz) {
+        int l16[16];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) l16[i] = lv[i + 1];
+        l16[15] = 0;
+        const CavlcInfo ci = cavlc_block_info(l16, 16, false);
+        w.c_sc[c][b] = ci.single_ctr; w.c_tc[c][b] = ci.total_coeff;
+    }
+}
+HLB_HD void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane != 0) return;
+    int single[2] = {0, 0}, totc[2] = {0, 0};
+    w.cbp_ac[0] = w.cbp_ac[1] = w.cbp_dc[0] = w.cbp_dc[1] = 0;
+    for (int b = 0; b < 4; ++b)
+        for (int c = 0; c < 2; ++c) {
+            if (w.c_resnz[c][b]) {
+                if (w.c_acnz[c][b]) w.cbp_ac[c] |= 1 << b;
+                if (w.c_dccoef[c][b]) w.cbp_dc[c] |= 1 << b;
+            }
+            if (single[c] < 7 && ((w.cbp_ac[c] >> b) & 1)) {
+                single[c] += w.c_sc[c][b]; totc[c] += w.c_tc[c][b];
+                w.tc_cac[c][b] = w.c_tc[c][b];
+                w.last_sctr = w.c_sc[c][b];
+            }
+        }
+    for (int c = 0; c < 2; ++c)
+        if (single[c] < 7 && totc[c] == 1) w.cbp_ac[c] = 0;
+    if (w.cbp_dc[0] || w.cbp_dc[1]) {
+        for (int c = 0; c < 2; ++c)
+            if (w.cbp_dc[c]) {
+                int h[4] = {w.c_dccoef[c][0], w.c_dccoef[c][1], w.c_dccoef[c][2], w.c_dccoef[c][3]};
+                hadamard2x2(h);
+                quant_dc(h, 4, f.qpc, w.mb_is_intra != 0);
+                int mask = 0;
+                for (int k = 0; k < 4; ++k) { w.chroma_dc[c][k] = (int16_t)h[k]; mask |= (h[k] != 0) << k; }
+                w.cbp_dc[c] = mask;
+            }
+    }
+    // de-quantised DC per block (transf.c:612), parked in c_dccoef for the reconstruction lanes
+    for (int c = 0; c < 2; ++c) {
+        int d[4] = {0, 0, 0, 0};
+        if (w.cbp_dc[c]) {
+            d[0] = w.chroma_dc[c][0]; d[1] = w.chroma_dc[c][1]; d[2] = w.chroma_dc[c][2]; d[3] = w.chroma_dc[c][3];
+            hadamard2x2(d);
+            const int ls = 16 * kNormAdjust[f.qpc % 6][0];
+            for (int k = 0; k < 4; ++k) d[k] = ((d[k] * ls) << (f.qpc / 6)) >> 5;
+        }
+        for (int k = 0; k < 4; ++k) w.c_dccoef[c][k] = d[k];
+    }
+}
+HLB_HD void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane >= 8) return;
+    const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+    const int dc = w.c_dccoef[c][b];
+    const bool use = (w.cbp_dc[c] || w.cbp_ac[c]) && (dc != 0 || ((w.cbp_ac[c] >> b) & 1));
+    int r4[16];
+    if (use) {
+        int l16[16], cc[16];
+        l16[0] = dc;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) l16[i] = w.chroma_ac[c][b][i - 1];
+        inv_zigzag4x4(l16, cc);
+        dequant4x4(cc, f.qpc, true);
+        inv_transform4x4(cc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r4[i] = cc[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r4[i] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w.rec_c[c][(y0 + r) * 8 + x0 + q] = (uint8_t)clip255((int)w.pred_c[c][(y0 + r) * 8 + x0 + q] + r4[r * 4 + q]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// load / store of the macroblock's samples: lanes 0..23 (16 luma 4x4 blocks raster + 8 chroma blocks)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void phase_load(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane < 16) {
+        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
+        const uint8_t* p = f.src[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) w.src_y[(by + r) * 16 + bx + q] = p[r * f.W + q];
+    } else if (lane < 24) {
+        const int c = (lane - 16) >> 2, b = (lane - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4, Wc = f.W >> 1;
+        const uint8_t* p = f.src[1 + c] + (w.mby * 8 + y0) * Wc + w.mbx * 8 + x0;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) w.src_c[c][(y0 + r) * 8 + x0 + q] = p[r * Wc + q];
+    }
+}
+// arg0 bit 0: luma, bit 1: chroma
+HLB_HD void phase_store(MbWork& w, const FrameCtx& f, int lane)
+{
+    if (lane < 16 && (w.arg0 & 1)) {
+        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
+        uint8_t* p = f.cur[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) p[r * f.W + q] = w.rec_y[(by + r) * 16 + bx + q];
+    } else if (lane >= 16 && lane < 24 && (w.arg0 & 2)) {
+        const int c = (lane - 16) >> 2, b = (lane - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4, Wc = f.W >> 1;
+        uint8_t* p = f.cur[1 + c] + (w.mby * 8 + y0) * Wc + w.mbx * 8 + x0;
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) p[r * Wc + q] = w.rec_c[c][(y0 + r) * 8 + x0 + q];
+    }
+}
+
+}  // namespace hlb
+
+#include "hlb_mbintra.cuh"
+
+namespace hlb {
+
+// number of phases and the phase dispatcher (the only place that knows which function a command runs)
+HLB_HD int cmd_phases(int cmd)
+{
+    switch (cmd) {
+    case CMD_ME_EVAL: return 4;
+    case CMD_CHROMA: return 3;
+    case CMD_I16_EVAL: return 2;
+    case CMD_I16_RATE: return 2;
+    case CMD_I4_EVAL: return 2;
+    default: return 1;
+    }
+}
+HLB_HD void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane)
+{
+    switch (cmd) {
+    case CMD_LOAD: phase_load(w, f, lane); break;
+    case CMD_ME_EVAL:
+        if (phase == 0) me_phase_trial(w, f, lane);
+        else if (phase == 1) me_phase_scan(w, lane);
+        else if (phase == 2) me_phase_token(w, lane);
+        else me_phase_sum(w, lane);
+        break;
+    case CMD_PRED_INTER: phase_pred_inter(w, f, lane); break;
+    case CMD_RECON_LUMA: phase_recon_luma(w, f, lane); break;
+    case CMD_CHROMA:
+        if (phase == 0) phase_chroma_tq(w, f, lane);
+        else if (phase == 1) phase_chroma_serial(w, f, lane);
+        else phase_chroma_recon(w, f, lane);
+        break;
+    case CMD_STORE: phase_store(w, f, lane); break;
+    case CMD_I16_EVAL: i16_phase(w, f, phase, lane); break;
+    case CMD_I16_RATE: i16_phase(w, f, phase + 2, lane); break;
+    case CMD_I16_RECON: i16_recon_phase(w, f, lane); break;
+    case CMD_I4_EVAL: i4_phase(w, f, phase, lane); break;
+    case CMD_I4_COMMIT: i4_commit_phase(w, f, lane); break;
+    case CMD_PRED_CHROMA_INTRA: intra_chroma_pred_phase(w, f, lane); break;
+    default: break;
+    }
+}
+// lanes a command needs at most (the GPU CTA must have at least this many threads)
+#define HLB_MB_LANES 160
+
+// ------------------------------------------------------------------------------------------------------------------
+// The macroblock: rdo.c:678-1270 (P) / rdo.c:99 (I)
+// ------------------------------------------------------------------------------------------------------------------
+template <class X>
+HLB_HD void chroma_code(X& x, MbWork& w) { x.run(CMD_CHROMA, 8); }
+
+HLB_HD void mb_begin(MbWork& w, const FrameCtx& f, int mb)
+{
+    w.mb = mb; w.mbx = mb % f.mbw; w.mby = mb / f.mbw;
+    w.availA = w.mbx > 0; w.availB = w.mby > 0; w.availC = w.mby > 0 && w.mbx < f.mbw - 1; w.availD = w.mbx > 0 && w.mby > 0;
+    const MbState& s = f.st[mb];
+    for (int i = 0; i < 16; ++i) w.tc[i] = s.tc_luma[i];
+    for (int c = 0; c < 2; ++c)
+        for (int b = 0; b < 4; ++b) {
+            w.tc_cac[c][b] = s.tc_cac[c][b];
+            w.chroma_dc[c][b] = s.chroma_dc[c][b];
+            for (int i = 0; i < 16; ++i) w.chroma_ac[c][b][i] = s.chroma_ac[c][b][i];
+        }
+    w.cbp_gate = s.cbp_luma;
+    for (int i = 0; i < 4; ++i) w.ref_cur[i] = s.ref_idx[i];
+    for (int p = 0; p < 4; ++p)
+        for (int q = 0; q < 4; ++q) { w.mv_cur[p][q][0] = s.mv[p][q][0]; w.mv_cur[p][q][1] = s.mv[p][q][1]; }
+    for (int i = 0; i < 16; ++i) w.i4_mode[i] = s.i4_mode[i];
+    for (int blk = 0; blk < 16; ++blk) {
+        const int bx = blk_x(blk), by = blk_y(blk);
+        w.extA[blk] = (int8_t)((bx == 0) ? (w.availA ? nb_count(f.st[mb - 1], blk_idx_from_xy(12, by)) : -1) : 0);
+        w.extB[blk] = (int8_t)((by == 0) ? (w.availB ? nb_count(f.st[mb - f.mbw], blk_idx_from_xy(bx, 12)) : -1) : 0);
+    }
+    w.last_sctr = -1; w.need_prev_sctr = 0;
+    w.mb_is_intra = 0;
+}
+
+// state the writer leaves behind (residual.c:903-1094) + publication of the macroblock's final state and record
+HLB_HD int nnz16(const int16_t* lv, int n) { int k = 0; for (int i = 0; i < n; ++i) k += (lv[i] != 0); return k; }
+
+HLB_HD void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad)
+{
+    MbState& s = f.st[w.mb];
+    hlb200_mb_record_t& r = f.rec[w.mb];
+    // ---- record (what the host writer consumes) ----
+    r.mb_class = (uint8_t)kind; r.mb_type = (uint8_t)mb_type;
+    r.part_mode = (uint8_t)w.fin_mode;
+    for (int i = 0; i < 4; ++i) { r.sub_mode[i] = (uint8_t)w.fin_sub[i]; r.ref_idx[i] = w.fin_ref[i]; }
+    r.i16_pred_mode = (uint8_t)w.i16_mode; r.intra_chroma_pred_mode = (uint8_t)w.intra_chroma_mode;
+    r.coded_block_pattern = (uint8_t)coded_block_pattern; r.cbp_luma = (uint8_t)cbp_luma; r.cbp_chroma = (uint8_t)cbp_chroma;
+    for (int c = 0; c < 2; ++c) { r.cbp_chroma_dc4x4[c] = (uint8_t)w.cbp_dc[c]; r.cbp_chroma_ac4x4[c] = (uint8_t)w.cbp_ac[c]; }
+    r.cbp_luma4x4 = (uint16_t)w.cbp_luma4x4;
+    r.mb_qp_delta = 0; r.qp_y = (uint8_t)f.qp; r.qp_c[0] = r.qp_c[1] = (uint8_t)f.qpc;
+    for (int i = 0; i < 16; ++i) { r.i4_pred_mode[i] = w.i4_mode[i]; r.prev_intra4x4_pred_mode_flag[i] = w.prev_i4[i]; r.rem_intra4x4_pred_mode[i] = w.rem_i4[i]; }
+    for (int p = 0; p < 4; ++p)
+        for (int q = 0; q < 4; ++q)
+            for (int k = 0; k < 2; ++k) { r.mv[p][q][k] = w.fin_mv[p][q][k]; r.mvd[p][q][k] = mvd ? mvd[p][q][k] : 0; }
+    r.mad = mad;
+    for (int b = 0; b < 16; ++b)
+        for (int i = 0; i < 16; ++i) { r.luma_level[b][i] = w.luma_level[b][i]; r.i16_ac_level[b][i] = w.i16_ac[b][i]; }
+    for (int i = 0; i < 16; ++i) r.i16_dc_level[i] = w.i16_dc[i];
+    for (int c = 0; c < 2; ++c)
+        for (int b = 0; b < 4; ++b) {
+            r.chroma_dc_level[c][b] = w.chroma_dc[c][b];
+            for (int i = 0; i < 16; ++i) r.chroma_ac_level[c][b][i] = w.chroma_ac[c][b][i];
+        }
+    // ---- TotalCoeffs as the writer finalises them ----
+    if (kind != MBK_PSKIP) {
+        if (kind == MBK_I16) w.tc[0] = (uint8_t)nnz16(w.i16_dc, 16);
+        for (int b8 = 0; b8 < 4; ++b8)
+            if ((cbp_luma >> b8) & 1)
+                for (int k = 0; k < 4; ++k) {
+                    const int b = b8 * 4 + k;
+                    w.tc[b] = (uint8_t)(kind == MBK_I16 ? nnz16(w.i16_ac[b], 15) : nnz16(w.luma_level[b], 16));
+                }
+        if (cbp_chroma & 2)
+            for (int c = 0; c < 2; ++c)
+                for (int b = 0; b < 4; ++b) w.tc_cac[c][b] = (uint8_t)(((w.cbp_ac[c] >> b) & 1) ? nnz16(w.chroma_ac[c][b], 15) : 0);
+    }
+    // ---- persistent state ----
+    s.kind = (uint8_t)kind;
+    s.part_mode = (uint8_t)w.fin_mode;
+    for (int i = 0; i < 4; ++i) { s.sub_mode[i] = (uint8_t)w.fin_sub[i]; s.ref_idx[i] = w.ref_cur[i]; }
+    s.cbp_luma = (uint8_t)cbp_luma; s.cbp_chroma = (uint8_t)cbp_chroma;
+    for (int i = 0; i < 16; ++i) { s.tc_luma[i] = w.tc[i]; s.i4_mode[i] = w.i4_mode[i]; }
+    for (int c = 0; c < 2; ++c)
+        for (int b = 0; b < 4; ++b) {
+            s.tc_cac[c][b] = w.tc_cac[c][b];
+            s.chroma_dc[c][b] = w.chroma_dc[c][b];
+            for (int i = 0; i < 16; ++i) s.chroma_ac[c][b][i] = w.chroma_ac[c][b][i];
+        }
+    for (int p = 0; p < 4; ++p)
+        for (int q = 0; q < 4; ++q) { s.mv[p][q][0] = w.mv_cur[p][q][0]; s.mv[p][q][1] = w.mv_cur[p][q][1]; }
+    s.last_sctr = (uint8_t)(w.last_sctr < 0 ? 255 : w.last_sctr);
+}
+
+HLB_HD int guess_cbp_luma(int cbp4x4, bool i16)
+{
+    if (i16) return cbp4x4 ? 15 : 0;
+    int c = 0;
+    for (int b8 = 0; b8 < 4; ++b8)
+        if ((cbp4x4 >> (b8 * 4)) & 15) c |= 1 << b8;
+    return c;
+}
+HLB_HD int guess_cbp_chroma(const MbWork& w)
+{
+    if ((w.cbp_dc[0] || w.cbp_dc[1]) && !w.cbp_ac[0] && !w.cbp_ac[1]) return 1;
+    if (w.cbp_ac[0] || w.cbp_ac[1]) return 2;
+    return 0;
+}
+
+template <class X>
+HLB_HD void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
+{
+    double best_cost = DBL_MAX;
+    int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0;
+    int16_t best_mv[4][4][2], best_mvp[4][4][2];
+    for (int u = 0; u < f.num_refs; ++u) {
+        if (!f.ref[u][0]) continue;
+        w.ref = u; w.ref_y = f.ref[u][0];
+        for (int g = 0; g < 4 && !found; ++g) {
+            const int m0 = g < 3 ? g : 3, m1 = g < 3 ? g : 6;
+            for (int mode = m0; mode <= m1; ++mode) {
+                me_find_best_cost(x, w, f, mode);
+                double cost_sum = 0;
+                int dist_sum = 0, sctr_sum = 0;
+                probably_pskip = w.probably_pskip;
+                const int np = mode_nparts(mode), ns = mode_nsub(mode);
+                for (int p = 0; p < np; ++p)
+                    for (int s = 0; s < ns; ++s) { cost_sum += w.best_cost[p][s]; dist_sum += w.best_dist[p][s]; sctr_sum += w.best_sctr[p][s]; }
+                if (!probably_pskip && cost_sum != 0 && sctr_sum < 6 && mode == 0) {  // rdo.c:1040-1054
+                    int sx, sy;
+                    derive_pskip_mv(w, f, sx, sy);
+                    probably_pskip = (sx == w.mvp[0][0][0] && sy == w.mvp[0][0][1]) && (w.mv_cur[0][0][0] == w.mvp[0][0][0] && w.mv_cur[0][0][1] == w.mvp[0][0][1]);
+                }
+                cost_sum += f.lambda * kHeaderBits[mode];
+                HLB_DBG("  mode %d ref %d: cost_sum %.4f dist %d sctr %d pskip %d | p0: mv (%d,%d) mvp (%d,%d) cost %.4f\n", mode, u, cost_sum, dist_sum, sctr_sum, probably_pskip,
+                        w.mv_cur[0][0][0], w.mv_cur[0][0][1], w.mvp[0][0][0], w.mvp[0][0][1], w.best_cost[0][0]);
+                if (cost_sum < best_cost) {
+                    best_cost = cost_sum; best_dist = dist_sum; best_sctr = sctr_sum; best_mode = mode; best_ref = u;
+                    for (int p = 0; p < np; ++p)
+                        for (int s = 0; s < ns; ++s)
+                            for (int k = 0; k < 2; ++k) { best_mv[p][s][k] = w.mv_cur[p][s][k]; best_mvp[p][s][k] = w.mvp[p][s][k]; }
+                }
+            }
+            b_pskip = probably_pskip;
+            if (b_pskip) {  // chroma must quantise to nothing (rdo.c:1125-1139, :2140)
+                w.fin_mode = 0; w.fin_sub[0] = w.fin_sub[1] = w.fin_sub[2] = w.fin_sub[3] = 0;
+                w.fin_ref[0] = 0; w.fin_mv[0][0][0] = best_mv[0][0][0]; w.fin_mv[0][0][1] = best_mv[0][0][1];
+                w.mb_is_intra = 0;
+                x.run(CMD_PRED_INTER, 24);
+                chroma_code(x, w);
+                b_pskip = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1];
+            }
+            found |= (best_cost == 0) || b_pskip;
+        }
+    }
+    if (!b_pskip) {
+        double intra_cost;
+        const int intra_kind = mb_encode_intra(x, w, f, intra_cost);  // reconstructs into the picture and commits when it wins (rdo.c:1161-1167)
+        HLB_DBG("  intra cost %.4f (kind %d) vs inter %.4f (mode %d)\n", intra_cost, intra_kind, best_cost, best_mode);
+        if (intra_cost <= best_cost) { mb_commit_intra(w, f, intra_kind); return; }
+    }
+    // ---- commit the best inter layout (rdo.c:1170-1218) ----
+    w.mb_is_intra = 0;
+    w.fin_mode = best_mode < 3 ? best_mode : 3;
+    const int fs = best_mode <= 3 ? 0 : best_mode - 3;
+    int16_t mvd[4][4][2];
+    for (int p = 0; p < 4; ++p) {
+        w.fin_sub[p] = fs; w.ref_cur[p] = 0; w.fin_ref[p] = 0;
+        for (int s = 0; s < 4; ++s) mvd[p][s][0] = mvd[p][s][1] = 0;
+    }
+    const int np = mode_nparts(best_mode), ns = mode_nsub(best_mode);
+    for (int p = 0; p < np; ++p) {
+        w.ref_cur[p] = (int8_t)best_ref; w.fin_ref[p] = (int8_t)best_ref;
+        for (int s = 0; s < ns; ++s)
+            for (int k = 0; k < 2; ++k) {
+                w.fin_mv[p][s][k] = best_mv[p][s][k]; w.mv_cur[p][s][k] = best_mv[p][s][k];
+                mvd[p][s][k] = (int16_t)(best_mv[p][s][k] - best_mvp[p][s][k]);
+            }
+    }
+    int kind, cbp_luma = 0, cbp_chroma = 0, cbp = 0, mb_type;
+    if (b_pskip) {
+        // luma = prediction; chroma already reconstructed by the zero check
+        w.luma_skip_residual = 1;
+        x.run(CMD_RECON_LUMA, 16);
+        w.arg0 = 3; x.run(CMD_STORE, 24);
+        w.cbp_luma4x4 = 0;
+        kind = MBK_PSKIP; mb_type = 5;
+    } else {
+        x.run(CMD_PRED_INTER, 24);
+        w.luma_skip_residual = best_sctr < 6;
+        x.run(CMD_RECON_LUMA, 16);
+        w.cbp_luma4x4 = 0;
+        if (!w.luma_skip_residual)
+            for (int b = 0; b < 16; ++b) w.cbp_luma4x4 |= w.r_nz[0][b] << b;
+        chroma_code(x, w);
+        w.arg0 = 3; x.run(CMD_STORE, 24);
+        cbp_luma = guess_cbp_luma(w.cbp_luma4x4, false);
+        cbp_chroma = guess_cbp_chroma(w);
+        cbp = (cbp_chroma << 4) | cbp_luma;
+        if (cbp > 47) { cbp -= 16; cbp_chroma = cbp >> 4; }
+        kind = MBK_INTER;
+        mb_type = best_mode < 3 ? best_mode : 4;  // P_8x8ref0
+        // late PSkip (rdo.c:1252-1262): the layout is 16x16 here, so the 16x16 derivation applies
+        if (cbp == 0 && best_mode == 0 && mvd[0][0][0] == 0 && mvd[0][0][1] == 0) {
+            int sx, sy;
+            w.mode = 0;
+            derive_pskip_mv(w, f, sx, sy);
+            if (sx == best_mvp[0][0][0] && sy == best_mvp[0][0][1]) { kind = MBK_PSKIP; mb_type = 5; }
+        }
+    }
+    mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, mvd, best_dist);
+}
+
+template <class X>
+HLB_HD void mb_encode(X& x, MbWork& w, const FrameCtx& f, int mb)
+{
+    mb_begin(w, f, mb);
+    x.run(CMD_LOAD, 24);
+    if (f.is_p) mb_encode_p(x, w, f);
+    else {
+        double c;
+        const int kind = mb_encode_intra(x, w, f, c);
+        mb_commit_intra(w, f, kind);
+    }
+}
+
+}  // namespace hlb

@@ -1,0 +1,367 @@
+// hlb_mbintra.cuh -- intra mode decision of one macroblock (I pictures, and inside P pictures after the inter search):
+//   hl_codec_264_rdo_mb_guess_best_intra_pred_avc            source/h264/hl_codec_264_rdo.c:99-300
+//   _hl_codec_264_rdo_mb_guess_best_intra16x16_pred          rdo.c:1526-1812
+//   _hl_codec_264_rdo_mb_guess_best_intra4x4_pred            rdo.c:1814-2090
+//   _hl_codec_264_rdo_mb_reconstruct_intra16x16_luma         rdo.c:2092-2137, source/h264/hl_codec_264_transf.c:298-373
+//   neighbouring samples                                     source/h264/hl_codec_264_pred_intra.c:325-461
+//   prev_intra4x4_pred_mode / rem_intra4x4_pred_mode         pred_intra.c:541-614
+// Included by hlb_mbcore.cuh (uses MbWork / FrameCtx and the lane-phase execution model described there).
+#pragma once
+
+namespace hlb {
+
+// reconstructed luma sample at (x,y) relative to the macroblock (may lie in a neighbouring macroblock), HLB_NA when unavailable
+// (6.4.11.1; constrained_intra_pred_flag = 0, so every already-coded neighbour counts)
+HLB_HD int intra_luma_at(const MbWork& w, const FrameCtx& f, int x, int y)
+{
+    if (x >= 0 && x <= 15 && y >= 0 && y <= 15) return w.rec_y[y * 16 + x];
+    bool ok;
+    if (y < 0 && x >= 0 && x <= 15) ok = w.availB;
+    else if (y < 0 && x > 15) ok = w.availC;
+    else if (y < 0 && x < 0) ok = w.availD;
+    else if (x < 0 && y >= 0 && y <= 15) ok = w.availA;
+    else ok = false;
+    if (!ok) return HLB_NA;
+    return f.cur[0][(w.mby * 16 + y) * f.W + w.mbx * 16 + x];
+}
+HLB_HD int intra_chroma_at(const MbWork& w, const FrameCtx& f, int c, int x, int y)
+{
+    bool ok;
+    if (y < 0 && x >= 0) ok = w.availB;
+    else if (y < 0 && x < 0) ok = w.availD;
+    else ok = w.availA;
+    if (!ok) return HLB_NA;
+    return f.cur[1 + c][(w.mby * 8 + y) * (f.W >> 1) + w.mbx * 8 + x];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CMD_I16_EVAL: 64 lanes = (mode, luma4x4BlkIdx)
+// ------------------------------------------------------------------------------------------------------------------
+struct I16Shared { I16Params q; };
+
+HLB_HD void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
+{
+    if (phase == 0) {
+        if (lane >= 64) return;
+        const int m = lane >> 4, blk = lane & 15;
+        if (!w.t_mode_ok[m]) return;
+        const int bx = blk_x(blk), by = blk_y(blk);
+        I16Params q;
+        q.dc = w.t_dcbits[0]; q.a = w.t_dcbits[1]; q.b = w.t_dcbits[2]; q.c = w.t_dcbits[3];  // parameters parked by the master
+        int res[16], lv[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int pv = i16_pred_px(m, w.p33, q, bx + c, by + r);
+                w.t_pred[m][(by + r) * 16 + bx + c] = (uint8_t)pv;
+                res[r * 4 + c] = (int)w.src_y[(by + r) * 16 + bx + c] - pv;
+            }
+        fwd_transform4x4(res);
+        w.t_dcw[m][blk] = res[0];
+        quant4x4_ac(res, f.qp, true);
+        zigzag4x4(res, lv);
+        bool nz = false;
+        int l16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nz |= (lv[i] != 0);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) { l16[i] = lv[i + 1]; w.t_ac[m][blk][i] = (int16_t)lv[i + 1]; }
+        l16[15] = 0; w.t_ac[m][blk][15] = 0;
+        const CavlcInfo ci = cavlc_block_info(l16, 16, false);
+        w.t_nz[m][blk] = nz ? 1 : 0; w.t_tc[m][blk] = ci.total_coeff; w.t_t1[m][blk] = ci.trailing_ones; w.t_sc[m][blk] = ci.single_ctr; w.t_bits[m][blk] = ci.bits_rest;
+    } else if (phase == 1) {  // luma DC of each mode: Hadamard (>>1), quantisation, scan (rdo.c:1667-1670)
+        if (lane >= 4 || !w.t_mode_ok[lane]) return;
+        const int m = lane;
+        int d[16], lv[16];
+        for (int blk = 0; blk < 16; ++blk) d[(blk_y(blk) >> 2) * 4 + (blk_x(blk) >> 2)] = w.t_dcw[m][blk];
+        hadamard4x4(d);
+        for (int i = 0; i < 16; ++i) d[i] >>= 1;
+        quant_dc(d, 16, f.qp, true);
+        zigzag4x4(d, lv);
+        for (int i = 0; i < 16; ++i) w.t_dc[m][i] = (int16_t)lv[i];
+    } else if (phase == 2) {  // serial: rate with the evolving nC state, single-coefficient elimination, DC token (rdo.c:1617-1679)
+        if (lane != 0) return;
+        for (int m = 0; m < 4; ++m) {
+            if (!w.t_mode_ok[m]) continue;
+            int sctr = 0, cbp = 0, bits = 0;
+            for (int blk = 0; blk < 16; ++blk) {
+                if (!w.t_nz[m][blk]) continue;
+                const int nC = luma_nc(w, w.tc, blk);
+                bits += w.t_bits[m][blk] + coeff_token_len(nC, w.t_tc[m][blk], w.t_t1[m][blk]);
+                w.tc[blk] = w.t_tc[m][blk];
+                cbp |= 1 << blk;
+                if (w.t_tc[m][blk] > 0) w.last_sctr = w.t_sc[m][blk];
+                else if (w.last_sctr < 0) { w.need_prev_sctr = 1; w.last_sctr = w.arg1; }  // chain value of the raster predecessor (residual.c:882 is skipped when TotalCoeffs == 0)
+                sctr += w.last_sctr;
+            }
+            if (cbp && sctr < 6) cbp = 0;
+            if (cbp) {
+                int l16[16];
+                for (int i = 0; i < 16; ++i) l16[i] = w.t_dc[m][i];
+                const CavlcInfo ci = cavlc_block_info(l16, 16, false);
+                const int nC = luma_nc(w, w.tc, 0);
+                bits += ci.bits_rest + coeff_token_len(nC, ci.total_coeff, ci.trailing_ones);
+                w.tc[0] = ci.total_coeff;
+                if (ci.total_coeff > 0) w.last_sctr = ci.single_ctr;
+            }
+            w.t_cbp[m] = cbp; w.t_rate[m] = bits;
+        }
+    } else {  // reconstruction + distortion per block (rdo.c:1683-1760)
+        if (lane >= 64) return;
+        const int m = lane >> 4, blk = lane & 15;
+        if (!w.t_mode_ok[m]) return;
+        const int bx = blk_x(blk), by = blk_y(blk);
+        int r4[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r4[i] = 0;
+        if (w.t_cbp[m]) {
+            // 8.5.10 (transf.c:498): every lane recomputes the 16 de-scaled DC values of its mode (cheap, avoids a phase)
+            int c[16], l16[16];
+            for (int i = 0; i < 16; ++i) l16[i] = w.t_dc[m][i];
+            inv_zigzag4x4(l16, c);
+            hadamard4x4(c);
+            const int ls = 16 * kNormAdjust[f.qp % 6][0], q6 = f.qp / 6;
+            const int k = (by >> 2) * 4 + (bx >> 2);
+            const int dcv = f.qp >= 36 ? ((c[k] * ls) << (q6 - 6)) : ((c[k] * ls + (1 << (5 - q6))) >> (6 - q6));
+            bool any = dcv != 0;
+            l16[0] = dcv;
+#pragma unroll
+            for (int i = 1; i < 16; ++i) { l16[i] = w.t_ac[m][blk][i - 1]; any |= (l16[i] != 0); }
+            if (any) {
+                inv_zigzag4x4(l16, r4);
+                dequant4x4(r4, f.qp, true);
+                inv_transform4x4(r4);
+            }
+        }
+        int dist = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int u = clip255((int)w.t_pred[m][(by + r) * 16 + bx + c] + r4[r * 4 + c]);
+                w.t_pred[m][(by + r) * 16 + bx + c] = (uint8_t)u;   // becomes the reconstruction of mode m
+                dist += iabs((int)w.src_y[(by + r) * 16 + bx + c] - u);
+            }
+        w.t_dist[m][blk] = dist;
+    }
+}
+HLB_HD void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
+{
+    (void)f;
+    if (lane >= 16) return;  // copy the reconstruction of the chosen Intra16x16 mode (identical to transf.c:298 on the same levels)
+    for (int i = 0; i < 16; ++i) w.rec_y[lane * 16 + i] = w.t_pred[w.i16_mode][lane * 16 + i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CMD_I4_EVAL for block w.i4_blk: 9 lanes = Intra4x4 modes (rdo.c:1903-2010)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void i4_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
+{
+    if (phase != 0 || lane >= 9) return;
+    const int mode = lane, blk = w.i4_blk, bx = blk_x(blk), by = blk_y(blk);
+    w.q_ok[mode] = i4_mode_allowed(mode, w.p13) ? 1 : 0;
+    if (!w.q_ok[mode]) return;
+    int pred[16], res[16], lv[16];
+    intra4x4_pred(mode, w.p13, pred);
+    bool rnz = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { res[r * 4 + c] = (int)w.src_y[(by + r) * 16 + bx + c] - pred[r * 4 + c]; rnz |= (res[r * 4 + c] != 0); }
+    w.q_res0[mode] = rnz ? 0 : 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { w.q_pred[mode][i] = (uint8_t)pred[i]; w.q_lv[mode][i] = 0; }
+    w.q_nz[mode] = 0; w.q_bits[mode] = 0; w.q_tc[mode] = 0; w.q_t1[mode] = 0; w.q_sc[mode] = 9; w.q_dist[mode] = 0;
+    if (!rnz) return;
+    fwd_transform4x4(res);
+    quant4x4_ac(res, f.qp, true);
+    zigzag4x4(res, lv);
+    bool nz = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { nz |= (lv[i] != 0); w.q_lv[mode][i] = (int16_t)lv[i]; }
+    int r4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r4[i] = 0;
+    if (nz) {
+        const CavlcInfo ci = cavlc_block_info(lv, 16, false);
+        w.q_nz[mode] = 1; w.q_bits[mode] = ci.bits_rest; w.q_tc[mode] = ci.total_coeff; w.q_t1[mode] = ci.trailing_ones; w.q_sc[mode] = ci.single_ctr;
+        inv_zigzag4x4(lv, r4);
+        dequant4x4(r4, f.qp, false);
+        inv_transform4x4(r4);
+    }
+    int dist = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int u = clip255(pred[r * 4 + c] + r4[r * 4 + c]);
+            w.q_pred[mode][r * 4 + c] = (uint8_t)u;   // reconstruction of this mode (prediction when nothing is coded)
+            dist += iabs((int)w.src_y[(by + r) * 16 + bx + c] - u);
+        }
+    w.q_dist[mode] = dist;
+}
+HLB_HD void i4_commit_phase(MbWork& w, const FrameCtx& f, int lane) { (void)w; (void)f; (void)lane; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// CMD_PRED_CHROMA_INTRA: 8 lanes = (plane, 4x4 block); p17 and the mode are set by the master (pred_intra.c:1044-1230)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD void intra_chroma_pred_phase(MbWork& w, const FrameCtx& f, int lane)
+{
+    (void)f;
+    if (lane >= 8) return;
+    const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+    const ICParams q = ic_params(w.p17[c]);
+    for (int r = 0; r < 4; ++r)
+        for (int k = 0; k < 4; ++k) w.pred_c[c][(y0 + r) * 8 + x0 + k] = (uint8_t)ic_pred_px(w.intra_chroma_mode, w.p17[c], q, x0 + k, y0 + r);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// master: rdo.c:99-300.  Returns MBK_I16 / MBK_I4 and the best intra cost; leaves the reconstruction in w.rec_y / w.rec_c and
+// in the picture, levels / modes / CBP flags in w.
+// ------------------------------------------------------------------------------------------------------------------
+template <class X>
+HLB_HD int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cost)
+{
+    // ---- Intra16x16 (no reconstruction into the picture yet) ----
+    w.p33[0] = intra_luma_at(w, f, -1, -1);
+    for (int i = 0; i < 16; ++i) { w.p33[1 + i] = intra_luma_at(w, f, -1, i); w.p33[17 + i] = intra_luma_at(w, f, i, -1); }
+    for (int m = 0; m < 4; ++m) w.t_mode_ok[m] = i16_mode_allowed(m, w.p33) ? 1 : 0;
+    {
+        const I16Params q = i16_params(w.p33);
+        w.t_dcbits[0] = q.dc; w.t_dcbits[1] = q.a; w.t_dcbits[2] = q.b; w.t_dcbits[3] = q.c;
+    }
+    x.run(CMD_I16_EVAL, 64);
+    // The Single_ctr of a block whose AC levels are all zero is whatever the previous residual_block call left behind
+    // (residual.c:882 only runs when TotalCoeffs > 0).  Fetch the chain value of the raster predecessor only when this
+    // macroblock has not produced one itself and the first flagged block would consume it.
+    w.arg1 = 0;
+    if (w.last_sctr < 0) {
+        bool need = false, done = false;
+        for (int m = 0; m < 4 && !done; ++m) {
+            if (!w.t_mode_ok[m]) continue;
+            for (int b = 0; b < 16 && !done; ++b)
+                if (w.t_nz[m][b]) { need = (w.t_tc[m][b] == 0); done = true; }
+        }
+        if (need) w.arg1 = x.prev_sctr(w.mb);
+    }
+    x.run(CMD_I16_RATE, 64);
+    double best16 = DBL_MAX;
+    int dist16 = 0;
+    w.i16_mode = 2; w.i16_cbp4x4 = 0;
+    for (int m = 0; m < 4; ++m) {
+        if (!w.t_mode_ok[m]) continue;
+        double d = 0;
+        for (int b = 0; b < 16; ++b) d += w.t_dist[m][b];
+        const double cost = d + (f.lambda * (double)w.t_rate[m]);
+        HLB_DBG("  I16 mode %d: dist %.0f rate %d cbp %x cost %.4f\n", m, d, w.t_rate[m], w.t_cbp[m], cost);
+        if (cost < best16) { best16 = cost; dist16 = (int)d; w.i16_mode = m; w.i16_cbp4x4 = w.t_cbp[m]; }
+    }
+    for (int b = 0; b < 16; ++b)
+        for (int i = 0; i < 16; ++i) w.i16_ac[b][i] = w.t_ac[w.i16_mode][b][i];
+    for (int i = 0; i < 16; ++i) w.i16_dc[i] = w.i16_cbp4x4 ? w.t_dc[w.i16_mode][i] : 0;
+
+    // ---- Intra4x4 (reconstructs block after block: later blocks predict from it) ----
+    double cost4 = DBL_MAX;
+    int dist4 = INT_MAX, cbp4 = 0;
+    if (best16 != 0) {
+        cost4 = 0; dist4 = 0;
+        for (int blk = 0; blk < 16; ++blk) {
+            const int bx = blk_x(blk), by = blk_y(blk);
+            w.p13[0] = intra_luma_at(w, f, bx - 1, by - 1);
+            for (int i = 0; i < 4; ++i) w.p13[1 + i] = intra_luma_at(w, f, bx - 1, by + i);
+            for (int i = 0; i < 8; ++i) w.p13[5 + i] = (i > 3 && (blk == 3 || blk == 11)) ? HLB_NA : intra_luma_at(w, f, bx + i, by - 1);
+            // in-MB positions to the right of an uncoded area (blocks 5, 7, 13, 15) fall outside the macroblock => HLB_NA from intra_luma_at
+            if ((blk == 5) && 0) {}
+            if (w.p13[9] == HLB_NA && w.p13[10] == HLB_NA && w.p13[11] == HLB_NA && w.p13[12] == HLB_NA && w.p13[8] != HLB_NA) w.p13[9] = w.p13[10] = w.p13[11] = w.p13[12] = w.p13[8];
+            w.i4_blk = blk;
+            w.i4_mode[blk] = 2;
+            x.run(CMD_I4_EVAL, 9);
+            double min_cost = DBL_MAX, min_dist = 0;
+            int best_mode = 2, best_allzero = 1;
+            const int nC = luma_nc(w, w.tc, blk);
+            for (int mode = 0; mode < 9; ++mode) {
+                if (!w.q_ok[mode]) continue;
+                if (w.q_res0[mode]) { min_cost = 0; min_dist = 0; best_mode = mode; best_allzero = 1; break; }
+                int bits = 0;
+                if (w.q_nz[mode]) {
+                    bits = w.q_bits[mode] + coeff_token_len(nC, w.q_tc[mode], w.q_t1[mode]);
+                    w.tc[blk] = w.q_tc[mode];
+                    w.last_sctr = w.q_sc[mode];
+                }
+                const double cost = (double)w.q_dist[mode] + (f.lambda * (double)bits);
+                if (cost < min_cost) { min_cost = cost; min_dist = w.q_dist[mode]; best_mode = mode; best_allzero = !w.q_nz[mode]; }
+            }
+            HLB_DBG("  I4 blk %d: mode %d cost %.4f dist %.0f nC %d\n", blk, best_mode, min_cost, min_dist, nC);
+            w.i4_mode[blk] = (uint8_t)best_mode;
+            for (int i = 0; i < 16; ++i) w.luma_level[blk][i] = w.q_lv[best_mode][i];
+            cost4 += min_cost; dist4 = (int)(dist4 + min_dist);
+            if (!best_allzero) cbp4 |= 1 << blk;
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) w.rec_y[(by + r) * 16 + bx + c] = w.q_pred[best_mode][r * 4 + c];
+        }
+    }
+    w.i4_cbp4x4 = cbp4;
+    // chroma prediction mode follows the Intra16x16 mode (rdo.c:165-179)
+    w.intra_chroma_mode = w.i16_mode == 0 ? 2 : (w.i16_mode == 3 ? 3 : (w.i16_mode == 1 ? 1 : 0));
+    int kind = MBK_I16, mad = dist16;
+    if (cost4 < best16) {
+        kind = MBK_I4;
+        w.cbp_luma4x4 = cbp4;
+        int zeros = 0;
+        for (int blk = 0; blk < 16; ++blk) {  // pred_intra.c:541-614
+            const int bx = blk_x(blk), by = blk_y(blk);
+            int mA = -1, mB = -1;  // -1: neighbour macroblock not available
+            if (bx > 0) mA = w.i4_mode[blk_idx_from_xy(bx - 4, by)];
+            else if (w.availA) { const MbState& s = f.st[w.mb - 1]; mA = s.kind == MBK_I4 ? s.i4_mode[blk_idx_from_xy(12, by)] : 2; }
+            if (by > 0) mB = w.i4_mode[blk_idx_from_xy(bx, by - 4)];
+            else if (w.availB) { const MbState& s = f.st[w.mb - f.mbw]; mB = s.kind == MBK_I4 ? s.i4_mode[blk_idx_from_xy(bx, 12)] : 2; }
+            if (mA < 0 || mB < 0) mA = mB = 2;
+            const int pm = mA < mB ? mA : mB, cur = w.i4_mode[blk];
+            if (pm == cur) { w.prev_i4[blk] = 1; }
+            else { w.prev_i4[blk] = 0; w.rem_i4[blk] = (uint8_t)(cur < pm ? cur : cur - 1); ++zeros; }
+        }
+        cost4 += f.lambda * (double)(16 + zeros * 3);
+        mad = dist4;
+    }
+    HLB_DBG("  intra: best16 %.4f cost4 %.4f\n", best16, cost4);
+    if (best16 <= cost4) { kind = MBK_I16; w.cbp_luma4x4 = w.i16_cbp4x4; mad = dist16; }
+    intra_cost = best16 < cost4 ? best16 : cost4;
+    w.arg0 = mad;  // parked for mb_commit_intra
+    // ---- chroma (rdo.c:216-246) ----
+    w.mb_is_intra = 1;
+    for (int c = 0; c < 2; ++c) {
+        w.p17[c][0] = intra_chroma_at(w, f, c, -1, -1);
+        for (int i = 0; i < 8; ++i) { w.p17[c][1 + i] = intra_chroma_at(w, f, c, -1, i); w.p17[c][9 + i] = intra_chroma_at(w, f, c, i, -1); }
+    }
+    const int mad_keep = w.arg0;
+    x.run(CMD_PRED_CHROMA_INTRA, 8);
+    x.run(CMD_CHROMA, 8);
+    if (kind == MBK_I16) x.run(CMD_I16_RECON, 16);
+    w.arg0 = 3; x.run(CMD_STORE, 24);
+    w.arg0 = mad_keep;
+    return kind;
+}
+
+HLB_HD void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad);
+HLB_HD int guess_cbp_luma(int cbp4x4, bool i16);
+HLB_HD int guess_cbp_chroma(const MbWork& w);
+
+HLB_HD void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind)
+{
+    const int mad = w.arg0;
+    const int cbp_luma = guess_cbp_luma(w.cbp_luma4x4, kind == MBK_I16);
+    int cbp_chroma = guess_cbp_chroma(w);
+    int cbp = (cbp_chroma << 4) | cbp_luma;
+    if (cbp > 47) { cbp -= 16; cbp_chroma = cbp >> 4; }
+    int mb_type = kind == MBK_I4 ? 0 : 1 + (cbp_chroma << 2) + w.i16_mode + (cbp_luma ? 12 : 0);
+    if (f.is_p) mb_type += 5;
+    w.fin_mode = 0; w.fin_sub[0] = w.fin_sub[1] = w.fin_sub[2] = w.fin_sub[3] = 0;
+    for (int p = 0; p < 4; ++p) {
+        w.fin_ref[p] = 0;
+        for (int s = 0; s < 4; ++s) w.fin_mv[p][s][0] = w.fin_mv[p][s][1] = 0;
+    }
+    mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, nullptr, mad);
+}
+
+}  // namespace hlb

@@ -43,7 +43,8 @@
 static FILE* g_trace = NULL;       /* int32 record stream */
 static FILE* g_recon = NULL;       /* raw recon planes, frame after frame */
 static int g_trace_cand = 0;       /* per-candidate records */
-static int g_trace_levels = 1;     /* include level arrays in MB records */
+static int g_trace_levels = 1;
+static int g_trace_state = 0;      /* per-MB post-writer state records (tag 5) */     /* include level arrays in MB records */
 static int g_frame_idx = -1;       /* index of the frame being encoded */
 static int g_width = 0, g_height = 0;
 
@@ -218,6 +219,34 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
         double l = p_codec->encoder.rdo.d_lambda_mode; float lf = (float)l; memcpy(&r[9], &lf, 4);
         put32(r, 10);
     }
+    if (g_trace && g_trace_state) {
+        /* tag 5: per-MB state AFTER the writer (what the next MBs / the next frame see):
+         * [5, n, frame, addr, e_type, flags_type, NumMbPart, MbPartWidth, MbPartHeight, NumSubMbPart[4], SubMbPartWidth[4], SubMbPartHeight[4],
+         *  CodedBlockPatternLuma, CodedBlockPatternChroma, RefIdxL0[4], predFlagL0[4], MvL0[16][2], TotalCoeffsLuma[16], TotalCoeffsChromaACCbCr[2][4],
+         *  Intra4x4PredMode[16], ChromaACLevel[2][4][16], last rdo.Single_ctr] */
+        int a;
+        for (a = p_esd->i_mb_start; a < p_esd->i_mb_end; ++a) {
+            const hl_codec_264_mb_t* m = pc_layer->pp_list_macroblocks[a];
+            int32_t r[512]; int k = 0, i, j, n;
+            if (!m) continue;
+            r[k++] = 5; r[k++] = 0; r[k++] = g_frame_idx; r[k++] = a; r[k++] = (int32_t)m->e_type; r[k++] = (int32_t)m->flags_type;
+            r[k++] = m->NumMbPart; r[k++] = m->MbPartWidth; r[k++] = m->MbPartHeight;
+            for (i = 0; i < 4; ++i) r[k++] = m->NumSubMbPart[i];
+            for (i = 0; i < 4; ++i) r[k++] = m->SubMbPartWidth[i];
+            for (i = 0; i < 4; ++i) r[k++] = m->SubMbPartHeight[i];
+            r[k++] = (int32_t)m->CodedBlockPatternLuma; r[k++] = (int32_t)m->CodedBlockPatternChroma;
+            for (i = 0; i < 4; ++i) r[k++] = m->RefIdxL0[i];
+            for (i = 0; i < 4; ++i) r[k++] = m->predFlagL0[i];
+            for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { r[k++] = m->MvL0[i][j].x; r[k++] = m->MvL0[i][j].y; }
+            for (i = 0; i < 16; ++i) r[k++] = m->TotalCoeffsLuma[i];
+            for (i = 0; i < 2; ++i) for (j = 0; j < 4; ++j) r[k++] = m->TotalCoeffsChromaACCbCr[i][j];
+            for (i = 0; i < 16; ++i) r[k++] = (int32_t)m->Intra4x4PredMode[i];
+            for (i = 0; i < 2; ++i) for (n = 0; n < 4; ++n) for (j = 0; j < 16; ++j) r[k++] = m->ChromaACLevel[i][n][j];
+            r[k++] = p_esd->rdo.Single_ctr;
+            r[1] = k;
+            put32(r, (size_t)k);
+        }
+    }
     if (g_recon) {
         fwrite(pict->pc_data_y, 1, (size_t)pict->uWidthL * pict->uHeightL, g_recon);
         fwrite(pict->pc_data_u, 1, (size_t)pict->uWidthC * pict->uHeightC, g_recon);
@@ -321,6 +350,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--dump-input") && i + 1 < argc) dump_in = argv[++i];
         else if (!strcmp(argv[i], "--trace-cand")) g_trace_cand = 1;
         else if (!strcmp(argv[i], "--no-levels")) g_trace_levels = 0;
+        else if (!strcmp(argv[i], "--trace-state")) g_trace_state = 1;
         else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
     }
     if ((w & 15) || (h & 15)) { fprintf(stderr, "W and H must be multiples of 16 (hl_codec_264.c:428-439)\n"); return 2; }

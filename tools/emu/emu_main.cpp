@@ -1,0 +1,102 @@
+// emu_main.cpp -- CPU emulation harness of hlb_mbcore.cuh (DEBUGGING AID, never shipped, never a fallback): compiles the same
+// per-macroblock control flow as the CUDA kernel as plain C++ (lanes become loops, macroblocks run in raster order) so that the
+// decision logic can be diffed against traces of the reference encoder without a GPU.
+//   emu --size W H --frames N --qp Q --me-range R --refs K --in frames.yuv --out prefix
+// writes prefix.recon (planes per frame), prefix.rec (hlb200_mb_record_t per MB per frame), prefix.st (MbState per MB per frame)
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define HLB_EMU_DEBUG 1
+int g_emu_dbg = 0;
+#include "../../hartallo_b200/csrc/hlb_mbcore.cuh"
+
+using namespace hlb;
+
+struct CpuExec {
+    MbWork* w;
+    const FrameCtx* f;
+    int prev_frame_sctr;
+    void run(int cmd, int nlanes)
+    {
+        w->cmd = cmd;
+        const int np = cmd_phases(cmd);
+        for (int p = 0; p < np; ++p)
+            for (int lane = 0; lane < nlanes; ++lane) cmd_phase(*w, *f, cmd, p, lane);
+    }
+    int prev_sctr(int mb)
+    {
+        for (int a = mb - 1; a >= 0; --a)
+            if (f->st[a].last_sctr != 255) return f->st[a].last_sctr;
+        return prev_frame_sctr;
+    }
+};
+
+int main(int argc, char** argv)
+{
+    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1;
+    const char *in = nullptr, *out = "emu";
+    int dbg_frame = -1, dbg_mb = -1;
+    if (getenv("EMU_DEBUG_MB")) sscanf(getenv("EMU_DEBUG_MB"), "%d:%d", &dbg_frame, &dbg_mb);
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "--size")) { W = atoi(argv[++i]); H = atoi(argv[++i]); }
+        else if (!strcmp(argv[i], "--frames")) frames = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--qp")) qp = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--me-range")) me_range = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--refs")) refs = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--in")) in = argv[++i];
+        else if (!strcmp(argv[i], "--out")) out = argv[++i];
+    }
+    if (!in) { fprintf(stderr, "--in required\n"); return 2; }
+    const int nmb = (W / 16) * (H / 16);
+    const size_t fb = (size_t)W * H * 3 / 2, ys = (size_t)W * H, cs = ys / 4;
+    std::vector<uint8_t> src(fb);
+    std::vector<std::vector<uint8_t>> slots(refs + 1, std::vector<uint8_t>(fb, 0));
+    std::vector<MbState> st(nmb);
+    memset(st.data(), 0, sizeof(MbState) * nmb);
+    std::vector<hlb200_mb_record_t> rec(nmb);
+    FILE* fi = fopen(in, "rb");
+    if (!fi) { perror(in); return 2; }
+    char path[512];
+    snprintf(path, sizeof(path), "%s.recon", out); FILE* fr = fopen(path, "wb");
+    snprintf(path, sizeof(path), "%s.rec", out); FILE* fc = fopen(path, "wb");
+    snprintf(path, sizeof(path), "%s.st", out); FILE* fs = fopen(path, "wb");
+    MbWork* w = new MbWork();
+    memset(w, 0, sizeof(*w));
+    int chain = 0;
+    std::vector<int> order;  // slots holding previous reconstructions, most recent first
+    for (int n = 0; n < frames; ++n) {
+        if (fread(src.data(), 1, fb, fi) != fb) break;
+        FrameCtx f;
+        memset(&f, 0, sizeof(f));
+        f.W = W; f.H = H; f.mbw = W / 16; f.mbh = H / 16; f.qp = qp;
+        { int q = qp < 0 ? 0 : (qp > 51 ? 51 : qp); static const unsigned char t[22] = {29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39}; f.qpc = q < 30 ? q : t[q - 30]; }
+        f.is_p = n > 0; f.me_range = me_range < 1 ? 1 : (me_range > 64 ? 64 : me_range);
+        f.lambda = 0.852 * (double)(1 << ((qp - 12) / 3));
+        int cur = 0;
+        for (int s = 0; s <= refs; ++s) { bool used = false; for (int o : order) used |= (o == s); if (!used) { cur = s; break; } }
+        f.num_refs = (int)order.size() < refs ? (int)order.size() : refs;
+        if (f.num_refs < 1) f.num_refs = 1;
+        for (int u = 0; u < (int)order.size() && u < refs; ++u) { f.ref[u][0] = slots[order[u]].data(); f.ref[u][1] = f.ref[u][0] + ys; f.ref[u][2] = f.ref[u][1] + cs; }
+        f.src[0] = src.data(); f.src[1] = f.src[0] + ys; f.src[2] = f.src[1] + cs;
+        f.cur[0] = slots[cur].data(); f.cur[1] = f.cur[0] + ys; f.cur[2] = f.cur[1] + cs;
+        f.st = st.data(); f.rec = rec.data();
+        CpuExec x{w, &f, chain};
+        for (int mb = 0; mb < nmb; ++mb) {
+            g_emu_dbg = (n == dbg_frame && mb == dbg_mb);
+            if (g_emu_dbg) fprintf(stderr, "frame %d mb %d\n", n, mb);
+            mb_encode(x, *w, f, mb);
+        }
+        chain = x.prev_sctr(nmb);
+        fwrite(slots[cur].data(), 1, fb, fr);
+        fwrite(rec.data(), sizeof(hlb200_mb_record_t), nmb, fc);
+        fwrite(st.data(), sizeof(MbState), nmb, fs);
+        order.insert(order.begin(), cur);
+        if ((int)order.size() > refs) order.pop_back();
+    }
+    fclose(fi); fclose(fr); fclose(fc); fclose(fs);
+    printf("emu: %d frames, sizeof(MbWork)=%zu sizeof(MbState)=%zu sizeof(rec)=%zu\n", frames, sizeof(MbWork), sizeof(MbState), sizeof(hlb200_mb_record_t));
+    return 0;
+}
