@@ -7,8 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libhl_b200.so")
 SOURCES = ["hlb_api.cu", "hlb_batch.cu", "hlb_slice.cu"]
+# -dlcm=cg: plain global loads are served from L2 (macroblock state / reconstruction written by other CTAs of the slice kernel);
+# read-only planes use __ldg explicitly.  --fmad=false: the RD cost is a double sum that must round like the reference's.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-Xptxas", "-v,-dlcm=cg"]
 
 
 def needs_build():

@@ -83,7 +83,6 @@ int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out
     }
     HLB_CUDA(cudaMalloc(&c->d_records, sizeof(hlb200_mb_record_t) * c->nmb));
     HLB_CUDA(cudaMalloc(&c->d_mbstate, mbstate_bytes(c->nmb)));
-    HLB_CUDA(cudaMalloc(&c->d_sched, sizeof(int) * (64 + c->nmb)));
     int rc = slice_reset_state(c);
     if (rc) return rc;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
@@ -100,6 +99,7 @@ int hlb200_stream_destroy(hlb200_ctx_t* c)
     }
     cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_sched); cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_jobs) cudaFreeHost(c->h_jobs);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;

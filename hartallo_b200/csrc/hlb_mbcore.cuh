@@ -106,7 +106,7 @@ enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_
 // Scratch of the macroblock being encoded (shared memory on the GPU)
 struct MbWork {
     // command mailbox
-    int cmd, arg0, arg1;
+    int cmd, arg0, arg1, arg0_lanes;
     // identity / neighbourhood
     int mb, mbx, mby;
     int availA, availB, availC, availD;
@@ -118,6 +118,7 @@ struct MbWork {
     uint8_t tc_cac[2][4];
     uint8_t cbp_gate;      // CodedBlockPatternLuma as left by the previous picture (gate of in-MB neighbours, utils.h:10-20)
     int8_t extA[16], extB[16];   // nA / nB contributed by the neighbouring macroblocks (-1 = not available), per luma4x4BlkIdx on the MB edge
+    int stuck;             // set when a search loop exceeded its iteration cap (cannot happen for a finite window; watchdog aid)
     int last_sctr;         // rdo.Single_ctr chain; -1 = not yet written by this macroblock
     int need_prev_sctr;    // set when the chain value of the raster predecessor was consumed
     int16_t chroma_ac[2][4][16];
@@ -184,7 +185,7 @@ struct MbWork {
 // ------------------------------------------------------------------------------------------------------------------
 struct NbMotion { int avail; int ref; int mvx, mvy; };
 
-HLB_HD NbMotion nb_motion_at(const MbWork& w, const FrameCtx& f, int xN, int yN, int cur_part, int cur_sub)
+HLB_FN NbMotion nb_motion_at(const MbWork& w, const FrameCtx& f, int xN, int yN, int cur_part, int cur_sub)
 {
     NbMotion r;
     r.avail = 0; r.ref = -1; r.mvx = 0; r.mvy = 0;
@@ -220,7 +221,7 @@ HLB_HD int median3(int a, int b, int c)
 }
 
 // 8.4.1.3 (utils.c:751-798).  (ox,oy,pw) = origin and predPartWidth of the partition under the current search mode
-HLB_HD void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, int ref, int& mx, int& my)
+HLB_FN void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, int ref, int& mx, int& my)
 {
     int ox, oy, pw, ph;
     mode_rect(w.mode, part, sub, ox, oy, pw, ph);
@@ -241,7 +242,7 @@ HLB_HD void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, in
 }
 
 // 8.4.1.1 (utils.c:709-748); only ever called with the 16x16 geometry
-HLB_HD void derive_pskip_mv(const MbWork& w, const FrameCtx& f, int& mx, int& my)
+HLB_FN void derive_pskip_mv(const MbWork& w, const FrameCtx& f, int& mx, int& my)
 {
     NbMotion A = nb_motion_at(w, f, -1, 0, 0, 0);
     NbMotion B = nb_motion_at(w, f, 0, -1, 0, 0);
@@ -288,13 +289,13 @@ HLB_HD void ref_window9(const uint8_t* plane, int W, int H, int X, int Y, uint8_
 #pragma unroll
         for (int r = 0; r < 9; ++r)
 #pragma unroll
-            for (int c = 0; c < 9; ++c) t[r * 9 + c] = p[r * W + c];
+            for (int c = 0; c < 9; ++c) t[r * 9 + c] = HLB_LDG(p + r * W + c);
     } else {
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
             const int y = clip3(0, H - 1, Y - 2 + r);
 #pragma unroll
-            for (int c = 0; c < 9; ++c) t[r * 9 + c] = plane[y * W + clip3(0, W - 1, X - 2 + c)];
+            for (int c = 0; c < 9; ++c) t[r * 9 + c] = HLB_LDG(plane + y * W + clip3(0, W - 1, X - 2 + c));
         }
     }
 }
@@ -312,7 +313,7 @@ HLB_HD void pred_luma_4x4(const FrameCtx& f, const uint8_t* ref_y, int mbx, int 
 // ------------------------------------------------------------------------------------------------------------------
 // CMD_ME_EVAL: the trial encodes of one search step (me_ds.c:527-688 for every candidate of the step)
 // ------------------------------------------------------------------------------------------------------------------
-HLB_HD void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
 {
     const int bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
     const int c = lane / nblk, k = lane - c * nblk;
@@ -359,7 +360,7 @@ HLB_HD bool blk_in_part(const MbWork& w, int blk)
     return x >= w.part_ox && x < w.part_ox + w.part_w && y >= w.part_oy && y < w.part_oy + w.part_h;
 }
 // per block: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806)
-HLB_HD void me_phase_scan(MbWork& w, int lane)
+HLB_FN void me_phase_scan(MbWork& w, int lane)
 {
     if (lane >= 16) return;
     int e = w.tc[lane];
@@ -370,7 +371,7 @@ HLB_HD void me_phase_scan(MbWork& w, int lane)
     }
     w.tc[lane] = (uint8_t)e;
 }
-HLB_HD void me_phase_token(MbWork& w, int lane)
+HLB_FN void me_phase_token(MbWork& w, int lane)
 {
     const int bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
     const int c = lane / nblk, k = lane - c * nblk;
@@ -381,7 +382,7 @@ HLB_HD void me_phase_token(MbWork& w, int lane)
     HLB_DBG("      token c%d blk %d: nC %d tc %d t1 %d gate %x eff[4]=%d eff[1]=%d extA %d extB %d\n", c, blk, nC, w.r_tc[c][blk], w.r_t1[c][blk], w.cbp_gate, w.eff[c][4], w.eff[c][1], w.extA[blk], w.extB[blk]);
     w.r_bits[c][blk] = (uint16_t)(w.r_bits[c][blk] + coeff_token_len(nC, w.r_tc[c][blk], w.r_t1[c][blk]));
 }
-HLB_HD void me_phase_sum(MbWork& w, int lane)
+HLB_FN void me_phase_sum(MbWork& w, int lane)
 {
     if (lane >= w.ncand) return;
     const int c = lane, bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
@@ -407,7 +408,7 @@ HLB_TABLE static const uint16_t kPruneQuarter[9] = {0x1B0, 0x1F8, 0x03F, 0x1B6, 
 HLB_TABLE static const uint8_t kHeaderBits[7] = {3, 5, 5, 11, 19, 19, 27};
 
 template <class X>
-HLB_HD void me_eval(X& x, MbWork& w)
+HLB_FN void me_eval(X& x, MbWork& w)
 {
     const int nblk = (w.part_w >> 2) * (w.part_h >> 2);
     x.run(CMD_ME_EVAL, w.ncand * nblk < 16 ? 16 : w.ncand * nblk);  // the scan phase needs one lane per luma block
@@ -422,7 +423,7 @@ HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
 }
 
 template <class X>
-HLB_HD void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
+HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
 {
     w.mode = mode;
     const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
@@ -458,7 +459,8 @@ HLB_HD void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
             }
             int cx = w.best_mv[p][s][0] >> 2, cy = w.best_mv[p][s][1] >> 2;
             int wl = cx - f.me_range, wr = cx + f.me_range, wt = cy - f.me_range, wb = cy + f.me_range;
-            for (;;) {
+            for (int iter = 0;; ++iter) {
+                if (iter > 4096) { w.stuck = 1; break; }
                 int best_idx = -1;
                 const int count = shift == 1 ? 5 : 9;
                 uint8_t idxs[HLB_MAXC];
@@ -514,7 +516,7 @@ HLB_HD void fin_rect(const MbWork& w, int x, int y, int& part, int& sub, int& ox
     int m = w.fin_mode < 3 ? w.fin_mode : 3 + w.fin_sub[part], pw, ph;
     mode_rect(m, part, sub, ox, oy, pw, ph);
 }
-HLB_HD void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane < 16) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
@@ -538,7 +540,7 @@ HLB_HD void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
                 const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
                 const int x0 = w.mbx * 8 + px + (mvx >> 3), y0 = w.mby * 8 + py + (mvy >> 3);
                 const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
-                w.pred_c[c][py * 8 + px] = (uint8_t)interp_chroma_px(rp[ya + xa], rp[ya + xb], rp[yc + xa], rp[yc + xb], mvx & 7, mvy & 7);
+                w.pred_c[c][py * 8 + px] = (uint8_t)interp_chroma_px(HLB_LDG(rp + ya + xa), HLB_LDG(rp + ya + xb), HLB_LDG(rp + yc + xa), HLB_LDG(rp + yc + xb), mvx & 7, mvy & 7);
             }
     }
 }
@@ -546,7 +548,7 @@ HLB_HD void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 // Luma residual coding + reconstruction of an inter macroblock (rdo.c:2418-2478): lanes 0..15 = luma4x4BlkIdx
 // ------------------------------------------------------------------------------------------------------------------
-HLB_HD void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane >= 16) return;
     const int bx = blk_x(lane), by = blk_y(lane);
@@ -600,7 +602,7 @@ HLB_HD void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
 // phase 1: lane 0: the serial bookkeeping (single-coefficient elimination, DC Hadamard + quantisation)
 // phase 2: lanes 0..7: reconstruction
 // ------------------------------------------------------------------------------------------------------------------
-HLB_HD void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane >= 8) return;
     const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
@@ -630,7 +632,7 @@ HLB_HD void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
         w.c_sc[c][b] = ci.single_ctr; w.c_tc[c][b] = ci.total_coeff;
     }
 }
-HLB_HD void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane != 0) return;
     int single[2] = {0, 0}, totc[2] = {0, 0};
@@ -672,7 +674,7 @@ HLB_HD void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
         for (int k = 0; k < 4; ++k) w.c_dccoef[c][k] = d[k];
     }
 }
-HLB_HD void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane >= 8) return;
     const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
@@ -702,22 +704,22 @@ HLB_HD void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 // load / store of the macroblock's samples: lanes 0..23 (16 luma 4x4 blocks raster + 8 chroma blocks)
 // ------------------------------------------------------------------------------------------------------------------
-HLB_HD void phase_load(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_load(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane < 16) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
         const uint8_t* p = f.src[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
         for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) w.src_y[(by + r) * 16 + bx + q] = p[r * f.W + q];
+            for (int q = 0; q < 4; ++q) w.src_y[(by + r) * 16 + bx + q] = HLB_LDG(p + r * f.W + q);
     } else if (lane < 24) {
         const int c = (lane - 16) >> 2, b = (lane - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4, Wc = f.W >> 1;
         const uint8_t* p = f.src[1 + c] + (w.mby * 8 + y0) * Wc + w.mbx * 8 + x0;
         for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) w.src_c[c][(y0 + r) * 8 + x0 + q] = p[r * Wc + q];
+            for (int q = 0; q < 4; ++q) w.src_c[c][(y0 + r) * 8 + x0 + q] = HLB_LDG(p + r * Wc + q);
     }
 }
 // arg0 bit 0: luma, bit 1: chroma
-HLB_HD void phase_store(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void phase_store(MbWork& w, const FrameCtx& f, int lane)
 {
     if (lane < 16 && (w.arg0 & 1)) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
@@ -750,7 +752,7 @@ HLB_HD int cmd_phases(int cmd)
     default: return 1;
     }
 }
-HLB_HD void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane)
+HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane)
 {
     switch (cmd) {
     case CMD_LOAD: phase_load(w, f, lane); break;
@@ -786,7 +788,7 @@ HLB_HD void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
 template <class X>
 HLB_HD void chroma_code(X& x, MbWork& w) { x.run(CMD_CHROMA, 8); }
 
-HLB_HD void mb_begin(MbWork& w, const FrameCtx& f, int mb)
+HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb)
 {
     w.mb = mb; w.mbx = mb % f.mbw; w.mby = mb / f.mbw;
     w.availA = w.mbx > 0; w.availB = w.mby > 0; w.availC = w.mby > 0 && w.mbx < f.mbw - 1; w.availD = w.mbx > 0 && w.mby > 0;
@@ -808,14 +810,14 @@ HLB_HD void mb_begin(MbWork& w, const FrameCtx& f, int mb)
         w.extA[blk] = (int8_t)((bx == 0) ? (w.availA ? nb_count(f.st[mb - 1], blk_idx_from_xy(12, by)) : -1) : 0);
         w.extB[blk] = (int8_t)((by == 0) ? (w.availB ? nb_count(f.st[mb - f.mbw], blk_idx_from_xy(bx, 12)) : -1) : 0);
     }
-    w.last_sctr = -1; w.need_prev_sctr = 0;
+    w.last_sctr = -1; w.need_prev_sctr = 0; w.stuck = 0;
     w.mb_is_intra = 0;
 }
 
 // state the writer leaves behind (residual.c:903-1094) + publication of the macroblock's final state and record
 HLB_HD int nnz16(const int16_t* lv, int n) { int k = 0; for (int i = 0; i < n; ++i) k += (lv[i] != 0); return k; }
 
-HLB_HD void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad)
+HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad)
 {
     MbState& s = f.st[w.mb];
     hlb200_mb_record_t& r = f.rec[w.mb];
@@ -887,7 +889,7 @@ HLB_HD int guess_cbp_chroma(const MbWork& w)
 }
 
 template <class X>
-HLB_HD void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
+HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
 {
     double best_cost = DBL_MAX;
     int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0;

@@ -39,7 +39,7 @@ HLB_HD int intra_chroma_at(const MbWork& w, const FrameCtx& f, int c, int x, int
 // ------------------------------------------------------------------------------------------------------------------
 struct I16Shared { I16Params q; };
 
-HLB_HD void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
+HLB_FN void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
 {
     if (phase == 0) {
         if (lane >= 64) return;
@@ -146,7 +146,7 @@ HLB_HD void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
         w.t_dist[m][blk] = dist;
     }
 }
-HLB_HD void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
 {
     (void)f;
     if (lane >= 16) return;  // copy the reconstruction of the chosen Intra16x16 mode (identical to transf.c:298 on the same levels)
@@ -156,7 +156,7 @@ HLB_HD void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 // CMD_I4_EVAL for block w.i4_blk: 9 lanes = Intra4x4 modes (rdo.c:1903-2010)
 // ------------------------------------------------------------------------------------------------------------------
-HLB_HD void i4_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
+HLB_FN void i4_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
 {
     if (phase != 0 || lane >= 9) return;
     const int mode = lane, blk = w.i4_blk, bx = blk_x(blk), by = blk_y(blk);
@@ -206,7 +206,7 @@ HLB_HD void i4_commit_phase(MbWork& w, const FrameCtx& f, int lane) { (void)w; (
 // ------------------------------------------------------------------------------------------------------------------
 // CMD_PRED_CHROMA_INTRA: 8 lanes = (plane, 4x4 block); p17 and the mode are set by the master (pred_intra.c:1044-1230)
 // ------------------------------------------------------------------------------------------------------------------
-HLB_HD void intra_chroma_pred_phase(MbWork& w, const FrameCtx& f, int lane)
+HLB_FN void intra_chroma_pred_phase(MbWork& w, const FrameCtx& f, int lane)
 {
     (void)f;
     if (lane >= 8) return;
@@ -221,7 +221,7 @@ HLB_HD void intra_chroma_pred_phase(MbWork& w, const FrameCtx& f, int lane)
 // in the picture, levels / modes / CBP flags in w.
 // ------------------------------------------------------------------------------------------------------------------
 template <class X>
-HLB_HD int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cost)
+HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cost)
 {
     // ---- Intra16x16 (no reconstruction into the picture yet) ----
     w.p33[0] = intra_luma_at(w, f, -1, -1);
@@ -343,11 +343,11 @@ HLB_HD int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     return kind;
 }
 
-HLB_HD void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad);
+HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad);
 HLB_HD int guess_cbp_luma(int cbp4x4, bool i16);
 HLB_HD int guess_cbp_chroma(const MbWork& w);
 
-HLB_HD void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind)
+HLB_FN void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind)
 {
     const int mad = w.arg0;
     const int cbp_luma = guess_cbp_luma(w.cbp_luma4x4, kind == MBK_I16);

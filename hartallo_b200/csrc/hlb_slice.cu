@@ -1,23 +1,328 @@
-// hlb_slice.cu -- slice-level hot path (ME + mode decision + reconstruction), wavefront-scheduled.  (under construction)
+// hlb_slice.cu -- slice-level hot path on the device: hlb200_slice_encode = the per-macroblock decide + reconstruct loop of
+// hl_codec_264_nal_slice_data_encode (source/h264/hl_codec_264_slice.c:1786-1894) for one picture of one or many streams.
+//
+// Scheduling.  A macroblock may start when its neighbours A, B, C, D are final: the 2:1 wavefront.  One persistent
+// kernel serves every picture of a batch (independent streams): CTAs pop ready macroblocks from a global queue; a finished
+// macroblock decrements the dependency counters of its successors (right neighbour; the MB whose top-right it is) and pushes
+// those that reach zero.  A CTA therefore never holds a blocked macroblock, so the scheme cannot deadlock whatever the grid
+// size.  I pictures add the raster predecessor as a dependency (the Single_ctr chain of residual.c:882, see hlb_mbintra.cuh);
+// in P pictures that chain is consumed almost never and is fetched lazily by waiting for the predecessor's done flag.
+//
+// One CTA per macroblock, warp-specialised: warp 0 (the master warp) runs the serial control flow of hlb_mbcore.cuh -- all 32 lanes
+// redundantly on identical data, so the warp stays converged -- and posts commands; warps 1..5 (HLB_MB_LANES = 160 lanes) execute
+// the command phases.  Master and workers meet at named barrier 1 from different code paths, which is legal for bar.sync as long
+// as every WARP is converged at its own call site (bar.sync == barrier.sync.aligned).  Global loads are compiled .cg (-Xptxas -dlcm=cg) so that state and
+// reconstruction written by other CTAs is read from L2; read-only planes go through __ldg.
+#include <new>
+
 #include "hlb_common.cuh"
+#include "hlb_mbcore.cuh"
 
 namespace hlb {
-size_t mbstate_bytes(int nmb) { return (size_t)nmb * 1024; }
+
+struct SliceJob {
+    FrameCtx f;
+    int nmb;
+    int base;            // first item index of this job in the scheduler arrays
+    int prev_frame_sctr; // Single_ctr chain value entering the picture
+    int* chain;          // per-stream carrier of that value across pictures (device)
+};
+
+struct Sched {
+    int head, tail, total, abort;   // abort != 0: a watchdog fired (code below); every spin loop gives up and the kernel drains
+    int dbg[12];                    // [0] code, [1] item, [2] queue index / neighbour, [3] blockIdx, [4..] spare
+};
+#define HLB_SCHED_WORDS 16
+enum { WD_QUEUE = 1, WD_PREV = 2, WD_SEARCH = 3 };
+#define HLB_SPIN_LIMIT (1 << 22)    // x ~200 ns sleep: about a second of waiting before a spin loop declares the kernel stuck
+// layout of the scheduler buffer: Sched | queue[total] | deps[total] | done[total]
+__device__ __forceinline__ void watchdog_fire(Sched* s, int code, int a, int b)
+{
+    if (atomicCAS(&s->abort, 0, code) == 0) { s->dbg[0] = code; s->dbg[1] = a; s->dbg[2] = b; s->dbg[3] = (int)blockIdx.x; __threadfence(); }
+}
+
+#define HLB_CTA_THREADS (HLB_MB_LANES + 32)
+__device__ __forceinline__ void cta_bar() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(HLB_CTA_THREADS) : "memory"); }
+__device__ __forceinline__ int ld_volatile(const int* p) { return *(const volatile int*)p; }
+
+struct GpuExec {
+    MbWork* w;
+    const FrameCtx* f;
+    const SliceJob* job;
+    const int* done;
+    Sched* sched;
+    __device__ __noinline__ void run(int cmd, int nlanes)
+    {
+        w->arg0_lanes = nlanes;
+        ((volatile int*)&w->cmd)[0] = cmd;
+        cta_bar();
+        const int np = cmd_phases(cmd);
+        for (int p = 0; p < np; ++p) cta_bar();   // the worker warps run the phases
+    }
+    __device__ __noinline__ int prev_sctr(int mb)
+    {
+        for (int a = mb - 1; a >= 0; --a) {
+            int spins = 0;
+            while (ld_volatile(done + job->base + a) == 0) {
+                if (ld_volatile(&sched->abort)) return 0;
+                if (++spins > HLB_SPIN_LIMIT) { watchdog_fire(sched, WD_PREV, job->base + mb, a); return 0; }
+                __nanosleep(200);
+            }
+            __threadfence();
+            const int v = *(volatile const uint8_t*)&f->st[a].last_sctr;
+            if (v != 255) return v;
+        }
+        return job->prev_frame_sctr;
+    }
+};
+
+__global__ void k_slice_init(SliceJob* jobs, int njobs, int* sched_buf, int total)
+{
+    Sched* s = (Sched*)sched_buf;
+    int* queue = sched_buf + HLB_SCHED_WORDS;
+    int* deps = queue + total;
+    int* done = deps + total;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { s->head = 0; s->tail = njobs; s->total = total; s->abort = 0; for (int k = 0; k < 12; ++k) s->dbg[k] = 0; }
+    if (t < njobs) {
+        queue[t] = jobs[t].base;  // macroblock 0 of every picture is ready
+        // Single_ctr chain entering the picture: last value any macroblock of the previous picture left (residual.c:882)
+        const SliceJob& j = jobs[t];
+        int v = *j.chain;
+        for (int a = j.nmb - 1; a >= 0; --a)
+            if (j.f.st[a].last_sctr != 255) { v = j.f.st[a].last_sctr; break; }
+        jobs[t].prev_frame_sctr = v;
+        *j.chain = v;
+    }
+    for (int i = t; i < total; i += gridDim.x * blockDim.x) {
+        if (i >= njobs) queue[i] = -1;
+        done[i] = 0;
+        // which job / macroblock is item i
+        int jb = 0;
+        while (jb + 1 < njobs && jobs[jb + 1].base <= i) ++jb;
+        const SliceJob& j = jobs[jb];
+        const int mb = i - j.base, x = mb % j.f.mbw, y = mb / j.f.mbw;
+        deps[i] = j.f.is_p ? ((x > 0) + (y > 0)) : (mb > 0);
+    }
+}
+
+__global__ void __launch_bounds__(HLB_CTA_THREADS) k_slice_encode(const SliceJob* __restrict__ jobs, int njobs, int* sched_buf)
+{
+    __shared__ MbWork w;
+    __shared__ FrameCtx sf;
+    __shared__ int s_item, s_job;
+    Sched* s = (Sched*)sched_buf;
+    const int total = s->total;
+    int* queue = sched_buf + HLB_SCHED_WORDS;
+    int* deps = queue + total;
+    int* done = deps + total;
+    const int tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) {
+            const int idx = atomicAdd(&s->head, 1);
+            int item = -1;
+            if (idx < total && !ld_volatile(&s->abort)) {
+                int spins = 0;
+                while ((item = ld_volatile(queue + idx)) < 0) {
+                    if (ld_volatile(&s->abort)) break;
+                    if (++spins > HLB_SPIN_LIMIT) { watchdog_fire(s, WD_QUEUE, idx, ld_volatile(&s->tail)); break; }
+                    __nanosleep(200);
+                }
+                __threadfence();
+            }
+            s_item = item;
+            if (item >= 0) {
+                int jb = 0;
+                while (jb + 1 < njobs && jobs[jb + 1].base <= item) ++jb;
+                s_job = jb;
+            }
+        }
+        __syncthreads();
+        const int item = s_item;
+        if (item < 0) break;
+        const SliceJob* job = jobs + s_job;
+        // picture context -> shared memory (read by every lane, many times)
+        {
+            const int* src = (const int*)&job->f;
+            int* dst = (int*)&sf;
+            for (int i = tid; i < (int)(sizeof(FrameCtx) / sizeof(int)); i += HLB_CTA_THREADS) dst[i] = src[i];
+        }
+        __syncthreads();
+        const int mb = item - job->base;
+        if (tid < 32) {   // master warp: every lane executes the same control flow on the same data
+            GpuExec x;
+            x.w = &w; x.f = &sf; x.job = job; x.done = done; x.sched = s;
+            mb_encode(x, w, sf, mb);
+            if (w.stuck) watchdog_fire(s, WD_SEARCH, item, 0);
+            ((volatile int*)&w.cmd)[0] = CMD_EXIT;
+            cta_bar();
+        } else {
+            const int lane = tid - 32;
+            for (;;) {
+                cta_bar();
+                const int cmd = ((volatile int*)&w.cmd)[0];
+                if (cmd == CMD_EXIT) break;
+                const int nl = w.arg0_lanes;
+                const int np = cmd_phases(cmd);
+                for (int p = 0; p < np; ++p) {
+                    if (lane < nl) cmd_phase(w, sf, cmd, p, lane);
+                    cta_bar();
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicExch(done + item, 1);
+            // successors (see the header comment)
+            const int mbw = sf.mbw, mbh = sf.mbh, x = mb % mbw, y = mb / mbw;
+            int succ[3], ns = 0;
+            if (sf.is_p) {
+                if (x + 1 < mbw) succ[ns++] = item + 1;
+                if (y + 1 < mbh) {
+                    if (x >= 1) succ[ns++] = item + mbw - 1;          // (x-1, y+1): its top-right is this macroblock
+                    if (x == mbw - 1) succ[ns++] = item + mbw;        // last column waits for its top neighbour
+                    if (mbw == 1) {}                                   // (covered by the line above)
+                }
+            } else if (mb + 1 < job->nmb) succ[ns++] = item + 1;
+            for (int k = 0; k < ns; ++k)
+                if (atomicSub(deps + succ[k], 1) == 1) {
+                    const int slot = atomicAdd(&s->tail, 1);
+                    atomicExch(queue + slot, succ[k]);
+                }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t state_array_bytes(int nmb) { return ((size_t)nmb * sizeof(MbState) + 255) & ~(size_t)255; }
+size_t mbstate_bytes(int nmb) { return state_array_bytes(nmb) + 256; }   // + the Single_ctr chain word
 int slice_reset_state(hlb200_ctx* c)
 {
     HLB_CUDA(cudaMemsetAsync(c->d_mbstate, 0, mbstate_bytes(c->nmb), c->stream));
     c->frame_count = 0;
     return HLB200_OK;
 }
+
+static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j, int base)
+{
+    if (!c || !p || p->qp < 12 || p->qp > 51 || p->cur_slot < 0 || p->cur_slot >= c->nslots || (p->slice_type != 0 && p->slice_type != 1)) return HLB200_ERR_INVALID_PARAMETER;
+    memset(j, 0, sizeof(*j));
+    FrameCtx& f = j->f;
+    f.W = c->width; f.H = c->height; f.mbw = c->mbw; f.mbh = c->mbh;
+    f.qp = p->qp; f.qpc = host_chroma_qp(p->qp, p->chroma_qp_index_offset);
+    f.is_p = p->slice_type == 1;
+    f.me_range = p->me_range < 1 ? 1 : (p->me_range > 64 ? 64 : p->me_range);   // rdo.c:847
+    f.num_refs = f.is_p ? p->num_refs : 0;
+    if (f.is_p && (f.num_refs < 1 || f.num_refs > c->max_refs)) return HLB200_ERR_INVALID_PARAMETER;
+    f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));                       // slice.c:1766 (integer division in the exponent)
+    for (int k = 0; k < 3; ++k) { f.src[k] = c->d_src[k]; f.cur[k] = c->d_slot[p->cur_slot][k]; }
+    for (int u = 0; u < f.num_refs; ++u) {
+        const int s = p->ref_slot[u];
+        if (s < 0 || s >= c->nslots || s == p->cur_slot) return HLB200_ERR_INVALID_PARAMETER;
+        for (int k = 0; k < 3; ++k) f.ref[u][k] = c->d_slot[s][k];
+    }
+    f.st = (MbState*)c->d_mbstate;
+    f.rec = c->d_records;
+    j->nmb = c->nmb; j->base = base; j->prev_frame_sctr = 0;
+    j->chain = (int*)((char*)c->d_mbstate + state_array_bytes(c->nmb));
+    return HLB200_OK;
+}
+
+static int g_slice_grid = 0;
+static int slice_grid()
+{
+    if (g_slice_grid) return g_slice_grid;
+    int dev = 0, sms = 0, per = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_slice_encode, HLB_CTA_THREADS, 0) != cudaSuccess || per < 1) {
+        cudaGetLastError();
+        return 148;
+    }
+    g_slice_grid = sms * per;
+    return g_slice_grid;
+}
+
 }  // namespace hlb
+using namespace hlb;
 
 extern "C" {
-int hlb200_slice_encode_async(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params) { (void)ctx; (void)params; return HLB200_ERR_NOT_IMPLEMENTED; }
-int hlb200_records_download(hlb200_ctx_t* ctx, hlb200_mb_record_t* out_records) { (void)ctx; (void)out_records; return HLB200_ERR_NOT_IMPLEMENTED; }
+
+int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_params_t* params, int n)
+{
+    if (!ctxs || !params || n < 1 || n > 4096) return HLB200_ERR_INVALID_PARAMETER;
+    hlb200_ctx* c0 = ctxs[0];
+    if (!c0) return HLB200_ERR_INVALID_PARAMETER;
+    int total = 0;
+    for (int i = 0; i < n; ++i) { if (!ctxs[i]) return HLB200_ERR_INVALID_PARAMETER; total += ctxs[i]->nmb; }
+    // scheduler + job storage lives in the first context of the batch
+    const size_t need = sizeof(SliceJob) * (size_t)n + sizeof(int) * (HLB_SCHED_WORDS + 3 * (size_t)total) + 512;
+    if (c0->sched_bytes < need) {
+        if (c0->d_sched) HLB_CUDA(cudaFree(c0->d_sched));
+        c0->d_sched = nullptr; c0->sched_bytes = 0;
+        HLB_CUDA(cudaMalloc((void**)&c0->d_sched, need));
+        c0->sched_bytes = need;
+        if (c0->h_jobs) HLB_CUDA(cudaFreeHost(c0->h_jobs));
+        c0->h_jobs = nullptr;
+    }
+    if (!c0->h_jobs || c0->h_jobs_cap < n) {
+        if (c0->h_jobs) HLB_CUDA(cudaFreeHost(c0->h_jobs));
+        HLB_CUDA(cudaMallocHost(&c0->h_jobs, sizeof(SliceJob) * (size_t)n));
+        c0->h_jobs_cap = n;
+    }
+    SliceJob* hj = (SliceJob*)c0->h_jobs;
+    int base = 0;
+    for (int i = 0; i < n; ++i) {
+        const int rc = build_job(ctxs[i], params + i, hj + i, base);
+        if (rc) return rc;
+        base += ctxs[i]->nmb;
+    }
+    SliceJob* dj = (SliceJob*)c0->d_sched;
+    int* sched = (int*)((char*)c0->d_sched + ((sizeof(SliceJob) * (size_t)n + 255) & ~(size_t)255));
+    cudaStream_t st = c0->stream;
+    // the pinned job array must not be rewritten while a previous copy is still in flight; uploads queued on the other contexts'
+    // streams must have landed before the batch kernel reads them
+    for (int i = 0; i < n; ++i) HLB_CUDA(cudaStreamSynchronize(ctxs[i]->stream));
+    HLB_CUDA(cudaMemcpyAsync(dj, hj, sizeof(SliceJob) * (size_t)n, cudaMemcpyHostToDevice, st));
+    c0->last_sched = sched;
+    k_slice_init<<<(total + 255) / 256, 256, 0, st>>>(dj, n, sched, total);
+    HLB_CUDA(cudaGetLastError());
+    int grid = slice_grid();
+    if (grid > total) grid = total;
+    k_slice_encode<<<grid, HLB_CTA_THREADS, 0, st>>>(dj, n, sched);
+    HLB_CUDA(cudaGetLastError());
+    for (int i = 0; i < n; ++i) ctxs[i]->frame_count++;
+    return HLB200_OK;
+}
+
+int hlb200_slice_encode_async(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params) { return hlb200_slice_encode_batch_async(&ctx, params, 1); }
+
+// reads the watchdog words of the last launch whose scheduler lives in `c` (after the stream has drained)
+int hlb200_slice_status(hlb200_ctx_t* c, int* out16)
+{
+    if (!c || !out16) return HLB200_ERR_INVALID_PARAMETER;
+    for (int k = 0; k < 16; ++k) out16[k] = 0;
+    if (!c->d_sched || !c->last_sched) return HLB200_OK;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    HLB_CUDA(cudaMemcpy(out16, c->last_sched, sizeof(int) * 16, cudaMemcpyDeviceToHost));
+    return out16[3] ? HLB200_ERR_INVALID_STATE : HLB200_OK;
+}
+
+int hlb200_records_download(hlb200_ctx_t* c, hlb200_mb_record_t* out_records)
+{
+    if (!c || !out_records) return HLB200_ERR_INVALID_PARAMETER;
+    HLB_CUDA(cudaMemcpyAsync(out_records, c->d_records, sizeof(hlb200_mb_record_t) * (size_t)c->nmb, cudaMemcpyDeviceToHost, c->stream));
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
 int hlb200_slice_encode(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params, hlb200_mb_record_t* out_records)
 {
     int rc = hlb200_slice_encode_async(ctx, params);
     if (rc) return rc;
     return hlb200_records_download(ctx, out_records);
 }
-}
+
+int hlb200_slice_grid_size(void) { return slice_grid(); }
+
+}  // extern "C"

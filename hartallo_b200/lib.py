@@ -52,6 +52,7 @@ def load():
         "hlb200_stream_sync": [vp], "hlb200_frame_upload": [vp, vp, vp, vp, ip, ip], "hlb200_slot_upload": [vp, ip, vp, vp, vp],
         "hlb200_slot_download": [vp, ip, vp, vp, vp], "hlb200_state_reset": [vp],
         "hlb200_slice_encode": [vp, C.POINTER(SliceParams), vp], "hlb200_slice_encode_async": [vp, C.POINTER(SliceParams)], "hlb200_records_download": [vp, vp],
+        "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_status": [vp, vp],
         "hlb200_interp_luma": [vp, ip, vp, vp], "hlb200_interp_chroma": [vp, ip, vp, vp, vp],
         "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
         "hlb200_dev_interp_luma": [vp, ip, ip, vp, vp, vp], "hlb200_dev_interp_chroma": [vp, vp, ip, ip, vp, vp, vp, vp],
@@ -152,7 +153,74 @@ class Stream:
         check(self.lib.hlb200_me_cost(self.ctx, ref_slot, qp, ptr(cands), len(cands), ptr(out)), "me_cost")
         return out
 
+    def slice_status(self):
+        st = np.zeros(16, np.int32)
+        rc = self.lib.hlb200_slice_status(self.ctx, ptr(st))
+        if rc != 0:
+            raise Hlb200Error("slice kernel watchdog fired: head %d tail %d total %d code %d dbg %s" % (st[0], st[1], st[2], st[3], st[4:12].tolist()))
+        return st
+
     def slice_encode(self, params):
         rec = np.zeros(self.nmb, MB_RECORD)
         check(self.lib.hlb200_slice_encode(self.ctx, C.byref(params), ptr(rec)), "slice_encode")
+        self.slice_status()
         return rec
+
+
+class Encoder:
+    """Host-side mirror of the reference's per-stream encode flow for the device path (source/h264/hl_codec_264.c:404-1006):
+    frame 0 (and every gop_size-th) is an IDR picture, the rest are P pictures predicted from the previous reconstructions;
+    fixed QP (rate control stays on the host).  Frame stores rotate exactly like a sliding-window DPB with `refs` references."""
+
+    def __init__(self, width, height, qp=31, me_range=16, refs=1, gop_size=400, device=0):
+        self.st = Stream(width, height, refs, device)
+        self.qp, self.me_range, self.refs, self.gop = qp, me_range, refs, gop_size
+        self.order = []      # slots holding reference pictures, most recent first
+        self.n = 0
+
+    def params(self):
+        p = SliceParams()
+        idr = (self.n % self.gop) == 0
+        if idr:
+            self.order = []
+        p.slice_type = 0 if idr else 1
+        p.qp, p.me_range, p.chroma_qp_index_offset = self.qp, self.me_range, 0
+        p.num_refs = min(len(self.order), self.refs) if not idr else 0
+        p.cur_slot = next(s for s in range(self.refs + 1) if s not in self.order)
+        for i, s in enumerate(self.order[:self.refs]):
+            p.ref_slot[i] = s
+        return p
+
+    def advance(self, p):
+        self.order.insert(0, p.cur_slot)
+        del self.order[self.refs:]
+        self.n += 1
+
+    def encode(self, yuv, want_recon=False):
+        p = self.params()
+        self.st.upload_frame(yuv)
+        rec = self.st.slice_encode(p)
+        recon = self.st.download_slot(p.cur_slot) if want_recon else None
+        self.advance(p)
+        return rec, recon
+
+    def close(self):
+        self.st.close()
+
+
+def encode_batch(encoders, frames):
+    """one picture of every encoder in a single launch (hlb200_slice_encode_batch_async); returns after the launch is queued"""
+    lib = load()
+    n = len(encoders)
+    ps = (SliceParams * n)()
+    ctxs = (C.c_void_p * n)()
+    for i, (e, f) in enumerate(zip(encoders, frames)):
+        p = e.params()
+        C.memmove(C.byref(ps[i]), C.byref(p), C.sizeof(SliceParams))
+        ctxs[i] = e.st.ctx
+        if f is not None:
+            e.st.upload_frame(f)
+    check(lib.hlb200_slice_encode_batch_async(ctxs, ps, n), "slice_encode_batch_async")
+    for i, e in enumerate(encoders):
+        e.advance(ps[i])
+    return ps

@@ -156,6 +156,12 @@ HLB200_API int hlb200_slice_encode(hlb200_ctx_t* ctx, const hlb200_slice_params_
 /* asynchronous form: records stay on the device until fetched */
 HLB200_API int hlb200_slice_encode_async(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params);
 HLB200_API int hlb200_records_download(hlb200_ctx_t* ctx, hlb200_mb_record_t* out_records);
+/* one picture of each of n independent streams in ONE launch (the contexts may differ in size); this is how a B200 is kept busy:
+ * a single 1080p picture exposes at most 60 macroblocks of wavefront parallelism */
+HLB200_API int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_params_t* params, int n);
+/* watchdog words of the last slice launch: out16[3] != 0 means a wait inside the kernel gave up (HLB200_ERR_INVALID_STATE) */
+HLB200_API int hlb200_slice_status(hlb200_ctx_t* ctx, int* out16);
+HLB200_API int hlb200_slice_grid_size(void); /* CTAs the slice kernel keeps resident on the current device */
 
 /* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
 HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);

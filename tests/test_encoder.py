@@ -1,0 +1,140 @@
+"""Slice-level parity (hlb200_slice_encode = the per-MB decide+reconstruct loop of hl_codec_264_nal_slice_data_encode):
+macroblock types, partitions, motion vectors, mvd, coded block patterns, quantised levels and reconstructed pictures must be
+identical to the reference encoder's.  Counterpart of the reference's source/test_encoder.c (which only prints fps).
+
+Golden data = outputs of the UNMODIFIED reference C path (tests/golden/make_golden_encoder.py).  Where oracle/_ref/hl_ref_driver
+is present the reference is additionally run live on fresh seeds.
+
+* CPU (`-m "not gpu"`): the control flow shared with the kernel, compiled as plain C++ (tools/emu), against the golden data.
+* GPU (`-m gpu`): the CUDA path through the C-ABI.
+"""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import reftrace as rt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38"]
+
+
+def frames_of(gen, seed, w, h, n):
+    from hartallo_b200 import synth
+    g = synth.make(gen, w, h, seed)
+    return [g.next() for _ in range(n)]
+
+
+def level_md5(kind, rec):
+    if kind == 1:
+        lv = rec["luma_level"].astype(np.int16) * ((int(rec["cbp_luma4x4"]) >> np.arange(16)) & 1)[:, None].astype(np.int16)
+    elif kind == 3:
+        lv = rec["luma_level"].astype(np.int16)
+    elif kind == 2:
+        lv = np.concatenate([rec["i16_dc_level"].reshape(1, 16), rec["i16_ac_level"]]).astype(np.int16)
+    else:
+        lv = np.zeros((1, 1), np.int16)
+    return hashlib.md5(lv.tobytes()).hexdigest()
+
+
+def check_frame(g, n, rec, recon, what):
+    """rec: MB_RECORD array of frame n; recon: tight planes"""
+    nmb = len(rec)
+    assert hashlib.md5(recon.tobytes()).hexdigest() == str(g["recon_md5"][n]), "%s: reconstruction of frame %d differs" % (what, n)
+    for a in range(nmb):
+        k = int(g["kind"][n, a])
+        r = rec[a]
+        assert int(r["mb_class"]) == k, (what, n, a, "class", int(r["mb_class"]), k)
+        if k != 0:
+            assert int(r["mb_type"]) == int(g["mb_type"][n, a]), (what, n, a, "mb_type")
+        if k in (0, 1):
+            npart = int(g["nparts"][n, a, 0])
+            for p in range(npart):
+                for q in range(int(g["nparts"][n, a, 1 + p])):
+                    assert tuple(r["mv"][p, q]) == tuple(g["mv"][n, a, p, q]), (what, n, a, "mv", p, q)
+                    if k == 1:
+                        assert tuple(r["mvd"][p, q]) == tuple(g["mvd"][n, a, p, q]), (what, n, a, "mvd", p, q)
+        assert (int(r["coded_block_pattern"]), int(r["cbp_luma"]), int(r["cbp_chroma"])) == tuple(int(v) for v in g["cbp"][n, a]), (what, n, a, "cbp")
+        if k == 3:
+            assert np.array_equal(r["i4_pred_mode"], g["i4_mode"][n, a]), (what, n, a, "i4 modes")
+        assert level_md5(k, r) == str(g["level_md5"][n, a]), (what, n, a, "levels")
+
+
+def run_emu(w, h, frames, qp, me_range, yuv_frames, tag):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools", "emu"), "emu"], stdout=subprocess.DEVNULL)
+    from hartallo_b200 import lib as hl
+    pre = "/tmp/test_emu_" + tag
+    with open(pre + ".yuv", "wb") as f:
+        for fr in yuv_frames:
+            f.write(fr.tobytes())
+    subprocess.check_call([os.path.join(ROOT, "tools", "emu", "emu"), "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp),
+                           "--me-range", str(me_range), "--in", pre + ".yuv", "--out", pre], stdout=subprocess.DEVNULL)
+    nmb = (w // 16) * (h // 16)
+    rec = np.fromfile(pre + ".rec", hl.MB_RECORD).reshape(frames, nmb)
+    recon = np.fromfile(pre + ".recon", np.uint8).reshape(frames, -1)
+    return rec, recon
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_control_flow_vs_reference_cpu(name):
+    g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
+    w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
+    fr = frames_of(str(g["gen"]), seed, w, h, frames)
+    rec, recon = run_emu(w, h, frames, qp, me_range, fr, name)
+    for n in range(frames):
+        check_frame(g, n, rec[n], recon[n], "emu/" + name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CONFIGS)
+def test_slice_encode_vs_reference(name):
+    from hartallo_b200 import lib as hl
+    g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
+    w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
+    fr = frames_of(str(g["gen"]), seed, w, h, frames)
+    enc = hl.Encoder(w, h, qp=qp, me_range=me_range)
+    for n in range(frames):
+        rec, recon = enc.encode(fr[n], want_recon=True)
+        check_frame(g, n, rec, recon, "gpu/" + name)
+    enc.close()
+
+
+@pytest.mark.gpu
+def test_slice_encode_batch_of_streams():
+    """several independent streams (different sizes and contents) in one launch give the same pictures as one by one"""
+    from hartallo_b200 import lib as hl
+    names = ["g2_qcif", "g1_qcif", "g2_small_q12"]
+    gs = [np.load(os.path.join(GOLD, "encoder_%s.npz" % n)) for n in names]
+    encs, frs = [], []
+    for g in gs:
+        w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
+        encs.append(hl.Encoder(w, h, qp=qp, me_range=me_range))
+        frs.append(frames_of(str(g["gen"]), seed, w, h, frames))
+    for n in range(5):
+        ps = hl.encode_batch(encs, [f[n] for f in frs])
+        for i, (e, g) in enumerate(zip(encs, gs)):
+            hl.check(e.st.lib.hlb200_stream_sync(encs[0].st.ctx), "sync")
+            rec = np.zeros(e.st.nmb, hl.MB_RECORD)
+            hl.check(e.st.lib.hlb200_records_download(e.st.ctx, hl.ptr(rec)), "records_download")
+            check_frame(g, n, rec, e.st.download_slot(ps[i].cur_slot), "batch/" + names[i])
+    for e in encs:
+        e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not rt.have_driver(), reason="oracle/_ref/hl_ref_driver not built")
+def test_slice_encode_vs_live_reference():
+    """fresh seed, reference run live beside the device path: reconstruction MD5 of every picture"""
+    from hartallo_b200 import lib as hl
+    w, h, frames, qp, me_range, seed = 176, 144, 4, 27, 24, 11
+    rt.run_driver("/tmp/live_ref", w, h, frames, gen="g2", seed=seed, qp=qp, me_range=me_range, levels=False)
+    ref = np.fromfile("/tmp/live_ref.recon", np.uint8).reshape(frames, -1)
+    fr = frames_of("g2", seed, w, h, frames)
+    enc = hl.Encoder(w, h, qp=qp, me_range=me_range)
+    for n in range(frames):
+        _, recon = enc.encode(fr[n], want_recon=True)
+        assert np.array_equal(recon, ref[n]), n
+    enc.close()
