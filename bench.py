@@ -180,7 +180,158 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# our arm
+# our arm, workload "slice": hlb200_slice_encode_batch_async = the whole per-MB decide + reconstruct loop on the device
+# ------------------------------------------------------------------------------------------------------------------
+def measure_int_peak(torch, hl, lib, dev, stream, sp):
+    sink = torch.empty(148 * 16 * 256, dtype=torch.int32, device=dev)
+    ops = C.c_uint64(0)
+    best = 0.0
+    for _ in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        hl.check(lib.hlb200_dev_int_alu_probe(148 * 16, 4096, sink.data_ptr(), sp, C.byref(ops)), "int_alu_probe")
+        b.record(stream)
+        torch.cuda.synchronize()
+        best = max(best, ops.value / (a.elapsed_time(b) * 1e-3) / 1e9)
+    return best
+
+
+def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, stream, sp):
+    S, K, Wm = args.streams, args.steps, args.warmup
+    ysz, csz = W * H, W * H // 4
+    frame_b = ysz + 2 * csz
+    nfr = 1 + Wm + K + 1                 # IDR + warm-up + timed + 1 spare
+    # ---- S independent streams: own context, frame stores, per-MB state; own synthetic sequence (G1, distinct seeds) ----
+    encs, d_frames, h_frames = [], [], []
+    for s_i in range(S):
+        e = hl.Encoder(W, H, qp=QP, me_range=ME_RANGE, refs=1, device=local)
+        hl.check(lib.hlb200_stream_set_cuda_stream(e.st.ctx, sp), "set_cuda_stream")
+        encs.append(e)
+        g = synth.G1(W, H, seed=12345 + 7919 * (rank * S + s_i))
+        fr = [g.next() for _ in range(nfr)]
+        d_frames.append([torch.from_numpy(f).to(dev) for f in fr])
+        if s_i < 2:
+            h_frames.append(fr)
+    e2e_frames = min(nfr, 6)
+    pinned = [[torch.from_numpy(h_frames[s_i % 2][n]).pin_memory() for n in range(e2e_frames)] for s_i in range(2)]
+
+    def set_src(s_i, n):
+        b = d_frames[s_i][n].data_ptr()
+        hl.check(lib.hlb200_frame_set_device(encs[s_i].st.ctx, b, b + ysz, b + ysz + csz), "frame_set_device")
+
+    def step(n):
+        for s_i in range(S):
+            set_src(s_i, n)
+        return hl.encode_batch(encs, [None] * S)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step(0)                                # IDR pictures
+    for i in range(Wm):
+        step(1 + i)
+    barrier()
+    encs[0].st.slice_status()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    t0 = time.perf_counter()
+    evs[0].record(stream)
+    last = None
+    for i in range(K):
+        last = step(1 + Wm + i)
+        evs[i + 1].record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    encs[0].st.slice_status()
+    ms = torch.tensor([evs[0].elapsed_time(evs[K])], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    value = world * S * NMB * K / (ms_total * 1e-3)
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+
+    # ---- algorithmic work of the last timed launch: the reference trajectory's trial encodes (identical by parity) ----
+    trials = interp = cands = intra = 0
+    kinds = np.zeros(4, np.int64)
+    for e in encs:
+        rec = np.zeros(NMB, hl.MB_RECORD)
+        hl.check(lib.hlb200_records_download(e.st.ctx, hl.ptr(rec)), "records_download")
+        trials += int(rec["me_trials"].sum()); interp += int(rec["me_interp_ops"].sum()); cands += int(rec["me_candidates"].sum()); intra += int(rec["intra_trials"].sum())
+        kinds += np.bincount(rec["mb_class"], minlength=4)[:4]
+    ops = (trials + intra) * 560 + interp
+    int_peak = measure_int_peak(torch, hl, lib, dev, stream, sp)
+    kms = step_ms[-1]
+    ach = ops / (kms * 1e-3) / 1e9
+    roof = {"kernel": "k_slice_encode", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak, "traffic": None, "ms": kms,
+            "peak_kind": "measured live (hlb200_dev_int_alu_probe: dependency-free IADD3/LOP3)", "algorithmic_ops_per_launch": ops,
+            "per_mb": {"me_candidates": cands / (S * NMB), "me_trials": trials / (S * NMB), "intra_trials": intra / (S * NMB), "int_ops": ops / (S * NMB)},
+            "note": "ops = (ME + intra 4x4 trial encodes) x 560 + interpolation ops by fractional class (SURVEY.md Appendix D), counted on the reference trajectory"}
+
+    # ---- end to end through the host-buffer C-ABI: upload of every source picture, download of every decision record ----
+    h_rec = [torch.empty(NMB * hl.MB_RECORD.itemsize, dtype=torch.uint8).pin_memory() for _ in range(S)]
+
+    def e2e_step(n):
+        for s_i, e in enumerate(encs):
+            f = pinned[s_i % 2][n % e2e_frames].numpy()
+            hl.check(lib.hlb200_frame_upload(e.st.ctx, hl.ptr(f[:ysz]), hl.ptr(f[ysz:ysz + csz]), hl.ptr(f[ysz + csz:]), W, W // 2), "frame_upload")
+        ps = (hl.SliceParams * S)()
+        ctxs = (C.c_void_p * S)()
+        for i, e in enumerate(encs):
+            p = e.params()
+            C.memmove(C.byref(ps[i]), C.byref(p), C.sizeof(hl.SliceParams))
+            ctxs[i] = e.st.ctx
+        hl.check(lib.hlb200_slice_encode_batch_async(ctxs, ps, S), "slice_encode_batch_async")
+        for i, e in enumerate(encs):
+            e.advance(ps[i])
+            hl.check(lib.hlb200_records_download(e.st.ctx, h_rec[i].data_ptr()), "records_download")
+    for i in range(2):
+        e2e_step(1 + i)
+    barrier()
+    te = time.perf_counter()
+    for i in range(K):
+        e2e_step(3 + i)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - te) * 1e3], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * NMB * K / (float(e2e_ms.item()) * 1e-3)
+    for e in encs:
+        e.close()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "%d independent 1080p (1920x1088) synthetic G1 YUV 4:2:0 streams per GPU, one P picture of each per step (one launch): Baseline/CAVLC "
+                                       "tools, 4x4 transform, 1 ref, quarter-pel ME +-%d over all 7 partition modes with the reference's RD cost, intra decision, "
+                                       "reconstruction; QP %d" % (S, ME_RANGE, QP),
+                           "l2": "inputs larger than L2: %d streams x (source + 2 frame stores + records + state) = %.0f MB touched per step, new source pictures every step" %
+                                 (S, S * (3 * frame_b + NMB * (hl.MB_RECORD.itemsize + 392)) / 1e6),
+                           "sharding": "independent streams per GPU, no collective", "parity": "bit-exact vs the reference encoder (tests/test_encoder.py)",
+                           "mb_classes_last_step": {"pskip": int(kinds[0]), "inter": int(kinds[1]), "i16": int(kinds[2]), "i4": int(kinds[3])}},
+                "clocks": clk, "gpu_launches": 2 * K,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * frame_b), "d2h_bytes_per_step": int(S * NMB * hl.MB_RECORD.itemsize),
+                        "ms_per_step": float(e2e_ms.item()) / K,
+                        "api": "hlb200_frame_upload (pinned host pictures) + hlb200_slice_encode_batch_async + hlb200_records_download (decision records to the host writer)"},
+                "roofline": roof, "step_ms": step_ms}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm, workload "batch" (stateless whole-frame kernels; kept for the HBM-roofline figures of interpolation / transform)
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -188,7 +339,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="batch", choices=["batch", "slice"])
+    ap.add_argument("--workload", default="slice", choices=["batch", "slice"])
+    ap.add_argument("--streams", type=int, default=16, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -211,6 +363,8 @@ def main():
     hl.check(lib.hlb200_init(local), "hlb200_init")
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
+    if args.workload == "slice":
+        return slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, stream, sp)
 
     # ---- synthetic pictures: `sets` (reference, source) pairs of consecutive G1 frames, distinct per rank ----
     g = synth.G1(W, H, seed=12345 + rank)

@@ -74,6 +74,7 @@ int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out
     c->own_stream = true;
     for (int p = 0; p < 3; ++p) {
         HLB_CUDA(cudaMalloc(&c->d_src[p], plane_bytes(c, p)));
+        c->d_src_cur[p] = c->d_src[p];
         HLB_CUDA(cudaMalloc(&c->d_pred[p], plane_bytes(c, p)));
         HLB_CUDA(cudaMalloc(&c->d_tmp[p], plane_bytes(c, p)));
         for (int s = 0; s < c->nslots; ++s) {
@@ -130,7 +131,15 @@ int hlb200_frame_upload(hlb200_ctx_t* c, const uint8_t* y, const uint8_t* u, con
     for (int p = 0; p < 3; ++p) {
         const int w = p ? c->width >> 1 : c->width, hh = p ? c->height >> 1 : c->height, st = p ? stride_c : stride_y;
         HLB_CUDA(cudaMemcpy2DAsync(c->d_src[p], w, h[p], st, w, hh, cudaMemcpyHostToDevice, c->stream));
+        c->d_src_cur[p] = c->d_src[p];
     }
+    return HLB200_OK;
+}
+
+int hlb200_frame_set_device(hlb200_ctx_t* c, const uint8_t* d_y, const uint8_t* d_u, const uint8_t* d_v)
+{
+    if (!c || !d_y || !d_u || !d_v) return HLB200_ERR_INVALID_PARAMETER;
+    c->d_src_cur[0] = d_y; c->d_src_cur[1] = d_u; c->d_src_cur[2] = d_v;
     return HLB200_OK;
 }
 

@@ -68,7 +68,8 @@ struct hlb200_ctx {
     int max_refs, nslots;
     cudaStream_t stream;
     bool own_stream;
-    uint8_t* d_src[3];                          // source frame planes
+    uint8_t* d_src[3];                          // source frame planes (owned)
+    const uint8_t* d_src_cur[3];                // planes the next slice reads: d_src, or caller-owned device planes (hlb200_frame_set_device)
     uint8_t* d_slot[HLB200_MAX_REFS + 1][3];    // frame stores: tight planes, pitch = width (dpb.c:88-166)
     uint8_t* d_pred[3];                         // scratch prediction planes (batch kernels)
     uint8_t* d_tmp[3];                          // scratch output planes (batch kernels)

@@ -118,6 +118,7 @@ struct MbWork {
     uint8_t tc_cac[2][4];
     uint8_t cbp_gate;      // CodedBlockPatternLuma as left by the previous picture (gate of in-MB neighbours, utils.h:10-20)
     int8_t extA[16], extB[16];   // nA / nB contributed by the neighbouring macroblocks (-1 = not available), per luma4x4BlkIdx on the MB edge
+    unsigned stat_trials, stat_interp, stat_cands, stat_intra;   // work counters of the trajectory (roofline accounting)
     int stuck;             // set when a search loop exceeded its iteration cap (cannot happen for a finite window; watchdog aid)
     int last_sctr;         // rdo.Single_ctr chain; -1 = not yet written by this macroblock
     int need_prev_sctr;    // set when the chain value of the raster predecessor was consumed
@@ -412,8 +413,14 @@ HLB_FN void me_eval(X& x, MbWork& w)
 {
     const int nblk = (w.part_w >> 2) * (w.part_h >> 2);
     x.run(CMD_ME_EVAL, w.ncand * nblk < 16 ? 16 : w.ncand * nblk);  // the scan phase needs one lane per luma block
-    for (int c = 0; c < w.ncand; ++c)
+    for (int c = 0; c < w.ncand; ++c) {
         if (w.c_last[c] >= 0) w.last_sctr = w.c_last[c];
+        // interpolation ops per 4x4 block by fractional class
+        const int xf = w.cmvx[c] & 3, yf = w.cmvy[c] & 3;
+        const int cls = (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
+        w.stat_interp += (unsigned)(cls * nblk);
+    }
+    w.stat_trials += (unsigned)(w.ncand * nblk); w.stat_cands += (unsigned)w.ncand;
 }
 
 HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
@@ -811,6 +818,7 @@ HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb)
         w.extB[blk] = (int8_t)((by == 0) ? (w.availB ? nb_count(f.st[mb - f.mbw], blk_idx_from_xy(bx, 12)) : -1) : 0);
     }
     w.last_sctr = -1; w.need_prev_sctr = 0; w.stuck = 0;
+    w.stat_trials = w.stat_interp = w.stat_cands = w.stat_intra = 0;
     w.mb_is_intra = 0;
 }
 
@@ -835,6 +843,7 @@ HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int 
         for (int q = 0; q < 4; ++q)
             for (int k = 0; k < 2; ++k) { r.mv[p][q][k] = w.fin_mv[p][q][k]; r.mvd[p][q][k] = mvd ? mvd[p][q][k] : 0; }
     r.mad = mad;
+    r.me_trials = w.stat_trials; r.me_interp_ops = w.stat_interp; r.me_candidates = (uint16_t)w.stat_cands; r.intra_trials = (uint16_t)w.stat_intra;
     for (int b = 0; b < 16; ++b)
         for (int i = 0; i < 16; ++i) { r.luma_level[b][i] = w.luma_level[b][i]; r.i16_ac_level[b][i] = w.i16_ac[b][i]; }
     for (int i = 0; i < 16; ++i) r.i16_dc_level[i] = w.i16_dc[i];

@@ -246,6 +246,7 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
         if (need) w.arg1 = x.prev_sctr(w.mb);
     }
     x.run(CMD_I16_RATE, 64);
+    for (int m = 0; m < 4; ++m) w.stat_intra += w.t_mode_ok[m] ? 16u : 0u;
     double best16 = DBL_MAX;
     int dist16 = 0;
     w.i16_mode = 2; w.i16_cbp4x4 = 0;
@@ -277,6 +278,7 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
             w.i4_blk = blk;
             w.i4_mode[blk] = 2;
             x.run(CMD_I4_EVAL, 9);
+            for (int m = 0; m < 9; ++m) w.stat_intra += w.q_ok[m] ? 1u : 0u;
             double min_cost = DBL_MAX, min_dist = 0;
             int best_mode = 2, best_allzero = 1;
             const int nC = luma_nc(w, w.tc, blk);

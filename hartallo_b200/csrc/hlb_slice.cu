@@ -216,7 +216,7 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     f.num_refs = f.is_p ? p->num_refs : 0;
     if (f.is_p && (f.num_refs < 1 || f.num_refs > c->max_refs)) return HLB200_ERR_INVALID_PARAMETER;
     f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));                       // slice.c:1766 (integer division in the exponent)
-    for (int k = 0; k < 3; ++k) { f.src[k] = c->d_src[k]; f.cur[k] = c->d_slot[p->cur_slot][k]; }
+    for (int k = 0; k < 3; ++k) { f.src[k] = c->d_src_cur[k]; f.cur[k] = c->d_slot[p->cur_slot][k]; }
     for (int u = 0; u < f.num_refs; ++u) {
         const int s = p->ref_slot[u];
         if (s < 0 || s >= c->nslots || s == p->cur_slot) return HLB200_ERR_INVALID_PARAMETER;

@@ -26,7 +26,8 @@ MB_RECORD = np.dtype([
     ("prev_intra4x4_pred_mode_flag", "u1", (16,)), ("rem_intra4x4_pred_mode", "u1", (16,)), ("pad", "u1", (3,)),
     ("mv", "<i2", (4, 4, 2)), ("mvd", "<i2", (4, 4, 2)), ("mad", "<i4"),
     ("luma_level", "<i2", (16, 16)), ("i16_dc_level", "<i2", (16,)), ("i16_ac_level", "<i2", (16, 16)),
-    ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16))], align=True)
+    ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16)),
+    ("me_trials", "<u4"), ("me_interp_ops", "<u4"), ("me_candidates", "<u2"), ("intra_trials", "<u2")], align=True)
 
 
 class SliceParams(C.Structure):
@@ -49,7 +50,7 @@ def load():
     sig = {
         "hlb200_init": [ip], "hlb200_device_count": [], "hlb200_version": [],
         "hlb200_stream_create": [ip, ip, ip, C.POINTER(vp)], "hlb200_stream_destroy": [vp], "hlb200_stream_set_cuda_stream": [vp, vp],
-        "hlb200_stream_sync": [vp], "hlb200_frame_upload": [vp, vp, vp, vp, ip, ip], "hlb200_slot_upload": [vp, ip, vp, vp, vp],
+        "hlb200_stream_sync": [vp], "hlb200_frame_upload": [vp, vp, vp, vp, ip, ip], "hlb200_frame_set_device": [vp, vp, vp, vp], "hlb200_slot_upload": [vp, ip, vp, vp, vp],
         "hlb200_slot_download": [vp, ip, vp, vp, vp], "hlb200_state_reset": [vp],
         "hlb200_slice_encode": [vp, C.POINTER(SliceParams), vp], "hlb200_slice_encode_async": [vp, C.POINTER(SliceParams)], "hlb200_records_download": [vp, vp],
         "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_status": [vp, vp],

@@ -94,6 +94,11 @@ typedef struct hlb200_mb_record {
     int16_t i16_ac_level[16][16];     /* Intra16x16ACLevel (15 used) */
     int16_t chroma_dc_level[2][4];    /* ChromaDCLevel */
     int16_t chroma_ac_level[2][4][16];/* ChromaACLevel (15 used) */
+    /* work the reference trajectory performed for this macroblock (roofline accounting) */
+    uint32_t me_trials;               /* 4x4 trial encodes of the motion search */
+    uint32_t me_interp_ops;           /* integer ops of the interpolation of those blocks, by fractional class */
+    uint16_t me_candidates;           /* candidate motion vectors costed */
+    uint16_t intra_trials;            /* 4x4 trial encodes of the intra decision */
 } hlb200_mb_record_t;
 
 typedef struct hlb200_slice_params {
@@ -146,6 +151,8 @@ HLB200_API int hlb200_stream_set_cuda_stream(hlb200_ctx_t* ctx, void* cuda_strea
 HLB200_API int hlb200_stream_sync(hlb200_ctx_t* ctx);
 /* source frame (hl_frame_video_t::data_ptr[0..2], include/hartallo/hl_frame.h:28-41) -> device */
 HLB200_API int hlb200_frame_upload(hlb200_ctx_t* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v, int stride_y, int stride_c);
+/* source frame already resident on the device (tight planes, pitch = width); caller-owned, must stay valid until the slice has run */
+HLB200_API int hlb200_frame_set_device(hlb200_ctx_t* ctx, const uint8_t* d_y, const uint8_t* d_u, const uint8_t* d_v);
 /* frame-store planes (DPB layout source/h264/hl_codec_264_dpb.c:88-166: tight Y|U|V, stride = width) */
 HLB200_API int hlb200_slot_upload(hlb200_ctx_t* ctx, int slot, const uint8_t* y, const uint8_t* u, const uint8_t* v);
 HLB200_API int hlb200_slot_download(hlb200_ctx_t* ctx, int slot, uint8_t* y, uint8_t* u, uint8_t* v);

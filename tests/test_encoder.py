@@ -138,3 +138,19 @@ def test_slice_encode_vs_live_reference():
         _, recon = enc.encode(fr[n], want_recon=True)
         assert np.array_equal(recon, ref[n]), n
     enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gen", ["g1", "g2"])
+def test_slice_encode_1080p_recon_md5(gen):
+    """BASELINE.json's full size (1920x1088, ME +-32): reconstruction MD5 of an IDR and a P picture against the reference's"""
+    import json
+    from hartallo_b200 import lib as hl
+    gold = json.load(open(os.path.join(GOLD, "encoder_1080p.json")))
+    c = gold["config"]
+    fr = frames_of(gen, c["seed"], c["w"], c["h"], c["frames"])
+    enc = hl.Encoder(c["w"], c["h"], qp=c["qp"], me_range=c["me_range"])
+    for n in range(c["frames"]):
+        _, recon = enc.encode(fr[n], want_recon=True)
+        assert hashlib.md5(recon.tobytes()).hexdigest() == gold["recon_md5"][gen][n], (gen, n)
+    enc.close()
