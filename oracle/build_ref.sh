@@ -46,4 +46,14 @@ if [ -f "$HERE/ref_kernels.c" ]; then
   gcc $CF -c "$HERE/ref_kernels.c" -o "$TMP/obj_kernels.o"
   gcc -shared -o "$OUT/libref_kernels.so" "$TMP/obj_kernels.o" -Wl,--whole-archive "$OUT/libhartallo_ref.a" -Wl,--no-whole-archive -lpthread -lm -ldl
 fi
+# the reference host code with the B200 hot path dropped in (host/hlb200_glue.c + libhl_b200.so): used by the bitstream-MD5 parity test
+GLUE="$HERE/../host/hlb200_glue.c"
+if [ -f "$GLUE" ] && [ -f "$HERE/ref_driver.c" ]; then
+  gcc $CF -DHL_DRIVER_NO_WRAPS -c "$HERE/ref_driver.c" -o "$TMP/obj_driver_nw.o"
+  gcc $CF -I"$HERE/../include" -c "$GLUE" -o "$TMP/obj_glue.o"
+  GW="-Wl,--wrap=hl_codec_264_nal_slice_data_encode -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc"
+  # libhl_b200.so is resolved at run time relative to the binary (oracle/_ref -> hartallo_b200)
+  gcc "$TMP/obj_driver_nw.o" "$TMP/obj_glue.o" $GW "$OUT/libhartallo_ref.a" -L"$HERE/../hartallo_b200" -lhl_b200 -Wl,-rpath,'$ORIGIN/../../hartallo_b200' -lpthread -lm -ldl -o "$OUT/hl_b200_encoder" \
+    || echo "build_ref: hl_b200_encoder not linked (build hartallo_b200/libhl_b200.so first)" >&2
+fi
 echo "build_ref: built $(ls "$OUT")"

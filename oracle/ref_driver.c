@@ -76,6 +76,7 @@ static int32_t traced_sad(const uint8_t* b1, int32_t s1, const uint8_t* b2, int3
     return v;
 }
 
+#ifndef HL_DRIVER_NO_WRAPS   /* tracing wrappers (oracle); the glue build (host/hlb200_glue.c) provides its own hooks instead */
 extern HL_ERROR_T __real_hl_codec_264_interpol_luma(hl_codec_264_t*, hl_codec_264_mb_t*, int32_t, int32_t,
         const hl_codec_264_mv_xt*, const hl_pixel_t*, void*, int32_t);
 HL_ERROR_T __wrap_hl_codec_264_interpol_luma(hl_codec_264_t* p_codec, hl_codec_264_mb_t* p_mb, int32_t mbPartIdx,
@@ -255,6 +256,8 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
     return err;
 }
 
+#endif /* HL_DRIVER_NO_WRAPS */
+
 /* ------------------------------------------------------------------------------------------------------------ */
 /* Synthetic inputs, SURVEY.md 8(d).  Mirrored bit-for-bit by hartallo_b200/synth.py.                            */
 static uint32_t g_lcg = 12345u;
@@ -367,7 +370,9 @@ int main(int argc, char** argv)
     hl_debug_set_level(HL_DEBUG_LEVEL_ERROR);
     hl_engine_set_cpu_flags(0);                       /* pure C path: the oracle */
     if ((err = hl_engine_init())) { fprintf(stderr, "engine init %d\n", err); return 1; }
+#ifndef HL_DRIVER_NO_WRAPS
     if (g_trace_cand) { g_real_sad = hl_math_sad4x4_u8; hl_math_sad4x4_u8 = traced_sad; }
+#endif
     if ((err = hl_codec_plugin_find(HL_CODEC_TYPE_H264_SVC, &plugin))) { fprintf(stderr, "plugin find %d\n", err); return 1; }
     if ((err = hl_codec_create(plugin, &codec))) { fprintf(stderr, "codec create %d\n", err); return 1; }
     if ((err = hl_codec_result_create(&result))) return 1;

@@ -154,3 +154,23 @@ def test_slice_encode_1080p_recon_md5(gen):
         _, recon = enc.encode(fr[n], want_recon=True)
         assert hashlib.md5(recon.tobytes()).hexdigest() == gold["recon_md5"][gen][n], (gen, n)
     enc.close()
+
+
+B200_ENCODER = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(B200_ENCODER), reason="oracle/_ref/hl_b200_encoder not built (needs the reference tree at build time)")
+@pytest.mark.parametrize("name", CONFIGS)
+def test_bitstream_md5_drop_in(name):
+    """The drop-in itself: the reference's unmodified host code (headers, CAVLC writer, DPB bookkeeping) linked with
+    host/hlb200_glue.c + libhl_b200.so must emit the same bitstream, byte for byte, as the all-CPU reference
+    (counterpart of source/test_encoder.c, which writes ./encoder.264 and checks nothing)."""
+    import json
+    g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
+    w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
+    out = subprocess.run([B200_ENCODER, "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", "1",
+                          "--gen", str(g["gen"]), "--seed", str(seed)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stderr[-500:]
+    got = json.loads(out.stdout.strip().splitlines()[-1])
+    assert got["md5"] == str(g["bitstream_md5"]), (got, str(g["bitstream_md5"]))
