@@ -21,11 +21,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    extra = ["-DHLB_SLICE_MIN_CTAS=" + os.environ["HLB_SLICE_MIN_CTAS"]] if os.environ.get("HLB_SLICE_MIN_CTAS") else []
+    if os.environ.get("HLB_WORKERS"):
+        extra.append("-DHLB_WORKERS=" + os.environ["HLB_WORKERS"])
+    extra += os.environ.get("HLB_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out or OUT]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
@@ -38,5 +42,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
-    print(OUT)
+    o = [a for a in sys.argv[1:] if a.endswith(".so")]
+    build(force=True, verbose="-v" in sys.argv, out=o[0] if o else None)
+    print(o[0] if o else OUT)

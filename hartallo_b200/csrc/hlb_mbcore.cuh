@@ -48,8 +48,8 @@ struct MbState {
     uint8_t i4_mode[16];   // Intra4x4PredMode
     uint8_t last_sctr;     // pc_esd->rdo.Single_ctr after this macroblock (a chain through raster order, residual.c:882)
     uint8_t pad[3];
-    int16_t mv[4][4][2];       // MvL0
-    int16_t chroma_ac[2][4][16];  // ChromaACLevel (persistent: only rewritten for blocks with a non-zero residual, rdo.c:2577)
+    alignas(4) int16_t mv[4][4][2];       // MvL0
+    alignas(4) int16_t chroma_ac[2][4][16];  // ChromaACLevel (persistent: only rewritten for blocks with a non-zero residual, rdo.c:2577)
     int16_t chroma_dc[2][4];      // ChromaDCLevel
 };
 
@@ -76,8 +76,12 @@ HLB_HD void mode_rect(int m, int part, int sub, int& ox, int& oy, int& w, int& h
 {
     const int pw = mode_part_w(m), ph = mode_part_h(m);
     w = mode_sub_w(m); h = mode_sub_h(m);
-    ox = (part % (16 / pw)) * pw; oy = (part / (16 / pw)) * ph;
-    if (m > 3) { ox += (sub % (8 / w)) * w; oy += (sub / (8 / w)) * h; }
+    if (pw == 16) { ox = 0; oy = part * ph; }
+    else { ox = (part & 1) * 8; oy = ph == 16 ? 0 : (part >> 1) * 8; }
+    if (m > 3) {
+        if (w == 8) oy += sub * h;
+        else { ox += (sub & 1) * 4; oy += h == 8 ? 0 : (sub >> 1) * 4; }
+    }
 }
 // (mbPartIdx, subMbPartIdx) covering luma position (x,y) for a geometry given as part_mode + sub_mode[] (6.4.12.4, mb.h:313)
 HLB_HD void part_at(int part_mode, const uint8_t* sub_mode, int x, int y, int& part, int& sub)
@@ -101,7 +105,9 @@ HLB_HD void part_at(int part_mode, const uint8_t* sub_mode, int x, int y, int& p
 }
 
 #define HLB_MAXC 9
-enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_LUMA, CMD_CHROMA, CMD_STORE, CMD_I16_EVAL, CMD_I16_RATE, CMD_I16_RECON, CMD_I4_EVAL, CMD_I4_COMMIT, CMD_PRED_CHROMA_INTRA };
+#define HLB_MB_LANES 160   /* lanes a command needs at most = worker threads of the GPU CTA */
+#define HLB_TILE 48   /* side of the shared-memory reference tile: partition (16) + 6-tap halo (5) + +-13 pixels of search freedom */
+enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_TILE, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_LUMA, CMD_CHROMA, CMD_STORE, CMD_I16_EVAL, CMD_I16_RATE, CMD_I16_RECON, CMD_I4_EVAL, CMD_I4_COMMIT, CMD_PRED_CHROMA_INTRA };
 
 // Scratch of the macroblock being encoded (shared memory on the GPU)
 struct MbWork {
@@ -118,29 +124,37 @@ struct MbWork {
     uint8_t tc_cac[2][4];
     uint8_t cbp_gate;      // CodedBlockPatternLuma as left by the previous picture (gate of in-MB neighbours, utils.h:10-20)
     int8_t extA[16], extB[16];   // nA / nB contributed by the neighbouring macroblocks (-1 = not available), per luma4x4BlkIdx on the MB edge
+    unsigned prof_run_cycles, prof_runs, prof_me_cycles;   // HLB_PROFILE_STEPS builds only
     unsigned stat_trials, stat_interp, stat_cands, stat_intra;   // work counters of the trajectory (roofline accounting)
     int stuck;             // set when a search loop exceeded its iteration cap (cannot happen for a finite window; watchdog aid)
     int last_sctr;         // rdo.Single_ctr chain; -1 = not yet written by this macroblock
     int need_prev_sctr;    // set when the chain value of the raster predecessor was consumed
-    int16_t chroma_ac[2][4][16];
+    alignas(4) int16_t chroma_ac[2][4][16];   // copied with 32-bit accesses
     int16_t chroma_dc[2][4];
     // ---- ME ----
     int mode, ref;
     const uint8_t* ref_y;
-    int16_t mv_cur[4][4][2];   // (*MvL0) of the current macroblock during the search
+    alignas(4) int16_t mv_cur[4][4][2];   // (*MvL0) of the current macroblock during the search
     int8_t ref_cur[4];         // RefIdxL0 of the current macroblock (stale during the search)
     int16_t mvp[4][4][2];
     int16_t best_mv[4][4][2];
     double best_cost[4][4];
     int best_dist[4][4], best_sctr[4][4], best_cbp[4][4];
     int probably_pskip;
+    // reference tile: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)] (per-sample clamp of interpol.c:108-131)
+    int tile_x0, tile_y0, tile_ref, tile_valid;
+    uint8_t tile[HLB_TILE * HLB_TILE];
     // one evaluation step
+    int c_begin, c_end;        // candidates evaluated by the current CMD_ME_EVAL
     int part_ox, part_oy, part_w, part_h, ncand;
     int16_t cmvx[HLB_MAXC], cmvy[HLB_MAXC];
-    int32_t r_dist[HLB_MAXC][16];
-    uint16_t r_bits[HLB_MAXC][16];
-    uint8_t r_tc[HLB_MAXC][16], r_t1[HLB_MAXC][16], r_sctr[HLB_MAXC][16], r_nz[HLB_MAXC][16], eff[HLB_MAXC][16];
-    int32_t c_dist[HLB_MAXC], c_rbc[HLB_MAXC], c_sctr[HLB_MAXC], c_cbp[HLB_MAXC], c_last[HLB_MAXC];
+    uint8_t r_tc[HLB_MAXC][16], r_t1[HLB_MAXC][16], r_nz[HLB_MAXC][16], eff[HLB_MAXC][16];
+    int32_t c_dist[HLB_MAXC], c_rbc[HLB_MAXC], c_sctr[HLB_MAXC], c_cbp[HLB_MAXC];
+    double c_cost[HLB_MAXC];
+    int step_last;             // ((c+1) << 12 | k << 8 | Single_ctr) of the last non-zero trial block of the step, -1 if none
+    int bw_log2, nblk_log2;    // log2 of the partition width / size in 4x4 blocks
+    uint8_t pat_ok[HLB_MAXC], cidx[HLB_MAXC];
+    int16_t pat_mv[HLB_MAXC][2];
     // ---- reconstruction ----
     int fin_mode, fin_sub[4];          // committed geometry (part_mode, sub_mode[])
     int16_t fin_mv[4][4][2];
@@ -149,7 +163,7 @@ struct MbWork {
     uint8_t pred_c[2][64];
     uint8_t rec_y[256];
     uint8_t rec_c[2][64];
-    int16_t luma_level[16][16];
+    alignas(4) int16_t luma_level[16][16];
     int luma_skip_residual;            // Single_ctr_luma < 6 (rdo.c:2419)
     int cbp_luma4x4;
     int cbp_ac[2], cbp_dc[2];
@@ -159,7 +173,7 @@ struct MbWork {
     // ---- intra ----
     int i16_mode, i16_cbp4x4, i4_cbp4x4, intra_chroma_mode;
     int16_t i16_dc[16];
-    int16_t i16_ac[16][16];
+    alignas(4) int16_t i16_ac[16][16];
     uint8_t i4_mode[16], prev_i4[16], rem_i4[16];
     int32_t p33[33];
     int32_t p17[2][17];
@@ -314,15 +328,45 @@ HLB_HD void pred_luma_4x4(const FrameCtx& f, const uint8_t* ref_y, int mbx, int 
 // ------------------------------------------------------------------------------------------------------------------
 // CMD_ME_EVAL: the trial encodes of one search step (me_ds.c:527-688 for every candidate of the step)
 // ------------------------------------------------------------------------------------------------------------------
+// origin (after the partition-origin clip of pred_inter.c:395-396) of candidate c's partition in picture coordinates
+HLB_HD void cand_origin(const MbWork& w, const FrameCtx& f, int c, int& X, int& Y)
+{
+    X = clip3(-17, f.W + 17, w.mbx * 16 + w.part_ox + (w.cmvx[c] >> 2));
+    Y = clip3(-17, f.H + 17, w.mby * 16 + w.part_oy + (w.cmvy[c] >> 2));
+}
+// CMD_TILE: lanes stride over the tile
+HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
+{
+    const uint8_t* plane = w.ref_y;
+    const int nl = w.arg0_lanes;
+    for (int i = lane; i < HLB_TILE * HLB_TILE; i += nl) {
+        const int ty = i / HLB_TILE, tx = i - ty * HLB_TILE;
+        const int y = clip3(0, f.H - 1, w.tile_y0 + ty), x = clip3(0, f.W - 1, w.tile_x0 + tx);
+        w.tile[i] = HLB_LDG(plane + y * f.W + x);
+    }
+}
+// sums shared by the lanes of one candidate (shared-memory atomics on the GPU, plain read-modify-write in the emulation)
+#if defined(__CUDA_ARCH__)
+#define HLB_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define HLB_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define HLB_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#else
+#define HLB_ATOMIC_ADD(p, v) (*(p) += (v))
+#define HLB_ATOMIC_OR(p, v) (*(p) |= (v))
+#define HLB_ATOMIC_MAX(p, v) (*(p) = *(p) > (v) ? *(p) : (v))
+#endif
+// CMD_ME_EVAL: lane = (candidate - c_begin) * nblk + k, k = raster index of the 4x4 block inside the partition
 HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
 {
-    const int bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
-    const int c = lane / nblk, k = lane - c * nblk;
-    if (c >= w.ncand) return;
-    const int bx = w.part_ox + (k % bw) * 4, by = w.part_oy + (k / bw) * 4;
+    const int c = w.c_begin + (lane >> w.nblk_log2), k = lane & ((1 << w.nblk_log2) - 1);
+    if (c >= w.c_end) return;
+    const int bx = w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), by = w.part_oy + ((k >> w.bw_log2) << 2);
     const int blk = blk_idx_from_xy(bx, by);
     uint8_t pv[16], sv[16];
-    pred_luma_4x4(f, w.ref_y, w.mbx, w.mby, w.part_ox, w.part_oy, bx, by, w.cmvx[c], w.cmvy[c], pv);
+    int X, Y;
+    cand_origin(w, f, c, X, Y);
+    const uint8_t* g = w.tile + (Y + (by - w.part_oy) - w.tile_y0) * HLB_TILE + (X + (bx - w.part_ox) - w.tile_x0);
+    interp_luma_4x4(g, HLB_TILE, w.cmvx[c] & 3, w.cmvy[c] & 3, pv);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -339,10 +383,9 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
 #pragma unroll
         for (int i = 0; i < 16; ++i) nz |= (lv[i] != 0);
     }
-    int dist, bits = 0, tc = 0, t1 = 0, sc = 0;
+    int dist;
     if (nz) {
         const CavlcInfo ci = cavlc_block_info(lv, 16, false);
-        bits = ci.bits_rest; tc = ci.total_coeff; t1 = ci.trailing_ones; sc = ci.single_ctr;
         int cc[16];
         inv_zigzag4x4(lv, cc);
         dequant4x4(cc, f.qp, false);
@@ -351,9 +394,16 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
 #pragma unroll
         for (int i = 0; i < 16; ++i) rec[i] = (uint8_t)((int)pv[i] + cc[i]);  // wraps mod 256 (hl_math.h:261)
         dist = sad16(sv, rec);
-    } else dist = sad16(sv, pv);
-    w.r_dist[c][blk] = dist; w.r_bits[c][blk] = (uint16_t)bits; w.r_tc[c][blk] = (uint8_t)tc; w.r_t1[c][blk] = (uint8_t)t1;
-    w.r_sctr[c][blk] = (uint8_t)sc; w.r_nz[c][blk] = nz ? 1 : 0;
+        w.r_tc[c][blk] = ci.total_coeff; w.r_t1[c][blk] = ci.trailing_ones; w.r_nz[c][blk] = 1;
+        HLB_ATOMIC_ADD(&w.c_rbc[c], (int)ci.bits_rest);
+        HLB_ATOMIC_ADD(&w.c_sctr[c], (int)ci.single_ctr);
+        HLB_ATOMIC_OR(&w.c_cbp[c], 1 << blk);
+        HLB_ATOMIC_MAX(&w.step_last, ((c + 1) << 12) | (k << 8) | ci.single_ctr);   // last non-zero block in evaluation order
+    } else {
+        dist = sad16(sv, pv);
+        w.r_nz[c][blk] = 0;
+    }
+    HLB_ATOMIC_ADD(&w.c_dist[c], dist);
 }
 HLB_HD bool blk_in_part(const MbWork& w, int blk)
 {
@@ -366,7 +416,8 @@ HLB_FN void me_phase_scan(MbWork& w, int lane)
     if (lane >= 16) return;
     int e = w.tc[lane];
     const bool in = blk_in_part(w, lane);
-    for (int c = 0; c < w.ncand; ++c) {
+#pragma unroll 1
+    for (int c = w.c_begin; c < w.c_end; ++c) {
         if (in && w.r_nz[c][lane]) e = w.r_tc[c][lane];
         w.eff[c][lane] = (uint8_t)e;
     }
@@ -374,53 +425,93 @@ HLB_FN void me_phase_scan(MbWork& w, int lane)
 }
 HLB_FN void me_phase_token(MbWork& w, int lane)
 {
-    const int bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
-    const int c = lane / nblk, k = lane - c * nblk;
-    if (c >= w.ncand) return;
-    const int blk = blk_idx_from_xy(w.part_ox + (k % bw) * 4, w.part_oy + (k / bw) * 4);
+    const int c = w.c_begin + (lane >> w.nblk_log2), k = lane & ((1 << w.nblk_log2) - 1);
+    if (c >= w.c_end) return;
+    const int blk = blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2));
     if (!w.r_nz[c][blk]) return;
     const int nC = luma_nc(w, w.eff[c], blk);
-    HLB_DBG("      token c%d blk %d: nC %d tc %d t1 %d gate %x eff[4]=%d eff[1]=%d extA %d extB %d\n", c, blk, nC, w.r_tc[c][blk], w.r_t1[c][blk], w.cbp_gate, w.eff[c][4], w.eff[c][1], w.extA[blk], w.extB[blk]);
-    w.r_bits[c][blk] = (uint16_t)(w.r_bits[c][blk] + coeff_token_len(nC, w.r_tc[c][blk], w.r_t1[c][blk]));
-}
-HLB_FN void me_phase_sum(MbWork& w, int lane)
-{
-    if (lane >= w.ncand) return;
-    const int c = lane, bw = w.part_w >> 2, nblk = bw * (w.part_h >> 2);
-    int dist = 0, rbc = 0, sc = 0, cbp = 0, last = -1;
-    for (int k = 0; k < nblk; ++k) {
-        const int blk = blk_idx_from_xy(w.part_ox + (k % bw) * 4, w.part_oy + (k / bw) * 4);
-        dist += w.r_dist[c][blk];
-        if (w.r_nz[c][blk]) { rbc += w.r_bits[c][blk]; sc += w.r_sctr[c][blk]; cbp |= 1 << blk; last = w.r_sctr[c][blk]; }
-    }
-    w.c_dist[c] = dist; w.c_rbc[c] = rbc; w.c_sctr[c] = sc; w.c_cbp[c] = cbp; w.c_last[c] = last;
+    HLB_ATOMIC_ADD(&w.c_rbc[c], coeff_token_len(nC, w.r_tc[c][blk], w.r_t1[c][blk]));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Search of one mode (me_ds.c:104-477)
 // ------------------------------------------------------------------------------------------------------------------
-HLB_TABLE static const int8_t kDspInt[9][2] = {{0, 2}, {-1, 1}, {1, 1}, {-2, 0}, {0, 0}, {2, 0}, {-1, -1}, {1, -1}, {0, -2}};
-HLB_TABLE static const int8_t kDspHalf[5][2] = {{0, 1}, {-1, 0}, {0, -1}, {1, 0}, {0, 0}};
-HLB_TABLE static const int8_t kDspQuarter[9][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {0, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+HLB_TABLE static const int8_t kDsp[3][9][2] = {   // [shift: 0 quarter, 1 half, 2 integer][pattern index]
+    {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {0, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}},
+    {{0, 1}, {-1, 0}, {0, -1}, {1, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}},
+    {{0, 2}, {-1, 1}, {1, 1}, {-2, 0}, {0, 0}, {2, 0}, {-1, -1}, {1, -1}, {0, -2}}};
 // points skipped in the next iteration after the best point `idx` (me_ds.c:384-465), as bit masks over pattern indices
-HLB_TABLE static const uint16_t kPruneInt[9] = {0x1D0, 0x130, 0x1DA, 0x0B4, 0x000, 0x05A, 0x0B7, 0x05F, 0x017};
-HLB_TABLE static const uint16_t kPruneHalf[5] = {0x014, 0x018, 0x011, 0x012, 0x000};
-HLB_TABLE static const uint16_t kPruneQuarter[9] = {0x1B0, 0x1F8, 0x03F, 0x1B6, 0x000, 0x0DB, 0x036, 0x03F, 0x01B};
+HLB_TABLE static const uint16_t kPrune[3][9] = {{0x1B0, 0x1F8, 0x03F, 0x1B6, 0x000, 0x0DB, 0x036, 0x03F, 0x01B},
+                                                {0x014, 0x018, 0x011, 0x012, 0x000, 0, 0, 0, 0},
+                                                {0x1D0, 0x130, 0x1DA, 0x0B4, 0x000, 0x05A, 0x0B7, 0x05F, 0x017}};
 HLB_TABLE static const uint8_t kHeaderBits[7] = {3, 5, 5, 11, 19, 19, 27};
 
-template <class X>
-HLB_FN void me_eval(X& x, MbWork& w)
+HLB_HD void set_part(MbWork& w, int mode, int p, int s)
 {
-    const int nblk = (w.part_w >> 2) * (w.part_h >> 2);
-    x.run(CMD_ME_EVAL, w.ncand * nblk < 16 ? 16 : w.ncand * nblk);  // the scan phase needs one lane per luma block
-    for (int c = 0; c < w.ncand; ++c) {
-        if (w.c_last[c] >= 0) w.last_sctr = w.c_last[c];
+    mode_rect(mode, p, s, w.part_ox, w.part_oy, w.part_w, w.part_h);
+    w.bw_log2 = w.part_w == 16 ? 2 : (w.part_w == 8 ? 1 : 0);
+    w.nblk_log2 = w.bw_log2 + (w.part_h == 16 ? 2 : (w.part_h == 8 ? 1 : 0));
+}
+
+// One evaluation of candidates [c0, c1) (they fit the reference tile together): trial encodes on the worker lanes, then the
+// history-exact coeff_token lengths on the master warp's own lanes.  (bx0..by1) = bounding box of the samples they read.
+template <class X>
+HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, int bx0, int by0, int bx1, int by1)
+{
+    if (!(w.tile_valid && w.tile_ref == w.ref && bx0 >= w.tile_x0 && by0 >= w.tile_y0 && bx1 <= w.tile_x0 + HLB_TILE && by1 <= w.tile_y0 + HLB_TILE)) {
+        w.tile_x0 = bx0 - ((HLB_TILE - (bx1 - bx0)) >> 1); w.tile_y0 = by0 - ((HLB_TILE - (by1 - by0)) >> 1);
+        w.tile_ref = w.ref; w.tile_valid = 1;
+        x.run(CMD_TILE, HLB_MB_LANES);
+    }
+    w.c_begin = c0; w.c_end = c1;
+    x.run(CMD_ME_EVAL, (c1 - c0) << w.nblk_log2);
+#pragma unroll 1
+    for (int b = x.lane(); b < 16; b += x.nlanes()) me_phase_scan(w, b);
+    x.sync();
+#pragma unroll 1
+    for (int i = x.lane(); i < ((c1 - c0) << w.nblk_log2); i += x.nlanes()) me_phase_token(w, i);
+    x.sync();
+}
+// Evaluates w.ncand candidates (w.cmvx/cmvy) of the current partition in order; leaves per-candidate dist / rbc / sctr / cbp and
+// the RD cost (me_ds.c:287,297,345: dist + (rbc + mvd bits) * lambda) in w.c_*.
+template <class X>
+HLB_FN void me_eval(X& x, MbWork& w, const FrameCtx& f, int px, int py)
+{
+    const int n = w.ncand;
+    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        const int vx = w.cmvx[c] >> 2, vy = w.cmvy[c] >> 2;
+        mnx = vx < mnx ? vx : mnx; mxx = vx > mxx ? vx : mxx; mny = vy < mny ? vy : mny; mxy = vy > mxy ? vy : mxy;
+    }
+#pragma unroll 1
+    for (int c = x.lane(); c < n; c += x.nlanes()) { w.c_dist[c] = 0; w.c_rbc[c] = 0; w.c_sctr[c] = 0; w.c_cbp[c] = 0; }
+    w.step_last = -1;
+    x.sync();
+    // the origin clip is monotonic, so the box of the clipped origins is the clipped box
+    const int ox = w.mbx * 16 + w.part_ox, oy = w.mby * 16 + w.part_oy;
+    const int X0 = clip3(-17, f.W + 17, ox + mnx), X1 = clip3(-17, f.W + 17, ox + mxx), Y0 = clip3(-17, f.H + 17, oy + mny), Y1 = clip3(-17, f.H + 17, oy + mxy);
+    if (X1 - X0 + w.part_w + 5 <= HLB_TILE && Y1 - Y0 + w.part_h + 5 <= HLB_TILE) me_eval_range(x, w, f, 0, n, X0 - 2, Y0 - 2, X1 + w.part_w + 3, Y1 + w.part_h + 3);
+    else {
+#pragma unroll 1
+        for (int c = 0; c < n; ++c) {   // windows too far apart for one tile: one by one, same order, same result
+            int PX, PY;
+            cand_origin(w, f, c, PX, PY);
+            me_eval_range(x, w, f, c, c + 1, PX - 2, PY - 2, PX + w.part_w + 3, PY + w.part_h + 3);
+        }
+    }
+    if (w.step_last >= 0) w.last_sctr = w.step_last & 255;
+#pragma unroll 1
+    for (int c = x.lane(); c < n; c += x.nlanes()) {
+        const int rbc_mv = se_len(w.cmvx[c] - px) + se_len(w.cmvy[c] - py);
+        w.c_cost[c] = w.c_dist[c] + ((w.c_rbc[c] + rbc_mv) * f.lambda);
         // interpolation ops per 4x4 block by fractional class
         const int xf = w.cmvx[c] & 3, yf = w.cmvy[c] & 3;
         const int cls = (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
-        w.stat_interp += (unsigned)(cls * nblk);
+        HLB_ATOMIC_ADD(&w.stat_interp, (unsigned)(cls << w.nblk_log2));
     }
-    w.stat_trials += (unsigned)(w.ncand * nblk); w.stat_cands += (unsigned)w.ncand;
+    if (x.lane() == 0) { w.stat_trials += (unsigned)(n << w.nblk_log2); w.stat_cands += (unsigned)n; }
+    x.sync();
 }
 
 HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
@@ -434,7 +525,9 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
 {
     w.mode = mode;
     const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
+#pragma unroll 1
     for (int p = 0; p < nparts; ++p)
+#pragma unroll 1
         for (int s = 0; s < nsub; ++s) { w.best_sctr[p][s] = 9; w.best_dist[p][s] = INT_MAX; w.best_cost[p][s] = DBL_MAX; }
     w.probably_pskip = 0;
     if (mode == 0 && w.ref == 0) {  // PSkip probe (me_ds.c:229-261)
@@ -442,52 +535,57 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
         derive_pskip_mv(w, f, sx, sy);
         derive_mvp(w, f, 0, 0, w.ref, px, py);
         if (px == sx && py == sy) {
-            mode_rect(mode, 0, 0, w.part_ox, w.part_oy, w.part_w, w.part_h);
+            set_part(w, mode, 0, 0);
             w.ncand = 1; w.cmvx[0] = (int16_t)px; w.cmvy[0] = (int16_t)py;
-            me_eval(x, w);
+            me_eval(x, w, f, px, py);
             if (w.c_rbc[0] == 0 || w.c_sctr[0] < 6) { w.probably_pskip = 1; set_best(w, 0, 0, 0.0, 0); }
         }
     }
+#pragma unroll 1
     for (int p = 0; p < nparts; ++p) {
+#pragma unroll 1
         for (int s = 0; s < nsub; ++s) {
             int shift = 2, flags = 0xFFFFFF, px, py;
             derive_mvp(w, f, p, s, w.ref, px, py);
             w.mvp[p][s][0] = (int16_t)px; w.mvp[p][s][1] = (int16_t)py;
-            mode_rect(mode, p, s, w.part_ox, w.part_oy, w.part_w, w.part_h);
+            set_part(w, mode, p, s);
             // cost at the predictor, then at (0,0) (me_ds.c:283-299)
             w.ncand = 1; w.cmvx[0] = (int16_t)px; w.cmvy[0] = (int16_t)py;
             if (px != 0 || py != 0) { w.ncand = 2; w.cmvx[1] = 0; w.cmvy[1] = 0; }
-            me_eval(x, w);
+            me_eval(x, w, f, px, py);
+#pragma unroll 1
             for (int c = 0; c < w.ncand; ++c) {
-                const int rbc_mv = se_len(w.cmvx[c] - px) + se_len(w.cmvy[c] - py);
-                const double cost = w.c_dist[c] + ((w.c_rbc[c] + rbc_mv) * f.lambda);
-                HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f [init]\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], cost);
-                if (cost < w.best_cost[p][s]) set_best(w, p, s, cost, c);
+                HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f [init]\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
+                if (w.c_cost[c] < w.best_cost[p][s]) set_best(w, p, s, w.c_cost[c], c);
             }
             int cx = w.best_mv[p][s][0] >> 2, cy = w.best_mv[p][s][1] >> 2;
             int wl = cx - f.me_range, wr = cx + f.me_range, wt = cy - f.me_range, wb = cy + f.me_range;
+#pragma unroll 1
             for (int iter = 0;; ++iter) {
                 if (iter > 4096) { w.stuck = 1; break; }
                 int best_idx = -1;
                 const int count = shift == 1 ? 5 : 9;
-                uint8_t idxs[HLB_MAXC];
-                w.ncand = 0;
-                for (int i = 0; i < count; ++i) {
-                    if (!(flags & (1 << i))) continue;
-                    const int8_t* o = shift == 2 ? kDspInt[i] : (shift == 1 ? kDspHalf[i] : kDspQuarter[i]);
-                    const int mx = cx + o[0], my = cy + o[1];
-                    if (mx < wl || mx > wr || my < wt || my > wb) continue;
-                    idxs[w.ncand] = (uint8_t)i;
-                    w.cmvx[w.ncand] = (int16_t)(mx * (1 << shift)); w.cmvy[w.ncand] = (int16_t)(my * (1 << shift));
-                    ++w.ncand;
+                // pattern points of this iteration: one master lane per point, then an ordered compaction
+#pragma unroll 1
+                for (int i = x.lane(); i < count; i += x.nlanes()) {
+                    const int mx = cx + kDsp[shift][i][0], my = cy + kDsp[shift][i][1];
+                    const bool ok = (flags & (1 << i)) && mx >= wl && mx <= wr && my >= wt && my <= wb;
+                    w.pat_ok[i] = ok ? 1 : 0;
+                    w.pat_mv[i][0] = (int16_t)(mx * (1 << shift)); w.pat_mv[i][1] = (int16_t)(my * (1 << shift));
                 }
-                if (w.ncand > 0) {
-                    me_eval(x, w);
-                    for (int c = 0; c < w.ncand; ++c) {
-                        const int rbc_mv = se_len(w.cmvx[c] - px) + se_len(w.cmvy[c] - py);
-                        const double cost = w.c_dist[c] + ((w.c_rbc[c] + rbc_mv) * f.lambda);
-                        HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], cost);
-                        if (cost < w.best_cost[p][s]) { best_idx = idxs[c]; set_best(w, p, s, cost, c); }
+                x.sync();
+                int n = 0;
+#pragma unroll 1
+                for (int i = 0; i < count; ++i)
+                    if (w.pat_ok[i]) { w.cidx[n] = (uint8_t)i; w.cmvx[n] = w.pat_mv[i][0]; w.cmvy[n] = w.pat_mv[i][1]; ++n; }
+                w.ncand = n;
+                x.sync();
+                if (n > 0) {
+                    me_eval(x, w, f, px, py);
+#pragma unroll 1
+                    for (int c = 0; c < n; ++c) {
+                        HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
+                        if (w.c_cost[c] < w.best_cost[p][s]) { best_idx = w.cidx[c]; set_best(w, p, s, w.c_cost[c], c); }
                     }
                 }
                 flags = 0xFFFFFF;
@@ -503,8 +601,9 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
                     } else break;
                 } else {
                     cx = w.best_mv[p][s][0] >> shift; cy = w.best_mv[p][s][1] >> shift;
-                    flags &= ~(int)(shift == 2 ? kPruneInt[best_idx] : (shift == 1 ? kPruneHalf[best_idx] : kPruneQuarter[best_idx]));
+                    flags &= ~(int)kPrune[shift][best_idx];
                 }
+                x.sync();
             }
             w.mv_cur[p][s][0] = w.best_mv[p][s][0]; w.mv_cur[p][s][1] = w.best_mv[p][s][1];
             HLB_DBG("   part m%d p%d s%d: mv (%d,%d) mvp (%d,%d) cost %.4f dist %d sctr %d\n", mode, p, s, w.best_mv[p][s][0], w.best_mv[p][s][1], px, py, w.best_cost[p][s], w.best_dist[p][s], w.best_sctr[p][s]);
@@ -751,7 +850,7 @@ namespace hlb {
 HLB_HD int cmd_phases(int cmd)
 {
     switch (cmd) {
-    case CMD_ME_EVAL: return 4;
+    case CMD_ME_EVAL: return 1;
     case CMD_CHROMA: return 3;
     case CMD_I16_EVAL: return 2;
     case CMD_I16_RATE: return 2;
@@ -763,12 +862,8 @@ HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
 {
     switch (cmd) {
     case CMD_LOAD: phase_load(w, f, lane); break;
-    case CMD_ME_EVAL:
-        if (phase == 0) me_phase_trial(w, f, lane);
-        else if (phase == 1) me_phase_scan(w, lane);
-        else if (phase == 2) me_phase_token(w, lane);
-        else me_phase_sum(w, lane);
-        break;
+    case CMD_TILE: phase_tile_load(w, f, lane); break;
+    case CMD_ME_EVAL: me_phase_trial(w, f, lane); break;
     case CMD_PRED_INTER: phase_pred_inter(w, f, lane); break;
     case CMD_RECON_LUMA: phase_recon_luma(w, f, lane); break;
     case CMD_CHROMA:
@@ -786,8 +881,6 @@ HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
     default: break;
     }
 }
-// lanes a command needs at most (the GPU CTA must have at least this many threads)
-#define HLB_MB_LANES 160
 
 // ------------------------------------------------------------------------------------------------------------------
 // The macroblock: rdo.c:678-1270 (P) / rdo.c:99 (I)
@@ -795,90 +888,118 @@ HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
 template <class X>
 HLB_HD void chroma_code(X& x, MbWork& w) { x.run(CMD_CHROMA, 8); }
 
-HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb)
+HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb, int lane, int nl)
 {
     w.mb = mb; w.mbx = mb % f.mbw; w.mby = mb / f.mbw;
     w.availA = w.mbx > 0; w.availB = w.mby > 0; w.availC = w.mby > 0 && w.mbx < f.mbw - 1; w.availD = w.mbx > 0 && w.mby > 0;
     const MbState& s = f.st[mb];
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) w.tc[i] = s.tc_luma[i];
+#pragma unroll 1
     for (int c = 0; c < 2; ++c)
-        for (int b = 0; b < 4; ++b) {
-            w.tc_cac[c][b] = s.tc_cac[c][b];
-            w.chroma_dc[c][b] = s.chroma_dc[c][b];
-            for (int i = 0; i < 16; ++i) w.chroma_ac[c][b][i] = s.chroma_ac[c][b][i];
-        }
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) { w.tc_cac[c][b] = s.tc_cac[c][b]; w.chroma_dc[c][b] = s.chroma_dc[c][b]; }
+#pragma unroll 1
+    for (int i = lane; i < 128; i += nl) (&w.chroma_ac[0][0][0])[i] = (&s.chroma_ac[0][0][0])[i];
     w.cbp_gate = s.cbp_luma;
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) w.ref_cur[i] = s.ref_idx[i];
+#pragma unroll 1
     for (int p = 0; p < 4; ++p)
+#pragma unroll 1
         for (int q = 0; q < 4; ++q) { w.mv_cur[p][q][0] = s.mv[p][q][0]; w.mv_cur[p][q][1] = s.mv[p][q][1]; }
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) w.i4_mode[i] = s.i4_mode[i];
+#pragma unroll 1
     for (int blk = 0; blk < 16; ++blk) {
         const int bx = blk_x(blk), by = blk_y(blk);
         w.extA[blk] = (int8_t)((bx == 0) ? (w.availA ? nb_count(f.st[mb - 1], blk_idx_from_xy(12, by)) : -1) : 0);
         w.extB[blk] = (int8_t)((by == 0) ? (w.availB ? nb_count(f.st[mb - f.mbw], blk_idx_from_xy(bx, 12)) : -1) : 0);
     }
-    w.last_sctr = -1; w.need_prev_sctr = 0; w.stuck = 0;
+    w.last_sctr = -1; w.need_prev_sctr = 0; w.stuck = 0; w.tile_valid = 0;
     w.stat_trials = w.stat_interp = w.stat_cands = w.stat_intra = 0;
+    w.prof_run_cycles = w.prof_runs = w.prof_me_cycles = 0;
     w.mb_is_intra = 0;
 }
 
 // state the writer leaves behind (residual.c:903-1094) + publication of the macroblock's final state and record
 HLB_HD int nnz16(const int16_t* lv, int n) { int k = 0; for (int i = 0; i < n; ++i) k += (lv[i] != 0); return k; }
 
-HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad)
+HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad, int lane, int nl)
 {
     MbState& s = f.st[w.mb];
     hlb200_mb_record_t& r = f.rec[w.mb];
     // ---- record (what the host writer consumes) ----
     r.mb_class = (uint8_t)kind; r.mb_type = (uint8_t)mb_type;
     r.part_mode = (uint8_t)w.fin_mode;
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) { r.sub_mode[i] = (uint8_t)w.fin_sub[i]; r.ref_idx[i] = w.fin_ref[i]; }
     r.i16_pred_mode = (uint8_t)w.i16_mode; r.intra_chroma_pred_mode = (uint8_t)w.intra_chroma_mode;
     r.coded_block_pattern = (uint8_t)coded_block_pattern; r.cbp_luma = (uint8_t)cbp_luma; r.cbp_chroma = (uint8_t)cbp_chroma;
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) { r.cbp_chroma_dc4x4[c] = (uint8_t)w.cbp_dc[c]; r.cbp_chroma_ac4x4[c] = (uint8_t)w.cbp_ac[c]; }
     r.cbp_luma4x4 = (uint16_t)w.cbp_luma4x4;
     r.mb_qp_delta = 0; r.qp_y = (uint8_t)f.qp; r.qp_c[0] = r.qp_c[1] = (uint8_t)f.qpc;
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) { r.i4_pred_mode[i] = w.i4_mode[i]; r.prev_intra4x4_pred_mode_flag[i] = w.prev_i4[i]; r.rem_intra4x4_pred_mode[i] = w.rem_i4[i]; }
+#pragma unroll 1
     for (int p = 0; p < 4; ++p)
+#pragma unroll 1
         for (int q = 0; q < 4; ++q)
+#pragma unroll 1
             for (int k = 0; k < 2; ++k) { r.mv[p][q][k] = w.fin_mv[p][q][k]; r.mvd[p][q][k] = mvd ? mvd[p][q][k] : 0; }
     r.mad = mad;
     r.me_trials = w.stat_trials; r.me_interp_ops = w.stat_interp; r.me_candidates = (uint16_t)w.stat_cands; r.intra_trials = (uint16_t)w.stat_intra;
-    for (int b = 0; b < 16; ++b)
-        for (int i = 0; i < 16; ++i) { r.luma_level[b][i] = w.luma_level[b][i]; r.i16_ac_level[b][i] = w.i16_ac[b][i]; }
+    // level arrays: two int16 per 32-bit store, lanes strided (on the GPU the 32 lanes of the master warp share the copy)
+    {
+        uint32_t* d0 = (uint32_t*)&r.luma_level[0][0]; const uint32_t* s0 = (const uint32_t*)&w.luma_level[0][0];
+        uint32_t* d1 = (uint32_t*)&r.i16_ac_level[0][0]; const uint32_t* s1 = (const uint32_t*)&w.i16_ac[0][0];
+        uint32_t* d2 = (uint32_t*)&r.chroma_ac_level[0][0][0]; const uint32_t* s2 = (const uint32_t*)&w.chroma_ac[0][0][0];
+        const bool intra16 = kind == MBK_I16;
+#pragma unroll 1
+        for (int i = lane; i < 128; i += nl) { d0[i] = intra16 ? 0u : s0[i]; d1[i] = intra16 ? s1[i] : 0u; }
+#pragma unroll 1
+        for (int i = lane; i < 64; i += nl) d2[i] = s2[i];
+    }
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) r.i16_dc_level[i] = w.i16_dc[i];
+#pragma unroll 1
     for (int c = 0; c < 2; ++c)
-        for (int b = 0; b < 4; ++b) {
-            r.chroma_dc_level[c][b] = w.chroma_dc[c][b];
-            for (int i = 0; i < 16; ++i) r.chroma_ac_level[c][b][i] = w.chroma_ac[c][b][i];
-        }
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) r.chroma_dc_level[c][b] = w.chroma_dc[c][b];
     // ---- TotalCoeffs as the writer finalises them ----
     if (kind != MBK_PSKIP) {
         if (kind == MBK_I16) w.tc[0] = (uint8_t)nnz16(w.i16_dc, 16);
+#pragma unroll 1
         for (int b8 = 0; b8 < 4; ++b8)
             if ((cbp_luma >> b8) & 1)
+#pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
                     const int b = b8 * 4 + k;
                     w.tc[b] = (uint8_t)(kind == MBK_I16 ? nnz16(w.i16_ac[b], 15) : nnz16(w.luma_level[b], 16));
                 }
         if (cbp_chroma & 2)
+#pragma unroll 1
             for (int c = 0; c < 2; ++c)
+#pragma unroll 1
                 for (int b = 0; b < 4; ++b) w.tc_cac[c][b] = (uint8_t)(((w.cbp_ac[c] >> b) & 1) ? nnz16(w.chroma_ac[c][b], 15) : 0);
     }
     // ---- persistent state ----
     s.kind = (uint8_t)kind;
     s.part_mode = (uint8_t)w.fin_mode;
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) { s.sub_mode[i] = (uint8_t)w.fin_sub[i]; s.ref_idx[i] = w.ref_cur[i]; }
     s.cbp_luma = (uint8_t)cbp_luma; s.cbp_chroma = (uint8_t)cbp_chroma;
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) { s.tc_luma[i] = w.tc[i]; s.i4_mode[i] = w.i4_mode[i]; }
+#pragma unroll 1
     for (int c = 0; c < 2; ++c)
-        for (int b = 0; b < 4; ++b) {
-            s.tc_cac[c][b] = w.tc_cac[c][b];
-            s.chroma_dc[c][b] = w.chroma_dc[c][b];
-            for (int i = 0; i < 16; ++i) s.chroma_ac[c][b][i] = w.chroma_ac[c][b][i];
-        }
-    for (int p = 0; p < 4; ++p)
-        for (int q = 0; q < 4; ++q) { s.mv[p][q][0] = w.mv_cur[p][q][0]; s.mv[p][q][1] = w.mv_cur[p][q][1]; }
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) { s.tc_cac[c][b] = w.tc_cac[c][b]; s.chroma_dc[c][b] = w.chroma_dc[c][b]; }
+#pragma unroll 1
+    for (int i = lane; i < 64; i += nl) ((uint32_t*)&s.chroma_ac[0][0][0])[i] = ((const uint32_t*)&w.chroma_ac[0][0][0])[i];
+#pragma unroll 1
+    for (int i = lane; i < 16; i += nl) ((uint32_t*)&s.mv[0][0][0])[i] = ((const uint32_t*)&w.mv_cur[0][0][0])[i];
     s.last_sctr = (uint8_t)(w.last_sctr < 0 ? 255 : w.last_sctr);
 }
 
@@ -903,18 +1024,23 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
     double best_cost = DBL_MAX;
     int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0;
     int16_t best_mv[4][4][2], best_mvp[4][4][2];
+#pragma unroll 1
     for (int u = 0; u < f.num_refs; ++u) {
         if (!f.ref[u][0]) continue;
         w.ref = u; w.ref_y = f.ref[u][0];
+#pragma unroll 1
         for (int g = 0; g < 4 && !found; ++g) {
             const int m0 = g < 3 ? g : 3, m1 = g < 3 ? g : 6;
+#pragma unroll 1
             for (int mode = m0; mode <= m1; ++mode) {
                 me_find_best_cost(x, w, f, mode);
                 double cost_sum = 0;
                 int dist_sum = 0, sctr_sum = 0;
                 probably_pskip = w.probably_pskip;
                 const int np = mode_nparts(mode), ns = mode_nsub(mode);
+#pragma unroll 1
                 for (int p = 0; p < np; ++p)
+#pragma unroll 1
                     for (int s = 0; s < ns; ++s) { cost_sum += w.best_cost[p][s]; dist_sum += w.best_dist[p][s]; sctr_sum += w.best_sctr[p][s]; }
                 if (!probably_pskip && cost_sum != 0 && sctr_sum < 6 && mode == 0) {  // rdo.c:1040-1054
                     int sx, sy;
@@ -926,8 +1052,11 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
                         w.mv_cur[0][0][0], w.mv_cur[0][0][1], w.mvp[0][0][0], w.mvp[0][0][1], w.best_cost[0][0]);
                 if (cost_sum < best_cost) {
                     best_cost = cost_sum; best_dist = dist_sum; best_sctr = sctr_sum; best_mode = mode; best_ref = u;
+#pragma unroll 1
                     for (int p = 0; p < np; ++p)
+#pragma unroll 1
                         for (int s = 0; s < ns; ++s)
+#pragma unroll 1
                             for (int k = 0; k < 2; ++k) { best_mv[p][s][k] = w.mv_cur[p][s][k]; best_mvp[p][s][k] = w.mvp[p][s][k]; }
                 }
             }
@@ -947,21 +1076,26 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         double intra_cost;
         const int intra_kind = mb_encode_intra(x, w, f, intra_cost);  // reconstructs into the picture and commits when it wins (rdo.c:1161-1167)
         HLB_DBG("  intra cost %.4f (kind %d) vs inter %.4f (mode %d)\n", intra_cost, intra_kind, best_cost, best_mode);
-        if (intra_cost <= best_cost) { mb_commit_intra(w, f, intra_kind); return; }
+        if (intra_cost <= best_cost) { mb_commit_intra(w, f, intra_kind, x.lane(), x.nlanes()); return; }
     }
     // ---- commit the best inter layout (rdo.c:1170-1218) ----
     w.mb_is_intra = 0;
     w.fin_mode = best_mode < 3 ? best_mode : 3;
     const int fs = best_mode <= 3 ? 0 : best_mode - 3;
     int16_t mvd[4][4][2];
+#pragma unroll 1
     for (int p = 0; p < 4; ++p) {
         w.fin_sub[p] = fs; w.ref_cur[p] = 0; w.fin_ref[p] = 0;
+#pragma unroll 1
         for (int s = 0; s < 4; ++s) mvd[p][s][0] = mvd[p][s][1] = 0;
     }
     const int np = mode_nparts(best_mode), ns = mode_nsub(best_mode);
+#pragma unroll 1
     for (int p = 0; p < np; ++p) {
         w.ref_cur[p] = (int8_t)best_ref; w.fin_ref[p] = (int8_t)best_ref;
+#pragma unroll 1
         for (int s = 0; s < ns; ++s)
+#pragma unroll 1
             for (int k = 0; k < 2; ++k) {
                 w.fin_mv[p][s][k] = best_mv[p][s][k]; w.mv_cur[p][s][k] = best_mv[p][s][k];
                 mvd[p][s][k] = (int16_t)(best_mv[p][s][k] - best_mvp[p][s][k]);
@@ -981,6 +1115,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         x.run(CMD_RECON_LUMA, 16);
         w.cbp_luma4x4 = 0;
         if (!w.luma_skip_residual)
+#pragma unroll 1
             for (int b = 0; b < 16; ++b) w.cbp_luma4x4 |= w.r_nz[0][b] << b;
         chroma_code(x, w);
         w.arg0 = 3; x.run(CMD_STORE, 24);
@@ -998,19 +1133,20 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
             if (sx == best_mvp[0][0][0] && sy == best_mvp[0][0][1]) { kind = MBK_PSKIP; mb_type = 5; }
         }
     }
-    mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, mvd, best_dist);
+    mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, mvd, best_dist, x.lane(), x.nlanes());
 }
 
 template <class X>
 HLB_HD void mb_encode(X& x, MbWork& w, const FrameCtx& f, int mb)
 {
-    mb_begin(w, f, mb);
+    mb_begin(w, f, mb, x.lane(), x.nlanes());
+    x.sync();
     x.run(CMD_LOAD, 24);
     if (f.is_p) mb_encode_p(x, w, f);
     else {
         double c;
         const int kind = mb_encode_intra(x, w, f, c);
-        mb_commit_intra(w, f, kind);
+        mb_commit_intra(w, f, kind, x.lane(), x.nlanes());
     }
 }
 

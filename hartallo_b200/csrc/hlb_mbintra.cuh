@@ -225,7 +225,9 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
 {
     // ---- Intra16x16 (no reconstruction into the picture yet) ----
     w.p33[0] = intra_luma_at(w, f, -1, -1);
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) { w.p33[1 + i] = intra_luma_at(w, f, -1, i); w.p33[17 + i] = intra_luma_at(w, f, i, -1); }
+#pragma unroll 1
     for (int m = 0; m < 4; ++m) w.t_mode_ok[m] = i16_mode_allowed(m, w.p33) ? 1 : 0;
     {
         const I16Params q = i16_params(w.p33);
@@ -238,28 +240,36 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     w.arg1 = 0;
     if (w.last_sctr < 0) {
         bool need = false, done = false;
+#pragma unroll 1
         for (int m = 0; m < 4 && !done; ++m) {
             if (!w.t_mode_ok[m]) continue;
+#pragma unroll 1
             for (int b = 0; b < 16 && !done; ++b)
                 if (w.t_nz[m][b]) { need = (w.t_tc[m][b] == 0); done = true; }
         }
         if (need) w.arg1 = x.prev_sctr(w.mb);
     }
     x.run(CMD_I16_RATE, 64);
+#pragma unroll 1
     for (int m = 0; m < 4; ++m) w.stat_intra += w.t_mode_ok[m] ? 16u : 0u;
     double best16 = DBL_MAX;
     int dist16 = 0;
     w.i16_mode = 2; w.i16_cbp4x4 = 0;
+#pragma unroll 1
     for (int m = 0; m < 4; ++m) {
         if (!w.t_mode_ok[m]) continue;
         double d = 0;
+#pragma unroll 1
         for (int b = 0; b < 16; ++b) d += w.t_dist[m][b];
         const double cost = d + (f.lambda * (double)w.t_rate[m]);
         HLB_DBG("  I16 mode %d: dist %.0f rate %d cbp %x cost %.4f\n", m, d, w.t_rate[m], w.t_cbp[m], cost);
         if (cost < best16) { best16 = cost; dist16 = (int)d; w.i16_mode = m; w.i16_cbp4x4 = w.t_cbp[m]; }
     }
+#pragma unroll 1
     for (int b = 0; b < 16; ++b)
+#pragma unroll 1
         for (int i = 0; i < 16; ++i) w.i16_ac[b][i] = w.t_ac[w.i16_mode][b][i];
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) w.i16_dc[i] = w.i16_cbp4x4 ? w.t_dc[w.i16_mode][i] : 0;
 
     // ---- Intra4x4 (reconstructs block after block: later blocks predict from it) ----
@@ -267,10 +277,13 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     int dist4 = INT_MAX, cbp4 = 0;
     if (best16 != 0) {
         cost4 = 0; dist4 = 0;
+#pragma unroll 1
         for (int blk = 0; blk < 16; ++blk) {
             const int bx = blk_x(blk), by = blk_y(blk);
             w.p13[0] = intra_luma_at(w, f, bx - 1, by - 1);
+#pragma unroll 1
             for (int i = 0; i < 4; ++i) w.p13[1 + i] = intra_luma_at(w, f, bx - 1, by + i);
+#pragma unroll 1
             for (int i = 0; i < 8; ++i) w.p13[5 + i] = (i > 3 && (blk == 3 || blk == 11)) ? HLB_NA : intra_luma_at(w, f, bx + i, by - 1);
             // in-MB positions to the right of an uncoded area (blocks 5, 7, 13, 15) fall outside the macroblock => HLB_NA from intra_luma_at
             if ((blk == 5) && 0) {}
@@ -278,10 +291,12 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
             w.i4_blk = blk;
             w.i4_mode[blk] = 2;
             x.run(CMD_I4_EVAL, 9);
+#pragma unroll 1
             for (int m = 0; m < 9; ++m) w.stat_intra += w.q_ok[m] ? 1u : 0u;
             double min_cost = DBL_MAX, min_dist = 0;
             int best_mode = 2, best_allzero = 1;
             const int nC = luma_nc(w, w.tc, blk);
+#pragma unroll 1
             for (int mode = 0; mode < 9; ++mode) {
                 if (!w.q_ok[mode]) continue;
                 if (w.q_res0[mode]) { min_cost = 0; min_dist = 0; best_mode = mode; best_allzero = 1; break; }
@@ -296,10 +311,13 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
             }
             HLB_DBG("  I4 blk %d: mode %d cost %.4f dist %.0f nC %d\n", blk, best_mode, min_cost, min_dist, nC);
             w.i4_mode[blk] = (uint8_t)best_mode;
+#pragma unroll 1
             for (int i = 0; i < 16; ++i) w.luma_level[blk][i] = w.q_lv[best_mode][i];
             cost4 += min_cost; dist4 = (int)(dist4 + min_dist);
             if (!best_allzero) cbp4 |= 1 << blk;
+#pragma unroll 1
             for (int r = 0; r < 4; ++r)
+#pragma unroll 1
                 for (int c = 0; c < 4; ++c) w.rec_y[(by + r) * 16 + bx + c] = w.q_pred[best_mode][r * 4 + c];
         }
     }
@@ -311,6 +329,7 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
         kind = MBK_I4;
         w.cbp_luma4x4 = cbp4;
         int zeros = 0;
+#pragma unroll 1
         for (int blk = 0; blk < 16; ++blk) {  // pred_intra.c:541-614
             const int bx = blk_x(blk), by = blk_y(blk);
             int mA = -1, mB = -1;  // -1: neighbour macroblock not available
@@ -332,8 +351,10 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     w.arg0 = mad;  // parked for mb_commit_intra
     // ---- chroma (rdo.c:216-246) ----
     w.mb_is_intra = 1;
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         w.p17[c][0] = intra_chroma_at(w, f, c, -1, -1);
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) { w.p17[c][1 + i] = intra_chroma_at(w, f, c, -1, i); w.p17[c][9 + i] = intra_chroma_at(w, f, c, i, -1); }
     }
     const int mad_keep = w.arg0;
@@ -345,11 +366,11 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     return kind;
 }
 
-HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad);
+HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad, int lane, int nl);
 HLB_HD int guess_cbp_luma(int cbp4x4, bool i16);
 HLB_HD int guess_cbp_chroma(const MbWork& w);
 
-HLB_FN void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind)
+HLB_FN void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind, int lane, int nl)
 {
     const int mad = w.arg0;
     const int cbp_luma = guess_cbp_luma(w.cbp_luma4x4, kind == MBK_I16);
@@ -363,7 +384,7 @@ HLB_FN void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind)
         w.fin_ref[p] = 0;
         for (int s = 0; s < 4; ++s) w.fin_mv[p][s][0] = w.fin_mv[p][s][1] = 0;
     }
-    mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, nullptr, mad);
+    mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, nullptr, mad, lane, nl);
 }
 
 }  // namespace hlb

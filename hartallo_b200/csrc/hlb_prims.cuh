@@ -16,8 +16,8 @@
 
 #if defined(__CUDACC__)
 #define HLB_HD __device__ __forceinline__
-#define HLB_FN __device__ __noinline__   /* phase / control functions of the slice kernel: one copy each (compile time, code size) */
-#define HLB_TABLE __device__
+#define HLB_FN __device__ __noinline__   /* phase / control functions of the slice kernel: one copy each */
+#define HLB_TABLE __constant__   /* small read-only tables: constant cache (plain global loads are compiled .cg and would go to L2) */
 #define HLB_LDG(p) __ldg(p)   /* read-only for the whole kernel (reference / source planes): non-coherent path, L1-cacheable */
 #else
 #define HLB_HD inline

@@ -9,8 +9,8 @@
 // in P pictures that chain is consumed almost never and is fetched lazily by waiting for the predecessor's done flag.
 //
 // One CTA per macroblock, warp-specialised: warp 0 (the master warp) runs the serial control flow of hlb_mbcore.cuh -- all 32 lanes
-// redundantly on identical data, so the warp stays converged -- and posts commands; warps 1..5 (HLB_MB_LANES = 160 lanes) execute
-// the command phases.  Master and workers meet at named barrier 1 from different code paths, which is legal for bar.sync as long
+// redundantly on identical data, so the warp stays converged -- and posts commands; the worker warps (HLB_WORKERS threads; a command's logical lanes are strided
+// over them) execute the command phases.  Master and workers meet at named barrier 1 from different code paths, which is legal for bar.sync as long
 // as every WARP is converged at its own call site (bar.sync == barrier.sync.aligned).  Global loads are compiled .cg (-Xptxas -dlcm=cg) so that state and
 // reconstruction written by other CTAs is read from L2; read-only planes go through __ldg.
 #include <new>
@@ -41,7 +41,13 @@ __device__ __forceinline__ void watchdog_fire(Sched* s, int code, int a, int b)
     if (atomicCAS(&s->abort, 0, code) == 0) { s->dbg[0] = code; s->dbg[1] = a; s->dbg[2] = b; s->dbg[3] = (int)blockIdx.x; __threadfence(); }
 }
 
-#define HLB_CTA_THREADS (HLB_MB_LANES + 32)
+#ifndef HLB_WORKERS
+#define HLB_WORKERS 64            /* worker threads per CTA; a command's logical lanes are strided over them */
+#endif
+#define HLB_CTA_THREADS (HLB_WORKERS + 32)
+#ifndef HLB_SLICE_MIN_CTAS
+#define HLB_SLICE_MIN_CTAS 3   /* register budget: 65536 / (3 x 192) = 113 -> ptxas rounds down */
+#endif
 __device__ __forceinline__ void cta_bar() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(HLB_CTA_THREADS) : "memory"); }
 __device__ __forceinline__ int ld_volatile(const int* p) { return *(const volatile int*)p; }
 
@@ -53,12 +59,22 @@ struct GpuExec {
     Sched* sched;
     __device__ __noinline__ void run(int cmd, int nlanes)
     {
+#ifdef HLB_PROFILE_STEPS
+        const long long t0 = clock64();
+#endif
         w->arg0_lanes = nlanes;
         ((volatile int*)&w->cmd)[0] = cmd;
         cta_bar();
         const int np = cmd_phases(cmd);
         for (int p = 0; p < np; ++p) cta_bar();   // the worker warps run the phases
+#ifdef HLB_PROFILE_STEPS
+        w->prof_run_cycles += (unsigned)(clock64() - t0); w->prof_runs++;
+        if (cmd == CMD_ME_EVAL) { w->prof_me_cycles += (unsigned)(clock64() - t0); }
+#endif
     }
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ int nlanes() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __noinline__ int prev_sctr(int mb)
     {
         for (int a = mb - 1; a >= 0; --a) {
@@ -106,7 +122,7 @@ __global__ void k_slice_init(SliceJob* jobs, int njobs, int* sched_buf, int tota
     }
 }
 
-__global__ void __launch_bounds__(HLB_CTA_THREADS) k_slice_encode(const SliceJob* __restrict__ jobs, int njobs, int* sched_buf)
+__global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_encode(const SliceJob* __restrict__ jobs, int njobs, int* sched_buf)
 {
     __shared__ MbWork w;
     __shared__ FrameCtx sf;
@@ -123,10 +139,12 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS) k_slice_encode(const SliceJob
             int item = -1;
             if (idx < total && !ld_volatile(&s->abort)) {
                 int spins = 0;
+                unsigned ns = 64;   // exponential back-off: idle CTAs must not steal issue slots / L2 bandwidth from working ones
                 while ((item = ld_volatile(queue + idx)) < 0) {
-                    if (ld_volatile(&s->abort)) break;
-                    if (++spins > HLB_SPIN_LIMIT) { watchdog_fire(s, WD_QUEUE, idx, ld_volatile(&s->tail)); break; }
-                    __nanosleep(200);
+                    if ((spins & 15) == 15 && ld_volatile(&s->abort)) break;
+                    if (++spins > HLB_SPIN_LIMIT / 8) { watchdog_fire(s, WD_QUEUE, idx, ld_volatile(&s->tail)); break; }
+                    __nanosleep(ns);
+                    if (ns < 2048) ns <<= 1;
                 }
                 __threadfence();
             }
@@ -149,6 +167,8 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS) k_slice_encode(const SliceJob
         }
         __syncthreads();
         const int mb = item - job->base;
+        unsigned t_start = 0;
+        if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); t_start = (unsigned)t; }
         if (tid < 32) {   // master warp: every lane executes the same control flow on the same data
             GpuExec x;
             x.w = &w; x.f = &sf; x.job = job; x.done = done; x.sched = s;
@@ -157,7 +177,7 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS) k_slice_encode(const SliceJob
             ((volatile int*)&w.cmd)[0] = CMD_EXIT;
             cta_bar();
         } else {
-            const int lane = tid - 32;
+            const int wt = tid - 32;
             for (;;) {
                 cta_bar();
                 const int cmd = ((volatile int*)&w.cmd)[0];
@@ -165,13 +185,18 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS) k_slice_encode(const SliceJob
                 const int nl = w.arg0_lanes;
                 const int np = cmd_phases(cmd);
                 for (int p = 0; p < np; ++p) {
-                    if (lane < nl) cmd_phase(w, sf, cmd, p, lane);
+                    for (int lane = wt; lane < nl; lane += HLB_WORKERS) cmd_phase(w, sf, cmd, p, lane);
                     cta_bar();
                 }
             }
         }
         __syncthreads();
         if (tid == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            sf.rec[mb].t_start_ns = t_start; sf.rec[mb].t_end_ns = (unsigned)t;
+#ifdef HLB_PROFILE_STEPS
+            sf.rec[mb].mad = (int)w.prof_run_cycles; sf.rec[mb].i16_dc_level[0] = (int16_t)w.prof_runs; sf.rec[mb].me_interp_ops = w.prof_me_cycles;
+#endif
             __threadfence();
             atomicExch(done + item, 1);
             // successors (see the header comment)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libhl_b200.so")
+SO_PATH = os.environ.get("HLB200_LIB", os.path.join(HERE, "libhl_b200.so"))   # HLB200_LIB: alternative build of the same library (tuning experiments)
 
 
 class Hlb200Error(RuntimeError):
@@ -27,7 +27,7 @@ MB_RECORD = np.dtype([
     ("mv", "<i2", (4, 4, 2)), ("mvd", "<i2", (4, 4, 2)), ("mad", "<i4"),
     ("luma_level", "<i2", (16, 16)), ("i16_dc_level", "<i2", (16,)), ("i16_ac_level", "<i2", (16, 16)),
     ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16)),
-    ("me_trials", "<u4"), ("me_interp_ops", "<u4"), ("me_candidates", "<u2"), ("intra_trials", "<u2")], align=True)
+    ("me_trials", "<u4"), ("me_interp_ops", "<u4"), ("me_candidates", "<u2"), ("intra_trials", "<u2"), ("t_start_ns", "<u4"), ("t_end_ns", "<u4")], align=True)
 
 
 class SliceParams(C.Structure):

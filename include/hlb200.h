@@ -99,6 +99,7 @@ typedef struct hlb200_mb_record {
     uint32_t me_interp_ops;           /* integer ops of the interpolation of those blocks, by fractional class */
     uint16_t me_candidates;           /* candidate motion vectors costed */
     uint16_t intra_trials;            /* 4x4 trial encodes of the intra decision */
+    uint32_t t_start_ns, t_end_ns;    /* device globaltimer (low 32 bits) when the macroblock started / finished: scheduling analysis */
 } hlb200_mb_record_t;
 
 typedef struct hlb200_slice_params {

@@ -21,11 +21,14 @@ struct CpuExec {
     int prev_frame_sctr;
     void run(int cmd, int nlanes)
     {
-        w->cmd = cmd;
+        w->cmd = cmd; w->arg0_lanes = nlanes;
         const int np = cmd_phases(cmd);
         for (int p = 0; p < np; ++p)
             for (int lane = 0; lane < nlanes; ++lane) cmd_phase(*w, *f, cmd, p, lane);
     }
+    int lane() const { return 0; }
+    int nlanes() const { return 1; }
+    void sync() const {}
     int prev_sctr(int mb)
     {
         for (int a = mb - 1; a >= 0; --a)
