@@ -197,7 +197,9 @@ def measure_int_peak(torch, hl, lib, dev, stream, sp):
 
 
 def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, stream, sp):
+    from hartallo_b200 import sharding
     S, K, Wm = args.streams, args.steps, args.warmup
+    my_streams = sharding.streams_of_rank(rank, world, S * world)   # weak scaling: S streams per GPU, world * S in total
     ysz, csz = W * H, W * H // 4
     frame_b = ysz + 2 * csz
     nfr = 1 + Wm + K + 1                 # IDR + warm-up + timed + 1 spare
@@ -207,7 +209,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
         e = hl.Encoder(W, H, qp=QP, me_range=ME_RANGE, refs=1, device=local)
         hl.check(lib.hlb200_stream_set_cuda_stream(e.st.ctx, sp), "set_cuda_stream")
         encs.append(e)
-        g = synth.G1(W, H, seed=12345 + 7919 * (rank * S + s_i))
+        g = synth.G1(W, H, seed=sharding.stream_seed(my_streams[s_i]))
         fr = [g.next() for _ in range(nfr)]
         d_frames.append([torch.from_numpy(f).to(dev) for f in fr])
         if s_i < 2:
@@ -336,11 +338,11 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="slice", choices=["batch", "slice"])
-    ap.add_argument("--streams", type=int, default=16, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
+    ap.add_argument("--streams", type=int, default=128, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
