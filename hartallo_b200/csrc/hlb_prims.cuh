@@ -104,7 +104,78 @@ HLB_HD int hl_h(const uint8_t* p) { return tap6(p[-2], p[-1], p[0], p[1], p[2], 
 HLB_HD int hl_v(const uint8_t* p, int s) { return tap6(p[-2 * s], p[-s], p[0], p[s], p[2 * s], p[3 * s]); }  // unrounded h
 HLB_HD int rnd5(int v) { return clip255((v + 16) >> 5); }
 
+// Compact formulation: three paths only (integer copy; positions built from the horizontal / vertical half samples b, h;
+// positions involving the centre half sample j), rows produced by small loops that are NOT unrolled.  The slice kernel runs
+// hundreds of CTAs that sit in different places of the code: short loops keep the instruction-cache footprint (and the
+// divergence between candidates with different fractional positions) small.  Same arithmetic as interpol.h:162-923.
 HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t out[16])
+{
+    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;   // rows, shifted in as they are produced (no dynamic register indexing)
+    if ((xf | yf) == 0) {
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const uint8_t* p = g + r * pitch;
+            o0 = o1; o1 = o2; o2 = o3;
+            o3 = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        }
+    } else if (xf != 2 && yf != 2 ? true : (xf == 0 || yf == 0)) {
+        // a b c d h n (one half sample, possibly averaged with an integer sample) and e g p r (average of b and h)
+        const bool needB = xf != 0, needH = yf != 0;
+        const int rowB = yf == 3 ? pitch : 0, colH = xf == 3 ? 1 : 0;
+        const int gofs = needB ? (xf == 3 ? 1 : 0) : (yf == 3 ? pitch : 0);   // integer sample averaged with a lone half sample
+        const bool lone_half = needB != needH && (needB ? xf == 2 : yf == 2);
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const uint8_t* p = g + r * pitch;
+            uint32_t row = 0;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int bb = rnd5(hl_h(p + rowB + x)), hh = rnd5(hl_v(p + x + colH, pitch));
+                int v;
+                if (needB && needH) v = (bb + hh + 1) >> 1;
+                else {
+                    const int hs = needB ? bb : hh;
+                    v = lone_half ? hs : ((p[x + gofs] + hs + 1) >> 1);
+                }
+                row |= (uint32_t)v << (8 * x);
+            }
+            o0 = o1; o1 = o2; o2 = o3; o3 = row;
+        }
+    } else {
+        // j and f q (xf == 2: partner b of row y / y+1) or i k (yf == 2: partner h of column x / x+1).  Streaming over the nine
+        // rows -2..+6 of unrounded horizontal half samples with a six-row window.
+        int w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) w0[x] = w1[x] = w2[x] = w3[x] = w4[x] = w5[x] = 0;
+        const int colH = xf == 3 ? 1 : 0;
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r) {
+            const uint8_t* p = g + (r - 2) * pitch;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { w0[x] = w1[x]; w1[x] = w2[x]; w2[x] = w3[x]; w3[x] = w4[x]; w4[x] = w5[x]; w5[x] = hl_h(p + x); }
+            if (r >= 5) {   // window = rows y-2 .. y+3 of output row y = r - 5
+                const uint8_t* q = g + (r - 5) * pitch;
+                uint32_t row = 0;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int j = clip255((tap6(w0[x], w1[x], w2[x], w3[x], w4[x], w5[x]) + 512) >> 10);
+                    int v = j;
+                    if (xf == 2) { if (yf != 2) v = (rnd5(yf == 3 ? w3[x] : w2[x]) + j + 1) >> 1; }
+                    else v = (rnd5(hl_v(q + x + colH, pitch)) + j + 1) >> 1;
+                    row |= (uint32_t)v << (8 * x);
+                }
+                o0 = o1; o1 = o2; o2 = o3; o3 = row;
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        out[x] = (uint8_t)(o0 >> (8 * x)); out[4 + x] = (uint8_t)(o1 >> (8 * x)); out[8 + x] = (uint8_t)(o2 >> (8 * x)); out[12 + x] = (uint8_t)(o3 >> (8 * x));
+    }
+}
+
+// the original per-position formulation (kept as the cross-check of the compact one in tools/emu/check_interp.cpp)
+HLB_HD void interp_luma_4x4_unrolled(const uint8_t* g, int pitch, int xf, int yf, uint8_t out[16])
 {
     if (xf == 0 && yf == 0) {
 #pragma unroll
@@ -360,7 +431,7 @@ HLB_HD int level_code_len(int suffix_length, int level_code)
 }
 
 // lv: coefficients in scan order, n = maxNumCoeff handed to the reference (16 for every RDO call; 4 for chroma DC)
-HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
+HLB_HD CavlcInfo cavlc_block_info_ref(const int* lv, int n, bool chroma_dc)
 {
     int nz[16];
     int run[16];
@@ -415,6 +486,57 @@ HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
     }
     r.bits_rest = (uint16_t)bits;
     return r;
+}
+
+
+// Register-only formulation for the only shape the kernels use (16 coefficients, luma/chroma-AC tables): the levels are packed
+// into a 256-bit shift register that is consumed from the high-frequency end by a loop that is NOT unrolled -- no local-memory
+// arrays, ~1 KB of code.  Run lengths and level codes are produced on the fly in coding order (residual.c:757-898).
+HLB_HD uint32_t funnel_l16(uint32_t lo, uint32_t hi) { return (hi << 16) | (lo >> 16); }
+HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
+{
+    if (n != 16 || chroma_dc) return cavlc_block_info_ref(lv, n, chroma_dc);
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, mask = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mask |= (uint32_t)(lv[i] != 0) << i;
+    CavlcInfo out;
+    out.total_coeff = 0; out.trailing_ones = 0; out.single_ctr = 9; out.bits_rest = 0;
+    if (mask == 0) return out;
+    r0 = ((uint32_t)lv[0] & 0xffffu) | ((uint32_t)lv[1] << 16); r1 = ((uint32_t)lv[2] & 0xffffu) | ((uint32_t)lv[3] << 16);
+    r2 = ((uint32_t)lv[4] & 0xffffu) | ((uint32_t)lv[5] << 16); r3 = ((uint32_t)lv[6] & 0xffffu) | ((uint32_t)lv[7] << 16);
+    r4 = ((uint32_t)lv[8] & 0xffffu) | ((uint32_t)lv[9] << 16); r5 = ((uint32_t)lv[10] & 0xffffu) | ((uint32_t)lv[11] << 16);
+    r6 = ((uint32_t)lv[12] & 0xffffu) | ((uint32_t)lv[13] << 16); r7 = ((uint32_t)lv[14] & 0xffffu) | ((uint32_t)lv[15] << 16);
+    int tc = 0, hb = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { tc += (mask >> i) & 1; if ((mask >> i) & 1) hb = i; }
+    const int tz = hb + 1 - tc;
+    int bits = 0, zl = 0;
+    if (tc < 16) { bits += kTotalZerosLen[tc - 1][tz]; zl = tz; }
+    int t1 = 0, sl = 0, j = 0, run = 0, first_level = 1, first_v = 0;
+    bool cnt = true;
+#pragma unroll 1
+    for (int p = 15; p >= 0 && j < tc; --p) {
+        const int c = (int)(int16_t)(r7 >> 16);
+        r7 = funnel_l16(r6, r7); r6 = funnel_l16(r5, r6); r5 = funnel_l16(r4, r5); r4 = funnel_l16(r3, r4);
+        r3 = funnel_l16(r2, r3); r2 = funnel_l16(r1, r2); r1 = funnel_l16(r0, r1); r0 <<= 16;
+        if (c == 0) { if (j > 0) ++run; continue; }
+        if (j > 0 && zl > 0) { bits += kRunBeforeLen[(zl > 7 ? 7 : zl) - 1][run]; zl -= run; }   // run_before of the previous coefficient
+        run = 0;
+        if (j == 0) first_v = c;
+        if (cnt && (c == 1 || c == -1)) { ++t1; bits += 1; cnt = t1 < 3; }
+        else {
+            cnt = false;
+            int lc = c > 0 ? (c << 1) - 2 : -(c << 1) - 1;
+            if (first_level) { sl = (tc > 10 && t1 < 3) ? 1 : 0; if (t1 < 3 && lc >= 2) lc -= 2; first_level = 0; }
+            bits += level_code_len(sl, lc);
+            if (sl == 0) sl = 1;
+            if (iabs(c) > (3 << (sl - 1)) && sl < 6) ++sl;
+        }
+        ++j;
+    }
+    out.total_coeff = (uint8_t)tc; out.trailing_ones = (uint8_t)t1; out.bits_rest = (uint16_t)bits;
+    if (tc == 1 && (first_v == 1 || first_v == -1)) out.single_ctr = (uint8_t)(hb < 6 ? (hb == 0 ? 3 : (hb < 3 ? 2 : 1)) : 0);
+    return out;
 }
 
 }  // namespace hlb

@@ -174,3 +174,13 @@ def test_bitstream_md5_drop_in(name):
     assert out.returncode == 0, out.stderr[-500:]
     got = json.loads(out.stdout.strip().splitlines()[-1])
     assert got["md5"] == str(g["bitstream_md5"]), (got, str(g["bitstream_md5"]))
+
+
+@pytest.mark.parametrize("prog", ["check_interp", "check_cavlc"])
+def test_compact_primitives_equal_reference_formulation(prog):
+    """the loop-form interpolation / register-only CAVLC length used by the kernels == the straightforward formulations
+    (which the oracle pins against the reference), on random inputs incl. saturated content"""
+    exe = "/tmp/hlb_" + prog
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-x", "c++", os.path.join(ROOT, "tools", "emu", prog + ".cpp"), "-o", exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout[-300:]
