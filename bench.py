@@ -204,13 +204,17 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     frame_b = ysz + 2 * csz
     nfr = 1 + Wm + K + 1                 # IDR + warm-up + timed + 1 spare
     # ---- S independent streams: own context, frame stores, per-MB state; own synthetic sequence (G1, distinct seeds) ----
-    encs, d_frames, h_frames = [], [], []
+    encs, d_frames, h_frames, seqs = [], [], [], {}
     for s_i in range(S):
         e = hl.Encoder(W, H, qp=QP, me_range=ME_RANGE, refs=1, device=local)
         hl.check(lib.hlb200_stream_set_cuda_stream(e.st.ctx, sp), "set_cuda_stream")
         encs.append(e)
-        g = synth.G1(W, H, seed=sharding.stream_seed(my_streams[s_i]))
-        fr = [g.next() for _ in range(nfr)]
+        # every stream has its own device buffers; the synthetic CONTENT repeats every `distinct` streams (host-side generation time)
+        key = my_streams[s_i] % args.distinct
+        if key not in seqs:
+            g = synth.G1(W, H, seed=sharding.stream_seed(key + 1000 * rank))
+            seqs[key] = [g.next() for _ in range(nfr)]
+        fr = seqs[key]
         d_frames.append([torch.from_numpy(f).to(dev) for f in fr])
         if s_i < 2:
             h_frames.append(fr)
@@ -309,7 +313,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": "%d independent 1080p (1920x1088) synthetic G1 YUV 4:2:0 streams per GPU, one P picture of each per step (one launch): Baseline/CAVLC "
+                "config": {"workload": "%d independent 1080p (1920x1088) synthetic G1 YUV 4:2:0 streams per GPU (own contexts and buffers; 16 distinct contents), one P picture of each per step (one launch): Baseline/CAVLC "
                                        "tools, 4x4 transform, 1 ref, quarter-pel ME +-%d over all 7 partition modes with the reference's RD cost, intra decision, "
                                        "reconstruction; QP %d" % (S, ME_RANGE, QP),
                            "l2": "inputs larger than L2: %d streams x (source + 2 frame stores + records + state) = %.0f MB touched per step, new source pictures every step" %
@@ -343,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="slice", choices=["batch", "slice"])
     ap.add_argument("--streams", type=int, default=128, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences; stream s shows sequence s %% distinct (own buffers)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -202,6 +202,7 @@ struct NbMotion { int avail; int ref; int mvx, mvy; };
 
 HLB_FN NbMotion nb_motion_at(const MbWork& w, const FrameCtx& f, int xN, int yN, int cur_part, int cur_sub)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     NbMotion r;
     r.avail = 0; r.ref = -1; r.mvx = 0; r.mvy = 0;
     if (xN >= 0 && xN <= 15 && yN >= 0 && yN <= 15) {  // inside the current macroblock: geometry of the mode being searched
@@ -238,6 +239,7 @@ HLB_HD int median3(int a, int b, int c)
 // 8.4.1.3 (utils.c:751-798).  (ox,oy,pw) = origin and predPartWidth of the partition under the current search mode
 HLB_FN void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, int ref, int& mx, int& my)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     int ox, oy, pw, ph;
     mode_rect(w.mode, part, sub, ox, oy, pw, ph);
     NbMotion A = nb_motion_at(w, f, ox - 1, oy, part, sub);
@@ -259,6 +261,7 @@ HLB_FN void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, in
 // 8.4.1.1 (utils.c:709-748); only ever called with the 16x16 geometry
 HLB_FN void derive_pskip_mv(const MbWork& w, const FrameCtx& f, int& mx, int& my)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     NbMotion A = nb_motion_at(w, f, -1, 0, 0, 0);
     NbMotion B = nb_motion_at(w, f, 0, -1, 0, 0);
     if (!A.avail || !B.avail || (A.ref == 0 && A.mvx == 0 && A.mvy == 0) || (B.ref == 0 && B.mvx == 0 && B.mvy == 0)) { mx = my = 0; return; }
@@ -337,6 +340,7 @@ HLB_HD void cand_origin(const MbWork& w, const FrameCtx& f, int c, int& X, int& 
 // CMD_TILE: lanes stride over the tile
 HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     const uint8_t* plane = w.ref_y;
     const int nl = w.arg0_lanes;
     for (int i = lane; i < HLB_TILE * HLB_TILE; i += nl) {
@@ -358,6 +362,7 @@ HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
 // CMD_ME_EVAL: lane = (candidate - c_begin) * nblk + k, k = raster index of the 4x4 block inside the partition
 HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     const int c = w.c_begin + (lane >> w.nblk_log2), k = lane & ((1 << w.nblk_log2) - 1);
     if (c >= w.c_end) return;
     const int bx = w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), by = w.part_oy + ((k >> w.bw_log2) << 2);
@@ -413,6 +418,7 @@ HLB_HD bool blk_in_part(const MbWork& w, int blk)
 // per block: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806)
 HLB_FN void me_phase_scan(MbWork& w, int lane)
 {
+    HLB_IN_SHARED(w);
     if (lane >= 16) return;
     int e = w.tc[lane];
     const bool in = blk_in_part(w, lane);
@@ -425,6 +431,7 @@ HLB_FN void me_phase_scan(MbWork& w, int lane)
 }
 HLB_FN void me_phase_token(MbWork& w, int lane)
 {
+    HLB_IN_SHARED(w);
     const int c = w.c_begin + (lane >> w.nblk_log2), k = lane & ((1 << w.nblk_log2) - 1);
     if (c >= w.c_end) return;
     const int blk = blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2));
@@ -458,6 +465,7 @@ HLB_HD void set_part(MbWork& w, int mode, int p, int s)
 template <class X>
 HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, int bx0, int by0, int bx1, int by1)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (!(w.tile_valid && w.tile_ref == w.ref && bx0 >= w.tile_x0 && by0 >= w.tile_y0 && bx1 <= w.tile_x0 + HLB_TILE && by1 <= w.tile_y0 + HLB_TILE)) {
         w.tile_x0 = bx0 - ((HLB_TILE - (bx1 - bx0)) >> 1); w.tile_y0 = by0 - ((HLB_TILE - (by1 - by0)) >> 1);
         w.tile_ref = w.ref; w.tile_valid = 1;
@@ -477,6 +485,7 @@ HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, in
 template <class X>
 HLB_FN void me_eval(X& x, MbWork& w, const FrameCtx& f, int px, int py)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     const int n = w.ncand;
     int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
 #pragma unroll 1
@@ -523,6 +532,7 @@ HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
 template <class X>
 HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     w.mode = mode;
     const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
 #pragma unroll 1
@@ -624,6 +634,7 @@ HLB_HD void fin_rect(const MbWork& w, int x, int y, int& part, int& sub, int& ox
 }
 HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane < 16) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
         int p, s, ox, oy;
@@ -656,6 +667,7 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 HLB_FN void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane >= 16) return;
     const int bx = blk_x(lane), by = blk_y(lane);
     uint8_t sv[16], pv[16];
@@ -710,6 +722,7 @@ HLB_FN void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 HLB_FN void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane >= 8) return;
     const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
     int m[16], lv[16];
@@ -740,6 +753,7 @@ HLB_FN void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
 }
 HLB_FN void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane != 0) return;
     int single[2] = {0, 0}, totc[2] = {0, 0};
     w.cbp_ac[0] = w.cbp_ac[1] = w.cbp_dc[0] = w.cbp_dc[1] = 0;
@@ -782,6 +796,7 @@ HLB_FN void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
 }
 HLB_FN void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane >= 8) return;
     const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
     const int dc = w.c_dccoef[c][b];
@@ -812,6 +827,7 @@ HLB_FN void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 HLB_FN void phase_load(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane < 16) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
         const uint8_t* p = f.src[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
@@ -827,6 +843,7 @@ HLB_FN void phase_load(MbWork& w, const FrameCtx& f, int lane)
 // arg0 bit 0: luma, bit 1: chroma
 HLB_FN void phase_store(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane < 16 && (w.arg0 & 1)) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
         uint8_t* p = f.cur[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
@@ -860,6 +877,7 @@ HLB_HD int cmd_phases(int cmd)
 }
 HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     switch (cmd) {
     case CMD_LOAD: phase_load(w, f, lane); break;
     case CMD_TILE: phase_tile_load(w, f, lane); break;
@@ -890,6 +908,7 @@ HLB_HD void chroma_code(X& x, MbWork& w) { x.run(CMD_CHROMA, 8); }
 
 HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb, int lane, int nl)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     w.mb = mb; w.mbx = mb % f.mbw; w.mby = mb / f.mbw;
     w.availA = w.mbx > 0; w.availB = w.mby > 0; w.availC = w.mby > 0 && w.mbx < f.mbw - 1; w.availD = w.mbx > 0 && w.mby > 0;
     const MbState& s = f.st[mb];
@@ -927,6 +946,7 @@ HLB_HD int nnz16(const int16_t* lv, int n) { int k = 0; for (int i = 0; i < n; +
 
 HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad, int lane, int nl)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     MbState& s = f.st[w.mb];
     hlb200_mb_record_t& r = f.rec[w.mb];
     // ---- record (what the host writer consumes) ----
@@ -1021,6 +1041,7 @@ HLB_HD int guess_cbp_chroma(const MbWork& w)
 template <class X>
 HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     double best_cost = DBL_MAX;
     int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0;
     int16_t best_mv[4][4][2], best_mvp[4][4][2];

@@ -41,6 +41,7 @@ struct I16Shared { I16Params q; };
 
 HLB_FN void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (phase == 0) {
         if (lane >= 64) return;
         const int m = lane >> 4, blk = lane & 15;
@@ -148,6 +149,7 @@ HLB_FN void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
 }
 HLB_FN void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     (void)f;
     if (lane >= 16) return;  // copy the reconstruction of the chosen Intra16x16 mode (identical to transf.c:298 on the same levels)
     for (int i = 0; i < 16; ++i) w.rec_y[lane * 16 + i] = w.t_pred[w.i16_mode][lane * 16 + i];
@@ -158,6 +160,7 @@ HLB_FN void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
 // ------------------------------------------------------------------------------------------------------------------
 HLB_FN void i4_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (phase != 0 || lane >= 9) return;
     const int mode = lane, blk = w.i4_blk, bx = blk_x(blk), by = blk_y(blk);
     w.q_ok[mode] = i4_mode_allowed(mode, w.p13) ? 1 : 0;
@@ -208,6 +211,7 @@ HLB_HD void i4_commit_phase(MbWork& w, const FrameCtx& f, int lane) { (void)w; (
 // ------------------------------------------------------------------------------------------------------------------
 HLB_FN void intra_chroma_pred_phase(MbWork& w, const FrameCtx& f, int lane)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     (void)f;
     if (lane >= 8) return;
     const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
@@ -223,6 +227,7 @@ HLB_FN void intra_chroma_pred_phase(MbWork& w, const FrameCtx& f, int lane)
 template <class X>
 HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cost)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     // ---- Intra16x16 (no reconstruction into the picture yet) ----
     w.p33[0] = intra_luma_at(w, f, -1, -1);
 #pragma unroll 1
@@ -372,6 +377,7 @@ HLB_HD int guess_cbp_chroma(const MbWork& w);
 
 HLB_FN void mb_commit_intra(MbWork& w, const FrameCtx& f, int kind, int lane, int nl)
 {
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     const int mad = w.arg0;
     const int cbp_luma = guess_cbp_luma(w.cbp_luma4x4, kind == MBK_I16);
     int cbp_chroma = guess_cbp_chroma(w);

@@ -19,11 +19,17 @@
 #define HLB_FN __device__ __noinline__   /* phase / control functions of the slice kernel: one copy each */
 #define HLB_TABLE __constant__   /* small read-only tables: constant cache (plain global loads are compiled .cg and would go to L2) */
 #define HLB_LDG(p) __ldg(p)   /* read-only for the whole kernel (reference / source planes): non-coherent path, L1-cacheable */
+#if defined(__CUDA_ARCH__)
+#define HLB_IN_SHARED(ref) __builtin_assume(__isShared(&(ref)))   /* lets nvcc emit LDS/STS instead of generic accesses in non-inlined functions */
+#else
+#define HLB_IN_SHARED(ref) ((void)0)
+#endif
 #else
 #define HLB_HD inline
 #define HLB_FN inline
 #define HLB_TABLE
 #define HLB_LDG(p) (*(p))
+#define HLB_IN_SHARED(ref) ((void)0)
 #endif
 
 namespace hlb {
