@@ -202,7 +202,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     my_streams = sharding.streams_of_rank(rank, world, S * world)   # weak scaling: S streams per GPU, world * S in total
     ysz, csz = W * H, W * H // 4
     frame_b = ysz + 2 * csz
-    nfr = 1 + Wm + K + 1                 # IDR + warm-up + timed + 1 spare
+    nfr = 1 + Wm + K + 2 + K             # IDR + warm-up + timed (device-resident) + e2e warm-up + e2e timed: one continuous sequence
     # ---- S independent streams: own context, frame stores, per-MB state; own synthetic sequence (G1, distinct seeds) ----
     encs, d_frames, h_frames, seqs = [], [], [], {}
     for s_i in range(S):
@@ -215,11 +215,9 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
             g = synth.G1(W, H, seed=sharding.stream_seed(key + 1000 * rank))
             seqs[key] = [g.next() for _ in range(nfr)]
         fr = seqs[key]
-        d_frames.append([torch.from_numpy(f).to(dev) for f in fr])
-        if s_i < 2:
-            h_frames.append(fr)
-    e2e_frames = min(nfr, 6)
-    pinned = [[torch.from_numpy(h_frames[s_i % 2][n]).pin_memory() for n in range(e2e_frames)] for s_i in range(2)]
+        d_frames.append([torch.from_numpy(f).to(dev) for f in fr[:1 + Wm + K]])
+    # pinned host copies of the pictures the end-to-end phase uploads (the sequences simply continue)
+    pinned = {key: {n: torch.from_numpy(fr[n]).pin_memory() for n in range(1 + Wm + K, nfr)} for key, fr in seqs.items()}
 
     def set_src(s_i, n):
         b = d_frames[s_i][n].data_ptr()
@@ -285,7 +283,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
 
     def e2e_step(n):
         for s_i, e in enumerate(encs):
-            f = pinned[s_i % 2][n % e2e_frames].numpy()
+            f = pinned[my_streams[s_i] % args.distinct][n].numpy()
             hl.check(lib.hlb200_frame_upload(e.st.ctx, hl.ptr(f[:ysz]), hl.ptr(f[ysz:ysz + csz]), hl.ptr(f[ysz + csz:]), W, W // 2), "frame_upload")
         ps = (hl.SliceParams * S)()
         ctxs = (C.c_void_p * S)()
@@ -298,11 +296,11 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
             e.advance(ps[i])
             hl.check(lib.hlb200_records_download(e.st.ctx, h_rec[i].data_ptr()), "records_download")
     for i in range(2):
-        e2e_step(1 + i)
+        e2e_step(1 + Wm + K + i)
     barrier()
     te = time.perf_counter()
     for i in range(K):
-        e2e_step(3 + i)
+        e2e_step(1 + Wm + K + 2 + i)
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([(time.perf_counter() - te) * 1e3], device=dev)
     if world > 1:
