@@ -17,6 +17,7 @@
 #pragma once
 #include <float.h>
 #include <limits.h>
+#include <stddef.h>
 
 #include "../../include/hlb200.h"
 #include "hlb_prims.cuh"
@@ -52,6 +53,9 @@ struct MbState {
     alignas(4) int16_t chroma_ac[2][4][16];  // ChromaACLevel (persistent: only rewritten for blocks with a non-zero residual, rdo.c:2577)
     int16_t chroma_dc[2][4];      // ChromaDCLevel
 };
+
+#define HLB_NB_WORDS 30   /* MbState up to and including mv[][][] */
+static_assert(offsetof(MbState, chroma_ac) == 4 * HLB_NB_WORDS, "MbState head layout");
 
 struct FrameCtx {
     int W, H, mbw, mbh;
@@ -109,6 +113,22 @@ HLB_HD void part_at(int part_mode, const uint8_t* sub_mode, int x, int y, int& p
 #define HLB_TILE 48   /* side of the shared-memory reference tile: partition (16) + 6-tap halo (5) + +-13 pixels of search freedom */
 enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_TILE, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_LUMA, CMD_CHROMA, CMD_STORE, CMD_I16_EVAL, CMD_I16_RATE, CMD_I16_RECON, CMD_I4_EVAL, CMD_I4_COMMIT, CMD_PRED_CHROMA_INTRA };
 
+// Lap timer of the profiling build: attributes the cycles since the previous HLB_LAP of this macroblock to section `slot`.
+// Sections: 0 begin/load, 1 mvp+pattern (search control), 2 me_eval prelude, 3 tile, 4 trial run, 5 scan+token, 6 cost, 7 compare,
+//           8 mode bookkeeping, 9 pskip chroma check, 10 intra, 11 final recon, 12 commit
+#if defined(HLB_PROFILE_STEPS) && defined(__CUDA_ARCH__)
+#define HLB_LAP(w, slot) do { const long long _t = clock64(); (w).prof_lap[slot] += (unsigned)(_t - (w).prof_last); (w).prof_cnt[slot]++; (w).prof_last = _t; } while (0)
+#else
+#define HLB_LAP(w, slot) do { } while (0)
+#endif
+
+// All lanes of the (master) warp call this converged; every loop is strided over them (lane, nl) -- on the CPU harness lane = 0, nl = 1.
+#if defined(__CUDA_ARCH__)
+#define HLB_LANE_SYNC() __syncwarp()
+#else
+#define HLB_LANE_SYNC() do { } while (0)
+#endif
+
 // Scratch of the macroblock being encoded (shared memory on the GPU)
 struct MbWork {
     // command mailbox
@@ -124,7 +144,14 @@ struct MbWork {
     uint8_t tc_cac[2][4];
     uint8_t cbp_gate;      // CodedBlockPatternLuma as left by the previous picture (gate of in-MB neighbours, utils.h:10-20)
     int8_t extA[16], extB[16];   // nA / nB contributed by the neighbouring macroblocks (-1 = not available), per luma4x4BlkIdx on the MB edge
+    // leading HLB_NB_WORDS words of the persistent state of [0] this address (as the previous picture left it), [1] A, [2] B, [3] C, [4] D:
+    // everything the motion / nC derivations read, fetched once with one coalesced copy instead of dependent L2 round trips per derivation
+    uint32_t nbw[5][HLB_NB_WORDS];
     unsigned prof_run_cycles, prof_runs, prof_me_cycles;   // HLB_PROFILE_STEPS builds only
+#ifdef HLB_PROFILE_STEPS
+    unsigned prof_lap[16], prof_cnt[16];                    // lap timer: cycles / visits per section (HLB_LAP)
+    long long prof_last;
+#endif
     unsigned stat_trials, stat_interp, stat_cands, stat_intra;   // work counters of the trajectory (roofline accounting)
     int stuck;             // set when a search loop exceeded its iteration cap (cannot happen for a finite window; watchdog aid)
     int last_sctr;         // rdo.Single_ctr chain; -1 = not yet written by this macroblock
@@ -215,13 +242,13 @@ HLB_FN NbMotion nb_motion_at(const MbWork& w, const FrameCtx& f, int xN, int yN,
         r.avail = 1; r.ref = w.ref_cur[p]; r.mvx = w.mv_cur[p][q][0]; r.mvy = w.mv_cur[p][q][1];
         return r;
     }
-    int addr;
-    if (yN < 0 && xN >= 0 && xN <= 15) { if (!w.availB) return r; addr = w.mb - f.mbw; }
-    else if (yN < 0 && xN > 15) { if (!w.availC) return r; addr = w.mb - f.mbw + 1; }
-    else if (yN < 0 && xN < 0) { if (!w.availD) return r; addr = w.mb - f.mbw - 1; }
-    else if (xN < 0 && yN >= 0 && yN <= 15) { if (!w.availA) return r; addr = w.mb - 1; }
+    int k;
+    if (yN < 0 && xN >= 0 && xN <= 15) { if (!w.availB) return r; k = 2; }
+    else if (yN < 0 && xN > 15) { if (!w.availC) return r; k = 3; }
+    else if (yN < 0 && xN < 0) { if (!w.availD) return r; k = 4; }
+    else if (xN < 0 && yN >= 0 && yN <= 15) { if (!w.availA) return r; k = 1; }
     else return r;
-    const MbState& s = f.st[addr];
+    const MbState& s = *(const MbState*)w.nbw[k];   // only the head (HLB_NB_WORDS words) is valid
     r.avail = 1;
     if (s.kind == MBK_I16 || s.kind == MBK_I4) return r;  // intra: ref -1, mv 0
     int p, q;
@@ -343,10 +370,23 @@ HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     const uint8_t* plane = w.ref_y;
     const int nl = w.arg0_lanes;
-    for (int i = lane; i < HLB_TILE * HLB_TILE; i += nl) {
-        const int ty = i / HLB_TILE, tx = i - ty * HLB_TILE;
-        const int y = clip3(0, f.H - 1, w.tile_y0 + ty), x = clip3(0, f.W - 1, w.tile_x0 + tx);
-        w.tile[i] = HLB_LDG(plane + y * f.W + x);
+    // eight independent loads in flight per lane (the loop was one L2 round trip per sample: 18 K cycles per tile, r01d lap profile)
+    const int W = f.W, Hm1 = f.H - 1, Wm1 = f.W - 1, x0 = w.tile_x0, y0 = w.tile_y0;
+#pragma unroll 1
+    for (int i0 = lane; i0 < HLB_TILE * HLB_TILE; i0 += 8 * nl) {
+        uint8_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * nl;
+            const int ty = i / HLB_TILE, tx = i - ty * HLB_TILE;
+            const int y = clip3(0, Hm1, y0 + ty), x = clip3(0, Wm1, x0 + tx);
+            v[u] = i < HLB_TILE * HLB_TILE ? HLB_LDG(plane + y * W + x) : (uint8_t)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * nl;
+            if (i < HLB_TILE * HLB_TILE) w.tile[i] = v[u];
+        }
     }
 }
 // sums shared by the lanes of one candidate (shared-memory atomics on the GPU, plain read-modify-write in the emulation)
@@ -469,16 +509,21 @@ HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, in
     if (!(w.tile_valid && w.tile_ref == w.ref && bx0 >= w.tile_x0 && by0 >= w.tile_y0 && bx1 <= w.tile_x0 + HLB_TILE && by1 <= w.tile_y0 + HLB_TILE)) {
         w.tile_x0 = bx0 - ((HLB_TILE - (bx1 - bx0)) >> 1); w.tile_y0 = by0 - ((HLB_TILE - (by1 - by0)) >> 1);
         w.tile_ref = w.ref; w.tile_valid = 1;
+        HLB_LAP(w, 2);
         x.run(CMD_TILE, HLB_MB_LANES);
+        HLB_LAP(w, 3);
     }
     w.c_begin = c0; w.c_end = c1;
+    HLB_LAP(w, 2);
     x.run(CMD_ME_EVAL, (c1 - c0) << w.nblk_log2);
+    HLB_LAP(w, 4);
 #pragma unroll 1
     for (int b = x.lane(); b < 16; b += x.nlanes()) me_phase_scan(w, b);
     x.sync();
 #pragma unroll 1
     for (int i = x.lane(); i < ((c1 - c0) << w.nblk_log2); i += x.nlanes()) me_phase_token(w, i);
     x.sync();
+    HLB_LAP(w, 5);
 }
 // Evaluates w.ncand candidates (w.cmvx/cmvy) of the current partition in order; leaves per-candidate dist / rbc / sctr / cbp and
 // the RD cost (me_ds.c:287,297,345: dist + (rbc + mvd bits) * lambda) in w.c_*.
@@ -486,6 +531,7 @@ template <class X>
 HLB_FN void me_eval(X& x, MbWork& w, const FrameCtx& f, int px, int py)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+    HLB_LAP(w, 1);
     const int n = w.ncand;
     int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
 #pragma unroll 1
@@ -521,6 +567,7 @@ HLB_FN void me_eval(X& x, MbWork& w, const FrameCtx& f, int px, int py)
     }
     if (x.lane() == 0) { w.stat_trials += (unsigned)(n << w.nblk_log2); w.stat_cands += (unsigned)n; }
     x.sync();
+    HLB_LAP(w, 6);
 }
 
 HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
@@ -623,7 +670,7 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
 
 // ------------------------------------------------------------------------------------------------------------------
 // Inter prediction of the whole macroblock with the committed geometry (rdo.c:2331-2416) -> w.pred_y / w.pred_c
-// lanes 0..15 luma blocks (raster), 16..23 chroma 4x4 blocks (Cb 0..3, Cr 0..3)
+// lanes 0..15 luma blocks (raster), 16..143 chroma samples (Cb 0..63, Cr 0..63)
 // ------------------------------------------------------------------------------------------------------------------
 HLB_HD void fin_rect(const MbWork& w, int x, int y, int& part, int& sub, int& ox, int& oy)
 {
@@ -645,20 +692,16 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) w.pred_y[(by + r) * 16 + bx + q] = pv[r * 4 + q];
-    } else if (lane < 24) {
-        const int c = (lane - 16) >> 2, b = (lane - 16) & 3, cx0 = (b & 1) * 4, cy0 = (b >> 1) * 4;
+    } else if (lane < 16 + 128) {   // one chroma sample per lane: the four reference loads of all samples are in flight together
+        const int idx = lane - 16, c = idx >> 6, px = idx & 7, py = (idx >> 3) & 7;
         const int Wc = f.W >> 1, Hc = f.H >> 1;
-        for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) {
-                const int px = cx0 + q, py = cy0 + r;
-                int p, s, ox, oy;
-                fin_rect(w, px * 2, py * 2, p, s, ox, oy);
-                const uint8_t* rp = f.ref[w.fin_ref[p]][1 + c];
-                const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
-                const int x0 = w.mbx * 8 + px + (mvx >> 3), y0 = w.mby * 8 + py + (mvy >> 3);
-                const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
-                w.pred_c[c][py * 8 + px] = (uint8_t)interp_chroma_px(HLB_LDG(rp + ya + xa), HLB_LDG(rp + ya + xb), HLB_LDG(rp + yc + xa), HLB_LDG(rp + yc + xb), mvx & 7, mvy & 7);
-            }
+        int p, s, ox, oy;
+        fin_rect(w, px * 2, py * 2, p, s, ox, oy);
+        const uint8_t* rp = f.ref[w.fin_ref[p]][1 + c];
+        const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
+        const int x0 = w.mbx * 8 + px + (mvx >> 3), y0 = w.mby * 8 + py + (mvy >> 3);
+        const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
+        w.pred_c[c][py * 8 + px] = (uint8_t)interp_chroma_px(HLB_LDG(rp + ya + xa), HLB_LDG(rp + ya + xb), HLB_LDG(rp + yc + xa), HLB_LDG(rp + yc + xb), mvx & 7, mvy & 7);
     }
 }
 
@@ -909,35 +952,47 @@ HLB_HD void chroma_code(X& x, MbWork& w) { x.run(CMD_CHROMA, 8); }
 HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb, int lane, int nl)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    w.mb = mb; w.mbx = mb % f.mbw; w.mby = mb / f.mbw;
-    w.availA = w.mbx > 0; w.availB = w.mby > 0; w.availC = w.mby > 0 && w.mbx < f.mbw - 1; w.availD = w.mbx > 0 && w.mby > 0;
+    const int mbx = mb % f.mbw, mby = mb / f.mbw;
+    const int availA = mbx > 0, availB = mby > 0, availC = mby > 0 && mbx < f.mbw - 1, availD = mbx > 0 && mby > 0;
+    w.mb = mb; w.mbx = mbx; w.mby = mby;
+    w.availA = availA; w.availB = availB; w.availC = availC; w.availD = availD;
     const MbState& s = f.st[mb];
+    // heads of the own and the four neighbour states: one coalesced copy
 #pragma unroll 1
-    for (int i = 0; i < 16; ++i) w.tc[i] = s.tc_luma[i];
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c)
-#pragma unroll 1
-        for (int b = 0; b < 4; ++b) { w.tc_cac[c][b] = s.tc_cac[c][b]; w.chroma_dc[c][b] = s.chroma_dc[c][b]; }
-#pragma unroll 1
-    for (int i = lane; i < 128; i += nl) (&w.chroma_ac[0][0][0])[i] = (&s.chroma_ac[0][0][0])[i];
-    w.cbp_gate = s.cbp_luma;
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) w.ref_cur[i] = s.ref_idx[i];
-#pragma unroll 1
-    for (int p = 0; p < 4; ++p)
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) { w.mv_cur[p][q][0] = s.mv[p][q][0]; w.mv_cur[p][q][1] = s.mv[p][q][1]; }
-#pragma unroll 1
-    for (int i = 0; i < 16; ++i) w.i4_mode[i] = s.i4_mode[i];
-#pragma unroll 1
-    for (int blk = 0; blk < 16; ++blk) {
-        const int bx = blk_x(blk), by = blk_y(blk);
-        w.extA[blk] = (int8_t)((bx == 0) ? (w.availA ? nb_count(f.st[mb - 1], blk_idx_from_xy(12, by)) : -1) : 0);
-        w.extB[blk] = (int8_t)((by == 0) ? (w.availB ? nb_count(f.st[mb - f.mbw], blk_idx_from_xy(bx, 12)) : -1) : 0);
+    for (int i = lane; i < 5 * HLB_NB_WORDS; i += nl) {
+        const int k = i / HLB_NB_WORDS, j = i - k * HLB_NB_WORDS;
+        const int addr = k == 0 ? mb : (k == 1 ? mb - 1 : (k == 2 ? mb - f.mbw : (k == 3 ? mb - f.mbw + 1 : mb - f.mbw - 1)));
+        const bool ok = k == 0 || (k == 1 ? availA : (k == 2 ? availB : (k == 3 ? availC : availD)));
+        w.nbw[k][j] = ok ? ((const uint32_t*)&f.st[addr])[j] : 0u;
     }
+#pragma unroll 1
+    for (int i = lane; i < 64; i += nl) ((uint32_t*)&w.chroma_ac[0][0][0])[i] = ((const uint32_t*)&s.chroma_ac[0][0][0])[i];
+#pragma unroll 1
+    for (int i = lane; i < 4; i += nl) ((uint32_t*)&w.chroma_dc[0][0])[i] = ((const uint32_t*)&s.chroma_dc[0][0])[i];
+    HLB_LANE_SYNC();
+    const MbState& o = *(const MbState*)w.nbw[0];
+    const MbState& sA = *(const MbState*)w.nbw[1];
+    const MbState& sB = *(const MbState*)w.nbw[2];
+#pragma unroll 1
+    for (int i = lane; i < 16; i += nl) {
+        w.tc[i] = o.tc_luma[i]; w.i4_mode[i] = o.i4_mode[i];
+        ((uint32_t*)&w.mv_cur[0][0][0])[i] = ((const uint32_t*)&o.mv[0][0][0])[i];
+        const int bx = blk_x(i), by = blk_y(i);
+        w.extA[i] = (int8_t)((bx == 0) ? (availA ? nb_count(sA, blk_idx_from_xy(12, by)) : -1) : 0);
+        w.extB[i] = (int8_t)((by == 0) ? (availB ? nb_count(sB, blk_idx_from_xy(bx, 12)) : -1) : 0);
+    }
+#pragma unroll 1
+    for (int i = lane; i < 8; i += nl) w.tc_cac[i >> 2][i & 3] = o.tc_cac[i >> 2][i & 3];
+#pragma unroll 1
+    for (int i = lane; i < 4; i += nl) w.ref_cur[i] = o.ref_idx[i];
+    w.cbp_gate = o.cbp_luma;
     w.last_sctr = -1; w.need_prev_sctr = 0; w.stuck = 0; w.tile_valid = 0;
     w.stat_trials = w.stat_interp = w.stat_cands = w.stat_intra = 0;
     w.prof_run_cycles = w.prof_runs = w.prof_me_cycles = 0;
+#if defined(HLB_PROFILE_STEPS) && defined(__CUDA_ARCH__)
+    for (int i = 0; i < 16; ++i) { w.prof_lap[i] = 0; w.prof_cnt[i] = 0; }
+    w.prof_last = clock64();
+#endif
     w.mb_is_intra = 0;
 }
 
@@ -950,27 +1005,28 @@ HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int 
     MbState& s = f.st[w.mb];
     hlb200_mb_record_t& r = f.rec[w.mb];
     // ---- record (what the host writer consumes) ----
-    r.mb_class = (uint8_t)kind; r.mb_type = (uint8_t)mb_type;
-    r.part_mode = (uint8_t)w.fin_mode;
+    if (lane == 0) {
+        r.mb_class = (uint8_t)kind; r.mb_type = (uint8_t)mb_type;
+        r.part_mode = (uint8_t)w.fin_mode;
+        r.i16_pred_mode = (uint8_t)w.i16_mode; r.intra_chroma_pred_mode = (uint8_t)w.intra_chroma_mode;
+        r.coded_block_pattern = (uint8_t)coded_block_pattern; r.cbp_luma = (uint8_t)cbp_luma; r.cbp_chroma = (uint8_t)cbp_chroma;
+        r.cbp_luma4x4 = (uint16_t)w.cbp_luma4x4;
+        r.mb_qp_delta = 0; r.qp_y = (uint8_t)f.qp; r.qp_c[0] = r.qp_c[1] = (uint8_t)f.qpc;
+        r.mad = mad;
+        r.me_trials = w.stat_trials; r.me_interp_ops = w.stat_interp; r.me_candidates = (uint16_t)w.stat_cands; r.intra_trials = (uint16_t)w.stat_intra;
+    }
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) { r.sub_mode[i] = (uint8_t)w.fin_sub[i]; r.ref_idx[i] = w.fin_ref[i]; }
-    r.i16_pred_mode = (uint8_t)w.i16_mode; r.intra_chroma_pred_mode = (uint8_t)w.intra_chroma_mode;
-    r.coded_block_pattern = (uint8_t)coded_block_pattern; r.cbp_luma = (uint8_t)cbp_luma; r.cbp_chroma = (uint8_t)cbp_chroma;
+    for (int i = lane; i < 4; i += nl) { r.sub_mode[i] = (uint8_t)w.fin_sub[i]; r.ref_idx[i] = w.fin_ref[i]; }
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) { r.cbp_chroma_dc4x4[c] = (uint8_t)w.cbp_dc[c]; r.cbp_chroma_ac4x4[c] = (uint8_t)w.cbp_ac[c]; }
-    r.cbp_luma4x4 = (uint16_t)w.cbp_luma4x4;
-    r.mb_qp_delta = 0; r.qp_y = (uint8_t)f.qp; r.qp_c[0] = r.qp_c[1] = (uint8_t)f.qpc;
+    for (int c = lane; c < 2; c += nl) { r.cbp_chroma_dc4x4[c] = (uint8_t)w.cbp_dc[c]; r.cbp_chroma_ac4x4[c] = (uint8_t)w.cbp_ac[c]; }
 #pragma unroll 1
-    for (int i = 0; i < 16; ++i) { r.i4_pred_mode[i] = w.i4_mode[i]; r.prev_intra4x4_pred_mode_flag[i] = w.prev_i4[i]; r.rem_intra4x4_pred_mode[i] = w.rem_i4[i]; }
+    for (int i = lane; i < 16; i += nl) { r.i4_pred_mode[i] = w.i4_mode[i]; r.prev_intra4x4_pred_mode_flag[i] = w.prev_i4[i]; r.rem_intra4x4_pred_mode[i] = w.rem_i4[i]; r.i16_dc_level[i] = w.i16_dc[i]; }
 #pragma unroll 1
-    for (int p = 0; p < 4; ++p)
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q)
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) { r.mv[p][q][k] = w.fin_mv[p][q][k]; r.mvd[p][q][k] = mvd ? mvd[p][q][k] : 0; }
-    r.mad = mad;
-    r.me_trials = w.stat_trials; r.me_interp_ops = w.stat_interp; r.me_candidates = (uint16_t)w.stat_cands; r.intra_trials = (uint16_t)w.stat_intra;
-    // level arrays: two int16 per 32-bit store, lanes strided (on the GPU the 32 lanes of the master warp share the copy)
+    for (int i = lane; i < 32; i += nl) {
+        const int p = i >> 3, q = (i >> 1) & 3, k = i & 1;
+        r.mv[p][q][k] = w.fin_mv[p][q][k]; r.mvd[p][q][k] = mvd ? mvd[p][q][k] : (int16_t)0;
+    }
+    // level arrays: two int16 per 32-bit store, lanes strided
     {
         uint32_t* d0 = (uint32_t*)&r.luma_level[0][0]; const uint32_t* s0 = (const uint32_t*)&w.luma_level[0][0];
         uint32_t* d1 = (uint32_t*)&r.i16_ac_level[0][0]; const uint32_t* s1 = (const uint32_t*)&w.i16_ac[0][0];
@@ -982,45 +1038,39 @@ HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int 
         for (int i = lane; i < 64; i += nl) d2[i] = s2[i];
     }
 #pragma unroll 1
-    for (int i = 0; i < 16; ++i) r.i16_dc_level[i] = w.i16_dc[i];
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c)
-#pragma unroll 1
-        for (int b = 0; b < 4; ++b) r.chroma_dc_level[c][b] = w.chroma_dc[c][b];
+    for (int i = lane; i < 8; i += nl) r.chroma_dc_level[i >> 2][i & 3] = w.chroma_dc[i >> 2][i & 3];
     // ---- TotalCoeffs as the writer finalises them ----
+    HLB_LANE_SYNC();
     if (kind != MBK_PSKIP) {
-        if (kind == MBK_I16) w.tc[0] = (uint8_t)nnz16(w.i16_dc, 16);
 #pragma unroll 1
-        for (int b8 = 0; b8 < 4; ++b8)
-            if ((cbp_luma >> b8) & 1)
-#pragma unroll 1
-                for (int k = 0; k < 4; ++k) {
-                    const int b = b8 * 4 + k;
-                    w.tc[b] = (uint8_t)(kind == MBK_I16 ? nnz16(w.i16_ac[b], 15) : nnz16(w.luma_level[b], 16));
-                }
+        for (int b = lane; b < 16; b += nl) {
+            int v = -1;
+            if ((cbp_luma >> (b >> 2)) & 1) v = kind == MBK_I16 ? nnz16(w.i16_ac[b], 15) : nnz16(w.luma_level[b], 16);
+            else if (kind == MBK_I16 && b == 0) v = nnz16(w.i16_dc, 16);
+            if (v >= 0) w.tc[b] = (uint8_t)v;
+        }
         if (cbp_chroma & 2)
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c)
-#pragma unroll 1
-                for (int b = 0; b < 4; ++b) w.tc_cac[c][b] = (uint8_t)(((w.cbp_ac[c] >> b) & 1) ? nnz16(w.chroma_ac[c][b], 15) : 0);
+            for (int i = lane; i < 8; i += nl) { const int c = i >> 2, b = i & 3; w.tc_cac[c][b] = (uint8_t)(((w.cbp_ac[c] >> b) & 1) ? nnz16(w.chroma_ac[c][b], 15) : 0); }
     }
+    HLB_LANE_SYNC();
     // ---- persistent state ----
-    s.kind = (uint8_t)kind;
-    s.part_mode = (uint8_t)w.fin_mode;
+    if (lane == 0) {
+        s.kind = (uint8_t)kind;
+        s.part_mode = (uint8_t)w.fin_mode;
+        s.cbp_luma = (uint8_t)cbp_luma; s.cbp_chroma = (uint8_t)cbp_chroma;
+        s.last_sctr = (uint8_t)(w.last_sctr < 0 ? 255 : w.last_sctr);
+    }
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) { s.sub_mode[i] = (uint8_t)w.fin_sub[i]; s.ref_idx[i] = w.ref_cur[i]; }
-    s.cbp_luma = (uint8_t)cbp_luma; s.cbp_chroma = (uint8_t)cbp_chroma;
+    for (int i = lane; i < 4; i += nl) { s.sub_mode[i] = (uint8_t)w.fin_sub[i]; s.ref_idx[i] = w.ref_cur[i]; }
 #pragma unroll 1
-    for (int i = 0; i < 16; ++i) { s.tc_luma[i] = w.tc[i]; s.i4_mode[i] = w.i4_mode[i]; }
+    for (int i = lane; i < 16; i += nl) { s.tc_luma[i] = w.tc[i]; s.i4_mode[i] = w.i4_mode[i]; }
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c)
-#pragma unroll 1
-        for (int b = 0; b < 4; ++b) { s.tc_cac[c][b] = w.tc_cac[c][b]; s.chroma_dc[c][b] = w.chroma_dc[c][b]; }
+    for (int i = lane; i < 8; i += nl) { s.tc_cac[i >> 2][i & 3] = w.tc_cac[i >> 2][i & 3]; s.chroma_dc[i >> 2][i & 3] = w.chroma_dc[i >> 2][i & 3]; }
 #pragma unroll 1
     for (int i = lane; i < 64; i += nl) ((uint32_t*)&s.chroma_ac[0][0][0])[i] = ((const uint32_t*)&w.chroma_ac[0][0][0])[i];
 #pragma unroll 1
     for (int i = lane; i < 16; i += nl) ((uint32_t*)&s.mv[0][0][0])[i] = ((const uint32_t*)&w.mv_cur[0][0][0])[i];
-    s.last_sctr = (uint8_t)(w.last_sctr < 0 ? 255 : w.last_sctr);
 }
 
 HLB_HD int guess_cbp_luma(int cbp4x4, bool i16)
@@ -1054,7 +1104,9 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
             const int m0 = g < 3 ? g : 3, m1 = g < 3 ? g : 6;
 #pragma unroll 1
             for (int mode = m0; mode <= m1; ++mode) {
+                HLB_LAP(w, 8);
                 me_find_best_cost(x, w, f, mode);
+                HLB_LAP(w, 7);
                 double cost_sum = 0;
                 int dist_sum = 0, sctr_sum = 0;
                 probably_pskip = w.probably_pskip;
@@ -1086,20 +1138,25 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
                 w.fin_mode = 0; w.fin_sub[0] = w.fin_sub[1] = w.fin_sub[2] = w.fin_sub[3] = 0;
                 w.fin_ref[0] = 0; w.fin_mv[0][0][0] = best_mv[0][0][0]; w.fin_mv[0][0][1] = best_mv[0][0][1];
                 w.mb_is_intra = 0;
-                x.run(CMD_PRED_INTER, 24);
+                HLB_LAP(w, 8);
+                x.run(CMD_PRED_INTER, 144);
                 chroma_code(x, w);
                 b_pskip = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1];
+                HLB_LAP(w, 9);
             }
             found |= (best_cost == 0) || b_pskip;
         }
     }
     if (!b_pskip) {
         double intra_cost;
+        HLB_LAP(w, 8);
         const int intra_kind = mb_encode_intra(x, w, f, intra_cost);  // reconstructs into the picture and commits when it wins (rdo.c:1161-1167)
+        HLB_LAP(w, 10);
         HLB_DBG("  intra cost %.4f (kind %d) vs inter %.4f (mode %d)\n", intra_cost, intra_kind, best_cost, best_mode);
         if (intra_cost <= best_cost) { mb_commit_intra(w, f, intra_kind, x.lane(), x.nlanes()); return; }
     }
     // ---- commit the best inter layout (rdo.c:1170-1218) ----
+    HLB_LAP(w, 8);
     w.mb_is_intra = 0;
     w.fin_mode = best_mode < 3 ? best_mode : 3;
     const int fs = best_mode <= 3 ? 0 : best_mode - 3;
@@ -1131,7 +1188,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         w.cbp_luma4x4 = 0;
         kind = MBK_PSKIP; mb_type = 5;
     } else {
-        x.run(CMD_PRED_INTER, 24);
+        x.run(CMD_PRED_INTER, 144);
         w.luma_skip_residual = best_sctr < 6;
         x.run(CMD_RECON_LUMA, 16);
         w.cbp_luma4x4 = 0;
@@ -1154,7 +1211,9 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
             if (sx == best_mvp[0][0][0] && sy == best_mvp[0][0][1]) { kind = MBK_PSKIP; mb_type = 5; }
         }
     }
+    HLB_LAP(w, 11);
     mb_commit(w, f, kind, cbp_luma, cbp_chroma, cbp, mb_type, mvd, best_dist, x.lane(), x.nlanes());
+    HLB_LAP(w, 12);
 }
 
 template <class X>
@@ -1163,6 +1222,7 @@ HLB_HD void mb_encode(X& x, MbWork& w, const FrameCtx& f, int mb)
     mb_begin(w, f, mb, x.lane(), x.nlanes());
     x.sync();
     x.run(CMD_LOAD, 24);
+    HLB_LAP(w, 0);
     if (f.is_p) mb_encode_p(x, w, f);
     else {
         double c;

@@ -339,9 +339,9 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
             const int bx = blk_x(blk), by = blk_y(blk);
             int mA = -1, mB = -1;  // -1: neighbour macroblock not available
             if (bx > 0) mA = w.i4_mode[blk_idx_from_xy(bx - 4, by)];
-            else if (w.availA) { const MbState& s = f.st[w.mb - 1]; mA = s.kind == MBK_I4 ? s.i4_mode[blk_idx_from_xy(12, by)] : 2; }
+            else if (w.availA) { const MbState& s = *(const MbState*)w.nbw[1]; mA = s.kind == MBK_I4 ? s.i4_mode[blk_idx_from_xy(12, by)] : 2; }
             if (by > 0) mB = w.i4_mode[blk_idx_from_xy(bx, by - 4)];
-            else if (w.availB) { const MbState& s = f.st[w.mb - f.mbw]; mB = s.kind == MBK_I4 ? s.i4_mode[blk_idx_from_xy(bx, 12)] : 2; }
+            else if (w.availB) { const MbState& s = *(const MbState*)w.nbw[2]; mB = s.kind == MBK_I4 ? s.i4_mode[blk_idx_from_xy(bx, 12)] : 2; }
             if (mA < 0 || mB < 0) mA = mB = 2;
             const int pm = mA < mB ? mA : mB, cur = w.i4_mode[blk];
             if (pm == cur) { w.prev_i4[blk] = 1; }

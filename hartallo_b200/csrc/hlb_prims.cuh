@@ -495,40 +495,60 @@ HLB_HD CavlcInfo cavlc_block_info_ref(const int* lv, int n, bool chroma_dc)
 }
 
 
-// Register-only formulation for the only shape the kernels use (16 coefficients, luma/chroma-AC tables): the levels are packed
-// into a 256-bit shift register that is consumed from the high-frequency end by a loop that is NOT unrolled -- no local-memory
-// arrays, ~1 KB of code.  Run lengths and level codes are produced on the fly in coding order (residual.c:757-898).
-HLB_HD uint32_t funnel_l16(uint32_t lo, uint32_t hi) { return (hi << 16) | (lo >> 16); }
+// Register-only formulation for the only shape the kernels use (16 coefficients, luma/chroma-AC tables).  The loop visits only the
+// NON-ZERO coefficients, from the high-frequency end, located with count-leading-zeros on the significance mask; a coefficient is
+// fetched from the eight packed registers with a 3-level select tree (no local-memory array, no dynamic register indexing).  Run
+// lengths come from the distance between consecutive set bits.  Typical residual blocks of the search hold 1-4 coefficients, so
+// this executes ~4x fewer instructions than a scan over all 16 positions (r01c profile: the scan form was 1/3 of the slice kernel).
+HLB_HD int hlb_clz(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+HLB_HD int hlb_popc(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
 HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
 {
     if (n != 16 || chroma_dc) return cavlc_block_info_ref(lv, n, chroma_dc);
-    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, mask = 0;
+    uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) mask |= (uint32_t)(lv[i] != 0) << i;
     CavlcInfo out;
     out.total_coeff = 0; out.trailing_ones = 0; out.single_ctr = 9; out.bits_rest = 0;
     if (mask == 0) return out;
-    r0 = ((uint32_t)lv[0] & 0xffffu) | ((uint32_t)lv[1] << 16); r1 = ((uint32_t)lv[2] & 0xffffu) | ((uint32_t)lv[3] << 16);
-    r2 = ((uint32_t)lv[4] & 0xffffu) | ((uint32_t)lv[5] << 16); r3 = ((uint32_t)lv[6] & 0xffffu) | ((uint32_t)lv[7] << 16);
-    r4 = ((uint32_t)lv[8] & 0xffffu) | ((uint32_t)lv[9] << 16); r5 = ((uint32_t)lv[10] & 0xffffu) | ((uint32_t)lv[11] << 16);
-    r6 = ((uint32_t)lv[12] & 0xffffu) | ((uint32_t)lv[13] << 16); r7 = ((uint32_t)lv[14] & 0xffffu) | ((uint32_t)lv[15] << 16);
-    int tc = 0, hb = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { tc += (mask >> i) & 1; if ((mask >> i) & 1) hb = i; }
+    const uint32_t r0 = ((uint32_t)lv[0] & 0xffffu) | ((uint32_t)lv[1] << 16), r1 = ((uint32_t)lv[2] & 0xffffu) | ((uint32_t)lv[3] << 16);
+    const uint32_t r2 = ((uint32_t)lv[4] & 0xffffu) | ((uint32_t)lv[5] << 16), r3 = ((uint32_t)lv[6] & 0xffffu) | ((uint32_t)lv[7] << 16);
+    const uint32_t r4 = ((uint32_t)lv[8] & 0xffffu) | ((uint32_t)lv[9] << 16), r5 = ((uint32_t)lv[10] & 0xffffu) | ((uint32_t)lv[11] << 16);
+    const uint32_t r6 = ((uint32_t)lv[12] & 0xffffu) | ((uint32_t)lv[13] << 16), r7 = ((uint32_t)lv[14] & 0xffffu) | ((uint32_t)lv[15] << 16);
+    const int tc = hlb_popc(mask), hb = 31 - hlb_clz(mask);
     const int tz = hb + 1 - tc;
     int bits = 0, zl = 0;
     if (tc < 16) { bits += kTotalZerosLen[tc - 1][tz]; zl = tz; }
-    int t1 = 0, sl = 0, j = 0, run = 0, first_level = 1, first_v = 0;
+    int t1 = 0, sl = 0, first_level = 1, first_v = 0, prev_p = hb;
     bool cnt = true;
+    uint32_t m = mask;
 #pragma unroll 1
-    for (int p = 15; p >= 0 && j < tc; --p) {
-        const int c = (int)(int16_t)(r7 >> 16);
-        r7 = funnel_l16(r6, r7); r6 = funnel_l16(r5, r6); r5 = funnel_l16(r4, r5); r4 = funnel_l16(r3, r4);
-        r3 = funnel_l16(r2, r3); r2 = funnel_l16(r1, r2); r1 = funnel_l16(r0, r1); r0 <<= 16;
-        if (c == 0) { if (j > 0) ++run; continue; }
-        if (j > 0 && zl > 0) { bits += kRunBeforeLen[(zl > 7 ? 7 : zl) - 1][run]; zl -= run; }   // run_before of the previous coefficient
-        run = 0;
-        if (j == 0) first_v = c;
+    while (m) {
+        const int p = 31 - hlb_clz(m);
+        m &= ~(1u << p);
+        const uint32_t q0 = (p & 2) ? r1 : r0, q1 = (p & 2) ? r3 : r2, q2 = (p & 2) ? r5 : r4, q3 = (p & 2) ? r7 : r6;
+        const uint32_t h0 = (p & 4) ? q1 : q0, h1 = (p & 4) ? q3 : q2;
+        const uint32_t wv = (p & 8) ? h1 : h0;
+        const int c = (int)(int16_t)(uint16_t)(wv >> ((p & 1) << 4));
+        if (p != hb) {   // run_before of the previous (higher-frequency) coefficient = zeros between it and this one
+            const int run = prev_p - p - 1;
+            if (zl > 0) { bits += kRunBeforeLen[(zl > 7 ? 7 : zl) - 1][run]; zl -= run; }
+        } else first_v = c;
+        prev_p = p;
         if (cnt && (c == 1 || c == -1)) { ++t1; bits += 1; cnt = t1 < 3; }
         else {
             cnt = false;
@@ -538,7 +558,6 @@ HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
             if (sl == 0) sl = 1;
             if (iabs(c) > (3 << (sl - 1)) && sl < 6) ++sl;
         }
-        ++j;
     }
     out.total_coeff = (uint8_t)tc; out.trailing_ones = (uint8_t)t1; out.bits_rest = (uint16_t)bits;
     if (tc == 1 && (first_v == 1 || first_v == -1)) out.single_ctr = (uint8_t)(hb < 6 ? (hb == 0 ? 3 : (hb < 3 ? 2 : 1)) : 0);

@@ -14,6 +14,8 @@
 // as every WARP is converged at its own call site (bar.sync == barrier.sync.aligned).  Global loads are compiled .cg (-Xptxas -dlcm=cg) so that state and
 // reconstruction written by other CTAs is read from L2; read-only planes go through __ldg.
 #include <new>
+#include <stdlib.h>
+#include <string.h>
 
 #include "hlb_common.cuh"
 #include "hlb_mbcore.cuh"
@@ -46,7 +48,7 @@ __device__ __forceinline__ void watchdog_fire(Sched* s, int code, int a, int b)
 #endif
 #define HLB_CTA_THREADS (HLB_WORKERS + 32)
 #ifndef HLB_SLICE_MIN_CTAS
-#define HLB_SLICE_MIN_CTAS 3   /* register budget: 65536 / (3 x 192) = 113 -> ptxas rounds down */
+#define HLB_SLICE_MIN_CTAS 6   /* register budget: 65536 / (6 x 96) = 113 -> ptxas settles at 96; measured best of {3,6,8} x {32,64,128} workers (r01c sweep) */
 #endif
 __device__ __forceinline__ void cta_bar() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(HLB_CTA_THREADS) : "memory"); }
 __device__ __forceinline__ int ld_volatile(const int* p) { return *(const volatile int*)p; }
@@ -122,6 +124,51 @@ __global__ void k_slice_init(SliceJob* jobs, int njobs, int* sched_buf, int tota
     }
 }
 
+// ---- scheduler steps shared by both kernels (executed by ONE thread) ----
+// pops the next ready macroblock: returns the item (or -1 when the batch is drained / aborted) and the job that owns it
+__device__ __forceinline__ int sched_pop(Sched* s, const int* queue, int total, const SliceJob* jobs, int njobs, int* job_out)
+{
+    const int idx = atomicAdd(&s->head, 1);
+    int item = -1;
+    if (idx < total && !ld_volatile(&s->abort)) {
+        int spins = 0;
+        unsigned ns = 64;   // exponential back-off: idle CTAs must not steal issue slots / L2 bandwidth from working ones
+        while ((item = ld_volatile(queue + idx)) < 0) {
+            if ((spins & 15) == 15 && ld_volatile(&s->abort)) break;
+            if (++spins > HLB_SPIN_LIMIT / 8) { watchdog_fire(s, WD_QUEUE, idx, ld_volatile(&s->tail)); break; }
+            __nanosleep(ns);
+            if (ns < 2048) ns <<= 1;
+        }
+        __threadfence();
+    }
+    if (item >= 0) {
+        int lo = 0, hi = njobs - 1;   // jobs[].base is ascending
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].base <= item) lo = mid; else hi = mid - 1; }
+        *job_out = lo;
+    }
+    return item;
+}
+// publishes a finished macroblock and releases its successors (see the header comment)
+__device__ __forceinline__ void sched_finish(Sched* s, int* queue, int* deps, int* done, const FrameCtx& sf, int nmb, int item, int mb)
+{
+    __threadfence();
+    atomicExch(done + item, 1);
+    const int mbw = sf.mbw, mbh = sf.mbh, x = mb % mbw, y = mb / mbw;
+    int succ[3], ns = 0;
+    if (sf.is_p) {
+        if (x + 1 < mbw) succ[ns++] = item + 1;
+        if (y + 1 < mbh) {
+            if (x >= 1) succ[ns++] = item + mbw - 1;          // (x-1, y+1): its top-right is this macroblock
+            if (x == mbw - 1) succ[ns++] = item + mbw;        // last column waits for its top neighbour
+        }
+    } else if (mb + 1 < nmb) succ[ns++] = item + 1;
+    for (int k = 0; k < ns; ++k)
+        if (atomicSub(deps + succ[k], 1) == 1) {
+            const int slot = atomicAdd(&s->tail, 1);
+            atomicExch(queue + slot, succ[k]);
+        }
+}
+
 __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_encode(const SliceJob* __restrict__ jobs, int njobs, int* sched_buf)
 {
     __shared__ MbWork w;
@@ -134,27 +181,7 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_e
     int* done = deps + total;
     const int tid = threadIdx.x;
     for (;;) {
-        if (tid == 0) {
-            const int idx = atomicAdd(&s->head, 1);
-            int item = -1;
-            if (idx < total && !ld_volatile(&s->abort)) {
-                int spins = 0;
-                unsigned ns = 64;   // exponential back-off: idle CTAs must not steal issue slots / L2 bandwidth from working ones
-                while ((item = ld_volatile(queue + idx)) < 0) {
-                    if ((spins & 15) == 15 && ld_volatile(&s->abort)) break;
-                    if (++spins > HLB_SPIN_LIMIT / 8) { watchdog_fire(s, WD_QUEUE, idx, ld_volatile(&s->tail)); break; }
-                    __nanosleep(ns);
-                    if (ns < 2048) ns <<= 1;
-                }
-                __threadfence();
-            }
-            s_item = item;
-            if (item >= 0) {
-                int jb = 0;
-                while (jb + 1 < njobs && jobs[jb + 1].base <= item) ++jb;
-                s_job = jb;
-            }
-        }
+        if (tid == 0) { int jb = 0; s_item = sched_pop(s, queue, total, jobs, njobs, &jb); s_job = jb; }
         __syncthreads();
         const int item = s_item;
         if (item < 0) break;
@@ -196,27 +223,98 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_e
             sf.rec[mb].t_start_ns = t_start; sf.rec[mb].t_end_ns = (unsigned)t;
 #ifdef HLB_PROFILE_STEPS
             sf.rec[mb].mad = (int)w.prof_run_cycles; sf.rec[mb].i16_dc_level[0] = (int16_t)w.prof_runs; sf.rec[mb].me_interp_ops = w.prof_me_cycles;
+            for (int i = 0; i < 16; ++i) { ((unsigned*)&sf.rec[mb].i16_ac_level[0][0])[i] = w.prof_lap[i]; ((unsigned*)&sf.rec[mb].i16_ac_level[0][0])[16 + i] = w.prof_cnt[i]; }
 #endif
-            __threadfence();
-            atomicExch(done + item, 1);
-            // successors (see the header comment)
-            const int mbw = sf.mbw, mbh = sf.mbh, x = mb % mbw, y = mb / mbw;
-            int succ[3], ns = 0;
-            if (sf.is_p) {
-                if (x + 1 < mbw) succ[ns++] = item + 1;
-                if (y + 1 < mbh) {
-                    if (x >= 1) succ[ns++] = item + mbw - 1;          // (x-1, y+1): its top-right is this macroblock
-                    if (x == mbw - 1) succ[ns++] = item + mbw;        // last column waits for its top neighbour
-                    if (mbw == 1) {}                                   // (covered by the line above)
-                }
-            } else if (mb + 1 < job->nmb) succ[ns++] = item + 1;
-            for (int k = 0; k < ns; ++k)
-                if (atomicSub(deps + succ[k], 1) == 1) {
-                    const int slot = atomicAdd(&s->tail, 1);
-                    atomicExch(queue + slot, succ[k]);
-                }
+            sched_finish(s, queue, deps, done, sf, job->nmb, item, mb);
         }
         __syncthreads();
+    }
+}
+
+// ---- throughput variant: ONE WARP per macroblock ----
+// The same warp runs the serial control flow (all lanes redundantly) and, inside run(), the command phases with the command's logical lanes
+// strided over its 32 lanes.  No CTA barrier exists, so no warp ever waits for another: with enough independent streams in the batch every
+// resident warp is runnable all the time (the CTA variant above keeps two thirds of its warps parked at a barrier, r01c profile).
+// One warp = one CTA, so the per-macroblock scratch is the CTA's static shared memory.
+#ifndef HLB_WARP_MIN_CTAS
+#define HLB_WARP_MIN_CTAS 16
+#endif
+struct WarpExec {
+    MbWork* w;
+    const FrameCtx* f;
+    const SliceJob* job;
+    const int* done;
+    Sched* sched;
+    __device__ __noinline__ void run(int cmd, int nlanes)
+    {
+        w->arg0_lanes = nlanes;
+        __syncwarp();
+        const int np = cmd_phases(cmd), l = (int)(threadIdx.x & 31);
+#pragma unroll 1
+        for (int p = 0; p < np; ++p) {
+#pragma unroll 1
+            for (int lane = l; lane < nlanes; lane += 32) cmd_phase(*w, *f, cmd, p, lane);
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ int nlanes() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __noinline__ int prev_sctr(int mb)
+    {
+        for (int a = mb - 1; a >= 0; --a) {
+            int spins = 0;
+            while (ld_volatile(done + job->base + a) == 0) {
+                if (ld_volatile(&sched->abort)) return 0;
+                if (++spins > HLB_SPIN_LIMIT) { watchdog_fire(sched, WD_PREV, job->base + mb, a); return 0; }
+                __nanosleep(200);
+            }
+            __threadfence();
+            const int v = *(volatile const uint8_t*)&f->st[a].last_sctr;
+            if (v != 255) return v;
+        }
+        return job->prev_frame_sctr;
+    }
+};
+
+__global__ void __launch_bounds__(32, HLB_WARP_MIN_CTAS) k_slice_encode_warp(const SliceJob* __restrict__ jobs, int njobs, int* sched_buf)
+{
+    __shared__ MbWork w;
+    __shared__ FrameCtx sf;
+    Sched* s = (Sched*)sched_buf;
+    const int total = s->total;
+    int* queue = sched_buf + HLB_SCHED_WORDS;
+    int* deps = queue + total;
+    int* done = deps + total;
+    const int tid = threadIdx.x;
+    for (;;) {
+        int item = -1, jb = 0;
+        if (tid == 0) item = sched_pop(s, queue, total, jobs, njobs, &jb);
+        item = __shfl_sync(0xffffffffu, item, 0); jb = __shfl_sync(0xffffffffu, jb, 0);
+        if (item < 0) break;
+        const SliceJob* job = jobs + jb;
+        {
+            const int* src = (const int*)&job->f;
+            int* dst = (int*)&sf;
+            for (int i = tid; i < (int)(sizeof(FrameCtx) / sizeof(int)); i += 32) dst[i] = src[i];
+        }
+        __syncwarp();
+        const int mb = item - job->base;
+        unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        WarpExec x;
+        x.w = &w; x.f = &sf; x.job = job; x.done = done; x.sched = s;
+        mb_encode(x, w, sf, mb);
+        __syncwarp();
+        if (tid == 0) {
+            if (w.stuck) watchdog_fire(s, WD_SEARCH, item, 0);
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            sf.rec[mb].t_start_ns = (unsigned)t0; sf.rec[mb].t_end_ns = (unsigned)t;
+#ifdef HLB_PROFILE_STEPS
+            for (int i = 0; i < 16; ++i) { ((unsigned*)&sf.rec[mb].i16_ac_level[0][0])[i] = w.prof_lap[i]; ((unsigned*)&sf.rec[mb].i16_ac_level[0][0])[16 + i] = w.prof_cnt[i]; }
+#endif
+            sched_finish(s, queue, deps, done, sf, job->nmb, item, mb);
+        }
+        __syncwarp();
     }
 }
 
@@ -254,18 +352,39 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     return HLB200_OK;
 }
 
-static int g_slice_grid = 0;
-static int slice_grid()
+static int g_slice_grid[2] = {0, 0};
+// resident CTAs of the whole device for variant v (0 = CTA per macroblock, 1 = warp per macroblock)
+static int slice_grid(int v)
 {
-    if (g_slice_grid) return g_slice_grid;
+    if (g_slice_grid[v]) return g_slice_grid[v];
     int dev = 0, sms = 0, per = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_slice_encode, HLB_CTA_THREADS, 0) != cudaSuccess || per < 1) {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_slice_encode_warp, 32, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_slice_encode, HLB_CTA_THREADS, 0);
+    if (e != cudaSuccess || per < 1) {
         cudaGetLastError();
         return 148;
     }
-    g_slice_grid = sms * per;
-    return g_slice_grid;
+    g_slice_grid[v] = sms * per;
+    return g_slice_grid[v];
+}
+// Which variant serves a batch.  The warp variant wins on throughput when the batch offers more ready macroblocks than the CTA variant has
+// CTAs (its macroblocks take longer individually); the CTA variant wins on latency for small batches.  HLB200_SLICE_KERNEL=cta|warp overrides.
+static int g_slice_force = -2;   // -2 = not initialised, -1 = automatic, 0 / 1 = forced
+static int g_slice_last = 0;
+static int slice_force()
+{
+    if (g_slice_force == -2) {
+        const char* e = getenv("HLB200_SLICE_KERNEL");
+        g_slice_force = !e ? -1 : (!strcmp(e, "warp") ? 1 : (!strcmp(e, "cta") ? 0 : -1));
+    }
+    return g_slice_force;
+}
+static int slice_variant(int n_pictures, int mean_wavefront)
+{
+    const int f = slice_force();
+    if (f >= 0) return f;
+    return (long long)n_pictures * mean_wavefront >= 2LL * slice_grid(0) ? 1 : 0;
 }
 
 }  // namespace hlb
@@ -312,9 +431,12 @@ int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_para
     c0->last_sched = sched;
     k_slice_init<<<(total + 255) / 256, 256, 0, st>>>(dj, n, sched, total);
     HLB_CUDA(cudaGetLastError());
-    int grid = slice_grid();
+    // mean width of the 2:1 wavefront of a picture = macroblocks / (mbw + 2 (mbh - 1)) dependency steps
+    const int variant = g_slice_last = slice_variant(n, (c0->nmb + c0->mbw + 2 * c0->mbh - 3) / (c0->mbw + 2 * c0->mbh - 2));
+    int grid = slice_grid(variant);
     if (grid > total) grid = total;
-    k_slice_encode<<<grid, HLB_CTA_THREADS, 0, st>>>(dj, n, sched);
+    if (variant) k_slice_encode_warp<<<grid, 32, 0, st>>>(dj, n, sched);
+    else k_slice_encode<<<grid, HLB_CTA_THREADS, 0, st>>>(dj, n, sched);
     HLB_CUDA(cudaGetLastError());
     for (int i = 0; i < n; ++i) ctxs[i]->frame_count++;
     return HLB200_OK;
@@ -348,6 +470,12 @@ int hlb200_slice_encode(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params, 
     return hlb200_records_download(ctx, out_records);
 }
 
-int hlb200_slice_grid_size(void) { return slice_grid(); }
+int hlb200_slice_grid_size(void) { return slice_grid(slice_force() >= 0 ? slice_force() : g_slice_last); }
+int hlb200_slice_set_variant(int variant)
+{
+    const int prev = slice_force();
+    g_slice_force = variant == 0 || variant == 1 ? variant : -1;
+    return prev;
+}
 
 }  // extern "C"

@@ -53,7 +53,7 @@ def load():
         "hlb200_stream_sync": [vp], "hlb200_frame_upload": [vp, vp, vp, vp, ip, ip], "hlb200_frame_set_device": [vp, vp, vp, vp], "hlb200_slot_upload": [vp, ip, vp, vp, vp],
         "hlb200_slot_download": [vp, ip, vp, vp, vp], "hlb200_state_reset": [vp],
         "hlb200_slice_encode": [vp, C.POINTER(SliceParams), vp], "hlb200_slice_encode_async": [vp, C.POINTER(SliceParams)], "hlb200_records_download": [vp, vp],
-        "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_status": [vp, vp],
+        "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_set_variant": [ip], "hlb200_slice_status": [vp, vp],
         "hlb200_interp_luma": [vp, ip, vp, vp], "hlb200_interp_chroma": [vp, ip, vp, vp, vp],
         "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
         "hlb200_dev_interp_luma": [vp, ip, ip, vp, vp, vp], "hlb200_dev_interp_chroma": [vp, vp, ip, ip, vp, vp, vp, vp],

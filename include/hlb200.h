@@ -169,7 +169,11 @@ HLB200_API int hlb200_records_download(hlb200_ctx_t* ctx, hlb200_mb_record_t* ou
 HLB200_API int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_params_t* params, int n);
 /* watchdog words of the last slice launch: out16[3] != 0 means a wait inside the kernel gave up (HLB200_ERR_INVALID_STATE) */
 HLB200_API int hlb200_slice_status(hlb200_ctx_t* ctx, int* out16);
-HLB200_API int hlb200_slice_grid_size(void); /* CTAs the slice kernel keeps resident on the current device */
+HLB200_API int hlb200_slice_grid_size(void); /* CTAs the slice kernel variant last launched (or selected) keeps resident on the current device */
+/* slice kernel variant: 0 = one CTA per macroblock (lowest latency per picture), 1 = one warp per macroblock (highest throughput for
+ * large batches), -1 = chosen per launch from the batch size (default).  Results are identical.  Returns the previous setting.
+ * The environment variable HLB200_SLICE_KERNEL=cta|warp sets the initial value. */
+HLB200_API int hlb200_slice_set_variant(int variant);
 
 /* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
 HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);

@@ -88,9 +88,18 @@ def test_control_flow_vs_reference_cpu(name):
         check_frame(g, n, rec[n], recon[n], "emu/" + name)
 
 
+@pytest.fixture(params=["cta", "warp"])
+def variant(request):
+    """both slice-kernel variants (one CTA / one warp per macroblock) must give the reference's results"""
+    from hartallo_b200 import lib as hl
+    prev = hl.load().hlb200_slice_set_variant(0 if request.param == "cta" else 1)
+    yield request.param
+    hl.load().hlb200_slice_set_variant(prev)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CONFIGS)
-def test_slice_encode_vs_reference(name):
+def test_slice_encode_vs_reference(name, variant):
     from hartallo_b200 import lib as hl
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
@@ -103,7 +112,7 @@ def test_slice_encode_vs_reference(name):
 
 
 @pytest.mark.gpu
-def test_slice_encode_batch_of_streams():
+def test_slice_encode_batch_of_streams(variant):
     """several independent streams (different sizes and contents) in one launch give the same pictures as one by one"""
     from hartallo_b200 import lib as hl
     names = ["g2_qcif", "g1_qcif", "g2_small_q12"]
@@ -142,7 +151,7 @@ def test_slice_encode_vs_live_reference():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("gen", ["g1", "g2"])
-def test_slice_encode_1080p_recon_md5(gen):
+def test_slice_encode_1080p_recon_md5(gen, variant):
     """BASELINE.json's full size (1920x1088, ME +-32): reconstruction MD5 of an IDR and a P picture against the reference's"""
     import json
     from hartallo_b200 import lib as hl

@@ -13,10 +13,27 @@ for n in range(3):
     for e in encs:
         hl.check(e.st.lib.hlb200_stream_sync(e.st.ctx), "sync")
 mbw = W // 16
+# whole-launch occupancy of the persistent CTAs: busy CTA-time / (span x grid), and MBs in flight over time
+allrec = []
+for e in encs:
+    r_ = np.zeros(e.st.nmb, hl.MB_RECORD)
+    hl.check(e.st.lib.hlb200_records_download(e.st.ctx, hl.ptr(r_)), "dl")
+    allrec.append(r_)
+A0 = np.concatenate([r_["t_start_ns"].astype(np.int64) for r_ in allrec]); A1 = np.concatenate([r_["t_end_ns"].astype(np.int64) for r_ in allrec])
+b0 = A0.min(); A0 -= b0; A1 -= b0
+A1 = np.where(A1 < A0, A1 + (1 << 32), A1)
+span = A1.max()
+grid = e.st.lib.hlb200_slice_grid_size()
+print("launch: %d streams, span %.1f ms, grid %d CTAs, busy CTA-time %.1f s -> CTA utilisation %.1f%%, mean MB latency %.0f us" % (S, span / 1e6, grid, (A1 - A0).sum() / 1e9, 100.0 * (A1 - A0).sum() / (span * grid), (A1 - A0).mean() / 1e3))
+ts = np.linspace(0, span, 21)[1:-1]
+print("MBs in flight at 5%..95% of the span:", [int(((A0 <= t) & (A1 > t)).sum()) for t in ts])
+fin = np.array([ (r_["t_end_ns"].astype(np.int64) - b0).max() for r_ in allrec]) / 1e6
+print("per-stream finish time ms: min %.1f median %.1f max %.1f" % (fin.min(), np.median(fin), fin.max()))
 for i, e in enumerate(encs[:1]):
     rec = np.zeros(e.st.nmb, hl.MB_RECORD)
     hl.check(e.st.lib.hlb200_records_download(e.st.ctx, hl.ptr(rec)), "dl")
     t0 = rec["t_start_ns"].astype(np.int64); t1 = rec["t_end_ns"].astype(np.int64)
+    t1 = np.where(t1 < t0, t1 + (1 << 32), t1)
     base = t0.min(); t0 -= base; t1 -= base
     lat = (t1 - t0) / 1e3
     print("frame span %.1f ms" % ((t1.max()) / 1e6))
@@ -46,6 +63,15 @@ for i, e in enumerate(encs[:1]):
     print("critical path: %d MBs, sum latency %.1f ms, classes %s, total cands %d" % (len(path), lat[path].sum() / 1e3, np.bincount(rec["mb_class"][path], minlength=4), rec["me_candidates"][path].sum()))
     print("us per candidate step (inter MBs): %.1f" % (lat[rec["mb_class"] == 1].sum() / max(1, rec["me_candidates"][rec["mb_class"] == 1].sum())))
     if os.environ.get("HLB200_LIB", "").endswith("_prof.so"):
+        names = ["begin/load", "search ctl", "eval prelude", "tile", "trial run", "scan+token", "cost", "find tail", "mode bookkeeping", "pskip chroma", "intra", "final recon", "commit"]
+        for k, name in enumerate(["pskip", "inter"]):
+            m = rec["mb_class"] == k
+            laps = rec["i16_ac_level"][m].reshape(m.sum(), -1).view(np.uint32)
+            cyc = laps[:, :13].astype(np.float64).mean(axis=0); cnt = laps[:, 16:29].astype(np.float64).mean(axis=0)
+            tot = ((t1[m] - t0[m]).astype(np.float64) * 1.965).mean()
+            print("%s: %.0f cycles per MB; sections (cycles/MB, %% of MB, visits, cycles/visit):" % (name, tot))
+            for i, nm in enumerate(names):
+                print("   %-18s %9.0f %5.1f%% %7.1f %8.0f" % (nm, cyc[i], 100 * cyc[i] / tot, cnt[i], cyc[i] / max(cnt[i], 1e-9)))
         for k, name in enumerate(["pskip", "inter"]):
             m = rec["mb_class"] == k
             cyc = (t1[m] - t0[m]).astype(np.float64) * 1.965   # ns -> cycles at 1965 MHz
