@@ -139,6 +139,7 @@ int hlb200_frame_upload(hlb200_ctx_t* c, const uint8_t* y, const uint8_t* u, con
 int hlb200_frame_set_device(hlb200_ctx_t* c, const uint8_t* d_y, const uint8_t* d_u, const uint8_t* d_v)
 {
     if (!c || !d_y || !d_u || !d_v) return HLB200_ERR_INVALID_PARAMETER;
+    if ((((uintptr_t)d_y) | ((uintptr_t)d_u) | ((uintptr_t)d_v)) & 3) return HLB200_ERR_INVALID_PARAMETER;   // the kernels move samples as aligned 32-bit words
     c->d_src_cur[0] = d_y; c->d_src_cur[1] = d_u; c->d_src_cur[2] = d_v;
     return HLB200_OK;
 }

@@ -137,8 +137,8 @@ struct MbWork {
     int mb, mbx, mby;
     int availA, availB, availC, availD;
     // source samples
-    uint8_t src_y[256];
-    uint8_t src_c[2][64];
+    alignas(4) uint8_t src_y[256];   // moved with 32-bit accesses
+    alignas(4) uint8_t src_c[2][64];
     // evolving state of the current macroblock
     uint8_t tc[16];        // TotalCoeffsLuma
     uint8_t tc_cac[2][4];
@@ -188,8 +188,8 @@ struct MbWork {
     int8_t fin_ref[4];
     uint8_t pred_y[256];
     uint8_t pred_c[2][64];
-    uint8_t rec_y[256];
-    uint8_t rec_c[2][64];
+    alignas(4) uint8_t rec_y[256];
+    alignas(4) uint8_t rec_c[2][64];
     alignas(4) int16_t luma_level[16][16];
     int luma_skip_residual;            // Single_ctr_luma < 6 (rdo.c:2419)
     int cbp_luma4x4;
@@ -202,6 +202,7 @@ struct MbWork {
     int16_t i16_dc[16];
     alignas(4) int16_t i16_ac[16][16];
     uint8_t i4_mode[16], prev_i4[16], rem_i4[16];
+    int32_t nbr_y[41], nbr_c[2][17];   // reconstructed samples around the macroblock (intra_fetch_borders)
     int32_t p33[33];
     int32_t p17[2][17];
     int32_t p13[13];
@@ -866,37 +867,30 @@ HLB_FN void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// load / store of the macroblock's samples: lanes 0..23 (16 luma 4x4 blocks raster + 8 chroma blocks)
+// load / store of the macroblock's samples: 96 lanes, one aligned 32-bit word each (64 luma words = 16 rows x 4, then 2 x 16 chroma words);
+// macroblock columns are 16-sample aligned and the plane pitch is a multiple of 16 (8 for chroma), the plane bases 4-byte aligned
 // ------------------------------------------------------------------------------------------------------------------
 HLB_FN void phase_load(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    if (lane < 16) {
-        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
-        const uint8_t* p = f.src[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
-        for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) w.src_y[(by + r) * 16 + bx + q] = HLB_LDG(p + r * f.W + q);
-    } else if (lane < 24) {
-        const int c = (lane - 16) >> 2, b = (lane - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4, Wc = f.W >> 1;
-        const uint8_t* p = f.src[1 + c] + (w.mby * 8 + y0) * Wc + w.mbx * 8 + x0;
-        for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) w.src_c[c][(y0 + r) * 8 + x0 + q] = HLB_LDG(p + r * Wc + q);
+    if (lane < 64) {
+        const int r = lane >> 2, q = lane & 3;
+        ((uint32_t*)w.src_y)[lane] = HLB_LDG((const uint32_t*)(f.src[0] + (w.mby * 16 + r) * f.W + w.mbx * 16) + q);
+    } else if (lane < 96) {
+        const int i = lane - 64, c = i >> 4, r = (i >> 1) & 7, q = i & 1, Wc = f.W >> 1;
+        ((uint32_t*)w.src_c[c])[i & 15] = HLB_LDG((const uint32_t*)(f.src[1 + c] + (w.mby * 8 + r) * Wc + w.mbx * 8) + q);
     }
 }
 // arg0 bit 0: luma, bit 1: chroma
 HLB_FN void phase_store(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    if (lane < 16 && (w.arg0 & 1)) {
-        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
-        uint8_t* p = f.cur[0] + (w.mby * 16 + by) * f.W + w.mbx * 16 + bx;
-        for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) p[r * f.W + q] = w.rec_y[(by + r) * 16 + bx + q];
-    } else if (lane >= 16 && lane < 24 && (w.arg0 & 2)) {
-        const int c = (lane - 16) >> 2, b = (lane - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4, Wc = f.W >> 1;
-        uint8_t* p = f.cur[1 + c] + (w.mby * 8 + y0) * Wc + w.mbx * 8 + x0;
-        for (int r = 0; r < 4; ++r)
-            for (int q = 0; q < 4; ++q) p[r * Wc + q] = w.rec_c[c][(y0 + r) * 8 + x0 + q];
+    if (lane < 64 && (w.arg0 & 1)) {
+        const int r = lane >> 2, q = lane & 3;
+        ((uint32_t*)(f.cur[0] + (w.mby * 16 + r) * f.W + w.mbx * 16))[q] = ((const uint32_t*)w.rec_y)[lane];
+    } else if (lane >= 64 && lane < 96 && (w.arg0 & 2)) {
+        const int i = lane - 64, c = i >> 4, r = (i >> 1) & 7, q = i & 1, Wc = f.W >> 1;
+        ((uint32_t*)(f.cur[1 + c] + (w.mby * 8 + r) * Wc + w.mbx * 8))[q] = ((const uint32_t*)w.rec_c[c])[i & 15];
     }
 }
 
@@ -1184,7 +1178,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         // luma = prediction; chroma already reconstructed by the zero check
         w.luma_skip_residual = 1;
         x.run(CMD_RECON_LUMA, 16);
-        w.arg0 = 3; x.run(CMD_STORE, 24);
+        w.arg0 = 3; x.run(CMD_STORE, 96);
         w.cbp_luma4x4 = 0;
         kind = MBK_PSKIP; mb_type = 5;
     } else {
@@ -1196,7 +1190,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
 #pragma unroll 1
             for (int b = 0; b < 16; ++b) w.cbp_luma4x4 |= w.r_nz[0][b] << b;
         chroma_code(x, w);
-        w.arg0 = 3; x.run(CMD_STORE, 24);
+        w.arg0 = 3; x.run(CMD_STORE, 96);
         cbp_luma = guess_cbp_luma(w.cbp_luma4x4, false);
         cbp_chroma = guess_cbp_chroma(w);
         cbp = (cbp_chroma << 4) | cbp_luma;
@@ -1221,7 +1215,7 @@ HLB_HD void mb_encode(X& x, MbWork& w, const FrameCtx& f, int mb)
 {
     mb_begin(w, f, mb, x.lane(), x.nlanes());
     x.sync();
-    x.run(CMD_LOAD, 24);
+    x.run(CMD_LOAD, 96);
     HLB_LAP(w, 0);
     if (f.is_p) mb_encode_p(x, w, f);
     else {

@@ -12,9 +12,11 @@ namespace hlb {
 
 // reconstructed luma sample at (x,y) relative to the macroblock (may lie in a neighbouring macroblock), HLB_NA when unavailable
 // (6.4.11.1; constrained_intra_pred_flag = 0, so every already-coded neighbour counts)
-HLB_HD int intra_luma_at(const MbWork& w, const FrameCtx& f, int x, int y)
+// Reconstructed samples around the macroblock (left column, corner, top row up to x = 23) are fetched ONCE per macroblock into
+// w.nbr_y / w.nbr_c by intra_fetch_borders (one coalesced pass over the lanes); the derivations below then read shared memory only.
+// nbr_y: [0] (-1,-1), [1..16] (-1, 0..15), [17..40] (0..23, -1).  nbr_c[c]: [0] (-1,-1), [1..8] (-1, 0..7), [9..16] (0..7, -1).
+HLB_HD int intra_luma_fetch(const MbWork& w, const FrameCtx& f, int x, int y)
 {
-    if (x >= 0 && x <= 15 && y >= 0 && y <= 15) return w.rec_y[y * 16 + x];
     bool ok;
     if (y < 0 && x >= 0 && x <= 15) ok = w.availB;
     else if (y < 0 && x > 15) ok = w.availC;
@@ -24,7 +26,7 @@ HLB_HD int intra_luma_at(const MbWork& w, const FrameCtx& f, int x, int y)
     if (!ok) return HLB_NA;
     return f.cur[0][(w.mby * 16 + y) * f.W + w.mbx * 16 + x];
 }
-HLB_HD int intra_chroma_at(const MbWork& w, const FrameCtx& f, int c, int x, int y)
+HLB_HD int intra_chroma_fetch(const MbWork& w, const FrameCtx& f, int c, int x, int y)
 {
     bool ok;
     if (y < 0 && x >= 0) ok = w.availB;
@@ -32,6 +34,33 @@ HLB_HD int intra_chroma_at(const MbWork& w, const FrameCtx& f, int c, int x, int
     else ok = w.availA;
     if (!ok) return HLB_NA;
     return f.cur[1 + c][(w.mby * 8 + y) * (f.W >> 1) + w.mbx * 8 + x];
+}
+HLB_FN void intra_fetch_borders(MbWork& w, const FrameCtx& f, int lane, int nl)
+{
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+#pragma unroll 1
+    for (int i = lane; i < 41 + 34; i += nl) {
+        if (i < 41) w.nbr_y[i] = (i == 0 ? intra_luma_fetch(w, f, -1, -1) : (i < 17 ? intra_luma_fetch(w, f, -1, i - 1) : intra_luma_fetch(w, f, i - 17, -1)));
+        else {
+            const int k = i - 41, c = k / 17, j = k - c * 17;
+            w.nbr_c[c][j] = (j == 0 ? intra_chroma_fetch(w, f, c, -1, -1) : (j < 9 ? intra_chroma_fetch(w, f, c, -1, j - 1) : intra_chroma_fetch(w, f, c, j - 9, -1)));
+        }
+    }
+    HLB_LANE_SYNC();
+}
+HLB_HD int intra_luma_at(const MbWork& w, const FrameCtx& f, int x, int y)
+{
+    (void)f;
+    if (x >= 0 && x <= 15 && y >= 0 && y <= 15) return w.rec_y[y * 16 + x];
+    if (y == -1 && x >= -1 && x <= 23) return x < 0 ? w.nbr_y[0] : w.nbr_y[17 + x];
+    if (x == -1 && y >= 0 && y <= 15) return w.nbr_y[1 + y];
+    return HLB_NA;
+}
+HLB_HD int intra_chroma_at(const MbWork& w, const FrameCtx& f, int c, int x, int y)
+{
+    (void)f;
+    if (y < 0) return x < 0 ? w.nbr_c[c][0] : w.nbr_c[c][9 + x];
+    return w.nbr_c[c][1 + y];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -228,6 +257,7 @@ template <class X>
 HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cost)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+    intra_fetch_borders(w, f, x.lane(), x.nlanes());
     // ---- Intra16x16 (no reconstruction into the picture yet) ----
     w.p33[0] = intra_luma_at(w, f, -1, -1);
 #pragma unroll 1
@@ -366,7 +396,7 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     x.run(CMD_PRED_CHROMA_INTRA, 8);
     x.run(CMD_CHROMA, 8);
     if (kind == MBK_I16) x.run(CMD_I16_RECON, 16);
-    w.arg0 = 3; x.run(CMD_STORE, 24);
+    w.arg0 = 3; x.run(CMD_STORE, 96);
     w.arg0 = mad_keep;
     return kind;
 }

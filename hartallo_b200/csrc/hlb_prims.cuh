@@ -93,10 +93,12 @@ HLB_HD int blk_idx_from_xy(int x, int y) { return ((y >> 3) << 3) | ((x >> 3) <<
 // se(v)/ue(v) Exp-Golomb lengths (include/hartallo/h264/hl_codec_264_bits.h:739-803)
 HLB_HD int ue_len(uint32_t k)
 {
-    int n = 0;
-    uint32_t v = k + 1;
-    while (v > 1) { v >>= 1; ++n; }
-    return 2 * n + 1;
+    const uint32_t v = k + 1;   // 2 * floor(log2(k + 1)) + 1
+#if defined(__CUDA_ARCH__)
+    return 2 * (31 - __clz((int)v)) + 1;
+#else
+    return 2 * (31 - (v ? __builtin_clz(v) : 32)) + 1;
+#endif
 }
 HLB_HD int se_len(int v) { return ue_len(v <= 0 ? (uint32_t)(-v) << 1 : ((uint32_t)v << 1) - 1); }
 

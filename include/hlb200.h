@@ -152,7 +152,7 @@ HLB200_API int hlb200_stream_set_cuda_stream(hlb200_ctx_t* ctx, void* cuda_strea
 HLB200_API int hlb200_stream_sync(hlb200_ctx_t* ctx);
 /* source frame (hl_frame_video_t::data_ptr[0..2], include/hartallo/hl_frame.h:28-41) -> device */
 HLB200_API int hlb200_frame_upload(hlb200_ctx_t* ctx, const uint8_t* y, const uint8_t* u, const uint8_t* v, int stride_y, int stride_c);
-/* source frame already resident on the device (tight planes, pitch = width); caller-owned, must stay valid until the slice has run */
+/* source frame already resident on the device (tight planes, pitch = width, plane bases 4-byte aligned); caller-owned, must stay valid until the slice has run */
 HLB200_API int hlb200_frame_set_device(hlb200_ctx_t* ctx, const uint8_t* d_y, const uint8_t* d_u, const uint8_t* d_v);
 /* frame-store planes (DPB layout source/h264/hl_codec_264_dpb.c:88-166: tight Y|U|V, stride = width) */
 HLB200_API int hlb200_slot_upload(hlb200_ctx_t* ctx, int slot, const uint8_t* y, const uint8_t* u, const uint8_t* v);
