@@ -273,7 +273,8 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     int_peak = measure_int_peak(torch, hl, lib, dev, stream, sp)
     kms = step_ms[-1]
     ach = ops / (kms * 1e-3) / 1e9
-    roof = {"kernel": "k_slice_encode", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak, "traffic": None, "ms": kms,
+    variant = int(lib.hlb200_slice_last_variant())
+    roof = {"kernel": "k_slice_encode_warp" if variant else "k_slice_encode", "variant": "one warp per macroblock" if variant else "one CTA per macroblock", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak, "traffic": None, "ms": kms,
             "peak_kind": "measured live (hlb200_dev_int_alu_probe: dependency-free IADD3/LOP3)", "algorithmic_ops_per_launch": ops,
             "per_mb": {"me_candidates": cands / (S * NMB), "me_trials": trials / (S * NMB), "intra_trials": intra / (S * NMB), "int_ops": ops / (S * NMB)},
             "note": "ops = (ME + intra 4x4 trial encodes) x 560 + interpolation ops by fractional class (SURVEY.md Appendix D), counted on the reference trajectory"}
@@ -344,7 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="slice", choices=["batch", "slice"])
-    ap.add_argument("--streams", type=int, default=128, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
+    ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences; stream s shows sequence s %% distinct (own buffers)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -384,7 +384,7 @@ static int slice_variant(int n_pictures, int mean_wavefront)
 {
     const int f = slice_force();
     if (f >= 0) return f;
-    return (long long)n_pictures * mean_wavefront >= 2LL * slice_grid(0) ? 1 : 0;
+    return (long long)n_pictures * mean_wavefront >= 8LL * slice_grid(0) ? 1 : 0;   // measured crossover at 1080p: ~200 pictures (r01d A/B: 128 -> CTA, 256+ -> warp)
 }
 
 }  // namespace hlb
@@ -471,6 +471,7 @@ int hlb200_slice_encode(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params, 
 }
 
 int hlb200_slice_grid_size(void) { return slice_grid(slice_force() >= 0 ? slice_force() : g_slice_last); }
+int hlb200_slice_last_variant(void) { return g_slice_last; }
 int hlb200_slice_set_variant(int variant)
 {
     const int prev = slice_force();

@@ -53,7 +53,7 @@ def load():
         "hlb200_stream_sync": [vp], "hlb200_frame_upload": [vp, vp, vp, vp, ip, ip], "hlb200_frame_set_device": [vp, vp, vp, vp], "hlb200_slot_upload": [vp, ip, vp, vp, vp],
         "hlb200_slot_download": [vp, ip, vp, vp, vp], "hlb200_state_reset": [vp],
         "hlb200_slice_encode": [vp, C.POINTER(SliceParams), vp], "hlb200_slice_encode_async": [vp, C.POINTER(SliceParams)], "hlb200_records_download": [vp, vp],
-        "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_set_variant": [ip], "hlb200_slice_status": [vp, vp],
+        "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_set_variant": [ip], "hlb200_slice_last_variant": [], "hlb200_slice_status": [vp, vp],
         "hlb200_interp_luma": [vp, ip, vp, vp], "hlb200_interp_chroma": [vp, ip, vp, vp, vp],
         "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
         "hlb200_dev_interp_luma": [vp, ip, ip, vp, vp, vp], "hlb200_dev_interp_chroma": [vp, vp, ip, ip, vp, vp, vp, vp],
@@ -171,11 +171,18 @@ class Stream:
 class Encoder:
     """Host-side mirror of the reference's per-stream encode flow for the device path (source/h264/hl_codec_264.c:404-1006):
     frame 0 (and every gop_size-th) is an IDR picture, the rest are P pictures predicted from the previous reconstructions;
-    fixed QP (rate control stays on the host).  Frame stores rotate exactly like a sliding-window DPB with `refs` references."""
+    fixed QP (rate control stays on the host).  Frame stores rotate like a sliding-window DPB with `refs` (= max_ref_frame) pictures.
 
-    def __init__(self, width, height, qp=31, me_range=16, refs=1, gop_size=400, device=0):
+    The reference's encoder writes num_ref_idx_l0_active_minus1 = 0 into every slice header it creates (hl_codec_264_slice.c:289-291)
+    and the search loop runs over num_ref_idx_l0_active_minus1 + 1 list entries (hl_codec_264_rdo.c:845,866), so whatever
+    max_ref_frame is, a P picture is searched in RefPicList0[0] = the previous reconstruction only (traced: hl_ref_driver --refs 4
+    visits refIdx 0 alone and reconstructs exactly like --refs 1).  `active_refs` is that count; raise it only to exercise the
+    kernel's multi-reference loop, for which the reference offers no behaviour to compare with."""
+
+    def __init__(self, width, height, qp=31, me_range=16, refs=1, gop_size=400, device=0, active_refs=1):
         self.st = Stream(width, height, refs, device)
         self.qp, self.me_range, self.refs, self.gop = qp, me_range, refs, gop_size
+        self.active_refs = active_refs
         self.order = []      # slots holding reference pictures, most recent first
         self.n = 0
 
@@ -186,9 +193,9 @@ class Encoder:
             self.order = []
         p.slice_type = 0 if idr else 1
         p.qp, p.me_range, p.chroma_qp_index_offset = self.qp, self.me_range, 0
-        p.num_refs = min(len(self.order), self.refs) if not idr else 0
+        p.num_refs = min(len(self.order), self.refs, self.active_refs) if not idr else 0
         p.cur_slot = next(s for s in range(self.refs + 1) if s not in self.order)
-        for i, s in enumerate(self.order[:self.refs]):
+        for i, s in enumerate(self.order[:p.num_refs]):
             p.ref_slot[i] = s
         return p
 

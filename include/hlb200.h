@@ -174,6 +174,7 @@ HLB200_API int hlb200_slice_grid_size(void); /* CTAs the slice kernel variant la
  * large batches), -1 = chosen per launch from the batch size (default).  Results are identical.  Returns the previous setting.
  * The environment variable HLB200_SLICE_KERNEL=cta|warp sets the initial value. */
 HLB200_API int hlb200_slice_set_variant(int variant);
+HLB200_API int hlb200_slice_last_variant(void);   /* variant the most recent slice launch used (0 / 1) */
 
 /* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
 HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);

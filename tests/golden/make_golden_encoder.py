@@ -12,11 +12,12 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import reftrace as rt  # noqa: E402
 
-CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range
+CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range[, max_ref_frame]
     ("g2_qcif", "g2", 5, 176, 144, 5, 30, 16),
     ("g1_qcif", "g1", 1, 176, 144, 5, 31, 16),
     ("g2_small_q12", "g2", 7, 64, 48, 6, 12, 64),
     ("g2_cif_q38", "g2", 2, 352, 288, 3, 38, 8),
+    ("g2_qcif_ref4", "g2", 9, 176, 144, 6, 29, 24, 4),   # BASELINE.json configs[2]: max_ref_frame = 4 (at the reference's real feature set)
 ]
 
 
@@ -24,9 +25,9 @@ def kind_of(e_type):
     return {306: 0, 301: 1, 302: 1, 303: 1, 304: 1, 305: 1, 101: 3}.get(e_type, 2)
 
 
-def build(name, gen, seed, w, h, frames, qp, me_range):
+def build(name, gen, seed, w, h, frames, qp, me_range, refs=1):
     pre = "/tmp/golden_" + name
-    s = rt.run_driver(pre, w, h, frames, gen=gen, seed=seed, qp=qp, me_range=me_range)
+    s = rt.run_driver(pre, w, h, frames, gen=gen, seed=seed, qp=qp, me_range=me_range, refs=refs)
     t = rt.parse(pre + ".trace")
     nmb = (w // 16) * (h // 16)
     rec = {}
@@ -36,7 +37,7 @@ def build(name, gen, seed, w, h, frames, qp, me_range):
     st = {(d["frame"], d["addr"]): d for d in map(rt.state_record, t[5])}
     fb = w * h * 3 // 2
     recon = np.fromfile(pre + ".recon", np.uint8).reshape(frames, fb)
-    out = dict(config=np.array([w, h, frames, qp, me_range, seed], np.int32), gen=np.array(gen), bitstream_md5=np.array(s["md5"]),
+    out = dict(config=np.array([w, h, frames, qp, me_range, seed], np.int32), refs=np.array(refs, np.int32), gen=np.array(gen), bitstream_md5=np.array(s["md5"]),
                recon_md5=np.array([hashlib.md5(recon[n].tobytes()).hexdigest() for n in range(frames)]))
     kind = np.zeros((frames, nmb), np.uint8)
     mb_type = np.zeros((frames, nmb), np.uint8)
@@ -76,5 +77,7 @@ def build(name, gen, seed, w, h, frames, qp, me_range):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for c in CONFIGS:
-        build(*c)
+        if not only or c[0] in only:
+            build(*c)

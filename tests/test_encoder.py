@@ -19,7 +19,12 @@ import reftrace as rt
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38"]
+CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38", "g2_qcif_ref4"]
+
+
+def refs_of(g):
+    """max_ref_frame of a golden configuration (1 unless stored)"""
+    return int(g["refs"]) if "refs" in g.files else 1
 
 
 def frames_of(gen, seed, w, h, n):
@@ -63,7 +68,7 @@ def check_frame(g, n, rec, recon, what):
         assert level_md5(k, r) == str(g["level_md5"][n, a]), (what, n, a, "levels")
 
 
-def run_emu(w, h, frames, qp, me_range, yuv_frames, tag):
+def run_emu(w, h, frames, qp, me_range, yuv_frames, tag, refs=1):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools", "emu"), "emu"], stdout=subprocess.DEVNULL)
     from hartallo_b200 import lib as hl
     pre = "/tmp/test_emu_" + tag
@@ -71,7 +76,7 @@ def run_emu(w, h, frames, qp, me_range, yuv_frames, tag):
         for fr in yuv_frames:
             f.write(fr.tobytes())
     subprocess.check_call([os.path.join(ROOT, "tools", "emu", "emu"), "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp),
-                           "--me-range", str(me_range), "--in", pre + ".yuv", "--out", pre], stdout=subprocess.DEVNULL)
+                           "--me-range", str(me_range), "--refs", str(refs), "--in", pre + ".yuv", "--out", pre], stdout=subprocess.DEVNULL)
     nmb = (w // 16) * (h // 16)
     rec = np.fromfile(pre + ".rec", hl.MB_RECORD).reshape(frames, nmb)
     recon = np.fromfile(pre + ".recon", np.uint8).reshape(frames, -1)
@@ -83,7 +88,7 @@ def test_control_flow_vs_reference_cpu(name):
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
     fr = frames_of(str(g["gen"]), seed, w, h, frames)
-    rec, recon = run_emu(w, h, frames, qp, me_range, fr, name)
+    rec, recon = run_emu(w, h, frames, qp, me_range, fr, name, refs_of(g))
     for n in range(frames):
         check_frame(g, n, rec[n], recon[n], "emu/" + name)
 
@@ -104,7 +109,7 @@ def test_slice_encode_vs_reference(name, variant):
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
     fr = frames_of(str(g["gen"]), seed, w, h, frames)
-    enc = hl.Encoder(w, h, qp=qp, me_range=me_range)
+    enc = hl.Encoder(w, h, qp=qp, me_range=me_range, refs=refs_of(g))
     for n in range(frames):
         rec, recon = enc.encode(fr[n], want_recon=True)
         check_frame(g, n, rec, recon, "gpu/" + name)
@@ -178,7 +183,7 @@ def test_bitstream_md5_drop_in(name):
     import json
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
-    out = subprocess.run([B200_ENCODER, "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", "1",
+    out = subprocess.run([B200_ENCODER, "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", str(refs_of(g)),
                           "--gen", str(g["gen"]), "--seed", str(seed)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stderr[-500:]
     got = json.loads(out.stdout.strip().splitlines()[-1])

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--qp", type=int, default=31)
     ap.add_argument("--me-range", type=int, default=16)
     ap.add_argument("--max-report", type=int, default=8)
+    ap.add_argument("--refs", type=int, default=1)
     a = ap.parse_args()
     w, h = a.size
     nmb = (w // 16) * (h // 16)
@@ -45,9 +46,9 @@ def main():
     with open(pre + ".yuv", "wb") as f:
         for _ in range(a.frames):
             f.write(g.next().tobytes())
-    s = rt.run_driver(pre + "_ref", w, h, a.frames, gen=a.gen, seed=a.seed, qp=a.qp, me_range=a.me_range)
+    s = rt.run_driver(pre + "_ref", w, h, a.frames, gen=a.gen, seed=a.seed, qp=a.qp, me_range=a.me_range, refs=a.refs)
     subprocess.check_call([os.path.join(ROOT, "tools", "emu", "emu"), "--size", str(w), str(h), "--frames", str(a.frames), "--qp", str(a.qp),
-                           "--me-range", str(a.me_range), "--in", pre + ".yuv", "--out", pre + "_emu"], stdout=subprocess.DEVNULL)
+                           "--me-range", str(a.me_range), "--refs", str(a.refs), "--in", pre + ".yuv", "--out", pre + "_emu"], stdout=subprocess.DEVNULL)
     t = rt.parse(pre + "_ref.trace")
     ref_rec = {}
     for r in t[1]:

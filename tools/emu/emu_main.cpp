@@ -39,7 +39,7 @@ struct CpuExec {
 
 int main(int argc, char** argv)
 {
-    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1;
+    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1, active_refs = 1;
     const char *in = nullptr, *out = "emu";
     int dbg_frame = -1, dbg_mb = -1;
     if (getenv("EMU_DEBUG_MB")) sscanf(getenv("EMU_DEBUG_MB"), "%d:%d", &dbg_frame, &dbg_mb);
@@ -49,6 +49,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--qp")) qp = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--me-range")) me_range = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--refs")) refs = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--active-refs")) active_refs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--in")) in = argv[++i];
         else if (!strcmp(argv[i], "--out")) out = argv[++i];
     }
@@ -80,9 +81,12 @@ int main(int argc, char** argv)
         f.lambda = 0.852 * (double)(1 << ((qp - 12) / 3));
         int cur = 0;
         for (int s = 0; s <= refs; ++s) { bool used = false; for (int o : order) used |= (o == s); if (!used) { cur = s; break; } }
-        f.num_refs = (int)order.size() < refs ? (int)order.size() : refs;
+        // the reference searches num_ref_idx_l0_active_minus1 + 1 = 1 list entry whatever max_ref_frame is (slice.c:289-291, rdo.c:845);
+        // --active-refs raises that only to exercise the multi-reference loop
+        f.num_refs = (int)order.size() < active_refs ? (int)order.size() : active_refs;
+        if (f.num_refs > refs) f.num_refs = refs;
         if (f.num_refs < 1) f.num_refs = 1;
-        for (int u = 0; u < (int)order.size() && u < refs; ++u) { f.ref[u][0] = slots[order[u]].data(); f.ref[u][1] = f.ref[u][0] + ys; f.ref[u][2] = f.ref[u][1] + cs; }
+        for (int u = 0; u < f.num_refs && u < (int)order.size(); ++u) { f.ref[u][0] = slots[order[u]].data(); f.ref[u][1] = f.ref[u][0] + ys; f.ref[u][2] = f.ref[u][1] + cs; }
         f.src[0] = src.data(); f.src[1] = f.src[0] + ys; f.src[2] = f.src[1] + cs;
         f.cur[0] = slots[cur].data(); f.cur[1] = f.cur[0] + ys; f.cur[2] = f.cur[1] + cs;
         f.st = st.data(); f.rec = rec.data();
