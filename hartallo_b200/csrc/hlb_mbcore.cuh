@@ -414,24 +414,25 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
     const uint8_t* g = w.tile + (Y + (by - w.part_oy) - w.tile_y0) * HLB_TILE + (X + (bx - w.part_ox) - w.tile_x0);
     interp_luma_4x4(g, HLB_TILE, w.cmvx[c] & 3, w.cmvy[c] & 3, pv);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t sw = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2];   // bx is a multiple of 4
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sv[r * 4 + q] = w.src_y[(by + r) * 16 + bx + q];
+        for (int q = 0; q < 4; ++q) sv[r * 4 + q] = (uint8_t)(sw >> (8 * q));
+    }
     int m[16], lv[16];
-    bool nz = false;
+    uint32_t any = 0, mask = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; nz |= (m[i] != 0); }
-    if (nz) {
+    for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; any |= (uint32_t)m[i]; }
+    if (any) {
         fwd_transform4x4(m);
         quant4x4_ac(m, f.qp, false);
         zigzag4x4(m, lv);
-        nz = false;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) nz |= (lv[i] != 0);
+        mask = level_mask16(lv);
     }
+    const bool nz = mask != 0;
     int dist;
     if (nz) {
-        const CavlcInfo ci = cavlc_block_info(lv, 16, false);
+        const CavlcInfo ci = cavlc_block_info16(lv, mask);
         int cc[16];
         inv_zigzag4x4(lv, cc);
         dequant4x4(cc, f.qp, false);

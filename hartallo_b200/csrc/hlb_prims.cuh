@@ -126,12 +126,48 @@ HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t
             o0 = o1; o1 = o2; o2 = o3;
             o3 = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
         }
-    } else if (xf != 2 && yf != 2 ? true : (xf == 0 || yf == 0)) {
-        // a b c d h n (one half sample, possibly averaged with an integer sample) and e g p r (average of b and h)
-        const bool needB = xf != 0, needH = yf != 0;
+    } else if (yf == 0) {
+        // a b c: one horizontal half sample per pixel (alone, or averaged with the integer sample on its left / right); the nine samples
+        // of a row are loaded once and shared by its four 6-tap filters
+        const int gofs = xf == 3 ? 3 : 2;
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const uint8_t* p = g + r * pitch - 2;
+            int t[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) t[i] = p[i];
+            uint32_t row = 0;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int b = rnd5(tap6(t[x], t[x + 1], t[x + 2], t[x + 3], t[x + 4], t[x + 5]));
+                const int v = xf == 2 ? b : ((t[x + gofs] + b + 1) >> 1);
+                row |= (uint32_t)v << (8 * x);
+            }
+            o0 = o1; o1 = o2; o2 = o3; o3 = row;
+        }
+    } else if (xf == 0) {
+        // d h n: one vertical half sample per pixel; columns are independent, the six samples of a column window slide down
+        const int gofs = yf == 3 ? pitch : 0;
+        int w0[4], w1[4], w2[4], w3[4], w4[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { w0[x] = g[x - 2 * pitch]; w1[x] = g[x - pitch]; w2[x] = g[x]; w3[x] = g[x + pitch]; w4[x] = g[x + 2 * pitch]; }
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const uint8_t* p = g + r * pitch;
+            uint32_t row = 0;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int w5 = p[x + 3 * pitch];
+                const int h = rnd5(tap6(w0[x], w1[x], w2[x], w3[x], w4[x], w5));
+                const int v = yf == 2 ? h : ((p[x + gofs] + h + 1) >> 1);
+                row |= (uint32_t)v << (8 * x);
+                w0[x] = w1[x]; w1[x] = w2[x]; w2[x] = w3[x]; w3[x] = w4[x]; w4[x] = w5;
+            }
+            o0 = o1; o1 = o2; o2 = o3; o3 = row;
+        }
+    } else if ((xf & 1) && (yf & 1)) {
+        // e g p r: average of the horizontal half sample of row y (+1) and the vertical half sample of column x (+1)
         const int rowB = yf == 3 ? pitch : 0, colH = xf == 3 ? 1 : 0;
-        const int gofs = needB ? (xf == 3 ? 1 : 0) : (yf == 3 ? pitch : 0);   // integer sample averaged with a lone half sample
-        const bool lone_half = needB != needH && (needB ? xf == 2 : yf == 2);
 #pragma unroll 1
         for (int r = 0; r < 4; ++r) {
             const uint8_t* p = g + r * pitch;
@@ -139,13 +175,7 @@ HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const int bb = rnd5(hl_h(p + rowB + x)), hh = rnd5(hl_v(p + x + colH, pitch));
-                int v;
-                if (needB && needH) v = (bb + hh + 1) >> 1;
-                else {
-                    const int hs = needB ? bb : hh;
-                    v = lone_half ? hs : ((p[x + gofs] + hs + 1) >> 1);
-                }
-                row |= (uint32_t)v << (8 * x);
+                row |= (uint32_t)((bb + hh + 1) >> 1) << (8 * x);
             }
             o0 = o1; o1 = o2; o2 = o3; o3 = row;
         }
@@ -518,12 +548,16 @@ HLB_HD int hlb_popc(uint32_t v)
     return __builtin_popcount(v);
 #endif
 }
-HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
+// significance mask of 16 levels in scan order (bit i = lv[i] != 0)
+HLB_HD uint32_t level_mask16(const int* lv)
 {
-    if (n != 16 || chroma_dc) return cavlc_block_info_ref(lv, n, chroma_dc);
     uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) mask |= (uint32_t)(lv[i] != 0) << i;
+    return mask;
+}
+HLB_HD CavlcInfo cavlc_block_info16(const int* lv, uint32_t mask)
+{
     CavlcInfo out;
     out.total_coeff = 0; out.trailing_ones = 0; out.single_ctr = 9; out.bits_rest = 0;
     if (mask == 0) return out;
@@ -564,6 +598,11 @@ HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
     out.total_coeff = (uint8_t)tc; out.trailing_ones = (uint8_t)t1; out.bits_rest = (uint16_t)bits;
     if (tc == 1 && (first_v == 1 || first_v == -1)) out.single_ctr = (uint8_t)(hb < 6 ? (hb == 0 ? 3 : (hb < 3 ? 2 : 1)) : 0);
     return out;
+}
+HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
+{
+    if (n != 16 || chroma_dc) return cavlc_block_info_ref(lv, n, chroma_dc);
+    return cavlc_block_info16(lv, level_mask16(lv));
 }
 
 }  // namespace hlb
