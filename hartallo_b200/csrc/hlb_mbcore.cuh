@@ -346,13 +346,23 @@ HLB_HD void ref_window9(const uint8_t* plane, int W, int H, int X, int Y, uint8_
     }
 }
 
-// luma prediction of the 4x4 block at (bx,by) (MB coordinates) belonging to a partition with origin (ox,oy) and motion (mvx,mvy)
-HLB_HD void pred_luma_4x4(const FrameCtx& f, const uint8_t* ref_y, int mbx, int mby, int ox, int oy, int bx, int by, int mvx, int mvy, uint8_t out[16])
+// luma prediction of the 4x4 block at (bx,by) (MB coordinates) belonging to a partition with origin (ox,oy) and motion (mvx,mvy).
+// `win` = 9x9 staging area of the calling lane (shared memory on the GPU): rows/cols -2..+6 around the block, fetched with the
+// reference's per-sample clamp (interpol.c:108-131) by a row loop that is not unrolled (runs once or twice per macroblock).
+HLB_HD void pred_luma_4x4(const FrameCtx& f, const uint8_t* ref_y, int mbx, int mby, int ox, int oy, int bx, int by, int mvx, int mvy, uint8_t* win, uint8_t out[16])
 {
     const int X = clip3(-17, f.W + 17, mbx * 16 + ox + (mvx >> 2)) + (bx - ox);   // origin clip of pred_inter.c:395 applies to the partition
     const int Y = clip3(-17, f.H + 17, mby * 16 + oy + (mvy >> 2)) + (by - oy);
-    uint8_t win[81];
-    ref_window9(ref_y, f.W, f.H, X, Y, win);
+    const int W = f.W, Hm1 = f.H - 1, Wm1 = f.W - 1;
+    int xc[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) xc[c] = clip3(0, Wm1, X - 2 + c);
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const uint8_t* row = ref_y + clip3(0, Hm1, Y - 2 + r) * W;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) win[r * 9 + c] = HLB_LDG(row + xc[c]);
+    }
     interp_luma_4x4(win + 20, 9, mvx & 3, mvy & 3, out);
 }
 
@@ -689,7 +699,8 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
         int p, s, ox, oy;
         fin_rect(w, bx, by, p, s, ox, oy);
         uint8_t pv[16];
-        pred_luma_4x4(f, f.ref[w.fin_ref[p]][0], w.mbx, w.mby, ox, oy, bx, by, w.fin_mv[p][s][0], w.fin_mv[p][s][1], pv);
+        uint8_t* win = (uint8_t*)&w.t_ac[0][0][0] + lane * 96;   // intra trial scratch, idle while an inter prediction is formed (16 x 96 <= sizeof t_ac)
+        pred_luma_4x4(f, f.ref[w.fin_ref[p]][0], w.mbx, w.mby, ox, oy, bx, by, w.fin_mv[p][s][0], w.fin_mv[p][s][1], win, pv);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -992,7 +1003,13 @@ HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb, int lane, int nl)
 }
 
 // state the writer leaves behind (residual.c:903-1094) + publication of the macroblock's final state and record
-HLB_HD int nnz16(const int16_t* lv, int n) { int k = 0; for (int i = 0; i < n; ++i) k += (lv[i] != 0); return k; }
+HLB_HD int nnz16(const int16_t* lv, int n)
+{
+    int k = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) k += (lv[i] != 0);
+    return k;
+}
 
 HLB_FN void mb_commit(MbWork& w, const FrameCtx& f, int kind, int cbp_luma, int cbp_chroma, int coded_block_pattern, int mb_type, const int16_t mvd[4][4][2], int mad, int lane, int nl)
 {

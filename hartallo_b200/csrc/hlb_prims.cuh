@@ -17,6 +17,13 @@
 #if defined(__CUDACC__)
 #define HLB_HD __device__ __forceinline__
 #define HLB_FN __device__ __noinline__   /* phase / control functions of the slice kernel: one copy each */
+#ifndef HLB_CAVLC_FN
+#define HLB_CAVLC_FN __device__ __forceinline__   /* hlb_slice.cu overrides: one out-of-line copy */
+#endif
+#ifndef HLB_INTERP_FN
+#define HLB_INTERP_FN __device__ __forceinline__
+#define HLB_INTERP_SRC(g) ((void)0)
+#endif
 #define HLB_TABLE __constant__   /* small read-only tables: constant cache (plain global loads are compiled .cg and would go to L2) */
 #define HLB_LDG(p) __ldg(p)   /* read-only for the whole kernel (reference / source planes): non-coherent path, L1-cacheable */
 #if defined(__CUDA_ARCH__)
@@ -27,6 +34,9 @@
 #else
 #define HLB_HD inline
 #define HLB_FN inline
+#define HLB_CAVLC_FN inline
+#define HLB_INTERP_FN inline
+#define HLB_INTERP_SRC(g) ((void)0)
 #define HLB_TABLE
 #define HLB_LDG(p) (*(p))
 #define HLB_IN_SHARED(ref) ((void)0)
@@ -116,8 +126,10 @@ HLB_HD int rnd5(int v) { return clip255((v + 16) >> 5); }
 // positions involving the centre half sample j), rows produced by small loops that are NOT unrolled.  The slice kernel runs
 // hundreds of CTAs that sit in different places of the code: short loops keep the instruction-cache footprint (and the
 // divergence between candidates with different fractional positions) small.  Same arithmetic as interpol.h:162-923.
-HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t out[16])
+struct Rows4 { uint32_t r[4]; };   // four rows of four samples, one byte each
+HLB_INTERP_FN Rows4 interp_luma_4x4_rows(const uint8_t* g, int pitch, int xf, int yf)
 {
+    HLB_INTERP_SRC(g);
     uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;   // rows, shifted in as they are produced (no dynamic register indexing)
     if ((xf | yf) == 0) {
 #pragma unroll 1
@@ -126,48 +138,12 @@ HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t
             o0 = o1; o1 = o2; o2 = o3;
             o3 = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
         }
-    } else if (yf == 0) {
-        // a b c: one horizontal half sample per pixel (alone, or averaged with the integer sample on its left / right); the nine samples
-        // of a row are loaded once and shared by its four 6-tap filters
-        const int gofs = xf == 3 ? 3 : 2;
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            const uint8_t* p = g + r * pitch - 2;
-            int t[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) t[i] = p[i];
-            uint32_t row = 0;
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int b = rnd5(tap6(t[x], t[x + 1], t[x + 2], t[x + 3], t[x + 4], t[x + 5]));
-                const int v = xf == 2 ? b : ((t[x + gofs] + b + 1) >> 1);
-                row |= (uint32_t)v << (8 * x);
-            }
-            o0 = o1; o1 = o2; o2 = o3; o3 = row;
-        }
-    } else if (xf == 0) {
-        // d h n: one vertical half sample per pixel; columns are independent, the six samples of a column window slide down
-        const int gofs = yf == 3 ? pitch : 0;
-        int w0[4], w1[4], w2[4], w3[4], w4[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) { w0[x] = g[x - 2 * pitch]; w1[x] = g[x - pitch]; w2[x] = g[x]; w3[x] = g[x + pitch]; w4[x] = g[x + 2 * pitch]; }
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            const uint8_t* p = g + r * pitch;
-            uint32_t row = 0;
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int w5 = p[x + 3 * pitch];
-                const int h = rnd5(tap6(w0[x], w1[x], w2[x], w3[x], w4[x], w5));
-                const int v = yf == 2 ? h : ((p[x + gofs] + h + 1) >> 1);
-                row |= (uint32_t)v << (8 * x);
-                w0[x] = w1[x]; w1[x] = w2[x]; w2[x] = w3[x]; w3[x] = w4[x]; w4[x] = w5;
-            }
-            o0 = o1; o1 = o2; o2 = o3; o3 = row;
-        }
-    } else if ((xf & 1) && (yf & 1)) {
-        // e g p r: average of the horizontal half sample of row y (+1) and the vertical half sample of column x (+1)
+    } else if (xf != 2 && yf != 2 ? true : (xf == 0 || yf == 0)) {
+        // a b c d h n (one half sample, possibly averaged with an integer sample) and e g p r (average of b and h)
+        const bool needB = xf != 0, needH = yf != 0;
         const int rowB = yf == 3 ? pitch : 0, colH = xf == 3 ? 1 : 0;
+        const int gofs = needB ? (xf == 3 ? 1 : 0) : (yf == 3 ? pitch : 0);   // integer sample averaged with a lone half sample
+        const bool lone_half = needB != needH && (needB ? xf == 2 : yf == 2);
 #pragma unroll 1
         for (int r = 0; r < 4; ++r) {
             const uint8_t* p = g + r * pitch;
@@ -175,7 +151,13 @@ HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const int bb = rnd5(hl_h(p + rowB + x)), hh = rnd5(hl_v(p + x + colH, pitch));
-                row |= (uint32_t)((bb + hh + 1) >> 1) << (8 * x);
+                int v;
+                if (needB && needH) v = (bb + hh + 1) >> 1;
+                else {
+                    const int hs = needB ? bb : hh;
+                    v = lone_half ? hs : ((p[x + gofs] + hs + 1) >> 1);
+                }
+                row |= (uint32_t)v << (8 * x);
             }
             o0 = o1; o1 = o2; o2 = o3; o3 = row;
         }
@@ -206,9 +188,16 @@ HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t
             }
         }
     }
+    Rows4 o;
+    o.r[0] = o0; o.r[1] = o1; o.r[2] = o2; o.r[3] = o3;
+    return o;
+}
+HLB_HD void interp_luma_4x4(const uint8_t* g, int pitch, int xf, int yf, uint8_t out[16])
+{
+    const Rows4 o = interp_luma_4x4_rows(g, pitch, xf, yf);
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-        out[x] = (uint8_t)(o0 >> (8 * x)); out[4 + x] = (uint8_t)(o1 >> (8 * x)); out[8 + x] = (uint8_t)(o2 >> (8 * x)); out[12 + x] = (uint8_t)(o3 >> (8 * x));
+        out[x] = (uint8_t)(o.r[0] >> (8 * x)); out[4 + x] = (uint8_t)(o.r[1] >> (8 * x)); out[8 + x] = (uint8_t)(o.r[2] >> (8 * x)); out[12 + x] = (uint8_t)(o.r[3] >> (8 * x));
     }
 }
 
@@ -556,15 +545,13 @@ HLB_HD uint32_t level_mask16(const int* lv)
     for (int i = 0; i < 16; ++i) mask |= (uint32_t)(lv[i] != 0) << i;
     return mask;
 }
-HLB_HD CavlcInfo cavlc_block_info16(const int* lv, uint32_t mask)
+// core on the eight packed level pairs (r_k = lv[2k] | lv[2k+1] << 16) and the significance mask: nine register arguments, so the slice
+// kernel can keep ONE out-of-line copy of it for all its callers (HLB_CAVLC_FN; its hot loop is instruction-fetch bound)
+HLB_CAVLC_FN CavlcInfo cavlc_block_info_packed(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7, uint32_t mask)
 {
     CavlcInfo out;
     out.total_coeff = 0; out.trailing_ones = 0; out.single_ctr = 9; out.bits_rest = 0;
     if (mask == 0) return out;
-    const uint32_t r0 = ((uint32_t)lv[0] & 0xffffu) | ((uint32_t)lv[1] << 16), r1 = ((uint32_t)lv[2] & 0xffffu) | ((uint32_t)lv[3] << 16);
-    const uint32_t r2 = ((uint32_t)lv[4] & 0xffffu) | ((uint32_t)lv[5] << 16), r3 = ((uint32_t)lv[6] & 0xffffu) | ((uint32_t)lv[7] << 16);
-    const uint32_t r4 = ((uint32_t)lv[8] & 0xffffu) | ((uint32_t)lv[9] << 16), r5 = ((uint32_t)lv[10] & 0xffffu) | ((uint32_t)lv[11] << 16);
-    const uint32_t r6 = ((uint32_t)lv[12] & 0xffffu) | ((uint32_t)lv[13] << 16), r7 = ((uint32_t)lv[14] & 0xffffu) | ((uint32_t)lv[15] << 16);
     const int tc = hlb_popc(mask), hb = 31 - hlb_clz(mask);
     const int tz = hb + 1 - tc;
     int bits = 0, zl = 0;
@@ -598,6 +585,14 @@ HLB_HD CavlcInfo cavlc_block_info16(const int* lv, uint32_t mask)
     out.total_coeff = (uint8_t)tc; out.trailing_ones = (uint8_t)t1; out.bits_rest = (uint16_t)bits;
     if (tc == 1 && (first_v == 1 || first_v == -1)) out.single_ctr = (uint8_t)(hb < 6 ? (hb == 0 ? 3 : (hb < 3 ? 2 : 1)) : 0);
     return out;
+}
+HLB_HD CavlcInfo cavlc_block_info16(const int* lv, uint32_t mask)
+{
+    const uint32_t r0 = ((uint32_t)lv[0] & 0xffffu) | ((uint32_t)lv[1] << 16), r1 = ((uint32_t)lv[2] & 0xffffu) | ((uint32_t)lv[3] << 16);
+    const uint32_t r2 = ((uint32_t)lv[4] & 0xffffu) | ((uint32_t)lv[5] << 16), r3 = ((uint32_t)lv[6] & 0xffffu) | ((uint32_t)lv[7] << 16);
+    const uint32_t r4 = ((uint32_t)lv[8] & 0xffffu) | ((uint32_t)lv[9] << 16), r5 = ((uint32_t)lv[10] & 0xffffu) | ((uint32_t)lv[11] << 16);
+    const uint32_t r6 = ((uint32_t)lv[12] & 0xffffu) | ((uint32_t)lv[13] << 16), r7 = ((uint32_t)lv[14] & 0xffffu) | ((uint32_t)lv[15] << 16);
+    return cavlc_block_info_packed(r0, r1, r2, r3, r4, r5, r6, r7, mask);
 }
 HLB_HD CavlcInfo cavlc_block_info(const int* lv, int n, bool chroma_dc)
 {
