@@ -280,7 +280,8 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
             "note": "ops = (ME + intra 4x4 trial encodes) x 560 + interpolation ops by fractional class (SURVEY.md Appendix D), counted on the reference trajectory"}
 
     # ---- end to end through the host-buffer C-ABI: upload of every source picture, download of every decision record ----
-    h_rec = [torch.empty(NMB * hl.MB_RECORD.itemsize, dtype=torch.uint8).pin_memory() for _ in range(S)]
+    # pinned landing buffers for the records: hlb200_records_download returns after its copy has completed, so a small ring is enough
+    h_rec = [torch.empty(NMB * hl.MB_RECORD.itemsize, dtype=torch.uint8).pin_memory() for _ in range(min(S, 8))]
 
     def e2e_step(n):
         for s_i, e in enumerate(encs):
@@ -295,7 +296,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
         hl.check(lib.hlb200_slice_encode_batch_async(ctxs, ps, S), "slice_encode_batch_async")
         for i, e in enumerate(encs):
             e.advance(ps[i])
-            hl.check(lib.hlb200_records_download(e.st.ctx, h_rec[i].data_ptr()), "records_download")
+            hl.check(lib.hlb200_records_download(e.st.ctx, h_rec[i % len(h_rec)].data_ptr()), "records_download")
     for i in range(2):
         e2e_step(1 + Wm + K + i)
     barrier()
@@ -345,7 +346,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="slice", choices=["batch", "slice"])
-    ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
+    ap.add_argument("--streams", type=int, default=512, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences; stream s shows sequence s %% distinct (own buffers)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
