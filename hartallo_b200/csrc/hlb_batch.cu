@@ -30,12 +30,14 @@ __device__ __forceinline__ void load_win9(const uint8_t* __restrict__ plane, int
 }
 
 // ---------------- luma interpolation: one thread per 4x4 block, raster block order inside the MB -------------------
+// blockIdx.y = picture of a batch: the planes of consecutive pictures lie `stride` bytes apart, their motion fields nmb entries apart
 __global__ void __launch_bounds__(128) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
-                                                     const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred)
+                                                     const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred, size_t stride)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int mb = t >> 4;
     if (mb >= nmb) return;
+    ref += blockIdx.y * stride; pred += blockIdx.y * stride; motion += (size_t)blockIdx.y * nmb;
     const int k = t & 15, bx = (k & 3) * 4, by = (k >> 2) * 4;
     const int mbx = mb % mbw, mby = mb / mbw;
     const hlb200_mb_motion_t* m = motion + mb;
@@ -56,11 +58,12 @@ __global__ void __launch_bounds__(128) k_interp_luma(const uint8_t* __restrict__
 
 // ---------------- chroma interpolation: one thread per chroma sample pair (Cb, Cr) ---------------------------------
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
-                                                       const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v)
+                                                       const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int mb = t >> 6;
     if (mb >= nmb) return;
+    ref_u += blockIdx.y * stride; ref_v += blockIdx.y * stride; pred_u += blockIdx.y * stride; pred_v += blockIdx.y * stride; motion += (size_t)blockIdx.y * nmb;
     const int px = t & 7, py = (t >> 3) & 7;
     const int mbx = mb % mbw, mby = mb / mbw;
     const int Wc = W >> 1, Hc = H >> 1;
@@ -94,10 +97,15 @@ __device__ __forceinline__ void store4x4(uint8_t* __restrict__ p, int pitch, con
 __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
                                                   const uint8_t* __restrict__ pred_y, const uint8_t* __restrict__ pred_u, const uint8_t* __restrict__ pred_v,
                                                   int W, int H, int mbw, int nmb, int qp, int qpc, hlb200_mb_coeffs_t* __restrict__ coeffs,
-                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v)
+                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nmb) return;  // warp-uniform
+    {
+        const size_t o = blockIdx.y * stride;
+        src_y += o; src_u += o; src_v += o; pred_y += o; pred_u += o; pred_v += o; rec_y += o; rec_u += o; rec_v += o;
+        coeffs += (size_t)blockIdx.y * nmb;
+    }
     const int mb = warp, mbx = mb % mbw, mby = mb / mbw;
     hlb200_mb_coeffs_t* out = coeffs + mb;
     const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
@@ -315,35 +323,56 @@ using namespace hlb;
 
 extern "C" {
 
-int hlb200_dev_interp_luma(const uint8_t* d_ref_y, int width, int height, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_y, void* cuda_stream)
+// A batch = n_pics pictures whose planes lie frame_stride bytes apart (e.g. consecutive tight Y|U|V frames: stride = W*H*3/2) and whose
+// per-macroblock arrays are contiguous (n_pics x nmb).  One launch for the whole batch: a single 1080p picture is only 3-16 MB, far too
+// little to load HBM3e.
+int hlb200_dev_interp_luma_batch(const uint8_t* d_ref_y, int width, int height, int n_pics, size_t frame_stride, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_y,
+                                 void* cuda_stream)
 {
-    if (!d_ref_y || !d_motion || !d_pred_y || (width & 15) || (height & 15)) return HLB200_ERR_INVALID_PARAMETER;
+    if (!d_ref_y || !d_motion || !d_pred_y || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_interp_luma<<<(nmb * 16 + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, width, height, mbw, nmb, d_motion, d_pred_y);
+    k_interp_luma<<<dim3((nmb * 16 + 127) / 128, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, width, height, mbw, nmb, d_motion, d_pred_y, frame_stride);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
+int hlb200_dev_interp_luma(const uint8_t* d_ref_y, int width, int height, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_y, void* cuda_stream)
+{
+    return hlb200_dev_interp_luma_batch(d_ref_y, width, height, 1, 0, d_motion, d_pred_y, cuda_stream);
+}
 
+int hlb200_dev_interp_chroma_batch(const uint8_t* d_ref_u, const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride, const hlb200_mb_motion_t* d_motion,
+                                   uint8_t* d_pred_u, uint8_t* d_pred_v, void* cuda_stream)
+{
+    if (!d_ref_u || !d_ref_v || !d_motion || !d_pred_u || !d_pred_v || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4);
+    k_interp_chroma<<<dim3((nmb * 64 + 255) / 256, n_pics), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v, frame_stride);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
 int hlb200_dev_interp_chroma(const uint8_t* d_ref_u, const uint8_t* d_ref_v, int width, int height, const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_u,
                              uint8_t* d_pred_v, void* cuda_stream)
 {
-    if (!d_ref_u || !d_ref_v || !d_motion || !d_pred_u || !d_pred_v || (width & 15) || (height & 15)) return HLB200_ERR_INVALID_PARAMETER;
+    return hlb200_dev_interp_chroma_batch(d_ref_u, d_ref_v, width, height, 1, 0, d_motion, d_pred_u, d_pred_v, cuda_stream);
+}
+
+int hlb200_dev_tq_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
+                              const uint8_t* d_pred_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
+                              hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream)
+{
+    if (!d_src_y || !d_pred_y || !d_coeffs || !d_recon_y || (width & 15) || (height & 15) || qp < 0 || qp > 51 || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_interp_chroma<<<(nmb * 64 + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v);
+    k_tq_recon<<<dim3((nmb * 32 + 127) / 128, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, mbw, nmb, qp,
+                                                                                            host_chroma_qp(qp, chroma_qp_index_offset), d_coeffs, d_recon_y, d_recon_u, d_recon_v,
+                                                                                            frame_stride);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
-
 int hlb200_dev_tq_recon(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
                         const uint8_t* d_pred_v, int width, int height, int qp, int chroma_qp_index_offset, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y,
                         uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream)
 {
-    if (!d_src_y || !d_pred_y || !d_coeffs || !d_recon_y || (width & 15) || (height & 15) || qp < 0 || qp > 51) return HLB200_ERR_INVALID_PARAMETER;
-    const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_tq_recon<<<(nmb * 32 + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, mbw, nmb, qp,
-                                                                            host_chroma_qp(qp, chroma_qp_index_offset), d_coeffs, d_recon_y, d_recon_u, d_recon_v);
-    HLB_CUDA(cudaGetLastError());
-    return HLB200_OK;
+    return hlb200_dev_tq_recon_batch(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, 1, 0, qp, chroma_qp_index_offset, d_coeffs, d_recon_y, d_recon_u,
+                                     d_recon_v, cuda_stream);
 }
 
 int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream)

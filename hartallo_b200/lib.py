@@ -57,7 +57,9 @@ def load():
         "hlb200_interp_luma": [vp, ip, vp, vp], "hlb200_interp_chroma": [vp, ip, vp, vp, vp],
         "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
         "hlb200_dev_interp_luma": [vp, ip, ip, vp, vp, vp], "hlb200_dev_interp_chroma": [vp, vp, ip, ip, vp, vp, vp, vp],
-        "hlb200_dev_tq_recon": [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp], "hlb200_dev_sad4x4": [vp, vp, ip, ip, ip, vp, vp],
+        "hlb200_dev_tq_recon": [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp],
+        "hlb200_dev_interp_luma_batch": [vp, ip, ip, ip, C.c_size_t, vp, vp, vp], "hlb200_dev_interp_chroma_batch": [vp, vp, ip, ip, ip, C.c_size_t, vp, vp, vp, vp],
+        "hlb200_dev_tq_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp], "hlb200_dev_sad4x4": [vp, vp, ip, ip, ip, vp, vp],
         "hlb200_dev_me_cost": [vp, vp, ip, ip, ip, vp, ip, vp, vp], "hlb200_dev_int_alu_probe": [ip, ip, vp, vp, C.POINTER(C.c_uint64)],
     }
     for name, args in sig.items():

@@ -29,6 +29,7 @@
 #ifndef HLB200_H_
 #define HLB200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -191,6 +192,16 @@ HLB200_API int hlb200_dev_interp_chroma(const uint8_t* d_ref_u, const uint8_t* d
 HLB200_API int hlb200_dev_tq_recon(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
                                    const uint8_t* d_pred_v, int width, int height, int qp, int chroma_qp_index_offset, hlb200_mb_coeffs_t* d_coeffs,
                                    uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
+/* picture batches of the three kernels above: n_pics pictures whose planes lie frame_stride bytes apart (consecutive tight Y|U|V frames:
+ * frame_stride = width * height * 3 / 2; every plane pointer addresses picture 0) and whose motion / coefficient arrays are contiguous
+ * (n_pics x macroblocks).  One launch per batch -- a single 1080p picture is far too small to load HBM3e. */
+HLB200_API int hlb200_dev_interp_luma_batch(const uint8_t* d_ref_y, int width, int height, int n_pics, size_t frame_stride, const hlb200_mb_motion_t* d_motion,
+                                            uint8_t* d_pred_y, void* cuda_stream);
+HLB200_API int hlb200_dev_interp_chroma_batch(const uint8_t* d_ref_u, const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride,
+                                              const hlb200_mb_motion_t* d_motion, uint8_t* d_pred_u, uint8_t* d_pred_v, void* cuda_stream);
+HLB200_API int hlb200_dev_tq_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
+                                         const uint8_t* d_pred_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
+                                         hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
 HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
 HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n,
                                   hlb200_me_cost_t* d_out, void* cuda_stream);
