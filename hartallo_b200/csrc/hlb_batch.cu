@@ -56,25 +56,33 @@ __global__ void __launch_bounds__(128) k_interp_luma(const uint8_t* __restrict__
         *reinterpret_cast<uint32_t*>(o + r * W) = out[r * 4] | (out[r * 4 + 1] << 8) | (out[r * 4 + 2] << 16) | ((uint32_t)out[r * 4 + 3] << 24);
 }
 
-// ---------------- chroma interpolation: one thread per chroma sample pair (Cb, Cr) ---------------------------------
+// ---------------- chroma interpolation: one thread per two horizontally adjacent chroma samples of both planes ---------
+// (a 2x2 chroma block is the smallest area with one motion vector, so the pair shares it: six reference samples per plane instead of eight,
+// 16-bit stores)
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
                                                        const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int mb = t >> 6;
+    const int mb = t >> 5;
     if (mb >= nmb) return;
     ref_u += blockIdx.y * stride; ref_v += blockIdx.y * stride; pred_u += blockIdx.y * stride; pred_v += blockIdx.y * stride; motion += (size_t)blockIdx.y * nmb;
-    const int px = t & 7, py = (t >> 3) & 7;
+    const int px = (t & 3) * 2, py = (t >> 2) & 7;
     const int mbx = mb % mbw, mby = mb / mbw;
     const int Wc = W >> 1, Hc = H >> 1;
     const hlb200_mb_motion_t* m = motion + mb;
     const PartGeom g = part_of(m->part_mode, m->sub_mode, px * 2, py * 2);
     const int mvx = m->mv[g.part][g.sub][0], mvy = m->mv[g.part][g.sub][1];
     const int x0 = mbx * 8 + px + (mvx >> 3), y0 = mby * 8 + py + (mvy >> 3), xf = mvx & 7, yf = mvy & 7;
-    const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
+    const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), xc = clip3(0, Wc - 1, x0 + 2), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
     const int o = (mby * 8 + py) * Wc + mbx * 8 + px;
-    pred_u[o] = (uint8_t)interp_chroma_px(__ldg(ref_u + ya + xa), __ldg(ref_u + ya + xb), __ldg(ref_u + yc + xa), __ldg(ref_u + yc + xb), xf, yf);
-    pred_v[o] = (uint8_t)interp_chroma_px(__ldg(ref_v + ya + xa), __ldg(ref_v + ya + xb), __ldg(ref_v + yc + xa), __ldg(ref_v + yc + xb), xf, yf);
+    {
+        const int a0 = __ldg(ref_u + ya + xa), a1 = __ldg(ref_u + ya + xb), a2 = __ldg(ref_u + ya + xc), c0 = __ldg(ref_u + yc + xa), c1 = __ldg(ref_u + yc + xb), c2 = __ldg(ref_u + yc + xc);
+        *reinterpret_cast<uint16_t*>(pred_u + o) = (uint16_t)(interp_chroma_px(a0, a1, c0, c1, xf, yf) | (interp_chroma_px(a1, a2, c1, c2, xf, yf) << 8));
+    }
+    {
+        const int a0 = __ldg(ref_v + ya + xa), a1 = __ldg(ref_v + ya + xb), a2 = __ldg(ref_v + ya + xc), c0 = __ldg(ref_v + yc + xa), c1 = __ldg(ref_v + yc + xb), c2 = __ldg(ref_v + yc + xc);
+        *reinterpret_cast<uint16_t*>(pred_v + o) = (uint16_t)(interp_chroma_px(a0, a1, c0, c1, xf, yf) | (interp_chroma_px(a1, a2, c1, c2, xf, yf) << 8));
+    }
 }
 
 // ---------------- residual coding + reconstruction: one warp per macroblock ----------------------------------------
@@ -345,7 +353,7 @@ int hlb200_dev_interp_chroma_batch(const uint8_t* d_ref_u, const uint8_t* d_ref_
 {
     if (!d_ref_u || !d_ref_v || !d_motion || !d_pred_u || !d_pred_v || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_interp_chroma<<<dim3((nmb * 64 + 255) / 256, n_pics), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v, frame_stride);
+    k_interp_chroma<<<dim3((nmb * 32 + 255) / 256, n_pics), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v, frame_stride);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
