@@ -68,3 +68,22 @@ def test_synth_matches_driver_generators():
         g = synth.make(gen, 64, 48, seed)
         for i in range(2):
             assert np.array_equal(g.next(), ref[i])
+
+
+def test_argument_errors_are_reported_not_executed():
+    """error behaviour of the boundary (HL_ERROR_INVALID_PARAMETER = 5 in the reference's enum order is what the glue maps): null pointers,
+    sizes that are not a multiple of 16, QP outside 0..51, picture batches of zero or too many pictures are refused before anything is
+    launched -- so this runs without a GPU"""
+    lib = _lib()
+    l = lib.load()
+    inv = l.hlb200_dev_interp_luma(None, 64, 48, None, None, None)
+    assert inv != 0
+    assert l.hlb200_dev_interp_luma_batch(1, 64, 48, 0, 0, 1, 1, None) == inv          # no pictures
+    assert l.hlb200_dev_interp_luma_batch(1, 60, 48, 1, 0, 1, 1, None) == inv          # width not a multiple of 16
+    assert l.hlb200_dev_interp_chroma_batch(1, 1, 64, 48, 70000, 0, 1, 1, 1, None) == inv
+    assert l.hlb200_dev_tq_recon_batch(1, 1, 1, 1, 1, 1, 64, 48, 1, 0, 52, 0, 1, 1, 1, 1, None) == inv   # QP 52
+    assert l.hlb200_slice_encode_batch_async(None, None, 1) == inv
+    assert l.hlb200_frame_set_device(None, 1, 1, 1) == inv
+    prev = l.hlb200_slice_set_variant(1)
+    assert l.hlb200_slice_set_variant(7) == 1      # out-of-range selects "automatic" and reports the previous setting
+    assert l.hlb200_slice_set_variant(prev) == -1
