@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="slice", choices=["batch", "slice"])
-    ap.add_argument("--streams", type=int, default=512, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
+    ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences; stream s shows sequence s %% distinct (own buffers)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

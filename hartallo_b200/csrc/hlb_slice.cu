@@ -36,6 +36,16 @@ struct Sched {
 };
 #define HLB_SCHED_WORDS 16
 enum { WD_QUEUE = 1, WD_PREV = 2, WD_SEARCH = 3 };
+// Longest sleep of an idle CTA between two looks at its queue slot.  Idle pollers are not free: every wake-up refetches its loop and
+// competes with the working warps of the SM for the instruction caches.  Measured (r01d): the warp variant at 256 pictures per launch
+// runs ~1,000 of its 2,368 warps idle; 2 us -> 131 us of back-off raised throughput 2.26 M -> 2.59 M MB/s (512 us: 2.51 M).  The CTA
+// variant serves small batches where pick-up latency sits on the critical path of a picture: 8 us there (32 us cost 1.5 % at 32 pictures).
+#ifndef HLB_SPIN_MAX_NS_CTA
+#define HLB_SPIN_MAX_NS_CTA 8192
+#endif
+#ifndef HLB_SPIN_MAX_NS_WARP
+#define HLB_SPIN_MAX_NS_WARP 131072
+#endif
 #define HLB_SPIN_LIMIT (1 << 22)    // x ~200 ns sleep: about a second of waiting before a spin loop declares the kernel stuck
 // layout of the scheduler buffer: Sched | queue[total] | deps[total] | done[total]
 __device__ __forceinline__ void watchdog_fire(Sched* s, int code, int a, int b)
@@ -126,7 +136,7 @@ __global__ void k_slice_init(SliceJob* jobs, int njobs, int* sched_buf, int tota
 
 // ---- scheduler steps shared by both kernels (executed by ONE thread) ----
 // pops the next ready macroblock: returns the item (or -1 when the batch is drained / aborted) and the job that owns it
-__device__ __forceinline__ int sched_pop(Sched* s, const int* queue, int total, const SliceJob* jobs, int njobs, int* job_out)
+__device__ __forceinline__ int sched_pop(Sched* s, const int* queue, int total, const SliceJob* jobs, int njobs, int* job_out, unsigned max_sleep_ns)
 {
     const int idx = atomicAdd(&s->head, 1);
     int item = -1;
@@ -137,7 +147,7 @@ __device__ __forceinline__ int sched_pop(Sched* s, const int* queue, int total, 
             if ((spins & 15) == 15 && ld_volatile(&s->abort)) break;
             if (++spins > HLB_SPIN_LIMIT / 8) { watchdog_fire(s, WD_QUEUE, idx, ld_volatile(&s->tail)); break; }
             __nanosleep(ns);
-            if (ns < 2048) ns <<= 1;
+            if (ns < max_sleep_ns) ns <<= 1;
         }
         __threadfence();
     }
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_e
     int* done = deps + total;
     const int tid = threadIdx.x;
     for (;;) {
-        if (tid == 0) { int jb = 0; s_item = sched_pop(s, queue, total, jobs, njobs, &jb); s_job = jb; }
+        if (tid == 0) { int jb = 0; s_item = sched_pop(s, queue, total, jobs, njobs, &jb, HLB_SPIN_MAX_NS_CTA); s_job = jb; }
         __syncthreads();
         const int item = s_item;
         if (item < 0) break;
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(32, HLB_WARP_MIN_CTAS) k_slice_encode_warp(con
     const int tid = threadIdx.x;
     for (;;) {
         int item = -1, jb = 0;
-        if (tid == 0) item = sched_pop(s, queue, total, jobs, njobs, &jb);
+        if (tid == 0) item = sched_pop(s, queue, total, jobs, njobs, &jb, HLB_SPIN_MAX_NS_WARP);
         item = __shfl_sync(0xffffffffu, item, 0); jb = __shfl_sync(0xffffffffu, jb, 0);
         if (item < 0) break;
         const SliceJob* job = jobs + jb;
@@ -384,7 +394,7 @@ static int slice_variant(int n_pictures, int mean_wavefront)
 {
     const int f = slice_force();
     if (f >= 0) return f;
-    return (long long)n_pictures * mean_wavefront >= 8LL * slice_grid(0) ? 1 : 0;   // measured crossover at 1080p: ~200 pictures (r01d A/B: 128 -> CTA, 256+ -> warp)
+    return (long long)n_pictures * mean_wavefront >= 4LL * slice_grid(0) ? 1 : 0;   // measured crossover at 1080p: ~100 pictures (r01d A/B: 64 -> CTA 1.41 M vs 1.21 M, 128 -> warp 2.13 M vs 2.05 M)
 }
 
 }  // namespace hlb
