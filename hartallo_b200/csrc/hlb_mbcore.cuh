@@ -172,7 +172,6 @@ struct MbWork {
     // reference tile: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)] (per-sample clamp of interpol.c:108-131)
     int tile_x0, tile_y0, tile_ref, tile_valid;
     uint8_t tile[HLB_TILE * HLB_TILE];
-    alignas(8) unsigned long long memo[16][HLB_MEMO_SLOTS];   // trial memo of the current macroblock (see me_phase_trial)
     // one evaluation step
     int c_begin, c_end;        // candidates evaluated by the current CMD_ME_EVAL
     int part_ox, part_oy, part_w, part_h, ncand;
@@ -208,7 +207,12 @@ struct MbWork {
     int32_t p33[33];
     int32_t p17[2][17];
     int32_t p13[13];
-    // scratch of the intra trials
+    // The trial memo of the inter search and the scratch of the intra trials are never live together (the intra decision of a P macroblock
+    // runs after its inter search, an I macroblock has no search): they share storage.
+    union {
+        alignas(8) unsigned long long memo[16][HLB_MEMO_SLOTS];   // trial memo of the current macroblock (see me_phase_trial)
+        struct {
+            // scratch of the intra trials
     int16_t t_ac[4][16][16];
     int32_t t_dcw[4][16];
     int16_t t_dc[4][16];
@@ -223,6 +227,8 @@ struct MbWork {
     uint8_t q_nz[9], q_tc[9], q_t1[9], q_sc[9], q_ok[9], q_res0[9];
     int16_t q_lv[9][16];
     uint8_t q_pred[9][16];
+        };
+    };
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -743,7 +749,7 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
         int p, s, ox, oy;
         fin_rect(w, bx, by, p, s, ox, oy);
         uint8_t pv[16];
-        uint8_t* win = (uint8_t*)&w.t_ac[0][0][0] + lane * 96;   // intra trial scratch, idle while an inter prediction is formed (16 x 96 <= sizeof t_ac)
+        uint8_t* win = w.tile + lane * 96;   // the reference tile is dead once a prediction is formed (the caller invalidates it): 16 x 96 <= sizeof tile
         pred_luma_4x4(f, f.ref[w.fin_ref[p]][0], w.mbx, w.mby, ox, oy, bx, by, w.fin_mv[p][s][0], w.fin_mv[p][s][1], win, pv);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -1197,7 +1203,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
                 w.fin_ref[0] = 0; w.fin_mv[0][0][0] = best_mv[0][0][0]; w.fin_mv[0][0][1] = best_mv[0][0][1];
                 w.mb_is_intra = 0;
                 HLB_LAP(w, 8);
-                x.run(CMD_PRED_INTER, 144);
+                w.tile_valid = 0; x.run(CMD_PRED_INTER, 144);   // the luma lanes stage their windows in the tile
                 chroma_code(x, w);
                 b_pskip = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1];
                 HLB_LAP(w, 9);
@@ -1246,7 +1252,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         w.cbp_luma4x4 = 0;
         kind = MBK_PSKIP; mb_type = 5;
     } else {
-        x.run(CMD_PRED_INTER, 144);
+        w.tile_valid = 0; x.run(CMD_PRED_INTER, 144);   // the luma lanes stage their windows in the tile
         w.luma_skip_residual = best_sctr < 6;
         x.run(CMD_RECON_LUMA, 16);
         w.cbp_luma4x4 = 0;
