@@ -259,9 +259,10 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     intra_fetch_borders(w, f, x.lane(), x.nlanes());
     // ---- Intra16x16 (no reconstruction into the picture yet) ----
-    w.p33[0] = intra_luma_at(w, f, -1, -1);
+    // the serial copies of this function are strided over the lanes of the master warp (x.lane(), x.nlanes(); one lane on the CPU harness)
 #pragma unroll 1
-    for (int i = 0; i < 16; ++i) { w.p33[1 + i] = intra_luma_at(w, f, -1, i); w.p33[17 + i] = intra_luma_at(w, f, i, -1); }
+    for (int i = x.lane(); i < 33; i += x.nlanes()) w.p33[i] = i == 0 ? intra_luma_at(w, f, -1, -1) : (i < 17 ? intra_luma_at(w, f, -1, i - 1) : intra_luma_at(w, f, i - 17, -1));
+    x.sync();
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) w.t_mode_ok[m] = i16_mode_allowed(m, w.p33) ? 1 : 0;
     {
@@ -300,12 +301,12 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
         HLB_DBG("  I16 mode %d: dist %.0f rate %d cbp %x cost %.4f\n", m, d, w.t_rate[m], w.t_cbp[m], cost);
         if (cost < best16) { best16 = cost; dist16 = (int)d; w.i16_mode = m; w.i16_cbp4x4 = w.t_cbp[m]; }
     }
+    x.sync();   // i16_mode / i16_cbp4x4 are written by every lane with the same value
 #pragma unroll 1
-    for (int b = 0; b < 16; ++b)
+    for (int i = x.lane(); i < 256; i += x.nlanes()) (&w.i16_ac[0][0])[i] = (&w.t_ac[w.i16_mode][0][0])[i];
 #pragma unroll 1
-        for (int i = 0; i < 16; ++i) w.i16_ac[b][i] = w.t_ac[w.i16_mode][b][i];
-#pragma unroll 1
-    for (int i = 0; i < 16; ++i) w.i16_dc[i] = w.i16_cbp4x4 ? w.t_dc[w.i16_mode][i] : 0;
+    for (int i = x.lane(); i < 16; i += x.nlanes()) w.i16_dc[i] = w.i16_cbp4x4 ? w.t_dc[w.i16_mode][i] : 0;
+    x.sync();
 
     // ---- Intra4x4 (reconstructs block after block: later blocks predict from it) ----
     double cost4 = DBL_MAX;
@@ -346,14 +347,15 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
             }
             HLB_DBG("  I4 blk %d: mode %d cost %.4f dist %.0f nC %d\n", blk, best_mode, min_cost, min_dist, nC);
             w.i4_mode[blk] = (uint8_t)best_mode;
+            x.sync();
 #pragma unroll 1
-            for (int i = 0; i < 16; ++i) w.luma_level[blk][i] = w.q_lv[best_mode][i];
+            for (int i = x.lane(); i < 16; i += x.nlanes()) {
+                w.luma_level[blk][i] = w.q_lv[best_mode][i];
+                w.rec_y[(by + (i >> 2)) * 16 + bx + (i & 3)] = w.q_pred[best_mode][i];
+            }
             cost4 += min_cost; dist4 = (int)(dist4 + min_dist);
             if (!best_allzero) cbp4 |= 1 << blk;
-#pragma unroll 1
-            for (int r = 0; r < 4; ++r)
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) w.rec_y[(by + r) * 16 + bx + c] = w.q_pred[best_mode][r * 4 + c];
+            x.sync();   // the next block predicts from these samples
         }
     }
     w.i4_cbp4x4 = cbp4;
