@@ -693,19 +693,34 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
                     w.pat_mv[i][0] = (int16_t)(mx * (1 << shift)); w.pat_mv[i][1] = (int16_t)(my * (1 << shift));
                 }
                 x.sync();
+                // ordered compaction without a serial pass: every kept point counts the kept points before it (independent loads)
                 int n = 0;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) n += (j < count) ? (int)w.pat_ok[j] : 0;
 #pragma unroll 1
-                for (int i = 0; i < count; ++i)
-                    if (w.pat_ok[i]) { w.cidx[n] = (uint8_t)i; w.cmvx[n] = w.pat_mv[i][0]; w.cmvy[n] = w.pat_mv[i][1]; ++n; }
+                for (int i = x.lane(); i < count; i += x.nlanes())
+                    if (w.pat_ok[i]) {
+                        int at = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) at += (j < i) ? (int)w.pat_ok[j] : 0;
+                        w.cidx[at] = (uint8_t)i; w.cmvx[at] = w.pat_mv[i][0]; w.cmvy[at] = w.pat_mv[i][1];
+                    }
                 w.ncand = n;
                 x.sync();
                 if (n > 0) {
                     me_eval(x, w, f, px, py);
-#pragma unroll 1
-                    for (int c = 0; c < n; ++c) {
-                        HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
-                        if (w.c_cost[c] < w.best_cost[p][s]) { best_idx = w.cidx[c]; set_best(w, p, s, w.c_cost[c], c); }
+                    // the first strictly smaller cost in candidate order wins (me_ds.c:345); only the final winner is committed
+                    double bc = w.best_cost[p][s];
+                    int win = -1;
+#pragma unroll
+                    for (int c = 0; c < HLB_MAXC; ++c) {
+                        if (c < n) {
+                            HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
+                            const double cc = w.c_cost[c];
+                            if (cc < bc) { bc = cc; win = c; }
+                        }
                     }
+                    if (win >= 0) { best_idx = w.cidx[win]; set_best(w, p, s, bc, win); }
                 }
                 flags = 0xFFFFFF;
                 if (shift == 2 && best_idx == -1) {
