@@ -434,6 +434,18 @@ HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
 #else
 #define HLB_MEMO_CAS(p, old, val) (*(p) == (old) ? (*(p) = (val), true) : false)
 #endif
+#if !defined(__CUDACC__)
+// CPU harness only (tools/emu --memo-stats): how many trials / search steps of the reference trajectory are repeats
+struct MemoStats { long trials, hits, steps, full_hit_steps, step_trials, step_hits; };
+static MemoStats g_memo_stats = {0, 0, 0, 0, 0, 0};
+#define HLB_MEMO_COUNT(hit) do { g_memo_stats.trials++; g_memo_stats.step_trials++; if (hit) { g_memo_stats.hits++; g_memo_stats.step_hits++; } } while (0)
+#define HLB_MEMO_STEP_BEGIN() do { g_memo_stats.step_trials = g_memo_stats.step_hits = 0; } while (0)
+#define HLB_MEMO_STEP_END() do { g_memo_stats.steps++; if (g_memo_stats.step_trials == g_memo_stats.step_hits) g_memo_stats.full_hit_steps++; } while (0)
+#else
+#define HLB_MEMO_COUNT(hit) do { } while (0)
+#define HLB_MEMO_STEP_BEGIN() do { } while (0)
+#define HLB_MEMO_STEP_END() do { } while (0)
+#endif
 HLB_HD void memo_reset(MbWork& w, int lane, int nl)
 {
     unsigned long long* t = &w.memo[0][0];
@@ -463,6 +475,7 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
         if ((uint32_t)e == key) { hit = true; val = (uint32_t)(e >> 32); break; }
         if ((uint32_t)e == HLB_MEMO_EMPTY_KEY) { ins = j; break; }
     }
+    HLB_MEMO_COUNT(hit);
     if (!hit) {
         uint8_t pv[16], sv[16];
         int X, Y;
@@ -577,7 +590,9 @@ HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, in
     }
     w.c_begin = c0; w.c_end = c1;
     HLB_LAP(w, 2);
+    HLB_MEMO_STEP_BEGIN();
     x.run(CMD_ME_EVAL, (c1 - c0) << w.nblk_log2);
+    HLB_MEMO_STEP_END();
     HLB_LAP(w, 4);
 #pragma unroll 1
     for (int b = x.lane(); b < 16; b += x.nlanes()) me_phase_scan(w, b);

@@ -39,7 +39,7 @@ struct CpuExec {
 
 int main(int argc, char** argv)
 {
-    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1, active_refs = 1;
+    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1, active_refs = 1, memo_stats = 0;
     const char *in = nullptr, *out = "emu";
     int dbg_frame = -1, dbg_mb = -1;
     if (getenv("EMU_DEBUG_MB")) sscanf(getenv("EMU_DEBUG_MB"), "%d:%d", &dbg_frame, &dbg_mb);
@@ -50,6 +50,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--me-range")) me_range = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--refs")) refs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--active-refs")) active_refs = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--memo-stats")) memo_stats = 1;
         else if (!strcmp(argv[i], "--in")) in = argv[++i];
         else if (!strcmp(argv[i], "--out")) out = argv[++i];
     }
@@ -104,6 +105,11 @@ int main(int argc, char** argv)
         if ((int)order.size() > refs) order.pop_back();
     }
     fclose(fi); fclose(fr); fclose(fc); fclose(fs);
+    if (memo_stats) {
+        const hlb::MemoStats& m = hlb::g_memo_stats;
+        printf("trial memo on the reference trajectory: %ld trials, %ld repeats (%.1f%%); %ld search steps, %ld of repeats only (%.1f%%)\n", m.trials, m.hits,
+               100.0 * m.hits / (m.trials ? m.trials : 1), m.steps, m.full_hit_steps, 100.0 * m.full_hit_steps / (m.steps ? m.steps : 1));
+    }
     printf("emu: %d frames, sizeof(MbWork)=%zu sizeof(MbState)=%zu sizeof(rec)=%zu\n", frames, sizeof(MbWork), sizeof(MbState), sizeof(hlb200_mb_record_t));
     return 0;
 }
