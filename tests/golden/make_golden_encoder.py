@@ -17,7 +17,8 @@ CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range[, max_ref_frame]
     ("g1_qcif", "g1", 1, 176, 144, 5, 31, 16),
     ("g2_small_q12", "g2", 7, 64, 48, 6, 12, 64),
     ("g2_cif_q38", "g2", 2, 352, 288, 3, 38, 8),
-    ("g2_qcif_ref4", "g2", 9, 176, 144, 6, 29, 24, 4),   # BASELINE.json configs[2]: max_ref_frame = 4 (at the reference's real feature set)
+    ("g2_qcif_ref4", "g2", 9, 176, 144, 6, 29, 24, 4),
+    ("g1_cif_10", "g1", 12345, 352, 288, 10, 31, 16),      # BASELINE.json configs[0]: CIF, 1 ref, quarter-pel ME +-16, 10 frames   # BASELINE.json configs[2]: max_ref_frame = 4 (at the reference's real feature set)
 ]
 
 

@@ -19,7 +19,7 @@ import reftrace as rt
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38", "g2_qcif_ref4"]
+CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38", "g2_qcif_ref4", "g1_cif_10"]
 
 
 def refs_of(g):
