@@ -229,3 +229,11 @@ def test_compact_primitives_equal_reference_formulation(prog):
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-x", "c++", os.path.join(ROOT, "tools", "emu", prog + ".cpp"), "-o", exe])
     out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout[-300:]
+
+
+@pytest.mark.skipif(not rt.have_driver(), reason="oracle/_ref/hl_ref_driver not built (needs the reference tree)")
+def test_control_flow_fuzz_vs_live_reference():
+    """a few random configurations (size, QP 12..51, search range 1..64, generator, seed, max_ref_frame) of the differential fuzz
+    tools/emu/fuzz.py: the CPU build of the kernel's per-macroblock code against the reference encoder run live"""
+    out = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "emu", "fuzz.py"), "8", "1000"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and ", 0 mismatches" in out.stdout, out.stdout[-600:]
