@@ -196,6 +196,9 @@ def measure_int_peak(torch, hl, lib, dev, stream, sp):
     return best
 
 
+NCU_DRAM_BYTES_PER_MB = 10592   # k_slice_encode_warp, profiles/r01f_summary.md
+
+
 def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, stream, sp):
     from hartallo_b200 import sharding
     S, K, Wm = args.streams, args.steps, args.warmup
@@ -274,7 +277,10 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     kms = step_ms[-1]
     ach = ops / (kms * 1e-3) / 1e9
     variant = int(lib.hlb200_slice_last_variant())
-    roof = {"kernel": "k_slice_encode_warp" if variant else "k_slice_encode", "variant": "one warp per macroblock" if variant else "one CTA per macroblock", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak, "traffic": None, "ms": kms,
+    roof = {"kernel": "k_slice_encode_warp" if variant else "k_slice_encode", "variant": "one warp per macroblock" if variant else "one CTA per macroblock", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak,
+            # DRAM bytes of the kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture
+            # (profiles/r01f_summary.md: 7.13 GB + 3.94 GB for 128 x 8160 macroblocks = 10,592 B per macroblock), scaled to this launch
+            "traffic": int(NCU_DRAM_BYTES_PER_MB * S * NMB), "traffic_unit": "bytes per launch (ncu capture profiles/r01f, scaled by macroblocks)", "ms": kms,
             "peak_kind": "measured live (hlb200_dev_int_alu_probe: dependency-free IADD3/LOP3)", "algorithmic_ops_per_launch": ops,
             "per_mb": {"me_candidates": cands / (S * NMB), "me_trials": trials / (S * NMB), "intra_trials": intra / (S * NMB), "int_ops": ops / (S * NMB)},
             "note": "ops = (ME + intra 4x4 trial encodes) x 560 + interpolation ops by fractional class (SURVEY.md Appendix D), counted on the reference trajectory"}
