@@ -1,0 +1,260 @@
+// hlb_svc.cuh -- SVC enhancement-layer inter macroblock (base_mode_flag = 1), SURVEY 8a row a14:
+// hl_codec_264_rdo_mb_guess_best_inter_pred_svc, source/h264/hl_codec_264_rdo.c:1273-1521.
+//
+// The reference does no search for these macroblocks: partitions and motion vectors come from the inter-layer derivation
+// (utils.c:966-2439, host side), the macroblock is predicted from RefPicList0[0] of its own layer
+// (rdo.c:1340-1424), the luma residual is transformed and quantised with the INTRA rounding offset (rdo.c:1468), chroma goes
+// through the shared _hl_codec_264_rdo_mb_reconstruct_chroma (rdo.c:1500, :2502-2700) with the macroblock counted as inter.
+// Prediction, residual coding and reconstruction are fused here: one lane owns one 4x4 block (16 luma + 2x4 chroma lanes per
+// macroblock) from the reference window to the reconstructed samples, so the prediction never travels through HBM
+// (1,152 B per macroblock = 384 reference + 384 source read, 384 reconstruction written, plus 768 B of levels).
+//
+// Two phases per lane with one exchange area between them (the 2x2 chroma DC stage and the single-coefficient elimination
+// look at all four blocks of a plane).  The phases are `HLB_HD`: under nvcc they are the body of k_svc_inter_recon
+// (hlb_batch.cu), compiled as plain C++ they run lane by lane in tools/emu/svc_emu.cpp -- the CPU tier checks the same source
+// against the reference's per-macroblock trace.
+#pragma once
+#include "../../include/hlb200.h"
+#include "hlb_prims.cuh"
+
+namespace hlb {
+
+// partition that contains luma position (bx, by); same geometry as part_of() in hlb_common.cuh (kept here so this header
+// compiles without the CUDA runtime)
+struct SvcPart { int part, sub, ox, oy; };
+HLB_HD SvcPart svc_part_of(int part_mode, const uint8_t sub_mode[4], int bx, int by)
+{
+    SvcPart g;
+    g.sub = 0;
+    if (part_mode == 0) { g.part = 0; g.ox = 0; g.oy = 0; }
+    else if (part_mode == 1) { g.part = by >> 3; g.ox = 0; g.oy = g.part * 8; }
+    else if (part_mode == 2) { g.part = bx >> 3; g.ox = g.part * 8; g.oy = 0; }
+    else {
+        g.part = ((by >> 3) << 1) | (bx >> 3);
+        const int px = (g.part & 1) * 8, py = (g.part >> 1) * 8, lx = bx & 7, ly = by & 7, sm = sub_mode[g.part];
+        if (sm == 0) { g.ox = px; g.oy = py; }
+        else if (sm == 1) { g.sub = ly >> 2; g.ox = px; g.oy = py + g.sub * 4; }
+        else if (sm == 2) { g.sub = lx >> 2; g.ox = px + g.sub * 4; g.oy = py; }
+        else { g.sub = ((ly >> 2) << 1) | (lx >> 2); g.ox = px + (g.sub & 1) * 4; g.oy = py + (g.sub >> 1) * 4; }
+    }
+    return g;
+}
+
+// what the four block lanes of a chroma plane tell each other (shared memory on the device, one per macroblock)
+struct SvcXchg {
+    int32_t dc_coef[2][4];   // W00 of the block before quantisation (rdo.c:2591)
+    uint8_t nnz[2][4];       // non-zero AC levels of a block whose AC bit is set
+    uint8_t big[2][4];       // any |level| > 1 among them
+    uint8_t coded[2][4];     // CodedBlockPatternChromaAC4x4 bit before the elimination
+    uint8_t luma_coded[16];  // CodedBlockPatternLuma4x4 bits
+};
+// what a chroma lane keeps between its two phases (registers on the device)
+struct SvcChromaLane {
+    uint8_t pv[16];   // prediction
+    int16_t ac[16];   // ChromaACLevel[plane][blk] as the macroblock object holds it after the forward pass (stale when the residual is zero)
+};
+
+// four samples of a row as one word (plane bases are 4-byte aligned, widths multiples of 16)
+HLB_HD uint32_t svc_ld4(const uint8_t* p) { return HLB_LDG(reinterpret_cast<const uint32_t*>(p)); }
+HLB_HD void svc_st4(uint8_t* p, int a, int b, int c, int d) { *reinterpret_cast<uint32_t*>(p) = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
+
+struct SvcPlanes {
+    const uint8_t *src_y, *src_u, *src_v, *ref_y, *ref_u, *ref_v;
+    uint8_t *rec_y, *rec_u, *rec_v;
+    int W, H;
+};
+
+// ---- luma lane (blk = luma4x4BlkIdx): prediction -> residual -> T -> Q (intra offset) -> Q^-1 -> T^-1 -> reconstruction (rdo.c:1428-1496) ----
+HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t& m, int qp, hlb200_mb_coeffs_t& out, SvcXchg& X)
+{
+    const int bx = blk_x(blk), by = blk_y(blk), W = P.W, H = P.H;
+    const SvcPart g = svc_part_of(m.part_mode, m.sub_mode, bx, by);
+    const int mvx = m.mv[g.part][g.sub][0], mvy = m.mv[g.part][g.sub][1];
+    // the origin clip applies to the PARTITION origin (pred_inter.c:395-396); samples are fetched with the per-sample
+    // clamp of the reference's index table (interpol.c:108-131)
+    const int X0 = clip3(-17, W + 17, mbx * 16 + g.ox + (mvx >> 2)) + (bx - g.ox);
+    const int Y0 = clip3(-17, H + 17, mby * 16 + g.oy + (mvy >> 2)) + (by - g.oy);
+    uint8_t win[81];
+    if (X0 >= 2 && Y0 >= 2 && X0 + 7 <= W && Y0 + 7 <= H) {
+        const uint8_t* p = P.ref_y + (Y0 - 2) * W + (X0 - 2);
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) win[r * 9 + c] = HLB_LDG(p + r * W + c);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int y = clip3(0, H - 1, Y0 - 2 + r);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) win[r * 9 + c] = HLB_LDG(P.ref_y + y * W + clip3(0, W - 1, X0 - 2 + c));
+        }
+    }
+    uint8_t pv[16];
+    interp_luma_4x4(win + 2 * 9 + 2, 9, mvx & 3, mvy & 3, pv);
+
+    const int off = (mby * 16 + by) * W + mbx * 16 + bx;
+    int mm[16], lv[16];
+    bool nz = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t sw = svc_ld4(P.src_y + off + r * W);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const int d = (int)((sw >> (8 * c)) & 255u) - (int)pv[r * 4 + c]; mm[r * 4 + c] = d; nz |= (d != 0); }
+    }
+    bool coded = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lv[i] = 0;
+    if (nz) {
+        fwd_transform4x4(mm);
+        quant4x4_ac(mm, qp, /*intra f*/ true);   // __isIntraBlockTrue, rdo.c:1468
+        zigzag4x4(mm, lv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) coded |= (lv[i] != 0);
+    }
+    int rec[16];
+    if (coded) {
+        int c[16];
+        inv_zigzag4x4(lv, c);
+        dequant4x4(c, qp, /*keep_dc*/ false);
+        inv_transform4x4(c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[i] = clip255((int)pv[i] + c[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[i] = pv[i];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) svc_st4(P.rec_y + off + r * W, rec[r * 4], rec[r * 4 + 1], rec[r * 4 + 2], rec[r * 4 + 3]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out.luma_level[blk][i] = (int16_t)lv[i];   // all zero when the block is not coded (rdo.c:1453,1462)
+    X.luma_coded[blk] = coded ? 1 : 0;
+}
+
+// ---- chroma lane, phase A (plane 0 = Cb, 1 = Cr; blk raster 0..3): prediction, forward pass of the block (rdo.c:2561-2638) ----
+HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t& m, int qpc, hlb200_svc_mb_state_t& st,
+                              SvcChromaLane& L, SvcXchg& X)
+{
+    const int Wc = P.W >> 1, Hc = P.H >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
+    const uint8_t* ref = plane ? P.ref_v : P.ref_u;
+    const uint8_t* src = plane ? P.src_v : P.src_u;
+    // 8.4.2.2.2 per sample; a 2x2 chroma area is the smallest one with its own motion vector
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; x += 2) {
+            const SvcPart g = svc_part_of(m.part_mode, m.sub_mode, (bx + x) * 2, (by + y) * 2);
+            const int mvx = m.mv[g.part][g.sub][0], mvy = m.mv[g.part][g.sub][1];
+            const int x0 = mbx * 8 + bx + x + (mvx >> 3), y0 = mby * 8 + by + y + (mvy >> 3), xf = mvx & 7, yf = mvy & 7;
+            const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), xc = clip3(0, Wc - 1, x0 + 2);
+            const int ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
+            const int a0 = HLB_LDG(ref + ya + xa), a1 = HLB_LDG(ref + ya + xb), a2 = HLB_LDG(ref + ya + xc);
+            const int c0 = HLB_LDG(ref + yc + xa), c1 = HLB_LDG(ref + yc + xb), c2 = HLB_LDG(ref + yc + xc);
+            L.pv[y * 4 + x] = (uint8_t)interp_chroma_px(a0, a1, c0, c1, xf, yf);
+            L.pv[y * 4 + x + 1] = (uint8_t)interp_chroma_px(a1, a2, c1, c2, xf, yf);
+        }
+    const int off = (mby * 8 + by) * Wc + mbx * 8 + bx;
+    int mm[16];
+    bool nz = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t sw = svc_ld4(src + off + r * Wc);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const int d = (int)((sw >> (8 * c)) & 255u) - (int)L.pv[r * 4 + c]; mm[r * 4 + c] = d; nz |= (d != 0); }
+    }
+    // ChromaACLevel lives in the macroblock object from picture to picture: a block whose residual is zero keeps what an earlier picture
+    // left there, and transf.c:236-245 reads it again whenever the block's de-quantised DC is not zero.  Element [15] is never written.
+#pragma unroll
+    for (int i = 0; i < 16; ++i) L.ac[i] = st.chroma_ac_level[plane][blk][i];
+    int dc = 0;
+    bool coded = false;
+    int nnz = 0, big = 0;
+    if (nz) {
+        int lv[16];
+        fwd_transform4x4(mm);
+        dc = mm[0];
+        quant4x4_ac(mm, qpc, /*intra f*/ true);   // chroma AC always uses the intra offset (rdo.c:2588)
+        zigzag4x4(mm, lv);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) L.ac[i - 1] = (int16_t)lv[i];   // Scan4x4_AC_C, utils.h:183
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { coded |= (L.ac[i] != 0); nnz += (L.ac[i] != 0); big |= (iabs(L.ac[i]) > 1); }
+    }
+    X.dc_coef[plane][blk] = dc;
+    X.coded[plane][blk] = coded ? 1 : 0;
+    X.nnz[plane][blk] = (uint8_t)(coded ? nnz : 0);
+    X.big[plane][blk] = (uint8_t)(coded ? big : 0);
+}
+
+// ---- chroma lane, phase B: elimination, 2x2 DC, reconstruction of the block (rdo.c:2640-2682, transf.c:161-296) ----
+HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, int blk, int qpc, hlb200_svc_mb_state_t& st, const SvcChromaLane& L,
+                              const SvcXchg& X, hlb200_mb_coeffs_t& out)
+{
+    const int Wc = P.W >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
+    int tot = 0, anybig = 0;
+    unsigned ac_mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { tot += X.nnz[plane][k]; anybig |= X.big[plane][k]; ac_mask |= (unsigned)X.coded[plane][k] << k; }
+    if (tot == 1 && !anybig) ac_mask = 0;   // exactly one +-1 AC coefficient in the plane: Single_ctr < 7 && TotalCoeffs == 1, rdo.c:2641-2649
+    int dcl[4], dcr[4] = {0, 0, 0, 0};
+    unsigned dc_mask = 0;
+    const bool dc_tent = (X.dc_coef[plane][0] | X.dc_coef[plane][1] | X.dc_coef[plane][2] | X.dc_coef[plane][3]) != 0;
+    if (dc_tent) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dcl[k] = X.dc_coef[plane][k];
+        hadamard2x2(dcl);
+        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ false);   // the inferred macroblock type is not an intra type (mb.h:46,57; rdo.c:2660)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dc_mask |= (unsigned)(dcl[k] != 0) << k;
+        if (dc_mask) {   // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dcr[k] = dcl[k];
+            hadamard2x2(dcr);
+            const int ls = 16 * kNormAdjust[qpc % 6][0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dcr[k] = ((dcr[k] * ls) << (qpc / 6)) >> 5;
+        }
+    } else {   // ChromaDCLevel keeps its old content (rdo.c:2653: not entered)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dcl[k] = st.chroma_dc_level[plane][k];
+    }
+    const int mydc = dcr[blk];
+    const bool use_res = mydc != 0 || ((ac_mask >> blk) & 1);   // AC levels are used whenever the DC is non-zero (transf.c:236)
+    const int off = (mby * 8 + by) * Wc + mbx * 8 + bx;
+    uint8_t* rec = plane ? P.rec_v : P.rec_u;
+    int c[16];
+    if (use_res) {
+        int l2[16];
+        l2[0] = mydc;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) l2[i] = L.ac[i - 1];
+        inv_zigzag4x4(l2, c);
+        dequant4x4(c, qpc, /*keep_dc*/ true);
+        inv_transform4x4(c);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        svc_st4(rec + off + r * Wc, clip255((int)L.pv[r * 4] + c[r * 4]), clip255((int)L.pv[r * 4 + 1] + c[r * 4 + 1]), clip255((int)L.pv[r * 4 + 2] + c[r * 4 + 2]),
+                clip255((int)L.pv[r * 4 + 3] + c[r * 4 + 3]));
+    // outputs = the macroblock object's fields after the call; state = the same fields, carried to the next picture of the layer
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { out.chroma_ac_level[plane][blk][i] = L.ac[i]; st.chroma_ac_level[plane][blk][i] = L.ac[i]; }
+    if (blk == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { out.chroma_dc_level[plane][k] = (int16_t)dcl[k]; st.chroma_dc_level[plane][k] = (int16_t)dcl[k]; }
+        out.cbp_chroma_dc4x4[plane] = (uint8_t)dc_mask;
+        out.cbp_chroma_ac4x4[plane] = (uint8_t)ac_mask;
+    }
+}
+
+HLB_HD unsigned svc_luma_cbp(const SvcXchg& X)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m |= (unsigned)X.luma_coded[i] << i;
+    return m;
+}
+
+}  // namespace hlb

@@ -16,6 +16,7 @@ class Hlb200Error(RuntimeError):
 MB_MOTION = np.dtype([("part_mode", "u1"), ("sub_mode", "u1", (4,)), ("ref_idx", "i1", (4,)), ("pad", "u1", (3,)), ("mv", "<i2", (4, 4, 2))])
 MB_COEFFS = np.dtype([("luma_level", "<i2", (16, 16)), ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16)),
                       ("cbp_luma4x4", "<u2"), ("cbp_chroma_dc4x4", "u1", (2,)), ("cbp_chroma_ac4x4", "u1", (2,)), ("pad", "u1", (2,))])
+SVC_STATE = np.dtype([("chroma_ac_level", "<i2", (2, 4, 16)), ("chroma_dc_level", "<i2", (2, 4))])   # hlb200_svc_mb_state_t
 ME_CAND = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("part_x", "u1"), ("part_y", "u1"), ("part_w", "u1"), ("part_h", "u1"), ("mv_x", "<i2"), ("mv_y", "<i2")])
 ME_COST = np.dtype([("dist", "<i4"), ("bits_rest", "<i4"), ("single_ctr", "<i4"), ("cbp_luma4x4", "<u2"), ("total_coeff", "u1", (16,)),
                     ("trailing_ones", "u1", (16,)), ("pad", "<u2")])
@@ -60,6 +61,7 @@ def load():
         "hlb200_dev_tq_recon": [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp],
         "hlb200_dev_interp_luma_batch": [vp, ip, ip, ip, C.c_size_t, vp, vp, vp], "hlb200_dev_interp_chroma_batch": [vp, vp, ip, ip, ip, C.c_size_t, vp, vp, vp, vp],
         "hlb200_dev_tq_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp], "hlb200_dev_sad4x4": [vp, vp, ip, ip, ip, vp, vp],
+        "hlb200_dev_svc_inter_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp, vp],
         "hlb200_dev_me_cost": [vp, vp, ip, ip, ip, vp, ip, vp, vp], "hlb200_dev_int_alu_probe": [ip, ip, vp, vp, C.POINTER(C.c_uint64)],
     }
     for name, args in sig.items():

@@ -19,6 +19,8 @@
  *                              hl_codec_264_interpol_chroma_cpp pred_inter.c:888 (whole-frame batch, one MV set per MB)
  *   hlb200_tq_recon            _hl_codec_264_rdo_mb_reconstruct_inter rdo.c:2274 (residual part :2428-2478) and
  *                              _hl_codec_264_rdo_mb_reconstruct_chroma rdo.c:2502 (whole-frame batch)
+ *   hlb200_dev_svc_inter_recon_batch  hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 (SVC enhancement layer, base-mode inter
+ *                              macroblocks: prediction + residual coding + reconstruction fused, whole-picture batch)
  *   hlb200_sad4x4/satd4x4      hl_math_sad4x4_u8 source/hl_math.c:239, hl_math_satd4x4_u8 hl_math.c:283 (whole-frame batch)
  *   hlb200_me_cost             hl_codec_264_me_ds_mb_compute_cost_mode me_ds.c:527 (batch of independent candidates)
  *
@@ -123,6 +125,14 @@ typedef struct hlb200_mb_coeffs {
     uint8_t pad[2];
 } hlb200_mb_coeffs_t;
 
+/* What the reference's macroblock object carries from one picture of an SVC layer to the next and reads again:
+ * ChromaACLevel is only rewritten for blocks with a non-zero residual but used whenever a block's de-quantised DC is non-zero
+ * (source/h264/hl_codec_264_transf.c:236-245); ChromaDCLevel is only rewritten when a plane has a non-zero DC coefficient (rdo.c:2653). */
+typedef struct hlb200_svc_mb_state {
+    int16_t chroma_ac_level[2][4][16];
+    int16_t chroma_dc_level[2][4];
+} hlb200_svc_mb_state_t;
+
 /* One independent ME candidate for hlb200_me_cost (me_ds.c:527): partition rectangle inside MB (mb_x, mb_y) */
 typedef struct hlb200_me_cand {
     int16_t mb_x, mb_y;     /* macroblock coordinates */
@@ -202,6 +212,18 @@ HLB200_API int hlb200_dev_interp_chroma_batch(const uint8_t* d_ref_u, const uint
 HLB200_API int hlb200_dev_tq_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
                                          const uint8_t* d_pred_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
                                          hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
+/* SVC enhancement-layer inter macroblocks with base_mode_flag = 1 -- hl_codec_264_rdo_mb_guess_best_inter_pred_svc, source/h264/hl_codec_264_rdo.c:1273-1521
+ * (prediction :1340-1424, luma residual coding with the INTRA rounding offset :1428-1496, chroma :1500, CBP :1506): one fused launch over n_pics layer
+ * pictures (prediction from the layer's own reference picture + residual coding + reconstruction; the prediction never goes through HBM).
+ * d_motion = the partitions / motion vectors the inter-layer derivation (host, utils.c:966-2439) inferred from the base layer; d_state (in/out,
+ * n_pics x macroblocks, zero for a new layer) = hlb200_svc_mb_state_t; layout of planes and arrays as for the *_batch entry points above.
+ * The reference calls this function for every macroblock of an enhancement P picture, also for those whose base macroblock is intra: these
+ * arrive with predFlagL0 = 0 and no partition, the reference then codes them against UNINITIALISED prediction memory (its bitstream differs
+ * from run to run on such content); no behaviour exists to reproduce for them -- give them any valid motion and intra-code them upstream. */
+HLB200_API int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_ref_y, const uint8_t* d_ref_u,
+                                                const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
+                                                const hlb200_mb_motion_t* d_motion, hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs,
+                                                uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
 HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
 HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n,
                                   hlb200_me_cost_t* d_out, void* cuda_stream);

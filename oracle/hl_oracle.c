@@ -333,8 +333,33 @@ HLO_API int hlo_trial_luma4x4(const uint8_t* src, int ss, const uint8_t* pred, i
  * Planes are tight (pitch W for luma, W/2 for chroma).  chroma_ac is IN/OUT: it is the persistent ChromaACLevel of
  * the macroblock object (the reference does not clear it for blocks whose residual is all zero, and uses it whenever
  * the de-quantised DC of the block is non-zero -- transf.c:236-245).  Pass zeros for a stateless call. */
+static void recon_inter_mb_impl(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
+                                const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int mb_is_intra, int luma_intra_f, int16_t* luma_level /*[16][16]*/,
+                                int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,
+                                int32_t* cbp_ac /*[2]*/, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v);
 HLO_API void hlo_recon_inter_mb(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
                                 const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int mb_is_intra, int16_t* luma_level /*[16][16]*/,
+                                int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,
+                                int32_t* cbp_ac /*[2]*/, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v)
+{
+    recon_inter_mb_impl(src_y, src_u, src_v, pred_y, pred_u, pred_v, W, mbx, mby, qp, qpc, mb_is_intra, 0, luma_level, chroma_dc, chroma_ac, cbp_luma4x4, cbp_dc, cbp_ac,
+                        rec_y, rec_u, rec_v);
+}
+/* SVC enhancement-layer inter macroblock (base_mode_flag = 1), SURVEY 8a row a14: hl_codec_264_rdo_mb_guess_best_inter_pred_svc, rdo.c:1273-1521.
+ * After the (host-side, serial) inter-layer derivation of partitions / motion vectors and the interpolation of the prediction, the residual
+ * coding differs from the AVC inter macroblock in ONE thing: the luma coefficients are quantised with the INTRA rounding offset
+ * (__isIntraBlockTrue, rdo.c:1468); de-quantisation takes the coefficient block before scanning (rdo.c:1483), which is the same data.
+ * Chroma is the shared _hl_codec_264_rdo_mb_reconstruct_chroma (rdo.c:1500) with the macroblock flagged INFERRED = inter (mb.h:46). */
+HLO_API void hlo_recon_svc_inter_mb(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
+                                    const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int16_t* luma_level /*[16][16]*/,
+                                    int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,
+                                    int32_t* cbp_ac /*[2]*/, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v)
+{
+    recon_inter_mb_impl(src_y, src_u, src_v, pred_y, pred_u, pred_v, W, mbx, mby, qp, qpc, 0, 1, luma_level, chroma_dc, chroma_ac, cbp_luma4x4, cbp_dc, cbp_ac,
+                        rec_y, rec_u, rec_v);
+}
+static void recon_inter_mb_impl(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
+                                const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int mb_is_intra, int luma_intra_f, int16_t* luma_level /*[16][16]*/,
                                 int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,
                                 int32_t* cbp_ac /*[2]*/, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v)
 {
@@ -350,7 +375,7 @@ HLO_API void hlo_recon_inter_mb(const uint8_t* src_y, const uint8_t* src_u, cons
         for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) { res[y * 4 + x] = (int)s[y * W + x] - (int)p[y * W + x]; if (res[y * 4 + x]) all0 = 0; }
         if (!all0) {
             hlo_fwd4x4(res, w);
-            hlo_quant4x4(qp, 0, w, z);
+            hlo_quant4x4(qp, luma_intra_f, w, z);
             all0 = 1;
             for (i = 0; i < 16; ++i) if (z[i]) all0 = 0;
             if (!all0) { hlo_zigzag(z, lv); *cbp_luma4x4 |= 1 << b; }

@@ -256,6 +256,69 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
     return err;
 }
 
+
+/* SVC enhancement-layer inter macroblocks: hl_codec_264_rdo_mb_guess_best_inter_pred_svc, rdo.c:1273-1521.
+ * tag 7 (once per layer picture, before its first tag 6): [7, n, frame, DQId, W, H, then W*H*3/2 source bytes and W*H*3/2 bytes of RefPicList0[0], 4 per word]
+ * tag 6 (per macroblock, after the call): [6, n, frame, DQId, addr, QPy, QPc[2], NumMbPart, MbPartWidth, MbPartHeight, NumSubMbPart[4], SubMbPartWidth[4],
+ *         SubMbPartHeight[4], predFlagL0[4], refIdxL0[4], mvL0[4][4][2], CodedBlockPatternLuma4x4, CodedBlockPatternChromaDC4x4[2], CodedBlockPatternChromaAC4x4[2],
+ *         CodedBlockPatternLuma, CodedBlockPatternChroma, LumaLevel[16][16], ChromaDCLevel[2][4], ChromaACLevel[2][4][16], reconstructed Y 16x16, Cb 8x8, Cr 8x8 (one sample per word),
+ *         ChromaACLevel[2][4][16] as it was BEFORE the call, e_type, partWidth/partHeight[4][0],
+ *         ChromaDCLevel[2][4] as it was BEFORE the call] */
+static int g_svc_last_frame = -1, g_svc_last_dqid = -1;
+static void put_planes(const uint8_t* y, const uint8_t* u, const uint8_t* v, int W, int H)
+{
+    fwrite(y, 1, (size_t)W * H, g_trace); fwrite(u, 1, (size_t)W * H / 4, g_trace); fwrite(v, 1, (size_t)W * H / 4, g_trace);
+}
+extern HL_ERROR_T __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t*, hl_codec_264_t*);
+HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
+{
+    int32_t dc_in[2][4];
+    int32_t ac_in[2][4][16];   /* ChromaACLevel persists in the macroblock object from picture to picture and is read again when a block's residual is zero (transf.c:236-245) */
+    HL_ERROR_T err;
+    { int c_, b_, i_; for (c_ = 0; c_ < 2; ++c_) for (b_ = 0; b_ < 4; ++b_) for (i_ = 0; i_ < 16; ++i_) ac_in[c_][b_][i_] = p_mb->ChromaACLevel[c_][b_][i_];
+      for (c_ = 0; c_ < 2; ++c_) for (b_ = 0; b_ < 4; ++b_) dc_in[c_][b_] = p_mb->ChromaDCLevel[c_][b_]; }
+    err = __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(p_mb, p_codec);
+    if (g_trace && !err) {
+        hl_codec_264_layer_t* pc_layer = p_codec->layers.pc_active;
+        const hl_codec_264_pict_t* pict = pc_layer->pc_fs_curr->p_pict;
+        const int W = (int)pict->uWidthL, H = (int)pict->uHeightL, dq = (int)p_codec->layers.currDQId;
+        int32_t r[1200]; int k = 0, i, j, n, x, y;
+        if (g_svc_last_frame != g_frame_idx || g_svc_last_dqid != dq) {
+            const hl_codec_264_dpb_fs_t* fs = pc_layer->pobj_poc->RefPicList0[0];
+            const hl_frame_video_t* in = p_codec->encoder.pc_frame;
+            int32_t h7[6] = { 7, 6 + 2 * (W * H * 3 / 2) / 4, g_frame_idx, dq, W, H };
+            put32(h7, 6);
+            put_planes((const uint8_t*)in->data_ptr[0], (const uint8_t*)in->data_ptr[1], (const uint8_t*)in->data_ptr[2], W, H);
+            put_planes(fs->p_pict->pc_data_y, fs->p_pict->pc_data_u, fs->p_pict->pc_data_v, W, H);
+            g_svc_last_frame = g_frame_idx; g_svc_last_dqid = dq;
+        }
+        r[k++] = 6; r[k++] = 0; r[k++] = g_frame_idx; r[k++] = dq; r[k++] = (int32_t)p_mb->u_addr; r[k++] = p_mb->QPy; r[k++] = p_mb->QPc[0]; r[k++] = p_mb->QPc[1];
+        r[k++] = p_mb->NumMbPart; r[k++] = p_mb->MbPartWidth; r[k++] = p_mb->MbPartHeight;
+        for (i = 0; i < 4; ++i) r[k++] = p_mb->NumSubMbPart[i];
+        for (i = 0; i < 4; ++i) r[k++] = p_mb->SubMbPartWidth[i];
+        for (i = 0; i < 4; ++i) r[k++] = p_mb->SubMbPartHeight[i];
+        for (i = 0; i < 4; ++i) r[k++] = p_mb->predFlagL0[i];
+        for (i = 0; i < 4; ++i) r[k++] = p_mb->refIdxL0[i];
+        for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { r[k++] = p_mb->mvL0[i][j].x; r[k++] = p_mb->mvL0[i][j].y; }
+        r[k++] = (int32_t)p_mb->CodedBlockPatternLuma4x4; r[k++] = (int32_t)p_mb->CodedBlockPatternChromaDC4x4[0]; r[k++] = (int32_t)p_mb->CodedBlockPatternChromaDC4x4[1];
+        r[k++] = (int32_t)p_mb->CodedBlockPatternChromaAC4x4[0]; r[k++] = (int32_t)p_mb->CodedBlockPatternChromaAC4x4[1];
+        r[k++] = (int32_t)p_mb->CodedBlockPatternLuma; r[k++] = (int32_t)p_mb->CodedBlockPatternChroma;
+        for (i = 0; i < 16; ++i) for (j = 0; j < 16; ++j) r[k++] = p_mb->LumaLevel[i][j];
+        for (i = 0; i < 2; ++i) for (j = 0; j < 4; ++j) r[k++] = p_mb->ChromaDCLevel[i][j];
+        for (i = 0; i < 2; ++i) for (n = 0; n < 4; ++n) for (j = 0; j < 16; ++j) r[k++] = p_mb->ChromaACLevel[i][n][j];
+        for (y = 0; y < 16; ++y) for (x = 0; x < 16; ++x) r[k++] = pict->pc_data_y[(p_mb->yL + y) * W + p_mb->xL + x];
+        for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = pict->pc_data_u[(p_mb->yL / 2 + y) * (W / 2) + p_mb->xL / 2 + x];
+        for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = pict->pc_data_v[(p_mb->yL / 2 + y) * (W / 2) + p_mb->xL / 2 + x];
+        for (i = 0; i < 2; ++i) for (n = 0; n < 4; ++n) for (j = 0; j < 16; ++j) r[k++] = ac_in[i][n][j];
+        r[k++] = (int32_t)p_mb->e_type;
+        for (i = 0; i < 4; ++i) { r[k++] = p_mb->partWidth[i][0]; r[k++] = p_mb->partHeight[i][0]; }
+        for (i = 0; i < 2; ++i) for (j = 0; j < 4; ++j) r[k++] = dc_in[i][j];
+        r[1] = k;
+        put32(r, (size_t)k);
+    }
+    return err;
+}
+
 #endif /* HL_DRIVER_NO_WRAPS */
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -324,7 +387,7 @@ static void md5_hex(const uint8_t* p, size_t n, char out[33])
 
 int main(int argc, char** argv)
 {
-    int w = 352, h = 288, frames = 3, qp = 31, me_range = 16, refs = 1, gen = 1, gop = 400, early = 0, i;
+    int w = 352, h = 288, frames = 3, qp = 31, me_range = 16, refs = 1, gen = 1, gop = 400, early = 0, layers = 1, l, i;
     uint32_t seed = 1;
     const char *in_path = NULL, *out_path = NULL, *trace_path = NULL, *recon_path = NULL, *dump_in = NULL;
     const struct hl_codec_plugin_def_s* plugin = NULL;
@@ -343,6 +406,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--me-range") && i + 1 < argc) me_range = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--refs") && i + 1 < argc) refs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gop") && i + 1 < argc) gop = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--layers") && i + 1 < argc) layers = atoi(argv[++i]);   /* SVC spatial layers: layer l is (w << l) x (h << l), source/test_encoder.c:150-202 */
         else if (!strcmp(argv[i], "--early-term") && i + 1 < argc) early = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gen") && i + 1 < argc) { ++i; gen = !strcmp(argv[i], "g2") ? 2 : 1; }
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = (uint32_t)atoi(argv[++i]);
@@ -358,7 +422,8 @@ int main(int argc, char** argv)
     }
     if ((w & 15) || (h & 15)) { fprintf(stderr, "W and H must be multiples of 16 (hl_codec_264.c:428-439)\n"); return 2; }
     g_width = w; g_height = h;
-    frame_bytes = (size_t)w * h * 3 / 2;
+    if (layers < 1 || layers > 3) layers = 1;
+    frame_bytes = (size_t)(w << (layers - 1)) * (h << (layers - 1)) * 3 / 2;   /* largest layer */
     yuv = (uint8_t*)malloc(frame_bytes);
     stream_cap = frame_bytes * (size_t)(frames + 1) + 65536; stream = (uint8_t*)malloc(stream_cap);
     if (in_path && !(fin = fopen(in_path, "rb"))) { perror(in_path); return 2; }
@@ -393,30 +458,38 @@ int main(int argc, char** argv)
     codec->me_subpart_types = HL_VIDEO_ME_SUBPART_TYPE_ALL;
     codec->me_early_term_flag = early;
 
+    if (layers > 1)
+        for (l = 0; l < layers; ++l)
+            if ((err = hl_codec_add_layer(codec, (uint32_t)(w << l), (uint32_t)(h << l), 0, 0))) { fprintf(stderr, "add_layer %d failed: %d\n", l, err); return 1; }
     for (i = 0; i < frames; ++i) {
-        double t0, t1;
-        if (fin) { if (fread(yuv, 1, frame_bytes, fin) != frame_bytes) break; }
-        else if (gen == 1) gen_g1(yuv, w, h, i);
-        else gen_g2(yuv, w, h, i, seed);
-        if (fdump) fwrite(yuv, 1, frame_bytes, fdump);
-        if ((err = hl_frame_video_fill(frame, HL_VIDEO_CHROMA_YUV420, w, h, yuv, frame_bytes))) { fprintf(stderr, "fill %d\n", err); return 1; }
-        frame->encoding = HL_VIDEO_ENCODING_TYPE_AUTO;
-        g_frame_idx = i;
-        t0 = now_ms();
-        err = hl_codec_encode(codec, (hl_frame_t*)frame, result);
-        t1 = now_ms();
-        if (err) { fprintf(stderr, "encode frame %d failed: %d\n", i, err); return 1; }
-        t_total += t1 - t0; if (i > 0) { t_p += t1 - t0; ++n_p; }
-        if (result->type & HL_CODEC_RESULT_TYPE_HDR) {
-            memcpy(stream + stream_n, codec->hdr_bytes, codec->hdr_bytes_count); stream_n += codec->hdr_bytes_count;
+        for (l = 0; l < layers; ++l) {   /* one hl_codec_encode per layer per access unit (test_encoder.c:174-202) */
+            double t0, t1;
+            const int lw = w << l, lh = h << l;
+            const size_t lbytes = (size_t)lw * lh * 3 / 2;
+            if (fin) { if (fread(yuv, 1, lbytes, fin) != lbytes) goto done; }
+            else if (gen == 1) gen_g1(yuv, lw, lh, i);
+            else gen_g2(yuv, lw, lh, i, seed);
+            if (fdump) fwrite(yuv, 1, lbytes, fdump);
+            if ((err = hl_frame_video_fill(frame, HL_VIDEO_CHROMA_YUV420, lw, lh, yuv, lbytes))) { fprintf(stderr, "fill %d\n", err); return 1; }
+            frame->encoding = HL_VIDEO_ENCODING_TYPE_AUTO;
+            g_frame_idx = i;
+            t0 = now_ms();
+            err = hl_codec_encode(codec, (hl_frame_t*)frame, result);
+            t1 = now_ms();
+            if (err) { fprintf(stderr, "encode frame %d layer %d failed: %d\n", i, l, err); return 1; }
+            t_total += t1 - t0; if (i > 0) { t_p += t1 - t0; if (l == layers - 1) ++n_p; }
+            if (result->type & HL_CODEC_RESULT_TYPE_HDR) {
+                memcpy(stream + stream_n, codec->hdr_bytes, codec->hdr_bytes_count); stream_n += codec->hdr_bytes_count;
+            }
+            if ((result->type & HL_CODEC_RESULT_TYPE_DATA) && l == layers - 1) {   /* the access unit is returned with its last layer */
+                static const uint8_t scp[3] = { 0, 0, 1 };
+                memcpy(stream + stream_n, scp, 3); stream_n += 3;
+                memcpy(stream + stream_n, result->data_ptr, result->data_size); stream_n += result->data_size;
+            }
+            fprintf(stderr, "frame %d layer %d: %.1f ms, %zu bytes so far\n", i, l, t1 - t0, stream_n);
         }
-        if (result->type & HL_CODEC_RESULT_TYPE_DATA) {
-            static const uint8_t scp[3] = { 0, 0, 1 };
-            memcpy(stream + stream_n, scp, 3); stream_n += 3;
-            memcpy(stream + stream_n, result->data_ptr, result->data_size); stream_n += result->data_size;
-        }
-        fprintf(stderr, "frame %d: %.1f ms, %zu bytes so far\n", i, t1 - t0, stream_n);
     }
+done:
     if (fout) fwrite(stream, 1, stream_n, fout);
     md5_hex(stream, stream_n, md5);
     {

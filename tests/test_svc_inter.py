@@ -1,0 +1,239 @@
+"""SVC enhancement-layer inter macroblocks (base_mode_flag = 1) -- SURVEY 8a row a14, hl_codec_264_rdo_mb_guess_best_inter_pred_svc (rdo.c:1273-1521).
+
+CPU tier: the oracle restatement (oracle/hl_oracle.c: hlo_recon_svc_inter_mb, prediction by hlo_interp_luma/chroma) and the device source of the
+fused kernel run lane by lane on the CPU (tools/emu/svc_emu.cpp compiles hartallo_b200/csrc/hlb_svc.cuh as C++) against
+ * the committed golden fixture tests/golden/svc_inter.npz (made by tests/golden/make_golden_svc.py from the unmodified reference), and
+ * a live multi-layer encode of the reference where oracle/_ref exists (this container).
+GPU tier: hlb200_dev_svc_inter_recon_batch through the C-ABI against the same fixture, against the oracle on random pictures / motion fields
+(all partition shapes, vectors far outside the picture, random carried state), and a picture batch in one launch."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import reftrace
+import svc_util
+from oracle_lib import chroma_qp, i16p, i32p, load_oracle_mb, oracle_predict_frame, u8p
+from svc_util import MB_COEFFS, MB_MOTION, SVC_STATE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle():
+    o = load_oracle_mb()
+    o.hlo_recon_svc_inter_mb.restype = None
+    o.hlo_recon_svc_inter_mb.argtypes = [u8p] * 6 + [C.c_int] * 5 + [i16p, i16p, i16p, i32p, i32p, i32p, u8p, u8p, u8p]
+    return o
+
+
+def oracle_picture(o, src, ref, w, h, qp, qpc, motion, state_in):
+    """whole picture through the oracle: returns (coeffs, rec_yuv, state_out)"""
+    ysz, csz = w * h, w * h // 4
+    nmb = (w // 16) * (h // 16)
+    py, pu, pv = oracle_predict_frame(o, ref, w, h, motion)
+    sy, su, sv = (np.ascontiguousarray(src[:ysz]), np.ascontiguousarray(src[ysz:ysz + csz]), np.ascontiguousarray(src[ysz + csz:]))
+    ry, ru, rv = np.zeros(ysz, np.uint8), np.zeros(csz, np.uint8), np.zeros(csz, np.uint8)
+    coeffs, state = np.zeros(nmb, MB_COEFFS), state_in.copy()
+    c4, cdc, cac = np.zeros(1, np.int32), np.zeros(2, np.int32), np.zeros(2, np.int32)
+    for mb in range(nmb):
+        ll, dc = np.zeros(256, np.int16), np.ascontiguousarray(state[mb]["chroma_dc_level"].reshape(-1))
+        ac = np.ascontiguousarray(state[mb]["chroma_ac_level"].reshape(-1))
+        o.hlo_recon_svc_inter_mb(sy, su, sv, py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, mb % (w // 16), mb // (w // 16), qp, qpc, ll, dc, ac, c4, cdc, cac, ry, ru, rv)
+        c = coeffs[mb]
+        c["luma_level"], c["chroma_dc_level"], c["chroma_ac_level"] = ll.reshape(16, 16), dc.reshape(2, 4), ac.reshape(2, 4, 16)
+        c["cbp_luma4x4"], c["cbp_chroma_dc4x4"], c["cbp_chroma_ac4x4"] = int(c4[0]), cdc, cac
+        state[mb]["chroma_ac_level"], state[mb]["chroma_dc_level"] = ac.reshape(2, 4, 16), dc.reshape(2, 4)
+    return coeffs, np.concatenate([ry, ru, rv]), state
+
+
+_emu = None
+
+
+def _emu_lib():
+    """tools/emu/libsvc_emu.so: hartallo_b200/csrc/hlb_svc.cuh compiled as plain C++ (built on demand; g++ only)"""
+    global _emu
+    if _emu is None:
+        d = os.path.join(ROOT, "tools", "emu")
+        subprocess.check_call(["make", "-C", d, "libsvc_emu.so"], stdout=subprocess.DEVNULL)
+        _emu = C.CDLL(os.path.join(d, "libsvc_emu.so"))
+        _emu.svc_emu_inter_recon_batch.restype = C.c_int
+        _emu.svc_emu_inter_recon_batch.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 6
+    return _emu
+
+
+def emu_picture(src, ref, w, h, qp, motion, state_in):
+    ysz, csz = w * h, w * h // 4
+    src, ref, motion = np.ascontiguousarray(src), np.ascontiguousarray(ref), np.ascontiguousarray(motion)
+    rec, state, coeffs = np.zeros_like(src), state_in.copy(), np.zeros(len(motion), MB_COEFFS)
+    s, r, o = src.ctypes.data, ref.ctypes.data, rec.ctypes.data
+    rc = _emu_lib().svc_emu_inter_recon_batch(s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, 1, 0, qp, 0, motion.ctypes.data, state.ctypes.data,
+                                              coeffs.ctypes.data, o, o + ysz, o + ysz + csz)
+    assert rc == 0
+    return coeffs, rec, state
+
+
+def _fill_invalid(p):
+    """macroblocks without reference behaviour get zero motion (any valid motion will do; they are not compared)"""
+    return p["motion"].copy()
+
+
+# ------------------------------------------------------------------ CPU tier ------------------------------------------------------------------
+def test_golden_fixture_shape():
+    pics = svc_util.load_golden()
+    assert len(pics) == 9
+    modes = set()
+    for p in pics:
+        assert p["qp"] in (24, 31) and len(p["motion"]) == (p["w"] // 16) * (p["h"] // 16)
+        modes |= set(int(m) for m, v in zip(p["motion"]["part_mode"], p["valid"]) if v)
+    assert modes == {0, 1, 2, 3}                                    # 16x16, 16x8, 8x16, 8x8 all occur
+    assert any((p["valid"] == 0).any() for p in pics)               # and macroblocks whose base macroblock is intra (excluded from comparison)
+    assert any(p["dqid"] == 32 for p in pics)                       # third spatial layer
+
+
+def test_oracle_vs_golden():
+    o = _oracle()
+    n = 0
+    for p in svc_util.load_golden():
+        coeffs, rec, state = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], chroma_qp(p["qp"]), _fill_invalid(p), p["state_in"])
+        n += svc_util.compare_picture(p, coeffs, rec, state, "oracle")
+    assert n >= 500
+
+
+def test_device_source_on_cpu_vs_golden():
+    n = 0
+    for p in svc_util.load_golden():
+        coeffs, rec, state = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], _fill_invalid(p), p["state_in"])
+        n += svc_util.compare_picture(p, coeffs, rec, state, "hlb_svc.cuh on the CPU")
+    assert n >= 500
+
+
+@pytest.mark.skipif(not reftrace.have_driver(), reason="oracle/_ref/hl_ref_driver only exists where the reference tree is available")
+@pytest.mark.parametrize("args", [["--size", "176", "144", "--layers", "2", "--frames", "3", "--gen", "g1"],
+                                  ["--size", "80", "64", "--layers", "3", "--frames", "3", "--gen", "g2", "--seed", "11", "--qp", "28"],
+                                  ["--size", "96", "80", "--layers", "2", "--frames", "4", "--gen", "g2", "--seed", "4", "--qp", "40"]])
+def test_live_reference(tmp_path, args):
+    """oracle and device source against a fresh multi-layer encode of the reference (QCIF -> CIF is the lower half of BASELINE.json configs[3])"""
+    tr = str(tmp_path / "svc.trace")
+    svc_util.run_driver_svc(args, tr)
+    o = _oracle()
+    n = 0
+    for p in svc_util.pictures_from_trace(tr):
+        c1, r1, s1 = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], p["qpc"], p["motion"], p["state_in"])
+        n += svc_util.compare_picture(p, c1, r1, s1, "oracle")
+        c2, r2, s2 = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], p["motion"], p["state_in"])
+        svc_util.compare_picture(p, c2, r2, s2, "hlb_svc.cuh on the CPU")
+    assert n > 100
+
+
+def _random_case(rng, w, h, far_every=0):
+    from test_oracle_pinned import stress_plane
+    nmb = (w // 16) * (h // 16)
+
+    def frame():
+        return np.concatenate([stress_plane(rng, h, w).reshape(-1), stress_plane(rng, h // 2, w // 2).reshape(-1), stress_plane(rng, h // 2, w // 2).reshape(-1)])
+    ref = frame()
+    # source = reference moved a little + noise, so that zero / small / large residuals all occur
+    src = ref.copy()
+    ysz = w * h
+    src[:ysz] = np.roll(ref[:ysz].reshape(h, w), (1, 2), (0, 1)).reshape(-1)
+    noise = rng.integers(-3, 4, src.shape)
+    mask = rng.random(src.shape) < 0.3
+    src = np.clip(src.astype(np.int32) + noise * mask, 0, 255).astype(np.uint8)
+    flat = rng.integers(0, nmb, max(1, nmb // 6))             # some macroblocks identical to the reference (zero residual -> stale state is read)
+    mbw = w // 16
+    m = np.zeros(nmb, MB_MOTION)
+    m["part_mode"] = rng.integers(0, 4, nmb)
+    m["sub_mode"] = rng.integers(0, 4, (nmb, 4))
+    m["mv"] = rng.integers(-40, 41, (nmb, 4, 4, 2))
+    if far_every:
+        idx = np.arange(0, nmb, far_every)
+        m["mv"][idx] = rng.integers(-9000, 9001, (len(idx), 4, 4, 2))
+    for a in flat:
+        m["part_mode"][a] = 0
+        m["mv"][a] = 0
+        x, y = (a % mbw) * 16, (a // mbw) * 16
+        sy, ry_ = src[:ysz].reshape(h, w), ref[:ysz].reshape(h, w)
+        sy[y:y + 16, x:x + 16] = ry_[y:y + 16, x:x + 16]
+        for pl in range(2):
+            o = ysz + pl * (ysz // 4)
+            sc, rc = src[o:o + ysz // 4].reshape(h // 2, w // 2), ref[o:o + ysz // 4].reshape(h // 2, w // 2)
+            sc[y // 2:y // 2 + 8, x // 2:x // 2 + 8] = rc[y // 2:y // 2 + 8, x // 2:x // 2 + 8]
+            if rng.random() < 0.5:
+                sc[y // 2:y // 2 + 4, x // 2:x // 2 + 4] += 9          # one block with a DC-only difference: its three neighbours read their stale AC levels
+    st = np.zeros(nmb, SVC_STATE)
+    st["chroma_ac_level"][:, :, :, :15] = rng.integers(-2, 3, (nmb, 2, 4, 15)) * (rng.random((nmb, 2, 4, 15)) < 0.2)
+    st["chroma_dc_level"] = rng.integers(-3, 4, (nmb, 2, 4))
+    return src, ref, m, st
+
+
+@pytest.mark.parametrize("w,h,qp,far", [(64, 48, 28, 0), (48, 64, 12, 3), (80, 32, 44, 0)])
+def test_device_source_on_cpu_vs_oracle_random(w, h, qp, far):
+    """all partition shapes (also the sub-8x8 ones the dyadic inter-layer derivation never produces), out-of-picture vectors, carried state"""
+    rng = np.random.default_rng(w * 131 + qp)
+    src, ref, m, st = _random_case(rng, w, h, far)
+    c1, r1, s1 = oracle_picture(_oracle(), src, ref, w, h, qp, chroma_qp(qp), m, st)
+    c2, r2, s2 = emu_picture(src, ref, w, h, qp, m, st)
+    assert np.array_equal(r1, r2)
+    assert c1.tobytes() == c2.tobytes()
+    assert s1.tobytes() == s2.tobytes()
+    assert (c1["cbp_luma4x4"] != 0).any() and (c1["cbp_luma4x4"] != 0xffff).any()
+
+
+# ------------------------------------------------------------------ GPU tier ------------------------------------------------------------------
+def gpu_pictures(pics_in, qp):
+    """pics_in: list of (src, ref, motion, state) of ONE size -> one launch of hlb200_dev_svc_inter_recon_batch over all of them"""
+    import torch
+    from hartallo_b200 import lib as hl
+    lib = hl.load()
+    assert hl.MB_COEFFS.itemsize == MB_COEFFS.itemsize and hl.MB_MOTION.itemsize == MB_MOTION.itemsize and hl.SVC_STATE.itemsize == SVC_STATE.itemsize
+    n = len(pics_in)
+    dev = torch.device("cuda:0")
+    srcs, refs = np.stack([p[0] for p in pics_in]), np.stack([p[1] for p in pics_in])
+    motion, state = np.concatenate([p[2] for p in pics_in]), np.concatenate([p[3] for p in pics_in])
+    w, h = gpu_pictures.size
+    ysz, csz = w * h, w * h // 4
+    fb = ysz + 2 * csz
+    nmb = (w // 16) * (h // 16)
+    d_src, d_ref = torch.from_numpy(srcs).to(dev), torch.from_numpy(refs).to(dev)
+    d_rec = torch.zeros_like(d_src)
+    d_motion = torch.from_numpy(np.ascontiguousarray(motion).view(np.uint8)).to(dev)
+    d_state = torch.from_numpy(np.ascontiguousarray(state).view(np.uint8).copy()).to(dev)
+    d_coef = torch.zeros(n * nmb * MB_COEFFS.itemsize, dtype=torch.uint8, device=dev)
+    s, r, o = d_src.data_ptr(), d_ref.data_ptr(), d_rec.data_ptr()
+    hl.check(lib.hlb200_dev_svc_inter_recon_batch(s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, n, fb, qp, 0, d_motion.data_ptr(), d_state.data_ptr(),
+                                                  d_coef.data_ptr(), o, o + ysz, o + ysz + csz, torch.cuda.current_stream().cuda_stream), "svc_inter_recon_batch")
+    torch.cuda.synchronize()
+    coef = d_coef.cpu().numpy().view(MB_COEFFS).reshape(n, nmb)
+    st = d_state.cpu().numpy().view(SVC_STATE).reshape(n, nmb)
+    return coef, d_rec.cpu().numpy(), st
+
+
+@pytest.mark.gpu
+def test_gpu_vs_golden():
+    n = 0
+    for p in svc_util.load_golden():
+        gpu_pictures.size = (p["w"], p["h"])
+        coef, rec, st = gpu_pictures([(p["src"], p["ref"], _fill_invalid(p), p["state_in"])], p["qp"])
+        n += svc_util.compare_picture(p, coef[0], rec[0], st[0], "GPU")
+    assert n >= 500
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,qp,n", [(64, 48, 28, 1), (176, 144, 31, 5), (48, 64, 12, 3), (1920, 1088, 31, 1)])
+def test_gpu_vs_oracle_random(w, h, qp, n):
+    rng = np.random.default_rng(w + 7 * qp + n)
+    cases = [_random_case(rng, w, h, far_every=3 if i == 1 or n == 1 else 0) for i in range(n)]
+    gpu_pictures.size = (w, h)
+    coef, rec, st = gpu_pictures(cases, qp)
+    o = _oracle()
+    for i, (src, ref, m, s0) in enumerate(cases):
+        if w >= 1920:   # full size: the oracle on a band of macroblock rows is enough for a picture whose rows are independent; the rest against the CPU run of the device source
+            c2, r2, s2 = emu_picture(src, ref, w, h, qp, m, s0)
+            assert np.array_equal(rec[i], r2) and coef[i].tobytes() == c2.tobytes() and st[i].tobytes() == s2.tobytes()
+            continue
+        c1, r1, s1 = oracle_picture(o, src, ref, w, h, qp, chroma_qp(qp), m, s0)
+        assert np.array_equal(rec[i], r1), i
+        assert coef[i].tobytes() == c1.tobytes(), i
+        assert st[i].tobytes() == s1.tobytes(), i

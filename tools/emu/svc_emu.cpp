@@ -1,0 +1,40 @@
+// CPU run of the SVC enhancement-layer macroblock phases of hartallo_b200/csrc/hlb_svc.cuh (the body of k_svc_inter_recon): the lanes of a warp become a
+// loop, the __syncwarp between the phases becomes the end of the first loop.  Same argument list as hlb200_dev_svc_inter_recon_batch, host pointers.
+// A debugging aid and the CPU-tier check of that source against the reference's trace (tests/test_svc_inter.py); NOT linked into libhl_b200.so and
+// not an oracle (the oracle is oracle/hl_oracle.c: hlo_recon_svc_inter_mb).
+#include <stddef.h>
+#include <stdint.h>
+#include "../../hartallo_b200/csrc/hlb_svc.cuh"
+
+static int host_chroma_qp(int qp_y, int offset) { int q = qp_y + offset; q = q < 0 ? 0 : (q > 51 ? 51 : q); return hlb::kQpc[q]; }
+
+extern "C" __attribute__((visibility("default"))) int svc_emu_inter_recon_batch(
+    const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v, int width, int height, int n_pics,
+    size_t frame_stride, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion, hlb200_svc_mb_state_t* state, hlb200_mb_coeffs_t* coeffs, uint8_t* rec_y,
+    uint8_t* rec_u, uint8_t* rec_v)
+{
+    if ((width & 15) || (height & 15) || qp < 0 || qp > 51 || n_pics < 1) return HLB200_ERR_INVALID_PARAMETER;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4), qpc = host_chroma_qp(qp, chroma_qp_index_offset);
+    for (int pic = 0; pic < n_pics; ++pic) {
+        const size_t o = (size_t)pic * frame_stride;
+        hlb::SvcPlanes P;
+        P.src_y = src_y + o; P.src_u = src_u + o; P.src_v = src_v + o; P.ref_y = ref_y + o; P.ref_u = ref_u + o; P.ref_v = ref_v + o;
+        P.rec_y = rec_y + o; P.rec_u = rec_u + o; P.rec_v = rec_v + o; P.W = width; P.H = height;
+        for (int mb = 0; mb < nmb; ++mb) {
+            const size_t idx = (size_t)pic * nmb + mb;
+            const int mbx = mb % mbw, mby = mb / mbw;
+            hlb::SvcXchg X;
+            hlb::SvcChromaLane L[8];
+            for (int lane = 0; lane < 24; ++lane) {
+                if (lane < 16) hlb::svc_luma_lane(P, mbx, mby, lane, motion[idx], qp, coeffs[idx], X);
+                else hlb::svc_chroma_lane_a(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, motion[idx], qpc, state[idx], L[lane - 16], X);
+            }
+            // all phase-A reads of the state happen before any phase-B write, as on the device; run phase B on a snapshot of the DC state so that
+            // lane order cannot matter here either
+            for (int lane = 16; lane < 24; ++lane)
+                hlb::svc_chroma_lane_b(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, qpc, state[idx], L[lane - 16], X, coeffs[idx]);
+            coeffs[idx].cbp_luma4x4 = (uint16_t)hlb::svc_luma_cbp(X);
+        }
+    }
+    return HLB200_OK;
+}
