@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ sr
 // ---------------- SVC enhancement-layer inter macroblock (base mode): prediction + residual coding + reconstruction, one warp per MB -----------
 // lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks; lanes 20..23: Cr blocks; the per-lane phases live in hlb_svc.cuh (the same source runs on the
 // CPU in tools/emu/svc_emu.cpp).  The 2x2 chroma DC stage / elimination exchange goes through 56 bytes of shared memory per warp.
+// BL = true: I_BL macroblocks (enhancement-layer I pictures, hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301-461): P.ref_* are the prediction planes, no motion.
+template <bool BL>
 __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, int nmb, int qp, int qpc, const hlb200_mb_motion_t* __restrict__ motion,
                                                          hlb200_svc_mb_state_t* __restrict__ state, hlb200_mb_coeffs_t* __restrict__ coeffs, size_t stride)
 {
@@ -260,16 +262,16 @@ __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, i
     }
     const size_t idx = (size_t)blockIdx.y * nmb + warp;
     const int mbx = warp % mbw, mby = warp / mbw;
-    const hlb200_mb_motion_t& m = motion[idx];
+    const hlb200_mb_motion_t* m = BL ? nullptr : motion + idx;
     hlb200_mb_coeffs_t& out = coeffs[idx];
     hlb200_svc_mb_state_t& st = state[idx];
     SvcXchg& X = xs[threadIdx.x >> 5];
     SvcChromaLane L;
     const int plane = (lane - 16) >> 2, cblk = (lane - 16) & 3;
-    if (lane < 16) svc_luma_lane(P, mbx, mby, lane, m, qp, out, X);
-    else if (lane < 24) svc_chroma_lane_a(P, mbx, mby, plane, cblk, m, qpc, st, L, X);
+    if (lane < 16) svc_luma_lane<BL>(P, mbx, mby, lane, m, qp, out, X);
+    else if (lane < 24) svc_chroma_lane_a<BL>(P, mbx, mby, plane, cblk, m, qpc, st, L, X);
     __syncwarp();
-    if (lane >= 16 && lane < 24) svc_chroma_lane_b(P, mbx, mby, plane, cblk, qpc, st, L, X, out);
+    if (lane >= 16 && lane < 24) svc_chroma_lane_b<BL>(P, mbx, mby, plane, cblk, qpc, st, L, X, out);
     if (lane == 0) out.cbp_luma4x4 = (uint16_t)svc_luma_cbp(X);
 }
 
@@ -412,22 +414,37 @@ int hlb200_dev_tq_recon(const uint8_t* d_src_y, const uint8_t* d_src_u, const ui
                                      d_recon_v, cuda_stream);
 }
 
+static int launch_svc(bool bl, const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_ref_y, const uint8_t* d_ref_u, const uint8_t* d_ref_v,
+                      int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* d_motion,
+                      hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream)
+{
+    if (!d_src_y || !d_src_u || !d_src_v || !d_ref_y || !d_ref_u || !d_ref_v || (!bl && !d_motion) || !d_state || !d_coeffs || !d_recon_y || !d_recon_u || !d_recon_v ||
+        width < 16 || height < 16 || (width & 15) || (height & 15) || qp < 0 || qp > 51 || n_pics < 1 || n_pics > 65535)
+        return HLB200_ERR_INVALID_PARAMETER;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4), qpc = host_chroma_qp(qp, chroma_qp_index_offset);
+    SvcPlanes P;
+    P.src_y = d_src_y; P.src_u = d_src_u; P.src_v = d_src_v; P.ref_y = d_ref_y; P.ref_u = d_ref_u; P.ref_v = d_ref_v;
+    P.rec_y = d_recon_y; P.rec_u = d_recon_u; P.rec_v = d_recon_v; P.W = width; P.H = height;
+    const dim3 grid((nmb * 32 + 127) / 128, n_pics);
+    if (bl) k_svc_inter_recon<true><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, nullptr, d_state, d_coeffs, frame_stride);
+    else k_svc_inter_recon<false><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, d_motion, d_state, d_coeffs, frame_stride);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
 int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_ref_y, const uint8_t* d_ref_u,
                                      const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
                                      const hlb200_mb_motion_t* d_motion, hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y,
                                      uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream)
 {
-    if (!d_src_y || !d_src_u || !d_src_v || !d_ref_y || !d_ref_u || !d_ref_v || !d_motion || !d_state || !d_coeffs || !d_recon_y || !d_recon_u || !d_recon_v ||
-        width < 16 || height < 16 || (width & 15) || (height & 15) || qp < 0 || qp > 51 || n_pics < 1 || n_pics > 65535)
-        return HLB200_ERR_INVALID_PARAMETER;
-    const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    SvcPlanes P;
-    P.src_y = d_src_y; P.src_u = d_src_u; P.src_v = d_src_v; P.ref_y = d_ref_y; P.ref_u = d_ref_u; P.ref_v = d_ref_v;
-    P.rec_y = d_recon_y; P.rec_u = d_recon_u; P.rec_v = d_recon_v; P.W = width; P.H = height;
-    k_svc_inter_recon<<<dim3((nmb * 32 + 127) / 128, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, host_chroma_qp(qp, chroma_qp_index_offset), d_motion, d_state,
-                                                                                                   d_coeffs, frame_stride);
-    HLB_CUDA(cudaGetLastError());
-    return HLB200_OK;
+    return launch_svc(false, d_src_y, d_src_u, d_src_v, d_ref_y, d_ref_u, d_ref_v, width, height, n_pics, frame_stride, qp, chroma_qp_index_offset, d_motion, d_state, d_coeffs,
+                      d_recon_y, d_recon_u, d_recon_v, cuda_stream);
+}
+int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
+                                  const uint8_t* d_pred_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
+                                  hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream)
+{
+    return launch_svc(true, d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, n_pics, frame_stride, qp, chroma_qp_index_offset, nullptr, d_state, d_coeffs,
+                      d_recon_y, d_recon_u, d_recon_v, cuda_stream);
 }
 
 int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream)

@@ -59,13 +59,15 @@ HLB_HD uint32_t svc_ld4(const uint8_t* p) { return HLB_LDG(reinterpret_cast<cons
 HLB_HD void svc_st4(uint8_t* p, int a, int b, int c, int d) { *reinterpret_cast<uint32_t*>(p) = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
 
 struct SvcPlanes {
-    const uint8_t *src_y, *src_u, *src_v, *ref_y, *ref_u, *ref_v;
+    const uint8_t *src_y, *src_u, *src_v;
+    const uint8_t *ref_y, *ref_u, *ref_v;   // inter (base mode): reference picture of the layer, or
+                                            // I_BL: the PREDICTION planes (base-layer reconstruction resampled by the host, G.8.6.2)
     uint8_t *rec_y, *rec_u, *rec_v;
     int W, H;
 };
 
 // ---- luma lane (blk = luma4x4BlkIdx): prediction -> residual -> T -> Q (intra offset) -> Q^-1 -> T^-1 -> reconstruction (rdo.c:1428-1496) ----
-HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t& m, int qp, hlb200_mb_coeffs_t& out, SvcXchg& X)
+HLB_HD void svc_luma_predict(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t& m, uint8_t pv[16])
 {
     const int bx = blk_x(blk), by = blk_y(blk), W = P.W, H = P.H;
     const SvcPart g = svc_part_of(m.part_mode, m.sub_mode, bx, by);
@@ -89,10 +91,25 @@ HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const h
             for (int c = 0; c < 9; ++c) win[r * 9 + c] = HLB_LDG(P.ref_y + y * W + clip3(0, W - 1, X0 - 2 + c));
         }
     }
-    uint8_t pv[16];
     interp_luma_4x4(win + 2 * 9 + 2, 9, mvx & 3, mvy & 3, pv);
-
+}
+// I_BL: the prediction is a plane (rdo.c:363, mbPredL)
+HLB_HD void svc_load_pred4x4(const uint8_t* plane, int off, int pitch, uint8_t pv[16])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t w = svc_ld4(plane + off + r * pitch);
+        pv[r * 4] = (uint8_t)w; pv[r * 4 + 1] = (uint8_t)(w >> 8); pv[r * 4 + 2] = (uint8_t)(w >> 16); pv[r * 4 + 3] = (uint8_t)(w >> 24);
+    }
+}
+template <bool BL>
+HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t* m, int qp, hlb200_mb_coeffs_t& out, SvcXchg& X)
+{
+    const int bx = blk_x(blk), by = blk_y(blk), W = P.W;
     const int off = (mby * 16 + by) * W + mbx * 16 + bx;
+    uint8_t pv[16];
+    if (BL) svc_load_pred4x4(P.ref_y, off, W, pv);
+    else svc_luma_predict(P, mbx, mby, blk, *m, pv);
     int mm[16], lv[16];
     bool nz = false;
 #pragma unroll
@@ -131,12 +148,10 @@ HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const h
 }
 
 // ---- chroma lane, phase A (plane 0 = Cb, 1 = Cr; blk raster 0..3): prediction, forward pass of the block (rdo.c:2561-2638) ----
-HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t& m, int qpc, hlb200_svc_mb_state_t& st,
-                              SvcChromaLane& L, SvcXchg& X)
+HLB_HD void svc_chroma_predict(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t& m, SvcChromaLane& L)
 {
     const int Wc = P.W >> 1, Hc = P.H >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
     const uint8_t* ref = plane ? P.ref_v : P.ref_u;
-    const uint8_t* src = plane ? P.src_v : P.src_u;
     // 8.4.2.2.2 per sample; a 2x2 chroma area is the smallest one with its own motion vector
 #pragma unroll
     for (int y = 0; y < 4; ++y)
@@ -152,7 +167,16 @@ HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, i
             L.pv[y * 4 + x] = (uint8_t)interp_chroma_px(a0, a1, c0, c1, xf, yf);
             L.pv[y * 4 + x + 1] = (uint8_t)interp_chroma_px(a1, a2, c1, c2, xf, yf);
         }
+}
+template <bool BL>
+HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t* m, int qpc, hlb200_svc_mb_state_t& st,
+                              SvcChromaLane& L, SvcXchg& X)
+{
+    const int Wc = P.W >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
+    const uint8_t* src = plane ? P.src_v : P.src_u;
     const int off = (mby * 8 + by) * Wc + mbx * 8 + bx;
+    if (BL) svc_load_pred4x4(plane ? P.ref_v : P.ref_u, off, Wc, L.pv);
+    else svc_chroma_predict(P, mbx, mby, plane, blk, *m, L);
     int mm[16];
     bool nz = false;
 #pragma unroll
@@ -186,6 +210,7 @@ HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, i
 }
 
 // ---- chroma lane, phase B: elimination, 2x2 DC, reconstruction of the block (rdo.c:2640-2682, transf.c:161-296) ----
+template <bool BL>
 HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, int blk, int qpc, hlb200_svc_mb_state_t& st, const SvcChromaLane& L,
                               const SvcXchg& X, hlb200_mb_coeffs_t& out)
 {
@@ -202,7 +227,8 @@ HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, i
 #pragma unroll
         for (int k = 0; k < 4; ++k) dcl[k] = X.dc_coef[plane][k];
         hadamard2x2(dcl);
-        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ false);   // the inferred macroblock type is not an intra type (mb.h:46,57; rdo.c:2660)
+        // rdo.c:2660 uses the macroblock's own intra flag: an inferred macroblock with inter prediction is not intra (mb.h:46,57), an I_BL one is
+        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ BL);
 #pragma unroll
         for (int k = 0; k < 4; ++k) dc_mask |= (unsigned)(dcl[k] != 0) << k;
         if (dc_mask) {   // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5

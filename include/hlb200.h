@@ -21,6 +21,8 @@
  *                              _hl_codec_264_rdo_mb_reconstruct_chroma rdo.c:2502 (whole-frame batch)
  *   hlb200_dev_svc_inter_recon_batch  hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 (SVC enhancement layer, base-mode inter
  *                              macroblocks: prediction + residual coding + reconstruction fused, whole-picture batch)
+ *   hlb200_dev_svc_bl_recon_batch     hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301 (I_BL macroblocks: residual coding + reconstruction
+ *                              against the host-resampled base layer)
  *   hlb200_sad4x4/satd4x4      hl_math_sad4x4_u8 source/hl_math.c:239, hl_math_satd4x4_u8 hl_math.c:283 (whole-frame batch)
  *   hlb200_me_cost             hl_codec_264_me_ds_mb_compute_cost_mode me_ds.c:527 (batch of independent candidates)
  *
@@ -224,6 +226,13 @@ HLB200_API int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const ui
                                                 const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
                                                 const hlb200_mb_motion_t* d_motion, hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs,
                                                 uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
+/* I_BL macroblocks (enhancement-layer I pictures) -- hl_codec_264_rdo_mb_guess_best_intra_pred_svc, rdo.c:301-461: the prediction is the base-layer reconstruction
+ * resampled by the host (G.8.6.2.1, _hl_codec_264_decode_svc_resample_intra_colour_comps, source/h264/hl_codec_264_decode_svc.c:216) and arrives as
+ * planes; residual coding and reconstruction are those of the base-mode inter macroblock above (rdo.c:387-446). */
+HLB200_API int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_pred_y, const uint8_t* d_pred_u,
+                                             const uint8_t* d_pred_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
+                                             hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v,
+                                             void* cuda_stream);
 HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
 HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n,
                                   hlb200_me_cost_t* d_out, void* cuda_stream);

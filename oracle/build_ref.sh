@@ -36,7 +36,7 @@ ar rcs "$OUT/libhartallo_ref.a" "$TMP"/obj/*.o
 # shared object with every reference symbol visible: lets tests call the *_cpp kernels directly (ctypes)
 gcc -shared -o "$OUT/libhartallo_ref.so" -Wl,--whole-archive "$OUT/libhartallo_ref.a" -Wl,--no-whole-archive -lpthread -lm -ldl
 # driver (our code, reference public API + link-time wrappers that record per-MB decisions / per-candidate traces)
-WRAPS="-Wl,--wrap=hl_codec_264_interpol_luma -Wl,--wrap=hl_codec_264_residual_write_block_cavlc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc -Wl,--wrap=hl_codec_264_me_ds_mb_find_best_cost -Wl,--wrap=hl_codec_264_nal_slice_data_encode -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_svc"
+WRAPS="-Wl,--wrap=hl_codec_264_interpol_luma -Wl,--wrap=hl_codec_264_residual_write_block_cavlc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc -Wl,--wrap=hl_codec_264_me_ds_mb_find_best_cost -Wl,--wrap=hl_codec_264_nal_slice_data_encode -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_svc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_svc"
 if [ -f "$HERE/ref_driver.c" ]; then
   gcc $CF -c "$HERE/ref_driver.c" -o "$TMP/obj_driver.o"
   gcc "$TMP/obj_driver.o" $WRAPS "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_ref_driver"

@@ -358,6 +358,17 @@ HLO_API void hlo_recon_svc_inter_mb(const uint8_t* src_y, const uint8_t* src_u, 
     recon_inter_mb_impl(src_y, src_u, src_v, pred_y, pred_u, pred_v, W, mbx, mby, qp, qpc, 0, 1, luma_level, chroma_dc, chroma_ac, cbp_luma4x4, cbp_dc, cbp_ac,
                         rec_y, rec_u, rec_v);
 }
+/* SVC enhancement-layer I_BL macroblock (enhancement I pictures): hl_codec_264_rdo_mb_guess_best_intra_pred_svc, rdo.c:301-461.  pred_* = the base-layer
+ * reconstruction resampled by G.8.6.2.1 (decode_svc.c:216, host side).  Luma as above (intra offset, rdo.c:404); in the shared chroma function the macroblock
+ * now counts as INTRA (the SVC initialisation process flags an I_BL macroblock intra), so the 2x2 DC quantisation uses the intra offset too (rdo.c:2660). */
+HLO_API void hlo_recon_svc_bl_mb(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
+                                 const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int16_t* luma_level /*[16][16]*/,
+                                 int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,
+                                 int32_t* cbp_ac /*[2]*/, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v)
+{
+    recon_inter_mb_impl(src_y, src_u, src_v, pred_y, pred_u, pred_v, W, mbx, mby, qp, qpc, 1, 1, luma_level, chroma_dc, chroma_ac, cbp_luma4x4, cbp_dc, cbp_ac,
+                        rec_y, rec_u, rec_v);
+}
 static void recon_inter_mb_impl(const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* pred_y, const uint8_t* pred_u,
                                 const uint8_t* pred_v, int W, int mbx, int mby, int qp, int qpc, int mb_is_intra, int luma_intra_f, int16_t* luma_level /*[16][16]*/,
                                 int16_t* chroma_dc /*[2][4]*/, int16_t* chroma_ac /*[2][4][16]*/, int32_t* cbp_luma4x4, int32_t* cbp_dc /*[2]*/,

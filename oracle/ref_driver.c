@@ -319,6 +319,58 @@ HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_
     return err;
 }
 
+/* SVC enhancement-layer I_BL macroblocks (enhancement I pictures): hl_codec_264_rdo_mb_guess_best_intra_pred_svc, rdo.c:301-461.  The prediction is the
+ * resampled base-layer reconstruction (G.8.6.2.1, _hl_codec_264_decode_svc_resample_intra_colour_comps in decode_svc.c -- host side); it is not
+ * stored anywhere, so the hook calls the same resampling function once more after the macroblock is done (it reads the reference layer only).
+ * tag 9 (once per layer picture): [9, n, frame, DQId, W, H, then W*H*3/2 source bytes, 4 per word]
+ * tag 8 (per macroblock): [8, n, frame, DQId, addr, QPy, QPc[2], CodedBlockPatternLuma4x4, CodedBlockPatternChromaDC4x4[2], CodedBlockPatternChromaAC4x4[2],
+ *         CodedBlockPatternLuma, CodedBlockPatternChroma, LumaLevel[16][16], ChromaDCLevel[2][4], ChromaACLevel[2][4][16], reconstructed Y 16x16, Cb 8x8, Cr 8x8,
+ *         ChromaACLevel / ChromaDCLevel as they were BEFORE the call, prediction Y 16x16, Cb 8x8, Cr 8x8] */
+extern HL_ERROR_T _hl_codec_264_decode_svc_resample_intra_colour_comps(hl_codec_264_t* p_codec, hl_codec_264_mb_t* p_mb, int32_t chromaFlag, int32_t iCbCr, int32_t mbW,
+                                                                        int32_t mbH, int32_t mbPred[16][16]);
+extern HL_ERROR_T __real_hl_codec_264_rdo_mb_guess_best_intra_pred_svc(hl_codec_264_mb_t*, hl_codec_264_t*);
+HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_intra_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
+{
+    int32_t dc_in[2][4], ac_in[2][4][16];
+    HL_ERROR_T err;
+    { int c_, b_, i_; for (c_ = 0; c_ < 2; ++c_) for (b_ = 0; b_ < 4; ++b_) { dc_in[c_][b_] = p_mb->ChromaDCLevel[c_][b_]; for (i_ = 0; i_ < 16; ++i_) ac_in[c_][b_][i_] = p_mb->ChromaACLevel[c_][b_][i_]; } }
+    err = __real_hl_codec_264_rdo_mb_guess_best_intra_pred_svc(p_mb, p_codec);
+    if (g_trace && !err) {
+        static HL_ALIGNED(16) int32_t pl[16][16], pcb[16][16], pcr[16][16];
+        hl_codec_264_layer_t* pc_layer = p_codec->layers.pc_active;
+        const hl_codec_264_pict_t* pict = pc_layer->pc_fs_curr->p_pict;
+        const int W = (int)pict->uWidthL, H = (int)pict->uHeightL, dq = (int)p_codec->layers.currDQId;
+        int32_t r[1400]; int k = 0, i, j, n, x, y;
+        if (g_svc_last_frame != g_frame_idx || g_svc_last_dqid != dq) {
+            const hl_frame_video_t* in = p_codec->encoder.pc_frame;
+            int32_t h9[6] = { 9, 6 + (W * H * 3 / 2) / 4, g_frame_idx, dq, W, H };
+            put32(h9, 6);
+            put_planes((const uint8_t*)in->data_ptr[0], (const uint8_t*)in->data_ptr[1], (const uint8_t*)in->data_ptr[2], W, H);
+            g_svc_last_frame = g_frame_idx; g_svc_last_dqid = dq;
+        }
+        if (_hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 0, -1, 16, 16, pl) || _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 0, 8, 8, pcb) ||
+            _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 1, 8, 8, pcr)) return err;
+        r[k++] = 8; r[k++] = 0; r[k++] = g_frame_idx; r[k++] = dq; r[k++] = (int32_t)p_mb->u_addr; r[k++] = p_mb->QPy; r[k++] = p_mb->QPc[0]; r[k++] = p_mb->QPc[1];
+        r[k++] = (int32_t)p_mb->CodedBlockPatternLuma4x4; r[k++] = (int32_t)p_mb->CodedBlockPatternChromaDC4x4[0]; r[k++] = (int32_t)p_mb->CodedBlockPatternChromaDC4x4[1];
+        r[k++] = (int32_t)p_mb->CodedBlockPatternChromaAC4x4[0]; r[k++] = (int32_t)p_mb->CodedBlockPatternChromaAC4x4[1];
+        r[k++] = (int32_t)p_mb->CodedBlockPatternLuma; r[k++] = (int32_t)p_mb->CodedBlockPatternChroma;
+        for (i = 0; i < 16; ++i) for (j = 0; j < 16; ++j) r[k++] = p_mb->LumaLevel[i][j];
+        for (i = 0; i < 2; ++i) for (j = 0; j < 4; ++j) r[k++] = p_mb->ChromaDCLevel[i][j];
+        for (i = 0; i < 2; ++i) for (n = 0; n < 4; ++n) for (j = 0; j < 16; ++j) r[k++] = p_mb->ChromaACLevel[i][n][j];
+        for (y = 0; y < 16; ++y) for (x = 0; x < 16; ++x) r[k++] = pict->pc_data_y[(p_mb->yL + y) * W + p_mb->xL + x];
+        for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = pict->pc_data_u[(p_mb->yL / 2 + y) * (W / 2) + p_mb->xL / 2 + x];
+        for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = pict->pc_data_v[(p_mb->yL / 2 + y) * (W / 2) + p_mb->xL / 2 + x];
+        for (i = 0; i < 2; ++i) for (n = 0; n < 4; ++n) for (j = 0; j < 16; ++j) r[k++] = ac_in[i][n][j];
+        for (i = 0; i < 2; ++i) for (j = 0; j < 4; ++j) r[k++] = dc_in[i][j];
+        for (y = 0; y < 16; ++y) for (x = 0; x < 16; ++x) r[k++] = pl[y][x];
+        for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = pcb[y][x];
+        for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = pcr[y][x];
+        r[1] = k;
+        put32(r, (size_t)k);
+    }
+    return err;
+}
+
 #endif /* HL_DRIVER_NO_WRAPS */
 
 /* ------------------------------------------------------------------------------------------------------------ */

@@ -65,6 +65,7 @@ def pictures_from_trace(path):
         ok = mode >= 0 and all(int(nsub[i]) >= 1 and int(pflag[i]) == 1 and int(ridx[i]) == 0 and int(pwh[i, 0]) == pw and int(pwh[i, 1]) == ph for i in range(nparts))
         ok = ok and e_type in (301, 302, 303, 304)
         p["valid"][a] = 1 if ok else 0
+        p["kind"] = 0
         if ok:
             m = p["motion"][a]
             m["part_mode"] = mode
@@ -79,6 +80,53 @@ def pictures_from_trace(path):
     return out
 
 
+def planes_of_mb(mbs, w, h):
+    """inverse of mb_of_planes: (nmb, 384) macroblock samples -> tight Y|U|V"""
+    mbw, mbh = w // 16, h // 16
+    y = mbs[:, :256].reshape(mbh, mbw, 16, 16).transpose(0, 2, 1, 3).reshape(-1)
+    u = mbs[:, 256:320].reshape(mbh, mbw, 8, 8).transpose(0, 2, 1, 3).reshape(-1)
+    v = mbs[:, 320:].reshape(mbh, mbw, 8, 8).transpose(0, 2, 1, 3).reshape(-1)
+    return np.concatenate([y, u, v]).astype(np.uint8)
+
+
+def bl_pictures_from_trace(path):
+    """enhancement-layer I pictures (I_BL macroblocks, tags 8 / 9): same dicts, `ref` holds the PREDICTION planes (resampled base layer), kind = 1"""
+    t = reftrace.parse(path)
+    pics, order = {}, []
+    for r in t.get(9, []):
+        W, H = int(r[4]), int(r[5])
+        n = W * H * 3 // 2
+        nmb = (W // 16) * (H // 16)
+        key = (int(r[2]), int(r[3]))
+        order.append(key)
+        pics[key] = dict(frame=key[0], dqid=key[1], w=W, h=H, qp=-1, kind=1, src=r[6:].view(np.uint8)[:n].copy(), pred_mb=np.zeros((nmb, 384), np.int32),
+                         motion=np.zeros(nmb, MB_MOTION), valid=np.ones(nmb, np.uint8), state_in=np.zeros(nmb, SVC_STATE), expect=np.zeros(nmb, MB_COEFFS),
+                         rec=np.zeros((nmb, 384), np.uint8), seen=0)
+    for r in t.get(8, []):
+        p = pics[(int(r[2]), int(r[3]))]
+        a = int(r[4])
+        p["qp"], p["qpc"] = int(r[5]), int(r[6])
+        k = 8
+        e = p["expect"][a]
+        e["cbp_luma4x4"] = int(r[k]); e["cbp_chroma_dc4x4"] = r[k + 1:k + 3]; e["cbp_chroma_ac4x4"] = r[k + 3:k + 5]; k += 7
+        e["luma_level"] = r[k:k + 256].reshape(16, 16); k += 256
+        e["chroma_dc_level"] = r[k:k + 8].reshape(2, 4); k += 8
+        e["chroma_ac_level"] = r[k:k + 128].reshape(2, 4, 16); k += 128
+        p["rec"][a] = r[k:k + 384]; k += 384
+        p["state_in"][a]["chroma_ac_level"] = r[k:k + 128].reshape(2, 4, 16); k += 128
+        p["state_in"][a]["chroma_dc_level"] = r[k:k + 8].reshape(2, 4); k += 8
+        p["pred_mb"][a] = r[k:k + 384]
+        p["seen"] += 1
+    out = []
+    for key in order:
+        p = pics[key]
+        assert p["seen"] == len(p["valid"])
+        assert p["pred_mb"].min() >= 0 and p["pred_mb"].max() <= 255     # the resampling process clips to the sample range (G.8.6.2.3)
+        p["ref"] = planes_of_mb(p.pop("pred_mb"), p["w"], p["h"])
+        out.append(p)
+    return out
+
+
 _KEYS = ("src", "ref", "motion", "valid", "state_in", "expect", "rec")
 
 
@@ -88,7 +136,7 @@ def save_golden(named_pics, path=GOLDEN):
         for i, p in enumerate(pics):
             tag = "%s.%d" % (name, i)
             index.append(tag)
-            d[tag + ".meta"] = np.array([p["w"], p["h"], p["qp"], p["frame"], p["dqid"]], np.int32)
+            d[tag + ".meta"] = np.array([p["w"], p["h"], p["qp"], p["frame"], p["dqid"], p.get("kind", 0)], np.int32)
             for k in _KEYS:
                 d[tag + "." + k] = p[k].view(np.uint8) if p[k].dtype.names else p[k]
     d["index"] = np.array(index)
@@ -100,8 +148,8 @@ def load_golden(path=GOLDEN):
     out = []
     for tag in z["index"]:
         tag = str(tag)
-        w, h, qp, frame, dqid = (int(v) for v in z[tag + ".meta"])
-        p = dict(name=tag, w=w, h=h, qp=qp, frame=frame, dqid=dqid)
+        w, h, qp, frame, dqid, kind = (int(v) for v in z[tag + ".meta"])
+        p = dict(name=tag, w=w, h=h, qp=qp, frame=frame, dqid=dqid, kind=kind)   # kind 0: base-mode inter picture, 1: I_BL picture (ref = prediction planes)
         for k, dt in (("src", None), ("ref", None), ("motion", MB_MOTION), ("valid", None), ("state_in", SVC_STATE), ("expect", MB_COEFFS), ("rec", None)):
             a = z[tag + "." + k]
             p[k] = a.view(dt).reshape(-1) if dt is not None else a

@@ -25,14 +25,19 @@ def _oracle():
     o = load_oracle_mb()
     o.hlo_recon_svc_inter_mb.restype = None
     o.hlo_recon_svc_inter_mb.argtypes = [u8p] * 6 + [C.c_int] * 5 + [i16p, i16p, i16p, i32p, i32p, i32p, u8p, u8p, u8p]
+    o.hlo_recon_svc_bl_mb.restype = None
+    o.hlo_recon_svc_bl_mb.argtypes = o.hlo_recon_svc_inter_mb.argtypes
     return o
 
 
-def oracle_picture(o, src, ref, w, h, qp, qpc, motion, state_in):
-    """whole picture through the oracle: returns (coeffs, rec_yuv, state_out)"""
+def oracle_picture(o, src, ref, w, h, qp, qpc, motion, state_in, bl=0):
+    """whole picture through the oracle: returns (coeffs, rec_yuv, state_out); bl: `ref` holds the prediction planes (I_BL, rdo.c:301: same residual coding)"""
     ysz, csz = w * h, w * h // 4
     nmb = (w // 16) * (h // 16)
-    py, pu, pv = oracle_predict_frame(o, ref, w, h, motion)
+    if bl:
+        py, pu, pv = (np.ascontiguousarray(ref[:ysz]), np.ascontiguousarray(ref[ysz:ysz + csz]), np.ascontiguousarray(ref[ysz + csz:]))
+    else:
+        py, pu, pv = oracle_predict_frame(o, ref, w, h, motion)
     sy, su, sv = (np.ascontiguousarray(src[:ysz]), np.ascontiguousarray(src[ysz:ysz + csz]), np.ascontiguousarray(src[ysz + csz:]))
     ry, ru, rv = np.zeros(ysz, np.uint8), np.zeros(csz, np.uint8), np.zeros(csz, np.uint8)
     coeffs, state = np.zeros(nmb, MB_COEFFS), state_in.copy()
@@ -40,7 +45,7 @@ def oracle_picture(o, src, ref, w, h, qp, qpc, motion, state_in):
     for mb in range(nmb):
         ll, dc = np.zeros(256, np.int16), np.ascontiguousarray(state[mb]["chroma_dc_level"].reshape(-1))
         ac = np.ascontiguousarray(state[mb]["chroma_ac_level"].reshape(-1))
-        o.hlo_recon_svc_inter_mb(sy, su, sv, py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, mb % (w // 16), mb // (w // 16), qp, qpc, ll, dc, ac, c4, cdc, cac, ry, ru, rv)
+        (o.hlo_recon_svc_bl_mb if bl else o.hlo_recon_svc_inter_mb)(sy, su, sv, py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, mb % (w // 16), mb // (w // 16), qp, qpc, ll, dc, ac, c4, cdc, cac, ry, ru, rv)
         c = coeffs[mb]
         c["luma_level"], c["chroma_dc_level"], c["chroma_ac_level"] = ll.reshape(16, 16), dc.reshape(2, 4), ac.reshape(2, 4, 16)
         c["cbp_luma4x4"], c["cbp_chroma_dc4x4"], c["cbp_chroma_ac4x4"] = int(c4[0]), cdc, cac
@@ -58,17 +63,17 @@ def _emu_lib():
         d = os.path.join(ROOT, "tools", "emu")
         subprocess.check_call(["make", "-C", d, "libsvc_emu.so"], stdout=subprocess.DEVNULL)
         _emu = C.CDLL(os.path.join(d, "libsvc_emu.so"))
-        _emu.svc_emu_inter_recon_batch.restype = C.c_int
-        _emu.svc_emu_inter_recon_batch.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 6
+        _emu.svc_emu_recon_batch.restype = C.c_int
+        _emu.svc_emu_recon_batch.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 6
     return _emu
 
 
-def emu_picture(src, ref, w, h, qp, motion, state_in):
+def emu_picture(src, ref, w, h, qp, motion, state_in, bl=0):
     ysz, csz = w * h, w * h // 4
     src, ref, motion = np.ascontiguousarray(src), np.ascontiguousarray(ref), np.ascontiguousarray(motion)
     rec, state, coeffs = np.zeros_like(src), state_in.copy(), np.zeros(len(motion), MB_COEFFS)
     s, r, o = src.ctypes.data, ref.ctypes.data, rec.ctypes.data
-    rc = _emu_lib().svc_emu_inter_recon_batch(s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, 1, 0, qp, 0, motion.ctypes.data, state.ctypes.data,
+    rc = _emu_lib().svc_emu_recon_batch(bl, s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, 1, 0, qp, 0, motion.ctypes.data, state.ctypes.data,
                                               coeffs.ctypes.data, o, o + ysz, o + ysz + csz)
     assert rc == 0
     return coeffs, rec, state
@@ -82,11 +87,11 @@ def _fill_invalid(p):
 # ------------------------------------------------------------------ CPU tier ------------------------------------------------------------------
 def test_golden_fixture_shape():
     pics = svc_util.load_golden()
-    assert len(pics) == 9
+    assert len(pics) == 13 and sum(p["kind"] for p in pics) == 4     # 9 P pictures (base-mode inter) + 4 I pictures (I_BL)
     modes = set()
     for p in pics:
         assert p["qp"] in (24, 31) and len(p["motion"]) == (p["w"] // 16) * (p["h"] // 16)
-        modes |= set(int(m) for m, v in zip(p["motion"]["part_mode"], p["valid"]) if v)
+        modes |= set(int(m) for m, v in zip(p["motion"]["part_mode"], p["valid"]) if v and not p["kind"])
     assert modes == {0, 1, 2, 3}                                    # 16x16, 16x8, 8x16, 8x8 all occur
     assert any((p["valid"] == 0).any() for p in pics)               # and macroblocks whose base macroblock is intra (excluded from comparison)
     assert any(p["dqid"] == 32 for p in pics)                       # third spatial layer
@@ -96,17 +101,17 @@ def test_oracle_vs_golden():
     o = _oracle()
     n = 0
     for p in svc_util.load_golden():
-        coeffs, rec, state = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], chroma_qp(p["qp"]), _fill_invalid(p), p["state_in"])
+        coeffs, rec, state = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], chroma_qp(p["qp"]), _fill_invalid(p), p["state_in"], p["kind"])
         n += svc_util.compare_picture(p, coeffs, rec, state, "oracle")
-    assert n >= 500
+    assert n >= 700
 
 
 def test_device_source_on_cpu_vs_golden():
     n = 0
     for p in svc_util.load_golden():
-        coeffs, rec, state = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], _fill_invalid(p), p["state_in"])
+        coeffs, rec, state = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], _fill_invalid(p), p["state_in"], p["kind"])
         n += svc_util.compare_picture(p, coeffs, rec, state, "hlb_svc.cuh on the CPU")
-    assert n >= 500
+    assert n >= 700
 
 
 @pytest.mark.skipif(not reftrace.have_driver(), reason="oracle/_ref/hl_ref_driver only exists where the reference tree is available")
@@ -119,10 +124,10 @@ def test_live_reference(tmp_path, args):
     svc_util.run_driver_svc(args, tr)
     o = _oracle()
     n = 0
-    for p in svc_util.pictures_from_trace(tr):
-        c1, r1, s1 = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], p["qpc"], p["motion"], p["state_in"])
+    for p in svc_util.bl_pictures_from_trace(tr) + svc_util.pictures_from_trace(tr):
+        c1, r1, s1 = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], p["qpc"], p["motion"], p["state_in"], p["kind"])
         n += svc_util.compare_picture(p, c1, r1, s1, "oracle")
-        c2, r2, s2 = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], p["motion"], p["state_in"])
+        c2, r2, s2 = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], p["motion"], p["state_in"], p["kind"])
         svc_util.compare_picture(p, c2, r2, s2, "hlb_svc.cuh on the CPU")
     assert n > 100
 
@@ -168,13 +173,13 @@ def _random_case(rng, w, h, far_every=0):
     return src, ref, m, st
 
 
-@pytest.mark.parametrize("w,h,qp,far", [(64, 48, 28, 0), (48, 64, 12, 3), (80, 32, 44, 0)])
-def test_device_source_on_cpu_vs_oracle_random(w, h, qp, far):
+@pytest.mark.parametrize("w,h,qp,far,bl", [(64, 48, 28, 0, 0), (48, 64, 12, 3, 0), (80, 32, 44, 0, 0), (64, 64, 30, 0, 1)])
+def test_device_source_on_cpu_vs_oracle_random(w, h, qp, far, bl):
     """all partition shapes (also the sub-8x8 ones the dyadic inter-layer derivation never produces), out-of-picture vectors, carried state"""
     rng = np.random.default_rng(w * 131 + qp)
     src, ref, m, st = _random_case(rng, w, h, far)
-    c1, r1, s1 = oracle_picture(_oracle(), src, ref, w, h, qp, chroma_qp(qp), m, st)
-    c2, r2, s2 = emu_picture(src, ref, w, h, qp, m, st)
+    c1, r1, s1 = oracle_picture(_oracle(), src, ref, w, h, qp, chroma_qp(qp), m, st, bl)
+    c2, r2, s2 = emu_picture(src, ref, w, h, qp, m, st, bl)
     assert np.array_equal(r1, r2)
     assert c1.tobytes() == c2.tobytes()
     assert s1.tobytes() == s2.tobytes()
@@ -182,7 +187,7 @@ def test_device_source_on_cpu_vs_oracle_random(w, h, qp, far):
 
 
 # ------------------------------------------------------------------ GPU tier ------------------------------------------------------------------
-def gpu_pictures(pics_in, qp):
+def gpu_pictures(pics_in, qp, bl=0):
     """pics_in: list of (src, ref, motion, state) of ONE size -> one launch of hlb200_dev_svc_inter_recon_batch over all of them"""
     import torch
     from hartallo_b200 import lib as hl
@@ -202,8 +207,13 @@ def gpu_pictures(pics_in, qp):
     d_state = torch.from_numpy(np.ascontiguousarray(state).view(np.uint8).copy()).to(dev)
     d_coef = torch.zeros(n * nmb * MB_COEFFS.itemsize, dtype=torch.uint8, device=dev)
     s, r, o = d_src.data_ptr(), d_ref.data_ptr(), d_rec.data_ptr()
-    hl.check(lib.hlb200_dev_svc_inter_recon_batch(s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, n, fb, qp, 0, d_motion.data_ptr(), d_state.data_ptr(),
-                                                  d_coef.data_ptr(), o, o + ysz, o + ysz + csz, torch.cuda.current_stream().cuda_stream), "svc_inter_recon_batch")
+    sp = torch.cuda.current_stream().cuda_stream
+    if bl:
+        hl.check(lib.hlb200_dev_svc_bl_recon_batch(s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, n, fb, qp, 0, d_state.data_ptr(), d_coef.data_ptr(),
+                                                   o, o + ysz, o + ysz + csz, sp), "svc_bl_recon_batch")
+    else:
+        hl.check(lib.hlb200_dev_svc_inter_recon_batch(s, s + ysz, s + ysz + csz, r, r + ysz, r + ysz + csz, w, h, n, fb, qp, 0, d_motion.data_ptr(), d_state.data_ptr(),
+                                                      d_coef.data_ptr(), o, o + ysz, o + ysz + csz, sp), "svc_inter_recon_batch")
     torch.cuda.synchronize()
     coef = d_coef.cpu().numpy().view(MB_COEFFS).reshape(n, nmb)
     st = d_state.cpu().numpy().view(SVC_STATE).reshape(n, nmb)
@@ -215,25 +225,26 @@ def test_gpu_vs_golden():
     n = 0
     for p in svc_util.load_golden():
         gpu_pictures.size = (p["w"], p["h"])
-        coef, rec, st = gpu_pictures([(p["src"], p["ref"], _fill_invalid(p), p["state_in"])], p["qp"])
+        coef, rec, st = gpu_pictures([(p["src"], p["ref"], _fill_invalid(p), p["state_in"])], p["qp"], p["kind"])
         n += svc_util.compare_picture(p, coef[0], rec[0], st[0], "GPU")
-    assert n >= 500
+    assert n >= 700
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,qp,n", [(64, 48, 28, 1), (176, 144, 31, 5), (48, 64, 12, 3), (1920, 1088, 31, 1)])
-def test_gpu_vs_oracle_random(w, h, qp, n):
+@pytest.mark.parametrize("w,h,qp,n,bl", [(64, 48, 28, 1, 0), (176, 144, 31, 5, 0), (48, 64, 12, 3, 0), (1920, 1088, 31, 1, 0), (176, 144, 26, 3, 1), (1920, 1088, 31, 2, 1)])
+def test_gpu_vs_oracle_random(w, h, qp, n, bl):
+    """bl = 1: the second plane set is used as the prediction itself (I_BL entry point)"""
     rng = np.random.default_rng(w + 7 * qp + n)
     cases = [_random_case(rng, w, h, far_every=3 if i == 1 or n == 1 else 0) for i in range(n)]
     gpu_pictures.size = (w, h)
-    coef, rec, st = gpu_pictures(cases, qp)
+    coef, rec, st = gpu_pictures(cases, qp, bl)
     o = _oracle()
     for i, (src, ref, m, s0) in enumerate(cases):
         if w >= 1920:   # full size: the oracle on a band of macroblock rows is enough for a picture whose rows are independent; the rest against the CPU run of the device source
-            c2, r2, s2 = emu_picture(src, ref, w, h, qp, m, s0)
+            c2, r2, s2 = emu_picture(src, ref, w, h, qp, m, s0, bl)
             assert np.array_equal(rec[i], r2) and coef[i].tobytes() == c2.tobytes() and st[i].tobytes() == s2.tobytes()
             continue
-        c1, r1, s1 = oracle_picture(o, src, ref, w, h, qp, chroma_qp(qp), m, s0)
+        c1, r1, s1 = oracle_picture(o, src, ref, w, h, qp, chroma_qp(qp), m, s0, bl)
         assert np.array_equal(rec[i], r1), i
         assert coef[i].tobytes() == c1.tobytes(), i
         assert st[i].tobytes() == s1.tobytes(), i

@@ -8,7 +8,8 @@
 
 static int host_chroma_qp(int qp_y, int offset) { int q = qp_y + offset; q = q < 0 ? 0 : (q > 51 ? 51 : q); return hlb::kQpc[q]; }
 
-extern "C" __attribute__((visibility("default"))) int svc_emu_inter_recon_batch(
+// bl != 0: I_BL macroblocks, ref_* are the prediction planes and motion is not read (hlb200_dev_svc_bl_recon_batch)
+extern "C" __attribute__((visibility("default"))) int svc_emu_recon_batch(int bl,
     const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v, int width, int height, int n_pics,
     size_t frame_stride, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion, hlb200_svc_mb_state_t* state, hlb200_mb_coeffs_t* coeffs, uint8_t* rec_y,
     uint8_t* rec_u, uint8_t* rec_v)
@@ -26,13 +27,21 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_inter_recon_batch(
             hlb::SvcXchg X;
             hlb::SvcChromaLane L[8];
             for (int lane = 0; lane < 24; ++lane) {
-                if (lane < 16) hlb::svc_luma_lane(P, mbx, mby, lane, motion[idx], qp, coeffs[idx], X);
-                else hlb::svc_chroma_lane_a(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, motion[idx], qpc, state[idx], L[lane - 16], X);
+                const int plane = (lane - 16) >> 2, cblk = (lane - 16) & 3;
+                if (bl) {
+                    if (lane < 16) hlb::svc_luma_lane<true>(P, mbx, mby, lane, nullptr, qp, coeffs[idx], X);
+                    else hlb::svc_chroma_lane_a<true>(P, mbx, mby, plane, cblk, nullptr, qpc, state[idx], L[lane - 16], X);
+                } else {
+                    if (lane < 16) hlb::svc_luma_lane<false>(P, mbx, mby, lane, motion + idx, qp, coeffs[idx], X);
+                    else hlb::svc_chroma_lane_a<false>(P, mbx, mby, plane, cblk, motion + idx, qpc, state[idx], L[lane - 16], X);
+                }
             }
-            // all phase-A reads of the state happen before any phase-B write, as on the device; run phase B on a snapshot of the DC state so that
-            // lane order cannot matter here either
-            for (int lane = 16; lane < 24; ++lane)
-                hlb::svc_chroma_lane_b(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, qpc, state[idx], L[lane - 16], X, coeffs[idx]);
+            // all phase-A reads of the state happen before any phase-B write, as on the device (phase B rewrites ChromaDCLevel with the values its
+            // other lanes read, or with new ones that nobody reads)
+            for (int lane = 16; lane < 24; ++lane) {
+                if (bl) hlb::svc_chroma_lane_b<true>(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, qpc, state[idx], L[lane - 16], X, coeffs[idx]);
+                else hlb::svc_chroma_lane_b<false>(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, qpc, state[idx], L[lane - 16], X, coeffs[idx]);
+            }
             coeffs[idx].cbp_luma4x4 = (uint16_t)hlb::svc_luma_cbp(X);
         }
     }
