@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Achieved HBM bandwidth of the stateless whole-picture kernels (luma / chroma interpolation, transform-quantisation-reconstruction) as a
 function of the picture batch per launch (GPU box only).  Algorithmic bytes per macroblock: SURVEY.md 8(d) -- interpolation 768 B
-(512 luma + 256 chroma), tq_recon 1,920 B.  Peak = MEASURED_PEAKS.json hbm_gbs.  Prints one JSON line per batch size."""
+(512 luma + 256 chroma), tq_recon 1,920 B, the fused SVC base-mode kernel (prediction + residual coding + reconstruction, no prediction planes)
+1,920 B = 384 reference + 384 source + 384 reconstruction + 768 levels, against 2,688 B for the three separate kernels.  Peak = MEASURED_PEAKS.json hbm_gbs.  Prints one JSON line per batch size."""
 import json
 import os
 import sys
@@ -34,13 +35,16 @@ for n in [int(a) for a in (sys.argv[1:] or ["1", "8", "32", "128"])]:
     pred, rec = torch.zeros_like(ref), torch.zeros_like(ref)
     motion = torch.from_numpy(np.concatenate([m1] * n).view(np.uint8)).to(dev)
     coef = torch.zeros(n * nmb * hl.MB_COEFFS.itemsize, dtype=torch.uint8, device=dev)
+    state = torch.zeros(n * nmb * hl.SVC_STATE.itemsize, dtype=torch.uint8, device=dev)
     b, p, s, r = ref.data_ptr(), pred.data_ptr(), src.data_ptr(), rec.data_ptr()
     ks = {
         "interp_luma": lambda: lib.hlb200_dev_interp_luma_batch(b, W, H, n, fb, motion.data_ptr(), p, sp),
         "interp_chroma": lambda: lib.hlb200_dev_interp_chroma_batch(b + ysz, b + ysz + csz, W, H, n, fb, motion.data_ptr(), p + ysz, p + ysz + csz, sp),
         "tq_recon": lambda: lib.hlb200_dev_tq_recon_batch(s, s + ysz, s + ysz + csz, p, p + ysz, p + ysz + csz, W, H, n, fb, QP, 0, coef.data_ptr(), r, r + ysz, r + ysz + csz, sp),
+        "svc_inter_recon": lambda: lib.hlb200_dev_svc_inter_recon_batch(s, s + ysz, s + ysz + csz, b, b + ysz, b + ysz + csz, W, H, n, fb, QP, 0, motion.data_ptr(), state.data_ptr(),
+                                                                        coef.data_ptr(), r, r + ysz, r + ysz + csz, sp),
     }
-    alg = {"interp_luma": 512, "interp_chroma": 256, "tq_recon": 1920}
+    alg = {"interp_luma": 512, "interp_chroma": 256, "tq_recon": 1920, "svc_inter_recon": 1920}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {"pictures_per_launch": n, "peak_gbs": PEAK, "peak_kind": PEAK_KIND, "kernels": {}}
     for name, k in ks.items():
@@ -57,4 +61,4 @@ for n in [int(a) for a in (sys.argv[1:] or ["1", "8", "32", "128"])]:
         gbs = alg[name] * nmb * n / (ms * 1e-3) / 1e9
         out["kernels"][name] = {"ms": round(ms, 4), "algorithmic_bytes": alg[name] * nmb * n, "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / PEAK, 4)}
     print(json.dumps(out))
-    del ref, src, pred, rec, motion, coef
+    del ref, src, pred, rec, motion, coef, state
