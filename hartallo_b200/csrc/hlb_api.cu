@@ -98,7 +98,7 @@ int hlb200_stream_destroy(hlb200_ctx_t* c)
         cudaFree(c->d_src[p]); cudaFree(c->d_pred[p]); cudaFree(c->d_tmp[p]);
         for (int s = 0; s < c->nslots; ++s) cudaFree(c->d_slot[s][p]);
     }
-    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_sched); cudaFree(c->d_scratch);
+    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_svc_state); cudaFree(c->d_sched); cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_jobs) cudaFreeHost(c->h_jobs);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -165,7 +165,44 @@ int hlb200_slot_download(hlb200_ctx_t* c, int slot, uint8_t* y, uint8_t* u, uint
 int hlb200_state_reset(hlb200_ctx_t* c)
 {
     if (!c) return HLB200_ERR_INVALID_PARAMETER;
+    if (c->d_svc_state) HLB_CUDA(cudaMemsetAsync(c->d_svc_state, 0, sizeof(hlb200_svc_mb_state_t) * c->nmb, c->stream));
     return slice_reset_state(c);
+}
+
+// One picture of an SVC enhancement layer (the context is the layer: its source picture was uploaded with hlb200_frame_upload, its frame stores hold
+// the layer's own reference pictures).  ref_slot >= 0: P picture, base-mode inter macroblocks predicted from that slot with `motion`;
+// ref_slot < 0: I picture, I_BL macroblocks predicted by the host-resampled planes pred_y/u/v.  The reconstruction is written to cur_slot.
+int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion, const uint8_t* pred_y,
+                             const uint8_t* pred_u, const uint8_t* pred_v, hlb200_mb_coeffs_t* out_coeffs)
+{
+    const bool bl = ref_slot < 0;
+    if (!c || ref_slot >= c->nslots || cur_slot < 0 || cur_slot >= c->nslots || cur_slot == ref_slot || !out_coeffs || qp < 0 || qp > 51) return HLB200_ERR_INVALID_PARAMETER;
+    if (bl ? (!pred_y || !pred_u || !pred_v) : !motion) return HLB200_ERR_INVALID_PARAMETER;
+    const size_t mbytes = (sizeof(hlb200_mb_motion_t) * c->nmb + 255) & ~(size_t)255, cbytes = sizeof(hlb200_mb_coeffs_t) * c->nmb;
+    int rc = ensure_scratch(c, mbytes + cbytes);
+    if (rc) return rc;
+    if (!c->d_svc_state) {
+        HLB_CUDA(cudaMalloc(&c->d_svc_state, sizeof(hlb200_svc_mb_state_t) * c->nmb));
+        HLB_CUDA(cudaMemsetAsync(c->d_svc_state, 0, sizeof(hlb200_svc_mb_state_t) * c->nmb, c->stream));
+    }
+    hlb200_mb_motion_t* d_motion = (hlb200_mb_motion_t*)c->d_scratch;
+    hlb200_mb_coeffs_t* d_coeffs = (hlb200_mb_coeffs_t*)((char*)c->d_scratch + mbytes);
+    if (bl) {
+        const uint8_t* hp[3] = {pred_y, pred_u, pred_v};
+        for (int p = 0; p < 3; ++p) if ((rc = h2d(c, c->d_pred[p], hp[p], plane_bytes(c, p)))) return rc;
+        rc = hlb200_dev_svc_bl_recon_batch(c->d_src_cur[0], c->d_src_cur[1], c->d_src_cur[2], c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, 1, 0, qp,
+                                           chroma_qp_index_offset, (hlb200_svc_mb_state_t*)c->d_svc_state, d_coeffs, c->d_slot[cur_slot][0], c->d_slot[cur_slot][1],
+                                           c->d_slot[cur_slot][2], c->stream);
+    } else {
+        if ((rc = h2d(c, d_motion, motion, sizeof(hlb200_mb_motion_t) * c->nmb))) return rc;
+        rc = hlb200_dev_svc_inter_recon_batch(c->d_src_cur[0], c->d_src_cur[1], c->d_src_cur[2], c->d_slot[ref_slot][0], c->d_slot[ref_slot][1], c->d_slot[ref_slot][2],
+                                              c->width, c->height, 1, 0, qp, chroma_qp_index_offset, d_motion, (hlb200_svc_mb_state_t*)c->d_svc_state, d_coeffs,
+                                              c->d_slot[cur_slot][0], c->d_slot[cur_slot][1], c->d_slot[cur_slot][2], c->stream);
+    }
+    if (rc) return rc;
+    if ((rc = d2h(c, out_coeffs, d_coeffs, cbytes))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
 }
 
 // ---- host-buffer batch wrappers -----------------------------------------------------------------------------------

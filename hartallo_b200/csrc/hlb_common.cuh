@@ -77,6 +77,7 @@ struct hlb200_ctx {
     void* h_pinned; size_t pinned_bytes;        // pinned staging
     struct hlb200_mb_record* d_records;
     void* d_mbstate;                            // per-MB state carried across MBs and frames
+    void* d_svc_state;                          // hlb200_svc_mb_state_t[nmb] when the context is an SVC enhancement layer (allocated on first use)
     void* d_sched; size_t sched_bytes;          // job descriptors + ready-queue scheduler words (hlb_slice.cu)
     void* h_jobs; int h_jobs_cap;               // pinned staging of the job descriptors
     int* last_sched;                            // scheduler words of the last launch (watchdog status)

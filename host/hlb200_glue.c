@@ -4,6 +4,8 @@
  *     -Wl,--wrap=hl_codec_264_nal_slice_data_encode
  *     -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc
  *     -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc
+ *     -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_svc      (SVC enhancement layers)
+ *     -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_svc
  * (or, inside the reference tree, call hlb200_glue_slice_begin() at the top of hl_codec_264_nal_slice_data_encode and replace
  * the two guess functions' bodies by hlb200_glue_apply()).
  *
@@ -123,6 +125,218 @@ static void glue_apply(hl_codec_264_mb_t* p_mb, const hlb200_mb_record_t* r, int
 }
 
 extern HL_ERROR_T __real_hl_codec_264_nal_slice_data_encode(hl_codec_264_t*, hl_codec_264_encode_slice_data_t*);
+
+/* ================================================================================================================================
+ * SVC enhancement layers (currDQId > 0).  The reference does no search there (base_mode_flag = 1 for every macroblock): what it computes per
+ * macroblock is (a) the inter-layer derivation of partitions / vectors (P) or the resampling of the base reconstruction (I) -- host code, serial,
+ * reads the reference layer only -- and (b) prediction + residual coding + reconstruction, hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 /
+ * ..._intra_pred_svc rdo.c:301.  (b) is independent per macroblock, so the hook runs (a) for the whole picture first, hands the picture to the device
+ * in ONE call (hlb200_svc_layer_picture) and lets the reference's own loop serialise the result.
+ * ================================================================================================================================ */
+#include "hartallo/h264/hl_codec_264_utils.h"
+#include "hartallo/h264/hl_codec_264_sps.h"
+
+#define GLUE_SVC_MAX_LAYERS 8
+typedef struct glue_svc_layer_s {
+    hlb200_ctx_t* ctx;
+    int w, h, nmb;
+    hlb200_mb_motion_t* motion;
+    hlb200_mb_coeffs_t* coeffs;
+    uint8_t* valid;          /* 0: a macroblock the reference itself codes against uninitialised memory (base macroblock intra inside a P picture): left to the host */
+    uint8_t *pred, *rec;     /* tight Y|U|V */
+} glue_svc_layer_t;
+static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
+static glue_svc_layer_t* g_svc_active = NULL;
+static int g_svc_intra = 0;
+
+extern HL_ERROR_T _hl_codec_264_decode_svc_resample_intra_colour_comps(hl_codec_264_t* p_codec, hl_codec_264_mb_t* p_mb, int32_t chromaFlag, int32_t iCbCr, int32_t mbW,
+                                                                        int32_t mbH, int32_t mbPred[16][16]);   /* source/h264/hl_codec_264_decode_svc.c:216 */
+
+/* the part of the two guess functions that precedes the prediction (rdo.c:1318-1346 / rdo.c:353-368): defaults + G.8.1.5.1 (+ G.8.4.1 for P) */
+static HL_ERROR_T glue_svc_derive(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec, int intra)
+{
+    HL_ERROR_T err;
+    p_mb->ext.svc.base_mode_flag = 1;
+    p_mb->mb_type = HL_CODEC_264_SVC_MB_TYPE_INFERRED;
+    p_mb->e_type = HL_CODEC_264_MB_TYPE_SVC_I_BL;
+    p_mb->flags_type = HL_CODEC_264_MB_TYPE_FLAGS_INFERRED;
+    p_mb->MbPartPredMode[0] = intra ? HL_CODEC_264_MB_MODE_INTRA_BL : HL_CODEC_264_MB_MODE_INTER_BL;
+    p_mb->NumMbPart = 1;
+    p_mb->MbPartWidth = p_mb->MbPartHeight = 16;
+    p_mb->CodedBlockPatternLuma4x4 = 0;
+    if ((err = hl_codec_264_utils_derivation_process_initialisation_svc(p_codec, p_mb))) return err;
+    if (!intra && (err = hl_codec_264_utils_derivation_process_for_mv_comps_and_ref_indices_svc(p_codec, p_mb))) return err;
+    return HL_ERROR_SUCCESS;
+}
+
+/* what the reference's macroblock loop does before it calls the guess function (slice.c:1787-1865) */
+static HL_ERROR_T glue_svc_loop_prologue(hl_codec_264_t* p_codec, hl_codec_264_encode_slice_data_t* p_esd, uint32_t addr, hl_codec_264_mb_t** pp_mb)
+{
+    hl_codec_264_layer_t* pc_layer = p_codec->layers.pc_active;
+    const hl_codec_264_nal_slice_header_t* hdr = p_esd->pc_slice->p_header;
+    const hl_codec_264_nal_sps_t* pc_sps = hdr->pc_pps->pc_sps;
+    hl_codec_264_mb_t* p_mb;
+    HL_ERROR_T err;
+    if (!(p_mb = pc_layer->pp_list_macroblocks[addr])) {
+        if ((err = hl_codec_264_mb_create(addr, &p_mb))) return err;
+        pc_layer->pp_list_macroblocks[addr] = p_mb;
+    }
+    p_mb->u_slice_idx = p_esd->pc_slice->u_idx;
+    if ((err = hl_codec_264_utils_init_mb_current_avc(p_codec, addr, hdr->l_id, HL_FALSE))) return err;
+    if (hdr->SVCExtFlag) {
+        p_mb->mb_type = HL_CODEC_264_SVC_MB_TYPE_INFERRED;
+        if (pc_sps->profile_idc == HL_CODEC_264_PROFILE_BASELINE_SVC) p_mb->ext.svc.InCropWindow = 1;
+        else {
+            const int32_t mbX = p_mb->u_x, mbY0 = p_mb->u_y, mbY1 = hdr->MbaffFrameFlag ? (mbY0 + 1) : mbY0, scalMbH = ((1 + hdr->field_pic_flag) << 4);
+            p_mb->ext.svc.InCropWindow = (!hdr->ext.svc.NoInterLayerPredFlag && (mbX >= ((hdr->ext.svc.ScaledRefLayerLeftOffset + 15) >> 4)) &&
+                                          (mbX < ((hdr->ext.svc.ScaledRefLayerLeftOffset + hdr->ext.svc.ScaledRefLayerPicWidthInSamplesL) >> 4)) &&
+                                          (mbY0 >= ((hdr->ext.svc.ScaledRefLayerTopOffset + scalMbH - 1) / scalMbH)) &&
+                                          (mbY1 < ((hdr->ext.svc.ScaledRefLayerTopOffset + hdr->ext.svc.ScaledRefLayerPicHeightInSamplesL) / scalMbH)));
+        }
+        p_mb->ext.svc.base_mode_flag = 1;
+    }
+    if ((err = hl_codec_264_mb_set_default_quant_values(p_mb, p_codec))) return err;
+    *pp_mb = p_mb;
+    return HL_ERROR_SUCCESS;
+}
+
+static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_slice_data_t* p_esd)
+{
+    hl_codec_264_layer_t* pc_layer = p_codec->layers.pc_active;
+    const hl_codec_264_nal_slice_header_t* hdr = p_esd->pc_slice->p_header;
+    const hl_frame_video_t* frame = p_codec->encoder.pc_frame;
+    const int W = (int)hdr->PicWidthInSamplesL, H = (int)hdr->PicHeightInSamplesL, Wc = W >> 1, Hc = H >> 1, mbw = W >> 4;
+    const int li = (int)(p_codec->layers.currDQId >> 4), intra = (p_codec->encoder.encoding_curr == HL_VIDEO_ENCODING_TYPE_INTRA);
+    const size_t ysz = (size_t)W * H, csz = (size_t)Wc * Hc;
+    glue_svc_layer_t* L;
+    HL_ERROR_T err;
+    int rc, qp = -1, x, y;
+    uint32_t addr;
+    static HL_ALIGNED(16) int32_t pl[16][16], pcb[16][16], pcr[16][16];
+
+    if (li <= 0 || li >= GLUE_SVC_MAX_LAYERS || (p_codec->layers.currDQId & 15) || p_esd->i_mb_start != 0 || p_esd->i_mb_end != (int32_t)hdr->PicSizeInMbs) {
+        HL_DEBUG_ERROR("hlb200: only single-slice spatial enhancement layers are supported by the device path");
+        return HL_ERROR_NOT_IMPLEMENTED;
+    }
+    L = &g_svc[li];
+    if (!L->ctx || L->w != W || L->h != H) {
+        const char* dev = getenv("HLB200_DEVICE");
+        if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->valid); free(L->pred); free(L->rec); }
+        if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
+        if ((rc = hlb200_stream_create(W, H, 1, &L->ctx))) return glue_fail("hlb200_stream_create", rc);
+        L->w = W; L->h = H; L->nmb = mbw * (H >> 4);
+        L->motion = (hlb200_mb_motion_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_motion_t));
+        L->coeffs = (hlb200_mb_coeffs_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_coeffs_t));
+        L->valid = (uint8_t*)calloc((size_t)L->nmb, 1);
+        L->pred = (uint8_t*)malloc(ysz + 2 * csz);
+        L->rec = (uint8_t*)malloc(ysz + 2 * csz);
+        if (!L->motion || !L->coeffs || !L->valid || !L->pred || !L->rec) return HL_ERROR_OUTOFMEMMORY;
+    }
+    /* (a) host, serial: inferred motion (P) or resampled base-layer prediction (I) of every macroblock */
+    memset(L->motion, 0, sizeof(hlb200_mb_motion_t) * (size_t)L->nmb);
+    for (addr = 0; addr < (uint32_t)L->nmb; ++addr) {
+        hl_codec_264_mb_t* p_mb;
+        const int mbx = (int)(addr % (uint32_t)mbw), mby = (int)(addr / (uint32_t)mbw);
+        if ((err = glue_svc_loop_prologue(p_codec, p_esd, addr, &p_mb))) return err;
+        if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;
+        if (qp < 0) qp = p_mb->QPy;
+        if (p_mb->QPy != qp) { HL_DEBUG_ERROR("hlb200: per-macroblock QP is not supported"); return HL_ERROR_NOT_IMPLEMENTED; }
+        if (intra) {
+            if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 0, -1, 16, 16, pl))) return err;
+            if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 0, 8, 8, pcb))) return err;
+            if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 1, 8, 8, pcr))) return err;
+            for (y = 0; y < 16; ++y) for (x = 0; x < 16; ++x) L->pred[(size_t)(mby * 16 + y) * W + mbx * 16 + x] = (uint8_t)pl[y][x];
+            for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) {
+                L->pred[ysz + (size_t)(mby * 8 + y) * Wc + mbx * 8 + x] = (uint8_t)pcb[y][x];
+                L->pred[ysz + csz + (size_t)(mby * 8 + y) * Wc + mbx * 8 + x] = (uint8_t)pcr[y][x];
+            }
+            L->valid[addr] = 1;
+        }
+        else {
+            hlb200_mb_motion_t* m = &L->motion[addr];
+            const int n = p_mb->NumMbPart, pw = p_mb->MbPartWidth, ph = p_mb->MbPartHeight;
+            const int mode = (n == 1 && pw == 16 && ph == 16) ? 0 : (n == 2 && pw == 16 && ph == 8) ? 1 : (n == 2 && pw == 8 && ph == 16) ? 2 : (n == 4 && pw == 8 && ph == 8) ? 3 : -1;
+            int p, ok = mode >= 0;
+            for (p = 0; ok && p < n; ++p) ok = p_mb->NumSubMbPart[p] >= 1 && p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == 0 && p_mb->partWidth[p][0] == pw && p_mb->partHeight[p][0] == ph;
+            L->valid[addr] = (uint8_t)ok;
+            if (ok) {
+                m->part_mode = (uint8_t)mode;
+                for (p = 0; p < n; ++p) { m->mv[p][0][0] = (int16_t)p_mb->mvL0[p][0].x; m->mv[p][0][1] = (int16_t)p_mb->mvL0[p][0].y; }
+            }
+        }
+    }
+    /* (b) device: one call for the picture */
+    if ((rc = hlb200_frame_upload(L->ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, Wc))) return glue_fail("hlb200_frame_upload", rc);
+    if (intra) rc = hlb200_svc_layer_picture(L->ctx, -1, 1, qp, hdr->pc_pps->chroma_qp_index_offset, NULL, L->pred, L->pred + ysz, L->pred + ysz + csz, L->coeffs);
+    else {
+        /* the layer's reference picture travels from the host DPB every time: macroblocks the host coded itself (valid = 0) are part of it */
+        const hl_codec_264_pict_t* ref = pc_layer->pobj_poc->RefPicList0[0] ? pc_layer->pobj_poc->RefPicList0[0]->p_pict : NULL;
+        if (!ref) return HL_ERROR_INVALID_STATE;
+        if ((rc = hlb200_slot_upload(L->ctx, 0, ref->pc_data_y, ref->pc_data_u, ref->pc_data_v))) return glue_fail("hlb200_slot_upload", rc);
+        rc = hlb200_svc_layer_picture(L->ctx, 0, 1, qp, hdr->pc_pps->chroma_qp_index_offset, L->motion, NULL, NULL, NULL, L->coeffs);
+    }
+    if (rc) return glue_fail("hlb200_svc_layer_picture", rc);
+    if ((rc = hlb200_slot_download(L->ctx, 1, L->rec, L->rec + ysz, L->rec + ysz + csz))) return glue_fail("hlb200_slot_download", rc);
+    /* the reference's own loop: same prologue again, the wrapped guess functions copy the device's results, the real writer serialises them */
+    g_svc_active = L; g_svc_intra = intra;
+    err = __real_hl_codec_264_nal_slice_data_encode(p_codec, p_esd);
+    g_svc_active = NULL;
+    return err;
+}
+
+static HL_ERROR_T glue_svc_apply(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec, int intra)
+{
+    glue_svc_layer_t* L = g_svc_active;
+    const hl_codec_264_pict_t* pict = p_codec->layers.pc_active->pc_fs_curr->p_pict;
+    const hlb200_mb_coeffs_t* c;
+    const int W = L->w, Wc = W >> 1;
+    const size_t ysz = (size_t)W * L->h, csz = ysz >> 2;
+    HL_ERROR_T err;
+    int b, i, k, y, i8;
+    if (p_mb->u_addr >= (uint32_t)L->nmb) return HL_ERROR_INVALID_STATE;
+    if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;   /* the fields later layers / pictures derive from */
+    c = &L->coeffs[p_mb->u_addr];
+    p_mb->CodedBlockPatternLuma4x4 = c->cbp_luma4x4;
+    for (b = 0; b < 16; ++b) for (i = 0; i < 16; ++i) p_mb->LumaLevel[b][i] = c->luma_level[b][i];
+    for (k = 0; k < 2; ++k) {
+        p_mb->CodedBlockPatternChromaDC4x4[k] = c->cbp_chroma_dc4x4[k];
+        p_mb->CodedBlockPatternChromaAC4x4[k] = c->cbp_chroma_ac4x4[k];
+        for (b = 0; b < 4; ++b) {
+            p_mb->ChromaDCLevel[k][b] = c->chroma_dc_level[k][b];
+            for (i = 0; i < 16; ++i) p_mb->ChromaACLevel[k][b][i] = c->chroma_ac_level[k][b][i];
+        }
+    }
+    for (y = 0; y < 16; ++y) memcpy(pict->pc_data_y + (size_t)(p_mb->yL + y) * W + p_mb->xL, L->rec + (size_t)(p_mb->yL + y) * W + p_mb->xL, 16);
+    for (y = 0; y < 8; ++y) {
+        memcpy(pict->pc_data_u + (size_t)(p_mb->yL / 2 + y) * Wc + p_mb->xL / 2, L->rec + ysz + (size_t)(p_mb->yL / 2 + y) * Wc + p_mb->xL / 2, 8);
+        memcpy(pict->pc_data_v + (size_t)(p_mb->yL / 2 + y) * Wc + p_mb->xL / 2, L->rec + ysz + csz + (size_t)(p_mb->yL / 2 + y) * Wc + p_mb->xL / 2, 8);
+    }
+    /* _hl_codec_264_rdo_mb_guess_cbp, rdo.c:2703-2781 (static there), for a macroblock that is not Intra16x16 */
+    p_mb->CodedBlockPatternLuma = 0;
+    for (i8 = 0; i8 < 4; ++i8) if ((p_mb->CodedBlockPatternLuma4x4 >> (i8 << 2)) & 15) p_mb->CodedBlockPatternLuma |= (1 << i8);
+    if ((p_mb->CodedBlockPatternChromaDC4x4[0] || p_mb->CodedBlockPatternChromaDC4x4[1]) && !p_mb->CodedBlockPatternChromaAC4x4[0] && !p_mb->CodedBlockPatternChromaAC4x4[1])
+        p_mb->CodedBlockPatternChroma = 1;
+    else if (p_mb->CodedBlockPatternChromaAC4x4[0] || p_mb->CodedBlockPatternChromaAC4x4[1]) p_mb->CodedBlockPatternChroma = 2;
+    else p_mb->CodedBlockPatternChroma = 0;
+    p_mb->coded_block_pattern = (p_mb->CodedBlockPatternChroma << 4 | p_mb->CodedBlockPatternLuma);
+    if (p_mb->coded_block_pattern > 47) { p_mb->coded_block_pattern -= 16; p_mb->CodedBlockPatternChroma = p_mb->coded_block_pattern >> 4; }
+    return HL_ERROR_SUCCESS;
+}
+
+extern HL_ERROR_T __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t*, hl_codec_264_t*);
+HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
+{
+    if (!g_svc_active) return HL_ERROR_INVALID_STATE;
+    /* base macroblock intra inside a P picture: the reference codes it against uninitialised memory; nothing to reproduce, the host keeps it */
+    if (p_mb->u_addr < (uint32_t)g_svc_active->nmb && !g_svc_active->valid[p_mb->u_addr]) return __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(p_mb, p_codec);
+    return glue_svc_apply(p_mb, p_codec, 0);
+}
+HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_intra_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
+{
+    if (!g_svc_active) return HL_ERROR_INVALID_STATE;
+    return glue_svc_apply(p_mb, p_codec, 1);
+}
+
 HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl_codec_264_encode_slice_data_t* p_esd)
 {
     hl_codec_264_layer_t* pc_layer = p_codec->layers.pc_active;
@@ -132,7 +346,11 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
     hlb200_slice_params_t prm;
     int rc, u, s, cur = -1;
 
-    if (p_codec->layers.currDQId > 0 || p_esd->i_mb_start != 0 || p_esd->i_mb_end != (int32_t)hdr->PicSizeInMbs) {
+    if (p_codec->layers.currDQId > 0) return glue_svc_slice(p_codec, p_esd);
+#ifdef HLB200_GLUE_HOST_BASE_LAYER   /* test builds without a GPU: the base layer stays on the reference's CPU path, only the enhancement-layer hook is exercised */
+    return __real_hl_codec_264_nal_slice_data_encode(p_codec, p_esd);
+#endif
+    if (p_esd->i_mb_start != 0 || p_esd->i_mb_end != (int32_t)hdr->PicSizeInMbs) {
         HL_DEBUG_ERROR("hlb200: only single-slice AVC pictures are supported by the device path");
         return HL_ERROR_NOT_IMPLEMENTED;
     }
@@ -173,7 +391,7 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
 
     if ((rc = hlb200_frame_upload(g.ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, W >> 1))) return glue_fail("hlb200_frame_upload", rc);
     if ((rc = hlb200_slice_encode(g.ctx, &prm, g.rec))) return glue_fail("hlb200_slice_encode", rc);
-    if (getenv("HLB200_SYNC_RECON")) {   /* only when something on the host reads the reconstruction (MD5 hooks, decoder round trip) */
+    if (getenv("HLB200_SYNC_RECON") || p_codec->encoder.b_svc_enabled) {   /* SVC: the enhancement layers resample / derive from the base picture on the host */   /* only when something on the host reads the reconstruction (MD5 hooks, decoder round trip) */
         const hl_codec_264_pict_t* pict = pc_layer->pc_fs_curr->p_pict;
         if ((rc = hlb200_slot_download(g.ctx, cur, (uint8_t*)pict->pc_data_y, (uint8_t*)pict->pc_data_u, (uint8_t*)pict->pc_data_v))) return glue_fail("hlb200_slot_download", rc);
     }

@@ -189,6 +189,15 @@ HLB200_API int hlb200_slice_grid_size(void); /* CTAs the slice kernel variant la
 HLB200_API int hlb200_slice_set_variant(int variant);
 HLB200_API int hlb200_slice_last_variant(void);   /* variant the most recent slice launch used (0 / 1) */
 
+/* ---- SVC enhancement layers (currDQId > 0): one picture of one layer; the context IS the layer (created with the layer's size; source picture uploaded with
+ * hlb200_frame_upload; frame stores = the layer's own reference pictures).  Replaces, for all macroblocks of the picture at once, the part of
+ * hl_codec_264_rdo_mb_guess_best_inter_pred_svc (rdo.c:1273; ref_slot >= 0, `motion` = what the inter-layer derivation inferred) or of
+ * hl_codec_264_rdo_mb_guess_best_intra_pred_svc (rdo.c:301; ref_slot < 0, pred_* = host-resampled base layer) that follows the derivation.  The reconstruction
+ * goes to frame store cur_slot (fetch it with hlb200_slot_download: the next layer's resampling runs on the host); the per-macroblock state the reference
+ * carries from picture to picture lives in the context (hlb200_state_reset clears it). ---- */
+HLB200_API int hlb200_svc_layer_picture(hlb200_ctx_t* ctx, int ref_slot, int cur_slot, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion,
+                                        const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v, hlb200_mb_coeffs_t* out_coeffs);
+
 /* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
 HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);
 HLB200_API int hlb200_interp_chroma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_u, uint8_t* pred_v);

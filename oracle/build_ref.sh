@@ -51,9 +51,18 @@ GLUE="$HERE/../host/hlb200_glue.c"
 if [ -f "$GLUE" ] && [ -f "$HERE/ref_driver.c" ]; then
   gcc $CF -DHL_DRIVER_NO_WRAPS -c "$HERE/ref_driver.c" -o "$TMP/obj_driver_nw.o"
   gcc $CF -I"$HERE/../include" -c "$GLUE" -o "$TMP/obj_glue.o"
-  GW="-Wl,--wrap=hl_codec_264_nal_slice_data_encode -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc"
+  GS="-Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_svc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_svc"
+  GW="-Wl,--wrap=hl_codec_264_nal_slice_data_encode -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_inter_pred_avc -Wl,--wrap=hl_codec_264_rdo_mb_guess_best_intra_pred_avc $GS"
   # libhl_b200.so is resolved at run time relative to the binary (oracle/_ref -> hartallo_b200)
   gcc "$TMP/obj_driver_nw.o" "$TMP/obj_glue.o" $GW "$OUT/libhartallo_ref.a" -L"$HERE/../hartallo_b200" -lhl_b200 -Wl,-rpath,'$ORIGIN/../../hartallo_b200' -lpthread -lm -ldl -o "$OUT/hl_b200_encoder" \
     || echo "build_ref: hl_b200_encoder not linked (build hartallo_b200/libhl_b200.so first)" >&2
+fi
+# CPU check of the SVC enhancement-layer hook of the glue: base layer on the reference's CPU path, enhancement layers through the glue with the device source
+# compiled as C++ standing in for libhl_b200.so (tools/emu/svc_shim.cpp + svc_emu.cpp)
+if [ -f "$GLUE" ] && [ -f "$HERE/../tools/emu/svc_shim.cpp" ]; then
+  gcc $CF -I"$HERE/../include" -DHLB200_GLUE_HOST_BASE_LAYER -c "$GLUE" -o "$TMP/obj_glue_svc.o"
+  g++ -std=c++17 -O2 -w -fPIC -x c++ -c "$HERE/../tools/emu/svc_shim.cpp" -o "$TMP/obj_shim.o"
+  g++ -std=c++17 -O2 -w -fPIC -x c++ -c "$HERE/../tools/emu/svc_emu.cpp" -o "$TMP/obj_emu.o"
+  g++ "$TMP/obj_driver_nw.o" "$TMP/obj_glue_svc.o" "$TMP/obj_shim.o" "$TMP/obj_emu.o" -Wl,--wrap=hl_codec_264_nal_slice_data_encode $GS "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_svc_glue_check"
 fi
 echo "build_ref: built $(ls "$OUT")"

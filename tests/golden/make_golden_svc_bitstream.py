@@ -1,0 +1,31 @@
+"""Generates tests/golden/svc_bitstream.json: size and MD5 of the multi-layer (SVC, dyadic spatial) bitstreams the UNMODIFIED reference produces
+(oracle/_ref/hl_ref_driver --layers N, the counterpart of source/test_encoder.c:150-202) on G1 content.  G1 only: on G2 content the reference's own
+multi-layer bitstream changes from run to run (it reads uninitialised memory; deterministic only with address-space randomisation switched off)."""
+import json
+import os
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import reftrace  # noqa: E402
+
+CONFIGS = {
+    "g1_qcif_cif": ["--size", "176", "144", "--layers", "2", "--frames", "3", "--gen", "g1"],                    # lower two layers of BASELINE.json configs[3]
+    "g1_qcif_cif_4cif": ["--size", "176", "144", "--layers", "3", "--frames", "2", "--gen", "g1"],              # configs[3]: QCIF -> CIF -> 4CIF
+    "g1_3layer_small_q24": ["--size", "64", "48", "--layers", "3", "--frames", "4", "--gen", "g1", "--qp", "24"],
+    "g1_2layer_q38": ["--size", "96", "80", "--layers", "2", "--frames", "4", "--gen", "g1", "--qp", "38"],
+}
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "svc_bitstream.json")
+
+if __name__ == "__main__":
+    res = {}
+    for name, args in CONFIGS.items():
+        runs = []
+        for _ in range(3):   # three runs each: the entry is only kept if the reference agrees with itself
+            o = subprocess.run([reftrace.DRIVER] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+            j = json.loads(o.stdout.strip().splitlines()[-1])
+            runs.append((j["bytes"], j["md5"]))
+        assert len(set(runs)) == 1, (name, runs)
+        res[name] = {"args": args, "bytes": runs[0][0], "md5": runs[0][1]}
+        print(name, runs[0])
+    json.dump(res, open(OUT, "w"), indent=1)

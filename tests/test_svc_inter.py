@@ -248,3 +248,39 @@ def test_gpu_vs_oracle_random(w, h, qp, n, bl):
         assert np.array_equal(rec[i], r1), i
         assert coef[i].tobytes() == c1.tobytes(), i
         assert st[i].tobytes() == s1.tobytes(), i
+
+
+# ------------------------------------------------------ the drop-in hook for enhancement layers ------------------------------------------------------
+import json  # noqa: E402
+
+SVC_STREAMS = json.load(open(os.path.join(ROOT, "tests", "golden", "svc_bitstream.json")))
+GLUE_CHECK = os.path.join(ROOT, "oracle", "_ref", "hl_svc_glue_check")
+B200_ENCODER = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder")
+
+
+def _encode(exe, args):
+    out = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stderr[-800:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not os.path.exists(GLUE_CHECK), reason="oracle/_ref/hl_svc_glue_check only exists where the reference tree is available")
+@pytest.mark.parametrize("name", sorted(SVC_STREAMS))
+def test_svc_glue_hook_bitstream_md5_cpu(name):
+    """host/hlb200_glue.c's enhancement-layer hook (derivation pre-pass -> ONE picture call -> the reference's own loop and CAVLC writer) with the device source
+    compiled as C++ standing in for the library (tools/emu/svc_shim.cpp), base layer on the reference's CPU path: the multi-layer bitstream must equal the
+    all-reference one byte for byte (QCIF -> CIF -> 4CIF is BASELINE.json configs[3])"""
+    g = SVC_STREAMS[name]
+    got = _encode(GLUE_CHECK, g["args"])
+    assert (got["bytes"], got["md5"]) == (g["bytes"], g["md5"]), (got, g)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(B200_ENCODER), reason="oracle/_ref/hl_b200_encoder not built (needs the reference tree at build time)")
+@pytest.mark.parametrize("name", sorted(SVC_STREAMS))
+def test_svc_bitstream_md5_drop_in(name):
+    """the same through the real library: every layer on the B200 (base layer: slice kernel; enhancement layers: k_svc_inter_recon), the reference's
+    unmodified host code around it"""
+    g = SVC_STREAMS[name]
+    got = _encode(B200_ENCODER, g["args"])
+    assert (got["bytes"], got["md5"]) == (g["bytes"], g["md5"]), (got, g)
