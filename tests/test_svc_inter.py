@@ -132,6 +132,14 @@ def test_live_reference(tmp_path, args):
     assert n > 100
 
 
+@pytest.mark.skipif(not reftrace.have_driver(), reason="oracle/_ref/hl_ref_driver only exists where the reference tree is available")
+def test_svc_fuzz_vs_live_reference():
+    """a few random multi-layer configurations of tools/emu/fuzz_svc.py (oracle + device source against the reference run live; bitstream MD5 through the
+    glue hook on G1 content)"""
+    out = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "emu", "fuzz_svc.py"), "6", "500"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and ", 0 mismatches" in out.stdout, out.stdout[-800:]
+
+
 def _random_case(rng, w, h, far_every=0):
     from test_oracle_pinned import stress_plane
     nmb = (w // 16) * (h // 16)
@@ -187,8 +195,8 @@ def test_device_source_on_cpu_vs_oracle_random(w, h, qp, far, bl):
 
 
 # ------------------------------------------------------------------ GPU tier ------------------------------------------------------------------
-def gpu_pictures(pics_in, qp, bl=0):
-    """pics_in: list of (src, ref, motion, state) of ONE size -> one launch of hlb200_dev_svc_inter_recon_batch over all of them"""
+def gpu_pictures(pics_in, size, qp, bl=0):
+    """pics_in: list of (src, ref, motion, state) of ONE size (w, h) -> one launch of hlb200_dev_svc_inter_recon_batch / _bl_recon_batch over all of them"""
     import torch
     from hartallo_b200 import lib as hl
     lib = hl.load()
@@ -197,7 +205,7 @@ def gpu_pictures(pics_in, qp, bl=0):
     dev = torch.device("cuda:0")
     srcs, refs = np.stack([p[0] for p in pics_in]), np.stack([p[1] for p in pics_in])
     motion, state = np.concatenate([p[2] for p in pics_in]), np.concatenate([p[3] for p in pics_in])
-    w, h = gpu_pictures.size
+    w, h = size
     ysz, csz = w * h, w * h // 4
     fb = ysz + 2 * csz
     nmb = (w // 16) * (h // 16)
@@ -224,8 +232,7 @@ def gpu_pictures(pics_in, qp, bl=0):
 def test_gpu_vs_golden():
     n = 0
     for p in svc_util.load_golden():
-        gpu_pictures.size = (p["w"], p["h"])
-        coef, rec, st = gpu_pictures([(p["src"], p["ref"], _fill_invalid(p), p["state_in"])], p["qp"], p["kind"])
+        coef, rec, st = gpu_pictures([(p["src"], p["ref"], _fill_invalid(p), p["state_in"])], (p["w"], p["h"]), p["qp"], p["kind"])
         n += svc_util.compare_picture(p, coef[0], rec[0], st[0], "GPU")
     assert n >= 700
 
@@ -236,8 +243,7 @@ def test_gpu_vs_oracle_random(w, h, qp, n, bl):
     """bl = 1: the second plane set is used as the prediction itself (I_BL entry point)"""
     rng = np.random.default_rng(w + 7 * qp + n)
     cases = [_random_case(rng, w, h, far_every=3 if i == 1 or n == 1 else 0) for i in range(n)]
-    gpu_pictures.size = (w, h)
-    coef, rec, st = gpu_pictures(cases, qp, bl)
+    coef, rec, st = gpu_pictures(cases, (w, h), qp, bl)
     o = _oracle()
     for i, (src, ref, m, s0) in enumerate(cases):
         if w >= 1920:   # full size: the oracle on a band of macroblock rows is enough for a picture whose rows are independent; the rest against the CPU run of the device source

@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Differential fuzz of the SVC enhancement-layer macroblock code (oracle restatement AND the kernel's per-lane source compiled as C++) against the
+unmodified reference encoder run live with 2 or 3 spatial layers: random base sizes, QPs, generators, seeds.  Compares, macroblock by macroblock,
+levels, coded-block patterns, carried state and reconstructed samples of every enhancement-layer picture (I_BL and base-mode inter macroblocks); the
+macroblocks the reference codes against uninitialised memory are counted and skipped.  For G1 content (deterministic reference
+bitstream) it also runs the glue hook end to end (oracle/_ref/hl_svc_glue_check) and compares the bitstream MD5.
+Build container only (needs oracle/_ref).  usage: fuzz_svc.py [n_cases] [first_seed]"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import reftrace as rt  # noqa: E402
+import svc_util  # noqa: E402
+import test_svc_inter as T  # noqa: E402
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+GLUE = os.path.join(ROOT, "oracle", "_ref", "hl_svc_glue_check")
+o = T._oracle()
+bad = n_mb = n_skip = n_md5 = 0
+for case in range(first, first + n_cases):
+    rng = np.random.default_rng(case)
+    layers = int(rng.choice([2, 2, 3]))
+    w, h = int(rng.integers(1, 9 if layers == 2 else 6)) * 16, int(rng.integers(1, 8 if layers == 2 else 5)) * 16
+    frames = int(rng.integers(2, 5))
+    qp = int(rng.integers(20, 52))
+    gen = str(rng.choice(["g1", "g2"]))
+    seed = int(rng.integers(1, 10000))
+    args = ["--size", str(w), str(h), "--layers", str(layers), "--frames", str(frames), "--gen", gen, "--seed", str(seed), "--qp", str(qp)]
+    tr = "/tmp/fuzz_svc_%d.trace" % case
+    try:
+        out = subprocess.run([rt.DRIVER] + args + ["--trace", tr], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+    except subprocess.CalledProcessError:
+        print("case %d: %s -> reference encoder failed, skipped" % (case, " ".join(args)), flush=True)
+        continue
+    ref_json = json.loads(out.stdout.strip().splitlines()[-1])
+    ok, mbs, skipped = True, 0, 0
+    try:
+        for p in svc_util.bl_pictures_from_trace(tr) + svc_util.pictures_from_trace(tr):
+            skipped += int((p["valid"] == 0).sum())
+            c1, r1, s1 = T.oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], p["qpc"], p["motion"], p["state_in"], p["kind"])
+            mbs += svc_util.compare_picture(p, c1, r1, s1, "oracle")
+            c2, r2, s2 = T.emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], p["motion"], p["state_in"], p["kind"])
+            svc_util.compare_picture(p, c2, r2, s2, "device source on the CPU")
+    except AssertionError as e:
+        ok = False
+        print(str(e)[:400])
+    md5 = ""
+    if ok and gen == "g1" and skipped == 0 and os.path.exists(GLUE):   # with skipped macroblocks the reference's own bitstream is not reproducible
+        g = subprocess.run([GLUE] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        gj = json.loads(g.stdout.strip().splitlines()[-1]) if g.returncode == 0 else {"md5": "failed"}
+        if gj["md5"] != ref_json["md5"]:
+            again = json.loads(subprocess.run([rt.DRIVER] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout.strip().splitlines()[-1])
+            if again["md5"] != ref_json["md5"]:
+                md5 = " (reference bitstream differs between two runs of the reference: not compared)"
+            else:
+                md5, ok = " bitstream MD5 DIFFERENT", False
+                n_md5 += 1
+        else:
+            md5 = " bitstream MD5 equal"
+            n_md5 += 1
+    print("case %d: %s -> %s (%d macroblocks, %d skipped)%s" % (case, " ".join(args), "OK" if ok else "MISMATCH", mbs, skipped, md5), flush=True)
+    bad += not ok
+    n_mb += mbs
+    n_skip += skipped
+    os.remove(tr)
+print("%d cases, %d mismatches, %d macroblocks compared, %d skipped (no reference behaviour), %d bitstream MD5 comparisons" % (n_cases, bad, n_mb, n_skip, n_md5))
+sys.exit(1 if bad else 0)
