@@ -149,6 +149,19 @@ class Stream:
         check(self.lib.hlb200_tq_recon(self.ctx, qp, chroma_qp_index_offset, ptr(py), ptr(pu), ptr(pv), ptr(coeffs), ptr(ry), ptr(ru), ptr(rv)), "tq_recon")
         return coeffs, rec
 
+    def svc_layer_picture(self, qp, motion=None, pred_yuv=None, ref_slot=0, cur_slot=1, chroma_qp_index_offset=0):
+        """one picture of an SVC enhancement layer (this context = the layer): base-mode inter macroblocks predicted from ref_slot with `motion`, or -- pred_yuv
+        given -- I_BL macroblocks predicted by the host-resampled planes; returns (coefficients, reconstruction = frame store cur_slot)"""
+        coeffs = np.zeros(self.nmb, MB_COEFFS)
+        if pred_yuv is not None:
+            py, pu, pv = self._planes(pred_yuv)
+            rc = self.lib.hlb200_svc_layer_picture(self.ctx, -1, cur_slot, qp, chroma_qp_index_offset, None, ptr(py), ptr(pu), ptr(pv), ptr(coeffs))
+        else:
+            m = np.ascontiguousarray(motion)
+            rc = self.lib.hlb200_svc_layer_picture(self.ctx, ref_slot, cur_slot, qp, chroma_qp_index_offset, ptr(m), None, None, None, ptr(coeffs))
+        check(rc, "svc_layer_picture")
+        return coeffs, self.download_slot(cur_slot)
+
     def sad4x4(self, pred_y, satd=False):
         out = np.zeros((self.h // 4, self.w // 4), np.int32)
         p = np.ascontiguousarray(pred_y, np.uint8)

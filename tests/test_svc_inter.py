@@ -238,6 +238,33 @@ def test_gpu_vs_golden():
 
 
 @pytest.mark.gpu
+def test_gpu_layer_picture_host_api_vs_golden():
+    """hlb200_svc_layer_picture (host buffers, one context per layer, the per-macroblock state carried inside the context from picture to picture): the
+    pictures of each fixture encode in coding order, every layer in its own context -- the call sequence of host/hlb200_glue.c"""
+    from hartallo_b200 import lib as hl
+    ctxs, n = {}, 0
+    for p in svc_util.load_golden():
+        key = (p["name"].split(".")[0], p["dqid"])
+        if key not in ctxs:
+            ctxs[key] = hl.Stream(p["w"], p["h"], 1)
+        st = ctxs[key]
+        st.upload_frame(p["src"])
+        if p["kind"]:
+            coef, rec = st.svc_layer_picture(p["qp"], pred_yuv=p["ref"])
+        else:
+            st.upload_slot(0, p["ref"])
+            coef, rec = st.svc_layer_picture(p["qp"], motion=_fill_invalid(p).view(hl.MB_MOTION))
+        # the context's carried state equals the reference's only while every macroblock so far had reference behaviour; the fixture's state_in is what the
+        # reference really held, so compare just the pictures for which both agree (all of them except after a picture with host-coded macroblocks)
+        if getattr(st, "svc_state_ok", True):
+            n += svc_util.compare_picture(p, coef, rec, None, "GPU host API")
+        st.svc_state_ok = getattr(st, "svc_state_ok", True) and bool(p["valid"].all())
+    for st in ctxs.values():
+        st.close()
+    assert n >= 600
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("w,h,qp,n,bl", [(64, 48, 28, 1, 0), (176, 144, 31, 5, 0), (48, 64, 12, 3, 0), (1920, 1088, 31, 1, 0), (176, 144, 26, 3, 1), (1920, 1088, 31, 2, 1)])
 def test_gpu_vs_oracle_random(w, h, qp, n, bl):
     """bl = 1: the second plane set is used as the prediction itself (I_BL entry point)"""
