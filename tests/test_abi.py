@@ -85,6 +85,8 @@ def test_argument_errors_are_reported_not_executed():
     assert l.hlb200_dev_tq_recon_batch(1, 1, 1, 1, 1, 1, 64, 48, 1, 0, 52, 0, 1, 1, 1, 1, None) == inv   # QP 52
     assert l.hlb200_dev_svc_inter_recon_batch(1, 1, 1, 1, 1, 1, 64, 48, 1, 0, 31, 0, 1, None, 1, 1, 1, 1, None) == inv   # no state array
     assert l.hlb200_dev_svc_inter_recon_batch(1, 1, 1, 1, 1, 1, 64, 40, 1, 0, 31, 0, 1, 1, 1, 1, 1, 1, None) == inv      # height not a multiple of 16
+    assert l.hlb200_svc_layer_picture(None, 0, 1, 31, 0, 1, None, None, None, 1) == inv                                  # no layer context
+    assert l.hlb200_dev_svc_bl_recon_batch(1, 1, 1, 1, 1, 1, 64, 48, 0, 0, 31, 0, 1, 1, 1, 1, 1, None) == inv            # no pictures
     assert l.hlb200_slice_encode_batch_async(None, None, 1) == inv
     assert l.hlb200_frame_set_device(None, 1, 1, 1) == inv
     prev = l.hlb200_slice_set_variant(1)
