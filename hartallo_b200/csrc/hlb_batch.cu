@@ -262,16 +262,18 @@ __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, i
     }
     const size_t idx = (size_t)blockIdx.y * nmb + warp;
     const int mbx = warp % mbw, mby = warp / mbw;
-    const hlb200_mb_motion_t* m = BL ? nullptr : motion + idx;
+    SvcPredSrc ps;
+    if (BL) { ps.m = nullptr; ps.mbx = mbx; ps.mby = mby; ps.inherited = false; }
+    else ps = svc_pred_src(motion + (size_t)blockIdx.y * nmb, warp, mbw);
     hlb200_mb_coeffs_t& out = coeffs[idx];
     hlb200_svc_mb_state_t& st = state[idx];
     SvcXchg& X = xs[threadIdx.x >> 5];
     SvcChromaLane L;
     const int plane = (lane - 16) >> 2, cblk = (lane - 16) & 3;
-    if (lane < 16) svc_luma_lane<BL>(P, mbx, mby, lane, m, qp, out, X);
-    else if (lane < 24) svc_chroma_lane_a<BL>(P, mbx, mby, plane, cblk, m, qpc, st, L, X);
+    if (lane < 16) svc_luma_lane<BL>(P, mbx, mby, lane, ps.m, ps.mbx, ps.mby, qp, out, X);
+    else if (lane < 24) svc_chroma_lane_a<BL>(P, mbx, mby, plane, cblk, ps.m, ps.mbx, ps.mby, qpc, st, L, X);
     __syncwarp();
-    if (lane >= 16 && lane < 24) svc_chroma_lane_b<BL>(P, mbx, mby, plane, cblk, qpc, st, L, X, out);
+    if (lane >= 16 && lane < 24) svc_chroma_lane_b(P, mbx, mby, plane, cblk, qpc, BL || ps.inherited, st, L, X, out);
     if (lane == 0) out.cbp_luma4x4 = (uint16_t)svc_luma_cbp(X);
 }
 

@@ -102,14 +102,32 @@ HLB_HD void svc_load_pred4x4(const uint8_t* plane, int off, int pitch, uint8_t p
         pv[r * 4] = (uint8_t)w; pv[r * 4 + 1] = (uint8_t)(w >> 8); pv[r * 4 + 2] = (uint8_t)(w >> 16); pv[r * 4 + 3] = (uint8_t)(w >> 24);
     }
 }
+// Where a macroblock's prediction comes from.  Normally itself.  A macroblock of a P picture whose base macroblock is intra reaches the reference's inter
+// function without any partition (predFlagL0 = 0, NumSubMbPart = 0): the prediction loops (rdo.c:1350-1424) do not run and predMbL/Cb/Cr -- scratch blocks
+// that the allocator hands out at the same position on every call (hl_memory.h:226-241) -- still hold the prediction of the last macroblock that had
+// partitions.  The macroblock is then coded against THAT prediction, and because the SVC initialisation process flags it intra, with the intra offset in
+// the 2x2 chroma DC quantisation (rdo.c:2660).  The host marks such a macroblock in hlb200_mb_motion_t::pad: pad[0] bit 0, pad[1..2] = address of the
+// macroblock whose prediction it inherits (traced: tag 10 of oracle/ref_driver.c; tests/test_svc_inter.py::test_stale_prediction_model).
+struct SvcPredSrc { int mbx, mby; const hlb200_mb_motion_t* m; bool inherited; };
+HLB_HD SvcPredSrc svc_pred_src(const hlb200_mb_motion_t* pic_motion, int mb, int mbw)
+{
+    SvcPredSrc s;
+    const hlb200_mb_motion_t* m = pic_motion + mb;
+    s.inherited = (m->pad[0] & 1) != 0;
+    const int from = s.inherited ? ((int)m->pad[1] | ((int)m->pad[2] << 8)) : mb;
+    s.m = pic_motion + from; s.mbx = from % mbw; s.mby = from / mbw;
+    return s;
+}
+
+// m / (pmbx, pmby): motion and position the prediction is formed with (the macroblock itself, or the one it inherits from); unused for BL
 template <bool BL>
-HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t* m, int qp, hlb200_mb_coeffs_t& out, SvcXchg& X)
+HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t* m, int pmbx, int pmby, int qp, hlb200_mb_coeffs_t& out, SvcXchg& X)
 {
     const int bx = blk_x(blk), by = blk_y(blk), W = P.W;
     const int off = (mby * 16 + by) * W + mbx * 16 + bx;
     uint8_t pv[16];
     if (BL) svc_load_pred4x4(P.ref_y, off, W, pv);
-    else svc_luma_predict(P, mbx, mby, blk, *m, pv);
+    else svc_luma_predict(P, pmbx, pmby, blk, *m, pv);
     int mm[16], lv[16];
     bool nz = false;
 #pragma unroll
@@ -169,14 +187,14 @@ HLB_HD void svc_chroma_predict(const SvcPlanes& P, int mbx, int mby, int plane, 
         }
 }
 template <bool BL>
-HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t* m, int qpc, hlb200_svc_mb_state_t& st,
-                              SvcChromaLane& L, SvcXchg& X)
+HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t* m, int pmbx, int pmby, int qpc,
+                              hlb200_svc_mb_state_t& st, SvcChromaLane& L, SvcXchg& X)
 {
     const int Wc = P.W >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
     const uint8_t* src = plane ? P.src_v : P.src_u;
     const int off = (mby * 8 + by) * Wc + mbx * 8 + bx;
     if (BL) svc_load_pred4x4(plane ? P.ref_v : P.ref_u, off, Wc, L.pv);
-    else svc_chroma_predict(P, mbx, mby, plane, blk, *m, L);
+    else svc_chroma_predict(P, pmbx, pmby, plane, blk, *m, L);
     int mm[16];
     bool nz = false;
 #pragma unroll
@@ -210,8 +228,8 @@ HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, i
 }
 
 // ---- chroma lane, phase B: elimination, 2x2 DC, reconstruction of the block (rdo.c:2640-2682, transf.c:161-296) ----
-template <bool BL>
-HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, int blk, int qpc, hlb200_svc_mb_state_t& st, const SvcChromaLane& L,
+// mb_intra: the macroblock counts as intra in rdo.c:2660 (I_BL, or a macroblock with an inherited prediction -- see SvcPredSrc)
+HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, int blk, int qpc, bool mb_intra, hlb200_svc_mb_state_t& st, const SvcChromaLane& L,
                               const SvcXchg& X, hlb200_mb_coeffs_t& out)
 {
     const int Wc = P.W >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
@@ -228,7 +246,7 @@ HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, i
         for (int k = 0; k < 4; ++k) dcl[k] = X.dc_coef[plane][k];
         hadamard2x2(dcl);
         // rdo.c:2660 uses the macroblock's own intra flag: an inferred macroblock with inter prediction is not intra (mb.h:46,57), an I_BL one is
-        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ BL);
+        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ mb_intra);
 #pragma unroll
         for (int k = 0; k < 4; ++k) dc_mask |= (unsigned)(dcl[k] != 0) << k;
         if (dc_mask) {   // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5

@@ -142,7 +142,8 @@ typedef struct glue_svc_layer_s {
     int w, h, nmb;
     hlb200_mb_motion_t* motion;
     hlb200_mb_coeffs_t* coeffs;
-    uint8_t* valid;          /* 0: a macroblock the reference itself codes against uninitialised memory (base macroblock intra inside a P picture): left to the host */
+    uint8_t* valid;          /* 0: a macroblock without partitions that precedes every macroblock with partitions of its picture: the reference codes it against
+                              * scratch memory left by an earlier picture -- left to the reference's own function */
     uint8_t *pred, *rec;     /* tight Y|U|V */
 } glue_svc_layer_t;
 static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
@@ -210,7 +211,7 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     const size_t ysz = (size_t)W * H, csz = (size_t)Wc * Hc;
     glue_svc_layer_t* L;
     HL_ERROR_T err;
-    int rc, qp = -1, x, y;
+    int rc, qp = -1, x, y, last_with_parts = -1;
     uint32_t addr;
     static HL_ALIGNED(16) int32_t pl[16][16], pcb[16][16], pcr[16][16];
 
@@ -262,6 +263,13 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
             if (ok) {
                 m->part_mode = (uint8_t)mode;
                 for (p = 0; p < n; ++p) { m->mv[p][0][0] = (int16_t)p_mb->mvL0[p][0].x; m->mv[p][0][1] = (int16_t)p_mb->mvL0[p][0].y; }
+                last_with_parts = (int)addr;
+            }
+            else if (n == 1 && p_mb->NumSubMbPart[0] == 0 && last_with_parts >= 0 && last_with_parts < 65536) {
+                /* base macroblock intra: no partition, the reference's prediction loops do not run and it codes the macroblock against what its scratch blocks
+                 * still hold = the prediction of the last macroblock that had partitions; the device does the same (hlb_svc.cuh: SvcPredSrc) */
+                m->pad[0] = 1; m->pad[1] = (uint8_t)(last_with_parts & 255); m->pad[2] = (uint8_t)(last_with_parts >> 8);
+                L->valid[addr] = 1;
             }
         }
     }
@@ -327,7 +335,7 @@ extern HL_ERROR_T __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_
 HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
 {
     if (!g_svc_active) return HL_ERROR_INVALID_STATE;
-    /* base macroblock intra inside a P picture: the reference codes it against uninitialised memory; nothing to reproduce, the host keeps it */
+    /* no partition and nothing to inherit from inside this picture (see glue_svc_slice): the host keeps it */
     if (p_mb->u_addr < (uint32_t)g_svc_active->nmb && !g_svc_active->valid[p_mb->u_addr]) return __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(p_mb, p_codec);
     return glue_svc_apply(p_mb, p_codec, 0);
 }

@@ -228,10 +228,10 @@ HLB200_API int hlb200_dev_tq_recon_batch(const uint8_t* d_src_y, const uint8_t* 
  * pictures (prediction from the layer's own reference picture + residual coding + reconstruction; the prediction never goes through HBM).
  * d_motion = the partitions / motion vectors the inter-layer derivation (host, utils.c:966-2439) inferred from the base layer; d_state (in/out,
  * n_pics x macroblocks, zero for a new layer) = hlb200_svc_mb_state_t; layout of planes and arrays as for the *_batch entry points above.
- * The reference calls this function for every macroblock of an enhancement P picture, also for those whose base macroblock is intra: these
- * arrive with predFlagL0 = 0 and no partition, the reference then codes them against whatever its scratch allocator holds (never initialised for the
- * macroblock; on some content its bitstream differs from run to run); no behaviour exists to reproduce for them -- give them any valid motion here and
- * let the host code them (host/hlb200_glue.c does). */
+ * The reference calls this function for every macroblock of an enhancement P picture, also for those whose base macroblock is intra: these arrive with
+ * predFlagL0 = 0 and no partition, and the reference codes them against the prediction its scratch blocks still hold from the last macroblock that had
+ * partitions (with the intra offset in the chroma DC quantisation).  Mark such a macroblock with pad[0] = 1, pad[1] | pad[2] << 8 = address of the macroblock
+ * (same picture, itself not marked) whose prediction it inherits; its own part_mode / mv are not read. */
 HLB200_API int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, const uint8_t* d_src_v, const uint8_t* d_ref_y, const uint8_t* d_ref_u,
                                                 const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
                                                 const hlb200_mb_motion_t* d_motion, hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs,

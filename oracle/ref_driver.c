@@ -27,6 +27,7 @@
 #include "hartallo/hl_debug.h"
 #include "hartallo/hl_math.h"
 #include "hartallo/hl_md5.h"
+#include "hartallo/hl_memory.h"
 #include "hartallo/h264/hl_codec_264.h"
 #include "hartallo/h264/hl_codec_264_mb.h"
 #include "hartallo/h264/hl_codec_264_layer.h"
@@ -315,6 +316,21 @@ HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_
         for (i = 0; i < 2; ++i) for (j = 0; j < 4; ++j) r[k++] = dc_in[i][j];
         r[1] = k;
         put32(r, (size_t)k);
+        /* tag 10: a macroblock without any partition (base macroblock intra inside a P picture) is coded against whatever the scratch blocks of the
+         * function's predMbL / predMbCb / predMbCr hold (4th, 5th, 6th block mapped: rdo.c:1309-1311; the allocator hands out blocks 31, 30, ... in order,
+         * hl_memory.h:226-241) -- the function does not write them for such a macroblock, so they still hold what it used:
+         * [10, n, frame, DQId, addr, Y 16x16, Cb 8x8, Cr 8x8] */
+        if (p_mb->NumSubMbPart[0] == 0) {
+            const int32_t* mem = pc_layer->encoder.p_list_esd[p_mb->u_slice_idx]->pc_mem_blocks->p_memory;
+            const int32_t *bl = mem + (28 << 8), *bcb = mem + (27 << 8), *bcr = mem + (26 << 8);
+            k = 0;
+            r[k++] = 10; r[k++] = 0; r[k++] = g_frame_idx; r[k++] = dq; r[k++] = (int32_t)p_mb->u_addr;
+            for (y = 0; y < 16; ++y) for (x = 0; x < 16; ++x) r[k++] = bl[y * 16 + x];
+            for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = bcb[y * 16 + x];
+            for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) r[k++] = bcr[y * 16 + x];
+            r[1] = k;
+            put32(r, (size_t)k);
+        }
     }
     return err;
 }
@@ -392,14 +408,18 @@ static void gen_g1(uint8_t* yuv, int w, int h, int n)
 
 /* G2 "stress": a fixed random base picture (half the pixels < 34, 8x8 patches of 0 / 255), translated by (3n, -2n)
  * with wrap-around, plus chroma from the same recipe.  Exercises both clip branches, the F7 wrap and F13. */
-static uint8_t* g2_base = NULL; static int g2_bw, g2_bh;
+/* one base picture per picture size (SVC: every spatial layer has its own, same recipe and seed at the layer's size) */
+static struct { uint8_t* base; int w, h; } g2_bases[4];
 static void gen_g2(uint8_t* yuv, int w, int h, int n, uint32_t seed)
 {
-    int x, y, c;
+    int x, y, c, k;
+    uint8_t* g2_base = NULL;
+    for (k = 0; k < 4 && g2_bases[k].base; ++k) if (g2_bases[k].w == w && g2_bases[k].h == h) g2_base = g2_bases[k].base;
     if (!g2_base) {
         uint32_t s = seed * 2654435761u + 97u;
         size_t i, tot = (size_t)w * h * 3 / 2;
-        g2_bw = w; g2_bh = h; g2_base = (uint8_t*)malloc(tot);
+        if (k >= 4) { fprintf(stderr, "gen_g2: too many picture sizes\n"); exit(2); }
+        g2_base = (uint8_t*)malloc(tot); g2_bases[k].base = g2_base; g2_bases[k].w = w; g2_bases[k].h = h;
         for (i = 0; i < tot; ++i) {
             uint32_t a, b;
             s = s * 1664525u + 1013904223u; a = s >> 8;

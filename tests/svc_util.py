@@ -19,8 +19,8 @@ SVC_STATE = np.dtype([("chroma_ac_level", "<i2", (2, 4, 16)), ("chroma_dc_level"
 # (name, driver arguments): small multi-layer encodes whose enhancement P pictures make the fixture
 CONFIGS = [
     ("g2_2layer", ["--size", "64", "48", "--layers", "2", "--frames", "4", "--gen", "g2", "--seed", "3"]),
-    ("g2_3layer", ["--size", "48", "32", "--layers", "3", "--frames", "3", "--gen", "g2", "--seed", "5"]),
-    ("g1_2layer_q24", ["--size", "64", "64", "--layers", "2", "--frames", "3", "--gen", "g1", "--qp", "24"]),
+    ("g2_3layer", ["--size", "32", "32", "--layers", "3", "--frames", "3", "--gen", "g2", "--seed", "9", "--qp", "36"]),
+    ("g1_2layer_q24", ["--size", "48", "48", "--layers", "2", "--frames", "3", "--gen", "g1", "--qp", "24"]),
 ]
 
 
@@ -61,7 +61,7 @@ def pictures_from_trace(path):
         p["state_in"][a]["chroma_dc_level"] = r[k:k + 8].reshape(2, 4)
         mode = {(1, 16, 16): 0, (2, 16, 8): 1, (2, 8, 16): 2, (4, 8, 8): 3}.get((nparts, pw, ph), -1)
         # macroblocks the reference predicts from real motion; the others (base macroblock intra: no partition, predFlagL0 = 0) are coded by the
-        # reference against uninitialised memory and have no behaviour to compare with
+        # reference against the prediction of an earlier macroblock: mark_inherited() below
         ok = mode >= 0 and all(int(nsub[i]) >= 1 and int(pflag[i]) == 1 and int(ridx[i]) == 0 and int(pwh[i, 0]) == pw and int(pwh[i, 1]) == ph for i in range(nparts))
         ok = ok and e_type in (301, 302, 303, 304)
         p["valid"][a] = 1 if ok else 0
@@ -72,12 +72,31 @@ def pictures_from_trace(path):
             for i in range(nparts):
                 m["mv"][i, 0] = mv[i, 0]
         p["seen"] += 1
+    stale = {(int(r[2]), int(r[3]), int(r[4])): r[5:5 + 384].copy() for r in t.get(10, [])}
     out = []
     for key in order:
         p = pics[key]
         assert p["seen"] == len(p["valid"]), "trace holds %d of %d macroblocks of picture %r" % (p["seen"], len(p["valid"]), key)
+        mark_inherited(p["motion"], p["valid"])
+        p["stale"] = {a: stale[(key[0], key[1], a)] for a in range(len(p["valid"])) if (key[0], key[1], a) in stale}   # what the scratch blocks really held
         out.append(p)
     return out
+
+
+def mark_inherited(motion, valid):
+    """A macroblock without partitions (base macroblock intra inside a P picture) is coded by the reference against the prediction its scratch blocks still
+    hold: that of the last macroblock WITH partitions.  Inside one picture that is expressible: pad[0] bit 0 + pad[1..2] = address of
+    that macroblock (hlb_svc.cuh: SvcPredSrc); such a macroblock then has reference behaviour (valid = 1).  One that precedes every macroblock with partitions
+    of its picture inherits from an earlier picture (or from the I_BL function's temporaries) and stays without (valid = 0)."""
+    last = -1
+    for a in range(len(valid)):
+        if valid[a]:
+            if not (motion[a]["pad"][0] & 1):
+                last = a
+        elif last >= 0:
+            motion[a]["part_mode"] = 0
+            motion[a]["pad"] = (1, last & 255, last >> 8)
+            valid[a] = 1
 
 
 def planes_of_mb(mbs, w, h):

@@ -34,10 +34,20 @@ def oracle_picture(o, src, ref, w, h, qp, qpc, motion, state_in, bl=0):
     """whole picture through the oracle: returns (coeffs, rec_yuv, state_out); bl: `ref` holds the prediction planes (I_BL, rdo.c:301: same residual coding)"""
     ysz, csz = w * h, w * h // 4
     nmb = (w // 16) * (h // 16)
+    inherit = {}
     if bl:
         py, pu, pv = (np.ascontiguousarray(ref[:ysz]), np.ascontiguousarray(ref[ysz:ysz + csz]), np.ascontiguousarray(ref[ysz + csz:]))
     else:
         py, pu, pv = oracle_predict_frame(o, ref, w, h, motion)
+        # macroblocks that inherit the prediction of an earlier macroblock of the picture (svc_util.mark_inherited): copy it over, code them as I_BL
+        inherit = {a: int(m["pad"][1]) | (int(m["pad"][2]) << 8) for a, m in enumerate(motion) if m["pad"][0] & 1}
+        if inherit:
+            mbs = svc_util.mb_of_planes(py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, h)
+            for a, b in inherit.items():
+                assert not (motion[b]["pad"][0] & 1)
+                mbs[a] = mbs[b]
+            pl = svc_util.planes_of_mb(mbs, w, h)
+            py, pu, pv = np.ascontiguousarray(pl[:ysz]), np.ascontiguousarray(pl[ysz:ysz + csz]), np.ascontiguousarray(pl[ysz + csz:])
     sy, su, sv = (np.ascontiguousarray(src[:ysz]), np.ascontiguousarray(src[ysz:ysz + csz]), np.ascontiguousarray(src[ysz + csz:]))
     ry, ru, rv = np.zeros(ysz, np.uint8), np.zeros(csz, np.uint8), np.zeros(csz, np.uint8)
     coeffs, state = np.zeros(nmb, MB_COEFFS), state_in.copy()
@@ -45,7 +55,7 @@ def oracle_picture(o, src, ref, w, h, qp, qpc, motion, state_in, bl=0):
     for mb in range(nmb):
         ll, dc = np.zeros(256, np.int16), np.ascontiguousarray(state[mb]["chroma_dc_level"].reshape(-1))
         ac = np.ascontiguousarray(state[mb]["chroma_ac_level"].reshape(-1))
-        (o.hlo_recon_svc_bl_mb if bl else o.hlo_recon_svc_inter_mb)(sy, su, sv, py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, mb % (w // 16), mb // (w // 16), qp, qpc, ll, dc, ac, c4, cdc, cac, ry, ru, rv)
+        (o.hlo_recon_svc_bl_mb if (bl or mb in inherit) else o.hlo_recon_svc_inter_mb)(sy, su, sv, py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, mb % (w // 16), mb // (w // 16), qp, qpc, ll, dc, ac, c4, cdc, cac, ry, ru, rv)
         c = coeffs[mb]
         c["luma_level"], c["chroma_dc_level"], c["chroma_ac_level"] = ll.reshape(16, 16), dc.reshape(2, 4), ac.reshape(2, 4, 16)
         c["cbp_luma4x4"], c["cbp_chroma_dc4x4"], c["cbp_chroma_ac4x4"] = int(c4[0]), cdc, cac
@@ -90,10 +100,10 @@ def test_golden_fixture_shape():
     assert len(pics) == 13 and sum(p["kind"] for p in pics) == 4     # 9 P pictures (base-mode inter) + 4 I pictures (I_BL)
     modes = set()
     for p in pics:
-        assert p["qp"] in (24, 31) and len(p["motion"]) == (p["w"] // 16) * (p["h"] // 16)
+        assert p["qp"] in (24, 31, 36) and len(p["motion"]) == (p["w"] // 16) * (p["h"] // 16)
         modes |= set(int(m) for m, v in zip(p["motion"]["part_mode"], p["valid"]) if v and not p["kind"])
     assert modes == {0, 1, 2, 3}                                    # 16x16, 16x8, 8x16, 8x8 all occur
-    assert any((p["valid"] == 0).any() for p in pics)               # and macroblocks whose base macroblock is intra (excluded from comparison)
+    assert sum(int((p["motion"]["pad"][:, 0] & 1).sum()) for p in pics) >= 8   # and macroblocks without partitions that inherit an earlier prediction
     assert any(p["dqid"] == 32 for p in pics)                       # third spatial layer
 
 
@@ -103,7 +113,7 @@ def test_oracle_vs_golden():
     for p in svc_util.load_golden():
         coeffs, rec, state = oracle_picture(o, p["src"], p["ref"], p["w"], p["h"], p["qp"], chroma_qp(p["qp"]), _fill_invalid(p), p["state_in"], p["kind"])
         n += svc_util.compare_picture(p, coeffs, rec, state, "oracle")
-    assert n >= 700
+    assert n >= 540
 
 
 def test_device_source_on_cpu_vs_golden():
@@ -111,7 +121,7 @@ def test_device_source_on_cpu_vs_golden():
     for p in svc_util.load_golden():
         coeffs, rec, state = emu_picture(p["src"], p["ref"], p["w"], p["h"], p["qp"], _fill_invalid(p), p["state_in"], p["kind"])
         n += svc_util.compare_picture(p, coeffs, rec, state, "hlb_svc.cuh on the CPU")
-    assert n >= 700
+    assert n >= 540
 
 
 @pytest.mark.skipif(not reftrace.have_driver(), reason="oracle/_ref/hl_ref_driver only exists where the reference tree is available")
@@ -138,6 +148,30 @@ def test_svc_fuzz_vs_live_reference():
     glue hook on G1 content)"""
     out = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "emu", "fuzz_svc.py"), "6", "500"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert out.returncode == 0 and ", 0 mismatches" in out.stdout, out.stdout[-800:]
+
+
+@pytest.mark.skipif(not reftrace.have_driver(), reason="oracle/_ref/hl_ref_driver only exists where the reference tree is available")
+def test_stale_prediction_model(tmp_path):
+    """what the reference's scratch blocks really hold when it codes a macroblock without partitions (trace tag 10) == the prediction of the last macroblock
+    with partitions, as svc_util.mark_inherited / SvcPredSrc model it"""
+    tr = str(tmp_path / "svc.trace")
+    svc_util.run_driver_svc(["--size", "176", "144", "--layers", "2", "--frames", "4", "--gen", "g2"], tr)
+    o = _oracle()
+    n = 0
+    for p in svc_util.pictures_from_trace(tr):
+        if not p["stale"]:
+            continue
+        w, h = p["w"], p["h"]
+        plain = p["motion"].copy()
+        plain["pad"] = 0
+        py, pu, pv = oracle_predict_frame(o, p["ref"], w, h, plain)
+        mbs = svc_util.mb_of_planes(py.reshape(-1), pu.reshape(-1), pv.reshape(-1), w, h)
+        for a, held in p["stale"].items():
+            m = p["motion"][a]
+            if m["pad"][0] & 1:
+                assert np.array_equal(held, mbs[int(m["pad"][1]) | (int(m["pad"][2]) << 8)]), a
+                n += 1
+    assert n >= 8
 
 
 def _random_case(rng, w, h, far_every=0):
@@ -175,6 +209,10 @@ def _random_case(rng, w, h, far_every=0):
             sc[y // 2:y // 2 + 8, x // 2:x // 2 + 8] = rc[y // 2:y // 2 + 8, x // 2:x // 2 + 8]
             if rng.random() < 0.5:
                 sc[y // 2:y // 2 + 4, x // 2:x // 2 + 4] += 9          # one block with a DC-only difference: its three neighbours read their stale AC levels
+    for a in rng.integers(1, nmb, max(1, nmb // 8)):           # macroblocks that inherit the prediction of an earlier one (never of another inheriting one)
+        b = int(rng.integers(0, a))
+        if not (m["pad"][b][0] & 1):
+            m["pad"][a] = (1, b & 255, b >> 8)
     st = np.zeros(nmb, SVC_STATE)
     st["chroma_ac_level"][:, :, :, :15] = rng.integers(-2, 3, (nmb, 2, 4, 15)) * (rng.random((nmb, 2, 4, 15)) < 0.2)
     st["chroma_dc_level"] = rng.integers(-3, 4, (nmb, 2, 4))
@@ -234,7 +272,7 @@ def test_gpu_vs_golden():
     for p in svc_util.load_golden():
         coef, rec, st = gpu_pictures([(p["src"], p["ref"], _fill_invalid(p), p["state_in"])], (p["w"], p["h"]), p["qp"], p["kind"])
         n += svc_util.compare_picture(p, coef[0], rec[0], st[0], "GPU")
-    assert n >= 700
+    assert n >= 540
 
 
 @pytest.mark.gpu
@@ -261,7 +299,7 @@ def test_gpu_layer_picture_host_api_vs_golden():
         st.svc_state_ok = getattr(st, "svc_state_ok", True) and bool(p["valid"].all())
     for st in ctxs.values():
         st.close()
-    assert n >= 600
+    assert n >= 500
 
 
 @pytest.mark.gpu

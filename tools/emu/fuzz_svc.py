@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Differential fuzz of the SVC enhancement-layer macroblock code (oracle restatement AND the kernel's per-lane source compiled as C++) against the
 unmodified reference encoder run live with 2 or 3 spatial layers: random base sizes, QPs, generators, seeds.  Compares, macroblock by macroblock,
-levels, coded-block patterns, carried state and reconstructed samples of every enhancement-layer picture (I_BL and base-mode inter macroblocks); the
-macroblocks the reference codes against uninitialised memory are counted and skipped.  For G1 content (deterministic reference
-bitstream) it also runs the glue hook end to end (oracle/_ref/hl_svc_glue_check) and compares the bitstream MD5.
+levels, coded-block patterns, carried state and reconstructed samples of every enhancement-layer picture (I_BL macroblocks, base-mode inter macroblocks,
+macroblocks without partitions that inherit the prediction of an earlier macroblock of the picture); the few macroblocks without partitions at the very
+start of a picture (they inherit scratch memory of an earlier picture) are counted and skipped.  When a stream has none of those it
+also runs the glue hook end to end (oracle/_ref/hl_svc_glue_check) and compares the bitstream MD5.
 Build container only (needs oracle/_ref).  usage: fuzz_svc.py [n_cases] [first_seed]"""
 import json
 import os
@@ -52,7 +53,7 @@ for case in range(first, first + n_cases):
         ok = False
         print(str(e)[:400])
     md5 = ""
-    if ok and gen == "g1" and skipped == 0 and os.path.exists(GLUE):   # with skipped macroblocks the reference's own bitstream is not reproducible
+    if ok and skipped == 0 and os.path.exists(GLUE):   # the glue leaves skipped macroblocks to the host function, whose scratch memory then differs from the reference's
         g = subprocess.run([GLUE] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         gj = json.loads(g.stdout.strip().splitlines()[-1]) if g.returncode == 0 else {"md5": "failed"}
         if gj["md5"] != ref_json["md5"]:
@@ -70,5 +71,5 @@ for case in range(first, first + n_cases):
     n_mb += mbs
     n_skip += skipped
     os.remove(tr)
-print("%d cases, %d mismatches, %d macroblocks compared, %d skipped (no reference behaviour), %d bitstream MD5 comparisons" % (n_cases, bad, n_mb, n_skip, n_md5))
+print("%d cases, %d mismatches, %d macroblocks compared, %d skipped (inherit scratch memory of an earlier picture), %d bitstream MD5 comparisons" % (n_cases, bad, n_mb, n_skip, n_md5))
 sys.exit(1 if bad else 0)
