@@ -58,6 +58,16 @@ struct SvcChromaLane {
 HLB_HD uint32_t svc_ld4(const uint8_t* p) { return HLB_LDG(reinterpret_cast<const uint32_t*>(p)); }
 HLB_HD void svc_st4(uint8_t* p, int a, int b, int c, int d) { *reinterpret_cast<uint32_t*>(p) = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
 
+// bytes sh8/8 .. sh8/8+3 of the eight bytes {lo, hi} (little endian); sh8 in {0, 8, 16, 24}
+HLB_HD uint32_t svc_funnel(uint32_t lo, uint32_t hi, int sh8)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh8);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> sh8);
+#endif
+}
+
 struct SvcPlanes {
     const uint8_t *src_y, *src_u, *src_v;
     const uint8_t *ref_y, *ref_u, *ref_v;   // inter (base mode): reference picture of the layer, or
@@ -76,22 +86,32 @@ HLB_HD void svc_luma_predict(const SvcPlanes& P, int mbx, int mby, int blk, cons
     // clamp of the reference's index table (interpol.c:108-131)
     const int X0 = clip3(-17, W + 17, mbx * 16 + g.ox + (mvx >> 2)) + (bx - g.ox);
     const int Y0 = clip3(-17, H + 17, mby * 16 + g.oy + (mvy >> 2)) + (by - g.oy);
-    uint8_t win[81];
-    if (X0 >= 2 && Y0 >= 2 && X0 + 7 <= W && Y0 + 7 <= H) {
-        const uint8_t* p = P.ref_y + (Y0 - 2) * W + (X0 - 2);
+    // 9 rows x 12 bytes, kept as words.  Inside the picture a row is fetched as four ALIGNED 32-bit words and shifted into place (the r01d profile of
+    // k_interp_luma showed the byte-wise window fetch L1-bound: 81 byte loads per block); the words of a row never leave that row of the plane.
+    uint32_t win[27];
+    const int xa = (X0 - 2) & ~3, sh8 = ((X0 - 2) & 3) * 8;
+    if (X0 >= 2 && Y0 >= 2 && xa + 16 <= W && Y0 + 7 <= H) {
+        const uint8_t* p = P.ref_y + (Y0 - 2) * W + xa;
 #pragma unroll
-        for (int r = 0; r < 9; ++r)
-#pragma unroll
-            for (int c = 0; c < 9; ++c) win[r * 9 + c] = HLB_LDG(p + r * W + c);
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p + r * W);
+            const uint32_t w0 = HLB_LDG(q), w1 = HLB_LDG(q + 1), w2 = HLB_LDG(q + 2), w3 = HLB_LDG(q + 3);
+            win[r * 3] = svc_funnel(w0, w1, sh8); win[r * 3 + 1] = svc_funnel(w1, w2, sh8); win[r * 3 + 2] = svc_funnel(w2, w3, sh8);
+        }
     } else {
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
-            const int y = clip3(0, H - 1, Y0 - 2 + r);
+            const uint8_t* row = P.ref_y + clip3(0, H - 1, Y0 - 2 + r) * W;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) win[r * 9 + c] = HLB_LDG(P.ref_y + y * W + clip3(0, W - 1, X0 - 2 + c));
+            for (int k = 0; k < 3; ++k) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w |= (uint32_t)HLB_LDG(row + clip3(0, W - 1, X0 - 2 + 4 * k + j)) << (8 * j);
+                win[r * 3 + k] = w;
+            }
         }
     }
-    interp_luma_4x4(win + 2 * 9 + 2, 9, mvx & 3, mvy & 3, pv);
+    interp_luma_4x4(reinterpret_cast<const uint8_t*>(win) + 2 * 12 + 2, 12, mvx & 3, mvy & 3, pv);
 }
 // I_BL: the prediction is a plane (rdo.c:363, mbPredL)
 HLB_HD void svc_load_pred4x4(const uint8_t* plane, int off, int pitch, uint8_t pv[16])
@@ -160,8 +180,11 @@ HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const h
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) svc_st4(P.rec_y + off + r * W, rec[r * 4], rec[r * 4 + 1], rec[r * 4 + 2], rec[r * 4 + 3]);
+    {   // all zero when the block is not coded (rdo.c:1453,1462); two levels per store
+        uint32_t* o = reinterpret_cast<uint32_t*>(&out.luma_level[blk][0]);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) out.luma_level[blk][i] = (int16_t)lv[i];   // all zero when the block is not coded (rdo.c:1453,1462)
+        for (int i = 0; i < 8; ++i) o[i] = (uint32_t)(uint16_t)lv[2 * i] | ((uint32_t)(uint16_t)lv[2 * i + 1] << 16);
+    }
     X.luma_coded[blk] = coded ? 1 : 0;
 }
 
