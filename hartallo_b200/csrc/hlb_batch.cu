@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ sr
 }
 
 // ---------------- SVC enhancement-layer inter macroblock (base mode): prediction + residual coding + reconstruction, one warp per MB -----------
-// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks; lanes 20..23: Cr blocks; the per-lane phases live in hlb_svc.cuh (the same source runs on the
+// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks; lanes 20..23: Cr blocks (24..31 idle); the per-lane phases live in hlb_svc.cuh (the same source runs on the
 // CPU in tools/emu/svc_emu.cpp).  The 2x2 chroma DC stage / elimination exchange goes through 56 bytes of shared memory per warp.
 // BL = true: I_BL macroblocks (enhancement-layer I pictures, hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301-461): P.ref_* are the prediction planes, no motion.
 template <bool BL>
@@ -268,12 +268,10 @@ __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, i
     hlb200_mb_coeffs_t& out = coeffs[idx];
     hlb200_svc_mb_state_t& st = state[idx];
     SvcXchg& X = xs[threadIdx.x >> 5];
-    SvcChromaLane L;
-    const int plane = (lane - 16) >> 2, cblk = (lane - 16) & 3;
-    if (lane < 16) svc_luma_lane<BL>(P, mbx, mby, lane, ps.m, ps.mbx, ps.mby, qp, out, X);
-    else if (lane < 24) svc_chroma_lane_a<BL>(P, mbx, mby, plane, cblk, ps.m, ps.mbx, ps.mby, qpc, st, L, X);
+    SvcLane L;
+    if (lane < 24) svc_lane_a<BL>(P, mbx, mby, lane, ps, qp, qpc, st, L, X);
     __syncwarp();
-    if (lane >= 16 && lane < 24) svc_chroma_lane_b(P, mbx, mby, plane, cblk, qpc, BL || ps.inherited, st, L, X, out);
+    if (lane < 24) svc_lane_b(P, mbx, mby, lane, qp, qpc, BL || ps.inherited, st, L, X, out);
     if (lane == 0) out.cbp_luma4x4 = (uint16_t)svc_luma_cbp(X);
 }
 

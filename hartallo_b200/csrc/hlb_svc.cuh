@@ -10,7 +10,9 @@
 // (1,152 B per macroblock = 384 reference + 384 source read, 384 reconstruction written, plus 768 B of levels).
 //
 // Two phases per lane with one exchange area between them (the 2x2 chroma DC stage and the single-coefficient elimination
-// look at all four blocks of a plane).  The phases are `HLB_HD`: under nvcc they are the body of k_svc_inter_recon
+// look at all four blocks of a plane).  Only the prediction differs between luma and chroma lanes; residual, transform,
+// quantisation, scan (phase A) and de-quantisation, inverse transform, add/clip, stores (phase B) are the same instructions
+// for all 24 lanes, so the warp executes them once (converged) instead of once per kind of lane.  The phases are `HLB_HD`: under nvcc they are the body of k_svc_inter_recon
 // (hlb_batch.cu), compiled as plain C++ they run lane by lane in tools/emu/svc_emu.cpp -- the CPU tier checks the same source
 // against the reference's per-macroblock trace.
 #pragma once
@@ -48,10 +50,12 @@ struct SvcXchg {
     uint8_t coded[2][4];     // CodedBlockPatternChromaAC4x4 bit before the elimination
     uint8_t luma_coded[16];  // CodedBlockPatternLuma4x4 bits
 };
-// what a chroma lane keeps between its two phases (registers on the device)
-struct SvcChromaLane {
-    uint8_t pv[16];   // prediction
-    int16_t ac[16];   // ChromaACLevel[plane][blk] as the macroblock object holds it after the forward pass (stale when the residual is zero)
+// what a lane keeps between its two phases (registers on the device)
+struct SvcLane {
+    uint8_t pv[16];   // prediction of the lane's 4x4 block
+    int16_t lv[16];   // luma lane: LumaLevel[blk]; chroma lane: ChromaACLevel[plane][blk] as the macroblock object holds it after the forward pass
+                      // (15 AC levels + the never-written [15]; stale when the residual is zero)
+    bool coded;       // luma lane: its CodedBlockPatternLuma4x4 bit
 };
 
 // four samples of a row as one word (plane bases are 4-byte aligned, widths multiples of 16)
@@ -139,57 +143,8 @@ HLB_HD SvcPredSrc svc_pred_src(const hlb200_mb_motion_t* pic_motion, int mb, int
     return s;
 }
 
-// m / (pmbx, pmby): motion and position the prediction is formed with (the macroblock itself, or the one it inherits from); unused for BL
-template <bool BL>
-HLB_HD void svc_luma_lane(const SvcPlanes& P, int mbx, int mby, int blk, const hlb200_mb_motion_t* m, int pmbx, int pmby, int qp, hlb200_mb_coeffs_t& out, SvcXchg& X)
-{
-    const int bx = blk_x(blk), by = blk_y(blk), W = P.W;
-    const int off = (mby * 16 + by) * W + mbx * 16 + bx;
-    uint8_t pv[16];
-    if (BL) svc_load_pred4x4(P.ref_y, off, W, pv);
-    else svc_luma_predict(P, pmbx, pmby, blk, *m, pv);
-    int mm[16], lv[16];
-    bool nz = false;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const uint32_t sw = svc_ld4(P.src_y + off + r * W);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { const int d = (int)((sw >> (8 * c)) & 255u) - (int)pv[r * 4 + c]; mm[r * 4 + c] = d; nz |= (d != 0); }
-    }
-    bool coded = false;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) lv[i] = 0;
-    if (nz) {
-        fwd_transform4x4(mm);
-        quant4x4_ac(mm, qp, /*intra f*/ true);   // __isIntraBlockTrue, rdo.c:1468
-        zigzag4x4(mm, lv);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) coded |= (lv[i] != 0);
-    }
-    int rec[16];
-    if (coded) {
-        int c[16];
-        inv_zigzag4x4(lv, c);
-        dequant4x4(c, qp, /*keep_dc*/ false);
-        inv_transform4x4(c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rec[i] = clip255((int)pv[i] + c[i]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rec[i] = pv[i];
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) svc_st4(P.rec_y + off + r * W, rec[r * 4], rec[r * 4 + 1], rec[r * 4 + 2], rec[r * 4 + 3]);
-    {   // all zero when the block is not coded (rdo.c:1453,1462); two levels per store
-        uint32_t* o = reinterpret_cast<uint32_t*>(&out.luma_level[blk][0]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (uint32_t)(uint16_t)lv[2 * i] | ((uint32_t)(uint16_t)lv[2 * i + 1] << 16);
-    }
-    X.luma_coded[blk] = coded ? 1 : 0;
-}
-
-// ---- chroma lane, phase A (plane 0 = Cb, 1 = Cr; blk raster 0..3): prediction, forward pass of the block (rdo.c:2561-2638) ----
-HLB_HD void svc_chroma_predict(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t& m, SvcChromaLane& L)
+// chroma prediction of one 4x4 block (plane 0 = Cb, 1 = Cr; blk raster 0..3)
+HLB_HD void svc_chroma_predict(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t& m, SvcLane& L)
 {
     const int Wc = P.W >> 1, Hc = P.H >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
     const uint8_t* ref = plane ? P.ref_v : P.ref_u;
@@ -209,93 +164,132 @@ HLB_HD void svc_chroma_predict(const SvcPlanes& P, int mbx, int mby, int plane, 
             L.pv[y * 4 + x + 1] = (uint8_t)interp_chroma_px(a1, a2, c1, c2, xf, yf);
         }
 }
+// ---- phase A, lanes 0..23 (0..15: luma4x4BlkIdx; 16..19: Cb blocks; 20..23: Cr blocks): prediction, then residual -> T -> Q (intra rounding offset for
+// luma, rdo.c:1468, and always for chroma AC, rdo.c:2588) -> scan (rdo.c:1428-1466, :2561-2638) ----
+// ps: motion and position the prediction is formed with (the macroblock itself, or the one it inherits from); unused for BL
 template <bool BL>
-HLB_HD void svc_chroma_lane_a(const SvcPlanes& P, int mbx, int mby, int plane, int blk, const hlb200_mb_motion_t* m, int pmbx, int pmby, int qpc,
-                              hlb200_svc_mb_state_t& st, SvcChromaLane& L, SvcXchg& X)
+HLB_HD void svc_lane_a(const SvcPlanes& P, int mbx, int mby, int lane, const SvcPredSrc& ps, int qp, int qpc, const hlb200_svc_mb_state_t& st, SvcLane& L, SvcXchg& X)
 {
-    const int Wc = P.W >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
-    const uint8_t* src = plane ? P.src_v : P.src_u;
-    const int off = (mby * 8 + by) * Wc + mbx * 8 + bx;
-    if (BL) svc_load_pred4x4(plane ? P.ref_v : P.ref_u, off, Wc, L.pv);
-    else svc_chroma_predict(P, pmbx, pmby, plane, blk, *m, L);
+    const bool is_luma = lane < 16;
+    const int plane = (lane - 16) >> 2, cblk = (lane - 16) & 3;
+    const int pitch = is_luma ? P.W : (P.W >> 1);
+    const int bx = is_luma ? blk_x(lane) : (cblk & 1) * 4, by = is_luma ? blk_y(lane) : (cblk >> 1) * 4;
+    const int off = is_luma ? (mby * 16 + by) * pitch + mbx * 16 + bx : (mby * 8 + by) * pitch + mbx * 8 + bx;
+    const uint8_t* src = is_luma ? P.src_y : (plane ? P.src_v : P.src_u);
+    if (BL) svc_load_pred4x4(is_luma ? P.ref_y : (plane ? P.ref_v : P.ref_u), off, pitch, L.pv);
+    else if (is_luma) svc_luma_predict(P, ps.mbx, ps.mby, lane, *ps.m, L.pv);
+    else svc_chroma_predict(P, ps.mbx, ps.mby, plane, cblk, *ps.m, L);
     int mm[16];
     bool nz = false;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const uint32_t sw = svc_ld4(src + off + r * Wc);
+        const uint32_t sw = svc_ld4(src + off + r * pitch);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { const int d = (int)((sw >> (8 * c)) & 255u) - (int)L.pv[r * 4 + c]; mm[r * 4 + c] = d; nz |= (d != 0); }
     }
-    // ChromaACLevel lives in the macroblock object from picture to picture: a block whose residual is zero keeps what an earlier picture
-    // left there, and transf.c:236-245 reads it again whenever the block's de-quantised DC is not zero.  Element [15] is never written.
+    // ChromaACLevel lives in the macroblock object from picture to picture: a block whose residual is zero keeps what an earlier picture left there, and
+    // transf.c:236-245 reads it again whenever the block's de-quantised DC is not zero.  Element [15] is never written.  LumaLevel is cleared (rdo.c:1453,1462).
 #pragma unroll
-    for (int i = 0; i < 16; ++i) L.ac[i] = st.chroma_ac_level[plane][blk][i];
+    for (int i = 0; i < 16; ++i) L.lv[i] = is_luma ? (int16_t)0 : st.chroma_ac_level[is_luma ? 0 : plane][cblk][i];
     int dc = 0;
+    if (nz) {
+        int z[16];
+        fwd_transform4x4(mm);
+        dc = mm[0];   // chroma: W00 before quantisation, input of the 2x2 DC stage (rdo.c:2591)
+        quant4x4_ac(mm, is_luma ? qp : qpc, /*intra f*/ true);
+        zigzag4x4(mm, z);
+        if (is_luma) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) L.lv[i] = (int16_t)z[i];
+        } else {
+#pragma unroll
+            for (int i = 1; i < 16; ++i) L.lv[i - 1] = (int16_t)z[i];   // Scan4x4_AC_C, utils.h:183
+        }
+    }
     bool coded = false;
     int nnz = 0, big = 0;
     if (nz) {
-        int lv[16];
-        fwd_transform4x4(mm);
-        dc = mm[0];
-        quant4x4_ac(mm, qpc, /*intra f*/ true);   // chroma AC always uses the intra offset (rdo.c:2588)
-        zigzag4x4(mm, lv);
 #pragma unroll
-        for (int i = 1; i < 16; ++i) L.ac[i - 1] = (int16_t)lv[i];   // Scan4x4_AC_C, utils.h:183
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { coded |= (L.ac[i] != 0); nnz += (L.ac[i] != 0); big |= (iabs(L.ac[i]) > 1); }
+        for (int i = 0; i < 16; ++i) { coded |= (L.lv[i] != 0); nnz += (L.lv[i] != 0); big |= (iabs(L.lv[i]) > 1); }
     }
-    X.dc_coef[plane][blk] = dc;
-    X.coded[plane][blk] = coded ? 1 : 0;
-    X.nnz[plane][blk] = (uint8_t)(coded ? nnz : 0);
-    X.big[plane][blk] = (uint8_t)(coded ? big : 0);
+    L.coded = coded;
+    if (is_luma) X.luma_coded[lane] = coded ? 1 : 0;
+    else {
+        X.dc_coef[plane][cblk] = dc;
+        X.coded[plane][cblk] = coded ? 1 : 0;
+        X.nnz[plane][cblk] = (uint8_t)(coded ? nnz : 0);
+        X.big[plane][cblk] = (uint8_t)(coded ? big : 0);
+    }
 }
 
-// ---- chroma lane, phase B: elimination, 2x2 DC, reconstruction of the block (rdo.c:2640-2682, transf.c:161-296) ----
+// ---- phase B, lanes 0..23: chroma lanes first resolve the elimination and the 2x2 DC of their plane (rdo.c:2640-2672); then Q^-1 -> T^-1 -> add/clip ->
+// reconstruction and the outputs (rdo.c:1469-1496, transf.c:161-296) ----
 // mb_intra: the macroblock counts as intra in rdo.c:2660 (I_BL, or a macroblock with an inherited prediction -- see SvcPredSrc)
-HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, int blk, int qpc, bool mb_intra, hlb200_svc_mb_state_t& st, const SvcChromaLane& L,
-                              const SvcXchg& X, hlb200_mb_coeffs_t& out)
+HLB_HD void svc_lane_b(const SvcPlanes& P, int mbx, int mby, int lane, int qp, int qpc, bool mb_intra, hlb200_svc_mb_state_t& st, const SvcLane& L, const SvcXchg& X,
+                       hlb200_mb_coeffs_t& out)
 {
-    const int Wc = P.W >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
-    int tot = 0, anybig = 0;
-    unsigned ac_mask = 0;
+    const bool is_luma = lane < 16;
+    const int plane = is_luma ? 0 : (lane - 16) >> 2, cblk = (lane - 16) & 3;
+    const int pitch = is_luma ? P.W : (P.W >> 1);
+    const int bx = is_luma ? blk_x(lane) : (cblk & 1) * 4, by = is_luma ? blk_y(lane) : (cblk >> 1) * 4;
+    const int off = is_luma ? (mby * 16 + by) * pitch + mbx * 16 + bx : (mby * 8 + by) * pitch + mbx * 8 + bx;
+    uint8_t* rec = is_luma ? P.rec_y : (plane ? P.rec_v : P.rec_u);
+    int l2[16];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { tot += X.nnz[plane][k]; anybig |= X.big[plane][k]; ac_mask |= (unsigned)X.coded[plane][k] << k; }
-    if (tot == 1 && !anybig) ac_mask = 0;   // exactly one +-1 AC coefficient in the plane: Single_ctr < 7 && TotalCoeffs == 1, rdo.c:2641-2649
-    int dcl[4], dcr[4] = {0, 0, 0, 0};
-    unsigned dc_mask = 0;
-    const bool dc_tent = (X.dc_coef[plane][0] | X.dc_coef[plane][1] | X.dc_coef[plane][2] | X.dc_coef[plane][3]) != 0;
-    if (dc_tent) {
+    for (int i = 0; i < 16; ++i) l2[i] = L.lv[i];
+    bool use_res = L.coded;
+    if (!is_luma) {
+        int tot = 0, anybig = 0;
+        unsigned ac_mask = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dcl[k] = X.dc_coef[plane][k];
-        hadamard2x2(dcl);
-        // rdo.c:2660 uses the macroblock's own intra flag: an inferred macroblock with inter prediction is not intra (mb.h:46,57), an I_BL one is
-        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ mb_intra);
+        for (int k = 0; k < 4; ++k) { tot += X.nnz[plane][k]; anybig |= X.big[plane][k]; ac_mask |= (unsigned)X.coded[plane][k] << k; }
+        if (tot == 1 && !anybig) ac_mask = 0;   // exactly one +-1 AC coefficient in the plane: Single_ctr < 7 && TotalCoeffs == 1, rdo.c:2641-2649
+        int dcl[4], dcr[4] = {0, 0, 0, 0};
+        unsigned dc_mask = 0;
+        const bool dc_tent = (X.dc_coef[plane][0] | X.dc_coef[plane][1] | X.dc_coef[plane][2] | X.dc_coef[plane][3]) != 0;
+        if (dc_tent) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dc_mask |= (unsigned)(dcl[k] != 0) << k;
-        if (dc_mask) {   // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5
+            for (int k = 0; k < 4; ++k) dcl[k] = X.dc_coef[plane][k];
+            hadamard2x2(dcl);
+            // rdo.c:2660 uses the macroblock's own intra flag: an inferred macroblock with inter prediction is not intra (mb.h:46,57), an I_BL one is
+            quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ mb_intra);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dcr[k] = dcl[k];
-            hadamard2x2(dcr);
-            const int ls = 16 * kNormAdjust[qpc % 6][0];
+            for (int k = 0; k < 4; ++k) dc_mask |= (unsigned)(dcl[k] != 0) << k;
+            if (dc_mask) {   // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dcr[k] = ((dcr[k] * ls) << (qpc / 6)) >> 5;
+                for (int k = 0; k < 4; ++k) dcr[k] = dcl[k];
+                hadamard2x2(dcr);
+                const int ls = 16 * kNormAdjust[qpc % 6][0];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dcr[k] = ((dcr[k] * ls) << (qpc / 6)) >> 5;
+            }
+        } else {   // ChromaDCLevel keeps its old content (rdo.c:2653: not entered)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dcl[k] = st.chroma_dc_level[plane][k];
         }
-    } else {   // ChromaDCLevel keeps its old content (rdo.c:2653: not entered)
+        const int mydc = dcr[cblk];
+        use_res = mydc != 0 || ((ac_mask >> cblk) & 1);   // AC levels are used whenever the DC is non-zero (transf.c:236)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dcl[k] = st.chroma_dc_level[plane][k];
+        for (int i = 15; i >= 1; --i) l2[i] = L.lv[i - 1];
+        l2[0] = mydc;
+        // outputs = the macroblock object's fields after the call; state = the same fields, carried to the next picture of the layer
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { out.chroma_ac_level[plane][cblk][i] = L.lv[i]; st.chroma_ac_level[plane][cblk][i] = L.lv[i]; }
+        if (cblk == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { out.chroma_dc_level[plane][k] = (int16_t)dcl[k]; st.chroma_dc_level[plane][k] = (int16_t)dcl[k]; }
+            out.cbp_chroma_dc4x4[plane] = (uint8_t)dc_mask;
+            out.cbp_chroma_ac4x4[plane] = (uint8_t)ac_mask;
+        }
+    } else {   // two levels per store; all zero when the block is not coded
+        uint32_t* o = reinterpret_cast<uint32_t*>(&out.luma_level[lane][0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (uint32_t)(uint16_t)L.lv[2 * i] | ((uint32_t)(uint16_t)L.lv[2 * i + 1] << 16);
     }
-    const int mydc = dcr[blk];
-    const bool use_res = mydc != 0 || ((ac_mask >> blk) & 1);   // AC levels are used whenever the DC is non-zero (transf.c:236)
-    const int off = (mby * 8 + by) * Wc + mbx * 8 + bx;
-    uint8_t* rec = plane ? P.rec_v : P.rec_u;
     int c[16];
     if (use_res) {
-        int l2[16];
-        l2[0] = mydc;
-#pragma unroll
-        for (int i = 1; i < 16; ++i) l2[i] = L.ac[i - 1];
         inv_zigzag4x4(l2, c);
-        dequant4x4(c, qpc, /*keep_dc*/ true);
+        dequant4x4(c, is_luma ? qp : qpc, /*keep_dc*/ !is_luma);
         inv_transform4x4(c);
     } else {
 #pragma unroll
@@ -303,17 +297,8 @@ HLB_HD void svc_chroma_lane_b(const SvcPlanes& P, int mbx, int mby, int plane, i
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-        svc_st4(rec + off + r * Wc, clip255((int)L.pv[r * 4] + c[r * 4]), clip255((int)L.pv[r * 4 + 1] + c[r * 4 + 1]), clip255((int)L.pv[r * 4 + 2] + c[r * 4 + 2]),
+        svc_st4(rec + off + r * pitch, clip255((int)L.pv[r * 4] + c[r * 4]), clip255((int)L.pv[r * 4 + 1] + c[r * 4 + 1]), clip255((int)L.pv[r * 4 + 2] + c[r * 4 + 2]),
                 clip255((int)L.pv[r * 4 + 3] + c[r * 4 + 3]));
-    // outputs = the macroblock object's fields after the call; state = the same fields, carried to the next picture of the layer
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { out.chroma_ac_level[plane][blk][i] = L.ac[i]; st.chroma_ac_level[plane][blk][i] = L.ac[i]; }
-    if (blk == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { out.chroma_dc_level[plane][k] = (int16_t)dcl[k]; st.chroma_dc_level[plane][k] = (int16_t)dcl[k]; }
-        out.cbp_chroma_dc4x4[plane] = (uint8_t)dc_mask;
-        out.cbp_chroma_ac4x4[plane] = (uint8_t)ac_mask;
-    }
 }
 
 HLB_HD unsigned svc_luma_cbp(const SvcXchg& X)

@@ -25,24 +25,17 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_recon_batch(int bl
             const size_t idx = (size_t)pic * nmb + mb;
             const int mbx = mb % mbw, mby = mb / mbw;
             hlb::SvcXchg X;
-            hlb::SvcChromaLane L[8];
+            hlb::SvcLane L[24];
             hlb::SvcPredSrc ps;
             if (bl) { ps.m = nullptr; ps.mbx = mbx; ps.mby = mby; ps.inherited = false; }
             else ps = hlb::svc_pred_src(motion + (size_t)pic * nmb, mb, mbw);
             for (int lane = 0; lane < 24; ++lane) {
-                const int plane = (lane - 16) >> 2, cblk = (lane - 16) & 3;
-                if (bl) {
-                    if (lane < 16) hlb::svc_luma_lane<true>(P, mbx, mby, lane, ps.m, ps.mbx, ps.mby, qp, coeffs[idx], X);
-                    else hlb::svc_chroma_lane_a<true>(P, mbx, mby, plane, cblk, ps.m, ps.mbx, ps.mby, qpc, state[idx], L[lane - 16], X);
-                } else {
-                    if (lane < 16) hlb::svc_luma_lane<false>(P, mbx, mby, lane, ps.m, ps.mbx, ps.mby, qp, coeffs[idx], X);
-                    else hlb::svc_chroma_lane_a<false>(P, mbx, mby, plane, cblk, ps.m, ps.mbx, ps.mby, qpc, state[idx], L[lane - 16], X);
-                }
+                if (bl) hlb::svc_lane_a<true>(P, mbx, mby, lane, ps, qp, qpc, state[idx], L[lane], X);
+                else hlb::svc_lane_a<false>(P, mbx, mby, lane, ps, qp, qpc, state[idx], L[lane], X);
             }
             // all phase-A reads of the state happen before any phase-B write, as on the device (phase B rewrites ChromaDCLevel with the values its
             // other lanes read, or with new ones that nobody reads)
-            for (int lane = 16; lane < 24; ++lane)
-                hlb::svc_chroma_lane_b(P, mbx, mby, (lane - 16) >> 2, (lane - 16) & 3, qpc, bl || ps.inherited, state[idx], L[lane - 16], X, coeffs[idx]);
+            for (int lane = 0; lane < 24; ++lane) hlb::svc_lane_b(P, mbx, mby, lane, qp, qpc, bl || ps.inherited, state[idx], L[lane], X, coeffs[idx]);
             coeffs[idx].cbp_luma4x4 = (uint16_t)hlb::svc_luma_cbp(X);
         }
     }
