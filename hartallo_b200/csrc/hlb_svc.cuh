@@ -148,7 +148,32 @@ HLB_HD void svc_chroma_predict(const SvcPlanes& P, int mbx, int mby, int plane, 
 {
     const int Wc = P.W >> 1, Hc = P.H >> 1, bx = (blk & 1) * 4, by = (blk >> 1) * 4;
     const uint8_t* ref = plane ? P.ref_v : P.ref_u;
-    // 8.4.2.2.2 per sample; a 2x2 chroma area is the smallest one with its own motion vector
+    // A 4x4 chroma block is an 8x8 luma area: one motion vector unless the macroblock is 8x8-partitioned with sub-partitions there (never after the dyadic
+    // inter-layer derivation).  Then, inside the picture, the 5x5 window is fetched as two aligned words per row and shifted into place.
+    if (m.part_mode != 3 || m.sub_mode[blk] == 0) {
+        const int part = m.part_mode == 0 ? 0 : (m.part_mode == 1 ? (blk >> 1) : (m.part_mode == 2 ? (blk & 1) : blk));
+        const int mvx = m.mv[part][0][0], mvy = m.mv[part][0][1], xf = mvx & 7, yf = mvy & 7;
+        const int x0 = mbx * 8 + bx + (mvx >> 3), y0 = mby * 8 + by + (mvy >> 3), xa = x0 & ~3, sh8 = (x0 & 3) * 8;
+        if (x0 >= 0 && y0 >= 0 && xa + 8 <= Wc && y0 + 5 <= Hc) {
+            uint32_t lo[5], hi[5];   // samples x0..x0+3 and x0+4 of rows y0..y0+4
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(ref + (y0 + r) * Wc + xa);
+                const uint32_t w0 = HLB_LDG(q), w1 = HLB_LDG(q + 1);
+                lo[r] = svc_funnel(w0, w1, sh8); hi[r] = (w1 >> sh8) & 255u;
+            }
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int A = (lo[y] >> (8 * x)) & 255u, C = (lo[y + 1] >> (8 * x)) & 255u;
+                    const int B = x < 3 ? (int)((lo[y] >> (8 * x + 8)) & 255u) : (int)hi[y], D = x < 3 ? (int)((lo[y + 1] >> (8 * x + 8)) & 255u) : (int)hi[y + 1];
+                    L.pv[y * 4 + x] = (uint8_t)interp_chroma_px(A, B, C, D, xf, yf);
+                }
+            return;
+        }
+    }
+    // 8.4.2.2.2 per sample with the reference's clamp; a 2x2 chroma area is the smallest one with its own motion vector
 #pragma unroll
     for (int y = 0; y < 4; ++y)
 #pragma unroll
