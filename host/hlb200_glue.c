@@ -44,6 +44,7 @@ static struct {
     hlb200_mb_record_t* rec;
     const void* fs_of_slot[HLB200_MAX_REFS + 1];   /* host frame store whose picture lives in each device slot */
     int is_p;
+    int svc;                                       /* the stream has enhancement layers: they derive their motion from this layer's macroblock objects */
 } g;
 
 static HL_ERROR_T glue_fail(const char* what, int rc)
@@ -76,6 +77,20 @@ static void glue_apply(hl_codec_264_mb_t* p_mb, const hlb200_mb_record_t* r, int
         p_mb->flags_type = i16 ? HL_CODEC_264_MB_TYPE_FLAGS_INTRA_16x16 : HL_CODEC_264_MB_TYPE_FLAGS_INTRA_4x4;
         p_mb->MbPartPredMode[0] = i16 ? HL_CODEC_264_MB_MODE_INTRA_16X16 : HL_CODEC_264_MB_MODE_INTRA_4X4;
         p_mb->NumMbPart = 1;
+        if (g.svc && g.is_p) {
+            /* The enhancement layers' inter-layer derivation reads this object (utils.c:1701,1807-1834).  An Intra16x16 macroblock is recognised as intra by its
+             * e_type whatever else it holds; an Intra4x4 macroblock of a P picture is NOT (HL_CODEC_264_MB_TYPE_IS_I_4X4 tests the type that only I pictures get
+             * patched in, mb.c:326-345), so the reference derives enhancement-layer motion from whatever partitions / vectors the last search trial left in the
+             * object (rdo.c:851-967) -- leftovers the device does not report.  Leave a consistent state instead (one 16x16 partition, zero vector): the stream
+             * stays valid, but above such macroblocks the enhancement layers are not byte-identical to the reference's. */
+            p_mb->MbPartWidth = p_mb->MbPartHeight = 16;
+            for (p = 0; p < 4; ++p) {
+                p_mb->predFlagL0[p] = p_mb->PredFlagL0[p] = (p == 0);
+                p_mb->refIdxL0[p] = p_mb->RefIdxL0[p] = 0;
+                p_mb->NumSubMbPart[p] = 1; p_mb->SubMbPartWidth[p] = p_mb->SubMbPartHeight[p] = 16;
+                for (s = 0; s < 4; ++s) p_mb->mvL0[p][s].x = p_mb->mvL0[p][s].y = p_mb->MvL0[p][s].x = p_mb->MvL0[p][s].y = 0;
+            }
+        }
         p_mb->Intra16x16PredMode = (HL_CODEC_264_I16x16_MODE_T)r->i16_pred_mode;
         p_mb->intra_chroma_pred_mode = r->intra_chroma_pred_mode;
         for (b = 0; b < 16; ++b) {
@@ -260,6 +275,10 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
             int p, ok = mode >= 0;
             for (p = 0; ok && p < n; ++p) ok = p_mb->NumSubMbPart[p] >= 1 && p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == 0 && p_mb->partWidth[p][0] == pw && p_mb->partHeight[p][0] == ph;
             L->valid[addr] = (uint8_t)ok;
+            if (!ok && getenv("HLB200_GLUE_DEBUG"))
+                fprintf(stderr, "hlb200 glue: layer %d mb %u: NumMbPart %d %dx%d NumSubMbPart %d %d %d %d predFlagL0 %d %d %d %d refIdxL0 %d %d %d %d e_type %d\n", li, addr, n, pw, ph,
+                        p_mb->NumSubMbPart[0], p_mb->NumSubMbPart[1], p_mb->NumSubMbPart[2], p_mb->NumSubMbPart[3], p_mb->predFlagL0[0], p_mb->predFlagL0[1], p_mb->predFlagL0[2],
+                        p_mb->predFlagL0[3], p_mb->refIdxL0[0], p_mb->refIdxL0[1], p_mb->refIdxL0[2], p_mb->refIdxL0[3], (int)p_mb->e_type);
             if (ok) {
                 m->part_mode = (uint8_t)mode;
                 for (p = 0; p < n; ++p) { m->mv[p][0][0] = (int16_t)p_mb->mvL0[p][0].x; m->mv[p][0][1] = (int16_t)p_mb->mvL0[p][0].y; }
@@ -375,6 +394,7 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
         memset(g.fs_of_slot, 0, sizeof(g.fs_of_slot));
     }
     memset(&prm, 0, sizeof(prm));
+    g.svc = p_codec->encoder.b_svc_enabled ? 1 : 0;
     g.is_p = IsSliceHeaderP(hdr) ? 1 : 0;
     prm.slice_type = g.is_p;
     prm.qp = p_codec->encoder.rc.b_enabled ? p_codec->encoder.rc.qp : p_codec->encoder.i_qp;

@@ -64,5 +64,9 @@ if [ -f "$GLUE" ] && [ -f "$HERE/../tools/emu/svc_shim.cpp" ]; then
   g++ -std=c++17 -O2 -w -fPIC -x c++ -c "$HERE/../tools/emu/svc_shim.cpp" -o "$TMP/obj_shim.o"
   g++ -std=c++17 -O2 -w -fPIC -x c++ -c "$HERE/../tools/emu/svc_emu.cpp" -o "$TMP/obj_emu.o"
   g++ "$TMP/obj_driver_nw.o" "$TMP/obj_glue_svc.o" "$TMP/obj_shim.o" "$TMP/obj_emu.o" -Wl,--wrap=hl_codec_264_nal_slice_data_encode $GS "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_svc_glue_check"
+  # the WHOLE glue (base layer hook included, exactly the object linked into hl_b200_encoder) with the per-macroblock sources of BOTH kernels compiled as C++
+  # standing in for the library: every layer goes through the drop-in path, nothing through the reference's decision functions
+  g++ -std=c++17 -O2 -w -fPIC -ffp-contract=off -DSVC_SHIM_WITH_SLICE -x c++ -c "$HERE/../tools/emu/svc_shim.cpp" -o "$TMP/obj_shim_full.o"
+  g++ "$TMP/obj_driver_nw.o" "$TMP/obj_glue.o" "$TMP/obj_shim_full.o" "$TMP/obj_emu.o" $GW "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_glue_check_full"
 fi
 echo "build_ref: built $(ls "$OUT")"

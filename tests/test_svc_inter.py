@@ -326,6 +326,7 @@ import json  # noqa: E402
 
 SVC_STREAMS = json.load(open(os.path.join(ROOT, "tests", "golden", "svc_bitstream.json")))
 GLUE_CHECK = os.path.join(ROOT, "oracle", "_ref", "hl_svc_glue_check")
+GLUE_FULL = os.path.join(ROOT, "oracle", "_ref", "hl_glue_check_full")
 B200_ENCODER = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder")
 
 
@@ -344,6 +345,36 @@ def test_svc_glue_hook_bitstream_md5_cpu(name):
     g = SVC_STREAMS[name]
     got = _encode(GLUE_CHECK, g["args"])
     assert (got["bytes"], got["md5"]) == (g["bytes"], g["md5"]), (got, g)
+
+
+@pytest.mark.skipif(not os.path.exists(GLUE_FULL), reason="oracle/_ref/hl_glue_check_full only exists where the reference tree is available")
+@pytest.mark.parametrize("name", sorted(SVC_STREAMS))
+def test_whole_glue_bitstream_md5_cpu(name):
+    """the WHOLE glue object that is linked into hl_b200_encoder (base-layer hook + enhancement-layer hook), with the per-macroblock sources of both kernels
+    compiled as C++ standing in for the library (tools/emu/svc_shim.cpp -DSVC_SHIM_WITH_SLICE): no layer goes through the reference's decision functions, and
+    the multi-layer bitstream still equals the all-reference one.  This is the CPU-tier twin of test_svc_bitstream_md5_drop_in."""
+    g = SVC_STREAMS[name]
+    got = _encode(GLUE_FULL, g["args"])
+    assert (got["bytes"], got["md5"]) == (g["bytes"], g["md5"]), (got, g)
+
+
+@pytest.mark.skipif(not os.path.exists(GLUE_FULL), reason="oracle/_ref/hl_glue_check_full only exists where the reference tree is available")
+def test_single_layer_glue_bitstream_md5_cpu():
+    """CPU-tier twin of test_encoder.py::test_bitstream_md5_drop_in: the AVC drop-in (slice hook + decision records copied into the reference's macroblock
+    objects + the reference's own CAVLC writer) with the slice kernel's source standing in for the library, on every golden encoder configuration"""
+    import glob
+    n = 0
+    for f in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "encoder_*.npz"))):
+        g = np.load(f)
+        w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
+        if w * h * frames > 352 * 288 * 4:     # keep the CPU tier short: the big ones run on the GPU
+            continue
+        refs = int(g["refs"]) if "refs" in g.files else 1
+        got = _encode(GLUE_FULL, ["--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", str(refs), "--gen", str(g["gen"]),
+                                  "--seed", str(seed)])
+        assert got["md5"] == str(g["bitstream_md5"]), (f, got)
+        n += 1
+    assert n >= 3
 
 
 @pytest.mark.gpu

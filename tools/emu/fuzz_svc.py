@@ -22,12 +22,14 @@ import test_svc_inter as T  # noqa: E402
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-GLUE = os.path.join(ROOT, "oracle", "_ref", "hl_svc_glue_check")
+GLUE = os.path.join(ROOT, "oracle", "_ref", "hl_svc_glue_check")        # enhancement-layer hook only (base layer on the reference's CPU path)
+GLUE_FULL = os.path.join(ROOT, "oracle", "_ref", "hl_glue_check_full")   # the whole glue: base layer through the slice kernel's source as well
 o = T._oracle()
-bad = n_mb = n_skip = n_md5 = 0
+bad = n_mb = n_skip = n_md5 = n_full = n_full_diff = 0
+full_diff = []
 for case in range(first, first + n_cases):
     rng = np.random.default_rng(case)
-    layers = int(rng.choice([2, 2, 3]))
+    layers = int(rng.choice([2, 2, 3])) if os.environ.get("FUZZ_SVC_LAYERS") is None else int(os.environ["FUZZ_SVC_LAYERS"])
     w, h = int(rng.integers(1, 9 if layers == 2 else 6)) * 16, int(rng.integers(1, 8 if layers == 2 else 5)) * 16
     frames = int(rng.integers(2, 5))
     qp = int(rng.integers(20, 52))
@@ -66,10 +68,24 @@ for case in range(first, first + n_cases):
         else:
             md5 = " bitstream MD5 equal"
             n_md5 += 1
+        if ok and os.path.exists(GLUE_FULL):
+            g = subprocess.run([GLUE_FULL] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            gj = json.loads(g.stdout.strip().splitlines()[-1]) if g.returncode == 0 and g.stdout.strip() else {"md5": "failed"}
+            if gj["md5"] == ref_json["md5"]:
+                md5 += ", whole glue equal"
+                n_full += 1
+            else:
+                md5 += ", whole glue %s" % ("FAILED" if gj["md5"] == "failed" else "different")
+                n_full_diff += 1
+                full_diff.append(case)
     print("case %d: %s -> %s (%d macroblocks, %d skipped)%s" % (case, " ".join(args), "OK" if ok else "MISMATCH", mbs, skipped, md5), flush=True)
     bad += not ok
     n_mb += mbs
     n_skip += skipped
     os.remove(tr)
+if n_full or n_full_diff:
+    # informational: above Intra4x4 macroblocks of base-layer P pictures the reference derives enhancement motion from search leftovers the device does not
+    # report (host/hlb200_glue.c: glue_apply), so the whole-glue bitstream may differ there; a FAILED run is a bug
+    print("whole glue (base layer through the slice kernel's source too): %d bitstreams equal, %d different %s" % (n_full, n_full_diff, full_diff))
 print("%d cases, %d mismatches, %d macroblocks compared, %d skipped (inherit scratch memory of an earlier picture), %d bitstream MD5 comparisons" % (n_cases, bad, n_mb, n_skip, n_md5))
 sys.exit(1 if bad else 0)

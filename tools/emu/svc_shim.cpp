@@ -1,35 +1,61 @@
-// CPU stand-in for the few libhl_b200.so entry points the SVC part of host/hlb200_glue.c calls, backed by the CPU run of the device source
-// (svc_emu.cpp).  TEST INFRASTRUCTURE: lets oracle/_ref/hl_svc_glue_check exercise the enhancement-layer hook (pre-pass derivation -> one picture call ->
+// CPU stand-in for the libhl_b200.so entry points host/hlb200_glue.c calls, backed by the CPU run of the device sources (svc_emu.cpp for the SVC kernel;
+// with -DSVC_SHIM_WITH_SLICE also hlb_mbcore.cuh, the slice kernel's per-macroblock code, for the base layer).  TEST INFRASTRUCTURE: lets oracle/_ref/hl_svc_glue_check exercise the enhancement-layer hook (pre-pass derivation -> one picture call ->
 // the reference's own writer) end to end without a GPU and compare the bitstream MD5 with the reference's.  Never part of the product library.
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include "../../include/hlb200.h"
+#ifdef SVC_SHIM_WITH_SLICE   /* also stand in for hlb200_slice_encode: the slice kernel's per-macroblock source run in raster order, as tools/emu/emu_main.cpp does */
+#include <math.h>
+#include <stdio.h>
+int g_emu_dbg = 0;
+#define HLB_EMU_DEBUG 1
+#include "../../hartallo_b200/csrc/hlb_mbcore.cuh"
+#endif
 
 extern "C" int svc_emu_recon_batch(int bl, const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v,
                                    int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion,
                                    hlb200_svc_mb_state_t* state, hlb200_mb_coeffs_t* coeffs, uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v);
 
 struct hlb200_ctx {
-    int w, h, nmb;
+    int w, h, nmb, nslots;
     uint8_t* src;
-    uint8_t* slot[2];
+    uint8_t* slot[HLB200_MAX_REFS + 1];
     hlb200_svc_mb_state_t* state;
+#ifdef SVC_SHIM_WITH_SLICE
+    hlb::MbState* mbstate;
+    hlb::MbWork* work;
+    int chain;
+#endif
 };
 #define API extern "C" __attribute__((visibility("default")))
 API int hlb200_init(int) { return HLB200_OK; }
 API const char* hlb200_last_error(void) { return "svc_shim"; }
-API int hlb200_stream_create(int w, int h, int, hlb200_ctx_t** out)
+API int hlb200_stream_create(int w, int h, int max_refs, hlb200_ctx_t** out)
 {
     hlb200_ctx* c = (hlb200_ctx*)calloc(1, sizeof(hlb200_ctx));
     const size_t fb = (size_t)w * h * 3 / 2;
-    c->w = w; c->h = h; c->nmb = (w >> 4) * (h >> 4);
-    c->src = (uint8_t*)calloc(fb, 1); c->slot[0] = (uint8_t*)calloc(fb, 1); c->slot[1] = (uint8_t*)calloc(fb, 1);
+    c->w = w; c->h = h; c->nmb = (w >> 4) * (h >> 4); c->nslots = max_refs + 1;
+    c->src = (uint8_t*)calloc(fb, 1);
+    for (int s = 0; s < c->nslots; ++s) c->slot[s] = (uint8_t*)calloc(fb, 1);
     c->state = (hlb200_svc_mb_state_t*)calloc((size_t)c->nmb, sizeof(hlb200_svc_mb_state_t));
+#ifdef SVC_SHIM_WITH_SLICE
+    c->mbstate = (hlb::MbState*)calloc((size_t)c->nmb, sizeof(hlb::MbState));
+    c->work = (hlb::MbWork*)calloc(1, sizeof(hlb::MbWork));
+#endif
     *out = c;
     return HLB200_OK;
 }
-API int hlb200_stream_destroy(hlb200_ctx_t* c) { free(c->src); free(c->slot[0]); free(c->slot[1]); free(c->state); free(c); return HLB200_OK; }
+API int hlb200_stream_destroy(hlb200_ctx_t* c)
+{
+    free(c->src); free(c->state);
+    for (int s = 0; s < c->nslots; ++s) free(c->slot[s]);
+#ifdef SVC_SHIM_WITH_SLICE
+    free(c->mbstate); free(c->work);
+#endif
+    free(c);
+    return HLB200_OK;
+}
 API int hlb200_frame_upload(hlb200_ctx_t* c, const uint8_t* y, const uint8_t* u, const uint8_t* v, int sy, int sc)
 {
     const int W = c->w, H = c->h, Wc = W >> 1, Hc = H >> 1;
@@ -49,7 +75,55 @@ API int hlb200_slot_download(hlb200_ctx_t* c, int s, uint8_t* y, uint8_t* u, uin
     memcpy(y, c->slot[s], ysz); memcpy(u, c->slot[s] + ysz, csz); memcpy(v, c->slot[s] + ysz + csz, csz);
     return HLB200_OK;
 }
-API int hlb200_slice_encode(hlb200_ctx_t*, const hlb200_slice_params_t*, hlb200_mb_record_t*) { return HLB200_ERR_SYSTEM; }   // base layer: not emulated here
+#ifdef SVC_SHIM_WITH_SLICE
+namespace {
+struct CpuExec {   // the executor of tools/emu/emu_main.cpp: lanes become loops
+    hlb::MbWork* w;
+    const hlb::FrameCtx* f;
+    int prev_frame_sctr;
+    void run(int cmd, int nlanes)
+    {
+        w->cmd = cmd; w->arg0_lanes = nlanes;
+        const int np = hlb::cmd_phases(cmd);
+        for (int p = 0; p < np; ++p)
+            for (int lane = 0; lane < nlanes; ++lane) hlb::cmd_phase(*w, *f, cmd, p, lane);
+    }
+    int lane() const { return 0; }
+    int nlanes() const { return 1; }
+    void sync() const {}
+    int prev_sctr(int mb)
+    {
+        for (int a = mb - 1; a >= 0; --a)
+            if (f->st[a].last_sctr != 255) return f->st[a].last_sctr;
+        return prev_frame_sctr;
+    }
+};
+}
+// build_job() of hartallo_b200/csrc/hlb_slice.cu, then the macroblocks in raster order
+API int hlb200_slice_encode(hlb200_ctx_t* c, const hlb200_slice_params_t* p, hlb200_mb_record_t* out)
+{
+    const size_t ys = (size_t)c->w * c->h, cs = ys / 4;
+    hlb::FrameCtx f;
+    memset(&f, 0, sizeof(f));
+    f.W = c->w; f.H = c->h; f.mbw = c->w / 16; f.mbh = c->h / 16;
+    f.qp = p->qp;
+    { int q = p->qp + p->chroma_qp_index_offset; q = q < 0 ? 0 : (q > 51 ? 51 : q); f.qpc = hlb::kQpc[q]; }
+    f.is_p = p->slice_type == 1;
+    f.me_range = p->me_range < 1 ? 1 : (p->me_range > 64 ? 64 : p->me_range);
+    f.num_refs = f.is_p ? p->num_refs : 0;
+    f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));
+    f.src[0] = c->src; f.src[1] = c->src + ys; f.src[2] = c->src + ys + cs;
+    f.cur[0] = c->slot[p->cur_slot]; f.cur[1] = f.cur[0] + ys; f.cur[2] = f.cur[1] + cs;
+    for (int u = 0; u < f.num_refs; ++u) { f.ref[u][0] = c->slot[p->ref_slot[u]]; f.ref[u][1] = f.ref[u][0] + ys; f.ref[u][2] = f.ref[u][1] + cs; }
+    f.st = c->mbstate; f.rec = out;
+    CpuExec x{c->work, &f, c->chain};
+    for (int mb = 0; mb < c->nmb; ++mb) hlb::mb_encode(x, *c->work, f, mb);
+    c->chain = x.prev_sctr(c->nmb);
+    return HLB200_OK;
+}
+#else
+API int hlb200_slice_encode(hlb200_ctx_t*, const hlb200_slice_params_t*, hlb200_mb_record_t*) { return HLB200_ERR_SYSTEM; }   // base layer: not emulated in this build
+#endif
 API int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp, int off, const hlb200_mb_motion_t* motion, const uint8_t* pred_y, const uint8_t* pred_u,
                                  const uint8_t* pred_v, hlb200_mb_coeffs_t* out)
 {
