@@ -80,16 +80,16 @@ static void glue_apply(hl_codec_264_mb_t* p_mb, const hlb200_mb_record_t* r, int
         if (g.svc && g.is_p) {
             /* The enhancement layers' inter-layer derivation reads this object (utils.c:1701,1807-1834).  An Intra16x16 macroblock is recognised as intra by its
              * e_type whatever else it holds; an Intra4x4 macroblock of a P picture is NOT (HL_CODEC_264_MB_TYPE_IS_I_4X4 tests the type that only I pictures get
-             * patched in, mb.c:326-345), so the reference derives enhancement-layer motion from whatever partitions / vectors the last search trial left in the
-             * object (rdo.c:851-967) -- leftovers the device does not report.  Leave a consistent state instead (one 16x16 partition, zero vector): the stream
-             * stays valid, but above such macroblocks the enhancement layers are not byte-identical to the reference's. */
+             * patched in, mb.c:326-345), so the reference derives enhancement-layer motion from it.  What that derivation can see of it: flags_type is intra
+             * (rdo.c:194), so hl_codec_264_mb_get_sub_partition_indices (mb.h:313-339) answers partition 0 / sub-partition 0 for every 4x4 block, and
+             * utils.c:1807-1834 then reads predFlagL0[0], refIdxL0[0], mvL0[0][0] -- the LOWER-case fields.  The base layer's search (SVCExtFlag = 0) works on the
+             * upper-case ones (rdo.c:849-852) and only marks predFlagL0[0] = 1 (me_ds.c:183, the 16x16 mode is always tried); when intra wins nothing commits
+             * (rdo.c:1161-1167), so refIdxL0[0] / mvL0[0][0] are those of this macroblock's LAST INTER COMMIT in an earlier picture (0 if none: the object is
+             * never reset, utils.c:73-89).  The object here is the same persistent one and the inter branch below writes the same values at [0][0] as
+             * rdo.c:1180,1194, so leaving them alone reproduces the reference. */
             p_mb->MbPartWidth = p_mb->MbPartHeight = 16;
-            for (p = 0; p < 4; ++p) {
-                p_mb->predFlagL0[p] = p_mb->PredFlagL0[p] = (p == 0);
-                p_mb->refIdxL0[p] = p_mb->RefIdxL0[p] = 0;
-                p_mb->NumSubMbPart[p] = 1; p_mb->SubMbPartWidth[p] = p_mb->SubMbPartHeight[p] = 16;
-                for (s = 0; s < 4; ++s) p_mb->mvL0[p][s].x = p_mb->mvL0[p][s].y = p_mb->MvL0[p][s].x = p_mb->MvL0[p][s].y = 0;
-            }
+            p_mb->predFlagL0[0] = 1;
+            for (p = 0; p < 4; ++p) p_mb->NumSubMbPart[p] = 1, p_mb->SubMbPartWidth[p] = p_mb->SubMbPartHeight[p] = 16;
         }
         p_mb->Intra16x16PredMode = (HL_CODEC_264_I16x16_MODE_T)r->i16_pred_mode;
         p_mb->intra_chroma_pred_mode = r->intra_chroma_pred_mode;

@@ -14,6 +14,10 @@ CONFIGS = {
     "g1_3layer_small_q24": ["--size", "64", "48", "--layers", "3", "--frames", "4", "--gen", "g1", "--qp", "24"],
     "g1_2layer_q38": ["--size", "96", "80", "--layers", "2", "--frames", "4", "--gen", "g1", "--qp", "38"],
     "g2_qcif_cif": ["--size", "176", "144", "--layers", "2", "--frames", "4", "--gen", "g2"],                   # has macroblocks with an inherited prediction
+    # Intra4x4 macroblocks inside base-layer P pictures: the enhancement layers derive motion from the lower-case vector such a macroblock kept from its last
+    # inter commit (host/hlb200_glue.c: glue_apply); both differed through the whole glue before that was reproduced
+    "g2_i4_in_p_2layer": ["--size", "64", "64", "--layers", "2", "--frames", "4", "--gen", "g2", "--seed", "8931", "--qp", "29"],
+    "g2_i4_in_p_3layer": ["--size", "48", "16", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "1865", "--qp", "22"],
 }
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "svc_bitstream.json")
 

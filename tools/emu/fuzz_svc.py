@@ -78,14 +78,15 @@ for case in range(first, first + n_cases):
                 md5 += ", whole glue %s" % ("FAILED" if gj["md5"] == "failed" else "different")
                 n_full_diff += 1
                 full_diff.append(case)
+                ok = False
     print("case %d: %s -> %s (%d macroblocks, %d skipped)%s" % (case, " ".join(args), "OK" if ok else "MISMATCH", mbs, skipped, md5), flush=True)
     bad += not ok
     n_mb += mbs
     n_skip += skipped
     os.remove(tr)
 if n_full or n_full_diff:
-    # informational: above Intra4x4 macroblocks of base-layer P pictures the reference derives enhancement motion from search leftovers the device does not
-    # report (host/hlb200_glue.c: glue_apply), so the whole-glue bitstream may differ there; a FAILED run is a bug
+    # above Intra4x4 macroblocks of base-layer P pictures the reference derives enhancement motion from the vector the base macroblock kept from its last inter
+    # commit (host/hlb200_glue.c: glue_apply reproduces that); seeds 1-400: 0 different
     print("whole glue (base layer through the slice kernel's source too): %d bitstreams equal, %d different %s" % (n_full, n_full_diff, full_diff))
 print("%d cases, %d mismatches, %d macroblocks compared, %d skipped (inherit scratch memory of an earlier picture), %d bitstream MD5 comparisons" % (n_cases, bad, n_mb, n_skip, n_md5))
 sys.exit(1 if bad else 0)
