@@ -209,10 +209,12 @@ def _random_case(rng, w, h, far_every=0):
             sc[y // 2:y // 2 + 8, x // 2:x // 2 + 8] = rc[y // 2:y // 2 + 8, x // 2:x // 2 + 8]
             if rng.random() < 0.5:
                 sc[y // 2:y // 2 + 4, x // 2:x // 2 + 4] += 9          # one block with a DC-only difference: its three neighbours read their stale AC levels
+    sources = set()
     for a in rng.integers(1, nmb, max(1, nmb // 8)):           # macroblocks that inherit the prediction of an earlier one (never of another inheriting one)
         b = int(rng.integers(0, a))
-        if not (m["pad"][b][0] & 1):
+        if not (m["pad"][b][0] & 1) and int(a) not in sources:   # (a macroblock somebody inherits from must keep its own partitions)
             m["pad"][a] = (1, b & 255, b >> 8)
+            sources.add(b)
     st = np.zeros(nmb, SVC_STATE)
     st["chroma_ac_level"][:, :, :, :15] = rng.integers(-2, 3, (nmb, 2, 4, 15)) * (rng.random((nmb, 2, 4, 15)) < 0.2)
     st["chroma_dc_level"] = rng.integers(-3, 4, (nmb, 2, 4))
