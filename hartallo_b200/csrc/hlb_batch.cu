@@ -447,6 +447,43 @@ int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u
                       d_recon_y, d_recon_u, d_recon_v, cuda_stream);
 }
 
+// Intra_Base resampling (hlb_svc.cuh: svc_resample_px): one thread = four horizontally adjacent output samples of one plane, stored as one word;
+// blockIdx.y = picture, blockIdx.z = plane (Y, Cb, Cr).  Reads of the (four times smaller) reference plane go through the read-only path.
+__global__ void __launch_bounds__(256) k_svc_resample_intra(const uint8_t* __restrict__ ref_y, const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int refW,
+                                                            int refH, uint8_t* __restrict__ out_y, uint8_t* __restrict__ out_u, uint8_t* __restrict__ out_v, int W, int H,
+                                                            size_t ref_frame_stride, size_t frame_stride)
+{
+    const int plane = blockIdx.z, chroma = plane != 0;
+    const int w = W >> chroma, h = H >> chroma, rw = refW >> chroma, rh = refH >> chroma, wq = w >> 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= wq * h) return;
+    const int y = t / wq, x0 = (t - y * wq) * 4;
+    const uint8_t* ref = (plane == 0 ? ref_y : (plane == 1 ? ref_u : ref_v)) + (size_t)blockIdx.y * ref_frame_stride;
+    uint8_t* out = (plane == 0 ? out_y : (plane == 1 ? out_u : out_v)) + (size_t)blockIdx.y * frame_stride;
+    const SvcRsAxis ax = svc_rs_axis(rw, w), ay = svc_rs_axis(rh, h);
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) word |= (uint32_t)svc_resample_px(ref, rw, rh, ax, ay, x0 + i, y, chroma != 0) << (8 * i);
+    *reinterpret_cast<uint32_t*>(out + (size_t)y * w + x0) = word;
+}
+
+int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d_ref_u, const uint8_t* d_ref_v, int ref_width, int ref_height, uint8_t* d_pred_y,
+                                        uint8_t* d_pred_u, uint8_t* d_pred_v, int width, int height, int n_pics, size_t ref_frame_stride, size_t frame_stride, int level_idc,
+                                        void* cuda_stream)
+{
+    // level_idc > 30 selects another fixed-point precision ((G-43): shift = 31 - ceil(log2(refW))) for which there is no reference behaviour to compare with
+    // (the reference's int32 arithmetic overflows there): parity unpinned, refused
+    if (!d_ref_y || !d_ref_u || !d_ref_v || !d_pred_y || !d_pred_u || !d_pred_v || ref_width < 16 || ref_height < 16 || (ref_width & 15) || (ref_height & 15) || width < ref_width ||
+        height < ref_height || (width & 15) || (height & 15) || width > 8 * ref_width || height > 8 * ref_height || width > 8192 || height > 8192 || n_pics < 1 || n_pics > 65535 ||
+        level_idc < 0 || level_idc > 30 || (frame_stride & 3) || (((uintptr_t)d_pred_y | (uintptr_t)d_pred_u | (uintptr_t)d_pred_v) & 3))
+        return HLB200_ERR_INVALID_PARAMETER;
+    const int words = (width >> 2) * height;
+    k_svc_resample_intra<<<dim3((words + 255) / 256, n_pics, 3), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, d_ref_u, d_ref_v, ref_width, ref_height, d_pred_y, d_pred_u, d_pred_v,
+                                                                                                      width, height, ref_frame_stride, frame_stride);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+
 int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream)
 {
     if (!d_a || !d_b || !d_out || (width & 3) || (height & 3)) return HLB200_ERR_INVALID_PARAMETER;

@@ -334,4 +334,53 @@ HLB_HD unsigned svc_luma_cbp(const SvcXchg& X)
     return m;
 }
 
+// ---- Intra_Base resampling: the I_BL prediction of an enhancement-layer I picture from the reference layer's reconstruction (first half) ----
+// _hl_codec_264_decode_svc_resample_intra_colour_comps decode_svc.c:2864 -> array construction :2952 (in an I picture every reference macroblock is intra: the
+// array is a clamped gather, (G-280)/(G-281)) -> _hl_codec_264_decode_svc_interpol_intra_base :3071 (vertical pass (G-301), horizontal pass + clip (G-305);
+// chroma always takes the two-tap table, :3116,:3150), sample locations by utils.c:1064-1157 (G.6.3) for frame macroblocks, no cropping, chroma phases 0
+// (sps.c:810-813), level_idc <= 30 (shift 16, (G-43)).  The reference's per-macroblock window offsets are multiples of 16 samples, so the result is a function of
+// the plane position only: one output sample per call, no state.
+struct SvcRsAxis { int scale, add; };   // (G-45), (G-48) with shift = 16
+HLB_HD SvcRsAxis svc_rs_axis(int refDim, int scaledDim)
+{
+    SvcRsAxis a;
+    a.scale = ((refDim << 16) + (scaledDim >> 1)) / scaledDim;
+    a.add = (((refDim * 2) << 14) + (scaledDim >> 1)) / scaledDim + (1 << 11);
+    return a;
+}
+HLB_HD int svc_rs_ref16(int p, const SvcRsAxis& a) { return ((p * a.scale + a.add) >> 12) - 8; }   // (G-59)/(G-60), deltaX = 8
+
+// Table G-9 (tables.h:626-643), 4 signed bytes per phase packed low byte first; chroma: {32 - 2p, 2p} (tables.h:647-664)
+HLB_TABLE static const uint32_t kSvcRsLuma[16] = { 0x00002000u, 0xFF0220FFu, 0xFF041FFEu, 0xFF061EFDu, 0xFF081CFDu, 0xFF0B1AFCu, 0xFE0E18FCu, 0xFD1016FDu,
+                                                   0xFD1313FDu, 0xFD1610FDu, 0xFC180EFEu, 0xFC1A0BFFu, 0xFD1C08FFu, 0xFD1E06FFu, 0xFE1F04FFu, 0xFF2002FFu };
+HLB_HD int svc_rs_luma_tap(uint32_t packed, int k) { return (int)(int8_t)(packed >> (8 * k)); }
+
+HLB_HD uint8_t svc_resample_px(const uint8_t* ref, int refW, int refH, const SvcRsAxis& ax, const SvcRsAxis& ay, int x, int y, bool chroma)
+{
+    const int x16 = svc_rs_ref16(x, ax), y16 = svc_rs_ref16(y, ay), xr = x16 >> 4, xp = x16 & 15, yr = y16 >> 4, yp = y16 & 15;
+    int v = 0;
+    if (chroma) {
+        const uint8_t* r0 = ref + clip3(0, refH - 1, yr) * refW;
+        const uint8_t* r1 = ref + clip3(0, refH - 1, yr + 1) * refW;
+        const int xa = clip3(0, refW - 1, xr), xb = clip3(0, refW - 1, xr + 1);
+        const int t0 = (32 - 2 * yp) * (int)HLB_LDG(r0 + xa) + 2 * yp * (int)HLB_LDG(r1 + xa);
+        const int t1 = (32 - 2 * yp) * (int)HLB_LDG(r0 + xb) + 2 * yp * (int)HLB_LDG(r1 + xb);
+        v = (32 - 2 * xp) * t0 + 2 * xp * t1;
+    }
+    else {
+        int t[4] = {0, 0, 0, 0};
+        const uint32_t fy = kSvcRsLuma[yp], fx = kSvcRsLuma[xp];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint8_t* row = ref + clip3(0, refH - 1, yr - 1 + k) * refW;
+            const int f = svc_rs_luma_tap(fy, k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] += f * (int)HLB_LDG(row + clip3(0, refW - 1, xr - 1 + j));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v += svc_rs_luma_tap(fx, j) * t[j];
+    }
+    return (uint8_t)clip255((v + 512) >> 10);
+}
+
 }  // namespace hlb

@@ -21,6 +21,7 @@
  *                              _hl_codec_264_rdo_mb_reconstruct_chroma rdo.c:2502 (whole-frame batch)
  *   hlb200_dev_svc_inter_recon_batch  hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 (SVC enhancement layer, base-mode inter
  *                              macroblocks: prediction + residual coding + reconstruction fused, whole-picture batch)
+ *   hlb200_dev_svc_resample_intra_batch  _hl_codec_264_decode_svc_resample_intra_colour_comps decode_svc.c:2864 (Intra_Base resampling, I pictures)
  *   hlb200_dev_svc_bl_recon_batch     hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301 (I_BL macroblocks: residual coding + reconstruction
  *                              against the host-resampled base layer)
  *   hlb200_sad4x4/satd4x4      hl_math_sad4x4_u8 source/hl_math.c:239, hl_math_satd4x4_u8 hl_math.c:283 (whole-frame batch)
@@ -243,6 +244,16 @@ HLB200_API int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8
                                              const uint8_t* d_pred_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
                                              hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs, uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v,
                                              void* cuda_stream);
+/* Intra_Base resampling for enhancement-layer I pictures (first half) -- _hl_codec_264_decode_svc_resample_intra_colour_comps,
+ * source/h264/hl_codec_264_decode_svc.c:2864-3200 with the sample locations of utils.c:1064-1157 (G.6.3, G.8.6.2): the reference layer's reconstruction
+ * (ref_width x ref_height, tight planes, n_pics pictures ref_frame_stride bytes apart) is resampled into the prediction planes of the current layer
+ * (width x height, frame_stride bytes apart, multiple of 4) that hlb200_dev_svc_bl_recon_batch consumes -- the planes the reference builds macroblock by macroblock
+ * on the host.  Valid for pictures whose reference-layer macroblocks are all intra (I pictures: the only case the reference's encoder uses it for), frame
+ * macroblocks, no cropping offsets, chroma phases as the reference's SPS writes them (sps.c:810-813), level_idc <= 30 (the fixed-point precision of (G-43);
+ * larger values return HLB200_ERR_INVALID_PARAMETER: no reference behaviour to pin them on). */
+HLB200_API int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d_ref_u, const uint8_t* d_ref_v, int ref_width, int ref_height,
+                                                   uint8_t* d_pred_y, uint8_t* d_pred_u, uint8_t* d_pred_v, int width, int height, int n_pics, size_t ref_frame_stride,
+                                                   size_t frame_stride, int level_idc, void* cuda_stream);
 HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
 HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n,
                                   hlb200_me_cost_t* d_out, void* cuda_stream);

@@ -545,3 +545,62 @@ HLO_API int hlo_predict_recon_mbs(const uint8_t* src_yuv, const uint8_t* ref_yuv
     }
     return nz;
 }
+
+/* ---- SVC: resampling of the reference layer's reconstruction into the Intra_Base (I_BL) prediction of an enhancement-layer I picture ----
+ * _hl_codec_264_decode_svc_resample_intra_colour_comps decode_svc.c:2864 -> ..._ref_layer_array_construct_prior_to_intra_resampling :2952 (G.8.6.2.2; every
+ * reference macroblock of an I picture is intra, so every sample is available and the array is a clamped gather, (G-280)/(G-281)) -> ..._interpol_intra_base :3071
+ * (G.8.6.2.3: vertical pass (G-301) then horizontal pass + clip (G-305); chroma takes the two-tap table whatever filteringModeFlag says, :3116,:3150), with the
+ * sample locations of hl_codec_264_utils_derivation_process_for_ref_layer_sample_locs_in_resampling_svc utils.c:1064-1157 (G.6.3) for frame macroblocks, no
+ * cropping offsets, chroma phases as the encoder's SPS sets them (sps.c:810-813: phaseX = phaseY = refPhaseX = refPhaseY = 0).  The reference works per macroblock
+ * on a local window; window offsets (G-270..G-273) are multiples of 16 samples, so phases and absolute positions do not depend on the macroblock and the process is a
+ * function of the plane.  Tables: include/hartallo/h264/hl_codec_264_tables.h:624-664 (Table G-9 luma; bilinear chroma). */
+static const int8_t kSvcLumaF[16][4] = { {0, 32, 0, 0}, {-1, 32, 2, -1}, {-2, 31, 4, -1}, {-3, 30, 6, -1}, {-3, 28, 8, -1}, {-4, 26, 11, -1}, {-4, 24, 14, -2},
+    {-3, 22, 16, -3}, {-3, 19, 19, -3}, {-3, 16, 22, -3}, {-2, 14, 24, -4}, {-1, 11, 26, -4}, {-1, 8, 28, -3}, {-1, 6, 30, -3}, {-1, 4, 31, -2}, {-1, 2, 32, -1} };
+
+static int svc_ceil_log2(int v) { int n = 0; while ((1 << n) < v) ++n; return n; }
+
+/* (G-43)..(G-49),(G-59): 1/16-sample position in the reference plane of sample p of the current plane */
+static int svc_ref16(int p, int refDim, int scaledDim, int level_idc)
+{
+    const int shift = level_idc <= 30 ? 16 : 31 - svc_ceil_log2(refDim);
+    const int scale = ((refDim << shift) + (scaledDim >> 1)) / scaledDim;
+    const int add = (((refDim * 2) << (shift - 2)) + (scaledDim >> 1)) / scaledDim + (1 << (shift - 5));
+    return ((p * scale + add) >> (shift - 4)) - 8;
+}
+
+/* one plane: ref is refW x refH, out is W x H (both tight); chroma != 0 selects the two-tap filter */
+HLO_API void hlo_svc_resample_intra_plane(const uint8_t* ref, int refW, int refH, int W, int H, int chroma, int level_idc, uint8_t* out)
+{
+    int x, y, k, j;
+    for (y = 0; y < H; ++y) {
+        const int y16 = svc_ref16(y, refH, H, level_idc), yr = y16 >> 4, yp = y16 & 15;
+        for (x = 0; x < W; ++x) {
+            const int x16 = svc_ref16(x, refW, W, level_idc), xr = x16 >> 4, xp = x16 & 15;
+            int v = 0;
+            if (chroma) {
+                for (j = 0; j < 2; ++j) {
+                    int t = 0;
+                    for (k = 0; k < 2; ++k) t += (k ? 2 * yp : 32 - 2 * yp) * ref[clip3(0, refH - 1, yr + k) * refW + clip3(0, refW - 1, xr + j)];
+                    v += (j ? 2 * xp : 32 - 2 * xp) * t;
+                }
+            }
+            else {
+                for (j = 0; j < 4; ++j) {
+                    int t = 0;
+                    for (k = 0; k < 4; ++k) t += kSvcLumaF[yp][k] * ref[clip3(0, refH - 1, yr - 1 + k) * refW + clip3(0, refW - 1, xr - 1 + j)];
+                    v += kSvcLumaF[xp][j] * t;
+                }
+            }
+            out[y * W + x] = (uint8_t)clip3(0, 255, (v + 512) >> 10);
+        }
+    }
+}
+
+/* whole picture, tight Y|U|V in and out (4:2:0) */
+HLO_API void hlo_svc_resample_intra_yuv(const uint8_t* ref_yuv, int refW, int refH, int W, int H, int level_idc, uint8_t* out_yuv)
+{
+    const int rc = (refW >> 1) * (refH >> 1), oc = (W >> 1) * (H >> 1);
+    hlo_svc_resample_intra_plane(ref_yuv, refW, refH, W, H, 0, level_idc, out_yuv);
+    hlo_svc_resample_intra_plane(ref_yuv + refW * refH, refW >> 1, refH >> 1, W >> 1, H >> 1, 1, level_idc, out_yuv + W * H);
+    hlo_svc_resample_intra_plane(ref_yuv + refW * refH + rc, refW >> 1, refH >> 1, W >> 1, H >> 1, 1, level_idc, out_yuv + W * H + oc);
+}

@@ -41,3 +41,12 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_recon_batch(int bl
     }
     return HLB200_OK;
 }
+
+// CPU run of svc_resample_px (the body of k_svc_resample_intra): one plane, host pointers
+extern "C" __attribute__((visibility("default"))) int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma)
+{
+    const hlb::SvcRsAxis ax = hlb::svc_rs_axis(refW, W), ay = hlb::svc_rs_axis(refH, H);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) out[y * W + x] = hlb::svc_resample_px(ref, refW, refH, ax, ay, x, y, chroma != 0);
+    return HLB200_OK;
+}

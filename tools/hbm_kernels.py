@@ -43,8 +43,11 @@ for n in [int(a) for a in (sys.argv[1:] or ["1", "8", "32", "128"])]:
         "tq_recon": lambda: lib.hlb200_dev_tq_recon_batch(s, s + ysz, s + ysz + csz, p, p + ysz, p + ysz + csz, W, H, n, fb, QP, 0, coef.data_ptr(), r, r + ysz, r + ysz + csz, sp),
         "svc_inter_recon": lambda: lib.hlb200_dev_svc_inter_recon_batch(s, s + ysz, s + ysz + csz, b, b + ysz, b + ysz + csz, W, H, n, fb, QP, 0, motion.data_ptr(), state.data_ptr(),
                                                                         coef.data_ptr(), r, r + ysz, r + ysz + csz, sp),
+        # Intra_Base resampling: the first quarter of each reference picture's bytes stands in for a (W/2 x H/2) reference-layer picture
+        "svc_resample_intra": lambda: lib.hlb200_dev_svc_resample_intra_batch(b, b + ysz // 4, b + ysz // 4 + csz // 4, W // 2, H // 2, p, p + ysz, p + ysz + csz, W, H, n, fb, fb, 0, sp),
     }
-    alg = {"interp_luma": 512, "interp_chroma": 256, "tq_recon": 1920, "svc_inter_recon": 1920}
+    # algorithmic bytes per macroblock; resampling: 96 B of the reference layer read + 384 B of prediction written
+    alg = {"interp_luma": 512, "interp_chroma": 256, "tq_recon": 1920, "svc_inter_recon": 1920, "svc_resample_intra": 480}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {"pictures_per_launch": n, "peak_gbs": PEAK, "peak_kind": PEAK_KIND, "kernels": {}}
     for name, k in ks.items():
