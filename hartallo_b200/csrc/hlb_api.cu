@@ -205,6 +205,38 @@ int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp
     return HLB200_OK;
 }
 
+// An I picture of an SVC enhancement layer with the Intra_Base resampling on the device as well (first half): the caller hands over the reference
+// layer's reconstruction (ref_width x ref_height, a quarter of the samples at the dyadic ratio) instead of the full-size prediction planes it would otherwise have to
+// build macroblock by macroblock (rdo.c:363-377 -> decode_svc.c:2864); k_svc_resample_intra fills the context's prediction planes, k_svc_inter_recon<true> codes the
+// picture against them.  Same results as hlb200_svc_layer_picture(ref_slot = -1) with host-resampled planes.
+int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* c, int cur_slot, int qp, int chroma_qp_index_offset, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v,
+                                       int ref_width, int ref_height, int level_idc, hlb200_mb_coeffs_t* out_coeffs)
+{
+    if (!c || cur_slot < 0 || cur_slot >= c->nslots || !out_coeffs || qp < 0 || qp > 51 || !ref_y || !ref_u || !ref_v || ref_width < 16 || ref_height < 16 || (ref_width & 15) ||
+        (ref_height & 15) || ref_width > c->width || ref_height > c->height)
+        return HLB200_ERR_INVALID_PARAMETER;
+    const size_t cbytes = (sizeof(hlb200_mb_coeffs_t) * c->nmb + 255) & ~(size_t)255, rys = (size_t)ref_width * ref_height, rcs = rys >> 2;
+    int rc = ensure_scratch(c, cbytes + rys + 2 * rcs);
+    if (rc) return rc;
+    if (!c->d_svc_state) {
+        HLB_CUDA(cudaMalloc(&c->d_svc_state, sizeof(hlb200_svc_mb_state_t) * c->nmb));
+        HLB_CUDA(cudaMemsetAsync(c->d_svc_state, 0, sizeof(hlb200_svc_mb_state_t) * c->nmb, c->stream));
+    }
+    hlb200_mb_coeffs_t* d_coeffs = (hlb200_mb_coeffs_t*)c->d_scratch;
+    uint8_t* d_ref = (uint8_t*)c->d_scratch + cbytes;
+    if ((rc = h2d(c, d_ref, ref_y, rys)) || (rc = h2d(c, d_ref + rys, ref_u, rcs)) || (rc = h2d(c, d_ref + rys + rcs, ref_v, rcs))) return rc;
+    if ((rc = hlb200_dev_svc_resample_intra_batch(d_ref, d_ref + rys, d_ref + rys + rcs, ref_width, ref_height, c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, 1, 0, 0,
+                                                  level_idc, c->stream)))
+        return rc;
+    if ((rc = hlb200_dev_svc_bl_recon_batch(c->d_src_cur[0], c->d_src_cur[1], c->d_src_cur[2], c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, 1, 0, qp,
+                                            chroma_qp_index_offset, (hlb200_svc_mb_state_t*)c->d_svc_state, d_coeffs, c->d_slot[cur_slot][0], c->d_slot[cur_slot][1],
+                                            c->d_slot[cur_slot][2], c->stream)))
+        return rc;
+    if ((rc = d2h(c, out_coeffs, d_coeffs, sizeof(hlb200_mb_coeffs_t) * c->nmb))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
 // ---- host-buffer batch wrappers -----------------------------------------------------------------------------------
 int hlb200_interp_luma(hlb200_ctx_t* c, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y)
 {

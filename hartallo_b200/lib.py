@@ -63,6 +63,7 @@ def load():
         "hlb200_dev_tq_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp], "hlb200_dev_sad4x4": [vp, vp, ip, ip, ip, vp, vp],
         "hlb200_dev_svc_inter_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp, vp],
         "hlb200_svc_layer_picture": [vp, ip, ip, ip, ip, vp, vp, vp, vp, vp],
+        "hlb200_svc_layer_picture_resampled": [vp, ip, ip, ip, vp, vp, vp, ip, ip, ip, vp],
         "hlb200_dev_svc_resample_intra_batch": [vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, C.c_size_t, C.c_size_t, ip, vp],
         "hlb200_dev_svc_bl_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp],
         "hlb200_dev_me_cost": [vp, vp, ip, ip, ip, vp, ip, vp, vp], "hlb200_dev_int_alu_probe": [ip, ip, vp, vp, C.POINTER(C.c_uint64)],
@@ -161,6 +162,16 @@ class Stream:
             m = np.ascontiguousarray(motion)
             rc = self.lib.hlb200_svc_layer_picture(self.ctx, ref_slot, cur_slot, qp, chroma_qp_index_offset, ptr(m), None, None, None, ptr(coeffs))
         check(rc, "svc_layer_picture")
+        return coeffs, self.download_slot(cur_slot)
+
+    def svc_layer_picture_resampled(self, qp, ref_layer_yuv, ref_w, ref_h, cur_slot=1, chroma_qp_index_offset=0, level_idc=0):
+        """an I picture of an SVC enhancement layer, Intra_Base resampling on the device too: ref_layer_yuv = the reference layer's reconstruction (tight Y|U|V)"""
+        coeffs = np.zeros(self.nmb, MB_COEFFS)
+        r = np.ascontiguousarray(ref_layer_yuv, np.uint8)
+        ys, cs = ref_w * ref_h, ref_w * ref_h // 4
+        ry, ru, rv = np.ascontiguousarray(r[:ys]), np.ascontiguousarray(r[ys:ys + cs]), np.ascontiguousarray(r[ys + cs:ys + 2 * cs])
+        check(self.lib.hlb200_svc_layer_picture_resampled(self.ctx, cur_slot, qp, chroma_qp_index_offset, ptr(ry), ptr(ru), ptr(rv), ref_w, ref_h, level_idc, ptr(coeffs)),
+              "svc_layer_picture_resampled")
         return coeffs, self.download_slot(cur_slot)
 
     def sad4x4(self, pred_y, satd=False):

@@ -226,13 +226,31 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     const size_t ysz = (size_t)W * H, csz = (size_t)Wc * Hc;
     glue_svc_layer_t* L;
     HL_ERROR_T err;
-    int rc, qp = -1, x, y, last_with_parts = -1;
+    int rc, qp = -1, x, y, last_with_parts = -1, dev_rs = 0, level_idc = 0;
     uint32_t addr;
     static HL_ALIGNED(16) int32_t pl[16][16], pcb[16][16], pcr[16][16];
 
     if (li <= 0 || li >= GLUE_SVC_MAX_LAYERS || (p_codec->layers.currDQId & 15) || p_esd->i_mb_start != 0 || p_esd->i_mb_end != (int32_t)hdr->PicSizeInMbs) {
         HL_DEBUG_ERROR("hlb200: only single-slice spatial enhancement layers are supported by the device path");
         return HL_ERROR_NOT_IMPLEMENTED;
+    }
+    /* I pictures: the Intra_Base resampling (rdo.c:363-377 -> decode_svc.c:2864) runs on the device too when the picture is inside what
+     * hlb200_dev_svc_resample_intra_batch is pinned for (frame macroblocks, no cropping offsets, the chroma phases sps.c:810-813 writes, unconstrained resampling,
+     * level_idc <= 30 as utils.c:1075,1123 reads it); otherwise the host resamples macroblock by macroblock as before.  HLB200_GLUE_HOST_RESAMPLE=1 forces the host path. */
+    if (intra && !getenv("HLB200_GLUE_HOST_RESAMPLE")) {
+        const hl_codec_264_nal_sps_t* sps = hdr->pc_pps->pc_sps;
+        const hl_codec_264_layer_t* top = p_codec->layers.p_list[(p_codec->layers.currDQId >> 4) << 4];
+        /* Pictures of fewer than 64 macroblocks stay on the host path: the reference sizes its window array as PicSizeInMbs << 8 BYTES (layer.c:202) but fills it with
+         * refArrayW x refArrayH int32 (48x48 at the dyadic ratio, 64x64 at 1:1), so below 36 / 64 macroblocks it writes past the allocation and its prediction depends
+         * on the heap (traced: saturated rows in 96x32 pictures).  Only the reference's own function in the same process reproduces that. */
+        dev_rs = mbw * (H >> 4) >= 64 && pc_layer->pc_ref && pc_layer->pc_ref->pc_fs_curr && pc_layer->pc_ref->pc_fs_curr->p_pict && pc_layer->RefLayerFrameMbsOnlyFlag && sps->frame_mbs_only_flag &&
+                 !hdr->field_pic_flag && sps->ChromaArrayType == 1 && sps->p_svc && sps->p_svc->chroma_phase_x_plus1_flag == 1 && sps->p_svc->chroma_phase_y_plus1 == 1 &&
+                 hdr->ext.svc.ref_layer_chroma_phase_x_plus1_flag == 1 && hdr->ext.svc.ref_layer_chroma_phase_y_plus1 == 1 && !hdr->ext.svc.constrained_intra_resampling_flag &&
+                 hdr->ext.svc.ScaledRefLayerLeftOffset == 0 && hdr->ext.svc.ScaledRefLayerTopOffset == 0 && hdr->ext.svc.ScaledRefLayerPicWidthInSamplesL == W &&
+                 hdr->ext.svc.ScaledRefLayerPicHeightInSamplesL == H && top && top->pc_slice_hdr && top->pc_slice_hdr->pc_pps->pc_sps->level_idc <= 30 &&
+                 !(pc_layer->RefLayerPicWidthInSamplesL & 15) && !(pc_layer->RefLayerPicHeightInSamplesL & 15) && pc_layer->RefLayerPicWidthInSamplesL <= W &&
+                 pc_layer->RefLayerPicHeightInSamplesL <= H;
+        if (dev_rs) level_idc = (int)top->pc_slice_hdr->pc_pps->pc_sps->level_idc;
     }
     L = &g_svc[li];
     if (!L->ctx || L->w != W || L->h != H) {
@@ -257,7 +275,8 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
         if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;
         if (qp < 0) qp = p_mb->QPy;
         if (p_mb->QPy != qp) { HL_DEBUG_ERROR("hlb200: per-macroblock QP is not supported"); return HL_ERROR_NOT_IMPLEMENTED; }
-        if (intra) {
+        if (intra && dev_rs) L->valid[addr] = 1;
+        else if (intra) {
             if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 0, -1, 16, 16, pl))) return err;
             if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 0, 8, 8, pcb))) return err;
             if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 1, 8, 8, pcr))) return err;
@@ -294,7 +313,12 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     }
     /* (b) device: one call for the picture */
     if ((rc = hlb200_frame_upload(L->ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, Wc))) return glue_fail("hlb200_frame_upload", rc);
-    if (intra) rc = hlb200_svc_layer_picture(L->ctx, -1, 1, qp, hdr->pc_pps->chroma_qp_index_offset, NULL, L->pred, L->pred + ysz, L->pred + ysz + csz, L->coeffs);
+    if (intra && dev_rs) {
+        const hl_codec_264_pict_t* rp = pc_layer->pc_ref->pc_fs_curr->p_pict;   /* what decode_svc.c:2970 reads: the reference layer's reconstruction of this access unit */
+        rc = hlb200_svc_layer_picture_resampled(L->ctx, 1, qp, hdr->pc_pps->chroma_qp_index_offset, rp->pc_data_y, rp->pc_data_u, rp->pc_data_v,
+                                                (int)pc_layer->RefLayerPicWidthInSamplesL, (int)pc_layer->RefLayerPicHeightInSamplesL, level_idc, L->coeffs);
+    }
+    else if (intra) rc = hlb200_svc_layer_picture(L->ctx, -1, 1, qp, hdr->pc_pps->chroma_qp_index_offset, NULL, L->pred, L->pred + ysz, L->pred + ysz + csz, L->coeffs);
     else {
         /* the layer's reference picture travels from the host DPB every time: macroblocks the host coded itself (valid = 0) are part of it */
         const hl_codec_264_pict_t* ref = pc_layer->pobj_poc->RefPicList0[0] ? pc_layer->pobj_poc->RefPicList0[0]->p_pict : NULL;

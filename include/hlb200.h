@@ -198,6 +198,11 @@ HLB200_API int hlb200_slice_last_variant(void);   /* variant the most recent sli
  * carries from picture to picture lives in the context (hlb200_state_reset clears it). ---- */
 HLB200_API int hlb200_svc_layer_picture(hlb200_ctx_t* ctx, int ref_slot, int cur_slot, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion,
                                         const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v, hlb200_mb_coeffs_t* out_coeffs);
+/* The same for an I picture with the Intra_Base resampling on the device too (hlb200_dev_svc_resample_intra_batch below; decode_svc.c:2864-3200): the caller passes
+ * the reference layer's reconstruction (host planes, ref_width x ref_height) instead of full-size prediction planes.  Restrictions of that entry point apply
+ * (level_idc <= 30, no cropping offsets, the reference's chroma phases); callers fall back to hlb200_svc_layer_picture with host-resampled planes otherwise. */
+HLB200_API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* ctx, int cur_slot, int qp, int chroma_qp_index_offset, const uint8_t* ref_y, const uint8_t* ref_u,
+                                                  const uint8_t* ref_v, int ref_width, int ref_height, int level_idc, hlb200_mb_coeffs_t* out_coeffs);
 
 /* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
 HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);

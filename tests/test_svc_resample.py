@@ -104,6 +104,7 @@ def test_abi_arguments():
     assert l.hlb200_dev_svc_resample_intra_batch(4, 4, 4, 64, 48, 4, 4, 4, 128, 96, 1, 0, 0, 40, None) == inv
     assert l.hlb200_dev_svc_resample_intra_batch(4, 4, 4, 64, 48, 4, 4, 4, 128, 96, 2, 4608, 18433, 0, None) == inv
     assert l.hlb200_dev_svc_resample_intra_batch(4, 4, 4, 64, 48, 4, 4, 4, 128, 96, 0, 0, 0, 0, None) == inv
+    assert l.hlb200_svc_layer_picture_resampled(None, 1, 31, 0, 4, 4, 4, 64, 48, 0, 4) == inv     # no layer context
 
 
 def gpu_resample(bases, rsz, sz):
@@ -138,3 +139,21 @@ def test_gpu_vs_oracle_random(rsz, sz, n):
     got = gpu_resample(bases, rsz, sz)
     for i, b in enumerate(bases):
         assert np.array_equal(got[i], oracle_resample(b, rsz[0], rsz[1], sz[0], sz[1])), i
+
+
+@pytest.mark.gpu
+def test_gpu_layer_picture_resampled_vs_golden():
+    """hlb200_svc_layer_picture_resampled (what host/hlb200_glue.c calls for an enhancement-layer I picture): the fixture's layer-2 I picture from layer 1's
+    reconstruction must give the coefficients and the reconstruction the reference left, and exactly what the host-resampled entry point gives"""
+    from hartallo_b200 import lib as hl
+    base, (rw, rh), pred, (w, h) = golden_pair()
+    p = [q for q in svc_util.load_golden() if q["name"] == "g2_3layer.1"][0]
+    st = hl.Stream(w, h, 1)
+    st.upload_frame(p["src"])
+    coef, rec = st.svc_layer_picture_resampled(p["qp"], base, rw, rh)
+    st2 = hl.Stream(w, h, 1)
+    st2.upload_frame(p["src"])
+    coef2, rec2 = st2.svc_layer_picture(p["qp"], pred_yuv=pred)
+    assert coef.tobytes() == coef2.tobytes() and np.array_equal(rec, rec2)
+    assert svc_util.compare_picture(p, coef, rec, None, "GPU resampled layer picture") == (w // 16) * (h // 16)
+    st.close(); st2.close()

@@ -134,3 +134,17 @@ API int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, in
     else { ry = c->slot[ref_slot]; ru = ry + ysz; rv = ru + csz; }
     return svc_emu_recon_batch(ref_slot < 0, s, s + ysz, s + ysz + csz, ry, ru, rv, c->w, c->h, 1, 0, qp, off, motion, c->state, out, o, o + ysz, o + ysz + csz);
 }
+extern "C" int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma);
+API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* c, int cur_slot, int qp, int off, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v, int rw, int rh,
+                                           int level_idc, hlb200_mb_coeffs_t* out)
+{
+    if (level_idc > 30 || rw > c->w || rh > c->h) return HLB200_ERR_INVALID_PARAMETER;
+    const size_t ysz = (size_t)c->w * c->h, csz = ysz >> 2;
+    uint8_t* pred = (uint8_t*)malloc(ysz + 2 * csz);
+    svc_emu_resample_plane(ref_y, rw, rh, pred, c->w, c->h, 0);
+    svc_emu_resample_plane(ref_u, rw >> 1, rh >> 1, pred + ysz, c->w >> 1, c->h >> 1, 1);
+    svc_emu_resample_plane(ref_v, rw >> 1, rh >> 1, pred + ysz + csz, c->w >> 1, c->h >> 1, 1);
+    const int rc = hlb200_svc_layer_picture(c, -1, cur_slot, qp, off, nullptr, pred, pred + ysz, pred + ysz + csz, out);
+    free(pred);
+    return rc;
+}
