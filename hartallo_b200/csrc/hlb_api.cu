@@ -2,10 +2,12 @@
 // wrappers around the batch kernels.  No CPU fallback anywhere: a failing CUDA call is reported as an HL_ERROR_T value.
 #include <string.h>
 
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is resolved through the runtime, libcuda is not linked
+
 #include "hlb_common.cuh"
 
 namespace hlb {
-static thread_local char g_err[512] = "";
+thread_local char g_err[512] = "";
 void set_last_error(const char* what, cudaError_t e, const char* file, int line)
 {
     snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
@@ -24,6 +26,29 @@ static int ensure_scratch(hlb200_ctx* c, size_t bytes)
     c->d_scratch = nullptr; c->scratch_bytes = 0;
     HLB_CUDA(cudaMalloc(&c->d_scratch, bytes));
     c->scratch_bytes = bytes;
+    return HLB200_OK;
+}
+// TMA descriptors of the frame stores' luma planes: u8 tensor {W, H}, row pitch W, box HLB tile side x tile side, out-of-picture samples read as zero
+// (the kernel replicates the border samples itself, hlb_mbcore.cuh: phase_tile_load)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tile_maps(hlb200_ctx* c)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+    HLB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { snprintf(hlb::g_err, sizeof(hlb::g_err), "cuTensorMapEncodeTiled is not available in this driver"); return HLB200_ERR_SYSTEM; }
+    CUtensorMap maps[HLB200_MAX_REFS + 1];
+    for (int s = 0; s < c->nslots; ++s) {
+        const cuuint64_t dims[2] = {(cuuint64_t)c->width, (cuuint64_t)c->height}, strides[1] = {(cuuint64_t)c->width};
+        const cuuint32_t box[2] = {48, 48}, estr[2] = {1, 1};
+        const CUresult r = ((tmap_encode_fn)fn)(&maps[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_slot[s][0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(hlb::g_err, sizeof(hlb::g_err), "cuTensorMapEncodeTiled failed (%d) for a %dx%d plane", (int)r, c->width, c->height); return HLB200_ERR_SYSTEM; }
+    }
+    HLB_CUDA(cudaMalloc(&c->d_tmaps, sizeof(CUtensorMap) * (size_t)c->nslots));
+    HLB_CUDA(cudaMemcpy(c->d_tmaps, maps, sizeof(CUtensorMap) * (size_t)c->nslots, cudaMemcpyHostToDevice));
     return HLB200_OK;
 }
 static size_t plane_bytes(const hlb200_ctx* c, int p) { return p == 0 ? (size_t)c->width * c->height : (size_t)(c->width >> 1) * (c->height >> 1); }
@@ -86,6 +111,7 @@ int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out
     HLB_CUDA(cudaMalloc(&c->d_mbstate, mbstate_bytes(c->nmb)));
     int rc = slice_reset_state(c);
     if (rc) return rc;
+    if ((rc = make_tile_maps(c))) return rc;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
     return HLB200_OK;
 }
@@ -98,9 +124,11 @@ int hlb200_stream_destroy(hlb200_ctx_t* c)
         cudaFree(c->d_src[p]); cudaFree(c->d_pred[p]); cudaFree(c->d_tmp[p]);
         for (int s = 0; s < c->nslots; ++s) cudaFree(c->d_slot[s][p]);
     }
-    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_svc_state); cudaFree(c->d_sched); cudaFree(c->d_scratch);
+    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_svc_state); cudaFree(c->d_tmaps); cudaFree(c->d_sched); cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_jobs) cudaFreeHost(c->h_jobs);
+    if (c->ev_jobs) cudaEventDestroy(c->ev_jobs);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;

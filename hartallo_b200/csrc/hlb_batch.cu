@@ -3,6 +3,7 @@
 // independent ME candidate cost.  All are HBM-bound integer/byte kernels (no tensor cores: 4x4 butterflies are not
 // a dense contraction); one thread owns one 4x4 block in registers, one warp owns one (or two) macroblocks.
 #include "hlb_common.cuh"
+#include "hlb_fast.cuh"
 #include "hlb_svc.cuh"
 
 namespace hlb {
@@ -451,7 +452,7 @@ int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u
 // blockIdx.y = picture, blockIdx.z = plane (Y, Cb, Cr).  Reads of the (four times smaller) reference plane go through the read-only path.
 __global__ void __launch_bounds__(256) k_svc_resample_intra(const uint8_t* __restrict__ ref_y, const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int refW,
                                                             int refH, uint8_t* __restrict__ out_y, uint8_t* __restrict__ out_u, uint8_t* __restrict__ out_v, int W, int H,
-                                                            size_t ref_frame_stride, size_t frame_stride)
+                                                            size_t ref_frame_stride, size_t frame_stride, int level_idc)
 {
     const int plane = blockIdx.z, chroma = plane != 0;
     const int w = W >> chroma, h = H >> chroma, rw = refW >> chroma, rh = refH >> chroma, wq = w >> 2;
@@ -460,26 +461,27 @@ __global__ void __launch_bounds__(256) k_svc_resample_intra(const uint8_t* __res
     const int y = t / wq, x0 = (t - y * wq) * 4;
     const uint8_t* ref = (plane == 0 ? ref_y : (plane == 1 ? ref_u : ref_v)) + (size_t)blockIdx.y * ref_frame_stride;
     uint8_t* out = (plane == 0 ? out_y : (plane == 1 ? out_u : out_v)) + (size_t)blockIdx.y * frame_stride;
-    const SvcRsAxis ax = svc_rs_axis(rw, w), ay = svc_rs_axis(rh, h);
+    const SvcRsAxis ax = svc_rs_axis(rw, w, level_idc), ay = svc_rs_axis(rh, h, level_idc);
     uint32_t word = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) word |= (uint32_t)svc_resample_px(ref, rw, rh, ax, ay, x0 + i, y, chroma != 0) << (8 * i);
     *reinterpret_cast<uint32_t*>(out + (size_t)y * w + x0) = word;
 }
 
+static bool rs_ok(int dim, int level_idc) { return level_idc <= 30 || (dim & (dim - 1)) != 0; }   // host twin of svc_rs_precision_ok
 int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d_ref_u, const uint8_t* d_ref_v, int ref_width, int ref_height, uint8_t* d_pred_y,
                                         uint8_t* d_pred_u, uint8_t* d_pred_v, int width, int height, int n_pics, size_t ref_frame_stride, size_t frame_stride, int level_idc,
                                         void* cuda_stream)
 {
-    // level_idc > 30 selects another fixed-point precision ((G-43): shift = 31 - ceil(log2(refW))) for which there is no reference behaviour to compare with
-    // (the reference's int32 arithmetic overflows there): parity unpinned, refused
+    // level_idc > 30 selects another fixed-point precision ((G-43): shift = 31 - ceil(log2(refDim))); when a reference dimension (luma or chroma) is a power of two the
+    // reference's int32 `refDim << shift` overflows: no reference behaviour there, refused
     if (!d_ref_y || !d_ref_u || !d_ref_v || !d_pred_y || !d_pred_u || !d_pred_v || ref_width < 16 || ref_height < 16 || (ref_width & 15) || (ref_height & 15) || width < ref_width ||
         height < ref_height || (width & 15) || (height & 15) || width > 8 * ref_width || height > 8 * ref_height || width > 8192 || height > 8192 || n_pics < 1 || n_pics > 65535 ||
-        level_idc < 0 || level_idc > 30 || (frame_stride & 3) || (((uintptr_t)d_pred_y | (uintptr_t)d_pred_u | (uintptr_t)d_pred_v) & 3))
+        level_idc < 0 || !rs_ok(ref_width, level_idc) || !rs_ok(ref_height, level_idc) || !rs_ok(ref_width >> 1, level_idc) || !rs_ok(ref_height >> 1, level_idc) || (frame_stride & 3) || (((uintptr_t)d_pred_y | (uintptr_t)d_pred_u | (uintptr_t)d_pred_v) & 3))
         return HLB200_ERR_INVALID_PARAMETER;
     const int words = (width >> 2) * height;
     k_svc_resample_intra<<<dim3((words + 255) / 256, n_pics, 3), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, d_ref_u, d_ref_v, ref_width, ref_height, d_pred_y, d_pred_u, d_pred_v,
-                                                                                                      width, height, ref_frame_stride, frame_stride);
+                                                                                                      width, height, ref_frame_stride, frame_stride, level_idc);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
@@ -514,6 +516,88 @@ int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink, void* cuda
     k_int_alu_probe<<<blocks, 256, 0, (cudaStream_t)cuda_stream>>>(iters, d_sink);
     HLB_CUDA(cudaGetLastError());
     if (ops_out) *ops_out = (uint64_t)blocks * 256u * (uint64_t)iters * 32u;  // 16 adds + 16 xors per iteration
+    return HLB200_OK;
+}
+
+// ---- self-test of the packed formulations (hlb_fast.cuh) against the plain ones (hlb_prims.cuh) ON THE DEVICE: checks what the CPU check cannot, i.e. that the
+// hardware instructions behind the wrappers (IDP.4A.U8.S8, I2IP.SAT, VIADDMNMX.S16x2.RELU, PRMT, SHF.R.W, VABSDIFF4) do what their C++ twins do ----
+__global__ void __launch_bounds__(64) k_selftest_fast(int qp, unsigned seed, int* __restrict__ bad)
+{
+    __shared__ alignas(16) uint8_t tile[48 * 48 + 16];
+    __shared__ hlb::QuantK qk;
+    unsigned s = seed * 2654435761u + blockIdx.x * 40503u + 1u;
+    const int kind = blockIdx.x & 3;
+    for (int i = threadIdx.x; i < 48 * 48 + 16; i += blockDim.x) {
+        unsigned r = (s + (unsigned)i) * 1664525u + 1013904223u; r ^= r >> 13; r *= 2246822519u; r ^= r >> 16;
+        tile[i] = kind == 0 ? (uint8_t)r : kind == 1 ? (uint8_t)((r & 256) ? (r >> 9) % 34 : r) : kind == 2 ? (uint8_t)((r & 256) ? 255 : 0) : (uint8_t)(((r >> 9) & 7) == 0 ? ((r & 1) ? 255 : 0) : (r & 255));
+    }
+    if (threadIdx.x == 0) {
+        // the constants are computed on the host in the product (frame_ctx_derive); repeated here from the device tables as an independent derivation
+        const int r6 = qp % 6, q6 = qp / 6;
+        qk.qbits = 15 + q6; qk.f_pos = (1 << qk.qbits) / 6; qk.f_neg = (1 << qk.qbits) - 1 - qk.f_pos;
+        for (int c = 0; c < 3; ++c) { qk.mf[c] = hlb::kQuantMF[r6][c]; qk.dq_mul[c] = qp >= 24 ? (16 * hlb::kNormAdjust[r6][c]) << (q6 - 4) : 16 * hlb::kNormAdjust[r6][c]; }
+        qk.dq_shift = qp >= 24 ? 0 : 4 - q6; qk.dq_round = qp >= 24 ? 0 : 1 << (3 - q6);
+        const int lim = (1 << qk.qbits) - qk.f_pos - 1, t0 = lim / qk.mf[0], t1 = (lim / qk.mf[1]) / 4, t2 = (lim / qk.mf[2]) / 2;
+        qk.zero_sad = t0 < t1 ? (t0 < t2 ? t0 : t2) : (t1 < t2 ? t1 : t2);
+    }
+    __syncthreads();
+    unsigned r = (s ^ (threadIdx.x * 7919u)) * 1664525u + 1013904223u;
+    int nbad = 0;
+    for (int it = 0; it < 8; ++it) {
+        r = r * 1664525u + 1013904223u;
+        const int tx = 2 + (int)((r >> 8) % 39u), ty = 2 + (int)((r >> 16) % 39u);
+        for (int pos = 0; pos < 16; ++pos) {
+            const int xf = pos & 3, yf = pos >> 2;
+            uint8_t a[16];
+            hlb::interp_luma_4x4_unrolled(tile + ty * 48 + tx, 48, xf, yf, a);
+            const hlb::Rows4 b = hlb::fast_pred_luma((const uint32_t*)tile, 12, tx, ty, xf, yf);
+            bool ok = true;
+            for (int i = 0; i < 16; ++i) ok = ok && a[i] == (uint8_t)(b.r[i >> 2] >> (8 * (i & 3)));
+            nbad += !ok;
+            // trial encode of a source block (another place of the tile, or the prediction plus small noise) against this prediction
+            r = r * 1664525u + 1013904223u;
+            uint8_t sv[16];
+            const int sx = (int)((r >> 8) % 44u), sy = (int)((r >> 16) % 44u), mode = (r >> 28) & 3;
+            for (int i = 0; i < 16; ++i) {
+                unsigned q = (r + i * 2654435761u); q ^= q >> 15; q *= 2246822519u; q ^= q >> 13;
+                sv[i] = mode == 0 ? tile[(sy + (i >> 2)) * 48 + sx + (i & 3)] : (uint8_t)hlb::clip255((int)a[i] + (mode == 1 ? (int)(q % 5u) - 2 : mode == 2 ? (int)(q % 41u) - 20 : ((q & 15) == 0 ? 1 : 0)));
+            }
+            int m[16], lv[16];
+            uint32_t any = 0, mask = 0, ref;
+            for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)a[i]; any |= (uint32_t)m[i]; }
+            if (any) { hlb::fwd_transform4x4(m); hlb::quant4x4_ac(m, qp, false); hlb::zigzag4x4(m, lv); mask = hlb::level_mask16(lv); }
+            if (mask == 0) ref = (uint32_t)hlb::sad16(sv, a);
+            else {
+                const hlb::CavlcInfo ci = hlb::cavlc_block_info16(lv, mask);
+                int cc[16];
+                hlb::inv_zigzag4x4(lv, cc); hlb::dequant4x4(cc, qp, false); hlb::inv_transform4x4(cc);
+                uint8_t rec[16];
+                for (int i = 0; i < 16; ++i) rec[i] = (uint8_t)((int)a[i] + cc[i]);
+                ref = (uint32_t)hlb::sad16(sv, rec) | ((uint32_t)ci.bits_rest << 12) | ((uint32_t)ci.total_coeff << 22) | ((uint32_t)ci.trailing_ones << 27) | ((uint32_t)(ci.single_ctr & 3) << 29);
+            }
+            hlb::Rows4 sr;
+            for (int q = 0; q < 4; ++q) sr.r[q] = sv[4 * q] | (sv[4 * q + 1] << 8) | (sv[4 * q + 2] << 16) | ((uint32_t)sv[4 * q + 3] << 24);
+            const uint32_t got = hlb::fast_trial(sr, b, qk, false), cnt = hlb::fast_trial(sr, b, qk, true);
+            nbad += got != ref;
+            const int tc = (ref >> 22) & 31, t1 = (ref >> 27) & 3;
+            bool cok = (int)((cnt >> 22) & 31) == tc;
+            if (tc == 1) cok = cok && (int)((cnt >> 27) & 3) == t1 && (t1 != 1 || ((cnt >> 29) & 3) == ((ref >> 29) & 3));
+            nbad += !cok;
+        }
+    }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
+int hlb200_dev_selftest(int blocks, unsigned seed, int* mismatches_out)
+{
+    if (blocks <= 0 || !mismatches_out) return HLB200_ERR_INVALID_PARAMETER;
+    int* d_bad = nullptr;
+    HLB_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    HLB_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+    for (int qp = 12; qp <= 51; ++qp) k_selftest_fast<<<blocks, 64>>>(qp, seed + (unsigned)qp, d_bad);
+    HLB_CUDA(cudaGetLastError());
+    HLB_CUDA(cudaMemcpy(mismatches_out, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    HLB_CUDA(cudaFree(d_bad));
     return HLB200_OK;
 }
 

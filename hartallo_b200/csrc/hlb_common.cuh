@@ -10,6 +10,7 @@
 namespace hlb {
 
 void set_last_error(const char* what, cudaError_t e, const char* file, int line);
+extern thread_local char g_err[512];
 
 #define HLB_CUDA(expr)                                                     \
     do {                                                                   \
@@ -77,9 +78,13 @@ struct hlb200_ctx {
     void* h_pinned; size_t pinned_bytes;        // pinned staging
     struct hlb200_mb_record* d_records;
     void* d_mbstate;                            // per-MB state carried across MBs and frames
+    void* d_tmaps;                              // CUtensorMap[nslots] (device): 2D tile descriptors of the frame stores' luma planes for the slice kernel's TMA loads
     void* d_svc_state;                          // hlb200_svc_mb_state_t[nmb] when the context is an SVC enhancement layer (allocated on first use)
     void* d_sched; size_t sched_bytes;          // job descriptors + ready-queue scheduler words (hlb_slice.cu)
     void* h_jobs; int h_jobs_cap;               // pinned staging of the job descriptors
     int* last_sched;                            // scheduler words of the last launch (watchdog status)
+    struct hlb200_ctx* batch_owner;             // first context of the batch launch that last covered this context (owns the scheduler words)
+    int abort_state;                            // owner: -1 = not read back yet, 0 = the launch completed, > 0 = watchdog code
+    cudaEvent_t ev_jobs, ev_done;               // owner: job-array upload / launch completion; other contexts: ev_done orders their stream before the launch
     int frame_count;
 };

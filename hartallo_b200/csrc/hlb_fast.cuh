@@ -1,0 +1,358 @@
+// hlb_fast.cuh -- packed-byte formulations of the per-4x4-block primitives of the search (prediction, residual transform, quantisation,
+// trial reconstruction, SAD), written for the B200 integer pipes: rows of four samples stay packed in one register from the shared-memory
+// reference tile to the distortion, so that
+//   * windows are fetched as aligned 32-bit words + funnel shifts (SHF.R.W) instead of byte loads,
+//   * the 6-tap filter and the forward transform's row pass are byte dot products (IDP.4A.U8.S8: four multiply-adds per instruction),
+//   * vertical filters work on two samples per register (16-bit halves, VIADDMNMX.S16x2.RELU for the round-and-clip),
+//   * rounding + clipping + packing is one I2IP.U8.S32.SAT per two samples, averages are byte-parallel,
+//   * SAD is VABSDIFF4.U8.ACC (one instruction per row).
+// Arithmetic is the reference's, bit for bit (interpol.h:41-923, transf.c:716-768, quant.c:116-137, quant.c:68-111, transf.c:420-456,
+// hl_math.h:261,303-323, hl_math.c:239); tools/emu/check_fast.cpp checks every function against the plain formulations of hlb_prims.cuh
+// (which the oracle pins against the reference) on the CPU, hlb200_dev_selftest does the same on the device.
+#pragma once
+#include "hlb_prims.cuh"
+
+namespace hlb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// portable wrappers of the packed instructions (plain C++ when not compiling device code)
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD uint32_t p_shf_r(uint32_t lo, uint32_t hi, uint32_t sh)   // low word of (hi:lo) >> (sh & 31)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+HLB_HD uint32_t p_prmt(uint32_t a, uint32_t b, uint32_t sel)   // byte k of the result = byte (sel >> 4k) & 7 of (b:a)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xff) << (8 * k);
+    return r;
+#endif
+}
+HLB_HD int p_dp4a_us(uint32_t a_u8, uint32_t b_s8, int c)   // c + sum_k a.u8[k] * b.s8[k]
+{
+#if defined(__CUDA_ARCH__)
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8), "r"(b_s8), "r"(c));
+    return d;
+#else
+    for (int k = 0; k < 4; ++k) c += (int)((a_u8 >> (8 * k)) & 0xff) * (int)(int8_t)((b_s8 >> (8 * k)) & 0xff);
+    return c;
+#endif
+}
+HLB_HD uint32_t p_sad4(uint32_t a, uint32_t b, uint32_t c)   // c + sum_k |a.u8[k] - b.u8[k]|
+{
+#if defined(__CUDA_ARCH__)
+    return __vsadu4(a, b) + c;
+#else
+    for (int k = 0; k < 4; ++k) { const int d = (int)((a >> (8 * k)) & 0xff) - (int)((b >> (8 * k)) & 0xff); c += (uint32_t)(d < 0 ? -d : d); }
+    return c;
+#endif
+}
+HLB_HD uint32_t p_pack_sat_u8(int hi, int lo, uint32_t c)   // (sat_u8(hi) << 8 | sat_u8(lo)) | c << 16
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+    return d;
+#else
+    return ((uint32_t)clip255(hi) << 8) | (uint32_t)clip255(lo) | (c << 16);
+#endif
+}
+HLB_HD uint32_t p_addmin_relu_s16x2(uint32_t a, uint32_t b, uint32_t c)   // per signed 16-bit half: max(min(a + b, c), 0)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_s16x2_relu(a, b, c);
+#else
+    uint32_t r = 0;
+    for (int k = 0; k < 2; ++k) {
+        int v = (int)(int16_t)(uint16_t)((a >> (16 * k)) + (b >> (16 * k)));   // wraps like the instruction
+        const int m = (int16_t)(uint16_t)(c >> (16 * k));
+        v = v < m ? v : m;
+        v = v < 0 ? 0 : v;
+        r |= (uint32_t)(uint16_t)v << (16 * k);
+    }
+    return r;
+#endif
+}
+HLB_HD uint32_t p_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }                       // per byte (a + b + 1) >> 1
+HLB_HD uint32_t p_add4_wrap(uint32_t a, uint32_t b) { return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u); }   // per byte (a + b) mod 256
+HLB_HD uint32_t pack4_sat(int v0, int v1, int v2, int v3) { return p_pack_sat_u8(v1, v0, p_pack_sat_u8(v3, v2, 0)); }         // clip255 of each, v0 in the low byte
+
+// ------------------------------------------------------------------------------------------------------------------
+// window rows out of a byte tile addressed as 32-bit words (`t` 4-byte aligned, row pitch `pw` words)
+// ------------------------------------------------------------------------------------------------------------------
+// four samples starting at byte column c of row y
+HLB_HD uint32_t tile_row4(const uint32_t* t, int pw, int y, int c)
+{
+    const uint32_t* p = t + y * pw + (c >> 2);
+    return p_shf_r(p[0], p[1], (uint32_t)(c & 3) * 8);
+}
+// nine samples starting at byte column c of row y: R0 = samples 0..3, R1 = 4..7, R2 = sample 8 in its low byte (higher bytes unspecified)
+HLB_HD void tile_row9(const uint32_t* t, int pw, int y, int c, uint32_t& R0, uint32_t& R1, uint32_t& R2)
+{
+    const uint32_t* p = t + y * pw + (c >> 2);
+    const uint32_t sh = (uint32_t)(c & 3) * 8, w0 = p[0], w1 = p[1], w2 = p[2];
+    R0 = p_shf_r(w0, w1, sh); R1 = p_shf_r(w1, w2, sh); R2 = w2 >> sh;
+}
+
+// unrounded horizontal 6-tap values (+ acc) at the four positions whose window starts at samples 0..3 of (R0,R1,R2): tap6(b[x..x+5])
+#define HLB_TAP_A 0x1414FB01u   /* ( 1, -5, 20, 20) on window samples x   .. x+3 */
+#define HLB_TAP_B 0x000001FBu   /* (-5,  1,  0,  0) on window samples x+4 .. x+7 */
+HLB_HD void hrow_taps(uint32_t R0, uint32_t R1, uint32_t R2, int acc, int& v0, int& v1, int& v2, int& v3)
+{
+    v0 = p_dp4a_us(R1, HLB_TAP_B, p_dp4a_us(R0, HLB_TAP_A, acc));
+    v1 = p_dp4a_us(p_shf_r(R1, R2, 8), HLB_TAP_B, p_dp4a_us(p_shf_r(R0, R1, 8), HLB_TAP_A, acc));
+    v2 = p_dp4a_us(p_shf_r(R1, R2, 16), HLB_TAP_B, p_dp4a_us(p_shf_r(R0, R1, 16), HLB_TAP_A, acc));
+    v3 = p_dp4a_us(p_shf_r(R1, R2, 24), HLB_TAP_B, p_dp4a_us(p_shf_r(R0, R1, 24), HLB_TAP_A, acc));
+}
+// rounded horizontal half samples b of a row: clip255((tap6 + 16) >> 5), packed
+HLB_HD uint32_t half_h_row(uint32_t R0, uint32_t R1, uint32_t R2)
+{
+    int v0, v1, v2, v3;
+    hrow_taps(R0, R1, R2, 16, v0, v1, v2, v3);
+    return pack4_sat(v0 >> 5, v1 >> 5, v2 >> 5, v3 >> 5);
+}
+// rounded vertical half samples h of one row of four positions from the six packed rows e..j above / below it.  Two samples per register:
+// t = (E + J + K) + 20 (G + H) - 5 (F + I) with K = 2560 = 80 * 32 keeps both 16-bit halves non-negative (so plain 32-bit arithmetic never
+// borrows across them) and commutes with the >> 5; ((t + 16) >> 5) - 80 is then clamped to 0..255 by one VIADDMNMX.S16x2.RELU.
+HLB_HD uint32_t vtap_pair(uint32_t E, uint32_t F, uint32_t G, uint32_t H, uint32_t I, uint32_t J)
+{
+    const uint32_t t = (E + J + 0x0A000A00u) + 20u * (G + H) - 5u * (F + I);
+    const uint32_t r = ((t + 0x00100010u) >> 5) & 0x07FF07FFu;
+    return p_addmin_relu_s16x2(r, 0xFFB0FFB0u, 0x00FF00FFu);
+}
+HLB_HD uint32_t exp_lo(uint32_t r) { return p_prmt(r, 0, 0x4140); }   // samples 0,1 as 16-bit halves
+HLB_HD uint32_t exp_hi(uint32_t r) { return p_prmt(r, 0, 0x4342); }   // samples 2,3
+
+// ------------------------------------------------------------------------------------------------------------------
+// Luma prediction of one 4x4 block out of the reference tile (8.4.2.2.1): (tx,ty) = tile coordinates of integer sample G of the block's
+// pixel (0,0); the tile holds columns tx-2..tx+6 and rows ty-2..ty+6.  Returns the four rows packed.
+// ------------------------------------------------------------------------------------------------------------------
+HLB_INTERP_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
+{
+    Rows4 o;
+    if ((xf | yf) == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o.r[r] = tile_row4(t, pw, ty + r, tx);
+    } else if (yf == 0) {   // a b c
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t R0, R1, R2;
+            tile_row9(t, pw, ty + r, tx - 2, R0, R1, R2);
+            const uint32_t b = half_h_row(R0, R1, R2);
+            o.r[r] = xf == 2 ? b : p_avg4(p_shf_r(R0, R1, xf == 1 ? 16 : 24), b);
+        }
+    } else if (xf == 0) {   // d h n
+        uint32_t lo[9], hi[9], g[5];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t v = tile_row4(t, pw, ty - 2 + r, tx);
+            lo[r] = exp_lo(v); hi[r] = exp_hi(v);
+            if (r >= 2 && r < 7) g[r - 2] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t h = p_prmt(vtap_pair(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5]), vtap_pair(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5]), 0x6420);
+            o.r[r] = yf == 2 ? h : p_avg4(g[yf == 1 ? r : r + 1], h);
+        }
+    } else if ((xf & yf) & 1) {   // e g p r: average of b (row y or y+1) and h (column x or x+1)
+        const int cx = tx + (xf == 3 ? 1 : 0), ry = yf == 3 ? 1 : 0;
+        uint32_t lo[9], hi[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t v = tile_row4(t, pw, ty - 2 + r, cx);
+            lo[r] = exp_lo(v); hi[r] = exp_hi(v);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t R0, R1, R2;
+            tile_row9(t, pw, ty + r + ry, tx - 2, R0, R1, R2);
+            const uint32_t b = half_h_row(R0, R1, R2);
+            const uint32_t h = p_prmt(vtap_pair(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5]), vtap_pair(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5]), 0x6420);
+            o.r[r] = p_avg4(b, h);
+        }
+    } else {
+        // j, and f q (xf == 2: averaged with b of row y / y+1) or i k (yf == 2: averaged with h of column x / x+1): the nine rows of unrounded
+        // horizontal half samples stream through a six-row window
+        int w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) w0[x] = w1[x] = w2[x] = w3[x] = w4[x] = w5[x] = 0;
+        uint32_t j0 = 0, j1 = 0, j2 = 0, j3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        const int rb = yf == 3 ? 3 : 2;   // window row holding the horizontal half samples that f / q average with (row y / y+1)
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r) {
+            uint32_t R0, R1, R2;
+            tile_row9(t, pw, ty - 2 + r, tx - 2, R0, R1, R2);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { w0[x] = w1[x]; w1[x] = w2[x]; w2[x] = w3[x]; w3[x] = w4[x]; w4[x] = w5[x]; }
+            hrow_taps(R0, R1, R2, 0, w5[0], w5[1], w5[2], w5[3]);
+            if (r >= 5) {
+                int v[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) v[x] = (w0[x] + w5[x] + 512 - 5 * (w1[x] + w4[x]) + 20 * (w2[x] + w3[x])) >> 10;
+                j0 = j1; j1 = j2; j2 = j3; j3 = pack4_sat(v[0], v[1], v[2], v[3]);
+                if (xf == 2 && yf != 2) {
+                    b0 = b1; b1 = b2; b2 = b3;
+                    b3 = rb == 2 ? pack4_sat((w2[0] + 16) >> 5, (w2[1] + 16) >> 5, (w2[2] + 16) >> 5, (w2[3] + 16) >> 5)
+                                 : pack4_sat((w3[0] + 16) >> 5, (w3[1] + 16) >> 5, (w3[2] + 16) >> 5, (w3[3] + 16) >> 5);
+                }
+            }
+        }
+        o.r[0] = j0; o.r[1] = j1; o.r[2] = j2; o.r[3] = j3;
+        if (xf == 2) {
+            if (yf != 2) { o.r[0] = p_avg4(b0, j0); o.r[1] = p_avg4(b1, j1); o.r[2] = p_avg4(b2, j2); o.r[3] = p_avg4(b3, j3); }
+        } else {
+            const int cx = tx + (xf == 3 ? 1 : 0);
+            uint32_t lo[9], hi[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                const uint32_t v = tile_row4(t, pw, ty - 2 + r, cx);
+                lo[r] = exp_lo(v); hi[r] = exp_hi(v);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t h = p_prmt(vtap_pair(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5]), vtap_pair(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5]), 0x6420);
+                o.r[r] = p_avg4(h, o.r[r]);
+            }
+        }
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Quantiser constants of a picture (computed once per picture, host or device): the inter rounding offset of the search's trial encodes
+// ------------------------------------------------------------------------------------------------------------------
+struct QuantK {
+    int32_t qbits;        // 15 + QP / 6
+    int32_t f_pos;        // (1 << qbits) / 6: added to w * MF for w >= 0                      (quant.c:116-137)
+    int32_t f_neg;        // (1 << qbits) - 1 - f_pos: added to w * MF for w < 0, then an arithmetic shift gives -((|w| MF + f) >> qbits)
+    int32_t mf[3];        // by position class (even,even) / (odd,odd) / mixed
+    int32_t dq_mul[3];    // LevelScale4x4 by class, pre-shifted by QP/6 - 4 when QP >= 24           (quant.c:68-111)
+    int32_t dq_shift;     // QP < 24: (c * LevelScale + (1 << (3 - QP/6))) >> (4 - QP/6); else 0
+    int32_t dq_round;
+    int32_t zero_sad;     // a residual block whose SAD is <= this quantises to all-zero levels (see quantk_make); -1 = no shortcut
+};
+inline void quantk_make(QuantK& k, int qp)
+{
+    static const int MF[6][3] = {{13107, 5243, 8066}, {11916, 4660, 7490}, {10082, 4194, 6554}, {9362, 3647, 5825}, {8192, 3355, 5243}, {7282, 2893, 4559}};
+    static const int NA[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+    const int r = qp % 6, q6 = qp / 6;
+    k.qbits = 15 + q6;
+    k.f_pos = (1 << k.qbits) / 6;
+    k.f_neg = (1 << k.qbits) - 1 - k.f_pos;
+    for (int c = 0; c < 3; ++c) {
+        k.mf[c] = MF[r][c];
+        k.dq_mul[c] = qp >= 24 ? (16 * NA[r][c]) << (q6 - 4) : 16 * NA[r][c];
+    }
+    k.dq_shift = qp >= 24 ? 0 : 4 - q6;
+    k.dq_round = qp >= 24 ? 0 : 1 << (3 - q6);
+    // |W_ij| <= g_i g_j SAD with g = (1, 2, 1, 2) the largest magnitude in row i of the forward matrix; level_ij = 0 iff |W_ij| MF + f < 2^qbits.
+    // zero_sad = the largest SAD for which that holds for every class.
+    const int lim = (1 << k.qbits) - k.f_pos - 1;   // |W| * MF <= lim
+    const int t0 = lim / MF[r][0], t1 = (lim / MF[r][1]) / 4, t2 = (lim / MF[r][2]) / 2;
+    k.zero_sad = t0 < t1 ? (t0 < t2 ? t0 : t2) : (t1 < t2 ? t1 : t2);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One trial encode of a 4x4 block (me_ds.c:527-688 for one block): residual -> forward transform -> quantisation -> [CAVLC counts ->
+// de-quantisation -> inverse transform -> wrap-around reconstruction -> SAD].  Returns the memo word of me_phase_trial:
+// dist:12 | bits_rest:10 | TotalCoeff:5 | TrailingOnes:2 | lone-coefficient Single_ctr:2.  `counts_only`: the caller needs TotalCoeff /
+// TrailingOnes / Single_ctr but neither the distortion nor the bit count (searches that can no longer improve, see me_find_best_cost).
+// ------------------------------------------------------------------------------------------------------------------
+#define HLB_CF0 0x01010101u   /* ( 1,  1,  1,  1) */
+#define HLB_CF1 0xFEFF0102u   /* ( 2,  1, -1, -2) */
+#define HLB_CF2 0x01FFFF01u   /* ( 1, -1, -1,  1) */
+#define HLB_CF3 0xFF02FE01u   /* ( 1, -2,  2, -1) */
+#define HLB_NCF0 0xFFFFFFFFu
+#define HLB_NCF1 0x0201FFFEu
+#define HLB_NCF2 0xFF0101FFu
+#define HLB_NCF3 0x01FE02FFu
+HLB_HD uint32_t fast_trial(const Rows4& s, const Rows4& p, const QuantK& q, bool counts_only)
+{
+    uint32_t sad0 = p_sad4(s.r[0], p.r[0], 0);
+    sad0 = p_sad4(s.r[1], p.r[1], sad0); sad0 = p_sad4(s.r[2], p.r[2], sad0); sad0 = p_sad4(s.r[3], p.r[3], sad0);
+    if ((int)sad0 <= q.zero_sad) return sad0;   // every level is zero (and so is the block's residual when sad0 == 0)
+    // rows: (S - P) Cf^T as byte dot products; then columns: Cf (.)
+    int m[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        m[r * 4 + 0] = p_dp4a_us(s.r[r], HLB_CF0, p_dp4a_us(p.r[r], HLB_NCF0, 0));
+        m[r * 4 + 1] = p_dp4a_us(s.r[r], HLB_CF1, p_dp4a_us(p.r[r], HLB_NCF1, 0));
+        m[r * 4 + 2] = p_dp4a_us(s.r[r], HLB_CF2, p_dp4a_us(p.r[r], HLB_NCF2, 0));
+        m[r * 4 + 3] = p_dp4a_us(s.r[r], HLB_CF3, p_dp4a_us(p.r[r], HLB_NCF3, 0));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int a = m[j], b = m[4 + j], c = m[8 + j], d = m[12 + j];
+        const int s0 = a + d, s1 = b + c, d0 = a - d, d1 = b - c;
+        m[j] = s0 + s1; m[4 + j] = 2 * d0 + d1; m[8 + j] = s0 - s1; m[12 + j] = d0 - 2 * d1;
+    }
+    // quantisation: sign(w) * ((|w| MF + f) >> qbits) == (w MF + (w < 0 ? f_neg : f_pos)) >> qbits (arithmetic)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = pos_class(i, j);
+            const int t = m[i * 4 + j] * q.mf[c];
+            m[i * 4 + j] = (t + (t < 0 ? q.f_neg : q.f_pos)) >> q.qbits;
+        }
+    int lv[16];
+    zigzag4x4(m, lv);
+    const uint32_t mask = level_mask16(lv);
+    if (mask == 0) return sad0;
+    if (counts_only) {
+        const int tc = hlb_popc(mask);
+        uint32_t val = (uint32_t)tc << 22;
+        if (tc == 1) {
+            int sum = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum += lv[i];
+            if (sum == 1 || sum == -1) {
+                const int hb = 31 - hlb_clz(mask);
+                val |= (1u << 27) | ((uint32_t)(hb < 6 ? (hb == 0 ? 3 : (hb < 3 ? 2 : 1)) : 0) << 29);
+            }
+        }
+        return val;
+    }
+    const CavlcInfo ci = cavlc_block_info16(lv, mask);
+    // de-quantisation (flat scaling lists) with the +32 of the final rounding folded into the DC coefficient, inverse transform
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = m[i * 4 + j] * q.dq_mul[pos_class(i, j)];
+            m[i * 4 + j] = (v + q.dq_round) >> q.dq_shift;
+        }
+    m[0] += 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d0 = m[4 * i], d1 = m[4 * i + 1], d2 = m[4 * i + 2], d3 = m[4 * i + 3];
+        const int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+        m[4 * i] = e0 + e3; m[4 * i + 1] = e1 + e2; m[4 * i + 2] = e1 - e2; m[4 * i + 3] = e0 - e3;
+    }
+    uint32_t dist = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int f0 = m[j], f1 = m[4 + j], f2 = m[8 + j], f3 = m[12 + j];
+        const int g0 = f0 + f2, g1 = f0 - f2, g2 = (f1 >> 1) - f3, g3 = f1 + (f3 >> 1);
+        m[j] = (g0 + g3) >> 6; m[4 + j] = (g1 + g2) >> 6; m[8 + j] = (g1 - g2) >> 6; m[12 + j] = (g0 - g3) >> 6;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        // low bytes of the four residual samples of the row, added to the prediction modulo 256 (the reference's trial reconstruction wraps, hl_math.h:261)
+        const uint32_t res = p_prmt(p_prmt((uint32_t)m[r * 4], (uint32_t)m[r * 4 + 1], 0x0040), p_prmt((uint32_t)m[r * 4 + 2], (uint32_t)m[r * 4 + 3], 0x0040), 0x5410);
+        dist = p_sad4(s.r[r], p_add4_wrap(p.r[r], res), dist);
+    }
+    return dist | ((uint32_t)ci.bits_rest << 12) | ((uint32_t)ci.total_coeff << 22) | ((uint32_t)ci.trailing_ones << 27) | ((uint32_t)(ci.single_ctr & 3) << 29);
+}
+
+}  // namespace hlb

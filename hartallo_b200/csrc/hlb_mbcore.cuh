@@ -21,6 +21,7 @@
 
 #include "../../include/hlb200.h"
 #include "hlb_prims.cuh"
+#include "hlb_fast.cuh"
 #include "hlb_intra.cuh"
 
 #ifdef HLB_EMU_DEBUG
@@ -62,12 +63,17 @@ struct FrameCtx {
     int qp, qpc;
     int is_p, me_range, num_refs;
     double lambda;                       // lambda_mode = 0.852 * (1 << ((QP-12)/3)), slice.c:1766
+    QuantK qk;                           // quantiser constants of the luma trial encodes (hlb_fast.cuh), derived from qp by frame_ctx_derive()
     const uint8_t* src[3];
     uint8_t* cur[3];                     // reconstruction of the current picture (frame-store planes, pitch = W / W/2)
     const uint8_t* ref[HLB200_MAX_REFS][3];
+    const void* ref_tmap[HLB200_MAX_REFS];   // device: CUtensorMap (in global memory) of each reference luma plane for the TMA tile loads; null = plain loads
     MbState* st;
     hlb200_mb_record_t* rec;
 };
+
+// fields derived from the others (host side, once per picture)
+inline void frame_ctx_derive(FrameCtx& f) { quantk_make(f.qk, f.qp); }
 
 // ---- partition geometry of the 7 search modes (rdo.c:711-809): 0 16x16, 1 16x8, 2 8x16, 3 8x8, 4 8x4, 5 4x8, 6 4x4 ----
 HLB_HD int mode_nparts(int m) { return m == 0 ? 1 : (m < 3 ? 2 : 4); }
@@ -132,6 +138,10 @@ enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_TILE, CMD_ME_EVAL, CMD_PRED_INTER, 
 
 // Scratch of the macroblock being encoded (shared memory on the GPU)
 struct MbWork {
+    // reference tile: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)]; TMA destination (128-byte aligned, first member: no padding);
+    // the tail pads the word loads of the last row
+    alignas(128) uint8_t tile[HLB_TILE * HLB_TILE + 16];
+    alignas(8) unsigned long long tile_mbar;          // mbarrier the TMA tile load completes on (device)
     // command mailbox
     int cmd, arg0, arg1, arg0_lanes;
     // identity / neighbourhood
@@ -171,18 +181,20 @@ struct MbWork {
     int probably_pskip;
     // reference tile: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)] (per-sample clamp of interpol.c:108-131)
     int tile_x0, tile_y0, tile_ref, tile_valid;
-    uint8_t tile[HLB_TILE * HLB_TILE];
+    int tile_phase;                                   // parity of the next completion of tile_mbar
     // one evaluation step
     int c_begin, c_end;        // candidates evaluated by the current CMD_ME_EVAL
-    int part_ox, part_oy, part_w, part_h, ncand;
-    int16_t cmvx[HLB_MAXC], cmvy[HLB_MAXC];
-    uint8_t r_tc[HLB_MAXC][16], r_t1[HLB_MAXC][16], r_nz[HLB_MAXC][16], eff[HLB_MAXC][16];
+    int part_ox, part_oy, part_w, part_h;
+    int counts_only;           // the step's trials need TotalCoeff / TrailingOnes / Single_ctr only (me_step)
+    uint32_t cand_mv[HLB_MAXC];        // candidate vectors of the step: (uint16)mvx | (uint16)mvy << 16
+    uint8_t cand_pat[HLB_MAXC];        // their pattern indices
+    uint32_t r_val[HLB_MAXC][16];      // trial result words by (candidate, luma4x4BlkIdx): dist:12 | bits_rest:10 | TotalCoeff:5 | TrailingOnes:2 | lone Single_ctr:2
+    uint8_t eff[HLB_MAXC][16];
+    uint8_t blk_coded[16];             // final reconstruction: block has non-zero levels
     int32_t c_dist[HLB_MAXC], c_rbc[HLB_MAXC], c_sctr[HLB_MAXC], c_cbp[HLB_MAXC];
     double c_cost[HLB_MAXC];
     int step_last;             // ((c+1) << 12 | k << 8 | Single_ctr) of the last non-zero trial block of the step, -1 if none
     int bw_log2, nblk_log2;    // log2 of the partition width / size in 4x4 blocks
-    uint8_t pat_ok[HLB_MAXC], cidx[HLB_MAXC];
-    int16_t pat_mv[HLB_MAXC][2];
     // ---- reconstruction ----
     int fin_mode, fin_sub[4];          // committed geometry (part_mode, sub_mode[])
     int16_t fin_mv[4][4][2];
@@ -377,20 +389,75 @@ HLB_HD void pred_luma_4x4(const FrameCtx& f, const uint8_t* ref_y, int mbx, int 
 // ------------------------------------------------------------------------------------------------------------------
 // CMD_ME_EVAL: the trial encodes of one search step (me_ds.c:527-688 for every candidate of the step)
 // ------------------------------------------------------------------------------------------------------------------
-// origin (after the partition-origin clip of pred_inter.c:395-396) of candidate c's partition in picture coordinates
-HLB_HD void cand_origin(const MbWork& w, const FrameCtx& f, int c, int& X, int& Y)
+HLB_HD int mv_x(uint32_t mv) { return (int)(int16_t)(uint16_t)(mv & 0xffffu); }
+HLB_HD int mv_y(uint32_t mv) { return (int)(int16_t)(uint16_t)(mv >> 16); }
+HLB_HD uint32_t mv_pack(int x, int y) { return (uint32_t)(uint16_t)x | ((uint32_t)(uint16_t)y << 16); }
+// origin (after the partition-origin clip of pred_inter.c:395-396) of a candidate's partition in picture coordinates
+HLB_HD void cand_origin(const MbWork& w, const FrameCtx& f, uint32_t mv, int& X, int& Y)
 {
-    X = clip3(-17, f.W + 17, w.mbx * 16 + w.part_ox + (w.cmvx[c] >> 2));
-    Y = clip3(-17, f.H + 17, w.mby * 16 + w.part_oy + (w.cmvy[c] >> 2));
+    X = clip3(-17, f.W + 17, w.mbx * 16 + w.part_ox + (mv_x(mv) >> 2));
+    Y = clip3(-17, f.H + 17, w.mby * 16 + w.part_oy + (mv_y(mv) >> 2));
 }
-// CMD_TILE: lanes stride over the tile
-HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
+// CMD_TILE: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)].
+// Device: phase 0 = ONE TMA 2D tile load (cp.async.bulk.tensor, completion on an mbarrier; samples outside the picture arrive as zeros),
+//         phases 1, 2 = the picture-border fix-up: the reference clamps every sample coordinate (interpol.c:108-131), so out-of-picture columns (phase 1)
+//         and then rows (phase 2) of the tile are replicas of the nearest in-picture column / row -- only tiles that cross the picture edge have any.
+// A tile without a single in-picture column or row (vectors far outside the picture) and the CPU harness take the plain clamped loop.
+HLB_HD bool tile_uses_tma(const MbWork& w, const FrameCtx& f)
+{
+#if defined(__CUDA_ARCH__)
+    return f.ref_tmap[w.ref] != nullptr && w.tile_x0 > -HLB_TILE && w.tile_x0 < f.W && w.tile_y0 > -HLB_TILE && w.tile_y0 < f.H;
+#else
+    (void)w; (void)f;
+    return false;
+#endif
+}
+HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int phase, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    const uint8_t* plane = w.ref_y;
     const int nl = w.arg0_lanes;
-    // eight independent loads in flight per lane (the loop was one L2 round trip per sample: 18 K cycles per tile, r01d lap profile)
     const int W = f.W, Hm1 = f.H - 1, Wm1 = f.W - 1, x0 = w.tile_x0, y0 = w.tile_y0;
+#if defined(__CUDA_ARCH__)
+    if (tile_uses_tma(w, f)) {
+        if (phase == 0) {
+            if (lane == 0) {
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&w.tile_mbar), dst = (uint32_t)__cvta_generic_to_shared(w.tile);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the tile are ordered before the async-proxy write
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HLB_TILE * HLB_TILE) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(dst), "l"(f.ref_tmap[w.ref]), "r"(x0), "r"(y0), "r"(bar) : "memory");
+                const uint32_t parity = (uint32_t)w.tile_phase & 1u;
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                w.tile_phase ^= 1;
+            }
+            return;
+        }
+        const int cx0 = x0 < 0 ? -x0 : 0, cx1 = x0 + HLB_TILE > W ? W - x0 : HLB_TILE;           // in-picture columns [cx0, cx1)
+        const int ry0 = y0 < 0 ? -y0 : 0, ry1 = y0 + HLB_TILE > f.H ? f.H - y0 : HLB_TILE;       // in-picture rows    [ry0, ry1)
+        if (phase == 1 && (cx0 > 0 || cx1 < HLB_TILE)) {   // the nearest in-picture column into the out-of-picture columns of the in-picture rows
+            const int nbad = cx0 + (HLB_TILE - cx1);
+#pragma unroll 1
+            for (int i = lane; i < (ry1 - ry0) * nbad; i += nl) {
+                const int r = ry0 + i / nbad, k = i % nbad, c = k < cx0 ? k : cx1 + (k - cx0);
+                w.tile[r * HLB_TILE + c] = w.tile[r * HLB_TILE + (k < cx0 ? cx0 : cx1 - 1)];
+            }
+        }
+        if (phase == 2 && (ry0 > 0 || ry1 < HLB_TILE)) {   // whole rows, word-wise, from the (now column-complete) nearest in-picture row
+            const int nbad = ry0 + (HLB_TILE - ry1);
+#pragma unroll 1
+            for (int i = lane; i < nbad * (HLB_TILE / 4); i += nl) {
+                const int k = i / (HLB_TILE / 4), q = i % (HLB_TILE / 4), r = k < ry0 ? k : ry1 + (k - ry0);
+                ((uint32_t*)w.tile)[r * (HLB_TILE / 4) + q] = ((const uint32_t*)w.tile)[(k < ry0 ? ry0 : ry1 - 1) * (HLB_TILE / 4) + q];
+            }
+        }
+        return;
+    }
+#endif
+    if (phase != 0) return;
+    const uint8_t* plane = w.ref_y;
+    // eight independent loads in flight per lane
 #pragma unroll 1
     for (int i0 = lane; i0 < HLB_TILE * HLB_TILE; i0 += 8 * nl) {
         uint8_t v[8];
@@ -408,19 +475,9 @@ HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
         }
     }
 }
-// sums shared by the lanes of one candidate (shared-memory atomics on the GPU, plain read-modify-write in the emulation)
-#if defined(__CUDA_ARCH__)
-#define HLB_ATOMIC_ADD(p, v) atomicAdd((p), (v))
-#define HLB_ATOMIC_OR(p, v) atomicOr((p), (v))
-#define HLB_ATOMIC_MAX(p, v) atomicMax((p), (v))
-#else
-#define HLB_ATOMIC_ADD(p, v) (*(p) += (v))
-#define HLB_ATOMIC_OR(p, v) (*(p) |= (v))
-#define HLB_ATOMIC_MAX(p, v) (*(p) = *(p) > (v) ? *(p) : (v))
-#endif
 // ---- trial memo ----
 // A trial encode is a pure function of (4x4 block, motion vector): prediction, levels, CAVLC counts, reconstruction error.  Only the
-// coeff_token term depends on encoder history, and that is resolved afterwards from (TotalCoeff, TrailingOnes) by the scan / token phases.
+// coeff_token term depends on encoder history, and that is resolved afterwards from (TotalCoeff, TrailingOnes) by the scan / cost phases.
 // The seven partition modes of a macroblock walk almost the same diamonds around almost the same vectors, so most trials of modes 1..6 repeat
 // a (block, vector) pair an earlier search already encoded: on the reference trajectory 36 % (G1 1080p, mostly PSkip) to 87 % (G2 CIF) of all
 // trials, and 63 % / 95 % of the search STEPS consist of repeats only (measured with the CPU harness).  Each block keeps a small open-addressed
@@ -431,8 +488,10 @@ HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
 #define HLB_MEMO_PROBES 8
 #if defined(__CUDA_ARCH__)
 #define HLB_MEMO_CAS(p, old, val) (atomicCAS((p), (old), (val)) == (old))
+#define HLB_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #else
 #define HLB_MEMO_CAS(p, old, val) (*(p) == (old) ? (*(p) = (val), true) : false)
+#define HLB_ATOMIC_MAX(p, v) (*(p) = *(p) > (v) ? *(p) : (v))
 #endif
 #if !defined(__CUDACC__)
 // CPU harness only (tools/emu --memo-stats): how many trials / search steps of the reference trajectory are repeats
@@ -452,7 +511,8 @@ HLB_HD void memo_reset(MbWork& w, int lane, int nl)
 #pragma unroll 1
     for (int i = lane; i < 16 * HLB_MEMO_SLOTS; i += nl) t[i] = (unsigned long long)HLB_MEMO_EMPTY_KEY;
 }
-// CMD_ME_EVAL: lane = (candidate - c_begin) * nblk + k, k = raster index of the 4x4 block inside the partition
+// CMD_ME_EVAL: lane = (candidate - c_begin) * nblk + k, k = raster index of the 4x4 block inside the partition.  Result word -> w.r_val[c][blk].
+// The arithmetic is hlb_fast.cuh's: prediction straight out of the shared-memory tile as packed rows, dot-product transform, packed SAD.
 HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
@@ -460,99 +520,91 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
     if (c >= w.c_end) return;
     const int bx = w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), by = w.part_oy + ((k >> w.bw_log2) << 2);
     const int blk = blk_idx_from_xy(bx, by);
-    const int mvx = w.cmvx[c], mvy = w.cmvy[c];
-    // ---- memo lookup ----
-    const uint32_t key = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+    const uint32_t key = w.cand_mv[c];
+    const int mvx = mv_x(key), mvy = mv_y(key);
+    const bool counts_only = w.counts_only != 0;
     unsigned long long* tab = w.memo[blk];
-    const int h0 = (mvx * 5 + mvy * 23) & (HLB_MEMO_SLOTS - 1);
     uint32_t val = 0;
     bool hit = false;
     int ins = -1;
+    if (!counts_only) {   // a search that can no longer improve needs no distortion / bit count: nothing to remember, nothing worth looking up
+        const int h0 = (mvx * 5 + mvy * 23) & (HLB_MEMO_SLOTS - 1);
 #pragma unroll 1
-    for (int p = 0; p < HLB_MEMO_PROBES; ++p) {
-        const int j = (h0 + p) & (HLB_MEMO_SLOTS - 1);
-        const unsigned long long e = *(volatile unsigned long long*)&tab[j];
-        if ((uint32_t)e == key) { hit = true; val = (uint32_t)(e >> 32); break; }
-        if ((uint32_t)e == HLB_MEMO_EMPTY_KEY) { ins = j; break; }
+        for (int p = 0; p < HLB_MEMO_PROBES; ++p) {
+            const int j = (h0 + p) & (HLB_MEMO_SLOTS - 1);
+            const unsigned long long e = *(volatile unsigned long long*)&tab[j];
+            if ((uint32_t)e == key) { hit = true; val = (uint32_t)(e >> 32); break; }
+            if ((uint32_t)e == HLB_MEMO_EMPTY_KEY) { ins = j; break; }
+        }
+        HLB_MEMO_COUNT(hit);
     }
-    HLB_MEMO_COUNT(hit);
     if (!hit) {
-        uint8_t pv[16], sv[16];
         int X, Y;
-        cand_origin(w, f, c, X, Y);
-        const uint8_t* g = w.tile + (Y + (by - w.part_oy) - w.tile_y0) * HLB_TILE + (X + (bx - w.part_ox) - w.tile_x0);
-        interp_luma_4x4(g, HLB_TILE, mvx & 3, mvy & 3, pv);
+        cand_origin(w, f, key, X, Y);
+        const Rows4 p = fast_pred_luma((const uint32_t*)w.tile, HLB_TILE / 4, X + (bx - w.part_ox) - w.tile_x0, Y + (by - w.part_oy) - w.tile_y0, mvx & 3, mvy & 3);
+        Rows4 s;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t sw = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2];   // bx is a multiple of 4
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sv[r * 4 + q] = (uint8_t)(sw >> (8 * q));
-        }
-        int m[16], lv[16];
-        uint32_t any = 0, mask = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; any |= (uint32_t)m[i]; }
-        if (any) {
-            fwd_transform4x4(m);
-            quant4x4_ac(m, f.qp, false);
-            zigzag4x4(m, lv);
-            mask = level_mask16(lv);
-        }
-        if (mask != 0) {
-            const CavlcInfo ci = cavlc_block_info16(lv, mask);
-            int cc[16];
-            inv_zigzag4x4(lv, cc);
-            dequant4x4(cc, f.qp, false);
-            inv_transform4x4(cc);
-            uint8_t rec[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) rec[i] = (uint8_t)((int)pv[i] + cc[i]);  // wraps mod 256 (hl_math.h:261)
-            // Single_ctr is 9 unless the block holds one lone +-1 (TotalCoeff == TrailingOnes == 1): only then two bits are kept
-            val = (uint32_t)sad16(sv, rec) | ((uint32_t)ci.bits_rest << 12) | ((uint32_t)ci.total_coeff << 22) | ((uint32_t)ci.trailing_ones << 27) |
-                  ((uint32_t)(ci.single_ctr & 3) << 29);
-        } else val = (uint32_t)sad16(sv, pv);   // TotalCoeff 0
+        for (int r = 0; r < 4; ++r) s.r[r] = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2];   // bx is a multiple of 4
+        val = fast_trial(s, p, f.qk, counts_only);
         if (ins >= 0) (void)HLB_MEMO_CAS(&tab[ins], (unsigned long long)HLB_MEMO_EMPTY_KEY, ((unsigned long long)val << 32) | key);   // lost races / full rows: not cached
     }
-    // ---- publish (identical for computed and remembered trials) ----
-    const int dist = (int)(val & 4095u), tc = (int)((val >> 22) & 31u);
-    if (tc != 0) {
-        const int t1 = (int)((val >> 27) & 3u), sctr = (tc == 1 && t1 == 1) ? (int)((val >> 29) & 3u) : 9;
-        w.r_tc[c][blk] = (uint8_t)tc; w.r_t1[c][blk] = (uint8_t)t1; w.r_nz[c][blk] = 1;
-        HLB_ATOMIC_ADD(&w.c_rbc[c], (int)((val >> 12) & 1023u));
-        HLB_ATOMIC_ADD(&w.c_sctr[c], sctr);
-        HLB_ATOMIC_OR(&w.c_cbp[c], 1 << blk);
-        HLB_ATOMIC_MAX(&w.step_last, ((c + 1) << 12) | (k << 8) | sctr);   // last non-zero block in evaluation order
-    } else w.r_nz[c][blk] = 0;
-    HLB_ATOMIC_ADD(&w.c_dist[c], dist);
+    w.r_val[c][blk] = val;
 }
 HLB_HD bool blk_in_part(const MbWork& w, int blk)
 {
     const int x = blk_x(blk), y = blk_y(blk);
     return x >= w.part_ox && x < w.part_ox + w.part_w && y >= w.part_oy && y < w.part_oy + w.part_h;
 }
-// per block: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806)
-HLB_FN void me_phase_scan(MbWork& w, int lane)
+// per block: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806: only non-zero blocks are
+// stored), and the last non-zero trial block of the step in evaluation order (its Single_ctr stays in pc_esd->rdo.Single_ctr, residual.c:882)
+HLB_HD void me_scan_block(MbWork& w, int blk, int n, bool keep_eff)
 {
-    HLB_IN_SHARED(w);
-    if (lane >= 16) return;
-    int e = w.tc[lane];
-    const bool in = blk_in_part(w, lane);
+    int e = w.tc[blk];
+    if (!blk_in_part(w, blk)) {
+        if (keep_eff)
 #pragma unroll 1
-    for (int c = w.c_begin; c < w.c_end; ++c) {
-        if (in && w.r_nz[c][lane]) e = w.r_tc[c][lane];
-        w.eff[c][lane] = (uint8_t)e;
+            for (int c = 0; c < n; ++c) w.eff[c][blk] = (uint8_t)e;
+        return;
     }
-    w.tc[lane] = (uint8_t)e;
+    int last = -1;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        const uint32_t v = w.r_val[c][blk];
+        const int tcv = (int)((v >> 22) & 31u);
+        if (tcv) {
+            e = tcv;
+            const int t1 = (int)((v >> 27) & 3u);
+            last = ((c + 1) << 12) | ((tcv == 1 && t1 == 1) ? (int)((v >> 29) & 3u) : 9);
+        }
+        if (keep_eff) w.eff[c][blk] = (uint8_t)e;
+    }
+    w.tc[blk] = (uint8_t)e;
+    if (last >= 0) {
+        const int k = (((blk_y(blk) - w.part_oy) >> 2) << w.bw_log2) | ((blk_x(blk) - w.part_ox) >> 2);   // raster index inside the partition = evaluation order
+        HLB_ATOMIC_MAX(&w.step_last, last | (k << 8));
+    }
 }
-HLB_FN void me_phase_token(MbWork& w, int lane)
+// per candidate: distortion, bits (coeff_token resolved with the history-exact nC), Single_ctr, CBP bits, RD cost (me_ds.c:287,297,345)
+HLB_HD void me_cost_cand(MbWork& w, const FrameCtx& f, int c, int px, int py)
 {
-    HLB_IN_SHARED(w);
-    const int c = w.c_begin + (lane >> w.nblk_log2), k = lane & ((1 << w.nblk_log2) - 1);
-    if (c >= w.c_end) return;
-    const int blk = blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2));
-    if (!w.r_nz[c][blk]) return;
-    const int nC = luma_nc(w, w.eff[c], blk);
-    HLB_ATOMIC_ADD(&w.c_rbc[c], coeff_token_len(nC, w.r_tc[c][blk], w.r_t1[c][blk]));
+    int dist = 0, rbc = 0, sctr = 0, cbp = 0;
+    const int nblk = 1 << w.nblk_log2;
+#pragma unroll 1
+    for (int k = 0; k < nblk; ++k) {
+        const int blk = blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2));
+        const uint32_t v = w.r_val[c][blk];
+        dist += (int)(v & 4095u);
+        const int tcv = (int)((v >> 22) & 31u);
+        if (tcv) {
+            const int t1 = (int)((v >> 27) & 3u);
+            rbc += (int)((v >> 12) & 1023u) + coeff_token_len(luma_nc(w, w.eff[c], blk), tcv, t1);
+            sctr += (tcv == 1 && t1 == 1) ? (int)((v >> 29) & 3u) : 9;
+            cbp |= 1 << blk;
+        }
+    }
+    const uint32_t mv = w.cand_mv[c];
+    w.c_dist[c] = dist; w.c_rbc[c] = rbc; w.c_sctr[c] = sctr; w.c_cbp[c] = cbp;
+    w.c_cost[c] = dist + ((rbc + se_len(mv_x(mv) - px) + se_len(mv_y(mv) - py)) * f.lambda);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -575,13 +627,13 @@ HLB_HD void set_part(MbWork& w, int mode, int p, int s)
     w.nblk_log2 = w.bw_log2 + (w.part_h == 16 ? 2 : (w.part_h == 8 ? 1 : 0));
 }
 
-// One evaluation of candidates [c0, c1) (they fit the reference tile together): trial encodes on the worker lanes, then the
-// history-exact coeff_token lengths on the master warp's own lanes.  (bx0..by1) = bounding box of the samples they read.
+// Trial encodes of candidates [c0, c1) (they fit the reference tile together).  (bx0..by1) = bounding box of the samples they read.
 template <class X>
 HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, int bx0, int by0, int bx1, int by1)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (!(w.tile_valid && w.tile_ref == w.ref && bx0 >= w.tile_x0 && by0 >= w.tile_y0 && bx1 <= w.tile_x0 + HLB_TILE && by1 <= w.tile_y0 + HLB_TILE)) {
+        x.sync();   // every lane has evaluated the condition before the tile origin changes
         w.tile_x0 = bx0 - ((HLB_TILE - (bx1 - bx0)) >> 1); w.tile_y0 = by0 - ((HLB_TILE - (by1 - by0)) >> 1);
         w.tile_ref = w.ref; w.tile_valid = 1;
         HLB_LAP(w, 2);
@@ -594,168 +646,180 @@ HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, in
     x.run(CMD_ME_EVAL, (c1 - c0) << w.nblk_log2);
     HLB_MEMO_STEP_END();
     HLB_LAP(w, 4);
-#pragma unroll 1
-    for (int b = x.lane(); b < 16; b += x.nlanes()) me_phase_scan(w, b);
-    x.sync();
-#pragma unroll 1
-    for (int i = x.lane(); i < ((c1 - c0) << w.nblk_log2); i += x.nlanes()) me_phase_token(w, i);
-    x.sync();
-    HLB_LAP(w, 5);
 }
-// Evaluates w.ncand candidates (w.cmvx/cmvy) of the current partition in order; leaves per-candidate dist / rbc / sctr / cbp and
-// the RD cost (me_ds.c:287,297,345: dist + (rbc + mvd bits) * lambda) in w.c_*.
+// One search step: evaluates the n candidates w.cand_mv[0..n) of the current partition in order; leaves TotalCoeffsLuma / the Single_ctr chain
+// as the reference's sequential evaluation would and, unless counts_only, per-candidate dist / rbc / sctr / cbp and the RD cost
+// (me_ds.c:287,297,345: dist + (rbc + mvd bits) * lambda) in w.c_*.  counts_only = the search can no longer improve (its best cost is 0: costs are
+// never negative and a candidate only wins with a strictly smaller one), so nothing but the rate state the trials leave behind matters.
 template <class X>
-HLB_FN void me_eval(X& x, MbWork& w, const FrameCtx& f, int px, int py)
+HLB_FN void me_step(X& x, MbWork& w, const FrameCtx& f, int n, int px, int py, bool counts_only)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     HLB_LAP(w, 1);
-    const int n = w.ncand;
-    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+    int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN, iops = 0;
 #pragma unroll 1
-    for (int c = 0; c < n; ++c) {
-        const int vx = w.cmvx[c] >> 2, vy = w.cmvy[c] >> 2;
-        mnx = vx < mnx ? vx : mnx; mxx = vx > mxx ? vx : mxx; mny = vy < mny ? vy : mny; mxy = vy > mxy ? vy : mxy;
+    for (int c = x.lane(); c < n; c += x.nlanes()) {
+        const uint32_t mv = w.cand_mv[c];
+        int OX, OY;
+        cand_origin(w, f, mv, OX, OY);   // the origin clip is monotonic, so the box of the clipped origins is the clipped box
+        mnx = OX < mnx ? OX : mnx; mxx = OX > mxx ? OX : mxx; mny = OY < mny ? OY : mny; mxy = OY > mxy ? OY : mxy;
+        // SURVEY Appendix D: interpolation ops per 4x4 block by fractional class
+        const int xf = mv_x(mv) & 3, yf = mv_y(mv) & 3;
+        iops += (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
     }
-#pragma unroll 1
-    for (int c = x.lane(); c < n; c += x.nlanes()) { w.c_dist[c] = 0; w.c_rbc[c] = 0; w.c_sctr[c] = 0; w.c_cbp[c] = 0; }
-    w.step_last = -1;
-    x.sync();
-    // the origin clip is monotonic, so the box of the clipped origins is the clipped box
-    const int ox = w.mbx * 16 + w.part_ox, oy = w.mby * 16 + w.part_oy;
-    const int X0 = clip3(-17, f.W + 17, ox + mnx), X1 = clip3(-17, f.W + 17, ox + mxx), Y0 = clip3(-17, f.H + 17, oy + mny), Y1 = clip3(-17, f.H + 17, oy + mxy);
-    if (X1 - X0 + w.part_w + 5 <= HLB_TILE && Y1 - Y0 + w.part_h + 5 <= HLB_TILE) me_eval_range(x, w, f, 0, n, X0 - 2, Y0 - 2, X1 + w.part_w + 3, Y1 + w.part_h + 3);
+    mnx = x.reduce_min(mnx); mny = x.reduce_min(mny); mxx = x.reduce_max(mxx); mxy = x.reduce_max(mxy); iops = x.reduce_add(iops);
+    if (x.lane() == 0) {
+        w.counts_only = counts_only ? 1 : 0; w.step_last = -1;
+        w.stat_trials += (unsigned)(n << w.nblk_log2); w.stat_cands += (unsigned)n; w.stat_interp += (unsigned)(iops << w.nblk_log2);
+    }
+    if (mxx - mnx + w.part_w + 5 <= HLB_TILE && mxy - mny + w.part_h + 5 <= HLB_TILE) me_eval_range(x, w, f, 0, n, mnx - 2, mny - 2, mxx + w.part_w + 3, mxy + w.part_h + 3);
     else {
 #pragma unroll 1
-        for (int c = 0; c < n; ++c) {   // windows too far apart for one tile: one by one, same order, same result
+        for (int c = 0; c < n; ++c) {   // windows too far apart for one tile: one by one, same results
             int PX, PY;
-            cand_origin(w, f, c, PX, PY);
+            cand_origin(w, f, w.cand_mv[c], PX, PY);
             me_eval_range(x, w, f, c, c + 1, PX - 2, PY - 2, PX + w.part_w + 3, PY + w.part_h + 3);
         }
     }
-    if (w.step_last >= 0) w.last_sctr = w.step_last & 255;
 #pragma unroll 1
-    for (int c = x.lane(); c < n; c += x.nlanes()) {
-        const int rbc_mv = se_len(w.cmvx[c] - px) + se_len(w.cmvy[c] - py);
-        w.c_cost[c] = w.c_dist[c] + ((w.c_rbc[c] + rbc_mv) * f.lambda);
-        // SURVEY Appendix D: interpolation ops per 4x4 block by fractional class
-        const int xf = w.cmvx[c] & 3, yf = w.cmvy[c] & 3;
-        const int cls = (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
-        HLB_ATOMIC_ADD(&w.stat_interp, (unsigned)(cls << w.nblk_log2));
-    }
-    if (x.lane() == 0) { w.stat_trials += (unsigned)(n << w.nblk_log2); w.stat_cands += (unsigned)n; }
+    for (int b = x.lane(); b < 16; b += x.nlanes()) me_scan_block(w, b, n, !counts_only);
     x.sync();
+    if (w.step_last >= 0 && x.lane() == 0) w.last_sctr = w.step_last & 255;
+    HLB_LAP(w, 5);
+    if (!counts_only) {
+#pragma unroll 1
+        for (int c = x.lane(); c < n; c += x.nlanes()) me_cost_cand(w, f, c, px, py);
+        x.sync();
+    }
     HLB_LAP(w, 6);
 }
 
 HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
 {
     w.best_cost[p][s] = cost; w.best_sctr[p][s] = w.c_sctr[c]; w.best_dist[p][s] = w.c_dist[c]; w.best_cbp[p][s] = w.c_cbp[c];
-    w.best_mv[p][s][0] = w.cmvx[c]; w.best_mv[p][s][1] = w.cmvy[c];
+    w.best_mv[p][s][0] = (int16_t)mv_x(w.cand_mv[c]); w.best_mv[p][s][1] = (int16_t)mv_y(w.cand_mv[c]);
 }
 
 template <class X>
 HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    w.mode = mode;
+    if (x.lane() == 0) w.mode = mode;
     const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
 #pragma unroll 1
-    for (int p = 0; p < nparts; ++p)
-#pragma unroll 1
-        for (int s = 0; s < nsub; ++s) { w.best_sctr[p][s] = 9; w.best_dist[p][s] = INT_MAX; w.best_cost[p][s] = DBL_MAX; }
-    w.probably_pskip = 0;
+    for (int i = x.lane(); i < 16; i += x.nlanes()) { w.best_sctr[i >> 2][i & 3] = 9; w.best_dist[i >> 2][i & 3] = INT_MAX; w.best_cost[i >> 2][i & 3] = DBL_MAX; }
+    int probably_pskip = 0;
+    x.sync();
     if (mode == 0 && w.ref == 0) {  // PSkip probe (me_ds.c:229-261)
         int sx, sy, px, py;
         derive_pskip_mv(w, f, sx, sy);
         derive_mvp(w, f, 0, 0, w.ref, px, py);
         if (px == sx && py == sy) {
-            set_part(w, mode, 0, 0);
-            w.ncand = 1; w.cmvx[0] = (int16_t)px; w.cmvy[0] = (int16_t)py;
-            me_eval(x, w, f, px, py);
-            if (w.c_rbc[0] == 0 || w.c_sctr[0] < 6) { w.probably_pskip = 1; set_best(w, 0, 0, 0.0, 0); }
+            x.sync();
+            if (x.lane() == 0) { set_part(w, mode, 0, 0); w.cand_mv[0] = mv_pack(px, py); }
+            x.sync();
+            me_step(x, w, f, 1, px, py, false);
+            if (w.c_rbc[0] == 0 || w.c_sctr[0] < 6) {
+                probably_pskip = 1;
+                x.sync();
+                if (x.lane() == 0) set_best(w, 0, 0, 0.0, 0);
+            }
         }
     }
+    x.sync();
+    if (x.lane() == 0) w.probably_pskip = probably_pskip;
 #pragma unroll 1
     for (int p = 0; p < nparts; ++p) {
 #pragma unroll 1
         for (int s = 0; s < nsub; ++s) {
             int shift = 2, flags = 0xFFFFFF, px, py;
             derive_mvp(w, f, p, s, w.ref, px, py);
-            w.mvp[p][s][0] = (int16_t)px; w.mvp[p][s][1] = (int16_t)py;
-            set_part(w, mode, p, s);
-            // cost at the predictor, then at (0,0) (me_ds.c:283-299)
-            w.ncand = 1; w.cmvx[0] = (int16_t)px; w.cmvy[0] = (int16_t)py;
-            if (px != 0 || py != 0) { w.ncand = 2; w.cmvx[1] = 0; w.cmvy[1] = 0; }
-            me_eval(x, w, f, px, py);
-#pragma unroll 1
-            for (int c = 0; c < w.ncand; ++c) {
-                HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f [init]\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
-                if (w.c_cost[c] < w.best_cost[p][s]) set_best(w, p, s, w.c_cost[c], c);
+            // best candidate so far, identical in every lane: cost, vector (kept in registers; mirrored in w.best_* by lane 0)
+            double bcost = w.best_cost[p][s];
+            int bmx = w.best_mv[p][s][0], bmy = w.best_mv[p][s][1];
+            x.sync();
+            int n = (px != 0 || py != 0) ? 2 : 1;
+            if (x.lane() == 0) {
+                w.mvp[p][s][0] = (int16_t)px; w.mvp[p][s][1] = (int16_t)py;
+                set_part(w, mode, p, s);
+                // cost at the predictor, then at (0,0) (me_ds.c:283-299)
+                w.cand_mv[0] = mv_pack(px, py); w.cand_mv[1] = 0;
             }
-            int cx = w.best_mv[p][s][0] >> 2, cy = w.best_mv[p][s][1] >> 2;
+            x.sync();
+            me_step(x, w, f, n, px, py, bcost == 0.0);
+            if (bcost != 0.0) {
+#pragma unroll 1
+                for (int c = 0; c < n; ++c) {
+                    HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f [init]\n", mode, p, s, mv_x(w.cand_mv[c]), mv_y(w.cand_mv[c]), w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
+                    const double cc = w.c_cost[c];
+                    if (cc < bcost) { bcost = cc; bmx = mv_x(w.cand_mv[c]); bmy = mv_y(w.cand_mv[c]); if (x.lane() == 0) set_best(w, p, s, cc, c); }
+                }
+            }
+            int cx = bmx >> 2, cy = bmy >> 2;
             int wl = cx - f.me_range, wr = cx + f.me_range, wt = cy - f.me_range, wb = cy + f.me_range;
 #pragma unroll 1
             for (int iter = 0;; ++iter) {
                 if (iter > 4096) { w.stuck = 1; break; }
                 int best_idx = -1;
                 const int count = shift == 1 ? 5 : 9;
-                // pattern points of this iteration: one master lane per point, then an ordered compaction
-#pragma unroll 1
-                for (int i = x.lane(); i < count; i += x.nlanes()) {
-                    const int mx = cx + kDsp[shift][i][0], my = cy + kDsp[shift][i][1];
-                    const bool ok = (flags & (1 << i)) && mx >= wl && mx <= wr && my >= wt && my <= wb;
-                    w.pat_ok[i] = ok ? 1 : 0;
-                    w.pat_mv[i][0] = (int16_t)(mx * (1 << shift)); w.pat_mv[i][1] = (int16_t)(my * (1 << shift));
-                }
-                x.sync();
-                // ordered compaction without a serial pass: every kept point counts the kept points before it (independent loads)
-                int n = 0;
+                // pattern points of this iteration, in table order: kept when not pruned and inside the window (me_ds.c:317-328)
+                int okmask = 0;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) n += (j < count) ? (int)w.pat_ok[j] : 0;
+                for (int i = 0; i < 9; ++i) {
+                    const int mx = cx + kDsp[shift][i][0], my = cy + kDsp[shift][i][1];
+                    okmask |= (i < count && ((flags >> i) & 1) && mx >= wl && mx <= wr && my >= wt && my <= wb) ? (1 << i) : 0;
+                }
+                n = hlb_popc((uint32_t)okmask);
+                x.sync();   // the previous step's candidates have been read by every lane
 #pragma unroll 1
                 for (int i = x.lane(); i < count; i += x.nlanes())
-                    if (w.pat_ok[i]) {
-                        int at = 0;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) at += (j < i) ? (int)w.pat_ok[j] : 0;
-                        w.cidx[at] = (uint8_t)i; w.cmvx[at] = w.pat_mv[i][0]; w.cmvy[at] = w.pat_mv[i][1];
+                    if ((okmask >> i) & 1) {
+                        const int at = hlb_popc((uint32_t)okmask & ((1u << i) - 1u));
+                        w.cand_mv[at] = mv_pack((cx + kDsp[shift][i][0]) * (1 << shift), (cy + kDsp[shift][i][1]) * (1 << shift));
+                        w.cand_pat[at] = (uint8_t)i;
                     }
-                w.ncand = n;
                 x.sync();
                 if (n > 0) {
-                    me_eval(x, w, f, px, py);
-                    // the first strictly smaller cost in candidate order wins (me_ds.c:345); only the final winner is committed
-                    double bc = w.best_cost[p][s];
-                    int win = -1;
-#pragma unroll
-                    for (int c = 0; c < HLB_MAXC; ++c) {
-                        if (c < n) {
-                            HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, w.cmvx[c], w.cmvy[c], w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
+                    const bool dead = bcost == 0.0;
+                    me_step(x, w, f, n, px, py, dead);
+                    if (!dead) {
+                        // the first strictly smaller cost in candidate order wins (me_ds.c:345) = the smallest cost, the earliest candidate among equals
+                        double mc = DBL_MAX;
+                        int mi = INT_MAX;
+#pragma unroll 1
+                        for (int c = x.lane(); c < n; c += x.nlanes()) {
+                            HLB_DBG("    cand m%d p%d s%d mv (%d,%d) dist %d bits %d sctr %d cost %.4f\n", mode, p, s, mv_x(w.cand_mv[c]), mv_y(w.cand_mv[c]), w.c_dist[c], w.c_rbc[c], w.c_sctr[c], w.c_cost[c]);
                             const double cc = w.c_cost[c];
-                            if (cc < bc) { bc = cc; win = c; }
+                            if (cc < mc) { mc = cc; mi = c; }
+                        }
+                        x.reduce_argmin(mc, mi);
+                        if (mc < bcost) {
+                            bcost = mc; bmx = mv_x(w.cand_mv[mi]); bmy = mv_y(w.cand_mv[mi]);
+                            best_idx = w.cand_pat[mi];
+                            if (x.lane() == 0) set_best(w, p, s, mc, mi);
                         }
                     }
-                    if (win >= 0) { best_idx = w.cidx[win]; set_best(w, p, s, bc, win); }
                 }
                 flags = 0xFFFFFF;
                 if (shift == 2 && best_idx == -1) {
                     shift = 1;
-                    cx = w.best_mv[p][s][0] >> 2; cy = w.best_mv[p][s][1] >> 2;  // integer-pel value used as a half-pel centre
+                    cx = bmx >> 2; cy = bmy >> 2;  // integer-pel value used as a half-pel centre
                     wl = cx - f.me_range; wr = cx + f.me_range; wt = cy - f.me_range; wb = cy + f.me_range;
                 } else if (best_idx == -1) {
                     if (shift == 1) {
                         shift = 0;
-                        cx = w.best_mv[p][s][0]; cy = w.best_mv[p][s][1];
+                        cx = bmx; cy = bmy;
                         wl = cx - f.me_range; wr = cx + f.me_range; wt = cy - f.me_range; wb = cy + f.me_range;
                     } else break;
                 } else {
-                    cx = w.best_mv[p][s][0] >> shift; cy = w.best_mv[p][s][1] >> shift;
+                    cx = bmx >> shift; cy = bmy >> shift;
                     flags &= ~(int)kPrune[shift][best_idx];
                 }
-                x.sync();
             }
-            w.mv_cur[p][s][0] = w.best_mv[p][s][0]; w.mv_cur[p][s][1] = w.best_mv[p][s][1];
-            HLB_DBG("   part m%d p%d s%d: mv (%d,%d) mvp (%d,%d) cost %.4f dist %d sctr %d\n", mode, p, s, w.best_mv[p][s][0], w.best_mv[p][s][1], px, py, w.best_cost[p][s], w.best_dist[p][s], w.best_sctr[p][s]);
+            x.sync();
+            if (x.lane() == 0) { w.mv_cur[p][s][0] = (int16_t)bmx; w.mv_cur[p][s][1] = (int16_t)bmy; }
+            x.sync();
+            HLB_DBG("   part m%d p%d s%d: mv (%d,%d) mvp (%d,%d) cost %.4f dist %d sctr %d\n", mode, p, s, bmx, bmy, px, py, w.best_cost[p][s], w.best_dist[p][s], w.best_sctr[p][s]);
         }
     }
 }
@@ -847,7 +911,7 @@ HLB_FN void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int q = 0; q < 4; ++q) w.rec_y[(by + r) * 16 + bx + q] = (uint8_t)rec[r * 4 + q];
-    w.r_nz[0][lane] = coded ? 1 : 0;   // gathered into cbp_luma4x4 by the master
+    w.blk_coded[lane] = coded ? 1 : 0;   // gathered into cbp_luma4x4 by the master
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -997,6 +1061,7 @@ HLB_HD int cmd_phases(int cmd)
 {
     switch (cmd) {
     case CMD_ME_EVAL: return 1;
+    case CMD_TILE: return 3;
     case CMD_CHROMA: return 3;
     case CMD_I16_EVAL: return 2;
     case CMD_I16_RATE: return 2;
@@ -1009,7 +1074,7 @@ HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     switch (cmd) {
     case CMD_LOAD: phase_load(w, f, lane); break;
-    case CMD_TILE: phase_tile_load(w, f, lane); break;
+    case CMD_TILE: phase_tile_load(w, f, phase, lane); break;
     case CMD_ME_EVAL: me_phase_trial(w, f, lane); break;
     case CMD_PRED_INTER: phase_pred_inter(w, f, lane); break;
     case CMD_RECON_LUMA: phase_recon_luma(w, f, lane); break;
@@ -1049,12 +1114,12 @@ HLB_FN void mb_begin(MbWork& w, const FrameCtx& f, int mb, int lane, int nl)
         const int k = i / HLB_NB_WORDS, j = i - k * HLB_NB_WORDS;
         const int addr = k == 0 ? mb : (k == 1 ? mb - 1 : (k == 2 ? mb - f.mbw : (k == 3 ? mb - f.mbw + 1 : mb - f.mbw - 1)));
         const bool ok = k == 0 || (k == 1 ? availA : (k == 2 ? availB : (k == 3 ? availC : availD)));
-        w.nbw[k][j] = ok ? ((const uint32_t*)&f.st[addr])[j] : 0u;
+        w.nbw[k][j] = ok ? HLB_LDCG((const uint32_t*)&f.st[addr] + j) : 0u;   // neighbours' state was written by other CTAs of this launch
     }
 #pragma unroll 1
-    for (int i = lane; i < 64; i += nl) ((uint32_t*)&w.chroma_ac[0][0][0])[i] = ((const uint32_t*)&s.chroma_ac[0][0][0])[i];
+    for (int i = lane; i < 64; i += nl) ((uint32_t*)&w.chroma_ac[0][0][0])[i] = HLB_LDCG((const uint32_t*)&s.chroma_ac[0][0][0] + i);
 #pragma unroll 1
-    for (int i = lane; i < 4; i += nl) ((uint32_t*)&w.chroma_dc[0][0])[i] = ((const uint32_t*)&s.chroma_dc[0][0])[i];
+    for (int i = lane; i < 4; i += nl) ((uint32_t*)&w.chroma_dc[0][0])[i] = HLB_LDCG((const uint32_t*)&s.chroma_dc[0][0] + i);
     HLB_LANE_SYNC();
     const MbState& o = *(const MbState*)w.nbw[0];
     const MbState& sA = *(const MbState*)w.nbw[1];
@@ -1288,7 +1353,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         w.cbp_luma4x4 = 0;
         if (!w.luma_skip_residual)
 #pragma unroll 1
-            for (int b = 0; b < 16; ++b) w.cbp_luma4x4 |= w.r_nz[0][b] << b;
+            for (int b = 0; b < 16; ++b) w.cbp_luma4x4 |= w.blk_coded[b] << b;
         chroma_code(x, w);
         w.arg0 = 3; x.run(CMD_STORE, 96);
         cbp_luma = guess_cbp_luma(w.cbp_luma4x4, false);

@@ -24,7 +24,7 @@ HLB_HD int intra_luma_fetch(const MbWork& w, const FrameCtx& f, int x, int y)
     else if (x < 0 && y >= 0 && y <= 15) ok = w.availA;
     else ok = false;
     if (!ok) return HLB_NA;
-    return f.cur[0][(w.mby * 16 + y) * f.W + w.mbx * 16 + x];
+    return HLB_LDCG(f.cur[0] + (w.mby * 16 + y) * f.W + w.mbx * 16 + x);
 }
 HLB_HD int intra_chroma_fetch(const MbWork& w, const FrameCtx& f, int c, int x, int y)
 {
@@ -33,7 +33,7 @@ HLB_HD int intra_chroma_fetch(const MbWork& w, const FrameCtx& f, int c, int x, 
     else if (y < 0 && x < 0) ok = w.availD;
     else ok = w.availA;
     if (!ok) return HLB_NA;
-    return f.cur[1 + c][(w.mby * 8 + y) * (f.W >> 1) + w.mbx * 8 + x];
+    return HLB_LDCG(f.cur[1 + c] + (w.mby * 8 + y) * (f.W >> 1) + w.mbx * 8 + x);
 }
 HLB_FN void intra_fetch_borders(MbWork& w, const FrameCtx& f, int lane, int nl)
 {

@@ -26,6 +26,7 @@
 #endif
 #define HLB_TABLE __constant__   /* small read-only tables: constant cache (plain global loads are compiled .cg and would go to L2) */
 #define HLB_LDG(p) __ldg(p)   /* read-only for the whole kernel (reference / source planes): non-coherent path, L1-cacheable */
+#define HLB_LDCG(p) __ldcg(p)   /* written by other CTAs of the same launch (macroblock state, reconstruction): served from L2, never from a stale L1 line */
 #if defined(__CUDA_ARCH__)
 #define HLB_IN_SHARED(ref) __builtin_assume(__isShared(&(ref)))   /* lets nvcc emit LDS/STS instead of generic accesses in non-inlined functions */
 #else
@@ -39,6 +40,7 @@
 #define HLB_INTERP_SRC(g) ((void)0)
 #define HLB_TABLE
 #define HLB_LDG(p) (*(p))
+#define HLB_LDCG(p) (*(p))
 #define HLB_IN_SHARED(ref) ((void)0)
 #endif
 

@@ -87,6 +87,20 @@ struct GpuExec {
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
     __device__ __forceinline__ int nlanes() const { return 32; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    // cross-lane reductions of the (master) warp; every lane receives the result
+    __device__ __forceinline__ int reduce_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_add(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+    // best-MV argmin: the smallest cost wins, the smaller candidate index among equal costs (warp-shuffle butterfly)
+    __device__ __forceinline__ void reduce_argmin(double& c, int& i) const
+    {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, c, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (oc < c || (oc == c && oi < i)) { c = oc; i = oi; }
+        }
+    }
     __device__ __noinline__ int prev_sctr(int mb)
     {
         for (int a = mb - 1; a >= 0; --a) {
@@ -179,6 +193,15 @@ __device__ __forceinline__ void sched_finish(Sched* s, int* queue, int* deps, in
         }
 }
 
+__device__ __forceinline__ void tile_barrier_init(MbWork& w)
+{
+    // the mbarrier the TMA tile loads of this CTA complete on (one arrival = the issuing lane's expect_tx), made visible to the async proxy
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&w.tile_mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    w.tile_phase = 0;
+}
+
 __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_encode(const SliceJob* __restrict__ jobs, int njobs, int* sched_buf)
 {
     __shared__ MbWork w;
@@ -190,6 +213,8 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_e
     int* deps = queue + total;
     int* done = deps + total;
     const int tid = threadIdx.x;
+    if (tid == 0) tile_barrier_init(w);
+    __syncthreads();
     for (;;) {
         if (tid == 0) { int jb = 0; s_item = sched_pop(s, queue, total, jobs, njobs, &jb, HLB_SPIN_MAX_NS_CTA); s_job = jb; }
         __syncthreads();
@@ -270,6 +295,20 @@ struct WarpExec {
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
     __device__ __forceinline__ int nlanes() const { return 32; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    // cross-lane reductions of the (master) warp; every lane receives the result
+    __device__ __forceinline__ int reduce_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_add(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+    // best-MV argmin: the smallest cost wins, the smaller candidate index among equal costs (warp-shuffle butterfly)
+    __device__ __forceinline__ void reduce_argmin(double& c, int& i) const
+    {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, c, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (oc < c || (oc == c && oi < i)) { c = oc; i = oi; }
+        }
+    }
     __device__ __noinline__ int prev_sctr(int mb)
     {
         for (int a = mb - 1; a >= 0; --a) {
@@ -297,6 +336,8 @@ __global__ void __launch_bounds__(32, HLB_WARP_MIN_CTAS) k_slice_encode_warp(con
     int* deps = queue + total;
     int* done = deps + total;
     const int tid = threadIdx.x;
+    if (tid == 0) tile_barrier_init(w);
+    __syncwarp();
     for (;;) {
         int item = -1, jb = 0;
         if (tid == 0) item = sched_pop(s, queue, total, jobs, njobs, &jb, HLB_SPIN_MAX_NS_WARP);
@@ -349,11 +390,13 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     f.num_refs = f.is_p ? p->num_refs : 0;
     if (f.is_p && (f.num_refs < 1 || f.num_refs > c->max_refs)) return HLB200_ERR_INVALID_PARAMETER;
     f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));                       // slice.c:1766 (integer division in the exponent)
+    frame_ctx_derive(f);
     for (int k = 0; k < 3; ++k) { f.src[k] = c->d_src_cur[k]; f.cur[k] = c->d_slot[p->cur_slot][k]; }
     for (int u = 0; u < f.num_refs; ++u) {
         const int s = p->ref_slot[u];
         if (s < 0 || s >= c->nslots || s == p->cur_slot) return HLB200_ERR_INVALID_PARAMETER;
         for (int k = 0; k < 3; ++k) f.ref[u][k] = c->d_slot[s][k];
+        f.ref_tmap[u] = c->d_tmaps ? (const char*)c->d_tmaps + 128 * (size_t)s : nullptr;   // TMA descriptor of the slot's luma plane (hlb_api.cu)
     }
     f.st = (MbState*)c->d_mbstate;
     f.rec = c->d_records;
@@ -362,21 +405,23 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     return HLB200_OK;
 }
 
-static int g_slice_grid[2] = {0, 0};
-// resident CTAs of the whole device for variant v (0 = CTA per macroblock, 1 = warp per macroblock)
+// Process-wide read-mostly caches (the only globals of the library besides the kernel-variant override below): resident CTAs per device and variant.
+#define HLB_MAX_DEVICES 64
+static int g_slice_grid[HLB_MAX_DEVICES][2];
+// resident CTAs of the whole CURRENT device for variant v (0 = CTA per macroblock, 1 = warp per macroblock)
 static int slice_grid(int v)
 {
-    if (g_slice_grid[v]) return g_slice_grid[v];
     int dev = 0, sms = 0, per = 0;
     cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev >= 0 && dev < HLB_MAX_DEVICES && g_slice_grid[dev][v]) return g_slice_grid[dev][v];
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_slice_encode_warp, 32, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_slice_encode, HLB_CTA_THREADS, 0);
     if (e != cudaSuccess || per < 1) {
         cudaGetLastError();
         return 148;
     }
-    g_slice_grid[v] = sms * per;
-    return g_slice_grid[v];
+    if (dev >= 0 && dev < HLB_MAX_DEVICES) g_slice_grid[dev][v] = sms * per;
+    return sms * per;
 }
 // Which variant serves a batch.  The warp variant wins on throughput when the batch offers more ready macroblocks than the CTA variant has
 // CTAs (its macroblocks take longer individually); the CTA variant wins on latency for small batches.  HLB200_SLICE_KERNEL=cta|warp overrides.
@@ -402,6 +447,24 @@ using namespace hlb;
 
 extern "C" {
 
+// Watchdog state of the launch that last covered `c` (its scheduler words live in the batch owner): synchronises the owner's stream once per launch.
+static int slice_check_abort(hlb200_ctx* c)
+{
+    hlb200_ctx* o = c->batch_owner ? c->batch_owner : c;
+    if (!o->last_sched) return HLB200_OK;
+    if (o->abort_state < 0) {
+        int words[4] = {0, 0, 0, 0};
+        HLB_CUDA(cudaStreamSynchronize(o->stream));
+        HLB_CUDA(cudaMemcpy(words, o->last_sched, sizeof(words), cudaMemcpyDeviceToHost));
+        o->abort_state = words[3];
+    }
+    if (o->abort_state) {
+        snprintf(g_err, sizeof(g_err), "slice kernel watchdog fired (code %d): the launch was drained early, its records are incomplete (hlb200_slice_status has the details)", o->abort_state);
+        return HLB200_ERR_INVALID_STATE;
+    }
+    return HLB200_OK;
+}
+
 int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_params_t* params, int n)
 {
     if (!ctxs || !params || n < 1 || n > 4096) return HLB200_ERR_INVALID_PARAMETER;
@@ -409,6 +472,20 @@ int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_para
     if (!c0) return HLB200_ERR_INVALID_PARAMETER;
     int total = 0;
     for (int i = 0; i < n; ++i) { if (!ctxs[i]) return HLB200_ERR_INVALID_PARAMETER; total += ctxs[i]->nmb; }
+    // mean width of the 2:1 wavefront of a picture = macroblocks / (mbw + 2 (mbh - 1)) dependency steps
+    const int variant = g_slice_last = slice_variant(n, (c0->nmb + c0->mbw + 2 * c0->mbh - 3) / (c0->mbw + 2 * c0->mbh - 2));
+    int grid = slice_grid(variant);
+    // A macroblock of a P picture that needs the Single_ctr chain value of its raster predecessor waits for it while holding its CTA (prev_sctr): at most one CTA
+    // per picture can be parked that way (the parked macroblock blocks the first column below it), and the macroblock it waits for is always claimable by a
+    // free CTA.  With fewer pictures than resident CTAs a free CTA always exists, so the launch cannot deadlock; larger batches are split.
+    const int max_pictures = grid > 2 ? grid / 2 : 1;
+    if (n > max_pictures) {
+        for (int i = 0; i < n; i += max_pictures) {
+            const int rc = hlb200_slice_encode_batch_async(ctxs + i, params + i, n - i < max_pictures ? n - i : max_pictures);
+            if (rc) return rc;
+        }
+        return HLB200_OK;
+    }
     // scheduler + job storage lives in the first context of the batch
     const size_t need = sizeof(SliceJob) * (size_t)n + sizeof(int) * (HLB_SCHED_WORDS + 3 * (size_t)total) + 512;
     if (c0->sched_bytes < need) {
@@ -416,14 +493,14 @@ int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_para
         c0->d_sched = nullptr; c0->sched_bytes = 0;
         HLB_CUDA(cudaMalloc((void**)&c0->d_sched, need));
         c0->sched_bytes = need;
-        if (c0->h_jobs) HLB_CUDA(cudaFreeHost(c0->h_jobs));
-        c0->h_jobs = nullptr;
     }
     if (!c0->h_jobs || c0->h_jobs_cap < n) {
-        if (c0->h_jobs) HLB_CUDA(cudaFreeHost(c0->h_jobs));
+        if (c0->h_jobs) { HLB_CUDA(cudaStreamSynchronize(c0->stream)); HLB_CUDA(cudaFreeHost(c0->h_jobs)); c0->h_jobs = nullptr; }
         HLB_CUDA(cudaMallocHost(&c0->h_jobs, sizeof(SliceJob) * (size_t)n));
         c0->h_jobs_cap = n;
     }
+    if (!c0->ev_jobs) { HLB_CUDA(cudaEventCreateWithFlags(&c0->ev_jobs, cudaEventDisableTiming)); HLB_CUDA(cudaEventCreateWithFlags(&c0->ev_done, cudaEventDisableTiming)); }
+    else HLB_CUDA(cudaEventSynchronize(c0->ev_jobs));   // the pinned job array must not be rewritten while the previous launch's copy of it is still in flight
     SliceJob* hj = (SliceJob*)c0->h_jobs;
     int base = 0;
     for (int i = 0; i < n; ++i) {
@@ -434,21 +511,30 @@ int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_para
     SliceJob* dj = (SliceJob*)c0->d_sched;
     int* sched = (int*)((char*)c0->d_sched + ((sizeof(SliceJob) * (size_t)n + 255) & ~(size_t)255));
     cudaStream_t st = c0->stream;
-    // the pinned job array must not be rewritten while a previous copy is still in flight; uploads queued on the other contexts'
-    // streams must have landed before the batch kernel reads them
-    for (int i = 0; i < n; ++i) HLB_CUDA(cudaStreamSynchronize(ctxs[i]->stream));
+    // ORDERING RULE (include/hlb200.h): the batch kernel runs on the stream of ctxs[0].  Work queued earlier on the other contexts' streams (source uploads) is made
+    // a dependency of the launch, and everything queued later on them (record / slot downloads, the next upload) waits for the launch: events, no host sync.
+    for (int i = 1; i < n; ++i)
+        if (ctxs[i]->stream != st) {
+            if (!ctxs[i]->ev_done) HLB_CUDA(cudaEventCreateWithFlags(&ctxs[i]->ev_done, cudaEventDisableTiming));
+            HLB_CUDA(cudaEventRecord(ctxs[i]->ev_done, ctxs[i]->stream));
+            HLB_CUDA(cudaStreamWaitEvent(st, ctxs[i]->ev_done, 0));
+        }
     HLB_CUDA(cudaMemcpyAsync(dj, hj, sizeof(SliceJob) * (size_t)n, cudaMemcpyHostToDevice, st));
+    HLB_CUDA(cudaEventRecord(c0->ev_jobs, st));
     c0->last_sched = sched;
     k_slice_init<<<(total + 255) / 256, 256, 0, st>>>(dj, n, sched, total);
     HLB_CUDA(cudaGetLastError());
-    // mean width of the 2:1 wavefront of a picture = macroblocks / (mbw + 2 (mbh - 1)) dependency steps
-    const int variant = g_slice_last = slice_variant(n, (c0->nmb + c0->mbw + 2 * c0->mbh - 3) / (c0->mbw + 2 * c0->mbh - 2));
-    int grid = slice_grid(variant);
     if (grid > total) grid = total;
     if (variant) k_slice_encode_warp<<<grid, 32, 0, st>>>(dj, n, sched);
     else k_slice_encode<<<grid, HLB_CTA_THREADS, 0, st>>>(dj, n, sched);
     HLB_CUDA(cudaGetLastError());
-    for (int i = 0; i < n; ++i) ctxs[i]->frame_count++;
+    HLB_CUDA(cudaEventRecord(c0->ev_done, st));
+    c0->abort_state = -1;
+    for (int i = 0; i < n; ++i) {
+        ctxs[i]->frame_count++;
+        ctxs[i]->batch_owner = c0;
+        if (ctxs[i]->stream != st) HLB_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, c0->ev_done, 0));
+    }
     return HLB200_OK;
 }
 
@@ -459,6 +545,7 @@ int hlb200_slice_status(hlb200_ctx_t* c, int* out16)
 {
     if (!c || !out16) return HLB200_ERR_INVALID_PARAMETER;
     for (int k = 0; k < 16; ++k) out16[k] = 0;
+    if (c->batch_owner) c = c->batch_owner;   // the scheduler words live in the first context of the batch
     if (!c->d_sched || !c->last_sched) return HLB200_OK;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
     HLB_CUDA(cudaMemcpy(out16, c->last_sched, sizeof(int) * 16, cudaMemcpyDeviceToHost));
@@ -470,7 +557,7 @@ int hlb200_records_download(hlb200_ctx_t* c, hlb200_mb_record_t* out_records)
     if (!c || !out_records) return HLB200_ERR_INVALID_PARAMETER;
     HLB_CUDA(cudaMemcpyAsync(out_records, c->d_records, sizeof(hlb200_mb_record_t) * (size_t)c->nmb, cudaMemcpyDeviceToHost, c->stream));
     HLB_CUDA(cudaStreamSynchronize(c->stream));
-    return HLB200_OK;
+    return slice_check_abort(c);   // an aborted launch leaves macroblocks unencoded: never hand such records to a writer
 }
 
 int hlb200_slice_encode(hlb200_ctx_t* ctx, const hlb200_slice_params_t* params, hlb200_mb_record_t* out_records)

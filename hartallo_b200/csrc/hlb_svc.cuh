@@ -338,17 +338,23 @@ HLB_HD unsigned svc_luma_cbp(const SvcXchg& X)
 // _hl_codec_264_decode_svc_resample_intra_colour_comps decode_svc.c:2864 -> array construction :2952 (in an I picture every reference macroblock is intra: the
 // array is a clamped gather, (G-280)/(G-281)) -> _hl_codec_264_decode_svc_interpol_intra_base :3071 (vertical pass (G-301), horizontal pass + clip (G-305);
 // chroma always takes the two-tap table, :3116,:3150), sample locations by utils.c:1064-1157 (G.6.3) for frame macroblocks, no cropping, chroma phases 0
-// (sps.c:810-813), level_idc <= 30 (shift 16, (G-43)).  The reference's per-macroblock window offsets are multiples of 16 samples, so the result is a function of
-// the plane position only: one output sample per call, no state.
-struct SvcRsAxis { int scale, add; };   // (G-45), (G-48) with shift = 16
-HLB_HD SvcRsAxis svc_rs_axis(int refDim, int scaledDim)
+// (sps.c:810-813); fixed-point precision (G-43): shift = 16 for level_idc <= 30, else 31 - ceil(log2(refDim)) (QCIF -> CIF -> 4CIF runs its top layer at the
+// latter).  The reference's per-macroblock window offsets are multiples of 16 samples, so the result is a function of the plane position only: one output
+// sample per call, no state.  For a reference dimension that is a power of two and level_idc > 30 the reference's int32 `refDim << shift` is 2^31 (undefined): refused
+// by the callers (svc_rs_precision_ok).
+struct SvcRsAxis { int scale, add, shift4; };   // (G-45), (G-48), shift - 4
+HLB_HD int svc_ceil_log2(int v) { int k = 0; while ((1 << k) < v) ++k; return k; }
+HLB_HD bool svc_rs_precision_ok(int refDim, int level_idc) { return level_idc <= 30 || (refDim & (refDim - 1)) != 0; }
+HLB_HD SvcRsAxis svc_rs_axis(int refDim, int scaledDim, int level_idc)
 {
     SvcRsAxis a;
-    a.scale = ((refDim << 16) + (scaledDim >> 1)) / scaledDim;
-    a.add = (((refDim * 2) << 14) + (scaledDim >> 1)) / scaledDim + (1 << 11);
+    const int shift = level_idc <= 30 ? 16 : 31 - svc_ceil_log2(refDim);
+    a.scale = ((refDim << shift) + (scaledDim >> 1)) / scaledDim;
+    a.add = (((refDim * 2) << (shift - 2)) + (scaledDim >> 1)) / scaledDim + (1 << (shift - 5));
+    a.shift4 = shift - 4;
     return a;
 }
-HLB_HD int svc_rs_ref16(int p, const SvcRsAxis& a) { return ((p * a.scale + a.add) >> 12) - 8; }   // (G-59)/(G-60), deltaX = 8
+HLB_HD int svc_rs_ref16(int p, const SvcRsAxis& a) { return ((p * a.scale + a.add) >> a.shift4) - 8; }   // (G-59)/(G-60), deltaX = 8
 
 // Table G-9 (tables.h:626-643), 4 signed bytes per phase packed low byte first; chroma: {32 - 2p, 2p} (tables.h:647-664)
 HLB_TABLE static const uint32_t kSvcRsLuma[16] = { 0x00002000u, 0xFF0220FFu, 0xFF041FFEu, 0xFF061EFDu, 0xFF081CFDu, 0xFF0B1AFCu, 0xFE0E18FCu, 0xFD1016FDu,

@@ -141,6 +141,19 @@ static void glue_apply(hl_codec_264_mb_t* p_mb, const hlb200_mb_record_t* r, int
 
 extern HL_ERROR_T __real_hl_codec_264_nal_slice_data_encode(hl_codec_264_t*, hl_codec_264_encode_slice_data_t*);
 
+/* Settings the device path does not reproduce are REFUSED, never silently diverged from and never handed to the reference's CPU path:
+ *   deblock_flag != 0        in-loop filter (deblock.c:192, called slice.c:1897) -- library default 1 (hl_types.h:69)
+ *   me_early_term_flag != 0  early termination of the search (slice.c:1739-1757, rdo.c:889-1160) -- library default 1 (hl_types.h:67)
+ *   rate control             QP changes per picture / macroblock (rc.c)
+ * test_encoder.c:139-140 itself runs with rc_bitrate = -1 and deblock_flag = 0. */
+static HL_ERROR_T glue_check_settings(const hl_codec_264_t* p_codec)
+{
+    if (p_codec->pc_base->deblock_flag) { HL_DEBUG_ERROR("hlb200: deblock_flag = 1 is not implemented by the device path (set deblock_flag = 0)"); return HL_ERROR_NOT_IMPLEMENTED; }
+    if (p_codec->pc_base->me_early_term_flag) { HL_DEBUG_ERROR("hlb200: me_early_term_flag = 1 is not implemented by the device path (set me_early_term_flag = 0)"); return HL_ERROR_NOT_IMPLEMENTED; }
+    if (p_codec->encoder.rc.b_enabled) { HL_DEBUG_ERROR("hlb200: rate control is not implemented by the device path (set rc_bitrate <= 0)"); return HL_ERROR_NOT_IMPLEMENTED; }
+    return HL_ERROR_SUCCESS;
+}
+
 /* ================================================================================================================================
  * SVC enhancement layers (currDQId > 0).  The reference does no search there (base_mode_flag = 1 for every macroblock): what it computes per
  * macroblock is (a) the inter-layer derivation of partitions / vectors (P) or the resampling of the base reconstruction (I) -- host code, serial,
@@ -157,16 +170,11 @@ typedef struct glue_svc_layer_s {
     int w, h, nmb;
     hlb200_mb_motion_t* motion;
     hlb200_mb_coeffs_t* coeffs;
-    uint8_t* valid;          /* 0: a macroblock without partitions that precedes every macroblock with partitions of its picture: the reference codes it against
-                              * scratch memory left by an earlier picture -- left to the reference's own function */
-    uint8_t *pred, *rec;     /* tight Y|U|V */
+    uint8_t* rec;            /* tight Y|U|V */
 } glue_svc_layer_t;
 static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
 static glue_svc_layer_t* g_svc_active = NULL;
 static int g_svc_intra = 0;
-
-extern HL_ERROR_T _hl_codec_264_decode_svc_resample_intra_colour_comps(hl_codec_264_t* p_codec, hl_codec_264_mb_t* p_mb, int32_t chromaFlag, int32_t iCbCr, int32_t mbW,
-                                                                        int32_t mbH, int32_t mbPred[16][16]);   /* source/h264/hl_codec_264_decode_svc.c:216 */
 
 /* the part of the two guess functions that precedes the prediction (rdo.c:1318-1346 / rdo.c:353-368): defaults + G.8.1.5.1 (+ G.8.4.1 for P) */
 static HL_ERROR_T glue_svc_derive(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec, int intra)
@@ -226,74 +234,65 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     const size_t ysz = (size_t)W * H, csz = (size_t)Wc * Hc;
     glue_svc_layer_t* L;
     HL_ERROR_T err;
-    int rc, qp = -1, x, y, last_with_parts = -1, dev_rs = 0, level_idc = 0;
+    int rc, qp = -1, last_with_parts = -1, dev_rs = 0, level_idc = 0;
     uint32_t addr;
-    static HL_ALIGNED(16) int32_t pl[16][16], pcb[16][16], pcr[16][16];
 
     if (li <= 0 || li >= GLUE_SVC_MAX_LAYERS || (p_codec->layers.currDQId & 15) || p_esd->i_mb_start != 0 || p_esd->i_mb_end != (int32_t)hdr->PicSizeInMbs) {
         HL_DEBUG_ERROR("hlb200: only single-slice spatial enhancement layers are supported by the device path");
         return HL_ERROR_NOT_IMPLEMENTED;
     }
-    /* I pictures: the Intra_Base resampling (rdo.c:363-377 -> decode_svc.c:2864) runs on the device too when the picture is inside what
-     * hlb200_dev_svc_resample_intra_batch is pinned for (frame macroblocks, no cropping offsets, the chroma phases sps.c:810-813 writes, unconstrained resampling,
-     * level_idc <= 30 as utils.c:1075,1123 reads it); otherwise the host resamples macroblock by macroblock as before.  HLB200_GLUE_HOST_RESAMPLE=1 forces the host path. */
-    if (intra && !getenv("HLB200_GLUE_HOST_RESAMPLE")) {
+    /* I pictures: the Intra_Base resampling (rdo.c:363-377 -> decode_svc.c:2864) runs on the device (hlb200_svc_layer_picture_resampled) when the picture is inside what
+     * hlb200_dev_svc_resample_intra_batch is pinned for (frame macroblocks, no cropping offsets, the chroma phases sps.c:810-813 writes, unconstrained resampling;
+     * level_idc as utils.c:1075,1123 reads it selects the precision there).  Anything else is REFUSED (HL_ERROR_NOT_IMPLEMENTED): the product path never runs the reference's CPU resampling. */
+    if (intra) {
         const hl_codec_264_nal_sps_t* sps = hdr->pc_pps->pc_sps;
         const hl_codec_264_layer_t* top = p_codec->layers.p_list[(p_codec->layers.currDQId >> 4) << 4];
-        /* Pictures of fewer than 64 macroblocks stay on the host path: the reference sizes its window array as PicSizeInMbs << 8 BYTES (layer.c:202) but fills it with
-         * refArrayW x refArrayH int32 (48x48 at the dyadic ratio, 64x64 at 1:1), so below 36 / 64 macroblocks it writes past the allocation and its prediction depends
-         * on the heap (traced: saturated rows in 96x32 pictures).  Only the reference's own function in the same process reproduces that. */
-        dev_rs = mbw * (H >> 4) >= 64 && pc_layer->pc_ref && pc_layer->pc_ref->pc_fs_curr && pc_layer->pc_ref->pc_fs_curr->p_pict && pc_layer->RefLayerFrameMbsOnlyFlag && sps->frame_mbs_only_flag &&
+        /* Small pictures are refused as well: the reference sizes its window array as PicSizeInMbs << 8 BYTES (layer.c:202) but fills it with refArrayW x refArrayH int32
+         * (48x48 at the dyadic ratio, 64x64 at 1:1), so below 36 / 64 macroblocks it writes past the allocation and its own prediction depends on the heap (traced:
+         * saturated rows in 96x32 pictures) -- there is no reference behaviour to reproduce. */
+        const int dyadic = pc_layer->RefLayerPicWidthInSamplesL * 2 == (uint32_t)W && pc_layer->RefLayerPicHeightInSamplesL * 2 == (uint32_t)H;
+        dev_rs = mbw * (H >> 4) >= (dyadic ? 36 : 64) && pc_layer->pc_ref && pc_layer->pc_ref->pc_fs_curr && pc_layer->pc_ref->pc_fs_curr->p_pict && pc_layer->RefLayerFrameMbsOnlyFlag && sps->frame_mbs_only_flag &&
                  !hdr->field_pic_flag && sps->ChromaArrayType == 1 && sps->p_svc && sps->p_svc->chroma_phase_x_plus1_flag == 1 && sps->p_svc->chroma_phase_y_plus1 == 1 &&
                  hdr->ext.svc.ref_layer_chroma_phase_x_plus1_flag == 1 && hdr->ext.svc.ref_layer_chroma_phase_y_plus1 == 1 && !hdr->ext.svc.constrained_intra_resampling_flag &&
                  hdr->ext.svc.ScaledRefLayerLeftOffset == 0 && hdr->ext.svc.ScaledRefLayerTopOffset == 0 && hdr->ext.svc.ScaledRefLayerPicWidthInSamplesL == W &&
-                 hdr->ext.svc.ScaledRefLayerPicHeightInSamplesL == H && top && top->pc_slice_hdr && top->pc_slice_hdr->pc_pps->pc_sps->level_idc <= 30 &&
+                 hdr->ext.svc.ScaledRefLayerPicHeightInSamplesL == H && top && top->pc_slice_hdr &&
                  !(pc_layer->RefLayerPicWidthInSamplesL & 15) && !(pc_layer->RefLayerPicHeightInSamplesL & 15) && pc_layer->RefLayerPicWidthInSamplesL <= W &&
                  pc_layer->RefLayerPicHeightInSamplesL <= H;
-        if (dev_rs) level_idc = (int)top->pc_slice_hdr->pc_pps->pc_sps->level_idc;
+        if (!dev_rs) {
+            HL_DEBUG_ERROR("hlb200: Intra_Base resampling of this enhancement-layer I picture is not implemented by the device path (fewer than %d macroblocks, cropping, chroma phases or field coding)", dyadic ? 36 : 64);
+            return HL_ERROR_NOT_IMPLEMENTED;
+        }
+        level_idc = (int)top->pc_slice_hdr->pc_pps->pc_sps->level_idc;
     }
     L = &g_svc[li];
     if (!L->ctx || L->w != W || L->h != H) {
         const char* dev = getenv("HLB200_DEVICE");
-        if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->valid); free(L->pred); free(L->rec); }
+        if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; }
         if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
         if ((rc = hlb200_stream_create(W, H, 1, &L->ctx))) return glue_fail("hlb200_stream_create", rc);
         L->w = W; L->h = H; L->nmb = mbw * (H >> 4);
         L->motion = (hlb200_mb_motion_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_motion_t));
         L->coeffs = (hlb200_mb_coeffs_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_coeffs_t));
-        L->valid = (uint8_t*)calloc((size_t)L->nmb, 1);
-        L->pred = (uint8_t*)malloc(ysz + 2 * csz);
         L->rec = (uint8_t*)malloc(ysz + 2 * csz);
-        if (!L->motion || !L->coeffs || !L->valid || !L->pred || !L->rec) return HL_ERROR_OUTOFMEMMORY;
+        if (!L->motion || !L->coeffs || !L->rec) {
+            hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); L->motion = NULL; L->coeffs = NULL; L->rec = NULL;
+            return HL_ERROR_OUTOFMEMMORY;
+        }
     }
     /* (a) host, serial: inferred motion (P) or resampled base-layer prediction (I) of every macroblock */
     memset(L->motion, 0, sizeof(hlb200_mb_motion_t) * (size_t)L->nmb);
     for (addr = 0; addr < (uint32_t)L->nmb; ++addr) {
         hl_codec_264_mb_t* p_mb;
-        const int mbx = (int)(addr % (uint32_t)mbw), mby = (int)(addr / (uint32_t)mbw);
         if ((err = glue_svc_loop_prologue(p_codec, p_esd, addr, &p_mb))) return err;
         if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;
         if (qp < 0) qp = p_mb->QPy;
         if (p_mb->QPy != qp) { HL_DEBUG_ERROR("hlb200: per-macroblock QP is not supported"); return HL_ERROR_NOT_IMPLEMENTED; }
-        if (intra && dev_rs) L->valid[addr] = 1;
-        else if (intra) {
-            if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 0, -1, 16, 16, pl))) return err;
-            if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 0, 8, 8, pcb))) return err;
-            if ((err = _hl_codec_264_decode_svc_resample_intra_colour_comps(p_codec, p_mb, 1, 1, 8, 8, pcr))) return err;
-            for (y = 0; y < 16; ++y) for (x = 0; x < 16; ++x) L->pred[(size_t)(mby * 16 + y) * W + mbx * 16 + x] = (uint8_t)pl[y][x];
-            for (y = 0; y < 8; ++y) for (x = 0; x < 8; ++x) {
-                L->pred[ysz + (size_t)(mby * 8 + y) * Wc + mbx * 8 + x] = (uint8_t)pcb[y][x];
-                L->pred[ysz + csz + (size_t)(mby * 8 + y) * Wc + mbx * 8 + x] = (uint8_t)pcr[y][x];
-            }
-            L->valid[addr] = 1;
-        }
-        else {
+        if (!intra) {
             hlb200_mb_motion_t* m = &L->motion[addr];
             const int n = p_mb->NumMbPart, pw = p_mb->MbPartWidth, ph = p_mb->MbPartHeight;
             const int mode = (n == 1 && pw == 16 && ph == 16) ? 0 : (n == 2 && pw == 16 && ph == 8) ? 1 : (n == 2 && pw == 8 && ph == 16) ? 2 : (n == 4 && pw == 8 && ph == 8) ? 3 : -1;
             int p, ok = mode >= 0;
             for (p = 0; ok && p < n; ++p) ok = p_mb->NumSubMbPart[p] >= 1 && p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == 0 && p_mb->partWidth[p][0] == pw && p_mb->partHeight[p][0] == ph;
-            L->valid[addr] = (uint8_t)ok;
             if (!ok && getenv("HLB200_GLUE_DEBUG"))
                 fprintf(stderr, "hlb200 glue: layer %d mb %u: NumMbPart %d %dx%d NumSubMbPart %d %d %d %d predFlagL0 %d %d %d %d refIdxL0 %d %d %d %d e_type %d\n", li, addr, n, pw, ph,
                         p_mb->NumSubMbPart[0], p_mb->NumSubMbPart[1], p_mb->NumSubMbPart[2], p_mb->NumSubMbPart[3], p_mb->predFlagL0[0], p_mb->predFlagL0[1], p_mb->predFlagL0[2],
@@ -307,20 +306,26 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
                 /* base macroblock intra: no partition, the reference's prediction loops do not run and it codes the macroblock against what its scratch blocks
                  * still hold = the prediction of the last macroblock that had partitions; the device does the same (hlb_svc.cuh: SvcPredSrc) */
                 m->pad[0] = 1; m->pad[1] = (uint8_t)(last_with_parts & 255); m->pad[2] = (uint8_t)(last_with_parts >> 8);
-                L->valid[addr] = 1;
+            }
+            else {
+                /* A macroblock without partitions that precedes every macroblock with partitions of its picture: the reference codes it against scratch memory an
+                 * EARLIER picture left (after a layer's I picture: the I_BL function's int32 temporaries, rdo.c:1304-1312 / rdo.c:344-349 / hl_memory.h:226-241).
+                 * Not reproduced on the device, and never handed to the reference's CPU function: the picture is refused. */
+                HL_DEBUG_ERROR("hlb200: layer %d macroblock %u has no partition and no earlier macroblock of the picture to inherit a prediction from: not implemented by the device path", li, addr);
+                return HL_ERROR_NOT_IMPLEMENTED;
             }
         }
     }
     /* (b) device: one call for the picture */
     if ((rc = hlb200_frame_upload(L->ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, Wc))) return glue_fail("hlb200_frame_upload", rc);
-    if (intra && dev_rs) {
+    if (intra) {
         const hl_codec_264_pict_t* rp = pc_layer->pc_ref->pc_fs_curr->p_pict;   /* what decode_svc.c:2970 reads: the reference layer's reconstruction of this access unit */
         rc = hlb200_svc_layer_picture_resampled(L->ctx, 1, qp, hdr->pc_pps->chroma_qp_index_offset, rp->pc_data_y, rp->pc_data_u, rp->pc_data_v,
                                                 (int)pc_layer->RefLayerPicWidthInSamplesL, (int)pc_layer->RefLayerPicHeightInSamplesL, level_idc, L->coeffs);
     }
-    else if (intra) rc = hlb200_svc_layer_picture(L->ctx, -1, 1, qp, hdr->pc_pps->chroma_qp_index_offset, NULL, L->pred, L->pred + ysz, L->pred + ysz + csz, L->coeffs);
     else {
-        /* the layer's reference picture travels from the host DPB every time: macroblocks the host coded itself (valid = 0) are part of it */
+        /* the layer's reference picture travels from the host DPB (the picture this context reconstructed last time; kept as an upload so that a layer whose
+         * reference list was reordered by the host still predicts from what the reference would) */
         const hl_codec_264_pict_t* ref = pc_layer->pobj_poc->RefPicList0[0] ? pc_layer->pobj_poc->RefPicList0[0]->p_pict : NULL;
         if (!ref) return HL_ERROR_INVALID_STATE;
         if ((rc = hlb200_slot_upload(L->ctx, 0, ref->pc_data_y, ref->pc_data_u, ref->pc_data_v))) return glue_fail("hlb200_slot_upload", rc);
@@ -374,12 +379,9 @@ static HL_ERROR_T glue_svc_apply(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_code
     return HL_ERROR_SUCCESS;
 }
 
-extern HL_ERROR_T __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t*, hl_codec_264_t*);
 HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
 {
     if (!g_svc_active) return HL_ERROR_INVALID_STATE;
-    /* no partition and nothing to inherit from inside this picture (see glue_svc_slice): the host keeps it */
-    if (p_mb->u_addr < (uint32_t)g_svc_active->nmb && !g_svc_active->valid[p_mb->u_addr]) return __real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(p_mb, p_codec);
     return glue_svc_apply(p_mb, p_codec, 0);
 }
 HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_intra_pred_svc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec)
@@ -396,7 +398,9 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
     const int W = (int)hdr->PicWidthInSamplesL, H = (int)hdr->PicHeightInSamplesL;
     hlb200_slice_params_t prm;
     int rc, u, s, cur = -1;
+    HL_ERROR_T err;
 
+    if ((err = glue_check_settings(p_codec))) return err;
     if (p_codec->layers.currDQId > 0) return glue_svc_slice(p_codec, p_esd);
 #ifdef HLB200_GLUE_HOST_BASE_LAYER   /* test builds without a GPU: the base layer stays on the reference's CPU path, only the enhancement-layer hook is exercised */
     return __real_hl_codec_264_nal_slice_data_encode(p_codec, p_esd);

@@ -200,7 +200,7 @@ HLB200_API int hlb200_svc_layer_picture(hlb200_ctx_t* ctx, int ref_slot, int cur
                                         const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v, hlb200_mb_coeffs_t* out_coeffs);
 /* The same for an I picture with the Intra_Base resampling on the device too (hlb200_dev_svc_resample_intra_batch below; decode_svc.c:2864-3200): the caller passes
  * the reference layer's reconstruction (host planes, ref_width x ref_height) instead of full-size prediction planes.  Restrictions of that entry point apply
- * (level_idc <= 30, no cropping offsets, the reference's chroma phases); callers fall back to hlb200_svc_layer_picture with host-resampled planes otherwise. */
+ * (no cropping offsets, the reference's chroma phases, no power-of-two reference dimension when level_idc > 30): HLB200_ERR_INVALID_PARAMETER otherwise. */
 HLB200_API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* ctx, int cur_slot, int qp, int chroma_qp_index_offset, const uint8_t* ref_y, const uint8_t* ref_u,
                                                   const uint8_t* ref_v, int ref_width, int ref_height, int level_idc, hlb200_mb_coeffs_t* out_coeffs);
 
@@ -254,8 +254,9 @@ HLB200_API int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8
  * (ref_width x ref_height, tight planes, n_pics pictures ref_frame_stride bytes apart) is resampled into the prediction planes of the current layer
  * (width x height, frame_stride bytes apart, multiple of 4) that hlb200_dev_svc_bl_recon_batch consumes -- the planes the reference builds macroblock by macroblock
  * on the host.  Valid for pictures whose reference-layer macroblocks are all intra (I pictures: the only case the reference's encoder uses it for), frame
- * macroblocks, no cropping offsets, chroma phases as the reference's SPS writes them (sps.c:810-813), level_idc <= 30 (the fixed-point precision of (G-43);
- * larger values return HLB200_ERR_INVALID_PARAMETER: no reference behaviour to pin them on). */
+ * macroblocks, no cropping offsets, chroma phases as the reference's SPS writes them (sps.c:810-813).  level_idc selects the fixed-point precision of (G-43)
+ * (16 bits up to level 3.0, 31 - ceil(log2(dimension)) above); with level_idc > 30 a reference dimension (luma or chroma) that is a power of two makes the
+ * reference's own int32 arithmetic overflow -- no behaviour to pin, HLB200_ERR_INVALID_PARAMETER. */
 HLB200_API int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d_ref_u, const uint8_t* d_ref_v, int ref_width, int ref_height,
                                                    uint8_t* d_pred_y, uint8_t* d_pred_u, uint8_t* d_pred_v, int width, int height, int n_pics, size_t ref_frame_stride,
                                                    size_t frame_stride, int level_idc, void* cuda_stream);
@@ -267,6 +268,10 @@ HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y
  * Launches `blocks` x 256 threads, each doing `iters` x 32 independent IADD3/LOP3; writes one word per thread to d_sink; *ops_out = integer
  * operations executed. */
 HLB200_API int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink, void* cuda_stream, uint64_t* ops_out);
+
+/* ---- device self-test: the packed-instruction formulations of the search's 4x4 primitives (prediction at all 16 fractional positions, trial encode at
+ * QP 12..51) against the plain formulations, both run on the device over `blocks` x 64 threads of pseudo-random inputs; *mismatches_out = 0 when they agree. */
+HLB200_API int hlb200_dev_selftest(int blocks, unsigned seed, int* mismatches_out);
 
 #ifdef __cplusplus
 }

@@ -459,7 +459,7 @@ static void md5_hex(const uint8_t* p, size_t n, char out[33])
 
 int main(int argc, char** argv)
 {
-    int w = 352, h = 288, frames = 3, qp = 31, me_range = 16, refs = 1, gen = 1, gop = 400, early = 0, layers = 1, l, i;
+    int w = 352, h = 288, frames = 3, qp = 31, me_range = 16, refs = 1, gen = 1, gop = 400, early = 0, deblock = 0, defaults = 0, layers = 1, l, i;
     uint32_t seed = 1;
     const char *in_path = NULL, *out_path = NULL, *trace_path = NULL, *recon_path = NULL, *dump_in = NULL;
     const struct hl_codec_plugin_def_s* plugin = NULL;
@@ -480,6 +480,8 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--gop") && i + 1 < argc) gop = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--layers") && i + 1 < argc) layers = atoi(argv[++i]);   /* SVC spatial layers: layer l is (w << l) x (h << l), source/test_encoder.c:150-202 */
         else if (!strcmp(argv[i], "--early-term") && i + 1 < argc) early = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--deblock") && i + 1 < argc) deblock = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--defaults")) defaults = 1;   /* keep what hl_codec_create sets for deblock_flag / me_early_term_flag (both 1, hl_types.h:67,69) */
         else if (!strcmp(argv[i], "--gen") && i + 1 < argc) { ++i; gen = !strcmp(argv[i], "g2") ? 2 : 1; }
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "--in") && i + 1 < argc) in_path = argv[++i];
@@ -521,14 +523,14 @@ int main(int argc, char** argv)
     codec->qp = qp;
     codec->fps.num = 1; codec->fps.den = 30;
     codec->rc_bitrate = -1;
-    codec->deblock_flag = 0;
+    if (!defaults) codec->deblock_flag = deblock;
     codec->threads_count = 1;
     codec->max_ref_frame = refs;
     codec->distortion_mesure_type = HL_VIDEO_DISTORTION_MESURE_TYPE_SAD;
     codec->me_type = (HL_VIDEO_ME_TYPE_INTEGER | HL_VIDEO_ME_TYPE_HALF | HL_VIDEO_ME_TYPE_QUATER);
     codec->me_part_types = HL_VIDEO_ME_PART_TYPE_ALL;
     codec->me_subpart_types = HL_VIDEO_ME_SUBPART_TYPE_ALL;
-    codec->me_early_term_flag = early;
+    if (!defaults) codec->me_early_term_flag = early;
 
     if (layers > 1)
         for (l = 0; l < layers; ++l)

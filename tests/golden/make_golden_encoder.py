@@ -18,7 +18,12 @@ CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range[, max_ref_frame]
     ("g2_small_q12", "g2", 7, 64, 48, 6, 12, 64),
     ("g2_cif_q38", "g2", 2, 352, 288, 3, 38, 8),
     ("g2_qcif_ref4", "g2", 9, 176, 144, 6, 29, 24, 4),
-    ("g1_cif_10", "g1", 12345, 352, 288, 10, 31, 16),      # BASELINE.json configs[0]: CIF, 1 ref, quarter-pel ME +-16, 10 frames   # BASELINE.json configs[2]: max_ref_frame = 4 (at the reference's real feature set)
+    ("g1_cif_10", "g1", 12345, 352, 288, 10, 31, 16),      # BASELINE.json configs[0]: CIF, 1 ref, quarter-pel ME +-16, 10 frames
+    # the configuration bench.py quotes its number on (BASELINE.json configs[1] at the reference's real feature set): 1920x1088, QP 31, ME +-32, 1 ref,
+    # G1 with the seed of bench stream 0, IDR + 7 P pictures; the same on all-inter content (G2) and with max_ref_frame = 4 (configs[2])
+    ("g1_1080p_q31", "g1", 12345, 1920, 1088, 8, 31, 32),
+    ("g2_1080p_q31", "g2", 3, 1920, 1088, 4, 31, 32),
+    ("g1_1080p_ref4", "g1", 12345, 1920, 1088, 6, 31, 32, 4),
 ]
 
 
@@ -48,7 +53,8 @@ def build(name, gen, seed, w, h, frames, qp, me_range, refs=1):
     cbp = np.zeros((frames, nmb, 3), np.uint8)      # coded_block_pattern, luma, chroma
     tc_luma = np.zeros((frames, nmb, 16), np.uint8)
     i4 = np.zeros((frames, nmb, 16), np.uint8)
-    lvl_md5 = np.zeros((frames, nmb), "U32")
+    lvl_md5 = np.zeros((frames, nmb), "U32" if frames * nmb < 20000 else "U8")   # big pictures: the first 8 hex digits of each level digest
+    mad = np.zeros((frames, nmb), np.int32)                                          # *pi_mad of the decision that stood (rdo.c:1216: best distortion)
     for n in range(frames):
         for a in range(nmb):
             r, q = rec[(n, a)], st[(n, a)]
@@ -71,8 +77,9 @@ def build(name, gen, seed, w, h, frames, qp, me_range, refs=1):
                 lv = np.concatenate([r["i16_dc"].reshape(1, 16), r["i16_ac"]])
             else:
                 lv = np.zeros((1, 1), np.int32)
-            lvl_md5[n, a] = hashlib.md5(lv.astype(np.int16).tobytes()).hexdigest()
-    out.update(kind=kind, mb_type=mb_type, mv=mv, mvd=mvd, nparts=nparts, cbp=cbp, tc_luma=tc_luma, i4_mode=i4, level_md5=lvl_md5)
+            lvl_md5[n, a] = hashlib.md5(lv.astype(np.int16).tobytes()).hexdigest()[:lvl_md5.dtype.itemsize // 4]
+            mad[n, a] = r["mad"]
+    out.update(kind=kind, mb_type=mb_type, mv=mv, mvd=mvd, nparts=nparts, cbp=cbp, tc_luma=tc_luma, i4_mode=i4, level_md5=lvl_md5, mad=mad)
     np.savez_compressed(os.path.join(HERE, "encoder_%s.npz" % name), **out)
     print(name, s["md5"], "kinds", np.bincount(kind.reshape(-1), minlength=4))
 

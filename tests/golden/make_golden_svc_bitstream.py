@@ -1,5 +1,6 @@
 """Generates tests/golden/svc_bitstream.json: size and MD5 of the multi-layer (SVC, dyadic spatial) bitstreams the UNMODIFIED reference produces
-(oracle/_ref/hl_ref_driver --layers N, the counterpart of source/test_encoder.c:150-202) on configurations that contain no macroblock the glue leaves to the host."""
+(oracle/_ref/hl_ref_driver --layers N, the counterpart of source/test_encoder.c:150-202) on configurations the drop-in accepts (it refuses enhancement-layer I pictures of fewer than 36 macroblocks and macroblocks that would be coded against scratch memory of an
+earlier picture; tests/test_svc_inter.py checks the refusals)."""
 import json
 import os
 import subprocess
@@ -17,7 +18,7 @@ CONFIGS = {
     # Intra4x4 macroblocks inside base-layer P pictures: the enhancement layers derive motion from the lower-case vector such a macroblock kept from its last
     # inter commit (host/hlb200_glue.c: glue_apply); both differed through the whole glue before that was reproduced
     "g2_i4_in_p_2layer": ["--size", "64", "64", "--layers", "2", "--frames", "4", "--gen", "g2", "--seed", "8931", "--qp", "29"],
-    "g2_i4_in_p_3layer": ["--size", "48", "16", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "1865", "--qp", "22"],
+    "g2_3layer_48_q34": ["--size", "48", "48", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "22", "--qp", "34"],   # smallest layers the drop-in accepts (36 macroblocks at the dyadic ratio)
 }
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "svc_bitstream.json")
 

@@ -20,6 +20,8 @@ import reftrace as rt
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38", "g2_qcif_ref4", "g1_cif_10"]
+# the configuration bench.py quotes its number on (1920x1088, QP 31, ME +-32, G1 seed of bench stream 0), its all-inter twin (G2) and max_ref_frame = 4: GPU tier only
+CONFIGS_1080P = ["g1_1080p_q31", "g2_1080p_q31", "g1_1080p_ref4"]
 
 
 def refs_of(g):
@@ -65,7 +67,10 @@ def check_frame(g, n, rec, recon, what):
         assert (int(r["coded_block_pattern"]), int(r["cbp_luma"]), int(r["cbp_chroma"])) == tuple(int(v) for v in g["cbp"][n, a]), (what, n, a, "cbp")
         if k == 3:
             assert np.array_equal(r["i4_pred_mode"], g["i4_mode"][n, a]), (what, n, a, "i4 modes")
-        assert level_md5(k, r) == str(g["level_md5"][n, a]), (what, n, a, "levels")
+        gm = str(g["level_md5"][n, a])
+        assert level_md5(k, r)[:len(gm)] == gm, (what, n, a, "levels")
+        if k != 0 and "mad" in g.files:   # *pi_mad of the decision that stood: the search's best distortion (north star: "identical MVs and costs")
+            assert int(r["mad"]) == int(g["mad"][n, a]), (what, n, a, "mad", int(r["mad"]), int(g["mad"][n, a]))
 
 
 def run_emu(w, h, frames, qp, me_range, yuv_frames, tag, refs=1):
@@ -103,7 +108,7 @@ def variant(request):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("name", CONFIGS + CONFIGS_1080P)
 def test_slice_encode_vs_reference(name, variant):
     from hartallo_b200 import lib as hl
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
@@ -206,7 +211,7 @@ B200_ENCODER = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder")
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(B200_ENCODER), reason="oracle/_ref/hl_b200_encoder not built (needs the reference tree at build time)")
-@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("name", CONFIGS + CONFIGS_1080P)
 def test_bitstream_md5_drop_in(name):
     """The drop-in itself: the reference's unmodified host code (headers, CAVLC writer, DPB bookkeeping) linked with
     host/hlb200_glue.c + libhl_b200.so must emit the same bitstream, byte for byte, as the all-CPU reference
@@ -221,7 +226,7 @@ def test_bitstream_md5_drop_in(name):
     assert got["md5"] == str(g["bitstream_md5"]), (got, str(g["bitstream_md5"]))
 
 
-@pytest.mark.parametrize("prog", ["check_interp", "check_cavlc"])
+@pytest.mark.parametrize("prog", ["check_interp", "check_cavlc", "check_fast"])
 def test_compact_primitives_equal_reference_formulation(prog):
     """the loop-form interpolation / register-only CAVLC length used by the kernels == the straightforward formulations
     (which the oracle pins against the reference), on random inputs incl. saturated content"""

@@ -31,16 +31,16 @@ def oracle_resample(ref_yuv, rw, rh, w, h, level_idc=0):
     return out
 
 
-def emu_resample(ref_yuv, rw, rh, w, h):
+def emu_resample(ref_yuv, rw, rh, w, h, level_idc=0):
     e = _emu_lib()
     e.svc_emu_resample_plane.restype = C.c_int
-    e.svc_emu_resample_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    e.svc_emu_resample_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     ref_yuv = np.ascontiguousarray(ref_yuv, np.uint8)
     out = np.zeros(w * h * 3 // 2, np.uint8)
     ro, oo = [0, rw * rh, rw * rh * 5 // 4], [0, w * h, w * h * 5 // 4]
     for pl in range(3):
         c = pl != 0
-        assert e.svc_emu_resample_plane(ref_yuv.ctypes.data + ro[pl], rw >> c, rh >> c, out.ctypes.data + oo[pl], w >> c, h >> c, int(c)) == 0
+        assert e.svc_emu_resample_plane(ref_yuv.ctypes.data + ro[pl], rw >> c, rh >> c, out.ctypes.data + oo[pl], w >> c, h >> c, int(c), level_idc) == 0
     return out
 
 
@@ -68,7 +68,7 @@ def test_oracle_vs_golden():
 
 
 @pytest.mark.skipif(not os.path.exists(reftrace.DRIVER), reason="oracle/_ref/hl_ref_driver only exists where the reference tree is available")
-@pytest.mark.parametrize("args", [("96", "64", "g1", "5", "24"), ("160", "96", "g2", "7", "36"), ("32", "64", "g2", "11", "45")])
+@pytest.mark.parametrize("args", [("96", "64", "g1", "5", "24"), ("160", "96", "g2", "7", "36"), ("32", "64", "g2", "11", "45"), ("176", "144", "g1", "1", "31")])
 def test_oracle_vs_live_reference(tmp_path, args):
     """3 spatial layers: the prediction the reference resampled for layer 2's I picture must equal the oracle's resampling of layer 1's reconstruction"""
     tr = str(tmp_path / "t.trace")
@@ -77,7 +77,9 @@ def test_oracle_vs_live_reference(tmp_path, args):
     pics = {p["dqid"]: p for p in svc_util.bl_pictures_from_trace(tr)}
     lo, hi = pics[16], pics[32]
     base = svc_util.planes_of_mb(lo["rec"], lo["w"], lo["h"])
-    assert np.array_equal(oracle_resample(base, lo["w"], lo["h"], hi["w"], hi["h"]), hi["ref"])
+    # level_idc as hl_codec_264_utils_guess_level (utils.c:15) assigns it to the top layer: above 30 once the picture exceeds 720x480
+    level = 31 if (hi["w"] > 720 or hi["h"] > 480) else 30
+    assert np.array_equal(oracle_resample(base, lo["w"], lo["h"], hi["w"], hi["h"], level), hi["ref"])
 
 
 def test_device_source_on_cpu_vs_golden():
@@ -85,11 +87,19 @@ def test_device_source_on_cpu_vs_golden():
     assert np.array_equal(emu_resample(base, rw, rh, w, h), pred)
 
 
-@pytest.mark.parametrize("rsz,sz", SIZES)
+def _pow2(v):
+    return v & (v - 1) == 0
+
+
+@pytest.mark.parametrize("rsz,sz", SIZES + [((352, 288), (704, 576)), ((176, 144), (240, 208)), ((48, 80), (112, 96))])
 def test_device_source_on_cpu_vs_oracle_random(rsz, sz):
+    """both fixed-point precisions of (G-43): level_idc <= 30 (16 bits) and above (31 - ceil(log2(dimension)); what QCIF -> CIF -> 4CIF uses for its top layer),
+    the latter wherever the reference's int32 arithmetic is defined (no power-of-two luma / chroma reference dimension)"""
     rng = np.random.default_rng(rsz[0] * 7 + sz[1])
     base = random_yuv(rng, *rsz)
     assert np.array_equal(emu_resample(base, rsz[0], rsz[1], sz[0], sz[1]), oracle_resample(base, rsz[0], rsz[1], sz[0], sz[1]))
+    if not any(_pow2(d) for d in (rsz[0], rsz[1], rsz[0] // 2, rsz[1] // 2)):
+        assert np.array_equal(emu_resample(base, rsz[0], rsz[1], sz[0], sz[1], 31), oracle_resample(base, rsz[0], rsz[1], sz[0], sz[1], 31))
 
 
 def test_abi_arguments():

@@ -388,3 +388,31 @@ def test_svc_bitstream_md5_drop_in(name):
     g = SVC_STREAMS[name]
     got = _encode(B200_ENCODER, g["args"])
     assert (got["bytes"], got["md5"]) == (g["bytes"], g["md5"]), (got, g)
+
+
+# ------------------------------------------------------ what the drop-in refuses ------------------------------------------------------
+def _run_expect_refusal(exe, args, needle):
+    out = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode != 0, "the drop-in produced a stream where it must refuse: " + out.stdout[-200:]
+    assert "not implemented" in out.stderr.lower() and needle in out.stderr, out.stderr[-600:]
+
+
+@pytest.mark.skipif(not os.path.exists(GLUE_FULL), reason="oracle/_ref/hl_glue_check_full only exists where the reference tree is available")
+@pytest.mark.parametrize("args,needle", [
+    (["--size", "64", "48", "--frames", "2", "--defaults"], "deblock_flag"),                 # hl_codec_create's own settings: deblock_flag = 1, me_early_term_flag = 1
+    (["--size", "64", "48", "--frames", "2", "--deblock", "1"], "deblock_flag"),
+    (["--size", "64", "48", "--frames", "2", "--early-term", "1"], "me_early_term_flag"),
+    (["--size", "48", "16", "--layers", "3", "--frames", "2", "--gen", "g2", "--seed", "1865", "--qp", "22"], "Intra_Base"),   # 12-macroblock enhancement I picture (layer.c:202)
+    (["--size", "48", "48", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "21", "--qp", "30"], "no partition"),    # coded against an earlier picture's scratch memory
+])
+def test_glue_refuses_what_it_does_not_reproduce(args, needle):
+    """No silent divergence and no CPU fallback: library-default settings (in-loop deblocking, early termination), enhancement-layer I pictures too small for the
+    reference's own window array and macroblocks the reference codes against stale scratch memory all end in HL_ERROR_NOT_IMPLEMENTED (host/hlb200_glue.c)."""
+    _run_expect_refusal(GLUE_FULL, args, needle)
+
+
+def test_glue_has_no_reference_cpu_path():
+    """the product glue neither calls the reference's own SVC decision function nor its CPU resampling (round-1 finding)"""
+    src = open(os.path.join(ROOT, "host", "hlb200_glue.c")).read()
+    assert "__real_hl_codec_264_rdo_mb_guess_best_inter_pred_svc" not in src
+    assert "_hl_codec_264_decode_svc_resample_intra_colour_comps(" not in src

@@ -29,6 +29,11 @@ struct CpuExec {
     int lane() const { return 0; }
     int nlanes() const { return 1; }
     void sync() const {}
+    // cross-lane reductions of the master warp: one lane here, so each is the identity
+    int reduce_min(int v) const { return v; }
+    int reduce_max(int v) const { return v; }
+    int reduce_add(int v) const { return v; }
+    void reduce_argmin(double&, int&) const {}
     int prev_sctr(int mb)
     {
         for (int a = mb - 1; a >= 0; --a)
@@ -80,6 +85,7 @@ int main(int argc, char** argv)
         { int q = qp < 0 ? 0 : (qp > 51 ? 51 : qp); static const unsigned char t[22] = {29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39}; f.qpc = q < 30 ? q : t[q - 30]; }
         f.is_p = n > 0; f.me_range = me_range < 1 ? 1 : (me_range > 64 ? 64 : me_range);
         f.lambda = 0.852 * (double)(1 << ((qp - 12) / 3));
+        frame_ctx_derive(f);
         int cur = 0;
         for (int s = 0; s <= refs; ++s) { bool used = false; for (int o : order) used |= (o == s); if (!used) { cur = s; break; } }
         // the reference searches num_ref_idx_l0_active_minus1 + 1 = 1 list entry whatever max_ref_frame is (slice.c:289-291, rdo.c:845);

@@ -43,9 +43,9 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_recon_batch(int bl
 }
 
 // CPU run of svc_resample_px (the body of k_svc_resample_intra): one plane, host pointers
-extern "C" __attribute__((visibility("default"))) int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma)
+extern "C" __attribute__((visibility("default"))) int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma, int level_idc)
 {
-    const hlb::SvcRsAxis ax = hlb::svc_rs_axis(refW, W), ay = hlb::svc_rs_axis(refH, H);
+    const hlb::SvcRsAxis ax = hlb::svc_rs_axis(refW, W, level_idc), ay = hlb::svc_rs_axis(refH, H, level_idc);
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) out[y * W + x] = hlb::svc_resample_px(ref, refW, refH, ax, ay, x, y, chroma != 0);
     return HLB200_OK;

@@ -91,6 +91,11 @@ struct CpuExec {   // the executor of tools/emu/emu_main.cpp: lanes become loops
     int lane() const { return 0; }
     int nlanes() const { return 1; }
     void sync() const {}
+    // cross-lane reductions of the master warp: one lane here, so each is the identity
+    int reduce_min(int v) const { return v; }
+    int reduce_max(int v) const { return v; }
+    int reduce_add(int v) const { return v; }
+    void reduce_argmin(double&, int&) const {}
     int prev_sctr(int mb)
     {
         for (int a = mb - 1; a >= 0; --a)
@@ -112,6 +117,7 @@ API int hlb200_slice_encode(hlb200_ctx_t* c, const hlb200_slice_params_t* p, hlb
     f.me_range = p->me_range < 1 ? 1 : (p->me_range > 64 ? 64 : p->me_range);
     f.num_refs = f.is_p ? p->num_refs : 0;
     f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));
+    hlb::frame_ctx_derive(f);
     f.src[0] = c->src; f.src[1] = c->src + ys; f.src[2] = c->src + ys + cs;
     f.cur[0] = c->slot[p->cur_slot]; f.cur[1] = f.cur[0] + ys; f.cur[2] = f.cur[1] + cs;
     for (int u = 0; u < f.num_refs; ++u) { f.ref[u][0] = c->slot[p->ref_slot[u]]; f.ref[u][1] = f.ref[u][0] + ys; f.ref[u][2] = f.ref[u][1] + cs; }
@@ -134,16 +140,18 @@ API int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, in
     else { ry = c->slot[ref_slot]; ru = ry + ysz; rv = ru + csz; }
     return svc_emu_recon_batch(ref_slot < 0, s, s + ysz, s + ysz + csz, ry, ru, rv, c->w, c->h, 1, 0, qp, off, motion, c->state, out, o, o + ysz, o + ysz + csz);
 }
-extern "C" int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma);
+extern "C" int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma, int level_idc);
 API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* c, int cur_slot, int qp, int off, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v, int rw, int rh,
                                            int level_idc, hlb200_mb_coeffs_t* out)
 {
-    if (level_idc > 30 || rw > c->w || rh > c->h) return HLB200_ERR_INVALID_PARAMETER;
+    const int dims[4] = {rw, rh, rw >> 1, rh >> 1};
+    for (int i = 0; i < 4; ++i) if (level_idc > 30 && (dims[i] & (dims[i] - 1)) == 0) return HLB200_ERR_INVALID_PARAMETER;   // as the library: (G-43) overflows the reference's int32
+    if (rw > c->w || rh > c->h) return HLB200_ERR_INVALID_PARAMETER;
     const size_t ysz = (size_t)c->w * c->h, csz = ysz >> 2;
     uint8_t* pred = (uint8_t*)malloc(ysz + 2 * csz);
-    svc_emu_resample_plane(ref_y, rw, rh, pred, c->w, c->h, 0);
-    svc_emu_resample_plane(ref_u, rw >> 1, rh >> 1, pred + ysz, c->w >> 1, c->h >> 1, 1);
-    svc_emu_resample_plane(ref_v, rw >> 1, rh >> 1, pred + ysz + csz, c->w >> 1, c->h >> 1, 1);
+    svc_emu_resample_plane(ref_y, rw, rh, pred, c->w, c->h, 0, level_idc);
+    svc_emu_resample_plane(ref_u, rw >> 1, rh >> 1, pred + ysz, c->w >> 1, c->h >> 1, 1, level_idc);
+    svc_emu_resample_plane(ref_v, rw >> 1, rh >> 1, pred + ysz + csz, c->w >> 1, c->h >> 1, 1, level_idc);
     const int rc = hlb200_svc_layer_picture(c, -1, cur_slot, qp, off, nullptr, pred, pred + ysz, pred + ysz + csz, out);
     free(pred);
     return rc;
