@@ -32,6 +32,21 @@ static int ensure_scratch(hlb200_ctx* c, size_t bytes)
 // (the kernel replicates the border samples itself, hlb_mbcore.cuh: phase_tile_load)
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+namespace hlb {
+int encode_tile_map(void* out128, const uint8_t* d_plane, int width, int height)
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+    HLB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled is not available in this driver"); return HLB200_ERR_SYSTEM; }
+    const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)height}, strides[1] = {(cuuint64_t)width};
+    const cuuint32_t box[2] = {64, 40}, estr[2] = {1, 1};   // HLB_TILE_W x HLB_TILE_H of hlb_mbcore.cuh
+    const CUresult r = ((tmap_encode_fn)fn)((CUtensorMap*)out128, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)d_plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d) for a %dx%d plane", (int)r, width, height); return HLB200_ERR_SYSTEM; }
+    return HLB200_OK;
+}
+}  // namespace hlb
 static int make_tile_maps(hlb200_ctx* c)
 {
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
@@ -42,7 +57,7 @@ static int make_tile_maps(hlb200_ctx* c)
     CUtensorMap maps[HLB200_MAX_REFS + 1];
     for (int s = 0; s < c->nslots; ++s) {
         const cuuint64_t dims[2] = {(cuuint64_t)c->width, (cuuint64_t)c->height}, strides[1] = {(cuuint64_t)c->width};
-        const cuuint32_t box[2] = {48, 48}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {64, 40}, estr[2] = {1, 1};   // HLB_TILE_W x HLB_TILE_H of hlb_mbcore.cuh
         const CUresult r = ((tmap_encode_fn)fn)(&maps[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_slot[s][0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { snprintf(hlb::g_err, sizeof(hlb::g_err), "cuTensorMapEncodeTiled failed (%d) for a %dx%d plane", (int)r, c->width, c->height); return HLB200_ERR_SYSTEM; }

@@ -2,6 +2,8 @@
 // luma/chroma fractional interpolation, residual -> T -> Q -> Q^-1 -> T^-1 -> reconstruction, SAD/SATD and the
 // independent ME candidate cost.  All are HBM-bound integer/byte kernels (no tensor cores: 4x4 butterflies are not
 // a dense contraction); one thread owns one 4x4 block in registers, one warp owns one (or two) macroblocks.
+#include <cuda.h>
+
 #include "hlb_common.cuh"
 #include "hlb_fast.cuh"
 #include "hlb_svc.cuh"
@@ -586,6 +588,62 @@ __global__ void __launch_bounds__(64) k_selftest_fast(int qp, unsigned seed, int
         }
     }
     if (nbad) atomicAdd(bad, nbad);
+}
+
+// ---- TMA probe: one 64x40 tile of a plane fetched the way the slice kernel does it (descriptor in global memory, mbarrier completion, border fix-up) against plain clamped loads ----
+__device__ __forceinline__ void tma_probe_load(uint8_t* tile, unsigned long long* bar, const void* tmap, int x0, int y0, int fence_mode)
+{
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), dst = (uint32_t)__cvta_generic_to_shared(tile);
+    if (fence_mode == 1) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(64 * 40) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tmap), "r"(x0), "r"(y0), "r"(b) : "memory");
+    uint32_t done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b), "r"(0u) : "memory");
+}
+__global__ void __launch_bounds__(32) k_tma_probe(const uint8_t* __restrict__ plane, int W, int H, int x0, int y0, const void* tmap_g, const __grid_constant__ CUtensorMap tmap_p, int mode, int* __restrict__ bad)
+{
+    __shared__ alignas(128) uint8_t tile[64 * 40];
+    __shared__ alignas(8) unsigned long long bar;
+    if (threadIdx.x == 0) {
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(&bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    x0 &= ~15;   // the innermost start coordinate of a TMA tile load must sit on a 16-byte boundary
+    if (threadIdx.x == 0) tma_probe_load(tile, &bar, mode == 2 ? (const void*)&tmap_p : tmap_g, x0, y0, mode);
+    __syncwarp();
+    int nbad = 0;
+    for (int i = threadIdx.x; i < 64 * 40; i += 32) {
+        const int ty = i / 64, tx = i % 64, y = y0 + ty, x = x0 + tx;
+        const int want = (x >= 0 && x < W && y >= 0 && y < H) ? plane[y * W + x] : 0;   // out-of-picture samples arrive as zeros
+        nbad += tile[i] != want;
+    }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
+}  // extern "C"
+namespace hlb { int encode_tile_map(void* out128, const uint8_t* d_plane, int width, int height); }
+extern "C" {
+int hlb200_dev_tma_probe(const uint8_t* d_plane, int width, int height, int x0, int y0, int mode, int* mismatches_out)
+{
+    if (!d_plane || !mismatches_out || (width & 15) || width <= 0 || height <= 0 || mode < 0 || mode > 2) return HLB200_ERR_INVALID_PARAMETER;
+    alignas(64) CUtensorMap m;
+    int rc = hlb::encode_tile_map(&m, d_plane, width, height);
+    if (rc) return rc;
+    void* d_map = nullptr;
+    int* d_bad = nullptr;
+    HLB_CUDA(cudaMalloc(&d_map, sizeof(m)));
+    HLB_CUDA(cudaMemcpy(d_map, &m, sizeof(m), cudaMemcpyHostToDevice));
+    HLB_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    HLB_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+    k_tma_probe<<<1, 32>>>(d_plane, width, height, x0, y0, d_map, m, mode, d_bad);
+    HLB_CUDA(cudaGetLastError());
+    HLB_CUDA(cudaMemcpy(mismatches_out, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    HLB_CUDA(cudaFree(d_bad));
+    HLB_CUDA(cudaFree(d_map));
+    return HLB200_OK;
 }
 
 int hlb200_dev_selftest(int blocks, unsigned seed, int* mismatches_out)

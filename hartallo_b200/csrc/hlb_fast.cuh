@@ -137,8 +137,17 @@ HLB_HD uint32_t exp_hi(uint32_t r) { return p_prmt(r, 0, 0x4342); }   // samples
 // Luma prediction of one 4x4 block out of the reference tile (8.4.2.2.1): (tx,ty) = tile coordinates of integer sample G of the block's
 // pixel (0,0); the tile holds columns tx-2..tx+6 and rows ty-2..ty+6.  Returns the four rows packed.
 // ------------------------------------------------------------------------------------------------------------------
-HLB_INTERP_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
+#ifndef HLB_FASTPRED_FN   /* hlb_slice.cu overrides: one out-of-line copy for all callers, the tile known to live in shared memory */
+#if defined(__CUDACC__)
+#define HLB_FASTPRED_FN __device__ __forceinline__
+#else
+#define HLB_FASTPRED_FN inline
+#endif
+#define HLB_FASTPRED_SRC(t) ((void)0)
+#endif
+HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
 {
+    HLB_FASTPRED_SRC(t);
     Rows4 o;
     if ((xf | yf) == 0) {
 #pragma unroll

@@ -58,6 +58,7 @@ struct MbState {
 #define HLB_NB_WORDS 30   /* MbState up to and including mv[][][] */
 static_assert(offsetof(MbState, chroma_ac) == 4 * HLB_NB_WORDS, "MbState head layout");
 
+#define HLB_ACTIVE_REFS 4   /* list entries one launch can search (the picture context travels to shared memory: kept small) */
 struct FrameCtx {
     int W, H, mbw, mbh;
     int qp, qpc;
@@ -66,8 +67,8 @@ struct FrameCtx {
     QuantK qk;                           // quantiser constants of the luma trial encodes (hlb_fast.cuh), derived from qp by frame_ctx_derive()
     const uint8_t* src[3];
     uint8_t* cur[3];                     // reconstruction of the current picture (frame-store planes, pitch = W / W/2)
-    const uint8_t* ref[HLB200_MAX_REFS][3];
-    const void* ref_tmap[HLB200_MAX_REFS];   // device: CUtensorMap (in global memory) of each reference luma plane for the TMA tile loads; null = plain loads
+    const uint8_t* ref[HLB_ACTIVE_REFS][3];  // active list entries: the reference's slice headers always carry num_ref_idx_l0_active_minus1 = 0 (slice.c:289-291)
+    const void* ref_tmap[HLB_ACTIVE_REFS];   // device: CUtensorMap (in global memory) of each reference luma plane for the TMA tile loads; null = plain loads
     MbState* st;
     hlb200_mb_record_t* rec;
 };
@@ -117,8 +118,14 @@ HLB_HD void part_at(int part_mode, const uint8_t* sub_mode, int x, int y, int& p
 #define HLB_MAXC 9
 #define HLB_MB_LANES 160   /* lanes a command needs at most = worker threads of the GPU CTA */
 #define HLB_MEMO_SLOTS 32   /* per 4x4 block; a macroblock meets ~25 distinct vectors per block (G2 CIF), probing never evicts */
-#define HLB_TILE 48   /* side of the shared-memory reference tile: partition (16) + 6-tap halo (5) + +-13 pixels of search freedom */
-enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_TILE, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_LUMA, CMD_CHROMA, CMD_STORE, CMD_I16_EVAL, CMD_I16_RATE, CMD_I16_RECON, CMD_I4_EVAL, CMD_I4_COMMIT, CMD_PRED_CHROMA_INTRA };
+/* Shared-memory reference tile.  A TMA tile load wants its innermost start coordinate on a 16-byte boundary (measured: any other x faults, profiles/r02b), so
+ * the tile is 64 samples wide, starts at a multiple of 16 and guarantees a window of HLB_TILE_SPAN_W = 48 anywhere inside it; 40 rows = partition (16) + 6-tap
+ * halo (5) + +-9 rows of search freedom (a search step spans at most +-2 integer samples; wider steps are evaluated candidate by candidate). */
+#define HLB_TILE_W 64
+#define HLB_TILE_H 40
+#define HLB_TILE_SPAN_W 48
+#define HLB_TILE_BYTES (HLB_TILE_W * HLB_TILE_H)
+enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_TILE, CMD_TILE_TMA, CMD_TILE_FIX, CMD_ME_EVAL, CMD_PRED_INTER, CMD_RECON_LUMA, CMD_CHROMA, CMD_STORE, CMD_I16_EVAL, CMD_I16_RATE, CMD_I16_RECON, CMD_I4_EVAL, CMD_I4_COMMIT, CMD_PRED_CHROMA_INTRA };
 
 // Lap timer of the profiling build: attributes the cycles since the previous HLB_LAP of this macroblock to section `slot`.
 // Sections: 0 begin/load, 1 mvp+pattern (search control), 2 me_eval prelude, 3 tile, 4 trial run, 5 scan+token, 6 cost, 7 compare,
@@ -138,9 +145,9 @@ enum { CMD_NONE = 0, CMD_EXIT, CMD_LOAD, CMD_TILE, CMD_ME_EVAL, CMD_PRED_INTER, 
 
 // Scratch of the macroblock being encoded (shared memory on the GPU)
 struct MbWork {
-    // reference tile: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)]; TMA destination (128-byte aligned, first member: no padding);
+    // reference tile: tile[j * HLB_TILE_W + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)]; TMA destination (128-byte aligned, first member: no padding);
     // the tail pads the word loads of the last row
-    alignas(128) uint8_t tile[HLB_TILE * HLB_TILE + 16];
+    alignas(128) uint8_t tile[HLB_TILE_BYTES + 16];
     alignas(8) unsigned long long tile_mbar;          // mbarrier the TMA tile load completes on (device)
     // command mailbox
     int cmd, arg0, arg1, arg0_lanes;
@@ -179,7 +186,7 @@ struct MbWork {
     double best_cost[4][4];
     int best_dist[4][4], best_sctr[4][4], best_cbp[4][4];
     int probably_pskip;
-    // reference tile: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)] (per-sample clamp of interpol.c:108-131)
+    // reference tile origin (tile_x0 is a multiple of 16); samples follow the per-sample clamp of interpol.c:108-131
     int tile_x0, tile_y0, tile_ref, tile_valid;
     int tile_phase;                                   // parity of the next completion of tile_mbar
     // one evaluation step
@@ -191,6 +198,8 @@ struct MbWork {
     uint32_t r_val[HLB_MAXC][16];      // trial result words by (candidate, luma4x4BlkIdx): dist:12 | bits_rest:10 | TotalCoeff:5 | TrailingOnes:2 | lone Single_ctr:2
     uint8_t eff[HLB_MAXC][16];
     uint8_t blk_coded[16];             // final reconstruction: block has non-zero levels
+    uint32_t tail_mv[28];              // candidate list of me_pskip_tail
+    int tail_n;
     int32_t c_dist[HLB_MAXC], c_rbc[HLB_MAXC], c_sctr[HLB_MAXC], c_cbp[HLB_MAXC];
     double c_cost[HLB_MAXC];
     int step_last;             // ((c+1) << 12 | k << 8 | Single_ctr) of the last non-zero trial block of the step, -1 if none
@@ -199,7 +208,7 @@ struct MbWork {
     int fin_mode, fin_sub[4];          // committed geometry (part_mode, sub_mode[])
     int16_t fin_mv[4][4][2];
     int8_t fin_ref[4];
-    uint8_t pred_y[256];
+    alignas(4) uint8_t pred_y[256];
     uint8_t pred_c[2][64];
     alignas(4) uint8_t rec_y[256];
     alignas(4) uint8_t rec_c[2][64];
@@ -398,80 +407,90 @@ HLB_HD void cand_origin(const MbWork& w, const FrameCtx& f, uint32_t mv, int& X,
     X = clip3(-17, f.W + 17, w.mbx * 16 + w.part_ox + (mv_x(mv) >> 2));
     Y = clip3(-17, f.H + 17, w.mby * 16 + w.part_oy + (mv_y(mv) >> 2));
 }
-// CMD_TILE: tile[j * HLB_TILE + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)].
-// Device: phase 0 = ONE TMA 2D tile load (cp.async.bulk.tensor, completion on an mbarrier; samples outside the picture arrive as zeros),
-//         phases 1, 2 = the picture-border fix-up: the reference clamps every sample coordinate (interpol.c:108-131), so out-of-picture columns (phase 1)
-//         and then rows (phase 2) of the tile are replicas of the nearest in-picture column / row -- only tiles that cross the picture edge have any.
-// A tile without a single in-picture column or row (vectors far outside the picture) and the CPU harness take the plain clamped loop.
+// The reference tile: tile[j * HLB_TILE_W + i] = ref_y[clampY(tile_y0 + j)][clampX(tile_x0 + i)].
+// Device: ONE TMA 2D tile load (CMD_TILE_TMA: cp.async.bulk.tensor, completion on an mbarrier; samples outside the picture arrive as zeros), then, only for tiles
+//         that cross the picture edge, the border fix-up (CMD_TILE_FIX): the reference clamps every sample coordinate (interpol.c:108-131), so out-of-picture
+//         columns and then rows of the tile are replicas of the nearest in-picture column / row.
+// A tile without a single in-picture column or row (vectors far outside the picture) and the CPU harness take the plain clamped loop (CMD_TILE).
 HLB_HD bool tile_uses_tma(const MbWork& w, const FrameCtx& f)
 {
 #if defined(__CUDA_ARCH__)
-    return f.ref_tmap[w.ref] != nullptr && w.tile_x0 > -HLB_TILE && w.tile_x0 < f.W && w.tile_y0 > -HLB_TILE && w.tile_y0 < f.H;
+    return f.ref_tmap[w.ref] != nullptr && w.tile_x0 > -HLB_TILE_W && w.tile_x0 < f.W && w.tile_y0 > -HLB_TILE_H && w.tile_y0 < f.H;
 #else
     (void)w; (void)f;
     return false;
 #endif
 }
-HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int phase, int lane)
+// CMD_TILE_TMA (one lane): issue the load, wait for its bytes on the mbarrier
+HLB_FN void phase_tile_tma(MbWork& w, const FrameCtx& f, int lane)
+{
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+#if defined(__CUDA_ARCH__)
+    if (lane != 0) return;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&w.tile_mbar), dst = (uint32_t)__cvta_generic_to_shared(w.tile);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the tile are ordered before the async-proxy write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HLB_TILE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(f.ref_tmap[w.ref]), "r"(w.tile_x0), "r"(w.tile_y0), "r"(bar) : "memory");
+    const uint32_t parity = (uint32_t)w.tile_phase & 1u;
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1 << 16)) { w.stuck = 2; break; }   // a tile load that never completes is reported through the watchdog (hlb200_slice_status), not waited for
+    }
+    w.tile_phase ^= 1;
+#else
+    (void)w; (void)f; (void)lane;
+#endif
+}
+// CMD_TILE_FIX: phase 0 = out-of-picture columns of the in-picture rows, phase 1 = out-of-picture rows (word-wise, from the now column-complete nearest row)
+HLB_HD bool tile_crosses_edge(const MbWork& w, const FrameCtx& f) { return w.tile_x0 < 0 || w.tile_y0 < 0 || w.tile_x0 + HLB_TILE_W > f.W || w.tile_y0 + HLB_TILE_H > f.H; }
+HLB_FN void phase_tile_fix(MbWork& w, const FrameCtx& f, int phase, int lane)
+{
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+    const int nl = w.arg0_lanes, x0 = w.tile_x0, y0 = w.tile_y0;
+    const int cx0 = x0 < 0 ? -x0 : 0, cx1 = x0 + HLB_TILE_W > f.W ? f.W - x0 : HLB_TILE_W;           // in-picture columns [cx0, cx1)
+    const int ry0 = y0 < 0 ? -y0 : 0, ry1 = y0 + HLB_TILE_H > f.H ? f.H - y0 : HLB_TILE_H;           // in-picture rows    [ry0, ry1)
+    if (phase == 0 && (cx0 > 0 || cx1 < HLB_TILE_W)) {
+        const int nbad = cx0 + (HLB_TILE_W - cx1);
+#pragma unroll 1
+        for (int i = lane; i < (ry1 - ry0) * nbad; i += nl) {
+            const int r = ry0 + i / nbad, k = i % nbad, c = k < cx0 ? k : cx1 + (k - cx0);
+            w.tile[r * HLB_TILE_W + c] = w.tile[r * HLB_TILE_W + (k < cx0 ? cx0 : cx1 - 1)];
+        }
+    }
+    if (phase == 1 && (ry0 > 0 || ry1 < HLB_TILE_H)) {
+        const int nbad = ry0 + (HLB_TILE_H - ry1);
+#pragma unroll 1
+        for (int i = lane; i < nbad * (HLB_TILE_W / 4); i += nl) {
+            const int k = i / (HLB_TILE_W / 4), q = i % (HLB_TILE_W / 4), r = k < ry0 ? k : ry1 + (k - ry0);
+            ((uint32_t*)w.tile)[r * (HLB_TILE_W / 4) + q] = ((const uint32_t*)w.tile)[(k < ry0 ? ry0 : ry1 - 1) * (HLB_TILE_W / 4) + q];
+        }
+    }
+}
+// CMD_TILE: the plain clamped loads (tiles without an in-picture sample, launches without tensor maps, the CPU harness)
+HLB_FN void phase_tile_load(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     const int nl = w.arg0_lanes;
     const int W = f.W, Hm1 = f.H - 1, Wm1 = f.W - 1, x0 = w.tile_x0, y0 = w.tile_y0;
-#if defined(__CUDA_ARCH__)
-    if (tile_uses_tma(w, f)) {
-        if (phase == 0) {
-            if (lane == 0) {
-                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&w.tile_mbar), dst = (uint32_t)__cvta_generic_to_shared(w.tile);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the tile are ordered before the async-proxy write
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HLB_TILE * HLB_TILE) : "memory");
-                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                             ::"r"(dst), "l"(f.ref_tmap[w.ref]), "r"(x0), "r"(y0), "r"(bar) : "memory");
-                const uint32_t parity = (uint32_t)w.tile_phase & 1u;
-                uint32_t done = 0;
-                while (!done)
-                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-                w.tile_phase ^= 1;
-            }
-            return;
-        }
-        const int cx0 = x0 < 0 ? -x0 : 0, cx1 = x0 + HLB_TILE > W ? W - x0 : HLB_TILE;           // in-picture columns [cx0, cx1)
-        const int ry0 = y0 < 0 ? -y0 : 0, ry1 = y0 + HLB_TILE > f.H ? f.H - y0 : HLB_TILE;       // in-picture rows    [ry0, ry1)
-        if (phase == 1 && (cx0 > 0 || cx1 < HLB_TILE)) {   // the nearest in-picture column into the out-of-picture columns of the in-picture rows
-            const int nbad = cx0 + (HLB_TILE - cx1);
-#pragma unroll 1
-            for (int i = lane; i < (ry1 - ry0) * nbad; i += nl) {
-                const int r = ry0 + i / nbad, k = i % nbad, c = k < cx0 ? k : cx1 + (k - cx0);
-                w.tile[r * HLB_TILE + c] = w.tile[r * HLB_TILE + (k < cx0 ? cx0 : cx1 - 1)];
-            }
-        }
-        if (phase == 2 && (ry0 > 0 || ry1 < HLB_TILE)) {   // whole rows, word-wise, from the (now column-complete) nearest in-picture row
-            const int nbad = ry0 + (HLB_TILE - ry1);
-#pragma unroll 1
-            for (int i = lane; i < nbad * (HLB_TILE / 4); i += nl) {
-                const int k = i / (HLB_TILE / 4), q = i % (HLB_TILE / 4), r = k < ry0 ? k : ry1 + (k - ry0);
-                ((uint32_t*)w.tile)[r * (HLB_TILE / 4) + q] = ((const uint32_t*)w.tile)[(k < ry0 ? ry0 : ry1 - 1) * (HLB_TILE / 4) + q];
-            }
-        }
-        return;
-    }
-#endif
-    if (phase != 0) return;
     const uint8_t* plane = w.ref_y;
     // eight independent loads in flight per lane
 #pragma unroll 1
-    for (int i0 = lane; i0 < HLB_TILE * HLB_TILE; i0 += 8 * nl) {
+    for (int i0 = lane; i0 < HLB_TILE_BYTES; i0 += 8 * nl) {
         uint8_t v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * nl;
-            const int ty = i / HLB_TILE, tx = i - ty * HLB_TILE;
+            const int ty = i / HLB_TILE_W, tx = i - ty * HLB_TILE_W;
             const int y = clip3(0, Hm1, y0 + ty), x = clip3(0, Wm1, x0 + tx);
-            v[u] = i < HLB_TILE * HLB_TILE ? HLB_LDG(plane + y * W + x) : (uint8_t)0;
+            v[u] = i < HLB_TILE_BYTES ? HLB_LDG(plane + y * W + x) : (uint8_t)0;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * nl;
-            if (i < HLB_TILE * HLB_TILE) w.tile[i] = v[u];
+            if (i < HLB_TILE_BYTES) w.tile[i] = v[u];
         }
     }
 }
@@ -541,7 +560,7 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
     if (!hit) {
         int X, Y;
         cand_origin(w, f, key, X, Y);
-        const Rows4 p = fast_pred_luma((const uint32_t*)w.tile, HLB_TILE / 4, X + (bx - w.part_ox) - w.tile_x0, Y + (by - w.part_oy) - w.tile_y0, mvx & 3, mvy & 3);
+        const Rows4 p = fast_pred_luma((const uint32_t*)w.tile, HLB_TILE_W / 4, X + (bx - w.part_ox) - w.tile_x0, Y + (by - w.part_oy) - w.tile_y0, mvx & 3, mvy & 3);
         Rows4 s;
 #pragma unroll
         for (int r = 0; r < 4; ++r) s.r[r] = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2];   // bx is a multiple of 4
@@ -632,12 +651,18 @@ template <class X>
 HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, int bx0, int by0, int bx1, int by1)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    if (!(w.tile_valid && w.tile_ref == w.ref && bx0 >= w.tile_x0 && by0 >= w.tile_y0 && bx1 <= w.tile_x0 + HLB_TILE && by1 <= w.tile_y0 + HLB_TILE)) {
+    if (!(w.tile_valid && w.tile_ref == w.ref && bx0 >= w.tile_x0 && by0 >= w.tile_y0 && bx1 <= w.tile_x0 + HLB_TILE_W && by1 <= w.tile_y0 + HLB_TILE_H)) {
         x.sync();   // every lane has evaluated the condition before the tile origin changes
-        w.tile_x0 = bx0 - ((HLB_TILE - (bx1 - bx0)) >> 1); w.tile_y0 = by0 - ((HLB_TILE - (by1 - by0)) >> 1);
+        // centred as far as the 16-sample alignment of the origin allows: origin <= bx0 - m and origin + 64 >= bx1 for every origin in (bx0 - m - 16, bx0 - m]
+        const int span = bx1 - bx0, m = (HLB_TILE_W - span) >> 1 < HLB_TILE_W - 15 - span ? (HLB_TILE_W - span) >> 1 : HLB_TILE_W - 15 - span;
+        w.tile_x0 = (bx0 - m) & ~15; w.tile_y0 = by0 - ((HLB_TILE_H - (by1 - by0)) >> 1);
         w.tile_ref = w.ref; w.tile_valid = 1;
         HLB_LAP(w, 2);
-        x.run(CMD_TILE, HLB_MB_LANES);
+        x.sync();
+        if (tile_uses_tma(w, f)) {
+            x.run(CMD_TILE_TMA, 1);
+            if (tile_crosses_edge(w, f)) x.run(CMD_TILE_FIX, 64);
+        } else x.run(CMD_TILE, HLB_MB_LANES);
         HLB_LAP(w, 3);
     }
     w.c_begin = c0; w.c_end = c1;
@@ -652,7 +677,7 @@ HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, in
 // (me_ds.c:287,297,345: dist + (rbc + mvd bits) * lambda) in w.c_*.  counts_only = the search can no longer improve (its best cost is 0: costs are
 // never negative and a candidate only wins with a strictly smaller one), so nothing but the rate state the trials leave behind matters.
 template <class X>
-HLB_FN void me_step(X& x, MbWork& w, const FrameCtx& f, int n, int px, int py, bool counts_only)
+HLB_FN void me_step(X& x, MbWork& w, const FrameCtx& f, int n, int px, int py, bool counts_only, bool count_work = true)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     HLB_LAP(w, 1);
@@ -670,9 +695,9 @@ HLB_FN void me_step(X& x, MbWork& w, const FrameCtx& f, int n, int px, int py, b
     mnx = x.reduce_min(mnx); mny = x.reduce_min(mny); mxx = x.reduce_max(mxx); mxy = x.reduce_max(mxy); iops = x.reduce_add(iops);
     if (x.lane() == 0) {
         w.counts_only = counts_only ? 1 : 0; w.step_last = -1;
-        w.stat_trials += (unsigned)(n << w.nblk_log2); w.stat_cands += (unsigned)n; w.stat_interp += (unsigned)(iops << w.nblk_log2);
+        if (count_work) { w.stat_trials += (unsigned)(n << w.nblk_log2); w.stat_cands += (unsigned)n; w.stat_interp += (unsigned)(iops << w.nblk_log2); }
     }
-    if (mxx - mnx + w.part_w + 5 <= HLB_TILE && mxy - mny + w.part_h + 5 <= HLB_TILE) me_eval_range(x, w, f, 0, n, mnx - 2, mny - 2, mxx + w.part_w + 3, mxy + w.part_h + 3);
+    if (mxx - mnx + w.part_w + 5 <= HLB_TILE_SPAN_W && mxy - mny + w.part_h + 5 <= HLB_TILE_H) me_eval_range(x, w, f, 0, n, mnx - 2, mny - 2, mxx + w.part_w + 3, mxy + w.part_h + 3);
     else {
 #pragma unroll 1
         for (int c = 0; c < n; ++c) {   // windows too far apart for one tile: one by one, same results
@@ -700,12 +725,13 @@ HLB_HD void set_best(MbWork& w, int p, int s, double cost, int c)
     w.best_mv[p][s][0] = (int16_t)mv_x(w.cand_mv[c]); w.best_mv[p][s][1] = (int16_t)mv_y(w.cand_mv[c]);
 }
 
+// Start of the search of one mode (me_ds.c:104-228): resets the per-partition bests and, for the 16x16 mode on reference 0, runs the PSkip probe
+// (me_ds.c:229-261).  Returns 1 when the probe passed: the partition's best is then the predictor at cost 0, which no candidate can beat.
 template <class X>
-HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
+HLB_FN int me_search_begin(X& x, MbWork& w, const FrameCtx& f, int mode)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (x.lane() == 0) w.mode = mode;
-    const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
 #pragma unroll 1
     for (int i = x.lane(); i < 16; i += x.nlanes()) { w.best_sctr[i >> 2][i & 3] = 9; w.best_dist[i >> 2][i & 3] = INT_MAX; w.best_cost[i >> 2][i & 3] = DBL_MAX; }
     int probably_pskip = 0;
@@ -728,6 +754,17 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
     }
     x.sync();
     if (x.lane() == 0) w.probably_pskip = probably_pskip;
+    x.sync();
+    return probably_pskip;
+}
+
+// The partition searches of the mode (me_ds.c:262-477)
+template <class X>
+HLB_FN void me_search_parts(X& x, MbWork& w, const FrameCtx& f, int mode)
+{
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+    const int nparts = mode_nparts(mode), nsub = mode_nsub(mode);
+    int n;
 #pragma unroll 1
     for (int p = 0; p < nparts; ++p) {
 #pragma unroll 1
@@ -738,7 +775,7 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
             double bcost = w.best_cost[p][s];
             int bmx = w.best_mv[p][s][0], bmy = w.best_mv[p][s][1];
             x.sync();
-            int n = (px != 0 || py != 0) ? 2 : 1;
+            n = (px != 0 || py != 0) ? 2 : 1;
             if (x.lane() == 0) {
                 w.mvp[p][s][0] = (int16_t)px; w.mvp[p][s][1] = (int16_t)py;
                 set_part(w, mode, p, s);
@@ -824,6 +861,62 @@ HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
     }
 }
 
+template <class X>
+HLB_FN void me_find_best_cost(X& x, MbWork& w, const FrameCtx& f, int mode)
+{
+    me_search_begin(x, w, f, mode);
+    me_search_parts(x, w, f, mode);
+}
+
+// ---- the 16x16 search after a passed PSkip probe, when the macroblock is already known to end as P_Skip ----
+// After the probe the partition's best cost is 0, so the rest of the search (predictor + zero vector, one integer, one half-pel and one quarter-pel pattern
+// around the predictor, me_ds.c:283-477) evaluates a FIXED list of <= 26 candidates and changes nothing but (a) TotalCoeffsLuma[] of the macroblock and (b) the
+// Single_ctr chain (the value the LAST non-zero trial block leaves, residual.c:882).  (a) is dead state for a P_Skip macroblock: neighbours count 0 coefficients
+// for a skipped macroblock whatever it holds (residual.c:712,733), and the next picture gates every in-macroblock count by this macroblock's CodedBlockPatternLuma,
+// which a skip sets to 0 (utils.h:10-20; a later coded macroblock at this address rewrites the counts of every 8x8 it codes).  So only (b) is computed: the
+// candidates are walked from the last one backwards until a trial block with non-zero levels is found.  The work counters still count the whole list.
+template <class X>
+HLB_FN void me_pskip_tail(X& x, MbWork& w, const FrameCtx& f)
+{
+    HLB_IN_SHARED(w); HLB_IN_SHARED(f);
+    const int px = w.best_mv[0][0][0], py = w.best_mv[0][0][1], R = f.me_range;
+    x.sync();
+    if (x.lane() == 0) {
+        int n = 0;
+        w.mvp[0][0][0] = (int16_t)px; w.mvp[0][0][1] = (int16_t)py;
+        w.mv_cur[0][0][0] = (int16_t)px; w.mv_cur[0][0][1] = (int16_t)py;
+        set_part(w, 0, 0, 0);
+        w.tail_mv[n++] = mv_pack(px, py);
+        if (px != 0 || py != 0) w.tail_mv[n++] = 0;
+        for (int shift = 2; shift >= 0; --shift) {
+            // centres: integer and half-pel stage around (mvp >> 2), quarter-pel stage around mvp; window = centre +- me_range
+            const int cx = shift ? px >> 2 : px, cy = shift ? py >> 2 : py, count = shift == 1 ? 5 : 9;
+            for (int i = 0; i < count; ++i) {
+                const int dx = kDsp[shift][i][0], dy = kDsp[shift][i][1];
+                if (dx >= -R && dx <= R && dy >= -R && dy <= R) w.tail_mv[n++] = mv_pack((cx + dx) * (1 << shift), (cy + dy) * (1 << shift));
+            }
+        }
+        w.tail_n = n;
+        int iops = 0;
+        for (int c = 0; c < n; ++c) {
+            const int xf = mv_x(w.tail_mv[c]) & 3, yf = mv_y(w.tail_mv[c]) & 3;
+            iops += (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
+        }
+        w.stat_trials += (unsigned)(n << 4); w.stat_cands += (unsigned)n; w.stat_interp += (unsigned)(iops << 4);
+    }
+    x.sync();
+#pragma unroll 1
+    for (int c = w.tail_n - 1; c >= 0; --c) {
+        if (x.lane() == 0) w.cand_mv[0] = w.tail_mv[c];
+        x.sync();
+        me_step(x, w, f, 1, px, py, true, false);   // sets w.last_sctr when a trial block of the candidate has non-zero levels
+        const int found = w.step_last;
+        x.sync();
+        if (found >= 0) break;
+    }
+    x.sync();
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Inter prediction of the whole macroblock with the committed geometry (rdo.c:2331-2416) -> w.pred_y / w.pred_c
 // lanes 0..15 luma blocks (raster), 16..143 chroma samples (Cb 0..63, Cr 0..63)
@@ -842,13 +935,21 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
         int p, s, ox, oy;
         fin_rect(w, bx, by, p, s, ox, oy);
-        uint8_t pv[16];
-        uint8_t* win = w.tile + lane * 96;   // the reference tile is dead once a prediction is formed (the caller invalidates it): 16 x 96 <= sizeof tile
-        pred_luma_4x4(f, f.ref[w.fin_ref[p]][0], w.mbx, w.mby, ox, oy, bx, by, w.fin_mv[p][s][0], w.fin_mv[p][s][1], win, pv);
+        // straight out of the search's reference tile when it covers the block's window (it does for every vector the search ended on or near), with the packed
+        // formulation of the trials; otherwise from the picture with the reference's clamp
+        const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
+        const int tx = clip3(-17, f.W + 17, w.mbx * 16 + ox + (mvx >> 2)) + (bx - ox) - w.tile_x0, ty = clip3(-17, f.H + 17, w.mby * 16 + oy + (mvy >> 2)) + (by - oy) - w.tile_y0;
+        Rows4 o;
+        if (w.tile_valid && w.tile_ref == w.fin_ref[p] && tx >= 2 && ty >= 2 && tx + 7 <= HLB_TILE_W && ty + 7 <= HLB_TILE_H)
+            o = fast_pred_luma((const uint32_t*)w.tile, HLB_TILE_W / 4, tx, ty, mvx & 3, mvy & 3);
+        else {
+            uint8_t pv[16], win[84];
+            pred_luma_4x4(f, f.ref[w.fin_ref[p]][0], w.mbx, w.mby, ox, oy, bx, by, mvx, mvy, win, pv);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r) o.r[r] = (uint32_t)pv[r * 4] | ((uint32_t)pv[r * 4 + 1] << 8) | ((uint32_t)pv[r * 4 + 2] << 16) | ((uint32_t)pv[r * 4 + 3] << 24);
+        }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) w.pred_y[(by + r) * 16 + bx + q] = pv[r * 4 + q];
+        for (int r = 0; r < 4; ++r) ((uint32_t*)w.pred_y)[((by + r) * 16 + bx) >> 2] = o.r[r];
     } else if (lane < 16 + 128) {   // one chroma sample per lane: the four reference loads of all samples are in flight together
         const int idx = lane - 16, c = idx >> 6, px = idx & 7, py = (idx >> 3) & 7;
         const int Wc = f.W >> 1, Hc = f.H >> 1;
@@ -1061,7 +1162,7 @@ HLB_HD int cmd_phases(int cmd)
 {
     switch (cmd) {
     case CMD_ME_EVAL: return 1;
-    case CMD_TILE: return 3;
+    case CMD_TILE_FIX: return 2;
     case CMD_CHROMA: return 3;
     case CMD_I16_EVAL: return 2;
     case CMD_I16_RATE: return 2;
@@ -1074,7 +1175,9 @@ HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     switch (cmd) {
     case CMD_LOAD: phase_load(w, f, lane); break;
-    case CMD_TILE: phase_tile_load(w, f, phase, lane); break;
+    case CMD_TILE: phase_tile_load(w, f, lane); break;
+    case CMD_TILE_TMA: phase_tile_tma(w, f, lane); break;
+    case CMD_TILE_FIX: phase_tile_fix(w, f, phase, lane); break;
     case CMD_ME_EVAL: me_phase_trial(w, f, lane); break;
     case CMD_PRED_INTER: phase_pred_inter(w, f, lane); break;
     case CMD_RECON_LUMA: phase_recon_luma(w, f, lane); break;
@@ -1250,7 +1353,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     double best_cost = DBL_MAX;
-    int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0;
+    int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0, pskip_early = 0;
     int16_t best_mv[4][4][2], best_mvp[4][4][2];
 #pragma unroll 1
     for (int u = 0; u < f.num_refs; ++u) {
@@ -1261,10 +1364,36 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
 #pragma unroll 1
         for (int g = 0; g < 4 && !found; ++g) {
             const int m0 = g < 3 ? g : 3, m1 = g < 3 ? g : 6;
+            pskip_early = 0;
 #pragma unroll 1
             for (int mode = m0; mode <= m1; ++mode) {
                 HLB_LAP(w, 8);
-                me_find_best_cost(x, w, f, mode);
+                if (me_search_begin(x, w, f, mode)) {
+                    // The PSkip probe passed (16x16, reference 0): the macroblock is a P_Skip iff its chroma also quantises to nothing (rdo.c:1125-1139, :2140).  The
+                    // reference checks that after the rest of the 16x16 search; the two only meet in the Single_ctr chain, so the check runs first and the search
+                    // shrinks to its only observable effect when the answer is yes (me_pskip_tail).
+                    const int sctr_before = w.last_sctr;
+                    w.fin_mode = 0; w.fin_sub[0] = w.fin_sub[1] = w.fin_sub[2] = w.fin_sub[3] = 0;
+                    w.fin_ref[0] = 0; w.fin_mv[0][0][0] = w.best_mv[0][0][0]; w.fin_mv[0][0][1] = w.best_mv[0][0][1];
+                    w.mb_is_intra = 0;
+                    x.sync();
+                    if (x.lane() == 0) w.last_sctr = -2;   // "not written by the chroma pass"
+                    x.sync();
+                    x.run(CMD_PRED_INTER, 144);
+                    chroma_code(x, w);
+                    const int chroma_zero = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1], sctr_chroma = w.last_sctr;
+                    x.sync();
+                    if (x.lane() == 0) w.last_sctr = sctr_before;
+                    x.sync();
+                    HLB_LAP(w, 9);
+                    if (chroma_zero) { me_pskip_tail(x, w, f); pskip_early = 1; }
+                    else { me_search_parts(x, w, f, mode); pskip_early = 2; }
+                    if (sctr_chroma != -2) {   // the chroma pass comes last in the reference's order
+                        x.sync();
+                        if (x.lane() == 0) w.last_sctr = sctr_chroma;
+                        x.sync();
+                    }
+                } else me_search_parts(x, w, f, mode);
                 HLB_LAP(w, 7);
                 double cost_sum = 0;
                 int dist_sum = 0, sctr_sum = 0;
@@ -1293,12 +1422,13 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
                 }
             }
             b_pskip = probably_pskip;
-            if (b_pskip) {  // chroma must quantise to nothing (rdo.c:1125-1139, :2140)
+            if (pskip_early) b_pskip = pskip_early == 1;   // the chroma check has already run (above)
+            else if (b_pskip) {  // chroma must quantise to nothing (rdo.c:1125-1139, :2140)
                 w.fin_mode = 0; w.fin_sub[0] = w.fin_sub[1] = w.fin_sub[2] = w.fin_sub[3] = 0;
                 w.fin_ref[0] = 0; w.fin_mv[0][0][0] = best_mv[0][0][0]; w.fin_mv[0][0][1] = best_mv[0][0][1];
                 w.mb_is_intra = 0;
                 HLB_LAP(w, 8);
-                w.tile_valid = 0; x.run(CMD_PRED_INTER, 144);   // the luma lanes stage their windows in the tile
+                x.run(CMD_PRED_INTER, 144);
                 chroma_code(x, w);
                 b_pskip = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1];
                 HLB_LAP(w, 9);
@@ -1347,7 +1477,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         w.cbp_luma4x4 = 0;
         kind = MBK_PSKIP; mb_type = 5;
     } else {
-        w.tile_valid = 0; x.run(CMD_PRED_INTER, 144);   // the luma lanes stage their windows in the tile
+        x.run(CMD_PRED_INTER, 144);
         w.luma_skip_residual = best_sctr < 6;
         x.run(CMD_RECON_LUMA, 16);
         w.cbp_luma4x4 = 0;

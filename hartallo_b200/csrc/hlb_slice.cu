@@ -17,6 +17,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+// ONE out-of-line copy of the packed luma prediction for all its callers (trial encodes, final prediction): the slice kernels are instruction-fetch bound
+// (DESIGN.md 4.1), and the four packed rows travel in registers
+#define HLB_FASTPRED_FN __device__ __noinline__
+#define HLB_FASTPRED_SRC(t) __builtin_assume(__isShared(t))
 #include "hlb_common.cuh"
 #include "hlb_mbcore.cuh"
 
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(HLB_CTA_THREADS, HLB_SLICE_MIN_CTAS) k_slice_e
             GpuExec x;
             x.w = &w; x.f = &sf; x.job = job; x.done = done; x.sched = s;
             mb_encode(x, w, sf, mb);
-            if (w.stuck) watchdog_fire(s, WD_SEARCH, item, 0);
+            if (w.stuck) watchdog_fire(s, WD_SEARCH, item, w.stuck);
             ((volatile int*)&w.cmd)[0] = CMD_EXIT;
             cta_bar();
         } else {
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(32, HLB_WARP_MIN_CTAS) k_slice_encode_warp(con
         mb_encode(x, w, sf, mb);
         __syncwarp();
         if (tid == 0) {
-            if (w.stuck) watchdog_fire(s, WD_SEARCH, item, 0);
+            if (w.stuck) watchdog_fire(s, WD_SEARCH, item, w.stuck);
             unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             sf.rec[mb].t_start_ns = (unsigned)t0; sf.rec[mb].t_end_ns = (unsigned)t;
 #ifdef HLB_PROFILE_STEPS
@@ -378,6 +382,13 @@ int slice_reset_state(hlb200_ctx* c)
     return HLB200_OK;
 }
 
+// HLB200_NO_TMA=1: the reference tiles are filled by plain clamped loads instead of TMA + border fix-up (same results; A/B and debugging aid)
+static bool slice_no_tma()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HLB200_NO_TMA"); v = (e && *e && *e != '0') ? 1 : 0; }
+    return v != 0;
+}
 static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j, int base)
 {
     if (!c || !p || p->qp < 12 || p->qp > 51 || p->cur_slot < 0 || p->cur_slot >= c->nslots || (p->slice_type != 0 && p->slice_type != 1)) return HLB200_ERR_INVALID_PARAMETER;
@@ -388,7 +399,7 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     f.is_p = p->slice_type == 1;
     f.me_range = p->me_range < 1 ? 1 : (p->me_range > 64 ? 64 : p->me_range);   // rdo.c:847
     f.num_refs = f.is_p ? p->num_refs : 0;
-    if (f.is_p && (f.num_refs < 1 || f.num_refs > c->max_refs)) return HLB200_ERR_INVALID_PARAMETER;
+    if (f.is_p && (f.num_refs < 1 || f.num_refs > c->max_refs || f.num_refs > HLB_ACTIVE_REFS)) return HLB200_ERR_INVALID_PARAMETER;
     f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));                       // slice.c:1766 (integer division in the exponent)
     frame_ctx_derive(f);
     for (int k = 0; k < 3; ++k) { f.src[k] = c->d_src_cur[k]; f.cur[k] = c->d_slot[p->cur_slot][k]; }
@@ -396,7 +407,7 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
         const int s = p->ref_slot[u];
         if (s < 0 || s >= c->nslots || s == p->cur_slot) return HLB200_ERR_INVALID_PARAMETER;
         for (int k = 0; k < 3; ++k) f.ref[u][k] = c->d_slot[s][k];
-        f.ref_tmap[u] = c->d_tmaps ? (const char*)c->d_tmaps + 128 * (size_t)s : nullptr;   // TMA descriptor of the slot's luma plane (hlb_api.cu)
+        f.ref_tmap[u] = (c->d_tmaps && !slice_no_tma()) ? (const char*)c->d_tmaps + 128 * (size_t)s : nullptr;   // TMA descriptor of the slot's luma plane (hlb_api.cu)
     }
     f.st = (MbState*)c->d_mbstate;
     f.rec = c->d_records;

@@ -273,6 +273,11 @@ HLB200_API int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink,
  * QP 12..51) against the plain formulations, both run on the device over `blocks` x 64 threads of pseudo-random inputs; *mismatches_out = 0 when they agree. */
 HLB200_API int hlb200_dev_selftest(int blocks, unsigned seed, int* mismatches_out);
 
+/* ---- TMA probe: fetches the 64x40 tile at (x0 rounded down to a multiple of 16, y0) of a device plane (width multiple of 16) with one cp.async.bulk.tensor load, as the slice kernel does, and
+ * compares it with plain loads (out-of-picture samples must arrive as zeros).  mode 0: descriptor in global memory; 1: the same after a tensormap-proxy acquire
+ * fence; 2: descriptor passed as a __grid_constant__ kernel parameter. */
+HLB200_API int hlb200_dev_tma_probe(const uint8_t* d_plane, int width, int height, int x0, int y0, int mode, int* mismatches_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,30 +47,48 @@ def level_md5(kind, rec):
     return hashlib.md5(lv.tobytes()).hexdigest()
 
 
+def _first(mask):
+    """index of the first True of a per-macroblock mask (for the assertion message)"""
+    i = np.flatnonzero(mask.reshape(mask.shape[0], -1).any(axis=1))
+    return int(i[0]) if len(i) else -1
+
+
 def check_frame(g, n, rec, recon, what):
-    """rec: MB_RECORD array of frame n; recon: tight planes"""
-    nmb = len(rec)
+    """rec: MB_RECORD array of frame n; recon: tight planes.  Vectorised over the macroblocks of the picture (a 1080p picture has 8,160 of them)."""
     assert hashlib.md5(recon.tobytes()).hexdigest() == str(g["recon_md5"][n]), "%s: reconstruction of frame %d differs" % (what, n)
-    for a in range(nmb):
-        k = int(g["kind"][n, a])
-        r = rec[a]
-        assert int(r["mb_class"]) == k, (what, n, a, "class", int(r["mb_class"]), k)
-        if k != 0:
-            assert int(r["mb_type"]) == int(g["mb_type"][n, a]), (what, n, a, "mb_type")
-        if k in (0, 1):
-            npart = int(g["nparts"][n, a, 0])
-            for p in range(npart):
-                for q in range(int(g["nparts"][n, a, 1 + p])):
-                    assert tuple(r["mv"][p, q]) == tuple(g["mv"][n, a, p, q]), (what, n, a, "mv", p, q)
-                    if k == 1:
-                        assert tuple(r["mvd"][p, q]) == tuple(g["mvd"][n, a, p, q]), (what, n, a, "mvd", p, q)
-        assert (int(r["coded_block_pattern"]), int(r["cbp_luma"]), int(r["cbp_chroma"])) == tuple(int(v) for v in g["cbp"][n, a]), (what, n, a, "cbp")
-        if k == 3:
-            assert np.array_equal(r["i4_pred_mode"], g["i4_mode"][n, a]), (what, n, a, "i4 modes")
-        gm = str(g["level_md5"][n, a])
-        assert level_md5(k, r)[:len(gm)] == gm, (what, n, a, "levels")
-        if k != 0 and "mad" in g.files:   # *pi_mad of the decision that stood: the search's best distortion (north star: "identical MVs and costs")
-            assert int(r["mad"]) == int(g["mad"][n, a]), (what, n, a, "mad", int(r["mad"]), int(g["mad"][n, a]))
+    kind = g["kind"][n].astype(np.int64)
+    bad = rec["mb_class"] != kind
+    assert not bad.any(), (what, n, _first(bad), "class")
+    coded = kind != 0
+    bad = coded & (rec["mb_type"] != g["mb_type"][n])
+    assert not bad.any(), (what, n, _first(bad), "mb_type")
+    npart, nsub = g["nparts"][n][:, 0].astype(np.int64), g["nparts"][n][:, 1:5].astype(np.int64)
+    valid = (np.arange(4)[None, :, None] < npart[:, None, None]) & (np.arange(4)[None, None, :] < nsub[:, :, None])   # (nmb, part, sub)
+    inter = valid & np.isin(kind, (0, 1))[:, None, None]
+    bad = inter[..., None] & (rec["mv"] != g["mv"][n])
+    assert not bad.any(), (what, n, _first(bad), "mv")
+    bad = (valid & (kind == 1)[:, None, None])[..., None] & (rec["mvd"] != g["mvd"][n])
+    assert not bad.any(), (what, n, _first(bad), "mvd")
+    got_cbp = np.stack([rec["coded_block_pattern"], rec["cbp_luma"], rec["cbp_chroma"]], axis=1)
+    bad = got_cbp != g["cbp"][n]
+    assert not bad.any(), (what, n, _first(bad), "cbp")
+    bad = (kind == 3)[:, None] & (rec["i4_pred_mode"] != g["i4_mode"][n])
+    assert not bad.any(), (what, n, _first(bad), "i4 modes")
+    if "mad" in g.files:   # *pi_mad of the decision that stood: the search's best distortion (north star: "identical MVs and costs")
+        bad = coded & (rec["mad"] != g["mad"][n])
+        assert not bad.any(), (what, n, _first(bad), "mad", int(rec["mad"][_first(bad)]), int(g["mad"][n][_first(bad)]))
+    # level digests: what the writer consumes for the macroblock's type
+    gold = g["level_md5"][n]
+    glen = len(str(gold[0]))
+    mask16 = ((rec["cbp_luma4x4"].astype(np.int64)[:, None] >> np.arange(16)[None, :]) & 1).astype(np.int16)
+    inter_lv = np.ascontiguousarray(rec["luma_level"].astype(np.int16) * mask16[:, :, None])
+    i4_lv = np.ascontiguousarray(rec["luma_level"].astype(np.int16))
+    i16_lv = np.ascontiguousarray(np.concatenate([rec["i16_dc_level"].reshape(-1, 1, 16), rec["i16_ac_level"]], axis=1).astype(np.int16))
+    zero = hashlib.md5(np.zeros((1, 1), np.int16).tobytes()).hexdigest()[:glen]
+    for a in range(len(rec)):
+        k = kind[a]
+        d = zero if k == 0 else hashlib.md5((inter_lv[a] if k == 1 else (i4_lv[a] if k == 3 else i16_lv[a])).tobytes()).hexdigest()[:glen]
+        assert d == str(gold[a]), (what, n, a, "levels")
 
 
 def run_emu(w, h, frames, qp, me_range, yuv_frames, tag, refs=1):

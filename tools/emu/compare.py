@@ -93,7 +93,9 @@ def main():
                     diffs.append("i16 mode ref=%d emu=%d" % (rr["i16_mode"], er["i16_pred_mode"]))
                 if k != 0 and rr["mad"] != er["mad"]:
                     diffs.append("mad ref=%d emu=%d" % (rr["mad"], er["mad"]))
-            if not np.array_equal(rs["tc_luma"], es["tc_luma"]):
+            # TotalCoeffsLuma[] of a P_Skip macroblock is dead state (neighbours count 0 for a skipped macroblock, the next picture gates it by CodedBlockPatternLuma = 0):
+            # the kernel does not run the trials that would only update it (hlb_mbcore.cuh: me_pskip_tail), so it is not compared there
+            if es["kind"] != 0 and not np.array_equal(rs["tc_luma"], es["tc_luma"]):
                 diffs.append("tc_luma ref=%s emu=%s" % (rs["tc_luma"], es["tc_luma"]))
             if not np.array_equal(rs["tc_cac"], es["tc_cac"]):
                 diffs.append("tc_cac ref=%s emu=%s" % (rs["tc_cac"].reshape(-1), es["tc_cac"].reshape(-1)))
