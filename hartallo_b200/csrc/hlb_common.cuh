@@ -86,5 +86,7 @@ struct hlb200_ctx {
     struct hlb200_ctx* batch_owner;             // first context of the batch launch that last covered this context (owns the scheduler words)
     int abort_state;                            // owner: -1 = not read back yet, 0 = the launch completed, > 0 = watchdog code
     cudaEvent_t ev_jobs, ev_done;               // owner: job-array upload / launch completion; other contexts: ev_done orders their stream before the launch
+    void* d_bits; int bits_cap_words;           // device CAVLC output of the last picture: words | per-macroblock lengths / offsets | header (hlb_slice.cu)
+    void* d_bits_jobs; void* h_bits_jobs; int bits_jobs_cap; cudaEvent_t ev_bits;   // owner of a serialisation batch: job descriptors
     int frame_count;
 };

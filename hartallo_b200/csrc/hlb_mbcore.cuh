@@ -574,56 +574,80 @@ HLB_HD bool blk_in_part(const MbWork& w, int blk)
     const int x = blk_x(blk), y = blk_y(blk);
     return x >= w.part_ox && x < w.part_ox + w.part_w && y >= w.part_oy && y < w.part_oy + w.part_h;
 }
-// per block: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806: only non-zero blocks are
-// stored), and the last non-zero trial block of the step in evaluation order (its Single_ctr stays in pc_esd->rdo.Single_ctr, residual.c:882)
-HLB_HD void me_scan_block(MbWork& w, int blk, int n, bool keep_eff)
+// block k (raster index inside the current partition = evaluation order) -> luma4x4BlkIdx
+HLB_HD int part_blk(const MbWork& w, int k) { return blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2)); }
+// per block OF THE PARTITION: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806: only non-zero
+// blocks are stored), and the last non-zero trial block of the step in evaluation order (its Single_ctr stays in pc_esd->rdo.Single_ctr, residual.c:882).
+// Blocks outside the partition keep w.tc[] throughout the step.
+HLB_HD void me_scan_block(MbWork& w, int k, int n, bool keep_eff)
 {
-    int e = w.tc[blk];
-    if (!blk_in_part(w, blk)) {
-        if (keep_eff)
-#pragma unroll 1
-            for (int c = 0; c < n; ++c) w.eff[c][blk] = (uint8_t)e;
-        return;
-    }
-    int last = -1;
-#pragma unroll 1
-    for (int c = 0; c < n; ++c) {
-        const uint32_t v = w.r_val[c][blk];
-        const int tcv = (int)((v >> 22) & 31u);
+    const int blk = part_blk(w, k);
+    uint32_t v[HLB_MAXC];
+#pragma unroll
+    for (int c = 0; c < HLB_MAXC; ++c) v[c] = c < n ? w.r_val[c][blk] : 0u;   // independent loads, then the serial "last non-zero wins" in registers
+    int e = w.tc[blk], last = -1;
+#pragma unroll
+    for (int c = 0; c < HLB_MAXC; ++c) {
+        const int tcv = (int)((v[c] >> 22) & 31u);
         if (tcv) {
             e = tcv;
-            const int t1 = (int)((v >> 27) & 3u);
-            last = ((c + 1) << 12) | ((tcv == 1 && t1 == 1) ? (int)((v >> 29) & 3u) : 9);
+            last = ((c + 1) << 12) | ((tcv == 1 && ((v[c] >> 27) & 3u) == 1) ? (int)((v[c] >> 29) & 3u) : 9);
         }
-        if (keep_eff) w.eff[c][blk] = (uint8_t)e;
+        if (keep_eff && c < n) w.eff[c][blk] = (uint8_t)e;
     }
     w.tc[blk] = (uint8_t)e;
-    if (last >= 0) {
-        const int k = (((blk_y(blk) - w.part_oy) >> 2) << w.bw_log2) | ((blk_x(blk) - w.part_ox) >> 2);   // raster index inside the partition = evaluation order
-        HLB_ATOMIC_MAX(&w.step_last, last | (k << 8));
+    if (last >= 0) HLB_ATOMIC_MAX(&w.step_last, last | (k << 8));
+}
+// TotalCoeffsLuma of neighbour block `a` as candidate c sees it: its own evolving value inside the partition, the macroblock's current one outside
+HLB_HD int me_cnt(const MbWork& w, int c, int a) { return blk_in_part(w, a) ? w.eff[c][a] : w.tc[a]; }
+// contribution of one (candidate, block) pair to the candidate's sums: lo = dist | bits << 16 (coeff_token resolved with the history-exact nC), hi = Single_ctr | CBP bit << 8
+HLB_HD void me_cost_term(const MbWork& w, int c, int k, uint32_t& lo, uint32_t& hi)
+{
+    const int blk = part_blk(w, k);
+    const uint32_t v = w.r_val[c][blk];
+    lo = v & 4095u; hi = 0;
+    const int tcv = (int)((v >> 22) & 31u);
+    if (tcv) {
+        const int t1 = (int)((v >> 27) & 3u), x = blk_x(blk), y = blk_y(blk);
+        int nA, nB;
+        if (x > 0) { const int a = blk_idx_from_xy(x - 4, y); nA = ((w.cbp_gate >> (a >> 2)) & 1) ? me_cnt(w, c, a) : 0; }
+        else nA = w.extA[blk];
+        if (y > 0) { const int b = blk_idx_from_xy(x, y - 4); nB = ((w.cbp_gate >> (b >> 2)) & 1) ? me_cnt(w, c, b) : 0; }
+        else nB = w.extB[blk];
+        lo |= (uint32_t)((int)((v >> 12) & 1023u) + coeff_token_len(nc_from(nA, nB), tcv, t1)) << 16;
+        hi = (uint32_t)((tcv == 1 && t1 == 1) ? (int)((v >> 29) & 3u) : 9) | (1u << (8 + blk));
     }
 }
-// per candidate: distortion, bits (coeff_token resolved with the history-exact nC), Single_ctr, CBP bits, RD cost (me_ds.c:287,297,345)
-HLB_HD void me_cost_cand(MbWork& w, const FrameCtx& f, int c, int px, int py)
+// per candidate: distortion, bits, Single_ctr, CBP bits, RD cost (me_ds.c:287,297,345) from the sums of its blocks' terms
+HLB_HD void me_cost_finish(MbWork& w, const FrameCtx& f, int c, uint32_t lo, uint32_t hi, int px, int py)
 {
-    int dist = 0, rbc = 0, sctr = 0, cbp = 0;
-    const int nblk = 1 << w.nblk_log2;
-#pragma unroll 1
-    for (int k = 0; k < nblk; ++k) {
-        const int blk = blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2));
-        const uint32_t v = w.r_val[c][blk];
-        dist += (int)(v & 4095u);
-        const int tcv = (int)((v >> 22) & 31u);
-        if (tcv) {
-            const int t1 = (int)((v >> 27) & 3u);
-            rbc += (int)((v >> 12) & 1023u) + coeff_token_len(luma_nc(w, w.eff[c], blk), tcv, t1);
-            sctr += (tcv == 1 && t1 == 1) ? (int)((v >> 29) & 3u) : 9;
-            cbp |= 1 << blk;
-        }
-    }
+    const int dist = (int)(lo & 0xffffu), rbc = (int)(lo >> 16);
     const uint32_t mv = w.cand_mv[c];
-    w.c_dist[c] = dist; w.c_rbc[c] = rbc; w.c_sctr[c] = sctr; w.c_cbp[c] = cbp;
+    w.c_dist[c] = dist; w.c_rbc[c] = rbc; w.c_sctr[c] = (int)(hi & 255u); w.c_cbp[c] = (int)(hi >> 8);
     w.c_cost[c] = dist + ((rbc + se_len(mv_x(mv) - px) + se_len(mv_y(mv) - py)) * f.lambda);
+}
+// all candidates of a step: one lane per (candidate, block), the blocks of a candidate summed over its (aligned) group of lanes by a shuffle butterfly
+template <class X>
+HLB_HD void me_cost_all(X& x, MbWork& w, const FrameCtx& f, int n, int px, int py)
+{
+    const int total = n << w.nblk_log2, kmask = (1 << w.nblk_log2) - 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+    for (int i0 = 0; i0 < total; i0 += 32) {   // the master warp: 32 lanes, every lane takes part in the shuffles
+        const int i = i0 + x.lane(), c = i >> w.nblk_log2, k = i & kmask;
+        uint32_t lo = 0, hi = 0;
+        if (i < total) me_cost_term(w, c, k, lo, hi);
+#pragma unroll 1
+        for (int o = (1 << w.nblk_log2) >> 1; o; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+        if (i < total && k == 0) me_cost_finish(w, f, c, lo, hi, px, py);
+    }
+#else
+    for (int c = 0; c < n; ++c) {
+        uint32_t lo = 0, hi = 0;
+        for (int k = 0; k <= kmask; ++k) { uint32_t a, b; me_cost_term(w, c, k, a, b); lo += a; hi += b; }
+        me_cost_finish(w, f, c, lo, hi, px, py);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -668,7 +692,7 @@ HLB_FN void me_eval_range(X& x, MbWork& w, const FrameCtx& f, int c0, int c1, in
     w.c_begin = c0; w.c_end = c1;
     HLB_LAP(w, 2);
     HLB_MEMO_STEP_BEGIN();
-    x.run(CMD_ME_EVAL, (c1 - c0) << w.nblk_log2);
+    x.trials((c1 - c0) << w.nblk_log2);
     HLB_MEMO_STEP_END();
     HLB_LAP(w, 4);
 }
@@ -707,13 +731,12 @@ HLB_FN void me_step(X& x, MbWork& w, const FrameCtx& f, int n, int px, int py, b
         }
     }
 #pragma unroll 1
-    for (int b = x.lane(); b < 16; b += x.nlanes()) me_scan_block(w, b, n, !counts_only);
+    for (int k = x.lane(); k < (1 << w.nblk_log2); k += x.nlanes()) me_scan_block(w, k, n, !counts_only);
     x.sync();
     if (w.step_last >= 0 && x.lane() == 0) w.last_sctr = w.step_last & 255;
     HLB_LAP(w, 5);
     if (!counts_only) {
-#pragma unroll 1
-        for (int c = x.lane(); c < n; c += x.nlanes()) me_cost_cand(w, f, c, px, py);
+        me_cost_all(x, w, f, n, px, py);
         x.sync();
     }
     HLB_LAP(w, 6);
@@ -799,22 +822,32 @@ HLB_FN void me_search_parts(X& x, MbWork& w, const FrameCtx& f, int mode)
                 if (iter > 4096) { w.stuck = 1; break; }
                 int best_idx = -1;
                 const int count = shift == 1 ? 5 : 9;
-                // pattern points of this iteration, in table order: kept when not pruned and inside the window (me_ds.c:317-328)
-                int okmask = 0;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const int mx = cx + kDsp[shift][i][0], my = cy + kDsp[shift][i][1];
-                    okmask |= (i < count && ((flags >> i) & 1) && mx >= wl && mx <= wr && my >= wt && my <= wb) ? (1 << i) : 0;
-                }
-                n = hlb_popc((uint32_t)okmask);
+                // pattern points of this iteration, in table order: kept when not pruned and inside the window (me_ds.c:317-328); one lane per point
                 x.sync();   // the previous step's candidates have been read by every lane
-#pragma unroll 1
-                for (int i = x.lane(); i < count; i += x.nlanes())
-                    if ((okmask >> i) & 1) {
+                int okmask = 0;
+#if defined(__CUDA_ARCH__)
+                {
+                    const int i = x.lane() < 9 ? x.lane() : 8, mx = cx + kDsp[shift][i][0], my = cy + kDsp[shift][i][1];
+                    const bool ok = x.lane() < count && ((flags >> i) & 1) && mx >= wl && mx <= wr && my >= wt && my <= wb;
+                    okmask = (int)__ballot_sync(0xffffffffu, ok);
+                    if (ok) {
                         const int at = hlb_popc((uint32_t)okmask & ((1u << i) - 1u));
-                        w.cand_mv[at] = mv_pack((cx + kDsp[shift][i][0]) * (1 << shift), (cy + kDsp[shift][i][1]) * (1 << shift));
+                        w.cand_mv[at] = mv_pack(mx * (1 << shift), my * (1 << shift));
                         w.cand_pat[at] = (uint8_t)i;
                     }
+                }
+#else
+                for (int i = 0; i < count; ++i) {
+                    const int mx = cx + kDsp[shift][i][0], my = cy + kDsp[shift][i][1];
+                    if (((flags >> i) & 1) && mx >= wl && mx <= wr && my >= wt && my <= wb) {
+                        const int at = hlb_popc((uint32_t)okmask);
+                        okmask |= 1 << i;
+                        w.cand_mv[at] = mv_pack(mx * (1 << shift), my * (1 << shift));
+                        w.cand_pat[at] = (uint8_t)i;
+                    }
+                }
+#endif
+                n = hlb_popc((uint32_t)okmask);
                 x.sync();
                 if (n > 0) {
                     const bool dead = bcost == 0.0;

@@ -23,6 +23,7 @@
 #define HLB_FASTPRED_SRC(t) __builtin_assume(__isShared(t))
 #include "hlb_common.cuh"
 #include "hlb_mbcore.cuh"
+#include "hlb_bits.cuh"
 
 namespace hlb {
 
@@ -88,6 +89,7 @@ struct GpuExec {
         if (cmd == CMD_ME_EVAL) { w->prof_me_cycles += (unsigned)(clock64() - t0); }
 #endif
     }
+    __device__ __forceinline__ void trials(int nlanes) { run(CMD_ME_EVAL, nlanes); }   // the worker warps run the trial encodes of a search step
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
     __device__ __forceinline__ int nlanes() const { return 32; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -296,6 +298,13 @@ struct WarpExec {
             __syncwarp();
         }
     }
+    __device__ __forceinline__ void trials(int nlanes)   // the trial encodes of a search step, straight on this warp's lanes (no command dispatch)
+    {
+        __syncwarp();
+#pragma unroll 1
+        for (int lane = (int)(threadIdx.x & 31); lane < nlanes; lane += 32) me_phase_trial(*w, *f, lane);
+        __syncwarp();
+    }
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
     __device__ __forceinline__ int nlanes() const { return 32; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -453,6 +462,60 @@ static int slice_variant(int n_pictures, int mean_wavefront)
     return (long long)n_pictures * mean_wavefront >= 4LL * slice_grid(0) ? 1 : 0;   // measured crossover at 1080p: ~100 pictures (r01d A/B: 64 -> CTA 1.41 M vs 1.21 M, 128 -> warp 2.13 M vs 2.05 M)
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device-side CAVLC serialisation of slice_data(): the macroblock loop of hl_codec_264_nal_slice_data_encode as far as it WRITES
+// (slice.c:1786-1894 -> _hl_codec_264_mb_write_no_pcm mb.c:543 incl. the mb_skip_run bookkeeping :588-618 -> hl_codec_264_residual_write residual.c:903),
+// from the decision records and the per-macroblock state the slice kernel left.  Three kernels per batch of pictures:
+//   k_bits_len    one thread per macroblock: bit length of its mb_skip_run + macroblock_layer()            (same code as the writer, counting sink)
+//   k_bits_scan   one CTA per picture: exclusive prefix sum of the lengths, total, zeroing of the used part of the output
+//   k_bits_write  one thread per macroblock: the bits, OR-ed into the picture's word buffer at the macroblock's offset
+// Output = slice_data() WITHOUT rbsp_trailing_bits, MSB first in big-endian 32-bit words (the host appends them to the slice header with its own bit writer).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bits_len(const BitsJob* __restrict__ jobs)
+{
+    const BitsJob& j = jobs[blockIdx.y];
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb >= j.nmb) return;
+    BitCount c;
+    c.n = 0;
+    bits_put_mb(c, j, mb);
+    j.len[mb] = c.n;
+}
+__global__ void __launch_bounds__(256) k_bits_scan(const BitsJob* __restrict__ jobs)
+{
+    const BitsJob& j = jobs[blockIdx.x];
+    __shared__ uint32_t part[256];
+    const int t = threadIdx.x, per = (j.nmb + 255) / 256, a = t * per, b = min(j.nmb, a + per);
+    uint32_t sum = 0;
+    for (int i = a; i < b; ++i) sum += j.len[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {   // inclusive scan of the 256 partial sums
+        const uint32_t v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t off = t ? part[t - 1] : 0;
+    for (int i = a; i < b; ++i) { const uint32_t l = j.len[i]; j.len[i] = off; off += l; }
+    const uint32_t total = part[255];
+    const uint32_t words = (total + 31) / 32 + 2;
+    if (t == 0) { j.hdr[0] = total; j.hdr[1] = words > (uint32_t)j.cap_words ? 1u : 0u; }
+    const uint32_t nz = words > (uint32_t)j.cap_words ? (uint32_t)j.cap_words : words;
+    for (uint32_t i = t; i < nz; i += 256) j.out[i] = 0;
+}
+__global__ void __launch_bounds__(128) k_bits_write(const BitsJob* __restrict__ jobs)
+{
+    const BitsJob& j = jobs[blockIdx.y];
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb >= j.nmb || j.hdr[1]) return;
+    BitWriter w;
+    w.buf = j.out; w.pos = j.len[mb]; w.acc = 0; w.nacc = 0;
+    bits_put_mb(w, j, mb);
+    w.finish();
+}
+
 }  // namespace hlb
 using namespace hlb;
 
@@ -546,6 +609,80 @@ int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_para
         ctxs[i]->batch_owner = c0;
         if (ctxs[i]->stream != st) HLB_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, c0->ev_done, 0));
     }
+    return HLB200_OK;
+}
+
+
+// ---- slice_data() bits of the pictures the contexts encoded last (any mix of sizes); the launch goes to the stream of ctxs[0], ordered like the slice launch ----
+int hlb200_slice_bits_batch_async(hlb200_ctx_t** ctxs, const int32_t* slice_types, int n)
+{
+    if (!ctxs || !slice_types || n < 1 || n > 4096) return HLB200_ERR_INVALID_PARAMETER;
+    hlb200_ctx* c0 = ctxs[0];
+    if (!c0) return HLB200_ERR_INVALID_PARAMETER;
+    int maxnmb = 0;
+    for (int i = 0; i < n; ++i) {
+        hlb200_ctx* c = ctxs[i];
+        if (!c || (slice_types[i] != 0 && slice_types[i] != 1)) return HLB200_ERR_INVALID_PARAMETER;
+        if (!c->d_bits) {
+            c->bits_cap_words = c->nmb * HLB200_BITS_WORDS_PER_MB + 64;
+            HLB_CUDA(cudaMalloc(&c->d_bits, sizeof(uint32_t) * ((size_t)c->bits_cap_words + (size_t)c->nmb + 4)));
+        }
+        maxnmb = c->nmb > maxnmb ? c->nmb : maxnmb;
+    }
+    if (c0->bits_jobs_cap < n) {
+        if (c0->d_bits_jobs) { HLB_CUDA(cudaStreamSynchronize(c0->stream)); HLB_CUDA(cudaFree(c0->d_bits_jobs)); HLB_CUDA(cudaFreeHost(c0->h_bits_jobs)); c0->d_bits_jobs = nullptr; c0->h_bits_jobs = nullptr; }
+        HLB_CUDA(cudaMalloc(&c0->d_bits_jobs, sizeof(BitsJob) * (size_t)n));
+        HLB_CUDA(cudaMallocHost(&c0->h_bits_jobs, sizeof(BitsJob) * (size_t)n));
+        c0->bits_jobs_cap = n;
+    }
+    if (!c0->ev_bits) HLB_CUDA(cudaEventCreateWithFlags(&c0->ev_bits, cudaEventDisableTiming));
+    else HLB_CUDA(cudaEventSynchronize(c0->ev_bits));   // the pinned job array of the previous call has been consumed
+    BitsJob* hj = (BitsJob*)c0->h_bits_jobs;
+    for (int i = 0; i < n; ++i) {
+        hlb200_ctx* c = ctxs[i];
+        BitsJob& j = hj[i];
+        j.rec = c->d_records; j.st = (const MbState*)c->d_mbstate;
+        j.out = (uint32_t*)c->d_bits; j.len = j.out + c->bits_cap_words; j.hdr = j.len + c->nmb;
+        j.nmb = c->nmb; j.mbw = c->mbw; j.is_p = slice_types[i]; j.cap_words = c->bits_cap_words;
+    }
+    cudaStream_t st = c0->stream;
+    for (int i = 1; i < n; ++i)
+        if (ctxs[i]->stream != st) {
+            if (!ctxs[i]->ev_done) HLB_CUDA(cudaEventCreateWithFlags(&ctxs[i]->ev_done, cudaEventDisableTiming));
+            HLB_CUDA(cudaEventRecord(ctxs[i]->ev_done, ctxs[i]->stream));
+            HLB_CUDA(cudaStreamWaitEvent(st, ctxs[i]->ev_done, 0));
+        }
+    HLB_CUDA(cudaMemcpyAsync(c0->d_bits_jobs, hj, sizeof(BitsJob) * (size_t)n, cudaMemcpyHostToDevice, st));
+    HLB_CUDA(cudaEventRecord(c0->ev_bits, st));
+    const BitsJob* dj = (const BitsJob*)c0->d_bits_jobs;
+    k_bits_len<<<dim3((maxnmb + 127) / 128, n), 128, 0, st>>>(dj);
+    k_bits_scan<<<n, 256, 0, st>>>(dj);
+    k_bits_write<<<dim3((maxnmb + 127) / 128, n), 128, 0, st>>>(dj);
+    HLB_CUDA(cudaGetLastError());
+    if (!c0->ev_done) HLB_CUDA(cudaEventCreateWithFlags(&c0->ev_done, cudaEventDisableTiming));
+    HLB_CUDA(cudaEventRecord(c0->ev_done, st));
+    for (int i = 1; i < n; ++i)
+        if (ctxs[i]->stream != st) HLB_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, c0->ev_done, 0));
+    return HLB200_OK;
+}
+
+// Downloads the bits of the context's last picture: *nbits_out = length of slice_data() in bits, out_words[0 .. (nbits + 31) / 32) = the bits, MSB first, each
+// word in HOST byte order (word k holds bits 32k .. 32k+31 with bit 32k in its most significant position).
+int hlb200_slice_bits_download(hlb200_ctx_t* c, uint32_t* out_words, size_t cap_words, uint32_t* nbits_out)
+{
+    if (!c || !out_words || !nbits_out || !c->d_bits) return HLB200_ERR_INVALID_PARAMETER;
+    int rc = slice_check_abort(c);
+    if (rc) return rc;
+    uint32_t hdr[2] = {0, 0};
+    const uint32_t* d_hdr = (const uint32_t*)c->d_bits + c->bits_cap_words + c->nmb;
+    HLB_CUDA(cudaMemcpyAsync(hdr, d_hdr, sizeof(hdr), cudaMemcpyDeviceToHost, c->stream));
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    if (hdr[1]) { snprintf(g_err, sizeof(g_err), "slice data of %u bits does not fit the device bit buffer (%d words)", hdr[0], c->bits_cap_words); return HLB200_ERR_OUTOFMEMORY; }
+    const size_t words = ((size_t)hdr[0] + 31) / 32;
+    if (words > cap_words) return HLB200_ERR_OUTOFMEMORY;
+    HLB_CUDA(cudaMemcpyAsync(out_words, c->d_bits, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, c->stream));
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    *nbits_out = hdr[0];
     return HLB200_OK;
 }
 

@@ -35,17 +35,60 @@
 #include "hartallo/h264/hl_codec_264_dpb.h"
 #include "hartallo/h264/hl_codec_264_pps.h"
 #include "hartallo/h264/hl_codec_264_macros.h"
+#include "hartallo/h264/hl_codec_264_bits.h"
+#include "hartallo/h264/hl_codec_264_rbsp.h"
 
 #include "hlb200.h"
 
-static struct {
+#include "hlb200_glue.h"
+
+/* one entry per codec instance (= per stream): many streams may live in one process, each with its own device context */
+typedef struct glue_stream_s {
+    const void* codec;                             /* key: the hl_codec_264_t of the stream */
     hlb200_ctx_t* ctx;
     int w, h, nmb, nslots;
-    hlb200_mb_record_t* rec;
+    hlb200_mb_record_t* rec;                       /* records mode only */
+    uint32_t* bits; size_t bits_cap;               /* bits mode: landing buffer of the device-written slice data */
     const void* fs_of_slot[HLB200_MAX_REFS + 1];   /* host frame store whose picture lives in each device slot */
     int is_p;
     int svc;                                       /* the stream has enhancement layers: they derive their motion from this layer's macroblock objects */
-} g;
+} glue_stream_t;
+#define GLUE_MAX_STREAMS 1024
+static glue_stream_t g_streams[GLUE_MAX_STREAMS];
+static int g_nstreams = 0;
+static glue_stream_t* g_cur = NULL;                /* stream whose reference macroblock loop is running (records mode) */
+static glue_stream_t* glue_stream_of(const void* codec, int create)
+{
+    int i;
+    for (i = 0; i < g_nstreams; ++i) if (g_streams[i].codec == codec) return &g_streams[i];
+    if (!create || g_nstreams >= GLUE_MAX_STREAMS) return NULL;
+    memset(&g_streams[g_nstreams], 0, sizeof(glue_stream_t));
+    g_streams[g_nstreams].codec = codec;
+    return &g_streams[g_nstreams++];
+}
+
+/* ---- batch mode (hlb200_glue.h): the slice hooks of many codec instances submit their pictures, ONE launch encodes and serialises them all ---- */
+static struct {
+    int active;
+    hlb200_glue_yield_fn yield; void* yield_arg;
+    int n, rc;
+    hlb200_ctx_t* ctxs[GLUE_MAX_STREAMS];
+    hlb200_slice_params_t prm[GLUE_MAX_STREAMS];
+    int32_t types[GLUE_MAX_STREAMS];
+} g_batch;
+void hlb200_glue_batch_begin(hlb200_glue_yield_fn yield, void* arg) { g_batch.active = 1; g_batch.yield = yield; g_batch.yield_arg = arg; g_batch.n = 0; g_batch.rc = 0; }
+void hlb200_glue_batch_end(void) { g_batch.active = 0; g_batch.n = 0; }
+int hlb200_glue_batch_pending(void) { return g_batch.n; }
+int hlb200_glue_batch_flush(void)
+{
+    int rc = 0;
+    if (g_batch.n > 0) {
+        rc = hlb200_slice_encode_batch_async(g_batch.ctxs, g_batch.prm, g_batch.n);
+        if (!rc) rc = hlb200_slice_bits_batch_async(g_batch.ctxs, g_batch.types, g_batch.n);
+    }
+    g_batch.rc = rc; g_batch.n = 0;
+    return rc;
+}
 
 static HL_ERROR_T glue_fail(const char* what, int rc)
 {
@@ -77,7 +120,7 @@ static void glue_apply(hl_codec_264_mb_t* p_mb, const hlb200_mb_record_t* r, int
         p_mb->flags_type = i16 ? HL_CODEC_264_MB_TYPE_FLAGS_INTRA_16x16 : HL_CODEC_264_MB_TYPE_FLAGS_INTRA_4x4;
         p_mb->MbPartPredMode[0] = i16 ? HL_CODEC_264_MB_MODE_INTRA_16X16 : HL_CODEC_264_MB_MODE_INTRA_4X4;
         p_mb->NumMbPart = 1;
-        if (g.svc && g.is_p) {
+        if (g_cur->svc && g_cur->is_p) {
             /* The enhancement layers' inter-layer derivation reads this object (utils.c:1701,1807-1834).  An Intra16x16 macroblock is recognised as intra by its
              * e_type whatever else it holds; an Intra4x4 macroblock of a P picture is NOT (HL_CODEC_264_MB_TYPE_IS_I_4X4 tests the type that only I pictures get
              * patched in, mb.c:326-345), so the reference derives enhancement-layer motion from it.  What that derivation can see of it: flags_type is intra
@@ -397,7 +440,8 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
     const hl_frame_video_t* frame = p_codec->encoder.pc_frame;
     const int W = (int)hdr->PicWidthInSamplesL, H = (int)hdr->PicHeightInSamplesL;
     hlb200_slice_params_t prm;
-    int rc, u, s, cur = -1;
+    glue_stream_t* g;
+    int rc, u, s, cur = -1, bits_mode;
     HL_ERROR_T err;
 
     if ((err = glue_check_settings(p_codec))) return err;
@@ -409,63 +453,98 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
         HL_DEBUG_ERROR("hlb200: only single-slice AVC pictures are supported by the device path");
         return HL_ERROR_NOT_IMPLEMENTED;
     }
-    if (!g.ctx || g.w != W || g.h != H) {
+    if (!(g = glue_stream_of(p_codec, 1))) { HL_DEBUG_ERROR("hlb200: too many codec instances"); return HL_ERROR_OUTOFCAPACITY; }
+    if (!g->ctx || g->w != W || g->h != H) {
         const char* dev = getenv("HLB200_DEVICE");
         int refs = (int)p_codec->pc_base->max_ref_frame;
         if (refs < 1) refs = 1;
         if (refs > HLB200_MAX_REFS) refs = HLB200_MAX_REFS;
-        if (g.ctx) { hlb200_stream_destroy(g.ctx); g.ctx = NULL; free(g.rec); }
+        if (g->ctx) { hlb200_stream_destroy(g->ctx); g->ctx = NULL; free(g->rec); free(g->bits); g->rec = NULL; g->bits = NULL; }
         if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
-        if ((rc = hlb200_stream_create(W, H, refs, &g.ctx))) return glue_fail("hlb200_stream_create", rc);
-        g.w = W; g.h = H; g.nmb = (W >> 4) * (H >> 4); g.nslots = refs + 1;
-        g.rec = (hlb200_mb_record_t*)malloc(sizeof(hlb200_mb_record_t) * (size_t)g.nmb);
-        memset(g.fs_of_slot, 0, sizeof(g.fs_of_slot));
+        if ((rc = hlb200_stream_create(W, H, refs, &g->ctx))) return glue_fail("hlb200_stream_create", rc);
+        g->w = W; g->h = H; g->nmb = (W >> 4) * (H >> 4); g->nslots = refs + 1;
+        memset(g->fs_of_slot, 0, sizeof(g->fs_of_slot));
     }
     memset(&prm, 0, sizeof(prm));
-    g.svc = p_codec->encoder.b_svc_enabled ? 1 : 0;
-    g.is_p = IsSliceHeaderP(hdr) ? 1 : 0;
-    prm.slice_type = g.is_p;
-    prm.qp = p_codec->encoder.rc.b_enabled ? p_codec->encoder.rc.qp : p_codec->encoder.i_qp;
+    g->svc = p_codec->encoder.b_svc_enabled ? 1 : 0;
+    g->is_p = IsSliceHeaderP(hdr) ? 1 : 0;
+    /* Single-layer streams: the device also serialises slice_data() (hlb200_slice_bits_*), the reference's macroblock loop and CAVLC writer do not run.  Streams with
+     * SVC enhancement layers keep the decision records: the layers' inter-layer derivation reads this layer's macroblock objects on the host (utils.c:966-2439). */
+    bits_mode = !g->svc && !getenv("HLB200_GLUE_RECORDS");
+    prm.slice_type = g->is_p;
+    prm.qp = p_codec->encoder.i_qp;
     prm.me_range = (int32_t)p_codec->pc_base->me_range;
     prm.chroma_qp_index_offset = hdr->pc_pps->chroma_qp_index_offset;
-    prm.num_refs = g.is_p ? (int32_t)hdr->num_ref_idx_l0_active_minus1 + 1 : 0;
+    prm.num_refs = g->is_p ? (int32_t)hdr->num_ref_idx_l0_active_minus1 + 1 : 0;
     /* device slots of the reference pictures (RefPicList0 order), then a free slot for the current picture */
     for (u = 0; u < prm.num_refs; ++u) {
         const void* fs = pc_layer->pobj_poc->RefPicList0[u];
         prm.ref_slot[u] = -1;
-        for (s = 0; s < g.nslots; ++s) if (fs && g.fs_of_slot[s] == fs) prm.ref_slot[u] = s;
+        for (s = 0; s < g->nslots; ++s) if (fs && g->fs_of_slot[s] == fs) prm.ref_slot[u] = s;
         if (prm.ref_slot[u] < 0) { HL_DEBUG_ERROR("hlb200: reference picture %d is not resident on the device", u); return HL_ERROR_INVALID_STATE; }
     }
-    for (s = 0; s < g.nslots && cur < 0; ++s) {
+    for (s = 0; s < g->nslots && cur < 0; ++s) {
         int used = 0;
         for (u = 0; u < prm.num_refs; ++u) used |= (prm.ref_slot[u] == s);
         if (!used) cur = s;
     }
     prm.cur_slot = cur;
-    for (s = 0; s < g.nslots; ++s) if (g.fs_of_slot[s] == (const void*)pc_layer->pc_fs_curr) g.fs_of_slot[s] = NULL;
-    g.fs_of_slot[cur] = pc_layer->pc_fs_curr;
+    for (s = 0; s < g->nslots; ++s) if (g->fs_of_slot[s] == (const void*)pc_layer->pc_fs_curr) g->fs_of_slot[s] = NULL;
+    g->fs_of_slot[cur] = pc_layer->pc_fs_curr;
 
-    if ((rc = hlb200_frame_upload(g.ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, W >> 1))) return glue_fail("hlb200_frame_upload", rc);
-    if ((rc = hlb200_slice_encode(g.ctx, &prm, g.rec))) return glue_fail("hlb200_slice_encode", rc);
-    if (getenv("HLB200_SYNC_RECON") || p_codec->encoder.b_svc_enabled) {   /* SVC: the enhancement layers resample / derive from the base picture on the host */   /* only when something on the host reads the reconstruction (MD5 hooks, decoder round trip) */
-        const hl_codec_264_pict_t* pict = pc_layer->pc_fs_curr->p_pict;
-        if ((rc = hlb200_slot_download(g.ctx, cur, (uint8_t*)pict->pc_data_y, (uint8_t*)pict->pc_data_u, (uint8_t*)pict->pc_data_v))) return glue_fail("hlb200_slot_download", rc);
+    if ((rc = hlb200_frame_upload(g->ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, W >> 1))) return glue_fail("hlb200_frame_upload", rc);
+    if (bits_mode) {
+        uint32_t nbits = 0, k, nw;
+        const size_t need = (size_t)g->nmb * HLB200_BITS_WORDS_PER_MB + 64;   /* capacity of the device buffer (hlb200.h) */
+        if (!g->bits) { g->bits = (uint32_t*)malloc(sizeof(uint32_t) * need); g->bits_cap = need; if (!g->bits) return HL_ERROR_OUTOFMEMMORY; }
+        if (g_batch.active) {
+            /* submit, hand control back to the driver until every stream of the batch has submitted and ONE launch has encoded them all */
+            if (g_batch.n >= GLUE_MAX_STREAMS) return HL_ERROR_OUTOFCAPACITY;
+            g_batch.ctxs[g_batch.n] = g->ctx; g_batch.prm[g_batch.n] = prm; g_batch.types[g_batch.n] = prm.slice_type; ++g_batch.n;
+            g_batch.yield(g_batch.yield_arg);
+            if (g_batch.rc) return glue_fail("batch launch", g_batch.rc);
+        }
+        else {
+            int32_t type = prm.slice_type;
+            if ((rc = hlb200_slice_encode_async(g->ctx, &prm))) return glue_fail("hlb200_slice_encode_async", rc);
+            if ((rc = hlb200_slice_bits_batch_async(&g->ctx, &type, 1))) return glue_fail("hlb200_slice_bits_batch_async", rc);
+        }
+        if ((rc = hlb200_slice_bits_download(g->ctx, g->bits, g->bits_cap, &nbits))) return glue_fail("hlb200_slice_bits_download", rc);
+        /* slice_data() continues the slice header bit for bit: appended with the reference's own bit writer, then rbsp_trailing_bits() as slice.c:1931 */
+        nw = nbits >> 5;
+        for (k = 0; k < nw; ++k) hl_codec_264_bits_write_u(p_esd->pobj_bits, g->bits[k], 32);
+        if (nbits & 31) hl_codec_264_bits_write_u(p_esd->pobj_bits, g->bits[nw] >> (32 - (nbits & 31)), (nbits & 31));
+        pc_layer->i_mb_encode_count += g->nmb;
+        if (getenv("HLB200_SYNC_RECON")) {
+            const hl_codec_264_pict_t* pict = pc_layer->pc_fs_curr->p_pict;
+            if ((rc = hlb200_slot_download(g->ctx, cur, (uint8_t*)pict->pc_data_y, (uint8_t*)pict->pc_data_u, (uint8_t*)pict->pc_data_v))) return glue_fail("hlb200_slot_download", rc);
+        }
+        return hl_codec_264_rbsp_avc_trailing_bits_write(p_esd->pobj_bits);
     }
-    return __real_hl_codec_264_nal_slice_data_encode(p_codec, p_esd);
+    if (!g->rec && !(g->rec = (hlb200_mb_record_t*)malloc(sizeof(hlb200_mb_record_t) * (size_t)g->nmb))) return HL_ERROR_OUTOFMEMMORY;
+    if ((rc = hlb200_slice_encode(g->ctx, &prm, g->rec))) return glue_fail("hlb200_slice_encode", rc);
+    if (getenv("HLB200_SYNC_RECON") || p_codec->encoder.b_svc_enabled) {   /* SVC: the enhancement layers resample / derive from the base picture on the host */
+        const hl_codec_264_pict_t* pict = pc_layer->pc_fs_curr->p_pict;
+        if ((rc = hlb200_slot_download(g->ctx, cur, (uint8_t*)pict->pc_data_y, (uint8_t*)pict->pc_data_u, (uint8_t*)pict->pc_data_v))) return glue_fail("hlb200_slot_download", rc);
+    }
+    g_cur = g;
+    err = __real_hl_codec_264_nal_slice_data_encode(p_codec, p_esd);
+    g_cur = NULL;
+    return err;
 }
 
 HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_avc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec, int32_t* pi_mad)
 {
     (void)p_codec;
-    if (!g.rec || p_mb->u_addr >= (uint32_t)g.nmb) return HL_ERROR_INVALID_STATE;
-    glue_apply(p_mb, &g.rec[p_mb->u_addr], pi_mad);
+    if (!g_cur || !g_cur->rec || p_mb->u_addr >= (uint32_t)g_cur->nmb) return HL_ERROR_INVALID_STATE;
+    glue_apply(p_mb, &g_cur->rec[p_mb->u_addr], pi_mad);
     return HL_ERROR_SUCCESS;
 }
 
 HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_intra_pred_avc(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_codec, int32_t* pi_mad)
 {
     (void)p_codec;
-    if (!g.rec || p_mb->u_addr >= (uint32_t)g.nmb) return HL_ERROR_INVALID_STATE;
-    glue_apply(p_mb, &g.rec[p_mb->u_addr], pi_mad);
+    if (!g_cur || !g_cur->rec || p_mb->u_addr >= (uint32_t)g_cur->nmb) return HL_ERROR_INVALID_STATE;
+    glue_apply(p_mb, &g_cur->rec[p_mb->u_addr], pi_mad);
     return HL_ERROR_SUCCESS;
 }

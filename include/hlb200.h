@@ -269,6 +269,18 @@ HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y
  * operations executed. */
 HLB200_API int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink, void* cuda_stream, uint64_t* ops_out);
 
+/* ---- device-side CAVLC serialisation: slice_data() of the picture each context encoded last, written on the device from its decision records.
+ * Replaces the WRITING half of the reference's macroblock loop: mb_skip_run bookkeeping + _hl_codec_264_mb_write_no_pcm (source/h264/hl_codec_264_mb.c:543-860) +
+ * hl_codec_264_residual_write (source/h264/hl_codec_264_residual.c:903-1094) + the VLC writers (source/h264/hl_codec_264_cavlc.c:652-836), for the syntax the
+ * reference's encoder emits (Baseline, CAVLC, one slice per picture, no ref_idx).  slice_types[i]: 0 = I, 1 = P (as hlb200_slice_params_t).  One launch sequence
+ * for the whole batch on the stream of ctxs[0]; same ordering rule as hlb200_slice_encode_batch_async.  The output excludes rbsp_trailing_bits(): the host
+ * appends the bits to the slice header it wrote (e.g. hl_codec_264_bits_write_u, 32 bits per word) and finishes the NAL as before. */
+#define HLB200_BITS_WORDS_PER_MB 448   /* capacity of the per-picture bit buffer, 32-bit words per macroblock: above the CAVLC worst case (~1.7 KB per macroblock) */
+HLB200_API int hlb200_slice_bits_batch_async(hlb200_ctx_t** ctxs, const int32_t* slice_types, int n);
+/* *nbits_out = length of slice_data() in bits; out_words[k] holds bits 32k .. 32k+31, bit 32k in the most significant position, host byte order.
+ * HLB200_ERR_OUTOFMEMORY when the picture does not fit cap_words (nmb * HLB200_BITS_WORDS_PER_MB + 64 words always suffice). */
+HLB200_API int hlb200_slice_bits_download(hlb200_ctx_t* ctx, uint32_t* out_words, size_t cap_words, uint32_t* nbits_out);
+
 /* ---- device self-test: the packed-instruction formulations of the search's 4x4 primitives (prediction at all 16 fractional positions, trial encode at
  * QP 12..51) against the plain formulations, both run on the device over `blocks` x 64 threads of pseudo-random inputs; *mismatches_out = 0 when they agree. */
 HLB200_API int hlb200_dev_selftest(int blocks, unsigned seed, int* mismatches_out);

@@ -26,6 +26,7 @@ struct CpuExec {
         for (int p = 0; p < np; ++p)
             for (int lane = 0; lane < nlanes; ++lane) cmd_phase(*w, *f, cmd, p, lane);
     }
+    void trials(int nlanes) { for (int lane = 0; lane < nlanes; ++lane) me_phase_trial(*w, *f, lane); }
     int lane() const { return 0; }
     int nlanes() const { return 1; }
     void sync() const {}

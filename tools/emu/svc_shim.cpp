@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "../../include/hlb200.h"
 #ifdef SVC_SHIM_WITH_SLICE   /* also stand in for hlb200_slice_encode: the slice kernel's per-macroblock source run in raster order, as tools/emu/emu_main.cpp does */
 #include <math.h>
@@ -11,6 +12,7 @@
 int g_emu_dbg = 0;
 #define HLB_EMU_DEBUG 1
 #include "../../hartallo_b200/csrc/hlb_mbcore.cuh"
+#include "../../hartallo_b200/csrc/hlb_bits.cuh"
 #endif
 
 extern "C" int svc_emu_recon_batch(int bl, const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v,
@@ -26,6 +28,8 @@ struct hlb200_ctx {
     hlb::MbState* mbstate;
     hlb::MbWork* work;
     int chain;
+    hlb200_mb_record_t* rec;      /* records of the last picture (hlb200_slice_encode_async) */
+    uint32_t* bits; uint32_t nbits;
 #endif
 };
 #define API extern "C" __attribute__((visibility("default")))
@@ -42,6 +46,8 @@ API int hlb200_stream_create(int w, int h, int max_refs, hlb200_ctx_t** out)
 #ifdef SVC_SHIM_WITH_SLICE
     c->mbstate = (hlb::MbState*)calloc((size_t)c->nmb, sizeof(hlb::MbState));
     c->work = (hlb::MbWork*)calloc(1, sizeof(hlb::MbWork));
+    c->rec = (hlb200_mb_record_t*)calloc((size_t)c->nmb, sizeof(hlb200_mb_record_t));
+    c->bits = (uint32_t*)calloc((size_t)c->nmb * HLB200_BITS_WORDS_PER_MB + 64, sizeof(uint32_t));
 #endif
     *out = c;
     return HLB200_OK;
@@ -51,7 +57,7 @@ API int hlb200_stream_destroy(hlb200_ctx_t* c)
     free(c->src); free(c->state);
     for (int s = 0; s < c->nslots; ++s) free(c->slot[s]);
 #ifdef SVC_SHIM_WITH_SLICE
-    free(c->mbstate); free(c->work);
+    free(c->mbstate); free(c->work); free(c->rec); free(c->bits);
 #endif
     free(c);
     return HLB200_OK;
@@ -88,6 +94,7 @@ struct CpuExec {   // the executor of tools/emu/emu_main.cpp: lanes become loops
         for (int p = 0; p < np; ++p)
             for (int lane = 0; lane < nlanes; ++lane) hlb::cmd_phase(*w, *f, cmd, p, lane);
     }
+    void trials(int nlanes) { for (int lane = 0; lane < nlanes; ++lane) hlb::me_phase_trial(*w, *f, lane); }
     int lane() const { return 0; }
     int nlanes() const { return 1; }
     void sync() const {}
@@ -127,8 +134,48 @@ API int hlb200_slice_encode(hlb200_ctx_t* c, const hlb200_slice_params_t* p, hlb
     c->chain = x.prev_sctr(c->nmb);
     return HLB200_OK;
 }
+API int hlb200_slice_encode_async(hlb200_ctx_t* c, const hlb200_slice_params_t* p) { return hlb200_slice_encode(c, p, c->rec); }
+API int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_params_t* p, int n)
+{
+    for (int i = 0; i < n; ++i) { const int rc = hlb200_slice_encode(ctxs[i], p + i, ctxs[i]->rec); if (rc) return rc; }
+    return HLB200_OK;
+}
+// the three kernels of hlb_slice.cu (k_bits_len, k_bits_scan, k_bits_write) as loops over the same per-macroblock code (hlb_bits.cuh)
+API int hlb200_slice_bits_batch_async(hlb200_ctx_t** ctxs, const int32_t* types, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        hlb200_ctx* c = ctxs[i];
+        std::vector<uint32_t> len((size_t)c->nmb);
+        hlb::BitsJob j;
+        j.rec = c->rec; j.st = c->mbstate; j.len = len.data(); j.out = c->bits; j.hdr = nullptr; j.nmb = c->nmb; j.mbw = c->w >> 4; j.is_p = types[i]; j.cap_words = c->nmb * HLB200_BITS_WORDS_PER_MB + 64;
+        uint32_t total = 0;
+        for (int mb = 0; mb < c->nmb; ++mb) { hlb::BitCount k; k.n = 0; hlb::bits_put_mb(k, j, mb); len[mb] = total; total += k.n; }
+        memset(c->bits, 0, sizeof(uint32_t) * ((total + 31) / 32 + 2));
+        for (int mb = 0; mb < c->nmb; ++mb) {
+            hlb::BitWriter w;
+            w.buf = c->bits; w.pos = len[mb]; w.acc = 0; w.nacc = 0;
+            hlb::bits_put_mb(w, j, mb);
+            w.finish();
+            if (w.pos != (mb + 1 < c->nmb ? len[mb + 1] : total)) return HLB200_ERR_INVALID_STATE;   // the counting and the writing sink must agree
+        }
+        c->nbits = total;
+    }
+    return HLB200_OK;
+}
+API int hlb200_slice_bits_download(hlb200_ctx_t* c, uint32_t* out, size_t cap, uint32_t* nbits)
+{
+    const size_t words = ((size_t)c->nbits + 31) / 32;
+    if (words > cap) return HLB200_ERR_OUTOFMEMORY;
+    memcpy(out, c->bits, sizeof(uint32_t) * words);
+    *nbits = c->nbits;
+    return HLB200_OK;
+}
 #else
 API int hlb200_slice_encode(hlb200_ctx_t*, const hlb200_slice_params_t*, hlb200_mb_record_t*) { return HLB200_ERR_SYSTEM; }   // base layer: not emulated in this build
+API int hlb200_slice_encode_async(hlb200_ctx_t*, const hlb200_slice_params_t*) { return HLB200_ERR_SYSTEM; }
+API int hlb200_slice_encode_batch_async(hlb200_ctx_t**, const hlb200_slice_params_t*, int) { return HLB200_ERR_SYSTEM; }
+API int hlb200_slice_bits_batch_async(hlb200_ctx_t**, const int32_t*, int) { return HLB200_ERR_SYSTEM; }
+API int hlb200_slice_bits_download(hlb200_ctx_t*, uint32_t*, size_t, uint32_t*) { return HLB200_ERR_SYSTEM; }
 #endif
 API int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp, int off, const hlb200_mb_motion_t* motion, const uint8_t* pred_y, const uint8_t* pred_u,
                                  const uint8_t* pred_v, hlb200_mb_coeffs_t* out)
