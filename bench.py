@@ -196,7 +196,58 @@ def measure_int_peak(torch, hl, lib, dev, stream, sp):
     return best
 
 
-NCU_DRAM_BYTES_PER_MB = 10592   # k_slice_encode_warp, profiles/r01f_summary.md
+NCU_DRAM_BYTES_PER_MB = 11363   # k_slice_encode_warp, profiles/r02j (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its macroblocks)
+MULTI = os.path.join(ROOT, "oracle", "_ref", "hl_b200_multi")       # the reference's host code + host/hlb200_glue.c (batch mode) + libhl_b200.so: many streams through hl_codec_encode
+BENCH_GOLDEN = os.path.join(ROOT, "tests", "golden", "encoder_1080p_bench.json")
+
+
+def encode_and_serialise(hl, lib, encs, types_buf, ctxs_buf):
+    """one picture of every stream: the slice kernel (decide + reconstruct) and the device-side CAVLC serialisation of its slice data"""
+    ps = hl.encode_batch(encs, [None] * len(encs))
+    for i in range(len(encs)):
+        types_buf[i] = ps[i].slice_type
+    hl.check(lib.hlb200_slice_bits_batch_async(ctxs_buf, types_buf, len(encs)), "slice_bits_batch_async")
+    return ps
+
+
+def all_inter_line(args, local, dev, torch, hl, lib, synth, stream, sp, streams=64, steps=2):
+    """the same path on G2 content (SURVEY 8d "stress"): no macroblock is skipped, every one runs the full 7-mode search -- the per-class figure behind the headline"""
+    ysz, csz = W * H, W * H // 4
+    seqs = []
+    for k in range(4):
+        g = synth.G2(W, H, seed=3 + k)
+        seqs.append([torch.from_numpy(g.next()).to(dev) for _ in range(2 + steps)])
+    encs = [hl.Encoder(W, H, qp=QP, me_range=ME_RANGE, refs=1, device=local) for _ in range(streams)]
+    n = len(encs)
+    ctxs, types = (C.c_void_p * n)(), (C.c_int32 * n)()
+    for i, e in enumerate(encs):
+        hl.check(lib.hlb200_stream_set_cuda_stream(e.st.ctx, sp), "set_cuda_stream")
+        ctxs[i] = e.st.ctx
+
+    def step(nf):
+        for i, e in enumerate(encs):
+            b = seqs[i % 4][nf].data_ptr()
+            hl.check(lib.hlb200_frame_set_device(e.st.ctx, b, b + ysz, b + ysz + csz), "frame_set_device")
+        return encode_and_serialise(hl, lib, encs, types, ctxs)
+    step(0); step(1)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for k in range(steps):
+        step(2 + k)
+    b.record(stream)
+    torch.cuda.synchronize()
+    encs[0].st.slice_status()
+    ms = a.elapsed_time(b) / steps
+    kinds = np.zeros(4, np.int64)
+    rec = np.zeros(NMB, hl.MB_RECORD)
+    hl.check(lib.hlb200_records_download(encs[0].st.ctx, hl.ptr(rec)), "records_download")
+    kinds += np.bincount(rec["mb_class"], minlength=4)[:4]
+    for e in encs:
+        e.close()
+    return {"value": streams * NMB / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "streams": streams, "steps": steps,
+            "workload": "%d streams of 1920x1088 G2 content (random texture with saturated patches, translated): every macroblock searched over all 7 partition modes" % streams,
+            "mb_classes_stream0": {"pskip": int(kinds[0]), "inter": int(kinds[1]), "i16": int(kinds[2]), "i4": int(kinds[3])}}
 
 
 def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, stream, sp):
@@ -205,9 +256,9 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     my_streams = sharding.streams_of_rank(rank, world, S * world)   # weak scaling: S streams per GPU, world * S in total
     ysz, csz = W * H, W * H // 4
     frame_b = ysz + 2 * csz
-    nfr = 1 + Wm + K + 2 + K             # IDR + warm-up + timed (device-resident) + e2e warm-up + e2e timed: one continuous sequence
+    nfr = 1 + Wm + K             # IDR + warm-up + timed: one continuous sequence per stream
     # ---- S independent streams: own context, frame stores, per-MB state; own synthetic sequence (G1, distinct seeds) ----
-    encs, d_frames, h_frames, seqs = [], [], [], {}
+    encs, d_frames, seqs = [], [], {}
     for s_i in range(S):
         e = hl.Encoder(W, H, qp=QP, me_range=ME_RANGE, refs=1, device=local)
         hl.check(lib.hlb200_stream_set_cuda_stream(e.st.ctx, sp), "set_cuda_stream")
@@ -217,19 +268,16 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
         if key not in seqs:
             g = synth.G1(W, H, seed=sharding.stream_seed(key + 1000 * rank))
             seqs[key] = [g.next() for _ in range(nfr)]
-        fr = seqs[key]
-        d_frames.append([torch.from_numpy(f).to(dev) for f in fr[:1 + Wm + K]])
-    # pinned host copies of the pictures the end-to-end phase uploads (the sequences simply continue)
-    pinned = {key: {n: torch.from_numpy(fr[n]).pin_memory() for n in range(1 + Wm + K, nfr)} for key, fr in seqs.items()}
-
-    def set_src(s_i, n):
-        b = d_frames[s_i][n].data_ptr()
-        hl.check(lib.hlb200_frame_set_device(encs[s_i].st.ctx, b, b + ysz, b + ysz + csz), "frame_set_device")
+        d_frames.append([torch.from_numpy(f).to(dev) for f in seqs[key]])
+    ctxs, types = (C.c_void_p * S)(), (C.c_int32 * S)()
+    for i, e in enumerate(encs):
+        ctxs[i] = e.st.ctx
 
     def step(n):
         for s_i in range(S):
-            set_src(s_i, n)
-        return hl.encode_batch(encs, [None] * S)
+            b = d_frames[s_i][n].data_ptr()
+            hl.check(lib.hlb200_frame_set_device(encs[s_i].st.ctx, b, b + ysz, b + ysz + csz), "frame_set_device")
+        return encode_and_serialise(hl, lib, encs, types, ctxs)
 
     def barrier():
         if world > 1:
@@ -264,6 +312,20 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     value = world * S * NMB * K / (ms_total * 1e-3)
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
 
+    # ---- self-check: the picture stream 0 of rank 0 reconstructed last must be the reference encoder's (tests/golden/encoder_1080p_bench.json, made by the
+    # unmodified reference on this very sequence: G1 seed 12345, QP 31, ME +-32), and so must the slice data the device wrote (checked through the e2e arm) ----
+    parity = {"checked": False}
+    if rank == 0 and os.path.exists(BENCH_GOLDEN):
+        import hashlib
+        gold = json.load(open(BENCH_GOLDEN))
+        idx = Wm + K
+        if my_streams[0] % args.distinct == 0 and idx < len(gold["recon_md5"]):
+            recon = encs[0].st.download_slot(last[0].cur_slot)
+            ok = hashlib.md5(recon.tobytes()).hexdigest() == gold["recon_md5"][idx]
+            parity = {"checked": True, "recon_md5_equal": bool(ok), "picture": idx, "golden": "tests/golden/encoder_1080p_bench.json (unmodified reference encoder on the sequence of stream 0)"}
+            if not ok:
+                raise SystemExit("bench.py: the reconstruction of stream 0, picture %d differs from the reference encoder's" % idx)
+
     # ---- algorithmic work of the last timed launch: the reference trajectory's trial encodes (identical by parity) ----
     trials = interp = cands = intra = 0
     kinds = np.zeros(4, np.int64)
@@ -274,63 +336,75 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
         kinds += np.bincount(rec["mb_class"], minlength=4)[:4]
     ops = (trials + intra) * 560 + interp
     int_peak = measure_int_peak(torch, hl, lib, dev, stream, sp)
-    kms = step_ms[-1]
+    kms = float(np.mean(step_ms))          # mean launch duration over the timed region (CUDA events on the launching stream)
     ach = ops / (kms * 1e-3) / 1e9
     variant = int(lib.hlb200_slice_last_variant())
     roof = {"kernel": "k_slice_encode_warp" if variant else "k_slice_encode", "variant": "one warp per macroblock" if variant else "one CTA per macroblock", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak,
-            # DRAM bytes of the kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture
-            # (profiles/r01f_summary.md: 7.13 GB + 3.94 GB for 128 x 8160 macroblocks = 10,592 B per macroblock), scaled to this launch
-            "traffic": int(NCU_DRAM_BYTES_PER_MB * S * NMB), "traffic_unit": "bytes per launch (ncu capture profiles/r01f, scaled by macroblocks)", "ms": kms,
+            # DRAM bytes of the kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture, scaled to this launch
+            "traffic": int(NCU_DRAM_BYTES_PER_MB * S * NMB), "traffic_unit": "bytes per launch (ncu capture profiles/r02j, scaled by macroblocks)", "ms": kms,
+            "ms_kind": "mean of the timed launches (the three serialisation kernels of a step are included: < 1 % of it)",
             "peak_kind": "measured live (hlb200_dev_int_alu_probe: dependency-free IADD3/LOP3)", "algorithmic_ops_per_launch": ops,
             "per_mb": {"me_candidates": cands / (S * NMB), "me_trials": trials / (S * NMB), "intra_trials": intra / (S * NMB), "int_ops": ops / (S * NMB)},
-            "note": "ops = (ME + intra 4x4 trial encodes) x 560 + interpolation ops by fractional class (SURVEY.md Appendix D), counted on the reference trajectory"}
-
-    # ---- end to end through the host-buffer C-ABI: upload of every source picture, download of every decision record ----
-    # pinned landing buffers for the records: hlb200_records_download returns after its copy has completed, so a small ring is enough
-    h_rec = [torch.empty(NMB * hl.MB_RECORD.itemsize, dtype=torch.uint8).pin_memory() for _ in range(min(S, 8))]
-
-    def e2e_step(n):
-        for s_i, e in enumerate(encs):
-            f = pinned[my_streams[s_i] % args.distinct][n].numpy()
-            hl.check(lib.hlb200_frame_upload(e.st.ctx, hl.ptr(f[:ysz]), hl.ptr(f[ysz:ysz + csz]), hl.ptr(f[ysz + csz:]), W, W // 2), "frame_upload")
-        ps = (hl.SliceParams * S)()
-        ctxs = (C.c_void_p * S)()
-        for i, e in enumerate(encs):
-            p = e.params()
-            C.memmove(C.byref(ps[i]), C.byref(p), C.sizeof(hl.SliceParams))
-            ctxs[i] = e.st.ctx
-        hl.check(lib.hlb200_slice_encode_batch_async(ctxs, ps, S), "slice_encode_batch_async")
-        for i, e in enumerate(encs):
-            e.advance(ps[i])
-            hl.check(lib.hlb200_records_download(e.st.ctx, h_rec[i % len(h_rec)].data_ptr()), "records_download")
-    for i in range(2):
-        e2e_step(1 + Wm + K + i)
-    barrier()
-    te = time.perf_counter()
-    for i in range(K):
-        e2e_step(1 + Wm + K + 2 + i)
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([(time.perf_counter() - te) * 1e3], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * NMB * K / (float(e2e_ms.item()) * 1e-3)
+            "note": "ops = (ME + intra 4x4 trial encodes) x 560 + interpolation ops by fractional class (SURVEY.md Appendix D), counted on the reference trajectory of the last timed launch"}
     for e in encs:
         e.close()
+    del d_frames
+    torch.cuda.empty_cache()
+
+    # ---- the per-class figure: the same path on all-inter content (rank 0 only; not part of `value`) ----
+    all_inter = None
+    if rank == 0 and not args.no_all_inter:
+        all_inter = all_inter_line(args, local, dev, torch, hl, lib, synth, stream, sp)
+        torch.cuda.empty_cache()
+
+    # ---- end to end: S streams through the reference's public API (hl_codec_encode) with the drop-in glue in batch mode: host pictures in, H.264 bitstreams out ----
+    barrier()
+    e2e = None
+    if os.path.exists(MULTI) and os.access(MULTI, os.X_OK):
+        env = dict(os.environ, HLB200_DEVICE=str(local))
+        cmd = [MULTI, "--streams", str(S), "--frames", str(nfr), "--warmup", str(Wm), "--groups", "1", "--qp", str(QP), "--me-range", str(ME_RANGE), "--distinct", str(min(args.distinct, S))]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        if r.returncode != 0:
+            raise SystemExit("bench.py: %s failed: %s" % (os.path.basename(MULTI), r.stderr[-400:]))
+        mj = json.loads(r.stdout.strip().splitlines()[-1])
+        e2e_ms = torch.tensor([mj["ms_timed"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_value = world * S * NMB * K / (float(e2e_ms.item()) * 1e-3)
+        e2e = {"value": e2e_value, "unit": UNIT, "encode_fps": world * S * K / (float(e2e_ms.item()) * 1e-3), "fps_unit": "1080p pictures/s over all streams (H.264 bitstream produced)",
+               "h2d_bytes_per_step": int(S * frame_b), "d2h_bytes_per_step": int(mj["bitstream_bytes_timed"] // max(K, 1)), "ms_per_step": float(e2e_ms.item()) / K,
+               "bitstream_bytes_per_step": int(mj["bitstream_bytes_timed"] // max(K, 1)),
+               "api": "hl_codec_encode (the reference's unmodified host code: headers, DPB, NAL assembly, emulation prevention) x %d codec instances per GPU, host/hlb200_glue.c in batch mode: "
+                      "hlb200_frame_upload from page-locked host pictures + ONE hlb200_slice_encode_batch_async + ONE hlb200_slice_bits_batch_async per picture of all streams + "
+                      "hlb200_slice_bits_download (slice data written on the device)" % S,
+               "driver": "oracle/_ref/hl_b200_multi (host/hl_b200_multi.c)"}
+        if rank == 0 and os.path.exists(BENCH_GOLDEN):
+            gold = json.load(open(BENCH_GOLDEN))
+            pref = gold.get("bitstream_prefix", [])
+            if nfr <= len(pref):
+                ok = [mj["bytes"], mj["md5"]] == pref[nfr - 1]
+                parity["bitstream_md5_equal"] = bool(ok)
+                parity["bitstream"] = "stream 0 of the e2e arm, %d pictures: %d bytes, MD5 %s" % (nfr, mj["bytes"], mj["md5"])
+                if not ok:
+                    raise SystemExit("bench.py: the bitstream of stream 0 (%d pictures) differs from the reference encoder's" % nfr)
+    else:
+        raise SystemExit("bench.py: %s is missing (built by oracle/build_ref.sh where the reference tree is available); there is no other end-to-end path" % MULTI)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": "%d independent 1080p (1920x1088) synthetic G1 YUV 4:2:0 streams per GPU (own contexts and buffers; 16 distinct contents), one P picture of each per step (one launch): Baseline/CAVLC "
+                "config": {"workload": "%d independent 1080p (1920x1088) synthetic G1 YUV 4:2:0 streams per GPU (own contexts and buffers; %d distinct contents), one P picture of each per step (one launch): Baseline/CAVLC "
                                        "tools, 4x4 transform, 1 ref, quarter-pel ME +-%d over all 7 partition modes with the reference's RD cost, intra decision, "
-                                       "reconstruction; QP %d" % (S, ME_RANGE, QP),
+                                       "reconstruction, slice data serialised on the device; QP %d" % (S, min(args.distinct, S), ME_RANGE, QP),
                            "l2": "inputs larger than L2: %d streams x (source + 2 frame stores + records + state) = %.0f MB touched per step, new source pictures every step" %
                                  (S, S * (3 * frame_b + NMB * (hl.MB_RECORD.itemsize + 392)) / 1e6),
-                           "sharding": "independent streams per GPU, no collective", "parity": "bit-exact vs the reference encoder (tests/test_encoder.py)",
+                           "sharding": "independent streams per GPU, no collective", "parity": "bit-exact vs the reference encoder (tests/test_encoder.py, tests/test_bits.py; self-check below)",
                            "mb_classes_last_step": {"pskip": int(kinds[0]), "inter": int(kinds[1]), "i16": int(kinds[2]), "i4": int(kinds[3])}},
-                "clocks": clk, "gpu_launches": 2 * K,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * frame_b), "d2h_bytes_per_step": int(S * NMB * hl.MB_RECORD.itemsize),
-                        "ms_per_step": float(e2e_ms.item()) / K,
-                        "api": "hlb200_frame_upload (pinned host pictures) + hlb200_slice_encode_batch_async + hlb200_records_download (decision records to the host writer)"},
-                "roofline": roof, "step_ms": step_ms}
+                "clocks": clk, "gpu_launches": 5 * K, "e2e": e2e, "roofline": roof, "step_ms": step_ms,
+                "parity_checked": bool(parity.get("checked") and parity.get("recon_md5_equal") and parity.get("bitstream_md5_equal", True)), "parity": parity,
+                "encode_fps": e2e["encode_fps"]}
+        if all_inter:
+            line["all_inter"] = all_inter
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
@@ -356,6 +430,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences; stream s shows sequence s %% distinct (own buffers)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-all-inter", action="store_true", help="skip the G2 (all-inter) sub-measurement")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":

@@ -102,6 +102,20 @@ int hlb200_init(int device)
     return HLB200_OK;
 }
 
+// page-locks a caller-owned host buffer so that hlb200_frame_upload from it is a true asynchronous DMA (a host program in C has no other way to ask the CUDA runtime)
+int hlb200_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return HLB200_ERR_INVALID_PARAMETER;
+    HLB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return HLB200_OK;
+}
+int hlb200_host_unregister(void* p)
+{
+    if (!p) return HLB200_ERR_INVALID_PARAMETER;
+    HLB_CUDA(cudaHostUnregister(p));
+    return HLB200_OK;
+}
+
 int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out)
 {
     if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || max_refs < 1 || max_refs > HLB200_MAX_REFS) return HLB200_ERR_INVALID_PARAMETER;

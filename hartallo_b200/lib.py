@@ -68,6 +68,7 @@ def load():
         "hlb200_dev_svc_bl_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp],
         "hlb200_dev_me_cost": [vp, vp, ip, ip, ip, vp, ip, vp, vp], "hlb200_dev_int_alu_probe": [ip, ip, vp, vp, C.POINTER(C.c_uint64)],
         "hlb200_slice_bits_batch_async": [C.POINTER(vp), C.POINTER(C.c_int32), ip], "hlb200_slice_bits_download": [vp, vp, C.c_size_t, C.POINTER(C.c_uint32)],
+        "hlb200_host_register": [vp, C.c_size_t], "hlb200_host_unregister": [vp],
         "hlb200_dev_selftest": [ip, C.c_uint, C.POINTER(ip)], "hlb200_dev_tma_probe": [vp, ip, ip, ip, ip, ip, C.POINTER(ip)],
     }
     for name, args in sig.items():

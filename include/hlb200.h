@@ -269,6 +269,10 @@ HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y
  * operations executed. */
 HLB200_API int hlb200_dev_int_alu_probe(int blocks, int iters, uint32_t* d_sink, void* cuda_stream, uint64_t* ops_out);
 
+/* page-locks / releases a caller-owned host buffer (source pictures): uploads from it become asynchronous DMA transfers */
+HLB200_API int hlb200_host_register(void* p, size_t bytes);
+HLB200_API int hlb200_host_unregister(void* p);
+
 /* ---- device-side CAVLC serialisation: slice_data() of the picture each context encoded last, written on the device from its decision records.
  * Replaces the WRITING half of the reference's macroblock loop: mb_skip_run bookkeeping + _hl_codec_264_mb_write_no_pcm (source/h264/hl_codec_264_mb.c:543-860) +
  * hl_codec_264_residual_write (source/h264/hl_codec_264_residual.c:903-1094) + the VLC writers (source/h264/hl_codec_264_cavlc.c:652-836), for the syntax the

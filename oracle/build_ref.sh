@@ -56,6 +56,12 @@ if [ -f "$GLUE" ] && [ -f "$HERE/ref_driver.c" ]; then
   # libhl_b200.so is resolved at run time relative to the binary (oracle/_ref -> hartallo_b200)
   gcc "$TMP/obj_driver_nw.o" "$TMP/obj_glue.o" $GW "$OUT/libhartallo_ref.a" -L"$HERE/../hartallo_b200" -lhl_b200 -Wl,-rpath,'$ORIGIN/../../hartallo_b200' -lpthread -lm -ldl -o "$OUT/hl_b200_encoder" \
     || echo "build_ref: hl_b200_encoder not linked (build hartallo_b200/libhl_b200.so first)" >&2
+  # the multi-stream drop-in: many codec instances through hl_codec_encode, ONE device launch per picture of all of them (host/hl_b200_multi.c, glue batch mode)
+  if [ -f "$HERE/../host/hl_b200_multi.c" ]; then
+    gcc $CF -I"$HERE/../include" -I"$HERE/../host" -c "$HERE/../host/hl_b200_multi.c" -o "$TMP/obj_multi.o"
+    gcc "$TMP/obj_multi.o" "$TMP/obj_glue.o" $GW "$OUT/libhartallo_ref.a" -L"$HERE/../hartallo_b200" -lhl_b200 -Wl,-rpath,'$ORIGIN/../../hartallo_b200' -lpthread -lm -ldl -o "$OUT/hl_b200_multi" \
+      || echo "build_ref: hl_b200_multi not linked" >&2
+  fi
 fi
 # CPU check of the SVC enhancement-layer hook of the glue: base layer on the reference's CPU path, enhancement layers through the glue with the device source
 # compiled as C++ standing in for libhl_b200.so (tools/emu/svc_shim.cpp + svc_emu.cpp)
@@ -68,5 +74,9 @@ if [ -f "$GLUE" ] && [ -f "$HERE/../tools/emu/svc_shim.cpp" ]; then
   # standing in for the library: every layer goes through the drop-in path, nothing through the reference's decision functions
   g++ -std=c++17 -O2 -w -fPIC -ffp-contract=off -DSVC_SHIM_WITH_SLICE -x c++ -c "$HERE/../tools/emu/svc_shim.cpp" -o "$TMP/obj_shim_full.o"
   g++ "$TMP/obj_driver_nw.o" "$TMP/obj_glue.o" "$TMP/obj_shim_full.o" "$TMP/obj_emu.o" $GW "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_glue_check_full"
+  # CPU check of the multi-stream driver + the glue's batch mode (same stand-in for the library)
+  if [ -f "$TMP/obj_multi.o" ]; then
+    g++ "$TMP/obj_multi.o" "$TMP/obj_glue.o" "$TMP/obj_shim_full.o" "$TMP/obj_emu.o" $GW "$OUT/libhartallo_ref.a" -lpthread -lm -ldl -o "$OUT/hl_multi_check"
+  fi
 fi
 echo "build_ref: built $(ls "$OUT")"

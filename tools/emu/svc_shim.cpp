@@ -34,6 +34,8 @@ struct hlb200_ctx {
 };
 #define API extern "C" __attribute__((visibility("default")))
 API int hlb200_init(int) { return HLB200_OK; }
+API int hlb200_host_register(void*, size_t) { return HLB200_OK; }
+API int hlb200_host_unregister(void*) { return HLB200_OK; }
 API const char* hlb200_last_error(void) { return "svc_shim"; }
 API int hlb200_stream_create(int w, int h, int max_refs, hlb200_ctx_t** out)
 {
