@@ -150,6 +150,7 @@ int main(int argc, char** argv)
 {
     int streams = 8, distinct = 0, warm = 1, same = 0, groups = 2, refs = 1, i, f, g, failed = 0;
     uint32_t seed = 3;
+    const char* out_path = NULL;
     const struct hl_codec_plugin_def_s* plugin = NULL;
     stream_t* st;
     double t0 = 0, t1, t_first = 0;
@@ -168,6 +169,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--same-content")) same = 1;                                   /* every stream encodes sequence 0: all bitstreams must be equal */
         else if (!strcmp(argv[i], "--groups") && i + 1 < argc) groups = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = (uint32_t)atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];               /* bitstream of stream 0 */
         else if (!strcmp(argv[i], "--gen") && i + 1 < argc) { ++i; g_gen = !strcmp(argv[i], "g2") ? 2 : 1; }
         else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
     }
@@ -247,7 +249,8 @@ int main(int argc, char** argv)
     if (failed) return 1;
     for (i = 0; i < streams; ++i) bytes_timed += st[i].out_n;
     bytes_timed -= bytes_at_t0;
-    md5_hex(st[0].out, st[0].out_n, md5);
+    md5_hex(st[0].out, st[0].out_n, md5);   /* the reference's own hl_md5 (as oracle/ref_driver.c prints it) */
+    if (out_path) { FILE* fo = fopen(out_path, "wb"); if (!fo) { perror(out_path); return 2; } fwrite(st[0].out, 1, st[0].out_n, fo); fclose(fo); }
     {
         int all_equal = 1;
         const int timed = g_frames - 1 - warm, mbs = (g_w / 16) * (g_h / 16);
