@@ -33,64 +33,104 @@ __device__ __forceinline__ void load_win9(const uint8_t* __restrict__ plane, int
     }
 }
 
-// ---------------- luma interpolation: one thread per 4x4 block, raster block order inside the MB -------------------
+// ---------------- luma interpolation: one thread per 4x4 block, blocks in PICTURE raster order -------------------------------------------------
+// (a warp stores 32 adjacent words of each of its four output rows; the 9x9 window of an interior block is read straight from the plane as aligned 32-bit
+// words through the read-only path and funnel-shifted into place, the prediction is formed by the packed formulation of hlb_fast.cuh).
 // blockIdx.y = picture of a batch: the planes of consecutive pictures lie `stride` bytes apart, their motion fields nmb entries apart
-__global__ void __launch_bounds__(128) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
+__global__ void __launch_bounds__(256) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
                                                      const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred, size_t stride)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int mb = t >> 4;
-    if (mb >= nmb) return;
+    const int bw = W >> 2, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bw * (H >> 2)) return;
     ref += blockIdx.y * stride; pred += blockIdx.y * stride; motion += (size_t)blockIdx.y * nmb;
-    const int k = t & 15, bx = (k & 3) * 4, by = (k >> 2) * 4;
-    const int mbx = mb % mbw, mby = mb / mbw;
-    const hlb200_mb_motion_t* m = motion + mb;
+    const int gy4 = t / bw, gx = (t - gy4 * bw) << 2, gy = gy4 << 2;
+    const int mbx = gx >> 4, mby = gy >> 4, bx = gx & 15, by = gy & 15;
+    const hlb200_mb_motion_t* m = motion + mby * mbw + mbx;
     const PartGeom g = part_of(m->part_mode, m->sub_mode, bx, by);
     const int mvx = m->mv[g.part][g.sub][0], mvy = m->mv[g.part][g.sub][1];
     // origin clip applies to the PARTITION origin
     const int X = clip3(-17, W + 17, mbx * 16 + g.ox + (mvx >> 2)) + (bx - g.ox);
     const int Y = clip3(-17, H + 17, mby * 16 + g.oy + (mvy >> 2)) + (by - g.oy);
-    uint8_t win[81];
-    load_win9(ref, W, H, X, Y, win);
-    uint8_t out[16];
-    interp_luma_4x4(win + 2 * 9 + 2, 9, mvx & 3, mvy & 3, out);
-    uint8_t* o = pred + (mby * 16 + by) * W + mbx * 16 + bx;
+    Rows4 o;
+    if (X >= 2 && Y >= 2 && X + 7 <= W && Y + 7 <= H) o = fast_pred_luma_t<LdReadOnly>(reinterpret_cast<const uint32_t*>(ref), W >> 2, X, Y, mvx & 3, mvy & 3);
+    else {
+        // the window touches the picture edge: staged with the reference's per-sample clamp (interpol.c:108-131), 12 bytes per row
+        uint32_t win[9 * 3];
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r) {
+            const uint8_t* row = ref + clip3(0, H - 1, Y - 2 + r) * W;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        *reinterpret_cast<uint32_t*>(o + r * W) = out[r * 4] | (out[r * 4 + 1] << 8) | (out[r * 4 + 2] << 16) | ((uint32_t)out[r * 4 + 3] << 24);
+            for (int q = 0; q < 3; ++q) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v |= (uint32_t)__ldg(row + clip3(0, W - 1, X - 2 + q * 4 + c)) << (8 * c);
+                win[r * 3 + q] = v;
+            }
+        }
+        o = fast_pred_luma_t<LdPlain>(win, 3, 2, 2, mvx & 3, mvy & 3);
+    }
+    uint8_t* dst = pred + (size_t)gy * W + gx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t*>(dst + r * W) = o.r[r];
 }
 
-// ---------------- chroma interpolation: one thread per two horizontally adjacent chroma samples of both planes ---------
-// (a 2x2 chroma block is the smallest area with one motion vector, so the pair shares it: six reference samples per plane instead of eight,
-// 16-bit stores)
+// ---------------- chroma interpolation: one thread per four horizontally adjacent samples of one plane, PICTURE raster order ---------------------
+// (8 luma samples wide: one motion vector unless the macroblock is split into 4-wide sub-partitions, then two).  Interior: two rows of the reference fetched
+// as aligned words + funnel shift, the 1/8-pel bilinear sample as two byte dot products (weights (8-xf)(8-yf), xf(8-yf) | (8-xf)yf, xf yf).
+__device__ __forceinline__ uint32_t chroma_pair(const uint8_t* __restrict__ rp, int Wc, int Hc, int x0, int y0, int xf, int yf, int n)
+{
+    // n (2 or 4) samples starting at (x0, y0); returns them packed from the low byte
+    const uint32_t wa = (uint32_t)((8 - xf) * (8 - yf)) | ((uint32_t)(xf * (8 - yf)) << 8), wc = (uint32_t)((8 - xf) * yf) | ((uint32_t)(xf * yf) << 8);
+    uint32_t a0, a1, c0, c1;
+    if (x0 >= 0 && y0 >= 0 && x0 + n < Wc && y0 + 1 < Hc && (x0 >> 2) + 1 < (Wc >> 2)) {
+        const uint32_t* ra = reinterpret_cast<const uint32_t*>(rp + (size_t)y0 * Wc) + (x0 >> 2);
+        const uint32_t* rc = reinterpret_cast<const uint32_t*>(rp + (size_t)(y0 + 1) * Wc) + (x0 >> 2);
+        const uint32_t sh = (uint32_t)(x0 & 3) * 8, ua = __ldg(ra), va = __ldg(ra + 1), uc = __ldg(rc), vc = __ldg(rc + 1);
+        a0 = p_shf_r(ua, va, sh); a1 = va >> sh; c0 = p_shf_r(uc, vc, sh); c1 = vc >> sh;   // samples 0..3 and sample 4 (low byte)
+    } else {
+        a0 = a1 = c0 = c1 = 0;
+        const uint8_t* ra = rp + (size_t)clip3(0, Hc - 1, y0) * Wc;
+        const uint8_t* rc = rp + (size_t)clip3(0, Hc - 1, y0 + 1) * Wc;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int x = clip3(0, Wc - 1, x0 + i);
+            if (i < 4) { a0 |= (uint32_t)__ldg(ra + x) << (8 * i); c0 |= (uint32_t)__ldg(rc + x) << (8 * i); }
+            else { a1 = __ldg(ra + x); c1 = __ldg(rc + x); }
+        }
+    }
+    int v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = p_dp4a_us(p_shf_r(c0, c1, 8 * i), wc, p_dp4a_us(p_shf_r(a0, a1, 8 * i), wa, 32)) >> 6;
+    return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+}
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
                                                        const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride)
 {
+    const int Wc = W >> 1, Hc = H >> 1, sw = Wc >> 2, per_plane = sw * Hc;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int mb = t >> 5;
-    if (mb >= nmb) return;
-    ref_u += blockIdx.y * stride; ref_v += blockIdx.y * stride; pred_u += blockIdx.y * stride; pred_v += blockIdx.y * stride; motion += (size_t)blockIdx.y * nmb;
-    const int px = (t & 3) * 2, py = (t >> 2) & 7;
-    const int mbx = mb % mbw, mby = mb / mbw;
-    const int Wc = W >> 1, Hc = H >> 1;
-    const hlb200_mb_motion_t* m = motion + mb;
-    const PartGeom g = part_of(m->part_mode, m->sub_mode, px * 2, py * 2);
-    const int mvx = m->mv[g.part][g.sub][0], mvy = m->mv[g.part][g.sub][1];
-    const int x0 = mbx * 8 + px + (mvx >> 3), y0 = mby * 8 + py + (mvy >> 3), xf = mvx & 7, yf = mvy & 7;
-    const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), xc = clip3(0, Wc - 1, x0 + 2), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
-    const int o = (mby * 8 + py) * Wc + mbx * 8 + px;
-    {
-        const int a0 = __ldg(ref_u + ya + xa), a1 = __ldg(ref_u + ya + xb), a2 = __ldg(ref_u + ya + xc), c0 = __ldg(ref_u + yc + xa), c1 = __ldg(ref_u + yc + xb), c2 = __ldg(ref_u + yc + xc);
-        *reinterpret_cast<uint16_t*>(pred_u + o) = (uint16_t)(interp_chroma_px(a0, a1, c0, c1, xf, yf) | (interp_chroma_px(a1, a2, c1, c2, xf, yf) << 8));
+    if (t >= 2 * per_plane) return;
+    const int plane = t >= per_plane, s = t - plane * per_plane, cy = s / sw, cx = (s - cy * sw) << 2;
+    const uint8_t* rp = (plane ? ref_v : ref_u) + blockIdx.y * stride;
+    uint8_t* dst = (plane ? pred_v : pred_u) + blockIdx.y * stride + (size_t)cy * Wc + cx;
+    motion += (size_t)blockIdx.y * nmb;
+    const int mbx = cx >> 3, mby = cy >> 3, lx = (cx & 7) * 2, ly = (cy & 7) * 2;   // luma position inside the macroblock
+    const hlb200_mb_motion_t* m = motion + mby * mbw + mbx;
+    const PartGeom g0 = part_of(m->part_mode, m->sub_mode, lx, ly);
+    const int mvx = m->mv[g0.part][g0.sub][0], mvy = m->mv[g0.part][g0.sub][1];
+    uint32_t out;
+    if (g0.w >= 8) out = chroma_pair(rp, Wc, Hc, cx + (mvx >> 3), cy + (mvy >> 3), mvx & 7, mvy & 7, 4);
+    else {   // 4-wide sub-partitions: the right half has its own vector
+        const PartGeom g1 = part_of(m->part_mode, m->sub_mode, lx + 4, ly);
+        const int nvx = m->mv[g1.part][g1.sub][0], nvy = m->mv[g1.part][g1.sub][1];
+        out = (chroma_pair(rp, Wc, Hc, cx + (mvx >> 3), cy + (mvy >> 3), mvx & 7, mvy & 7, 2) & 0xffffu) |
+              (chroma_pair(rp, Wc, Hc, cx + 2 + (nvx >> 3), cy + (nvy >> 3), nvx & 7, nvy & 7, 2) << 16);
     }
-    {
-        const int a0 = __ldg(ref_v + ya + xa), a1 = __ldg(ref_v + ya + xb), a2 = __ldg(ref_v + ya + xc), c0 = __ldg(ref_v + yc + xa), c1 = __ldg(ref_v + yc + xb), c2 = __ldg(ref_v + yc + xc);
-        *reinterpret_cast<uint16_t*>(pred_v + o) = (uint16_t)(interp_chroma_px(a0, a1, c0, c1, xf, yf) | (interp_chroma_px(a1, a2, c1, c2, xf, yf) << 8));
-    }
+    *reinterpret_cast<uint32_t*>(dst) = out;
 }
 
 // ---------------- residual coding + reconstruction: one warp per macroblock ----------------------------------------
-// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks 0..3; lanes 20..23: Cr blocks 0..3 (raster); lanes 24..31 idle.
+// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks 0..3; lanes 20..23: Cr blocks 0..3 (raster); lanes 24..31 idle.  A lane keeps its block as four packed
+// rows: residual transform = byte dot products (hlb_fast.cuh), reconstruction = saturating pack.
 __device__ __forceinline__ void load4x4(const uint8_t* __restrict__ p, int pitch, uint8_t v[16])
 {
 #pragma unroll
@@ -99,18 +139,22 @@ __device__ __forceinline__ void load4x4(const uint8_t* __restrict__ p, int pitch
         v[r * 4] = w & 255; v[r * 4 + 1] = (w >> 8) & 255; v[r * 4 + 2] = (w >> 16) & 255; v[r * 4 + 3] = w >> 24;
     }
 }
-__device__ __forceinline__ void store4x4(uint8_t* __restrict__ p, int pitch, const int v[16])
+__device__ __forceinline__ void quantk_device(QuantK& k, int qp, bool intra)   // quantk_make from the device tables
 {
+    const int r = qp % 6, q6 = qp / 6;
+    k.qbits = 15 + q6; k.f_pos = (1 << k.qbits) / (intra ? 3 : 6); k.f_neg = (1 << k.qbits) - 1 - k.f_pos;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        *reinterpret_cast<uint32_t*>(p + r * pitch) = (uint32_t)v[r * 4] | ((uint32_t)v[r * 4 + 1] << 8) | ((uint32_t)v[r * 4 + 2] << 16) | ((uint32_t)v[r * 4 + 3] << 24);
+    for (int c = 0; c < 3; ++c) { k.mf[c] = kQuantMF[r][c]; k.dq_mul[c] = qp >= 24 ? (16 * kNormAdjust[r][c]) << (q6 - 4) : 16 * kNormAdjust[r][c]; }
+    k.dq_shift = qp >= 24 ? 0 : 4 - q6; k.dq_round = qp >= 24 ? 0 : 1 << (3 - q6); k.zero_sad = -1;
 }
-
 __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
                                                   const uint8_t* __restrict__ pred_y, const uint8_t* __restrict__ pred_u, const uint8_t* __restrict__ pred_v,
                                                   int W, int H, int mbw, int nmb, int qp, int qpc, hlb200_mb_coeffs_t* __restrict__ coeffs,
                                                   uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride)
 {
+    __shared__ QuantK s_qk[2];   // [0] luma (inter rounding offset), [1] chroma AC (always the intra offset, rdo.c:2588)
+    if (threadIdx.x < 2) quantk_device(s_qk[threadIdx.x], threadIdx.x ? qpc : qp, threadIdx.x != 0);
+    __syncthreads();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nmb) return;  // warp-uniform
     {
@@ -128,36 +172,34 @@ __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ sr
     const uint8_t* s = plane == 0 ? src_y : (plane == 1 ? src_u : src_v);
     const uint8_t* p = plane == 0 ? pred_y : (plane == 1 ? pred_u : pred_v);
     uint8_t* r = plane == 0 ? rec_y : (plane == 1 ? rec_u : rec_v);
+    const QuantK& qk = s_qk[is_luma ? 0 : 1];
 
-    uint8_t sv[16], pv[16];
+    Rows4 sv, pv;
     int m[16], lv[16];
     bool res_nz = false;
     if (is_luma || is_chroma) {
-        load4x4(s + off, pitch, sv);
-        load4x4(p + off, pitch, pv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; res_nz |= (m[i] != 0); }
+        for (int y = 0; y < 4; ++y) {
+            sv.r[y] = __ldg(reinterpret_cast<const uint32_t*>(s + off + y * pitch));
+            pv.r[y] = __ldg(reinterpret_cast<const uint32_t*>(p + off + y * pitch));
+            res_nz |= sv.r[y] != pv.r[y];
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { m[i] = 0; pv[i] = 0; }
+        for (int y = 0; y < 4; ++y) sv.r[y] = pv.r[y] = 0;
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) lv[i] = 0;
+    for (int i = 0; i < 16; ++i) { lv[i] = 0; m[i] = 0; }
 
     int dc_coef = 0;     // chroma: pre-quant W00 (rdo.c:2591)
     bool coded = false;  // luma: CBP4x4 bit; chroma: AC bit
     if (res_nz) {
-        fwd_transform4x4(m);
+        fast_fwd_transform(sv, pv, m);
         dc_coef = m[0];
-        quant4x4_ac(m, is_luma ? qp : qpc, /*intra f*/ !is_luma);  // chroma AC always uses the intra offset (rdo.c:2588)
+        fast_quant(m, qk);
         zigzag4x4(m, lv);
-        if (is_luma) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) coded |= (lv[i] != 0);
-        } else {
-#pragma unroll
-            for (int i = 1; i < 16; ++i) coded |= (lv[i] != 0);
-        }
+        const uint32_t mask = level_mask16(lv);
+        coded = (is_luma ? mask : (mask & ~1u)) != 0;
     }
     if (!is_chroma) dc_coef = 0;
 
@@ -201,7 +243,6 @@ __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ sr
     }
 
     // ---- reconstruction ----
-    int rec[16];
     bool use_res;
     int c[16];
     if (is_luma) {
@@ -216,16 +257,15 @@ __global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ sr
         for (int i = 1; i < 16; ++i) l2[i] = lv[i];
         inv_zigzag4x4(l2, c);
     }
+    Rows4 rec = pv;
     if (use_res) {
-        dequant4x4(c, is_luma ? qp : qpc, /*keep_dc*/ !is_luma);
-        inv_transform4x4(c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rec[i] = clip255((int)pv[i] + c[i]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rec[i] = pv[i];
+        fast_dequant_inverse(c, qk, /*keep_dc*/ !is_luma);
+        rec = fast_recon_clip(pv, c);
     }
-    if (is_luma || is_chroma) store4x4(r + off, pitch, rec);
+    if (is_luma || is_chroma) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t*>(r + off + y * pitch) = rec.r[y];
+    }
 
     // ---- outputs ----
     if (is_luma) {

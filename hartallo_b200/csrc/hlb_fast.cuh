@@ -90,17 +90,20 @@ HLB_HD uint32_t pack4_sat(int v0, int v1, int v2, int v3) { return p_pack_sat_u8
 // ------------------------------------------------------------------------------------------------------------------
 // window rows out of a byte tile addressed as 32-bit words (`t` 4-byte aligned, row pitch `pw` words)
 // ------------------------------------------------------------------------------------------------------------------
+// how a word of the tile is read: plain (shared memory tile, local staging, host) or through the read-only path (a picture plane in global memory)
+struct LdPlain { static HLB_HD uint32_t ld(const uint32_t* p) { return *p; } };
+struct LdReadOnly { static HLB_HD uint32_t ld(const uint32_t* p) { return HLB_LDG(p); } };
 // four samples starting at byte column c of row y
-HLB_HD uint32_t tile_row4(const uint32_t* t, int pw, int y, int c)
+template <class LD = LdPlain> HLB_HD uint32_t tile_row4(const uint32_t* t, int pw, int y, int c)
 {
     const uint32_t* p = t + y * pw + (c >> 2);
-    return p_shf_r(p[0], p[1], (uint32_t)(c & 3) * 8);
+    return p_shf_r(LD::ld(p), LD::ld(p + 1), (uint32_t)(c & 3) * 8);
 }
 // nine samples starting at byte column c of row y: R0 = samples 0..3, R1 = 4..7, R2 = sample 8 in its low byte (higher bytes unspecified)
-HLB_HD void tile_row9(const uint32_t* t, int pw, int y, int c, uint32_t& R0, uint32_t& R1, uint32_t& R2)
+template <class LD = LdPlain> HLB_HD void tile_row9(const uint32_t* t, int pw, int y, int c, uint32_t& R0, uint32_t& R1, uint32_t& R2)
 {
     const uint32_t* p = t + y * pw + (c >> 2);
-    const uint32_t sh = (uint32_t)(c & 3) * 8, w0 = p[0], w1 = p[1], w2 = p[2];
+    const uint32_t sh = (uint32_t)(c & 3) * 8, w0 = LD::ld(p), w1 = LD::ld(p + 1), w2 = LD::ld(p + 2);
     R0 = p_shf_r(w0, w1, sh); R1 = p_shf_r(w1, w2, sh); R2 = w2 >> sh;
 }
 
@@ -145,18 +148,17 @@ HLB_HD uint32_t exp_hi(uint32_t r) { return p_prmt(r, 0, 0x4342); }   // samples
 #endif
 #define HLB_FASTPRED_SRC(t) ((void)0)
 #endif
-HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
+template <class LD> HLB_HD Rows4 fast_pred_luma_t(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
 {
-    HLB_FASTPRED_SRC(t);
     Rows4 o;
     if ((xf | yf) == 0) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) o.r[r] = tile_row4(t, pw, ty + r, tx);
+        for (int r = 0; r < 4; ++r) o.r[r] = tile_row4<LD>(t, pw, ty + r, tx);
     } else if (yf == 0) {   // a b c
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             uint32_t R0, R1, R2;
-            tile_row9(t, pw, ty + r, tx - 2, R0, R1, R2);
+            tile_row9<LD>(t, pw, ty + r, tx - 2, R0, R1, R2);
             const uint32_t b = half_h_row(R0, R1, R2);
             o.r[r] = xf == 2 ? b : p_avg4(p_shf_r(R0, R1, xf == 1 ? 16 : 24), b);
         }
@@ -164,7 +166,7 @@ HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, 
         uint32_t lo[9], hi[9], g[5];
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
-            const uint32_t v = tile_row4(t, pw, ty - 2 + r, tx);
+            const uint32_t v = tile_row4<LD>(t, pw, ty - 2 + r, tx);
             lo[r] = exp_lo(v); hi[r] = exp_hi(v);
             if (r >= 2 && r < 7) g[r - 2] = v;
         }
@@ -178,13 +180,13 @@ HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, 
         uint32_t lo[9], hi[9];
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
-            const uint32_t v = tile_row4(t, pw, ty - 2 + r, cx);
+            const uint32_t v = tile_row4<LD>(t, pw, ty - 2 + r, cx);
             lo[r] = exp_lo(v); hi[r] = exp_hi(v);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             uint32_t R0, R1, R2;
-            tile_row9(t, pw, ty + r + ry, tx - 2, R0, R1, R2);
+            tile_row9<LD>(t, pw, ty + r + ry, tx - 2, R0, R1, R2);
             const uint32_t b = half_h_row(R0, R1, R2);
             const uint32_t h = p_prmt(vtap_pair(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5]), vtap_pair(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5]), 0x6420);
             o.r[r] = p_avg4(b, h);
@@ -200,7 +202,7 @@ HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, 
 #pragma unroll 1
         for (int r = 0; r < 9; ++r) {
             uint32_t R0, R1, R2;
-            tile_row9(t, pw, ty - 2 + r, tx - 2, R0, R1, R2);
+            tile_row9<LD>(t, pw, ty - 2 + r, tx - 2, R0, R1, R2);
 #pragma unroll
             for (int x = 0; x < 4; ++x) { w0[x] = w1[x]; w1[x] = w2[x]; w2[x] = w3[x]; w3[x] = w4[x]; w4[x] = w5[x]; }
             hrow_taps(R0, R1, R2, 0, w5[0], w5[1], w5[2], w5[3]);
@@ -224,7 +226,7 @@ HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, 
             uint32_t lo[9], hi[9];
 #pragma unroll
             for (int r = 0; r < 9; ++r) {
-                const uint32_t v = tile_row4(t, pw, ty - 2 + r, cx);
+                const uint32_t v = tile_row4<LD>(t, pw, ty - 2 + r, cx);
                 lo[r] = exp_lo(v); hi[r] = exp_hi(v);
             }
 #pragma unroll
@@ -235,6 +237,12 @@ HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, 
         }
     }
     return o;
+}
+// the shared-memory tile of the slice kernel (one out-of-line copy there, see hlb_slice.cu)
+HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
+{
+    HLB_FASTPRED_SRC(t);
+    return fast_pred_luma_t<LdPlain>(t, pw, tx, ty, xf, yf);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -250,13 +258,13 @@ struct QuantK {
     int32_t dq_round;
     int32_t zero_sad;     // a residual block whose SAD is <= this quantises to all-zero levels (see quantk_make); -1 = no shortcut
 };
-inline void quantk_make(QuantK& k, int qp)
+inline void quantk_make(QuantK& k, int qp, bool intra = false)
 {
     static const int MF[6][3] = {{13107, 5243, 8066}, {11916, 4660, 7490}, {10082, 4194, 6554}, {9362, 3647, 5825}, {8192, 3355, 5243}, {7282, 2893, 4559}};
     static const int NA[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
     const int r = qp % 6, q6 = qp / 6;
     k.qbits = 15 + q6;
-    k.f_pos = (1 << k.qbits) / 6;
+    k.f_pos = (1 << k.qbits) / (intra ? 3 : 6);
     k.f_neg = (1 << k.qbits) - 1 - k.f_pos;
     for (int c = 0; c < 3; ++c) {
         k.mf[c] = MF[r][c];
@@ -285,13 +293,9 @@ inline void quantk_make(QuantK& k, int qp)
 #define HLB_NCF1 0x0201FFFEu
 #define HLB_NCF2 0xFF0101FFu
 #define HLB_NCF3 0x01FE02FFu
-HLB_HD uint32_t fast_trial(const Rows4& s, const Rows4& p, const QuantK& q, bool counts_only)
+// forward 4x4 transform of the residual (source - prediction) of packed rows, raster order: rows (S - P) Cf^T as byte dot products, then columns Cf (.)
+HLB_HD void fast_fwd_transform(const Rows4& s, const Rows4& p, int m[16])
 {
-    uint32_t sad0 = p_sad4(s.r[0], p.r[0], 0);
-    sad0 = p_sad4(s.r[1], p.r[1], sad0); sad0 = p_sad4(s.r[2], p.r[2], sad0); sad0 = p_sad4(s.r[3], p.r[3], sad0);
-    if ((int)sad0 <= q.zero_sad) return sad0;   // every level is zero (and so is the block's residual when sad0 == 0)
-    // rows: (S - P) Cf^T as byte dot products; then columns: Cf (.)
-    int m[16];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         m[r * 4 + 0] = p_dp4a_us(s.r[r], HLB_CF0, p_dp4a_us(p.r[r], HLB_NCF0, 0));
@@ -305,15 +309,61 @@ HLB_HD uint32_t fast_trial(const Rows4& s, const Rows4& p, const QuantK& q, bool
         const int s0 = a + d, s1 = b + c, d0 = a - d, d1 = b - c;
         m[j] = s0 + s1; m[4 + j] = 2 * d0 + d1; m[8 + j] = s0 - s1; m[12 + j] = d0 - 2 * d1;
     }
-    // quantisation: sign(w) * ((|w| MF + f) >> qbits) == (w MF + (w < 0 ? f_neg : f_pos)) >> qbits (arithmetic)
+}
+// quantisation in place: sign(w) * ((|w| MF + f) >> qbits) == (w MF + (w < 0 ? f_neg : f_pos)) >> qbits (arithmetic shift)
+HLB_HD void fast_quant(int m[16], const QuantK& q)
+{
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int c = pos_class(i, j);
-            const int t = m[i * 4 + j] * q.mf[c];
+            const int t = m[i * 4 + j] * q.mf[pos_class(i, j)];
             m[i * 4 + j] = (t + (t < 0 ? q.f_neg : q.f_pos)) >> q.qbits;
         }
+}
+// de-quantisation (flat scaling lists; keep_dc: coefficient (0,0) is already de-quantised) + inverse transform, in place; `round` = 32 for the final (x + 32) >> 6
+HLB_HD void fast_dequant_inverse(int m[16], const QuantK& q, bool keep_dc)
+{
+    const int dc = m[0];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = m[i * 4 + j] * q.dq_mul[pos_class(i, j)];
+            m[i * 4 + j] = (v + q.dq_round) >> q.dq_shift;
+        }
+    if (keep_dc) m[0] = dc;
+    m[0] += 32;   // reaches every output sample once with weight 1: the rounding of the final >> 6
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d0 = m[4 * i], d1 = m[4 * i + 1], d2 = m[4 * i + 2], d3 = m[4 * i + 3];
+        const int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+        m[4 * i] = e0 + e3; m[4 * i + 1] = e1 + e2; m[4 * i + 2] = e1 - e2; m[4 * i + 3] = e0 - e3;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int f0 = m[j], f1 = m[4 + j], f2 = m[8 + j], f3 = m[12 + j];
+        const int g0 = f0 + f2, g1 = f0 - f2, g2 = (f1 >> 1) - f3, g3 = f1 + (f3 >> 1);
+        m[j] = (g0 + g3) >> 6; m[4 + j] = (g1 + g2) >> 6; m[8 + j] = (g1 - g2) >> 6; m[12 + j] = (g0 - g3) >> 6;
+    }
+}
+// final reconstruction of packed prediction rows + residual samples: clip255(p + r) (hl_math.h:278), packed
+HLB_HD Rows4 fast_recon_clip(const Rows4& p, const int r[16])
+{
+    Rows4 o;
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+        o.r[y] = pack4_sat((int)(p.r[y] & 255u) + r[y * 4], (int)((p.r[y] >> 8) & 255u) + r[y * 4 + 1], (int)((p.r[y] >> 16) & 255u) + r[y * 4 + 2], (int)(p.r[y] >> 24) + r[y * 4 + 3]);
+    return o;
+}
+HLB_HD uint32_t fast_trial(const Rows4& s, const Rows4& p, const QuantK& q, bool counts_only)
+{
+    uint32_t sad0 = p_sad4(s.r[0], p.r[0], 0);
+    sad0 = p_sad4(s.r[1], p.r[1], sad0); sad0 = p_sad4(s.r[2], p.r[2], sad0); sad0 = p_sad4(s.r[3], p.r[3], sad0);
+    if ((int)sad0 <= q.zero_sad) return sad0;   // every level is zero (and so is the block's residual when sad0 == 0)
+    int m[16];
+    fast_fwd_transform(s, p, m);
+    fast_quant(m, q);
     int lv[16];
     zigzag4x4(m, lv);
     const uint32_t mask = level_mask16(lv);
