@@ -156,7 +156,7 @@ int hlb200_stream_destroy(hlb200_ctx_t* c)
     cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_svc_state); cudaFree(c->d_tmaps); cudaFree(c->d_sched); cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_jobs) cudaFreeHost(c->h_jobs);
-    cudaFree(c->d_bits); cudaFree(c->d_bits_jobs);
+    cudaFree(c->d_bits); cudaFree(c->d_bits_jobs); cudaFree(c->d_dbk_bs);
     if (c->h_bits_jobs) cudaFreeHost(c->h_bits_jobs);
     if (c->ev_bits) cudaEventDestroy(c->ev_bits);
     if (c->ev_jobs) cudaEventDestroy(c->ev_jobs);

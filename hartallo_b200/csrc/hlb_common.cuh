@@ -88,5 +88,6 @@ struct hlb200_ctx {
     cudaEvent_t ev_jobs, ev_done;               // owner: job-array upload / launch completion; other contexts: ev_done orders their stream before the launch
     void* d_bits; int bits_cap_words;           // device CAVLC output of the last picture: words | per-macroblock lengths / offsets | header (hlb_slice.cu)
     void* d_bits_jobs; void* h_bits_jobs; int bits_jobs_cap; cudaEvent_t ev_bits;   // owner of a serialisation batch: job descriptors
+    void* d_dbk_bs;                             // deblocking: 32 boundary-strength bytes per macroblock (allocated on first use, hlb_deblock.cuh)
     int frame_count;
 };

@@ -63,6 +63,7 @@ struct FrameCtx {
     int W, H, mbw, mbh;
     int qp, qpc;
     int is_p, me_range, num_refs;
+    int early_term;                      // me_early_term_flag: homogeneous-block detection narrows the partition modes searched (rdo.c:889-935)
     double lambda;                       // lambda_mode = 0.852 * (1 << ((QP-12)/3)), slice.c:1766
     QuantK qk;                           // quantiser constants of the luma trial encodes (hlb_fast.cuh), derived from qp by frame_ctx_derive()
     const uint8_t* src[3];
@@ -1381,6 +1382,38 @@ HLB_HD int guess_cbp_chroma(const MbWork& w)
     return 0;
 }
 
+// ---- JVT-O079 2.1.3.4 homogeneous block detection (rdo.c:889-935): which of the 7 search modes stay enabled for this macroblock ----
+// The edge map of hl_math_homogeneousity8x8_u8 (hl_math.c:470-486): sum over an 8x8 block of |dx| + |dy| with the Sobel pair on the SOURCE picture.  The
+// reference starts the 16x16 area one sample inside the picture when the macroblock lies on the left / top edge and one sample to the left / above when it lies
+// on the right / bottom edge (rdo.c:894-895), so the 3x3 support never leaves the plane.  Bit m of the result = mode m of mode_rect() (reference Mode m + 1).
+template <class X>
+HLB_FN int me_mode_mask(X& x, const MbWork& w, const FrameCtx& f)
+{
+    const int xl = w.mbx * 16, yl = w.mby * 16;
+    const int x0 = xl == 0 ? 1 : (xl == f.W - 16 ? f.W - 17 : xl), y0 = yl == 0 ? 1 : (yl == f.H - 16 ? f.H - 17 : yl);
+    int hsum[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int p = x.lane(); p < 256; p += x.nlanes()) {
+        const int b = p >> 6, j = (p >> 3) & 7, i = p & 7;
+        const uint8_t* c = f.src[0] + (size_t)(y0 + (b >> 1) * 8 + j) * f.W + (x0 + (b & 1) * 8 + i);
+        const uint8_t *up = c - f.W, *dn = c + f.W;
+        const int ul = HLB_LDG(up - 1), um = HLB_LDG(up), ur = HLB_LDG(up + 1), ml = HLB_LDG(c - 1), mr = HLB_LDG(c + 1), dl = HLB_LDG(dn - 1), dm = HLB_LDG(dn), dr = HLB_LDG(dn + 1);
+        const int dx = dl + 2 * dm + dr - ul - 2 * um - ur, dy = ur + 2 * mr + dr - ul - 2 * ml - dl;
+        const int v = iabs(dx) + iabs(dy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hsum[k] += b == k ? v : 0;
+    }
+    int h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = x.reduce_add(hsum[k]);
+    HLB_DBG("  homogeneity %d %d %d %d\n", h[0], h[1], h[2], h[3]);
+    const int TH16 = 20000, TH8 = 5000, TH84 = 7500;   // HL_CODEC_264_RDO_HOMOGENEOUSITY_TH16X16 / TH8X8 / TH8X4 (hl_codec_264_defs.h:61-63)
+    if (h[0] < TH8 && h[1] < TH8 && h[2] < TH8 && h[3] < TH8) return 0x01;
+    if (h[0] + h[1] + h[2] + h[3] < TH16) return (h[0] < TH8 && h[1] < TH8) ? 0x03 : 0x05;
+    if (h[0] < TH84 && h[1] < TH84 && h[2] < TH84 && h[3] < TH84) return 0x3f;
+    return 0x7f;
+}
+
 template <class X>
 HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
 {
@@ -1388,6 +1421,8 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
     double best_cost = DBL_MAX;
     int best_dist = 0, best_mode = -1, best_sctr = 9, best_ref = 0, found = 0, b_pskip = 0, probably_pskip = 0, pskip_early = 0;
     int16_t best_mv[4][4][2], best_mvp[4][4][2];
+    // the mode flags are reset and recomputed per reference picture (rdo.c:875, :889) from the source alone: once is the same
+    const int mode_mask = f.early_term ? me_mode_mask(x, w, f) : 0x7f;
 #pragma unroll 1
     for (int u = 0; u < f.num_refs; ++u) {
         if (!f.ref[u][0]) continue;
@@ -1400,6 +1435,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
             pskip_early = 0;
 #pragma unroll 1
             for (int mode = m0; mode <= m1; ++mode) {
+                if (!((mode_mask >> mode) & 1)) continue;   // rdo.c:884
                 HLB_LAP(w, 8);
                 if (me_search_begin(x, w, f, mode)) {
                     // The PSkip probe passed (16x16, reference 0): the macroblock is a P_Skip iff its chroma also quantises to nothing (rdo.c:1125-1139, :2140).  The

@@ -24,11 +24,13 @@
 #include "hlb_common.cuh"
 #include "hlb_mbcore.cuh"
 #include "hlb_bits.cuh"
+#include "hlb_deblock.cuh"
 
 namespace hlb {
 
 struct SliceJob {
     FrameCtx f;
+    DbkJob d;            // loop filter over the finished picture (d.enabled; hlb_deblock.cuh)
     int nmb;
     int base;            // first item index of this job in the scheduler arrays
     int prev_frame_sctr; // Single_ctr chain value entering the picture
@@ -123,6 +125,51 @@ struct GpuExec {
         return job->prev_frame_sctr;
     }
 };
+
+// ---- loop filter of the pictures of a launch (hlb_deblock.cuh) -------------------------------------------------------------------------------------
+// boundary strengths: they depend on the decision records only, one thread per value.  blockIdx.y = picture
+__global__ void __launch_bounds__(256) k_dbk_bs(const SliceJob* __restrict__ jobs)
+{
+    const DbkJob& j = jobs[blockIdx.y].d;
+    if (!j.enabled) return;
+    const int t = blockIdx.x * 256 + threadIdx.x, mb = t >> 5;
+    if (mb >= j.mbw * j.mbh) return;
+    j.bs[t] = (uint8_t)dbk_bs_mb(j, mb % j.mbw, mb / j.mbw, t & 31);
+}
+// One CTA per picture, one warp per macroblock row in flight: row y filters macroblock x once row y-1 has finished macroblock x+1 (the raster order of 8.7
+// only orders a macroblock after its left, top and top-right neighbours, whose samples it reads or rewrites).  Progress counters live in shared memory, every
+// warp of the picture is resident in the same CTA, so the waits cannot deadlock; the samples travel through the L1 of the one SM all of them run on.
+#define HLB_DBK_WARPS 16
+__global__ void __launch_bounds__(HLB_DBK_WARPS * 32) k_dbk(const SliceJob* __restrict__ jobs)
+{
+    extern __shared__ int s_prog[];   // macroblocks finished per row
+    __shared__ DbkJob j;
+    __shared__ uint8_t s_bs[HLB_DBK_WARPS][32];
+    if (!jobs[blockIdx.x].d.enabled) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (int)(sizeof(DbkJob) / 4); i += blockDim.x) ((uint32_t*)&j)[i] = ((const uint32_t*)&jobs[blockIdx.x].d)[i];
+    for (int i = threadIdx.x; i < jobs[blockIdx.x].d.mbh; i += blockDim.x) s_prog[i] = 0;
+    __syncthreads();
+    volatile int* prog = s_prog;
+    for (int y = warp; y < j.mbh; y += HLB_DBK_WARPS) {
+        for (int x = 0; x < j.mbw; ++x) {
+            if (y) {
+                const int need = x + 2 < j.mbw ? x + 2 : j.mbw;
+                while (prog[y - 1] < need) __nanosleep(64);
+                __threadfence_block();
+            }
+            s_bs[warp][lane] = j.bs[((size_t)y * j.mbw + x) * 32 + lane];
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                dbk_edge(j, x, y, k >> 2, k & 3, lane, s_bs[warp]);
+                __syncwarp();
+            }
+            __threadfence_block();
+            if (lane == 0) prog[y] = x + 1;
+        }
+    }
+}
 
 __global__ void k_slice_init(SliceJob* jobs, int njobs, int* sched_buf, int total)
 {
@@ -408,6 +455,9 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     f.is_p = p->slice_type == 1;
     f.me_range = p->me_range < 1 ? 1 : (p->me_range > 64 ? 64 : p->me_range);   // rdo.c:847
     f.num_refs = f.is_p ? p->num_refs : 0;
+    f.early_term = p->me_early_term_flag != 0;
+    // the reference's edge map reads one sample around a 16x16 area shifted INTO the picture (rdo.c:894-895): with a 16-sample dimension it leaves the plane
+    if (f.early_term && f.is_p && (c->width < 32 || c->height < 32)) { snprintf(g_err, sizeof(g_err), "me_early_term_flag needs a picture of at least 32x32 (rdo.c:894)"); return HLB200_ERR_NOT_IMPLEMENTED; }
     if (f.is_p && (f.num_refs < 1 || f.num_refs > c->max_refs || f.num_refs > HLB_ACTIVE_REFS)) return HLB200_ERR_INVALID_PARAMETER;
     f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));                       // slice.c:1766 (integer division in the exponent)
     frame_ctx_derive(f);
@@ -422,6 +472,14 @@ static int build_job(hlb200_ctx* c, const hlb200_slice_params_t* p, SliceJob* j,
     f.rec = c->d_records;
     j->nmb = c->nmb; j->base = base; j->prev_frame_sctr = 0;
     j->chain = (int*)((char*)c->d_mbstate + state_array_bytes(c->nmb));
+    if (p->deblock_flag) {
+        if (!c->d_dbk_bs) HLB_CUDA(cudaMalloc(&c->d_dbk_bs, (size_t)c->nmb * 32));
+        DbkJob& d = j->d;
+        for (int k = 0; k < 3; ++k) d.plane[k] = f.cur[k];
+        d.rec = c->d_records; d.bs = (uint8_t*)c->d_dbk_bs;
+        d.W = f.W; d.H = f.H; d.mbw = f.mbw; d.mbh = f.mbh; d.enabled = 1;
+        dbk_job_thresholds(d, f.qp, f.qpc);
+    }
     return HLB200_OK;
 }
 
@@ -613,6 +671,16 @@ int hlb200_slice_encode_batch_async(hlb200_ctx_t** ctxs, const hlb200_slice_para
     if (variant) k_slice_encode_warp<<<grid, 32, 0, st>>>(dj, n, sched);
     else k_slice_encode<<<grid, HLB_CTA_THREADS, 0, st>>>(dj, n, sched);
     HLB_CUDA(cudaGetLastError());
+    {   // loop filter of the pictures that ask for it, before anything can read them as references
+        int any = 0, maxnmb = 0, maxmbh = 0;
+        for (int i = 0; i < n; ++i)
+            if (hj[i].d.enabled) { any = 1; maxnmb = hj[i].nmb > maxnmb ? hj[i].nmb : maxnmb; maxmbh = hj[i].d.mbh > maxmbh ? hj[i].d.mbh : maxmbh; }
+        if (any) {
+            k_dbk_bs<<<dim3((maxnmb * 32 + 255) / 256, n), 256, 0, st>>>(dj);
+            k_dbk<<<n, HLB_DBK_WARPS * 32, sizeof(int) * (size_t)maxmbh, st>>>(dj);
+            HLB_CUDA(cudaGetLastError());
+        }
+    }
     HLB_CUDA(cudaEventRecord(c0->ev_done, st));
     { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < HLB_MAX_DEVICES && g_batch_done[dev]) HLB_CUDA(cudaEventRecord(g_batch_done[dev], st)); }
     c0->abort_state = -1;

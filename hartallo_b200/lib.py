@@ -33,7 +33,7 @@ MB_RECORD = np.dtype([
 
 class SliceParams(C.Structure):
     _fields_ = [("slice_type", C.c_int32), ("qp", C.c_int32), ("me_range", C.c_int32), ("num_refs", C.c_int32), ("chroma_qp_index_offset", C.c_int32),
-                ("cur_slot", C.c_int32), ("ref_slot", C.c_int32 * 16)]
+                ("cur_slot", C.c_int32), ("ref_slot", C.c_int32 * 16), ("me_early_term_flag", C.c_int32), ("deblock_flag", C.c_int32)]
 
 
 _lib = None
@@ -213,8 +213,9 @@ class Encoder:
     visits refIdx 0 alone and reconstructs exactly like --refs 1).  `active_refs` is that count; raise it only to exercise the
     kernel's multi-reference loop, for which the reference offers no behaviour to compare with."""
 
-    def __init__(self, width, height, qp=31, me_range=16, refs=1, gop_size=400, device=0, active_refs=1):
+    def __init__(self, width, height, qp=31, me_range=16, refs=1, gop_size=400, device=0, active_refs=1, early_term=0, deblock=0):
         self.st = Stream(width, height, refs, device)
+        self.early_term, self.deblock = early_term, deblock
         self.qp, self.me_range, self.refs, self.gop = qp, me_range, refs, gop_size
         self.active_refs = active_refs
         self.order = []      # slots holding reference pictures, most recent first
@@ -227,6 +228,7 @@ class Encoder:
             self.order = []
         p.slice_type = 0 if idr else 1
         p.qp, p.me_range, p.chroma_qp_index_offset = self.qp, self.me_range, 0
+        p.me_early_term_flag, p.deblock_flag = self.early_term, self.deblock
         p.num_refs = min(len(self.order), self.refs, self.active_refs) if not idr else 0
         p.cur_slot = next(s for s in range(self.refs + 1) if s not in self.order)
         for i, s in enumerate(self.order[:p.num_refs]):

@@ -81,5 +81,30 @@ class G2:
         return np.concatenate([yy.reshape(-1), uu.reshape(-1), vv.reshape(-1)])
 
 
+class G3:
+    """translating picture whose 8x8 blocks carry hashed texture of seven amplitudes over a slow ramp + 2-bit LCG noise (oracle/ref_driver.c:gen_g3): the
+    block amplitudes straddle the homogeneity thresholds of the early-termination mode mask (rdo.c:889-935)"""
+    AMP = np.array([0, 4, 10, 20, 36, 56, 90], np.uint64)
+
+    def __init__(self, width, height, seed=1):
+        self.w, self.h, self.seed, self.state, self.n = width, height, np.uint64(seed), np.uint32(12345), 0
+
+    def next(self):
+        w, h, n = self.w, self.h, self.n
+        seq, self.state = lcg_sequence(self.state, w * h)
+        noise = ((seq >> np.uint32(8)) & np.uint32(3)).astype(np.int64).reshape(h, w)
+        X = (np.arange(w, dtype=np.uint64)[None, :] + np.uint64(2 * n))
+        Y = (np.arange(h, dtype=np.uint64)[:, None] + np.uint64(n))
+        v = (X * np.uint64(374761393) + Y * np.uint64(668265263) + self.seed * np.uint64(2246822519)) & _M
+        v = ((v ^ (v >> np.uint64(13))) * np.uint64(1274126177)) & _M
+        a = self.AMP[(((X >> np.uint64(3)) * np.uint64(73) + (Y >> np.uint64(3)) * np.uint64(151) + self.seed) & _M) % np.uint64(7)]
+        s = 96 + (((X + Y) >> np.uint64(2)) & np.uint64(31)).astype(np.int64) + ((((v >> np.uint64(16)) & np.uint64(127)) * a) >> np.uint64(7)).astype(np.int64) + noise
+        yp = np.minimum(s, 255).astype(np.uint8)
+        i = np.arange(w * h // 2, dtype=np.int32)
+        uv = (128 + ((i + n) & 15)).astype(np.uint8)
+        self.n += 1
+        return np.concatenate([yp.reshape(-1), uv])
+
+
 def make(gen, width, height, seed=1):
-    return G1(width, height) if gen == "g1" else G2(width, height, seed)
+    return G1(width, height) if gen == "g1" else (G3(width, height, seed) if gen == "g3" else G2(width, height, seed))

@@ -148,7 +148,7 @@ static void md5_hex(const uint8_t* p, size_t n, char out[33])
 
 int main(int argc, char** argv)
 {
-    int streams = 8, distinct = 0, warm = 1, same = 0, groups = 2, refs = 1, i, f, g, failed = 0;
+    int streams = 8, distinct = 0, warm = 1, same = 0, groups = 2, refs = 1, deblock = 0, early = 0, i, f, g, failed = 0;
     uint32_t seed = 3;
     const char* out_path = NULL;
     const struct hl_codec_plugin_def_s* plugin = NULL;
@@ -171,6 +171,9 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];               /* bitstream of stream 0 */
         else if (!strcmp(argv[i], "--gen") && i + 1 < argc) { ++i; g_gen = !strcmp(argv[i], "g2") ? 2 : 1; }
+        else if (!strcmp(argv[i], "--deblock") && i + 1 < argc) deblock = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--early-term") && i + 1 < argc) early = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--defaults")) deblock = early = 1;                                /* what hl_codec_create leaves (hl_types.h:67,69) */
         else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
     }
     if (streams < 1 || streams > 1024 || g_frames < 2 || (g_w & 15) || (g_h & 15)) { fprintf(stderr, "bad arguments\n"); return 2; }
@@ -206,11 +209,11 @@ int main(int argc, char** argv)
         /* same knobs as source/test_encoder.c:135-146 */
         s->codec->gop_size = 400; s->codec->me_range = g_me_range; s->codec->qp = g_qp;
         s->codec->fps.num = 1; s->codec->fps.den = 30;
-        s->codec->rc_bitrate = -1; s->codec->deblock_flag = 0; s->codec->threads_count = 1; s->codec->max_ref_frame = refs;
+        s->codec->rc_bitrate = -1; s->codec->deblock_flag = deblock; s->codec->threads_count = 1; s->codec->max_ref_frame = refs;
         s->codec->distortion_mesure_type = HL_VIDEO_DISTORTION_MESURE_TYPE_SAD;
         s->codec->me_type = (HL_VIDEO_ME_TYPE_INTEGER | HL_VIDEO_ME_TYPE_HALF | HL_VIDEO_ME_TYPE_QUATER);
         s->codec->me_part_types = HL_VIDEO_ME_PART_TYPE_ALL; s->codec->me_subpart_types = HL_VIDEO_ME_SUBPART_TYPE_ALL;
-        s->codec->me_early_term_flag = 0;
+        s->codec->me_early_term_flag = early;
         s->content = i % distinct;
         s->stack = mmap(NULL, 1u << 20, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
         if (s->stack == MAP_FAILED) { perror("mmap"); return 1; }

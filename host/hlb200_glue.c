@@ -185,14 +185,17 @@ static void glue_apply(hl_codec_264_mb_t* p_mb, const hlb200_mb_record_t* r, int
 extern HL_ERROR_T __real_hl_codec_264_nal_slice_data_encode(hl_codec_264_t*, hl_codec_264_encode_slice_data_t*);
 
 /* Settings the device path does not reproduce are REFUSED, never silently diverged from and never handed to the reference's CPU path:
- *   deblock_flag != 0        in-loop filter (deblock.c:192, called slice.c:1897) -- library default 1 (hl_types.h:69)
- *   me_early_term_flag != 0  early termination of the search (slice.c:1739-1757, rdo.c:889-1160) -- library default 1 (hl_types.h:67)
- *   rate control             QP changes per picture / macroblock (rc.c)
- * test_encoder.c:139-140 itself runs with rc_bitrate = -1 and deblock_flag = 0. */
+ *   deblock_flag != 0 with SVC layers   the inter-layer deblocking of deblock.c:175-186 and the host-side layer derivation that reads the base picture
+ *                                       (single-layer streams: the device filters the picture, hlb_deblock.cuh; library default 1, hl_types.h:69)
+ *   rate control                        QP changes per picture / macroblock (rc.c)
+ * me_early_term_flag (library default 1, hl_types.h:67) is reproduced on the device (homogeneous-block mode mask, rdo.c:889-935).
+ * test_encoder.c:139-146 itself runs with rc_bitrate = -1, deblock_flag = 0 and me_early_term_flag = 0. */
 static HL_ERROR_T glue_check_settings(const hl_codec_264_t* p_codec)
 {
-    if (p_codec->pc_base->deblock_flag) { HL_DEBUG_ERROR("hlb200: deblock_flag = 1 is not implemented by the device path (set deblock_flag = 0)"); return HL_ERROR_NOT_IMPLEMENTED; }
-    if (p_codec->pc_base->me_early_term_flag) { HL_DEBUG_ERROR("hlb200: me_early_term_flag = 1 is not implemented by the device path (set me_early_term_flag = 0)"); return HL_ERROR_NOT_IMPLEMENTED; }
+    if (p_codec->pc_base->deblock_flag && (p_codec->encoder.b_svc_enabled || getenv("HLB200_GLUE_RECORDS"))) {
+        HL_DEBUG_ERROR("hlb200: deblock_flag = 1 is not implemented by the device path for streams with SVC layers (set deblock_flag = 0)");
+        return HL_ERROR_NOT_IMPLEMENTED;
+    }
     if (p_codec->encoder.rc.b_enabled) { HL_DEBUG_ERROR("hlb200: rate control is not implemented by the device path (set rc_bitrate <= 0)"); return HL_ERROR_NOT_IMPLEMENTED; }
     return HL_ERROR_SUCCESS;
 }
@@ -474,6 +477,8 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
     prm.slice_type = g->is_p;
     prm.qp = p_codec->encoder.i_qp;
     prm.me_range = (int32_t)p_codec->pc_base->me_range;
+    prm.deblock_flag = p_codec->pc_base->deblock_flag ? 1 : 0;                /* loop filter over the finished picture, slice.c:1897 */
+    prm.me_early_term_flag = p_codec->pc_base->me_early_term_flag ? 1 : 0;   /* homogeneous-block mode mask, rdo.c:889-935 (the one live part of the flag) */
     prm.chroma_qp_index_offset = hdr->pc_pps->chroma_qp_index_offset;
     prm.num_refs = g->is_p ? (int32_t)hdr->num_ref_idx_l0_active_minus1 + 1 : 0;
     /* device slots of the reference pictures (RefPicList0 order), then a free slot for the current picture */

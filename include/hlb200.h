@@ -116,6 +116,8 @@ typedef struct hlb200_slice_params {
     int32_t chroma_qp_index_offset;
     int32_t cur_slot;    /* frame-store slot receiving the reconstruction */
     int32_t ref_slot[HLB200_MAX_REFS]; /* RefPicList0[i] -> frame-store slot */
+    int32_t me_early_term_flag; /* codec->me_early_term_flag: homogeneous-block detection masks partition modes (rdo.c:889-935, hl_math.c:470) */
+    int32_t deblock_flag;       /* codec->deblock_flag: loop filter over the finished picture before it becomes a reference (slice.c:1897, deblock.c:192) */
 } hlb200_slice_params_t;
 
 /* Levels / flags produced by the batch transform-quant-reconstruct kernel, per macroblock */

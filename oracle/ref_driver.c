@@ -447,6 +447,25 @@ static void gen_g2(uint8_t* yuv, int w, int h, int n, uint32_t seed)
     }
 }
 
+/* G3 "texture": a translating picture whose 8x8 blocks carry hashed texture of seven amplitudes (0..90) over a slow ramp, plus 2-bit noise from the LCG.
+ * The block amplitudes straddle the homogeneity thresholds of the early-termination mode mask (rdo.c:889-935), so all four of its outcomes occur. */
+static void gen_g3(uint8_t* yuv, int w, int h, int n, uint32_t seed)
+{
+    static const int amp[7] = {0, 4, 10, 20, 36, 56, 90};
+    int x, y, i;
+    uint8_t* Y = yuv; uint8_t* UV = yuv + (size_t)w * h;
+    for (y = 0; y < h; ++y) for (x = 0; x < w; ++x) {
+        const uint32_t X = (uint32_t)(x + 2 * n), Yc = (uint32_t)(y + n);
+        uint32_t v = X * 374761393u + Yc * 668265263u + seed * 2246822519u;
+        int a, s;
+        v = (v ^ (v >> 13)) * 1274126177u;
+        a = amp[(((X >> 3) * 73u + (Yc >> 3) * 151u + seed) % 7u)];
+        s = 96 + (int)(((X + Yc) >> 2) & 31u) + (int)((((v >> 16) & 127u) * (uint32_t)a) >> 7) + (int)(rnd() & 3);
+        Y[(size_t)y * w + x] = (uint8_t)(s > 255 ? 255 : s);
+    }
+    for (i = 0; i < (w * h) / 2; ++i) UV[i] = (uint8_t)(128 + ((i + n) & 15));
+}
+
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 static void md5_hex(const uint8_t* p, size_t n, char out[33])
@@ -482,7 +501,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--early-term") && i + 1 < argc) early = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--deblock") && i + 1 < argc) deblock = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--defaults")) defaults = 1;   /* keep what hl_codec_create sets for deblock_flag / me_early_term_flag (both 1, hl_types.h:67,69) */
-        else if (!strcmp(argv[i], "--gen") && i + 1 < argc) { ++i; gen = !strcmp(argv[i], "g2") ? 2 : 1; }
+        else if (!strcmp(argv[i], "--gen") && i + 1 < argc) { ++i; gen = !strcmp(argv[i], "g2") ? 2 : (!strcmp(argv[i], "g3") ? 3 : 1); }
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "--in") && i + 1 < argc) in_path = argv[++i];
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
@@ -542,6 +561,7 @@ int main(int argc, char** argv)
             const size_t lbytes = (size_t)lw * lh * 3 / 2;
             if (fin) { if (fread(yuv, 1, lbytes, fin) != lbytes) goto done; }
             else if (gen == 1) gen_g1(yuv, lw, lh, i);
+            else if (gen == 3) gen_g3(yuv, lw, lh, i, seed);
             else gen_g2(yuv, lw, lh, i, seed);
             if (fdump) fwrite(yuv, 1, lbytes, fdump);
             if ((err = hl_frame_video_fill(frame, HL_VIDEO_CHROMA_YUV420, lw, lh, yuv, lbytes))) { fprintf(stderr, "fill %d\n", err); return 1; }

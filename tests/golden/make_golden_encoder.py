@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import reftrace as rt  # noqa: E402
 
-CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range[, max_ref_frame]
+CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range[, max_ref_frame[, me_early_term_flag, deblock_flag]]
     ("g2_qcif", "g2", 5, 176, 144, 5, 30, 16),
     ("g1_qcif", "g1", 1, 176, 144, 5, 31, 16),
     ("g2_small_q12", "g2", 7, 64, 48, 6, 12, 64),
@@ -24,6 +24,12 @@ CONFIGS = [  # name, gen, seed, w, h, frames, qp, me_range[, max_ref_frame]
     ("g1_1080p_q31", "g1", 12345, 1920, 1088, 8, 31, 32),
     ("g2_1080p_q31", "g2", 3, 1920, 1088, 4, 31, 32),
     ("g1_1080p_ref4", "g1", 12345, 1920, 1088, 6, 31, 32, 4),
+    # the library's own defaults (hl_types.h:67,69): early termination (homogeneous-block mode mask, rdo.c:889-935) and the in-loop deblocking filter
+    # (deblock.c:192) -- G3 content straddles the homogeneity thresholds; the flags one at a time and together, and the defaults at the bench size
+    ("g3_cif_early", "g3", 4, 352, 288, 4, 20, 16, 1, 1, 0),
+    ("g2_qcif_deblock", "g2", 5, 176, 144, 5, 30, 16, 1, 0, 1),
+    ("g3_cif_defaults", "g3", 6, 352, 288, 5, 26, 16, 1, 1, 1),
+    ("g1_1080p_defaults", "g1", 12345, 1920, 1088, 4, 31, 32, 1, 1, 1),
 ]
 
 
@@ -31,9 +37,9 @@ def kind_of(e_type):
     return {306: 0, 301: 1, 302: 1, 303: 1, 304: 1, 305: 1, 101: 3}.get(e_type, 2)
 
 
-def build(name, gen, seed, w, h, frames, qp, me_range, refs=1):
+def build(name, gen, seed, w, h, frames, qp, me_range, refs=1, early_term=0, deblock=0):
     pre = "/tmp/golden_" + name
-    s = rt.run_driver(pre, w, h, frames, gen=gen, seed=seed, qp=qp, me_range=me_range, refs=refs)
+    s = rt.run_driver(pre, w, h, frames, gen=gen, seed=seed, qp=qp, me_range=me_range, refs=refs, early_term=early_term, deblock=deblock)
     t = rt.parse(pre + ".trace")
     nmb = (w // 16) * (h // 16)
     rec = {}
@@ -43,7 +49,7 @@ def build(name, gen, seed, w, h, frames, qp, me_range, refs=1):
     st = {(d["frame"], d["addr"]): d for d in map(rt.state_record, t[5])}
     fb = w * h * 3 // 2
     recon = np.fromfile(pre + ".recon", np.uint8).reshape(frames, fb)
-    out = dict(config=np.array([w, h, frames, qp, me_range, seed], np.int32), refs=np.array(refs, np.int32), gen=np.array(gen), bitstream_md5=np.array(s["md5"]),
+    out = dict(config=np.array([w, h, frames, qp, me_range, seed], np.int32), refs=np.array(refs, np.int32), flags=np.array([early_term, deblock], np.int32), gen=np.array(gen), bitstream_md5=np.array(s["md5"]),
                recon_md5=np.array([hashlib.md5(recon[n].tobytes()).hexdigest() for n in range(frames)]))
     kind = np.zeros((frames, nmb), np.uint8)
     mb_type = np.zeros((frames, nmb), np.uint8)

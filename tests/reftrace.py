@@ -13,11 +13,15 @@ def have_driver():
     return os.path.exists(DRIVER) and os.access(DRIVER, os.X_OK)
 
 
-def run_driver(out_prefix, w, h, frames, gen="g1", seed=1, qp=31, me_range=16, refs=1, cand=False, state=True, levels=True):
+def run_driver(out_prefix, w, h, frames, gen="g1", seed=1, qp=31, me_range=16, refs=1, cand=False, state=True, levels=True, early_term=0, deblock=0):
     """runs the reference encoder; returns dict(json summary) and writes <prefix>.trace/.recon/.264"""
     import json
     cmd = [DRIVER, "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", str(refs), "--gen", gen,
            "--seed", str(seed), "--trace", out_prefix + ".trace", "--recon", out_prefix + ".recon", "--out", out_prefix + ".264"]
+    if early_term:
+        cmd += ["--early-term", "1"]
+    if deblock:
+        cmd += ["--deblock", "1"]
     if cand:
         cmd.append("--trace-cand")
     if state:

@@ -62,7 +62,7 @@ def test_synth_matches_driver_generators():
     if not os.path.exists(drv):
         return
     from hartallo_b200 import synth
-    for gen, seed in (("g1", 1), ("g2", 3)):
+    for gen, seed in (("g1", 1), ("g2", 3), ("g3", 7)):
         subprocess.check_call([drv, "--size", "64", "48", "--frames", "2", "--gen", gen, "--seed", str(seed), "--dump-input", "/tmp/hlb_in.yuv"],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         ref = np.fromfile("/tmp/hlb_in.yuv", np.uint8).reshape(2, -1)

@@ -19,14 +19,19 @@ import reftrace as rt
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38", "g2_qcif_ref4", "g1_cif_10"]
+CONFIGS = ["g2_qcif", "g1_qcif", "g2_small_q12", "g2_cif_q38", "g2_qcif_ref4", "g1_cif_10", "g3_cif_early", "g2_qcif_deblock", "g3_cif_defaults"]
 # the configuration bench.py quotes its number on (1920x1088, QP 31, ME +-32, G1 seed of bench stream 0), its all-inter twin (G2) and max_ref_frame = 4: GPU tier only
-CONFIGS_1080P = ["g1_1080p_q31", "g2_1080p_q31", "g1_1080p_ref4"]
+CONFIGS_1080P = ["g1_1080p_q31", "g2_1080p_q31", "g1_1080p_ref4", "g1_1080p_defaults"]
 
 
 def refs_of(g):
     """max_ref_frame of a golden configuration (1 unless stored)"""
     return int(g["refs"]) if "refs" in g.files else 1
+
+
+def flags_of(g):
+    """(me_early_term_flag, deblock_flag) of a golden configuration (0, 0 unless stored: source/test_encoder.c:140,146)"""
+    return (int(g["flags"][0]), int(g["flags"][1])) if "flags" in g.files else (0, 0)
 
 
 def frames_of(gen, seed, w, h, n):
@@ -91,7 +96,7 @@ def check_frame(g, n, rec, recon, what):
         assert d == str(gold[a]), (what, n, a, "levels")
 
 
-def run_emu(w, h, frames, qp, me_range, yuv_frames, tag, refs=1):
+def run_emu(w, h, frames, qp, me_range, yuv_frames, tag, refs=1, flags=(0, 0)):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools", "emu"), "emu"], stdout=subprocess.DEVNULL)
     from hartallo_b200 import lib as hl
     pre = "/tmp/test_emu_" + tag
@@ -99,7 +104,8 @@ def run_emu(w, h, frames, qp, me_range, yuv_frames, tag, refs=1):
         for fr in yuv_frames:
             f.write(fr.tobytes())
     subprocess.check_call([os.path.join(ROOT, "tools", "emu", "emu"), "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp),
-                           "--me-range", str(me_range), "--refs", str(refs), "--in", pre + ".yuv", "--out", pre], stdout=subprocess.DEVNULL)
+                           "--me-range", str(me_range), "--refs", str(refs), "--early-term", str(flags[0]), "--deblock", str(flags[1]), "--in", pre + ".yuv", "--out", pre],
+                          stdout=subprocess.DEVNULL)
     nmb = (w // 16) * (h // 16)
     rec = np.fromfile(pre + ".rec", hl.MB_RECORD).reshape(frames, nmb)
     recon = np.fromfile(pre + ".recon", np.uint8).reshape(frames, -1)
@@ -111,7 +117,7 @@ def test_control_flow_vs_reference_cpu(name):
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
     fr = frames_of(str(g["gen"]), seed, w, h, frames)
-    rec, recon = run_emu(w, h, frames, qp, me_range, fr, name, refs_of(g))
+    rec, recon = run_emu(w, h, frames, qp, me_range, fr, name, refs_of(g), flags_of(g))
     for n in range(frames):
         check_frame(g, n, rec[n], recon[n], "emu/" + name)
 
@@ -132,7 +138,8 @@ def test_slice_encode_vs_reference(name, variant):
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
     fr = frames_of(str(g["gen"]), seed, w, h, frames)
-    enc = hl.Encoder(w, h, qp=qp, me_range=me_range, refs=refs_of(g))
+    early, deblock = flags_of(g)
+    enc = hl.Encoder(w, h, qp=qp, me_range=me_range, refs=refs_of(g), early_term=early, deblock=deblock)
     for n in range(frames):
         rec, recon = enc.encode(fr[n], want_recon=True)
         check_frame(g, n, rec, recon, "gpu/" + name)
@@ -238,7 +245,8 @@ def test_bitstream_md5_drop_in(name):
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
     out = subprocess.run([B200_ENCODER, "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", str(refs_of(g)),
-                          "--gen", str(g["gen"]), "--seed", str(seed)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                          "--gen", str(g["gen"]), "--seed", str(seed), "--early-term", str(flags_of(g)[0]), "--deblock", str(flags_of(g)[1])],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stderr[-500:]
     got = json.loads(out.stdout.strip().splitlines()[-1])
     assert got["md5"] == str(g["bitstream_md5"]), (got, str(g["bitstream_md5"]))

@@ -329,6 +329,7 @@ import json  # noqa: E402
 SVC_STREAMS = json.load(open(os.path.join(ROOT, "tests", "golden", "svc_bitstream.json")))
 GLUE_CHECK = os.path.join(ROOT, "oracle", "_ref", "hl_svc_glue_check")
 GLUE_FULL = os.path.join(ROOT, "oracle", "_ref", "hl_glue_check_full")
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "hl_ref_driver")
 B200_ENCODER = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder")
 
 
@@ -372,8 +373,9 @@ def test_single_layer_glue_bitstream_md5_cpu():
         if w * h * frames > 352 * 288 * 4:     # keep the CPU tier short: the big ones run on the GPU
             continue
         refs = int(g["refs"]) if "refs" in g.files else 1
+        early, deblock = (int(g["flags"][0]), int(g["flags"][1])) if "flags" in g.files else (0, 0)
         got = _encode(GLUE_FULL, ["--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--refs", str(refs), "--gen", str(g["gen"]),
-                                  "--seed", str(seed)])
+                                  "--seed", str(seed), "--early-term", str(early), "--deblock", str(deblock)])
         assert got["md5"] == str(g["bitstream_md5"]), (f, got)
         n += 1
     assert n >= 3
@@ -399,16 +401,28 @@ def _run_expect_refusal(exe, args, needle):
 
 @pytest.mark.skipif(not os.path.exists(GLUE_FULL), reason="oracle/_ref/hl_glue_check_full only exists where the reference tree is available")
 @pytest.mark.parametrize("args,needle", [
-    (["--size", "64", "48", "--frames", "2", "--defaults"], "deblock_flag"),                 # hl_codec_create's own settings: deblock_flag = 1, me_early_term_flag = 1
-    (["--size", "64", "48", "--frames", "2", "--deblock", "1"], "deblock_flag"),
-    (["--size", "64", "48", "--frames", "2", "--early-term", "1"], "me_early_term_flag"),
+    (["--size", "48", "48", "--layers", "2", "--frames", "2", "--deblock", "1"], "deblock_flag"),   # inter-layer deblocking (deblock.c:175-186) is not reproduced
     (["--size", "48", "16", "--layers", "3", "--frames", "2", "--gen", "g2", "--seed", "1865", "--qp", "22"], "Intra_Base"),   # 12-macroblock enhancement I picture (layer.c:202)
     (["--size", "48", "48", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "21", "--qp", "30"], "no partition"),    # coded against an earlier picture's scratch memory
 ])
 def test_glue_refuses_what_it_does_not_reproduce(args, needle):
-    """No silent divergence and no CPU fallback: library-default settings (in-loop deblocking, early termination), enhancement-layer I pictures too small for the
-    reference's own window array and macroblocks the reference codes against stale scratch memory all end in HL_ERROR_NOT_IMPLEMENTED (host/hlb200_glue.c)."""
+    """No silent divergence and no CPU fallback: deblocking of streams with SVC layers, enhancement-layer I pictures too small for the reference's own window
+    array and macroblocks the reference codes against stale scratch memory all end in HL_ERROR_NOT_IMPLEMENTED (host/hlb200_glue.c)."""
     _run_expect_refusal(GLUE_FULL, args, needle)
+
+
+@pytest.mark.skipif(not os.path.exists(GLUE_FULL) or not os.path.exists(REF_DRIVER), reason="needs oracle/_ref (built where the reference tree is available)")
+@pytest.mark.parametrize("args", [
+    ["--size", "176", "144", "--frames", "4", "--gen", "g2", "--seed", "8", "--qp", "33", "--defaults"],
+    ["--size", "96", "80", "--frames", "5", "--gen", "g3", "--seed", "2", "--qp", "22", "--defaults"],
+    ["--size", "64", "48", "--frames", "3", "--gen", "g1", "--defaults"],
+])
+def test_library_defaults_drop_in_cpu(args):
+    """hl_codec_create's own settings (deblock_flag = 1, me_early_term_flag = 1, hl_types.h:67,69) through the drop-in give the reference's stream byte for byte
+    (CPU tier: the kernels' per-macroblock source stands in for the library; the GPU twin is test_encoder.py::test_bitstream_md5_drop_in on the *_defaults goldens)"""
+    ref = _encode(REF_DRIVER, args)
+    got = _encode(GLUE_FULL, args)
+    assert (got["bytes"], got["md5"]) == (ref["bytes"], ref["md5"]), (got, ref)
 
 
 def test_glue_has_no_reference_cpu_path():

@@ -12,6 +12,7 @@
 #define HLB_EMU_DEBUG 1
 int g_emu_dbg = 0;
 #include "../../hartallo_b200/csrc/hlb_mbcore.cuh"
+#include "../../hartallo_b200/csrc/hlb_deblock.cuh"
 
 using namespace hlb;
 
@@ -45,7 +46,7 @@ struct CpuExec {
 
 int main(int argc, char** argv)
 {
-    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1, active_refs = 1, memo_stats = 0;
+    int W = 352, H = 288, frames = 2, qp = 31, me_range = 16, refs = 1, active_refs = 1, memo_stats = 0, early_term = 0, deblock = 0;
     const char *in = nullptr, *out = "emu";
     int dbg_frame = -1, dbg_mb = -1;
     if (getenv("EMU_DEBUG_MB")) sscanf(getenv("EMU_DEBUG_MB"), "%d:%d", &dbg_frame, &dbg_mb);
@@ -57,6 +58,8 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--refs")) refs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--active-refs")) active_refs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--memo-stats")) memo_stats = 1;
+        else if (!strcmp(argv[i], "--early-term")) early_term = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--deblock")) deblock = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--in")) in = argv[++i];
         else if (!strcmp(argv[i], "--out")) out = argv[++i];
     }
@@ -84,6 +87,7 @@ int main(int argc, char** argv)
         memset(&f, 0, sizeof(f));
         f.W = W; f.H = H; f.mbw = W / 16; f.mbh = H / 16; f.qp = qp;
         { int q = qp < 0 ? 0 : (qp > 51 ? 51 : qp); static const unsigned char t[22] = {29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39}; f.qpc = q < 30 ? q : t[q - 30]; }
+        f.early_term = early_term;
         f.is_p = n > 0; f.me_range = me_range < 1 ? 1 : (me_range > 64 ? 64 : me_range);
         f.lambda = 0.852 * (double)(1 << ((qp - 12) / 3));
         frame_ctx_derive(f);
@@ -105,6 +109,14 @@ int main(int argc, char** argv)
             mb_encode(x, *w, f, mb);
         }
         chain = x.prev_sctr(nmb);
+        if (deblock) {   // loop filter over the finished picture (slice.c:1897): what later pictures predict from
+            hlb::DbkJob d;
+            memset(&d, 0, sizeof(d));
+            for (int k = 0; k < 3; ++k) d.plane[k] = f.cur[k];
+            d.rec = rec.data(); d.W = W; d.H = H; d.mbw = f.mbw; d.mbh = f.mbh; d.enabled = 1;
+            hlb::dbk_job_thresholds(d, f.qp, f.qpc);
+            hlb::dbk_picture_serial(d);
+        }
         fwrite(slots[cur].data(), 1, fb, fr);
         fwrite(rec.data(), sizeof(hlb200_mb_record_t), nmb, fc);
         fwrite(st.data(), sizeof(MbState), nmb, fs);

@@ -24,12 +24,14 @@ for case in range(first, first + n_cases):
     frames = int(rng.integers(2, 6))
     qp = int(rng.integers(12, 52))
     me_range = int(rng.choice([1, 2, 4, 8, 16, 24, 32, 64]))
-    gen = str(rng.choice(["g1", "g2"]))
+    gen = str(rng.choice(["g1", "g2"] if not os.environ.get("FUZZ_GEN") else os.environ["FUZZ_GEN"].split(",")))
     seed = int(rng.integers(1, 10000))
     refs = int(rng.choice([1, 1, 1, 2, 4]))
+    early = int(os.environ.get("FUZZ_EARLY_TERM", "0"))
+    deblock = int(os.environ.get("FUZZ_DEBLOCK", "0"))
     pre = "/tmp/fuzz_%d" % case
     try:
-        rt.run_driver(pre, w, h, frames, gen=gen, seed=seed, qp=qp, me_range=me_range, refs=refs, levels=False, state=False)
+        rt.run_driver(pre, w, h, frames, gen=gen, seed=seed, qp=qp, me_range=me_range, refs=refs, levels=False, state=False, early_term=early, deblock=deblock)
     except subprocess.CalledProcessError:
         # the reference itself gives up on some inputs (e.g. "Memory too short" in hl_codec_264_rbsp_avc_escape for noisy pictures at low QP)
         print("case %d: %dx%d %s seed %d qp %d -> reference encoder failed, skipped" % (case, w, h, gen, seed, qp), flush=True)
@@ -40,7 +42,7 @@ for case in range(first, first + n_cases):
         for _ in range(frames):
             f.write(g.next().tobytes())
     subprocess.check_call([os.path.join(ROOT, "tools", "emu", "emu"), "--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range),
-                           "--refs", str(refs), "--in", pre + ".yuv", "--out", pre + "_emu"], stdout=subprocess.DEVNULL)
+                           "--refs", str(refs), "--early-term", str(early), "--deblock", str(deblock), "--in", pre + ".yuv", "--out", pre + "_emu"], stdout=subprocess.DEVNULL)
     emu = np.fromfile(pre + "_emu.recon", np.uint8).reshape(frames, -1)
     ok = [bool(np.array_equal(emu[i], ref[i])) for i in range(frames)]
     print("case %d: %dx%d %s seed %d frames %d qp %d range %d refs %d -> %s" % (case, w, h, gen, seed, frames, qp, me_range, refs, "OK" if all(ok) else "MISMATCH %s" % ok), flush=True)

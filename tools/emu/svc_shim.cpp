@@ -13,6 +13,7 @@ int g_emu_dbg = 0;
 #define HLB_EMU_DEBUG 1
 #include "../../hartallo_b200/csrc/hlb_mbcore.cuh"
 #include "../../hartallo_b200/csrc/hlb_bits.cuh"
+#include "../../hartallo_b200/csrc/hlb_deblock.cuh"
 #endif
 
 extern "C" int svc_emu_recon_batch(int bl, const uint8_t* src_y, const uint8_t* src_u, const uint8_t* src_v, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v,
@@ -125,6 +126,7 @@ API int hlb200_slice_encode(hlb200_ctx_t* c, const hlb200_slice_params_t* p, hlb
     f.is_p = p->slice_type == 1;
     f.me_range = p->me_range < 1 ? 1 : (p->me_range > 64 ? 64 : p->me_range);
     f.num_refs = f.is_p ? p->num_refs : 0;
+    f.early_term = p->me_early_term_flag != 0;
     f.lambda = 0.852 * (double)(1 << ((p->qp - 12) / 3));
     hlb::frame_ctx_derive(f);
     f.src[0] = c->src; f.src[1] = c->src + ys; f.src[2] = c->src + ys + cs;
@@ -134,6 +136,14 @@ API int hlb200_slice_encode(hlb200_ctx_t* c, const hlb200_slice_params_t* p, hlb
     CpuExec x{c->work, &f, c->chain};
     for (int mb = 0; mb < c->nmb; ++mb) hlb::mb_encode(x, *c->work, f, mb);
     c->chain = x.prev_sctr(c->nmb);
+    if (p->deblock_flag) {   // k_dbk_bs + k_dbk of hlb_slice.cu
+        hlb::DbkJob d;
+        memset(&d, 0, sizeof(d));
+        for (int k = 0; k < 3; ++k) d.plane[k] = f.cur[k];
+        d.rec = out; d.W = f.W; d.H = f.H; d.mbw = f.mbw; d.mbh = f.mbh; d.enabled = 1;
+        hlb::dbk_job_thresholds(d, f.qp, f.qpc);
+        hlb::dbk_picture_serial(d);
+    }
     return HLB200_OK;
 }
 API int hlb200_slice_encode_async(hlb200_ctx_t* c, const hlb200_slice_params_t* p) { return hlb200_slice_encode(c, p, c->rec); }
