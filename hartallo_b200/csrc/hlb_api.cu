@@ -356,6 +356,18 @@ int hlb200_sad4x4(hlb200_ctx_t* c, const uint8_t* pred_y, int use_satd, int32_t*
     return HLB200_OK;
 }
 
+int hlb200_homogeneity8x8(hlb200_ctx_t* c, int32_t* out_per_blk)
+{
+    if (!c || !out_per_blk) return HLB200_ERR_INVALID_PARAMETER;
+    const size_t nb = (size_t)(c->width >> 3) * (c->height >> 3);
+    int rc = ensure_scratch(c, nb * sizeof(int32_t));
+    if (rc) return rc;
+    if ((rc = hlb200_dev_homogeneity8x8(c->d_src[0], c->width, c->height, (int32_t*)c->d_scratch, c->stream))) return rc;
+    if ((rc = d2h(c, out_per_blk, c->d_scratch, nb * sizeof(int32_t)))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
 int hlb200_me_cost(hlb200_ctx_t* c, int ref_slot, int qp, const hlb200_me_cand_t* cands, int n, hlb200_me_cost_t* out)
 {
     if (!c || ref_slot < 0 || ref_slot >= c->nslots || !cands || !out || n < 0 || qp < 0 || qp > 51) return HLB200_ERR_INVALID_PARAMETER;

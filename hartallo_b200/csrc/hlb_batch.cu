@@ -328,7 +328,36 @@ __global__ void __launch_bounds__(256) k_sad4x4(const uint8_t* __restrict__ a, c
     uint8_t x[16], y[16];
     load4x4(a + by * W + bx, W, x);
     load4x4(b + by * W + bx, W, y);
-    out[t] = use_satd ? satd16(x, y) : sad16(x, y);
+    if (use_satd == 2) {   // hl_math_ssd4x4_u8, hl_math.c:360
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int d = (int)x[i] - (int)y[i]; s += d * d; }
+        out[t] = s;
+    } else out[t] = use_satd ? satd16(x, y) : sad16(x, y);
+}
+
+// ---------------- edge-map homogeneity of every 8x8 block of a plane (hl_math_homogeneousity8x8_u8, hl_math.c:470-486) ----------------------------
+// sum over the block of |dx| + |dy| (Sobel pair).  The 3x3 support of a block on the plane's border leaves the plane: such blocks get -1 (the encoder never
+// asks for them, rdo.c:894-895 shifts its window inwards).  One warp per block: lane = two horizontally adjacent samples of four rows... kept simple: one
+// thread per sample pair, 32 lanes x 2 samples = 64 samples, reduced by __reduce_add_sync.
+__global__ void __launch_bounds__(256) k_homogeneity8x8(const uint8_t* __restrict__ p, int W, int H, int32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31, blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int bw = W >> 3, nb = bw * (H >> 3);
+    if (blk >= nb) return;
+    const int bx = (blk % bw) * 8, by = (blk / bw) * 8;
+    if (bx == 0 || by == 0 || bx + 8 >= W || by + 8 >= H) { if (lane == 0) out[blk] = -1; return; }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = (lane & 3) * 2 + k, j = lane >> 2;
+        const uint8_t* c = p + (size_t)(by + j) * W + bx + i;
+        const uint8_t *up = c - W, *dn = c + W;
+        const int dx = dn[-1] + 2 * dn[0] + dn[1] - up[-1] - 2 * up[0] - up[1], dy = up[1] + 2 * c[1] + dn[1] - up[-1] - 2 * c[-1] - dn[-1];
+        s += iabs(dx) + iabs(dy);
+    }
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0) out[blk] = s;
 }
 
 // ---------------- independent ME candidate cost (me_ds.c:527-688): 16 lanes per candidate ---------------------------
@@ -528,9 +557,18 @@ int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d
     return HLB200_OK;
 }
 
+int hlb200_dev_homogeneity8x8(const uint8_t* d_plane, int width, int height, int32_t* d_out, void* cuda_stream)
+{
+    if (!d_plane || !d_out || width < 8 || height < 8 || (width & 7) || (height & 7)) return HLB200_ERR_INVALID_PARAMETER;
+    const int nb = (width >> 3) * (height >> 3);
+    k_homogeneity8x8<<<(nb * 32 + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_plane, width, height, d_out);
+    HLB_CUDA(cudaGetLastError());
+    return HLB200_OK;
+}
+
 int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream)
 {
-    if (!d_a || !d_b || !d_out || (width & 3) || (height & 3)) return HLB200_ERR_INVALID_PARAMETER;
+    if (!d_a || !d_b || !d_out || (width & 3) || (height & 3) || use_satd < 0 || use_satd > 2) return HLB200_ERR_INVALID_PARAMETER;
     const int nb = (width >> 2) * (height >> 2);
     k_sad4x4<<<(nb + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(d_a, d_b, width, height, use_satd, d_out);
     HLB_CUDA(cudaGetLastError());

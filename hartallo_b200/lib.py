@@ -56,7 +56,7 @@ def load():
         "hlb200_slice_encode": [vp, C.POINTER(SliceParams), vp], "hlb200_slice_encode_async": [vp, C.POINTER(SliceParams)], "hlb200_records_download": [vp, vp],
         "hlb200_slice_encode_batch_async": [C.POINTER(vp), C.POINTER(SliceParams), ip], "hlb200_slice_grid_size": [], "hlb200_slice_set_variant": [ip], "hlb200_slice_last_variant": [], "hlb200_slice_status": [vp, vp],
         "hlb200_interp_luma": [vp, ip, vp, vp], "hlb200_interp_chroma": [vp, ip, vp, vp, vp],
-        "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
+        "hlb200_tq_recon": [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp], "hlb200_sad4x4": [vp, vp, ip, vp], "hlb200_homogeneity8x8": [vp, vp], "hlb200_dev_homogeneity8x8": [vp, ip, ip, vp, vp], "hlb200_me_cost": [vp, ip, ip, vp, ip, vp],
         "hlb200_dev_interp_luma": [vp, ip, ip, vp, vp, vp], "hlb200_dev_interp_chroma": [vp, vp, ip, ip, vp, vp, vp, vp],
         "hlb200_dev_tq_recon": [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, vp, vp, vp, vp, vp],
         "hlb200_dev_interp_luma_batch": [vp, ip, ip, ip, C.c_size_t, vp, vp, vp], "hlb200_dev_interp_chroma_batch": [vp, vp, ip, ip, ip, C.c_size_t, vp, vp, vp, vp],
@@ -180,7 +180,12 @@ class Stream:
     def sad4x4(self, pred_y, satd=False):
         out = np.zeros((self.h // 4, self.w // 4), np.int32)
         p = np.ascontiguousarray(pred_y, np.uint8)
-        check(self.lib.hlb200_sad4x4(self.ctx, ptr(p), 1 if satd else 0, ptr(out)), "sad4x4")
+        check(self.lib.hlb200_sad4x4(self.ctx, ptr(p), int(satd), ptr(out)), "sad4x4")
+        return out
+
+    def homogeneity8x8(self):
+        out = np.zeros((self.h // 8, self.w // 8), np.int32)
+        check(self.lib.hlb200_homogeneity8x8(self.ctx, ptr(out)), "homogeneity8x8")
         return out
 
     def me_cost(self, ref_slot, qp, cands):

@@ -211,7 +211,11 @@ HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_
 HLB200_API int hlb200_interp_chroma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_u, uint8_t* pred_v);
 HLB200_API int hlb200_tq_recon(hlb200_ctx_t* ctx, int qp, int chroma_qp_index_offset, const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v,
                                hlb200_mb_coeffs_t* coeffs, uint8_t* recon_y, uint8_t* recon_u, uint8_t* recon_v);
+/* use_satd: 0 SAD (hl_math.c:239), 1 SATD (hl_math.c:283), 2 SSD (hl_math_ssd4x4_u8 hl_math.c:360) */
 HLB200_API int hlb200_sad4x4(hlb200_ctx_t* ctx, const uint8_t* pred_y, int use_satd, int32_t* out_per_blk /* (H/4)*(W/4) */);
+/* hl_math_homogeneousity8x8_u8 (hl_math.c:470) of every 8x8 block of the uploaded source luma: sum |dx| + |dy| of the Sobel pair; blocks touching the
+ * plane's border (whose 3x3 support leaves the plane) report -1.  Feeds the early-termination mode mask (rdo.c:889-935; inside the slice kernel: me_mode_mask). */
+HLB200_API int hlb200_homogeneity8x8(hlb200_ctx_t* ctx, int32_t* out_per_blk /* (H/8)*(W/8) */);
 HLB200_API int hlb200_me_cost(hlb200_ctx_t* ctx, int ref_slot, int qp, const hlb200_me_cand_t* cands, int n, hlb200_me_cost_t* out);
 
 /* ---- the same kernels on device pointers (inputs already resident in HBM; asynchronous on `cuda_stream`) ---- */
@@ -263,6 +267,7 @@ HLB200_API int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const
                                                    uint8_t* d_pred_y, uint8_t* d_pred_u, uint8_t* d_pred_v, int width, int height, int n_pics, size_t ref_frame_stride,
                                                    size_t frame_stride, int level_idc, void* cuda_stream);
 HLB200_API int hlb200_dev_sad4x4(const uint8_t* d_a, const uint8_t* d_b, int width, int height, int use_satd, int32_t* d_out, void* cuda_stream);
+HLB200_API int hlb200_dev_homogeneity8x8(const uint8_t* d_plane, int width, int height, int32_t* d_out, void* cuda_stream);
 HLB200_API int hlb200_dev_me_cost(const uint8_t* d_src_y, const uint8_t* d_ref_y, int width, int height, int qp, const hlb200_me_cand_t* d_cands, int n,
                                   hlb200_me_cost_t* d_out, void* cuda_stream);
 

@@ -206,6 +206,23 @@ HLO_API int hlo_sad4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
     for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) s += abs((int)a[y * sa + x] - (int)b[y * sb + x]);
     return s;
 }
+/* hl_math_ssd4x4_u8_cpp, source/hl_math.c:360-375 */
+HLO_API int hlo_ssd4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
+{
+    int s = 0, x, y;
+    for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) { const int d = (int)a[y * sa + x] - (int)b[y * sb + x]; s += d * d; }
+    return s;
+}
+/* hl_math_homogeneousity8x8_u8_cpp, source/hl_math.c:470-486: JVT-O079 edge map (2-35); p = top-left sample of the 8x8 block, not on the plane's border */
+HLO_API int hlo_homogeneity8x8(const uint8_t* p, int stride)
+{
+    int s = 0, i, j;
+    for (j = 0; j < 8; ++j) for (i = 0; i < 8; ++i) {
+        const uint8_t *c = p + j * stride + i, *up = c - stride, *dn = c + stride;
+        s += abs(dn[-1] + 2 * dn[0] + dn[1] - up[-1] - 2 * up[0] - up[1]) + abs(up[1] + 2 * c[1] + dn[1] - up[-1] - 2 * c[-1] - dn[-1]);
+    }
+    return s;
+}
 /* hl_math_satd4x4_u8_cpp, source/hl_math.c:283-357: sum |H.D.H| >> 1 */
 HLO_API int hlo_satd4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
 {

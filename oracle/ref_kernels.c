@@ -223,6 +223,15 @@ int ref_satd4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
     for (i = 0; i < 4; ++i) { memcpy(x + 4 * i, a + i * sa, 4); memcpy(y + 4 * i, b + i * sb, 4); }
     return hl_math_satd4x4_u8(x, 4, y, 4);
 }
+/* hl_math_ssd4x4_u8 (hl_math.c:360), hl_math_homogeneousity8x8_u8 (hl_math.c:470) */
+int ref_ssd4x4(const uint8_t* a, int sa, const uint8_t* b, int sb)
+{
+    HL_ALIGN(HL_ALIGN_V) uint8_t x[16], y[16]; int i;
+    ref_init();
+    for (i = 0; i < 4; ++i) { memcpy(x + 4 * i, a + i * sa, 4); memcpy(y + 4 * i, b + i * sb, 4); }
+    return hl_math_ssd4x4_u8(x, 4, y, 4);
+}
+int ref_homogeneity8x8(const uint8_t* p, int stride) { ref_init(); return hl_math_homogeneousity8x8_u8(p, stride); }
 /* hl_math_addclip_4x4_u8xi32 (hl_math.h:303, wraps) and hl_math_addclip_4x4 (hl_math.h:278, clips) */
 void ref_addclip_u8xi32(const uint8_t* pred /*16*/, const int32_t* res /*16*/, uint8_t* out /*16*/)
 {

@@ -36,6 +36,8 @@ _SIGS = {
     "scale_chroma_dc": (None, [C.c_int, i32p, i32p]),
     "sad4x4": (C.c_int, [u8p, C.c_int, u8p, C.c_int]),
     "satd4x4": (C.c_int, [u8p, C.c_int, u8p, C.c_int]),
+    "ssd4x4": (C.c_int, [u8p, C.c_int, u8p, C.c_int]),
+    "homogeneity8x8": (C.c_int, [C.c_void_p, C.c_int]),
     "addclip_u8xi32": (None, [u8p, i32p, u8p]),
     "addclip_i32": (None, [i32p, i32p, i32p]),
 }
@@ -95,6 +97,10 @@ def load_ref():
     lib.ref_sad4x4.argtypes = [u8p, C.c_int, u8p, C.c_int]
     lib.ref_satd4x4.restype = C.c_int
     lib.ref_satd4x4.argtypes = [u8p, C.c_int, u8p, C.c_int]
+    lib.ref_ssd4x4.restype = C.c_int
+    lib.ref_ssd4x4.argtypes = [u8p, C.c_int, u8p, C.c_int]
+    lib.ref_homogeneity8x8.restype = C.c_int
+    lib.ref_homogeneity8x8.argtypes = [C.c_void_p, C.c_int]
     lib.ref_addclip_u8xi32.argtypes = [u8p, i32p, u8p]
     lib.ref_addclip_i32.argtypes = [i32p, i32p, i32p]
     lib.ref_cavlc_luma_bits.restype = C.c_int

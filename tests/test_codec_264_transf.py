@@ -77,13 +77,20 @@ def test_sad_satd_parity():
     st = hl.Stream(w, h, 1)
     st.upload_frame(a)
     ya, yb = a[:w * h].reshape(h, w), np.ascontiguousarray(b[:w * h].reshape(h, w))
-    gs, gt = st.sad4x4(yb), st.sad4x4(yb, satd=True)
+    gs, gt, gq = st.sad4x4(yb), st.sad4x4(yb, satd=True), st.sad4x4(yb, satd=2)
+    gh = st.homogeneity8x8()
     ya = np.ascontiguousarray(ya)
     for by in range(0, h // 4, 3):
         for bx in range(w // 4):
             pa, pb = ya[by * 4:, bx * 4:], yb[by * 4:, bx * 4:]
             assert gs[by, bx] == o.hlo_sad4x4(np.ascontiguousarray(pa[:4, :4]), 4, np.ascontiguousarray(pb[:4, :4]), 4)
             assert gt[by, bx] == o.hlo_satd4x4(np.ascontiguousarray(pa[:4, :4]), 4, np.ascontiguousarray(pb[:4, :4]), 4)
+            assert gq[by, bx] == o.hlo_ssd4x4(np.ascontiguousarray(pa[:4, :4]), 4, np.ascontiguousarray(pb[:4, :4]), 4)
+    # edge-map homogeneity of every 8x8 block (hl_math.c:470): interior blocks against the oracle, border blocks flagged
+    assert (gh[0] == -1).all() and (gh[-1] == -1).all() and (gh[:, 0] == -1).all() and (gh[:, -1] == -1).all()
+    for by in range(1, h // 8 - 1):
+        for bx in range(1, w // 8 - 1):
+            assert gh[by, bx] == o.hlo_homogeneity8x8(ya.ctypes.data + by * 8 * w + bx * 8, w), (by, bx)
     # size-independent property at full size: SAD(a, a) == 0 everywhere
     assert not st.sad4x4(np.ascontiguousarray(ya)).any()
     st.close()

@@ -143,6 +143,9 @@ def test_math_live():
         b = stress_plane(rng, 16, 16)
         assert o.hlo_sad4x4(a, 16, b, 16) == r.ref_sad4x4(a, 16, b, 16)
         assert o.hlo_satd4x4(a, 16, b, 16) == r.ref_satd4x4(a, 16, b, 16)
+        assert o.hlo_ssd4x4(a, 16, b, 16) == r.ref_ssd4x4(a, 16, b, 16)
+        pa = a.ctypes.data + 16 * 3 + 2   # an 8x8 block whose 3x3 support stays inside the 16x16 plane
+        assert o.hlo_homogeneity8x8(pa, 16) == r.ref_homogeneity8x8(pa, 16)
         pred = rng.choice(np.array([0, 1, 3, 250, 255, 128, 200, 10], np.uint8), 16).astype(np.uint8)
         res = rng.integers(-300, 300, 16).astype(np.int32)
         oa, ob = np.zeros(16, np.uint8), np.zeros(16, np.uint8)
