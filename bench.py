@@ -363,8 +363,11 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     if os.path.exists(MULTI) and os.access(MULTI, os.X_OK):
         env = dict(os.environ, HLB200_DEVICE=str(local))
         out_264 = "/tmp/hlb200_bench_rank%d.264" % rank
-        cmd = [MULTI, "--streams", str(S), "--frames", str(nfr), "--warmup", str(Wm), "--groups", "1", "--qp", str(QP), "--me-range", str(ME_RANGE), "--distinct", str(min(args.distinct, S)),
-               "--out", out_264]
+        # two groups of S streams: each launch still covers S pictures (the device-resident number's launch), the host work of one group (hl_codec_encode around the hook,
+        # uploads, bit downloads) overlaps the kernel of the other -- measured 3.92 M MB/s with one group of 256, 4.49 M with two (profiles/r02s)
+        G = args.e2e_groups
+        cmd = [MULTI, "--streams", str(G * S), "--frames", str(nfr), "--warmup", str(Wm), "--groups", str(G), "--qp", str(QP), "--me-range", str(ME_RANGE),
+               "--distinct", str(min(args.distinct, S)), "--out", out_264]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         if r.returncode != 0:
             raise SystemExit("bench.py: %s failed: %s" % (os.path.basename(MULTI), r.stderr[-400:]))
@@ -372,14 +375,23 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
         e2e_ms = torch.tensor([mj["ms_timed"]], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e_value = world * S * NMB * K / (float(e2e_ms.item()) * 1e-3)
-        e2e = {"value": e2e_value, "unit": UNIT, "encode_fps": world * S * K / (float(e2e_ms.item()) * 1e-3), "fps_unit": "1080p pictures/s over all streams (H.264 bitstream produced)",
-               "h2d_bytes_per_step": int(S * frame_b), "d2h_bytes_per_step": int(mj["bitstream_bytes_timed"] // max(K, 1)), "ms_per_step": float(e2e_ms.item()) / K,
+        e2e_value = world * G * S * NMB * K / (float(e2e_ms.item()) * 1e-3)
+        e2e = {"value": e2e_value, "unit": UNIT, "encode_fps": world * G * S * K / (float(e2e_ms.item()) * 1e-3), "fps_unit": "1080p pictures/s over all streams (H.264 bitstream produced)",
+               "streams_per_gpu": G * S, "groups": G, "step": "one picture of each of the %d streams (%d launches of %d pictures)" % (G * S, G, S),
+               "h2d_bytes_per_step": int(G * S * frame_b), "d2h_bytes_per_step": int(mj["bitstream_bytes_timed"] // max(K, 1)), "ms_per_step": float(e2e_ms.item()) / K,
                "bitstream_bytes_per_step": int(mj["bitstream_bytes_timed"] // max(K, 1)),
                "api": "hl_codec_encode (the reference's unmodified host code: headers, DPB, NAL assembly, emulation prevention) x %d codec instances per GPU, host/hlb200_glue.c in batch mode: "
                       "hlb200_frame_upload from page-locked host pictures + ONE hlb200_slice_encode_batch_async + ONE hlb200_slice_bits_batch_async per picture of all streams + "
                       "hlb200_slice_bits_download (slice data written on the device)" % S,
                "driver": "oracle/_ref/hl_b200_multi (host/hl_b200_multi.c)"}
+        if rank == 0 and not args.no_all_inter:
+            # the library's own settings (hl_codec_create: deblock_flag = 1, me_early_term_flag = 1) on 64 streams, beside the test_encoder.c settings of the headline
+            r2 = subprocess.run([MULTI, "--streams", "64", "--frames", "5", "--warmup", "1", "--groups", "1", "--qp", str(QP), "--me-range", str(ME_RANGE), "--defaults"],
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+            if r2.returncode == 0:
+                dj = json.loads(r2.stdout.strip().splitlines()[-1])
+                e2e["library_defaults"] = {"streams": 64, "settings": "deblock_flag = 1, me_early_term_flag = 1 (hl_types.h:67,69)", "value": dj["mb_per_s"], "unit": UNIT, "encode_fps": dj["encode_fps"],
+                                           "api": "hl_codec_encode, loop filter (k_dbk_bs + k_dbk) and homogeneity mode mask on the device"}
         if rank == 0 and os.path.exists(BENCH_GOLDEN):
             gold = json.load(open(BENCH_GOLDEN))
             pref = gold.get("bitstream_prefix", [])
@@ -409,6 +421,12 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
                 "encode_fps": e2e["encode_fps"]}
         if all_inter:
             line["all_inter"] = all_inter
+        if world == 1 and not args.no_hbm_kernels:
+            # the stateless whole-picture kernels (interpolation, transform-quantisation-reconstruction, the SVC base-mode kernels): HBM rooflines at 128 pictures per launch
+            torch.cuda.empty_cache()
+            r3 = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "hbm_kernels.py"), "128"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            if r3.returncode == 0 and r3.stdout.strip():
+                line["hbm_kernels"] = json.loads(r3.stdout.strip().splitlines()[-1])
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
@@ -433,6 +451,8 @@ def main():
     ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU encoded concurrently (one picture each per step)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic sequences; stream s shows sequence s %% distinct (own buffers)")
     ap.add_argument("--sets", type=int, default=24, help="distinct picture buffer sets rotated through (footprint must exceed the 126 MB L2)")
+    ap.add_argument("--e2e-groups", type=int, default=2, help="the end-to-end arm drives this many groups of --streams codec instances, one launch per group in flight while the host works on the other")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the bandwidth rooflines of the stateless whole-picture kernels (tools/hbm_kernels.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-all-inter", action="store_true", help="skip the G2 (all-inter) sub-measurement")
     args = ap.parse_args()
