@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_interp_luma(const uint8_t* __restrict__
     const int X = clip3(-17, W + 17, mbx * 16 + g.ox + (mvx >> 2)) + (bx - g.ox);
     const int Y = clip3(-17, H + 17, mby * 16 + g.oy + (mvy >> 2)) + (by - g.oy);
     Rows4 o;
-    if (X >= 2 && Y >= 2 && X + 7 <= W && Y + 7 <= H) o = fast_pred_luma_t<LdReadOnly>(reinterpret_cast<const uint32_t*>(ref), W >> 2, X, Y, mvx & 3, mvy & 3);
+    if (X >= 2 && Y >= 2 && X + 7 <= W && Y + 7 <= H) o = fast_pred_luma_staged<LdReadOnly>(reinterpret_cast<const uint32_t*>(ref), W >> 2, X, Y, mvx & 3, mvy & 3);
     else {
         // the window touches the picture edge: staged with the reference's per-sample clamp (interpol.c:108-131), 12 bytes per row
         uint32_t win[9 * 3];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_interp_luma(const uint8_t* __restrict__
                 win[r * 3 + q] = v;
             }
         }
-        o = fast_pred_luma_t<LdPlain>(win, 3, 2, 2, mvx & 3, mvy & 3);
+        o = fast_pred_luma_staged<LdPlain>(win, 3, 2, 2, mvx & 3, mvy & 3);
     }
     uint8_t* dst = pred + (size_t)gy * W + gx;
 #pragma unroll
@@ -75,33 +75,33 @@ __global__ void __launch_bounds__(256) k_interp_luma(const uint8_t* __restrict__
 }
 
 // ---------------- chroma interpolation: one thread per four horizontally adjacent samples of one plane, PICTURE raster order ---------------------
-// (8 luma samples wide: one motion vector unless the macroblock is split into 4-wide sub-partitions, then two).  Interior: two rows of the reference fetched
-// as aligned words + funnel shift, the 1/8-pel bilinear sample as two byte dot products (weights (8-xf)(8-yf), xf(8-yf) | (8-xf)yf, xf yf).
-__device__ __forceinline__ uint32_t chroma_pair(const uint8_t* __restrict__ rp, int Wc, int Hc, int x0, int y0, int xf, int yf, int n)
+// (8 luma samples wide: one motion vector unless the macroblock is split into 4-wide sub-partitions, then two).  Written as ONE control flow for both cases:
+// every thread forms its two sample pairs from their own vectors (equal in the common case), so warps that straddle macroblocks of different partition layouts
+// do not run the two variants one after the other (the first packed version did: 360 warp instructions per thread, 17 of 32 lanes active on average).
+// Interior: two rows of the reference fetched as aligned words + funnel shift, the 1/8-pel bilinear sample as two byte dot products
+// (weights (8-xf)(8-yf), xf(8-yf) | (8-xf)yf, xf yf).
+__device__ __forceinline__ uint32_t chroma_two(const uint8_t* __restrict__ rp, int Wc, int Hc, int x0, int y0, int xf, int yf)
 {
-    // n (2 or 4) samples starting at (x0, y0); returns them packed from the low byte
+    // samples (x0, y0), (x0 + 1, y0) of the prediction; returned in the two low bytes
     const uint32_t wa = (uint32_t)((8 - xf) * (8 - yf)) | ((uint32_t)(xf * (8 - yf)) << 8), wc = (uint32_t)((8 - xf) * yf) | ((uint32_t)(xf * yf) << 8);
-    uint32_t a0, a1, c0, c1;
-    if (x0 >= 0 && y0 >= 0 && x0 + n < Wc && y0 + 1 < Hc && (x0 >> 2) + 1 < (Wc >> 2)) {
+    uint32_t a, c;   // three samples of row y0 / y0 + 1 starting at x0
+    if (x0 >= 0 && y0 >= 0 && y0 + 1 < Hc && (x0 >> 2) + 1 < (Wc >> 2)) {
         const uint32_t* ra = reinterpret_cast<const uint32_t*>(rp + (size_t)y0 * Wc) + (x0 >> 2);
-        const uint32_t* rc = reinterpret_cast<const uint32_t*>(rp + (size_t)(y0 + 1) * Wc) + (x0 >> 2);
-        const uint32_t sh = (uint32_t)(x0 & 3) * 8, ua = __ldg(ra), va = __ldg(ra + 1), uc = __ldg(rc), vc = __ldg(rc + 1);
-        a0 = p_shf_r(ua, va, sh); a1 = va >> sh; c0 = p_shf_r(uc, vc, sh); c1 = vc >> sh;   // samples 0..3 and sample 4 (low byte)
+        const uint32_t* rc = ra + (Wc >> 2);
+        const uint32_t sh = (uint32_t)(x0 & 3) * 8;
+        a = p_shf_r(__ldg(ra), __ldg(ra + 1), sh); c = p_shf_r(__ldg(rc), __ldg(rc + 1), sh);
     } else {
-        a0 = a1 = c0 = c1 = 0;
         const uint8_t* ra = rp + (size_t)clip3(0, Hc - 1, y0) * Wc;
         const uint8_t* rc = rp + (size_t)clip3(0, Hc - 1, y0 + 1) * Wc;
+        a = c = 0;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < 3; ++i) {
             const int x = clip3(0, Wc - 1, x0 + i);
-            if (i < 4) { a0 |= (uint32_t)__ldg(ra + x) << (8 * i); c0 |= (uint32_t)__ldg(rc + x) << (8 * i); }
-            else { a1 = __ldg(ra + x); c1 = __ldg(rc + x); }
+            a |= (uint32_t)__ldg(ra + x) << (8 * i); c |= (uint32_t)__ldg(rc + x) << (8 * i);
         }
     }
-    int v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = p_dp4a_us(p_shf_r(c0, c1, 8 * i), wc, p_dp4a_us(p_shf_r(a0, a1, 8 * i), wa, 32)) >> 6;
-    return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    const int v0 = p_dp4a_us(c, wc, p_dp4a_us(a, wa, 32)) >> 6, v1 = p_dp4a_us(c >> 8, wc, p_dp4a_us(a >> 8, wa, 32)) >> 6;
+    return (uint32_t)v0 | ((uint32_t)v1 << 8);
 }
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
                                                        const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride)
@@ -112,25 +112,24 @@ __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict
     const int plane = t >= per_plane, s = t - plane * per_plane, cy = s / sw, cx = (s - cy * sw) << 2;
     const uint8_t* rp = (plane ? ref_v : ref_u) + blockIdx.y * stride;
     uint8_t* dst = (plane ? pred_v : pred_u) + blockIdx.y * stride + (size_t)cy * Wc + cx;
-    motion += (size_t)blockIdx.y * nmb;
-    const int mbx = cx >> 3, mby = cy >> 3, lx = (cx & 7) * 2, ly = (cy & 7) * 2;   // luma position inside the macroblock
-    const hlb200_mb_motion_t* m = motion + mby * mbw + mbx;
-    const PartGeom g0 = part_of(m->part_mode, m->sub_mode, lx, ly);
-    const int mvx = m->mv[g0.part][g0.sub][0], mvy = m->mv[g0.part][g0.sub][1];
-    uint32_t out;
-    if (g0.w >= 8) out = chroma_pair(rp, Wc, Hc, cx + (mvx >> 3), cy + (mvy >> 3), mvx & 7, mvy & 7, 4);
-    else {   // 4-wide sub-partitions: the right half has its own vector
-        const PartGeom g1 = part_of(m->part_mode, m->sub_mode, lx + 4, ly);
-        const int nvx = m->mv[g1.part][g1.sub][0], nvy = m->mv[g1.part][g1.sub][1];
-        out = (chroma_pair(rp, Wc, Hc, cx + (mvx >> 3), cy + (mvy >> 3), mvx & 7, mvy & 7, 2) & 0xffffu) |
-              (chroma_pair(rp, Wc, Hc, cx + 2 + (nvx >> 3), cy + (nvy >> 3), nvx & 7, nvy & 7, 2) << 16);
-    }
+    const hlb200_mb_motion_t* m = motion + (size_t)blockIdx.y * nmb + (cy >> 3) * mbw + (cx >> 3);
+    // the thread's eight luma columns lie in one macroblock partition; the sub-partition of its left / right half (part_of, hlb_common.cuh)
+    const int hx = (cx >> 2) & 1, hy = (cy >> 2) & 1, pm = m->part_mode;
+    const int part = pm == 0 ? 0 : (pm == 1 ? hy : (pm == 2 ? hx : hy * 2 + hx));
+    const int sm = pm == 3 ? m->sub_mode[part] : 0, row = (cy >> 1) & 1;   // row: upper / lower 4 luma rows of the 8x8
+    const int sub_l = (sm & 1 ? row : 0) << (sm >> 1), sub_r = sub_l + (sm >> 1);
+    const uint32_t* mv = reinterpret_cast<const uint32_t*>(&m->mv[part][0][0]);
+    const uint32_t vl = __ldg(mv + sub_l), vr = __ldg(mv + sub_r);
+    const int lx = (int)(int16_t)(vl & 0xffffu), ly = (int)vl >> 16, rx = (int)(int16_t)(vr & 0xffffu), ry = (int)vr >> 16;
+    const uint32_t out = chroma_two(rp, Wc, Hc, cx + (lx >> 3), cy + (ly >> 3), lx & 7, ly & 7) | (chroma_two(rp, Wc, Hc, cx + 2 + (rx >> 3), cy + (ry >> 3), rx & 7, ry & 7) << 16);
     *reinterpret_cast<uint32_t*>(dst) = out;
 }
 
-// ---------------- residual coding + reconstruction: one warp per macroblock ----------------------------------------
-// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks 0..3; lanes 20..23: Cr blocks 0..3 (raster); lanes 24..31 idle.  A lane keeps its block as four packed
-// rows: residual transform = byte dot products (hlb_fast.cuh), reconstruction = saturating pack.
+// ---------------- residual coding + reconstruction: one thread per 4x4 block, warps of one kind of block ----------------------------------------
+// The luma blocks of a picture (16 per macroblock, luma4x4BlkIdx order) and its chroma blocks (8 per macroblock: Cb 0..3, Cr 0..3) form two index spaces
+// served by different CTAs of the same launch, so a warp never runs the luma and the chroma control flow one after the other (the first version gave 24 of
+// 32 lanes a block and executed both paths per warp: 908 warp instructions per macroblock, issue-bound at 0.29 of the HBM peak).  A lane keeps its block as
+// four packed rows: residual transform = byte dot products (hlb_fast.cuh), reconstruction = saturating pack, levels leave as four 8-byte stores, transposed over groups of four lanes so that every store instruction fills whole 32-byte sectors.
 __device__ __forceinline__ void load4x4(const uint8_t* __restrict__ p, int pitch, uint8_t v[16])
 {
 #pragma unroll
@@ -139,6 +138,11 @@ __device__ __forceinline__ void load4x4(const uint8_t* __restrict__ p, int pitch
         v[r * 4] = w & 255; v[r * 4 + 1] = (w >> 8) & 255; v[r * 4 + 2] = (w >> 16) & 255; v[r * 4 + 3] = w >> 24;
     }
 }
+struct TqConst {
+    QuantK luma, chroma;         // luma: inter rounding offset; chroma AC: always the intra offset (rdo.c:2588)
+    int dc_qbits1, dc_f2, dc_mf; // 2x2 chroma DC quantiser (quant.c:150-189) with the macroblock's own (inter) offset (rdo.c:2660)
+    int dc_ls, dc_q6;            // its de-quantisation (transf.c:612): ((f * LevelScale(qP % 6, 0, 0)) << (qP / 6)) >> 5
+};
 __device__ __forceinline__ void quantk_device(QuantK& k, int qp, bool intra)   // quantk_make from the device tables
 {
     const int r = qp % 6, q6 = qp / 6;
@@ -147,145 +151,170 @@ __device__ __forceinline__ void quantk_device(QuantK& k, int qp, bool intra)   /
     for (int c = 0; c < 3; ++c) { k.mf[c] = kQuantMF[r][c]; k.dq_mul[c] = qp >= 24 ? (16 * kNormAdjust[r][c]) << (q6 - 4) : 16 * kNormAdjust[r][c]; }
     k.dq_shift = qp >= 24 ? 0 : 4 - q6; k.dq_round = qp >= 24 ? 0 : 1 << (3 - q6); k.zero_sad = -1;
 }
-__global__ void __launch_bounds__(128) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
+// zig-zag levels two per word: word k = lv[2k] | lv[2k+1] << 16 from the raster block m
+__device__ __forceinline__ uint32_t pair16(int lo, int hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
+// The 32-byte level lists of four neighbouring lanes (= four consecutive blocks: 128 contiguous bytes) leave as four stores in which the four lanes together
+// write ONE full 32-byte sector each, instead of four sectors a quarter full: a 4x4 transpose of 8-byte elements over the lanes (two butterfly stages).
+// In: P[j] = 8-byte piece j of this lane's block.  Out: P[k] = piece (lane & 3) of the block of lane (lane & ~3) + k.
+__device__ __forceinline__ void transpose4_u2(uint2 P[4], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const bool o1 = lane & 1, o2 = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        const uint2 snd = o1 ? P[j] : P[j + 1];
+        const uint2 rcv = make_uint2(__shfl_xor_sync(full, snd.x, 1), __shfl_xor_sync(full, snd.y, 1));
+        if (o1) P[j] = rcv; else P[j + 1] = rcv;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint2 snd = o2 ? P[j] : P[j + 2];
+        const uint2 rcv = make_uint2(__shfl_xor_sync(full, snd.x, 2), __shfl_xor_sync(full, snd.y, 2));
+        if (o2) P[j] = rcv; else P[j + 2] = rcv;
+    }
+}
+__global__ void __launch_bounds__(128, 10) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
                                                   const uint8_t* __restrict__ pred_y, const uint8_t* __restrict__ pred_u, const uint8_t* __restrict__ pred_v,
                                                   int W, int H, int mbw, int nmb, int qp, int qpc, hlb200_mb_coeffs_t* __restrict__ coeffs,
-                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride)
+                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride, int luma_ctas)
 {
-    __shared__ QuantK s_qk[2];   // [0] luma (inter rounding offset), [1] chroma AC (always the intra offset, rdo.c:2588)
-    if (threadIdx.x < 2) quantk_device(s_qk[threadIdx.x], threadIdx.x ? qpc : qp, threadIdx.x != 0);
-    __syncthreads();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nmb) return;  // warp-uniform
-    {
-        const size_t o = blockIdx.y * stride;
-        src_y += o; src_u += o; src_v += o; pred_y += o; pred_u += o; pred_v += o; rec_y += o; rec_u += o; rec_v += o;
-        coeffs += (size_t)blockIdx.y * nmb;
+    __shared__ TqConst K;
+    if (threadIdx.x < 2) quantk_device(threadIdx.x ? K.chroma : K.luma, threadIdx.x ? qpc : qp, threadIdx.x != 0);
+    if (threadIdx.x == 2) {
+        K.dc_qbits1 = 16 + qpc / 6; K.dc_f2 = ((1 << (15 + qpc / 6)) / 6) << 1; K.dc_mf = kQuantMF[qpc % 6][0];
+        K.dc_ls = 16 * kNormAdjust[qpc % 6][0]; K.dc_q6 = qpc / 6;
     }
-    const int mb = warp, mbx = mb % mbw, mby = mb / mbw;
-    hlb200_mb_coeffs_t* out = coeffs + mb;
-    const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
-    const int plane = is_luma ? 0 : ((lane - 16) >> 2) + 1, cblk = (lane - 16) & 3;
-    const int pitch = is_luma ? W : (W >> 1);
-    const int bx = is_luma ? blk_x(lane) : (cblk & 1) * 4, by = is_luma ? blk_y(lane) : (cblk >> 1) * 4;
-    const int off = is_luma ? (mby * 16 + by) * W + mbx * 16 + bx : (mby * 8 + by) * pitch + mbx * 8 + bx;
-    const uint8_t* s = plane == 0 ? src_y : (plane == 1 ? src_u : src_v);
-    const uint8_t* p = plane == 0 ? pred_y : (plane == 1 ? pred_u : pred_v);
-    uint8_t* r = plane == 0 ? rec_y : (plane == 1 ? rec_u : rec_v);
-    const QuantK& qk = s_qk[is_luma ? 0 : 1];
-
-    Rows4 sv, pv;
-    int m[16], lv[16];
-    bool res_nz = false;
-    if (is_luma || is_chroma) {
+    __syncthreads();
+    const size_t po = blockIdx.y * stride;
+    coeffs += (size_t)blockIdx.y * nmb;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x < luma_ctas) {
+        // ---------------- luma: t = macroblock * 16 + luma4x4BlkIdx ----------------
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = t < nmb * 16;
+        const int mb = valid ? t >> 4 : 0, b = t & 15, mbx = mb % mbw, mby = mb / mbw;
+        const size_t off = po + (size_t)(mby * 16 + blk_y(b)) * W + mbx * 16 + blk_x(b);
+        Rows4 sv, pv;
+        bool res_nz = false;
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-            sv.r[y] = __ldg(reinterpret_cast<const uint32_t*>(s + off + y * pitch));
-            pv.r[y] = __ldg(reinterpret_cast<const uint32_t*>(p + off + y * pitch));
+            sv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(src_y + off + (size_t)y * W)) : 0u;
+            pv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(pred_y + off + (size_t)y * W)) : 0u;
             res_nz |= sv.r[y] != pv.r[y];
         }
-    } else {
+        int m[16];
+        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+        Rows4 rec = pv;
+        bool coded = false;
+        if (res_nz) {
+            fast_fwd_transform(sv, pv, m);
+            fast_quant(m, K.luma);
+            uint32_t any = 0;
 #pragma unroll
-        for (int y = 0; y < 4; ++y) sv.r[y] = pv.r[y] = 0;
+            for (int i = 0; i < 16; ++i) any |= (uint32_t)m[i];
+            coded = any != 0;
+            if (coded) {
+                // kZigzag = 0 1 4 8 | 5 2 3 6 | 9 12 13 10 | 7 11 14 15
+                o0 = make_uint4(pair16(m[0], m[1]), pair16(m[4], m[8]), pair16(m[5], m[2]), pair16(m[3], m[6]));
+                o1 = make_uint4(pair16(m[9], m[12]), pair16(m[13], m[10]), pair16(m[7], m[11]), pair16(m[14], m[15]));
+                fast_dequant_inverse(m, K.luma, false);
+                rec = fast_recon_clip(pv, m);
+            }
+        }
+        uint2 P[4] = {make_uint2(o0.x, o0.y), make_uint2(o0.z, o0.w), make_uint2(o1.x, o1.y), make_uint2(o1.z, o1.w)};
+        transpose4_u2(P, lane);   // all 32 lanes take part (nmb * 16 is a multiple of 4: a group of four lanes is valid or invalid as a whole)
+        if (valid) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t*>(rec_y + off + (size_t)y * W) = rec.r[y];
+            uint2* o = reinterpret_cast<uint2*>(coeffs[mb].luma_level[b & ~3]) + (b & 3);   // the structure is 792 bytes: 8-byte alignment is all it guarantees
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k * 4] = P[k];   // piece (b & 3) of block (b & ~3) + k
+        }
+        const unsigned lb = __ballot_sync(full, valid && coded);
+        if (valid && b == 0) coeffs[mb].cbp_luma4x4 = (uint16_t)((lb >> (lane & 16)) & 0xffffu);
+        return;
     }
+    // ---------------- chroma: t = macroblock * 8 + plane * 4 + block (raster) ----------------
+    const int t = ((int)blockIdx.x - luma_ctas) * blockDim.x + threadIdx.x;
+    const bool valid = t < nmb * 8;
+    const int mb = valid ? t >> 3 : 0, plane = (t >> 2) & 1, cblk = t & 3, mbx = mb % mbw, mby = mb / mbw, Wc = W >> 1;
+    const size_t off = po + (size_t)(mby * 8 + (cblk >> 1) * 4) * Wc + mbx * 8 + (cblk & 1) * 4;
+    const uint8_t* s = plane ? src_v : src_u;
+    const uint8_t* p = plane ? pred_v : pred_u;
+    uint8_t* r = plane ? rec_v : rec_u;
+    Rows4 sv, pv;
+    bool res_nz = false;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { lv[i] = 0; m[i] = 0; }
-
-    int dc_coef = 0;     // chroma: pre-quant W00 (rdo.c:2591)
-    bool coded = false;  // luma: CBP4x4 bit; chroma: AC bit
+    for (int y = 0; y < 4; ++y) {
+        sv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(s + off + (size_t)y * Wc)) : 0u;
+        pv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(p + off + (size_t)y * Wc)) : 0u;
+        res_nz |= sv.r[y] != pv.r[y];
+    }
+    int m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = 0;
+    int dc_coef = 0;   // pre-quantisation W00 (rdo.c:2591)
     if (res_nz) {
         fast_fwd_transform(sv, pv, m);
         dc_coef = m[0];
-        fast_quant(m, qk);
-        zigzag4x4(m, lv);
-        const uint32_t mask = level_mask16(lv);
-        coded = (is_luma ? mask : (mask & ~1u)) != 0;
+        fast_quant(m, K.chroma);
     }
-    if (!is_chroma) dc_coef = 0;
-
-    // ---- chroma: single-coefficient elimination + 2x2 DC (rdo.c:2599-2672) ----
+    // single-coefficient elimination over the plane's four blocks (rdo.c:2599-2625): AC levels only
     int nnz_ac = 0, big = 0;
-    if (is_chroma) {
 #pragma unroll
-        for (int i = 1; i < 16; ++i) { nnz_ac += (lv[i] != 0); big |= (iabs(lv[i]) > 1); }
-    }
-    const unsigned full = 0xffffffffu;
-    const int base = 16 + ((lane >= 20) ? 4 : 0);  // first lane of my chroma plane (for lanes >= 16)
-    int tot = 0, anybig = 0, dcs[4];
+    for (int i = 1; i < 16; ++i) { nnz_ac += (m[i] != 0); big |= (m[i] > 1) | (m[i] < -1); }
+    const int base = lane & ~3;
+    int tot = 0, anybig = 0, dcl[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int src_lane = is_chroma ? base + k : lane;
-        tot += __shfl_sync(full, nnz_ac, src_lane);
-        anybig |= __shfl_sync(full, big, src_lane);
-        dcs[k] = __shfl_sync(full, dc_coef, src_lane);
+        tot += __shfl_sync(full, nnz_ac, base + k);
+        anybig |= __shfl_sync(full, big, base + k);
+        dcl[k] = __shfl_sync(full, dc_coef, base + k);
     }
-    const unsigned ac_ballot = __ballot_sync(full, is_chroma && coded);
-    unsigned ac_mask = is_chroma ? ((ac_ballot >> base) & 15u) : 0u;  // CodedBlockPatternChromaAC4x4 of my plane
-    if (is_chroma && tot == 1 && !anybig) ac_mask = 0;                // exactly one +-1 AC coefficient in the plane
-    const bool dc_tent = is_chroma && (dcs[0] | dcs[1] | dcs[2] | dcs[3]) != 0;
-    int dcl[4] = {0, 0, 0, 0};
+    const unsigned ac_ballot = __ballot_sync(full, nnz_ac != 0);
+    unsigned ac_mask = (ac_ballot >> base) & 15u;   // CodedBlockPatternChromaAC4x4 of my plane
+    if (tot == 1 && !anybig) ac_mask = 0;           // exactly one +-1 AC coefficient in the plane
     unsigned dc_mask = 0;
-    int dcr[4] = {0, 0, 0, 0};
-    if (dc_tent) {
-        dcl[0] = dcs[0]; dcl[1] = dcs[1]; dcl[2] = dcs[2]; dcl[3] = dcs[3];
+    int mydc = 0;
+    if ((dcl[0] | dcl[1] | dcl[2] | dcl[3]) != 0) {
         hadamard2x2(dcl);
-        quant_dc(dcl, 4, qpc, /*isIntra(MB)*/ false);  // DC uses the MB's own intra flag: inter here (rdo.c:2660)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dc_mask |= (dcl[k] != 0) << k;
-        if (dc_mask) {  // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dcr[k] = dcl[k];
+        for (int k = 0; k < 4; ++k) {
+            const int w = dcl[k], z = (iabs(w) * K.dc_mf + K.dc_f2) >> K.dc_qbits1;
+            dcl[k] = w >= 0 ? z : -z;
+            dc_mask |= (unsigned)(dcl[k] != 0) << k;
+        }
+        if (dc_mask) {   // transf.c:612: f = H.c.H ; dcC = ((f*LS00) << (qP/6)) >> 5
+            int dcr[4] = {dcl[0], dcl[1], dcl[2], dcl[3]};
             hadamard2x2(dcr);
-            const int ls = 16 * kNormAdjust[qpc % 6][0];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dcr[k] = ((dcr[k] * ls) << (qpc / 6)) >> 5;
+            const int f = cblk == 0 ? dcr[0] : (cblk == 1 ? dcr[1] : (cblk == 2 ? dcr[2] : dcr[3]));
+            mydc = ((f * K.dc_ls) << K.dc_q6) >> 5;
         }
-    }
-
-    // ---- reconstruction ----
-    bool use_res;
-    int c[16];
-    if (is_luma) {
-        use_res = coded;
-        inv_zigzag4x4(lv, c);
-    } else {
-        const int mydc = dcr[cblk];
-        use_res = is_chroma && (mydc != 0 || ((ac_mask >> cblk) & 1));  // transf.c:236: AC levels are used whenever the DC is non-zero
-        int l2[16];
-        l2[0] = mydc;
-#pragma unroll
-        for (int i = 1; i < 16; ++i) l2[i] = lv[i];
-        inv_zigzag4x4(l2, c);
-    }
+    } else { dcl[0] = dcl[1] = dcl[2] = dcl[3] = 0; }
+    // levels as the reference leaves them (before the elimination decision; position 0 of the 15-entry AC list = zig-zag index 1)
+    const uint4 o0 = make_uint4(pair16(m[1], m[4]), pair16(m[8], m[5]), pair16(m[2], m[3]), pair16(m[6], m[9]));
+    const uint4 o1 = make_uint4(pair16(m[12], m[13]), pair16(m[10], m[7]), pair16(m[11], m[14]), pair16(m[15], 0));
     Rows4 rec = pv;
-    if (use_res) {
-        fast_dequant_inverse(c, qk, /*keep_dc*/ !is_luma);
-        rec = fast_recon_clip(pv, c);
+    if (mydc != 0 || ((ac_mask >> cblk) & 1)) {   // transf.c:236: AC levels are used whenever the DC is non-zero
+        m[0] = mydc;
+        fast_dequant_inverse(m, K.chroma, /*keep_dc*/ true);
+        rec = fast_recon_clip(pv, m);
     }
-    if (is_luma || is_chroma) {
+    uint2 P[4] = {make_uint2(o0.x, o0.y), make_uint2(o0.z, o0.w), make_uint2(o1.x, o1.y), make_uint2(o1.z, o1.w)};
+    transpose4_u2(P, lane);
+    if (valid) {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t*>(r + off + y * pitch) = rec.r[y];
-    }
-
-    // ---- outputs ----
-    if (is_luma) {
-        int16_t* o = out->luma_level[lane];
+        for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t*>(r + off + (size_t)y * Wc) = rec.r[y];
+        uint2* o = reinterpret_cast<uint2*>(coeffs[mb].chroma_ac_level[plane][0]) + cblk;
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) *reinterpret_cast<uint32_t*>(o + i) = (uint32_t)(uint16_t)(coded ? lv[i] : 0) | ((uint32_t)(uint16_t)(coded ? lv[i + 1] : 0) << 16);
-    } else if (is_chroma) {
-        int16_t* o = out->chroma_ac_level[plane - 1][cblk];
-#pragma unroll
-        for (int i = 0; i < 15; ++i) o[i] = (int16_t)lv[i + 1];
-        o[15] = 0;
+        for (int k = 0; k < 4; ++k) o[k * 4] = P[k];
         if (cblk == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out->chroma_dc_level[plane - 1][k] = (int16_t)dcl[k];
-            out->cbp_chroma_dc4x4[plane - 1] = (uint8_t)dc_mask;
-            out->cbp_chroma_ac4x4[plane - 1] = (uint8_t)ac_mask;
+            *reinterpret_cast<uint2*>(coeffs[mb].chroma_dc_level[plane]) = make_uint2(pair16(dcl[0], dcl[1]), pair16(dcl[2], dcl[3]));
+            coeffs[mb].cbp_chroma_dc4x4[plane] = (uint8_t)dc_mask;
+            coeffs[mb].cbp_chroma_ac4x4[plane] = (uint8_t)ac_mask;
         }
     }
-    const unsigned lb = __ballot_sync(full, is_luma && coded);
-    if (lane == 0) out->cbp_luma4x4 = (uint16_t)(lb & 0xffffu);
 }
 
 // ---------------- SVC enhancement-layer inter macroblock (base mode): prediction + residual coding + reconstruction, one warp per MB -----------
@@ -472,9 +501,11 @@ int hlb200_dev_tq_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, co
 {
     if (!d_src_y || !d_pred_y || !d_coeffs || !d_recon_y || (width & 15) || (height & 15) || qp < 0 || qp > 51 || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_tq_recon<<<dim3((nmb * 32 + 127) / 128, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, mbw, nmb, qp,
-                                                                                            host_chroma_qp(qp, chroma_qp_index_offset), d_coeffs, d_recon_y, d_recon_u, d_recon_v,
-                                                                                            frame_stride);
+    if (!d_src_u || !d_src_v || !d_pred_u || !d_pred_v || !d_recon_u || !d_recon_v) return HLB200_ERR_INVALID_PARAMETER;
+    const int luma_ctas = (nmb * 16 + 127) / 128, chroma_ctas = (nmb * 8 + 127) / 128;
+    k_tq_recon<<<dim3(luma_ctas + chroma_ctas, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, mbw, nmb, qp,
+                                                                                             host_chroma_qp(qp, chroma_qp_index_offset), d_coeffs, d_recon_y, d_recon_u, d_recon_v,
+                                                                                             frame_stride, luma_ctas);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }

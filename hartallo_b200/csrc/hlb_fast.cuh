@@ -238,6 +238,76 @@ template <class LD> HLB_HD Rows4 fast_pred_luma_t(const uint32_t* t, int pw, int
     }
     return o;
 }
+// The same prediction written as predicated STAGES instead of one branch per fractional class, for callers whose lanes hold blocks of different classes
+// (the whole-picture kernel k_interp_luma: every 4x4 block of a warp may carry its own vector).  Every class is avg(X, Y) of two of {G integer samples,
+// b horizontal half samples of row y / y+1, h vertical half samples of column x / x+1, j centre half samples} (8.4.2.2.1, Table 8-12; X = Y for the
+// positions that are one of them), so a warp runs at most: the horizontal tap rows (4, or all 9 when a lane needs j), the vertical pass over them, the
+// vertical half samples, the integer rows and one select + average -- about 550 instructions however mixed its lanes are, against the sum of all
+// sixteen branches of fast_pred_luma_t (measured 1,930 per warp on a random motion field).  Bit-exact with fast_pred_luma_t (tools/emu/check_fast.cpp).
+template <class LD> HLB_HD Rows4 fast_pred_luma_staged(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
+{
+    const bool sB = xf != 0 && yf != 2, sH = yf != 0 && xf != 2, sJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
+    const bool isG = (xf == 0 || yf == 0) && (((xf | yf) & 1) != 0 || (xf | yf) == 0);
+    Rows4 B, H, J, G;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) B.r[r] = H.r[r] = J.r[r] = G.r[r] = 0;
+    if (sB || sJ) {
+        const bool lower = yf == 3;   // b of row y+1 (positions p q r) instead of row y
+        int w[9][4];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0;
+            if (sJ || (r >= 2 && r <= 6 && (r != 2 || !lower) && (r != 6 || lower))) {
+                uint32_t R0, R1, R2;
+                tile_row9<LD>(t, pw, ty - 2 + r, tx - 2, R0, R1, R2);
+                hrow_taps(R0, R1, R2, 0, w[r][0], w[r][1], w[r][2], w[r][3]);
+            }
+        }
+        if (sB) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int v[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) v[x] = ((lower ? w[3 + k][x] : w[2 + k][x]) + 16) >> 5;
+                B.r[k] = pack4_sat(v[0], v[1], v[2], v[3]);
+            }
+        }
+        if (sJ) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int v[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) v[x] = (w[k][x] + w[k + 5][x] + 512 - 5 * (w[k + 1][x] + w[k + 4][x]) + 20 * (w[k + 2][x] + w[k + 3][x])) >> 10;
+                J.r[k] = pack4_sat(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+    if (sH) {
+        const int cx = tx + (xf == 3 ? 1 : 0);
+        uint32_t lo[9], hi[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t v = tile_row4<LD>(t, pw, ty - 2 + r, cx);
+            lo[r] = exp_lo(v); hi[r] = exp_hi(v);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            H.r[r] = p_prmt(vtap_pair(lo[r], lo[r + 1], lo[r + 2], lo[r + 3], lo[r + 4], lo[r + 5]), vtap_pair(hi[r], hi[r + 1], hi[r + 2], hi[r + 3], hi[r + 4], hi[r + 5]), 0x6420);
+    }
+    if (isG) {
+        const int gx = tx + (xf == 3 ? 1 : 0), gy = ty + (yf == 3 ? 1 : 0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) G.r[r] = tile_row4<LD>(t, pw, gy + r, gx);
+    }
+    Rows4 o;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t X = sB ? B.r[r] : (sH ? H.r[r] : (sJ ? J.r[r] : G.r[r]));
+        const uint32_t Y = sJ ? J.r[r] : ((sB && sH) ? H.r[r] : (isG ? G.r[r] : X));
+        o.r[r] = p_avg4(X, Y);
+    }
+    return o;
+}
 // the shared-memory tile of the slice kernel (one out-of-line copy there, see hlb_slice.cu)
 HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
 {

@@ -45,6 +45,10 @@ int main()
                 ++n;
                 for (int i = 0; i < 16; ++i)
                     if (a[i] != (uint8_t)(b.r[i >> 2] >> (8 * (i & 3)))) { if (bad < 10) printf("pred mismatch tx %d ty %d xf %d yf %d px %d: %d vs %d\n", tx, ty, xf, yf, i, a[i], (b.r[i >> 2] >> (8 * (i & 3))) & 255); ++bad; break; }
+                const Rows4 c = fast_pred_luma_staged<LdPlain>((const uint32_t*)tile, 12, tx, ty, xf, yf);   // the whole-picture kernel's formulation
+                ++n;
+                for (int r = 0; r < 4; ++r)
+                    if (c.r[r] != b.r[r]) { if (bad < 10) printf("staged pred mismatch tx %d ty %d xf %d yf %d row %d: %08x vs %08x\n", tx, ty, xf, yf, r, c.r[r], b.r[r]); ++bad; break; }
             }
     }
     // ---- trial encode ----
