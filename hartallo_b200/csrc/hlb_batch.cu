@@ -78,31 +78,7 @@ __global__ void __launch_bounds__(256) k_interp_luma(const uint8_t* __restrict__
 // (8 luma samples wide: one motion vector unless the macroblock is split into 4-wide sub-partitions, then two).  Written as ONE control flow for both cases:
 // every thread forms its two sample pairs from their own vectors (equal in the common case), so warps that straddle macroblocks of different partition layouts
 // do not run the two variants one after the other (the first packed version did: 360 warp instructions per thread, 17 of 32 lanes active on average).
-// Interior: two rows of the reference fetched as aligned words + funnel shift, the 1/8-pel bilinear sample as two byte dot products
-// (weights (8-xf)(8-yf), xf(8-yf) | (8-xf)yf, xf yf).
-__device__ __forceinline__ uint32_t chroma_two(const uint8_t* __restrict__ rp, int Wc, int Hc, int x0, int y0, int xf, int yf)
-{
-    // samples (x0, y0), (x0 + 1, y0) of the prediction; returned in the two low bytes
-    const uint32_t wa = (uint32_t)((8 - xf) * (8 - yf)) | ((uint32_t)(xf * (8 - yf)) << 8), wc = (uint32_t)((8 - xf) * yf) | ((uint32_t)(xf * yf) << 8);
-    uint32_t a, c;   // three samples of row y0 / y0 + 1 starting at x0
-    if (x0 >= 0 && y0 >= 0 && y0 + 1 < Hc && (x0 >> 2) + 1 < (Wc >> 2)) {
-        const uint32_t* ra = reinterpret_cast<const uint32_t*>(rp + (size_t)y0 * Wc) + (x0 >> 2);
-        const uint32_t* rc = ra + (Wc >> 2);
-        const uint32_t sh = (uint32_t)(x0 & 3) * 8;
-        a = p_shf_r(__ldg(ra), __ldg(ra + 1), sh); c = p_shf_r(__ldg(rc), __ldg(rc + 1), sh);
-    } else {
-        const uint8_t* ra = rp + (size_t)clip3(0, Hc - 1, y0) * Wc;
-        const uint8_t* rc = rp + (size_t)clip3(0, Hc - 1, y0 + 1) * Wc;
-        a = c = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int x = clip3(0, Wc - 1, x0 + i);
-            a |= (uint32_t)__ldg(ra + x) << (8 * i); c |= (uint32_t)__ldg(rc + x) << (8 * i);
-        }
-    }
-    const int v0 = p_dp4a_us(c, wc, p_dp4a_us(a, wa, 32)) >> 6, v1 = p_dp4a_us(c >> 8, wc, p_dp4a_us(a >> 8, wa, 32)) >> 6;
-    return (uint32_t)v0 | ((uint32_t)v1 << 8);
-}
+// The sample pairs come from fast_chroma_two (hlb_fast.cuh).
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
                                                        const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride)
 {
@@ -121,7 +97,7 @@ __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict
     const uint32_t* mv = reinterpret_cast<const uint32_t*>(&m->mv[part][0][0]);
     const uint32_t vl = __ldg(mv + sub_l), vr = __ldg(mv + sub_r);
     const int lx = (int)(int16_t)(vl & 0xffffu), ly = (int)vl >> 16, rx = (int)(int16_t)(vr & 0xffffu), ry = (int)vr >> 16;
-    const uint32_t out = chroma_two(rp, Wc, Hc, cx + (lx >> 3), cy + (ly >> 3), lx & 7, ly & 7) | (chroma_two(rp, Wc, Hc, cx + 2 + (rx >> 3), cy + (ry >> 3), rx & 7, ry & 7) << 16);
+    const uint32_t out = fast_chroma_two(rp, Wc, Hc, cx + (lx >> 3), cy + (ly >> 3), lx & 7, ly & 7) | (fast_chroma_two(rp, Wc, Hc, cx + 2 + (rx >> 3), cy + (ry >> 3), rx & 7, ry & 7) << 16);
     *reinterpret_cast<uint32_t*>(dst) = out;
 }
 

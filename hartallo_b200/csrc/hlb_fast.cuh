@@ -83,6 +83,7 @@ HLB_HD uint32_t p_addmin_relu_s16x2(uint32_t a, uint32_t b, uint32_t c)   // per
     return r;
 #endif
 }
+HLB_HD uint32_t pack16(int lo, int hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }   // two 16-bit levels per word
 HLB_HD uint32_t p_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }                       // per byte (a + b + 1) >> 1
 HLB_HD uint32_t p_add4_wrap(uint32_t a, uint32_t b) { return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u); }   // per byte (a + b) mod 256
 HLB_HD uint32_t pack4_sat(int v0, int v1, int v2, int v3) { return p_pack_sat_u8(v1, v0, p_pack_sat_u8(v3, v2, 0)); }         // clip255 of each, v0 in the low byte
@@ -313,6 +314,34 @@ HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, 
 {
     HLB_FASTPRED_SRC(t);
     return fast_pred_luma_t<LdPlain>(t, pw, tx, ty, xf, yf);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Chroma prediction (8.4.2.2.2, pred_inter.c:888-940, interpol.c:337-385): the two samples (x0, y0), (x0 + 1, y0) of a plane (pitch Wc, height Hc, a read-only
+// picture plane in global memory) at eighth-sample fraction (xf, yf), returned in the two low bytes.  Interior: two rows fetched as aligned words + funnel shift;
+// at the picture edge the reference's per-sample clamp.  The bilinear sample is two byte dot products (weights (8-xf)(8-yf), xf(8-yf) | (8-xf)yf, xf yf).
+// ------------------------------------------------------------------------------------------------------------------
+HLB_HD uint32_t fast_chroma_two(const uint8_t* rp, int Wc, int Hc, int x0, int y0, int xf, int yf)
+{
+    const uint32_t wa = (uint32_t)((8 - xf) * (8 - yf)) | ((uint32_t)(xf * (8 - yf)) << 8), wc = (uint32_t)((8 - xf) * yf) | ((uint32_t)(xf * yf) << 8);
+    uint32_t a, c;   // three samples of row y0 / y0 + 1 starting at x0
+    if (x0 >= 0 && y0 >= 0 && y0 + 1 < Hc && (x0 >> 2) + 1 < (Wc >> 2)) {
+        const uint32_t* ra = reinterpret_cast<const uint32_t*>(rp + (size_t)y0 * Wc) + (x0 >> 2);
+        const uint32_t* rc = ra + (Wc >> 2);
+        const uint32_t sh = (uint32_t)(x0 & 3) * 8;
+        a = p_shf_r(HLB_LDG(ra), HLB_LDG(ra + 1), sh); c = p_shf_r(HLB_LDG(rc), HLB_LDG(rc + 1), sh);
+    } else {
+        const uint8_t* ra = rp + (size_t)clip3(0, Hc - 1, y0) * Wc;
+        const uint8_t* rc = rp + (size_t)clip3(0, Hc - 1, y0 + 1) * Wc;
+        a = c = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int x = clip3(0, Wc - 1, x0 + i);
+            a |= (uint32_t)HLB_LDG(ra + x) << (8 * i); c |= (uint32_t)HLB_LDG(rc + x) << (8 * i);
+        }
+    }
+    const int v0 = p_dp4a_us(c, wc, p_dp4a_us(a, wa, 32)) >> 6, v1 = p_dp4a_us(c >> 8, wc, p_dp4a_us(a >> 8, wa, 32)) >> 6;
+    return (uint32_t)v0 | ((uint32_t)v1 << 8);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ struct FrameCtx {
     int early_term;                      // me_early_term_flag: homogeneous-block detection narrows the partition modes searched (rdo.c:889-935)
     double lambda;                       // lambda_mode = 0.852 * (1 << ((QP-12)/3)), slice.c:1766
     QuantK qk;                           // quantiser constants of the luma trial encodes (hlb_fast.cuh), derived from qp by frame_ctx_derive()
+    QuantK qkc;                          // chroma AC: QPC with the intra rounding offset whatever the macroblock is (rdo.c:2588)
     const uint8_t* src[3];
     uint8_t* cur[3];                     // reconstruction of the current picture (frame-store planes, pitch = W / W/2)
     const uint8_t* ref[HLB_ACTIVE_REFS][3];  // active list entries: the reference's slice headers always carry num_ref_idx_l0_active_minus1 = 0 (slice.c:289-291)
@@ -75,7 +76,7 @@ struct FrameCtx {
 };
 
 // fields derived from the others (host side, once per picture)
-inline void frame_ctx_derive(FrameCtx& f) { quantk_make(f.qk, f.qp); }
+inline void frame_ctx_derive(FrameCtx& f) { quantk_make(f.qk, f.qp); quantk_make(f.qkc, f.qpc, true); }
 
 // ---- partition geometry of the 7 search modes (rdo.c:711-809): 0 16x16, 1 16x8, 2 8x16, 3 8x8, 4 8x4, 5 4x8, 6 4x4 ----
 HLB_HD int mode_nparts(int m) { return m == 0 ? 1 : (m < 3 ? 2 : 4); }
@@ -210,7 +211,7 @@ struct MbWork {
     int16_t fin_mv[4][4][2];
     int8_t fin_ref[4];
     alignas(4) uint8_t pred_y[256];
-    uint8_t pred_c[2][64];
+    alignas(4) uint8_t pred_c[2][64];
     alignas(4) uint8_t rec_y[256];
     alignas(4) uint8_t rec_c[2][64];
     alignas(4) int16_t luma_level[16][16];
@@ -247,8 +248,8 @@ struct MbWork {
     int32_t q_dist[9];
     uint16_t q_bits[9];
     uint8_t q_nz[9], q_tc[9], q_t1[9], q_sc[9], q_ok[9], q_res0[9];
-    int16_t q_lv[9][16];
-    uint8_t q_pred[9][16];
+    alignas(4) int16_t q_lv[9][16];   // 32-bit accesses
+    alignas(4) uint8_t q_pred[9][16];
         };
     };
 };
@@ -984,16 +985,19 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) ((uint32_t*)w.pred_y)[((by + r) * 16 + bx) >> 2] = o.r[r];
-    } else if (lane < 16 + 128) {   // one chroma sample per lane: the four reference loads of all samples are in flight together
-        const int idx = lane - 16, c = idx >> 6, px = idx & 7, py = (idx >> 3) & 7;
+    } else if (lane < 16 + 32) {   // four chroma samples per lane (plane, row, half row): two sample pairs, each with the vector of its own (sub-)partition
+        const int g = lane - 16, c = g >> 4, py = (g >> 1) & 7, px = (g & 1) * 4;
         const int Wc = f.W >> 1, Hc = f.H >> 1;
-        int p, s, ox, oy;
-        fin_rect(w, px * 2, py * 2, p, s, ox, oy);
-        const uint8_t* rp = f.ref[w.fin_ref[p]][1 + c];
-        const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
-        const int x0 = w.mbx * 8 + px + (mvx >> 3), y0 = w.mby * 8 + py + (mvy >> 3);
-        const int xa = clip3(0, Wc - 1, x0), xb = clip3(0, Wc - 1, x0 + 1), ya = clip3(0, Hc - 1, y0) * Wc, yc = clip3(0, Hc - 1, y0 + 1) * Wc;
-        w.pred_c[c][py * 8 + px] = (uint8_t)interp_chroma_px(HLB_LDG(rp + ya + xa), HLB_LDG(rp + ya + xb), HLB_LDG(rp + yc + xa), HLB_LDG(rp + yc + xb), mvx & 7, mvy & 7);
+        uint8_t sm[4] = {(uint8_t)w.fin_sub[0], (uint8_t)w.fin_sub[1], (uint8_t)w.fin_sub[2], (uint8_t)w.fin_sub[3]};
+        uint32_t out = 0;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {   // rolled: this runs once per macroblock, its footprint in the instruction cache counts more than its instructions
+            int p, s;
+            part_at(w.fin_mode, sm, (px + 2 * h) * 2, py * 2, p, s);
+            const int mvx = w.fin_mv[p][s][0], mvy = w.fin_mv[p][s][1];
+            out |= fast_chroma_two(f.ref[w.fin_ref[p]][1 + c], Wc, Hc, w.mbx * 8 + px + 2 * h + (mvx >> 3), w.mby * 8 + py + (mvy >> 3), mvx & 7, mvy & 7) << (16 * h);
+        }
+        ((uint32_t*)w.pred_c[c])[(py * 8 + px) >> 2] = out;
     }
 }
 
@@ -1005,47 +1009,39 @@ HLB_FN void phase_recon_luma(MbWork& w, const FrameCtx& f, int lane)
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane >= 16) return;
     const int bx = blk_x(lane), by = blk_y(lane);
-    uint8_t sv[16], pv[16];
+    Rows4 sv, pv;
+    bool nz = false;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { sv[r * 4 + q] = w.src_y[(by + r) * 16 + bx + q]; pv[r * 4 + q] = w.pred_y[(by + r) * 16 + bx + q]; }
-    int rec[16];
+    for (int r = 0; r < 4; ++r) {
+        sv.r[r] = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2]; pv.r[r] = ((const uint32_t*)w.pred_y)[((by + r) * 16 + bx) >> 2];
+        nz |= sv.r[r] != pv.r[r];
+    }
+    Rows4 rec = pv;
     bool coded = false;
     if (!w.luma_skip_residual) {
-        int m[16], lv[16];
-        bool nz = false;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { m[i] = (int)sv[i] - (int)pv[i]; nz |= (m[i] != 0); }
+        uint32_t* lvw = (uint32_t*)w.luma_level[lane];
         if (nz) {
-            fwd_transform4x4(m);
-            quant4x4_ac(m, f.qp, false);
-            zigzag4x4(m, lv);
+            int m[16];
+            fast_fwd_transform(sv, pv, m);
+            fast_quant(m, f.qk);
+            uint32_t any = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) coded |= (lv[i] != 0);
+            for (int i = 0; i < 16; ++i) any |= (uint32_t)m[i];
+            coded = any != 0;
+            if (coded) {   // levels in zig-zag order (0 1 4 8 5 2 3 6 9 12 13 10 7 11 14 15), two per word
+                lvw[0] = pack16(m[0], m[1]); lvw[1] = pack16(m[4], m[8]); lvw[2] = pack16(m[5], m[2]); lvw[3] = pack16(m[3], m[6]);
+                lvw[4] = pack16(m[9], m[12]); lvw[5] = pack16(m[13], m[10]); lvw[6] = pack16(m[7], m[11]); lvw[7] = pack16(m[14], m[15]);
+                fast_dequant_inverse(m, f.qk, false);
+                rec = fast_recon_clip(pv, m);
+            }
         }
-        if (coded) {
+        if (!coded) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) w.luma_level[lane][i] = (int16_t)lv[i];
-            int c[16];
-            inv_zigzag4x4(lv, c);
-            dequant4x4(c, f.qp, false);
-            inv_transform4x4(c);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) rec[i] = clip255((int)pv[i] + c[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w.luma_level[lane][i] = 0;
+            for (int i = 0; i < 8; ++i) lvw[i] = 0;
         }
     }
-    if (!coded) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rec[i] = pv[i];
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) w.rec_y[(by + r) * 16 + bx + q] = (uint8_t)rec[r * 4 + q];
+    for (int r = 0; r < 4; ++r) ((uint32_t*)w.rec_y)[((by + r) * 16 + bx) >> 2] = rec.r[r];
     w.blk_coded[lane] = coded ? 1 : 0;   // gathered into cbp_luma4x4 by the master
 }
 
@@ -1059,30 +1055,31 @@ HLB_FN void phase_chroma_tq(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane >= 8) return;
-    const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
-    int m[16], lv[16];
+    const int c = lane >> 2, b = lane & 3, o4 = ((b >> 1) * 32 + (b & 1) * 4) >> 2;   // word offset of the block in the 8x8 plane
+    Rows4 sv, pv;
     bool nz = false;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { m[r * 4 + q] = (int)w.src_c[c][(y0 + r) * 8 + x0 + q] - (int)w.pred_c[c][(y0 + r) * 8 + x0 + q]; nz |= (m[r * 4 + q] != 0); }
+    for (int r = 0; r < 4; ++r) {
+        sv.r[r] = ((const uint32_t*)w.src_c[c])[o4 + 2 * r]; pv.r[r] = ((const uint32_t*)w.pred_c[c])[o4 + 2 * r];
+        nz |= sv.r[r] != pv.r[r];
+    }
     w.c_resnz[c][b] = nz ? 1 : 0;
     w.c_dccoef[c][b] = 0; w.c_acnz[c][b] = 0; w.c_sc[c][b] = 9; w.c_tc[c][b] = 0;
     if (!nz) return;
-    fwd_transform4x4(m);
+    uint32_t* acw = (uint32_t*)w.chroma_ac[c][b];   // ChromaACLevel[0..14] = zig-zag positions 1..15; element 15 is never written (kept from earlier pictures)
+    int m[16];
+    fast_fwd_transform(sv, pv, m);
     w.c_dccoef[c][b] = m[0];
-    quant4x4_ac(m, f.qpc, true);
-    zigzag4x4(m, lv);
-    bool acnz = false;
+    fast_quant(m, f.qkc);
+    // zig-zag 0 1 4 8 5 2 3 6 9 12 13 10 7 11 14 15: AC list = positions 1..15
+    int l16[16] = {m[1], m[4], m[8], m[5], m[2], m[3], m[6], m[9], m[12], m[13], m[10], m[7], m[11], m[14], m[15], 0};
 #pragma unroll
-    for (int i = 1; i < 16; ++i) { w.chroma_ac[c][b][i - 1] = (int16_t)lv[i]; acnz |= (lv[i] != 0); }
-    w.c_acnz[c][b] = acnz ? 1 : 0;
-    if (acnz) {
-        int l16[16];
-#pragma unroll
-        for (int i = 0; i < 15; ++i) l16[i] = lv[i + 1];
-        l16[15] = 0;
-        const CavlcInfo ci = cavlc_block_info(l16, 16, false);
+    for (int i = 0; i < 7; ++i) acw[i] = pack16(l16[2 * i], l16[2 * i + 1]);
+    w.chroma_ac[c][b][14] = (int16_t)l16[14];
+    const uint32_t mask = level_mask16(l16);
+    w.c_acnz[c][b] = mask ? 1 : 0;
+    if (mask) {
+        const CavlcInfo ci = cavlc_block_info16(l16, mask);
         w.c_sc[c][b] = ci.single_ctr; w.c_tc[c][b] = ci.total_coeff;
     }
 }
@@ -1090,9 +1087,12 @@ HLB_FN void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane != 0) return;
+    // one lane, once per macroblock: every loop stays rolled -- the footprint in the instruction cache matters more than the trip counts
     int single[2] = {0, 0}, totc[2] = {0, 0};
     w.cbp_ac[0] = w.cbp_ac[1] = w.cbp_dc[0] = w.cbp_dc[1] = 0;
+#pragma unroll 1
     for (int b = 0; b < 4; ++b)
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             if (w.c_resnz[c][b]) {
                 if (w.c_acnz[c][b]) w.cbp_ac[c] |= 1 << b;
@@ -1104,28 +1104,34 @@ HLB_FN void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
                 w.last_sctr = w.c_sc[c][b];
             }
         }
+#pragma unroll 1
     for (int c = 0; c < 2; ++c)
         if (single[c] < 7 && totc[c] == 1) w.cbp_ac[c] = 0;
-    if (w.cbp_dc[0] || w.cbp_dc[1]) {
-        for (int c = 0; c < 2; ++c)
-            if (w.cbp_dc[c]) {
-                int h[4] = {w.c_dccoef[c][0], w.c_dccoef[c][1], w.c_dccoef[c][2], w.c_dccoef[c][3]};
-                hadamard2x2(h);
-                quant_dc(h, 4, f.qpc, w.mb_is_intra != 0);
-                int mask = 0;
-                for (int k = 0; k < 4; ++k) { w.chroma_dc[c][k] = (int16_t)h[k]; mask |= (h[k] != 0) << k; }
-                w.cbp_dc[c] = mask;
-            }
-    }
-    // de-quantised DC per block (transf.c:612), parked in c_dccoef for the reconstruction lanes
+    // 2x2 DC: Hadamard, quantisation with the macroblock's own rounding offset (quant.c:150-189: qbits + 1, 2f, MF(0,0)), de-quantisation (transf.c:612:
+    // ((f * LevelScale(QPC % 6, 0, 0)) << (QPC / 6)) >> 5, with QuantK::dq_mul[0] = LevelScale << (QPC / 6 - 4) once QPC >= 24)
+    const int qb1 = f.qkc.qbits + 1, f2 = ((1 << f.qkc.qbits) / (w.mb_is_intra ? 3 : 6)) << 1, mf = f.qkc.mf[0], q6 = f.qkc.qbits - 15;
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         int d[4] = {0, 0, 0, 0};
         if (w.cbp_dc[c]) {
-            d[0] = w.chroma_dc[c][0]; d[1] = w.chroma_dc[c][1]; d[2] = w.chroma_dc[c][2]; d[3] = w.chroma_dc[c][3];
-            hadamard2x2(d);
-            const int ls = 16 * kNormAdjust[f.qpc % 6][0];
-            for (int k = 0; k < 4; ++k) d[k] = ((d[k] * ls) << (f.qpc / 6)) >> 5;
+            int h[4] = {w.c_dccoef[c][0], w.c_dccoef[c][1], w.c_dccoef[c][2], w.c_dccoef[c][3]};
+            hadamard2x2(h);
+            int mask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int z = (iabs(h[k]) * mf + f2) >> qb1;
+                h[k] = h[k] >= 0 ? z : -z;
+                w.chroma_dc[c][k] = (int16_t)h[k]; mask |= (h[k] != 0) << k;
+            }
+            w.cbp_dc[c] = mask;
+            if (mask) {
+                hadamard2x2(h);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const int v = h[k] * f.qkc.dq_mul[0]; d[k] = q6 >= 4 ? v >> 1 : (v << q6) >> 5; }
+            }
         }
+        // de-quantised DC per block, parked in c_dccoef for the reconstruction lanes
+#pragma unroll
         for (int k = 0; k < 4; ++k) w.c_dccoef[c][k] = d[k];
     }
 }
@@ -1133,28 +1139,21 @@ HLB_FN void phase_chroma_recon(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane >= 8) return;
-    const int c = lane >> 2, b = lane & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+    const int c = lane >> 2, b = lane & 3, o4 = ((b >> 1) * 32 + (b & 1) * 4) >> 2;
     const int dc = w.c_dccoef[c][b];
     const bool use = (w.cbp_dc[c] || w.cbp_ac[c]) && (dc != 0 || ((w.cbp_ac[c] >> b) & 1));
-    int r4[16];
+    Rows4 pv;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pv.r[r] = ((const uint32_t*)w.pred_c[c])[o4 + 2 * r];
+    Rows4 rec = pv;
     if (use) {
-        int l16[16], cc[16];
-        l16[0] = dc;
-#pragma unroll
-        for (int i = 1; i < 16; ++i) l16[i] = w.chroma_ac[c][b][i - 1];
-        inv_zigzag4x4(l16, cc);
-        dequant4x4(cc, f.qpc, true);
-        inv_transform4x4(cc);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r4[i] = cc[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r4[i] = 0;
+        const int16_t* e = w.chroma_ac[c][b];   // AC levels in zig-zag order back to raster positions
+        int m[16] = {dc, e[0], e[4], e[5], e[1], e[3], e[6], e[11], e[2], e[7], e[10], e[12], e[8], e[9], e[13], e[14]};
+        fast_dequant_inverse(m, f.qkc, /*keep_dc*/ true);
+        rec = fast_recon_clip(pv, m);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) w.rec_c[c][(y0 + r) * 8 + x0 + q] = (uint8_t)clip255((int)w.pred_c[c][(y0 + r) * 8 + x0 + q] + r4[r * 4 + q]);
+    for (int r = 0; r < 4; ++r) ((uint32_t*)w.rec_c[c])[o4 + 2 * r] = rec.r[r];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1448,7 +1447,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
                     x.sync();
                     if (x.lane() == 0) w.last_sctr = -2;   // "not written by the chroma pass"
                     x.sync();
-                    x.run(CMD_PRED_INTER, 144);
+                    x.run(CMD_PRED_INTER, 48);
                     chroma_code(x, w);
                     const int chroma_zero = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1], sctr_chroma = w.last_sctr;
                     x.sync();
@@ -1497,7 +1496,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
                 w.fin_ref[0] = 0; w.fin_mv[0][0][0] = best_mv[0][0][0]; w.fin_mv[0][0][1] = best_mv[0][0][1];
                 w.mb_is_intra = 0;
                 HLB_LAP(w, 8);
-                x.run(CMD_PRED_INTER, 144);
+                x.run(CMD_PRED_INTER, 48);
                 chroma_code(x, w);
                 b_pskip = !w.cbp_ac[0] && !w.cbp_ac[1] && !w.cbp_dc[0] && !w.cbp_dc[1];
                 HLB_LAP(w, 9);
@@ -1546,7 +1545,7 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
         w.cbp_luma4x4 = 0;
         kind = MBK_PSKIP; mb_type = 5;
     } else {
-        x.run(CMD_PRED_INTER, 144);
+        x.run(CMD_PRED_INTER, 48);
         w.luma_skip_residual = best_sctr < 6;
         x.run(CMD_RECON_LUMA, 16);
         w.cbp_luma4x4 = 0;

@@ -194,44 +194,48 @@ HLB_FN void i4_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
     const int mode = lane, blk = w.i4_blk, bx = blk_x(blk), by = blk_y(blk);
     w.q_ok[mode] = i4_mode_allowed(mode, w.p13) ? 1 : 0;
     if (!w.q_ok[mode]) return;
-    int pred[16], res[16], lv[16];
+    int pred[16];
     intra4x4_pred(mode, w.p13, pred);
+    // packed from here on (hlb_fast.cuh): the block as four words, the intra rounding offset (1/3) in the quantiser
+    Rows4 sv, pv;
     bool rnz = false;
+    uint32_t* qp4 = (uint32_t*)w.q_pred[mode];
+    uint32_t* lvw = (uint32_t*)w.q_lv[mode];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { res[r * 4 + c] = (int)w.src_y[(by + r) * 16 + bx + c] - pred[r * 4 + c]; rnz |= (res[r * 4 + c] != 0); }
+    for (int r = 0; r < 4; ++r) {
+        pv.r[r] = (uint32_t)pred[r * 4] | ((uint32_t)pred[r * 4 + 1] << 8) | ((uint32_t)pred[r * 4 + 2] << 16) | ((uint32_t)pred[r * 4 + 3] << 24);
+        sv.r[r] = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2];
+        rnz |= sv.r[r] != pv.r[r];
+        qp4[r] = pv.r[r];
+    }
     w.q_res0[mode] = rnz ? 0 : 1;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { w.q_pred[mode][i] = (uint8_t)pred[i]; w.q_lv[mode][i] = 0; }
+    for (int i = 0; i < 8; ++i) lvw[i] = 0;
     w.q_nz[mode] = 0; w.q_bits[mode] = 0; w.q_tc[mode] = 0; w.q_t1[mode] = 0; w.q_sc[mode] = 9; w.q_dist[mode] = 0;
     if (!rnz) return;
-    fwd_transform4x4(res);
-    quant4x4_ac(res, f.qp, true);
-    zigzag4x4(res, lv);
-    bool nz = false;
+    QuantK qi = f.qk;
+    qi.f_pos = (1 << qi.qbits) / 3; qi.f_neg = (1 << qi.qbits) - 1 - qi.f_pos;
+    int m[16];
+    fast_fwd_transform(sv, pv, m);
+    fast_quant(m, qi);
+    int lv[16];
+    zigzag4x4(m, lv);
+    const uint32_t mask = level_mask16(lv);
+    Rows4 rec = pv;
+    if (mask) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { nz |= (lv[i] != 0); w.q_lv[mode][i] = (int16_t)lv[i]; }
-    int r4[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r4[i] = 0;
-    if (nz) {
-        const CavlcInfo ci = cavlc_block_info(lv, 16, false);
+        for (int i = 0; i < 8; ++i) lvw[i] = pack16(lv[2 * i], lv[2 * i + 1]);
+        const CavlcInfo ci = cavlc_block_info16(lv, mask);
         w.q_nz[mode] = 1; w.q_bits[mode] = ci.bits_rest; w.q_tc[mode] = ci.total_coeff; w.q_t1[mode] = ci.trailing_ones; w.q_sc[mode] = ci.single_ctr;
-        inv_zigzag4x4(lv, r4);
-        dequant4x4(r4, f.qp, false);
-        inv_transform4x4(r4);
+        fast_dequant_inverse(m, qi, false);
+        rec = fast_recon_clip(pv, m);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) qp4[r] = rec.r[r];   // reconstruction of this mode (the prediction when nothing is coded)
     }
-    int dist = 0;
+    uint32_t dist = 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int u = clip255(pred[r * 4 + c] + r4[r * 4 + c]);
-            w.q_pred[mode][r * 4 + c] = (uint8_t)u;   // reconstruction of this mode (prediction when nothing is coded)
-            dist += iabs((int)w.src_y[(by + r) * 16 + bx + c] - u);
-        }
-    w.q_dist[mode] = dist;
+    for (int r = 0; r < 4; ++r) dist = p_sad4(sv.r[r], rec.r[r], dist);
+    w.q_dist[mode] = (int)dist;
 }
 HLB_HD void i4_commit_phase(MbWork& w, const FrameCtx& f, int lane) { (void)w; (void)f; (void)lane; }
 
@@ -316,37 +320,56 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
 #pragma unroll 1
         for (int blk = 0; blk < 16; ++blk) {
             const int bx = blk_x(blk), by = blk_y(blk);
-            w.p13[0] = intra_luma_at(w, f, bx - 1, by - 1);
+            // the 13 neighbouring samples, one per lane: [0] corner, [1..4] left column, [5..12] top row and top-right (pred_intra.c:325-461)
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) w.p13[1 + i] = intra_luma_at(w, f, bx - 1, by + i);
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) w.p13[5 + i] = (i > 3 && (blk == 3 || blk == 11)) ? HLB_NA : intra_luma_at(w, f, bx + i, by - 1);
-            // in-MB positions to the right of an uncoded area (blocks 5, 7, 13, 15) fall outside the macroblock => HLB_NA from intra_luma_at
-            if ((blk == 5) && 0) {}
-            if (w.p13[9] == HLB_NA && w.p13[10] == HLB_NA && w.p13[11] == HLB_NA && w.p13[12] == HLB_NA && w.p13[8] != HLB_NA) w.p13[9] = w.p13[10] = w.p13[11] = w.p13[12] = w.p13[8];
-            w.i4_blk = blk;
-            w.i4_mode[blk] = 2;
+            for (int i = x.lane(); i < 13; i += x.nlanes())
+                w.p13[i] = i == 0 ? intra_luma_at(w, f, bx - 1, by - 1) : (i < 5 ? intra_luma_at(w, f, bx - 1, by + i - 1) : ((i > 8 && (blk == 3 || blk == 11)) ? HLB_NA : intra_luma_at(w, f, bx + i - 5, by - 1)));
+            x.sync();
+            // in-MB positions to the right of an uncoded area (blocks 5, 7, 13, 15) fall outside the macroblock => HLB_NA from intra_luma_at; 8.3.1.2: substituted by p[3,-1]
+            if (w.p13[9] == HLB_NA && w.p13[10] == HLB_NA && w.p13[11] == HLB_NA && w.p13[12] == HLB_NA && w.p13[8] != HLB_NA) {
+                x.sync();
+                if (x.lane() == 0) w.p13[9] = w.p13[10] = w.p13[11] = w.p13[12] = w.p13[8];
+                x.sync();
+            }
+            if (x.lane() == 0) { w.i4_blk = blk; w.i4_mode[blk] = 2; }
+            x.sync();
             x.run(CMD_I4_EVAL, 9);
-#pragma unroll 1
-            for (int m = 0; m < 9; ++m) w.stat_intra += w.q_ok[m] ? 1u : 0u;
-            double min_cost = DBL_MAX, min_dist = 0;
-            int best_mode = 2, best_allzero = 1;
+            // The reference walks the nine modes in order (rdo.c:1903-2010): a mode whose prediction equals the source wins outright and ends the walk; every
+            // earlier mode that coded something leaves its TotalCoeff / Single_ctr behind (the last one stands); the cheapest mode wins, the first among equals.
+            // One mode per lane, three reductions.
             const int nC = luma_nc(w, w.tc, blk);
+            int first_res0 = 99, last_nz = -1, n_ok = 0;
 #pragma unroll 1
-            for (int mode = 0; mode < 9; ++mode) {
+            for (int mode = x.lane(); mode < 9; mode += x.nlanes()) {
                 if (!w.q_ok[mode]) continue;
-                if (w.q_res0[mode]) { min_cost = 0; min_dist = 0; best_mode = mode; best_allzero = 1; break; }
+                ++n_ok;
+                if (w.q_res0[mode] && mode < first_res0) first_res0 = mode;
+            }
+            first_res0 = x.reduce_min(first_res0);
+            n_ok = x.reduce_add(n_ok);
+            double mc = DBL_MAX;
+            int mi = 99;
+#pragma unroll 1
+            for (int mode = x.lane(); mode < 9; mode += x.nlanes()) {
+                if (!w.q_ok[mode] || mode >= first_res0) continue;
                 int bits = 0;
-                if (w.q_nz[mode]) {
-                    bits = w.q_bits[mode] + coeff_token_len(nC, w.q_tc[mode], w.q_t1[mode]);
-                    w.tc[blk] = w.q_tc[mode];
-                    w.last_sctr = w.q_sc[mode];
-                }
+                if (w.q_nz[mode]) { bits = w.q_bits[mode] + coeff_token_len(nC, w.q_tc[mode], w.q_t1[mode]); if (mode > last_nz) last_nz = mode; }
                 const double cost = (double)w.q_dist[mode] + (f.lambda * (double)bits);
-                if (cost < min_cost) { min_cost = cost; min_dist = w.q_dist[mode]; best_mode = mode; best_allzero = !w.q_nz[mode]; }
+                if (cost < mc) { mc = cost; mi = mode; }
+            }
+            last_nz = x.reduce_max(last_nz);
+            x.reduce_argmin(mc, mi);
+            double min_cost, min_dist;
+            int best_mode, best_allzero;
+            if (first_res0 < 99) { min_cost = 0; min_dist = 0; best_mode = first_res0; best_allzero = 1; }
+            else { min_cost = mc; min_dist = w.q_dist[mi]; best_mode = mi; best_allzero = !w.q_nz[mi]; }
+            x.sync();
+            if (x.lane() == 0) {
+                w.stat_intra += (unsigned)n_ok;
+                if (last_nz >= 0) { w.tc[blk] = w.q_tc[last_nz]; w.last_sctr = w.q_sc[last_nz]; }
+                w.i4_mode[blk] = (uint8_t)best_mode;
             }
             HLB_DBG("  I4 blk %d: mode %d cost %.4f dist %.0f nC %d\n", blk, best_mode, min_cost, min_dist, nC);
-            w.i4_mode[blk] = (uint8_t)best_mode;
             x.sync();
 #pragma unroll 1
             for (int i = x.lane(); i < 16; i += x.nlanes()) {
