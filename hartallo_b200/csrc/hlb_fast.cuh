@@ -313,7 +313,11 @@ template <class LD> HLB_HD Rows4 fast_pred_luma_staged(const uint32_t* t, int pw
 HLB_FASTPRED_FN Rows4 fast_pred_luma(const uint32_t* t, int pw, int tx, int ty, int xf, int yf)
 {
     HLB_FASTPRED_SRC(t);
+#ifdef HLB_PRED_STAGED   /* measured in the slice kernel: 4.99 M against 5.14 M macroblocks/s -- most search steps are integer-pel, where the per-class form is four word loads */
+    return fast_pred_luma_staged<LdPlain>(t, pw, tx, ty, xf, yf);
+#else
     return fast_pred_luma_t<LdPlain>(t, pw, tx, ty, xf, yf);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
