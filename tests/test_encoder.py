@@ -11,6 +11,7 @@ is present the reference is additionally run live on fresh seeds.
 import hashlib
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -182,6 +183,15 @@ def test_slice_encode_vs_live_reference():
         _, recon = enc.encode(fr[n], want_recon=True)
         assert np.array_equal(recon, ref[n]), n
     enc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not rt.have_driver(), reason="oracle/_ref/hl_ref_driver not built")
+def test_gpu_fuzz_vs_live_reference():
+    """tools/gpu_fuzz.py: random configurations (size, QP, range, generator, seed, max_ref_frame, early termination, deblocking), both kernel variants, against the
+    reference encoder run live on the box -- the 32-lane reductions of the search / intra decision have no CPU twin (the emulation harness runs one lane)"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_fuzz.py"), "16", "101"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout[-1500:]
 
 
 @pytest.mark.gpu
