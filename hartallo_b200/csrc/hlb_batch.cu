@@ -293,34 +293,226 @@ __global__ void __launch_bounds__(128, 10) k_tq_recon(const uint8_t* __restrict_
     }
 }
 
-// ---------------- SVC enhancement-layer inter macroblock (base mode): prediction + residual coding + reconstruction, one warp per MB -----------
-// lanes 0..15: luma4x4BlkIdx; lanes 16..19: Cb blocks; lanes 20..23: Cr blocks (24..31 idle); the per-lane phases live in hlb_svc.cuh (the same source runs on the
-// CPU in tools/emu/svc_emu.cpp).  The 2x2 chroma DC stage / elimination exchange goes through 56 bytes of shared memory per warp.
-// BL = true: I_BL macroblocks (enhancement-layer I pictures, hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301-461): P.ref_* are the prediction planes, no motion.
+// ---------------- SVC enhancement-layer macroblocks (base mode inter / I_BL): prediction + residual coding + reconstruction ------------------------------
+// Same organisation as k_tq_recon: the luma blocks (16 per macroblock) and the chroma blocks (8 per macroblock) of a picture are two index spaces served by
+// different CTAs of one launch, one thread per 4x4 block, the block in four packed registers, chroma planes exchanging through 4-lane shuffles.  On top of it:
+// the PREDICTION is formed in the kernel (BL = false: from the layer's reference picture with the inferred partitions / vectors, luma by the staged six-tap form
+// of hlb_fast.cuh, chroma by byte dot products; BL = true: P.ref_* are prediction planes) and the per-macroblock state the reference carries from picture to
+// picture (ChromaACLevel of blocks without residual, ChromaDCLevel of planes without DC) travels in / out through `state`.  The formulation checked against the
+// reference's trace on the CPU is the per-lane one of hlb_svc.cuh (tools/emu/svc_emu.cpp); this kernel is checked against the oracle and the golden
+// fixtures on the GPU (tests/test_svc_inter.py).  Round 1's kernel (one warp per macroblock on hlb_svc.cuh's phases) measured 0.056 of the HBM peak.
 template <bool BL>
 __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, int nmb, int qp, int qpc, const hlb200_mb_motion_t* __restrict__ motion,
-                                                         hlb200_svc_mb_state_t* __restrict__ state, hlb200_mb_coeffs_t* __restrict__ coeffs, size_t stride)
+                                                         hlb200_svc_mb_state_t* __restrict__ state, hlb200_mb_coeffs_t* __restrict__ coeffs, size_t stride, int luma_ctas)
 {
-    __shared__ SvcXchg xs[4];
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nmb) return;   // warp-uniform
-    {
-        const size_t o = blockIdx.y * stride;
-        P.src_y += o; P.src_u += o; P.src_v += o; P.ref_y += o; P.ref_u += o; P.ref_v += o; P.rec_y += o; P.rec_u += o; P.rec_v += o;
+    __shared__ TqConst K;
+    if (threadIdx.x < 2) quantk_device(threadIdx.x ? K.chroma : K.luma, threadIdx.x ? qpc : qp, true);   // luma too takes the intra offset here (rdo.c:1468)
+    if (threadIdx.x == 2) { K.dc_qbits1 = 16 + qpc / 6; K.dc_f2 = 0; K.dc_mf = kQuantMF[qpc % 6][0]; K.dc_ls = 16 * kNormAdjust[qpc % 6][0]; K.dc_q6 = qpc / 6; }
+    __syncthreads();
+    const size_t po = blockIdx.y * stride;
+    coeffs += (size_t)blockIdx.y * nmb; state += (size_t)blockIdx.y * nmb;
+    if (!BL) motion += (size_t)blockIdx.y * nmb;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, W = P.W, H = P.H;
+    if ((int)blockIdx.x < luma_ctas) {
+        // ---------------- luma: t = macroblock * 16 + luma4x4BlkIdx ----------------
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = t < nmb * 16;
+        const int mb = valid ? t >> 4 : 0, b = t & 15, mbx = mb % mbw, mby = mb / mbw, bx = blk_x(b), by = blk_y(b);
+        const size_t off = po + (size_t)(mby * 16 + by) * W + mbx * 16 + bx;
+        Rows4 sv, pv;
+        if (BL) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) pv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(P.ref_y + off + (size_t)y * W)) : 0u;
+        } else {
+            const SvcPredSrc ps = svc_pred_src(motion, mb, mbw);
+            const SvcPart g = svc_part_of(ps.m->part_mode, ps.m->sub_mode, bx, by);
+            const int mvx = ps.m->mv[g.part][g.sub][0], mvy = ps.m->mv[g.part][g.sub][1];
+            // the origin clip applies to the PARTITION origin (pred_inter.c:395-396)
+            const int X = clip3(-17, W + 17, ps.mbx * 16 + g.ox + (mvx >> 2)) + (bx - g.ox), Y = clip3(-17, H + 17, ps.mby * 16 + g.oy + (mvy >> 2)) + (by - g.oy);
+            const uint8_t* ref = P.ref_y + po;
+            if (X >= 2 && Y >= 2 && X + 7 <= W && Y + 7 <= H) pv = fast_pred_luma_staged<LdReadOnly>(reinterpret_cast<const uint32_t*>(ref), W >> 2, X, Y, mvx & 3, mvy & 3);
+            else {   // the window touches the picture edge: staged with the reference's per-sample clamp (interpol.c:108-131)
+                uint32_t win[9 * 3];
+#pragma unroll 1
+                for (int r = 0; r < 9; ++r) {
+                    const uint8_t* row = ref + (size_t)clip3(0, H - 1, Y - 2 + r) * W;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v |= (uint32_t)__ldg(row + clip3(0, W - 1, X - 2 + q * 4 + c)) << (8 * c);
+                        win[r * 3 + q] = v;
+                    }
+                }
+                pv = fast_pred_luma_staged<LdPlain>(win, 3, 2, 2, mvx & 3, mvy & 3);
+            }
+        }
+        bool res_nz = false;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            sv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(P.src_y + off + (size_t)y * W)) : 0u;
+            if (!valid) pv.r[y] = 0;
+            res_nz |= sv.r[y] != pv.r[y];
+        }
+        int m[16];
+        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;   // LumaLevel is cleared first (rdo.c:1453,1462)
+        Rows4 rec = pv;
+        bool coded = false;
+        if (res_nz) {
+            fast_fwd_transform(sv, pv, m);
+            fast_quant(m, K.luma);
+            uint32_t any = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) any |= (uint32_t)m[i];
+            coded = any != 0;
+            if (coded) {
+                o0 = make_uint4(pair16(m[0], m[1]), pair16(m[4], m[8]), pair16(m[5], m[2]), pair16(m[3], m[6]));
+                o1 = make_uint4(pair16(m[9], m[12]), pair16(m[13], m[10]), pair16(m[7], m[11]), pair16(m[14], m[15]));
+                fast_dequant_inverse(m, K.luma, false);
+                rec = fast_recon_clip(pv, m);
+            }
+        }
+        uint2 Pq[4] = {make_uint2(o0.x, o0.y), make_uint2(o0.z, o0.w), make_uint2(o1.x, o1.y), make_uint2(o1.z, o1.w)};
+        transpose4_u2(Pq, lane);
+        if (valid) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t*>(P.rec_y + off + (size_t)y * W) = rec.r[y];
+            uint2* o = reinterpret_cast<uint2*>(coeffs[mb].luma_level[b & ~3]) + (b & 3);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k * 4] = Pq[k];
+        }
+        const unsigned lb = __ballot_sync(full, valid && coded);
+        if (valid && b == 0) coeffs[mb].cbp_luma4x4 = (uint16_t)((lb >> (lane & 16)) & 0xffffu);
+        return;
     }
-    const size_t idx = (size_t)blockIdx.y * nmb + warp;
-    const int mbx = warp % mbw, mby = warp / mbw;
-    SvcPredSrc ps;
-    if (BL) { ps.m = nullptr; ps.mbx = mbx; ps.mby = mby; ps.inherited = false; }
-    else ps = svc_pred_src(motion + (size_t)blockIdx.y * nmb, warp, mbw);
-    hlb200_mb_coeffs_t& out = coeffs[idx];
-    hlb200_svc_mb_state_t& st = state[idx];
-    SvcXchg& X = xs[threadIdx.x >> 5];
-    SvcLane L;
-    if (lane < 24) svc_lane_a<BL>(P, mbx, mby, lane, ps, qp, qpc, st, L, X);
-    __syncwarp();
-    if (lane < 24) svc_lane_b(P, mbx, mby, lane, qp, qpc, BL || ps.inherited, st, L, X, out);
-    if (lane == 0) out.cbp_luma4x4 = (uint16_t)svc_luma_cbp(X);
+    // ---------------- chroma: t = macroblock * 8 + plane * 4 + block (raster) ----------------
+    const int t = ((int)blockIdx.x - luma_ctas) * blockDim.x + threadIdx.x;
+    const bool valid = t < nmb * 8;
+    const int mb = valid ? t >> 3 : 0, plane = (t >> 2) & 1, cblk = t & 3, mbx = mb % mbw, mby = mb / mbw, Wc = W >> 1, Hc = H >> 1;
+    const int bx = (cblk & 1) * 4, by = (cblk >> 1) * 4;
+    const size_t off = po + (size_t)(mby * 8 + by) * Wc + mbx * 8 + bx;
+    const uint8_t* s = plane ? P.src_v : P.src_u;
+    const uint8_t* refp = (plane ? P.ref_v : P.ref_u) + po;
+    uint8_t* r = plane ? P.rec_v : P.rec_u;
+    Rows4 sv, pv;
+    bool mb_intra = BL;   // the macroblock counts as intra in the 2x2 DC quantisation (rdo.c:2660): I_BL, or a macroblock with an inherited prediction
+    if (BL) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) pv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(refp - po + off + (size_t)y * Wc)) : 0u;
+    } else {
+        const SvcPredSrc ps = svc_pred_src(motion, mb, mbw);
+        mb_intra = ps.inherited;
+#pragma unroll 1
+        for (int y = 0; y < 4; ++y) {
+            uint32_t row = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x += 2) {   // a 2x2 chroma area is the smallest one with its own motion vector
+                const SvcPart g = svc_part_of(ps.m->part_mode, ps.m->sub_mode, (bx + x) * 2, (by + y) * 2);
+                const int mvx = ps.m->mv[g.part][g.sub][0], mvy = ps.m->mv[g.part][g.sub][1];
+                row |= fast_chroma_two(refp, Wc, Hc, ps.mbx * 8 + bx + x + (mvx >> 3), ps.mby * 8 + by + y + (mvy >> 3), mvx & 7, mvy & 7) << (8 * x);
+            }
+            pv.r[y] = row;
+        }
+    }
+    bool res_nz = false;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        sv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(s + off + (size_t)y * Wc)) : 0u;
+        if (!valid) pv.r[y] = 0;
+        res_nz |= sv.r[y] != pv.r[y];
+    }
+    // ChromaACLevel as the macroblock object holds it: 15 AC levels + the never-written [15]; kept from earlier pictures when the residual is zero
+    hlb200_svc_mb_state_t& st = state[mb];
+    uint32_t lvw[8];
+    {
+        const uint2* sp = reinterpret_cast<const uint2*>(st.chroma_ac_level[plane][cblk]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const uint2 v = valid ? sp[k] : make_uint2(0, 0); lvw[2 * k] = v.x; lvw[2 * k + 1] = v.y; }
+    }
+    int m[16];
+    int dc_coef = 0;
+    if (res_nz) {
+        fast_fwd_transform(sv, pv, m);
+        dc_coef = m[0];
+        fast_quant(m, K.chroma);
+        // Scan4x4_AC_C (utils.h:183): zig-zag positions 1..15 -> elements 0..14; element 15 keeps what it held
+        lvw[0] = pair16(m[1], m[4]); lvw[1] = pair16(m[8], m[5]); lvw[2] = pair16(m[2], m[3]); lvw[3] = pair16(m[6], m[9]);
+        lvw[4] = pair16(m[12], m[13]); lvw[5] = pair16(m[10], m[7]); lvw[6] = pair16(m[11], m[14]); lvw[7] = (lvw[7] & 0xffff0000u) | (uint32_t)(uint16_t)m[15];
+    }
+    // coded / counts look at all 16 elements of the list as it now stands (rdo.c:2599-2625 through the shared chroma function)
+    int nnz = 0, big = 0;
+    if (res_nz) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int lo = (int)(int16_t)(lvw[k] & 0xffffu), hi = (int)lvw[k] >> 16;
+            nnz += (lo != 0) + (hi != 0); big |= (lo > 1) | (lo < -1) | (hi > 1) | (hi < -1);
+        }
+    }
+    const bool coded = nnz != 0;
+    const int base = lane & ~3;
+    int tot = 0, anybig = 0, dcl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        tot += __shfl_sync(full, nnz, base + k);
+        anybig |= __shfl_sync(full, big, base + k);
+        dcl[k] = __shfl_sync(full, dc_coef, base + k);
+    }
+    const unsigned ac_ballot = __ballot_sync(full, coded);
+    unsigned ac_mask = (ac_ballot >> base) & 15u;
+    if (tot == 1 && !anybig) ac_mask = 0;   // exactly one +-1 AC coefficient in the plane: Single_ctr < 7 && TotalCoeffs == 1, rdo.c:2641-2649
+    unsigned dc_mask = 0;
+    int mydc = 0;
+    if ((dcl[0] | dcl[1] | dcl[2] | dcl[3]) != 0) {
+        hadamard2x2(dcl);
+        const int f2 = ((1 << (K.dc_qbits1 - 1)) / (mb_intra ? 3 : 6)) << 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int w = dcl[k], z = (iabs(w) * K.dc_mf + f2) >> K.dc_qbits1;
+            dcl[k] = w >= 0 ? z : -z;
+            dc_mask |= (unsigned)(dcl[k] != 0) << k;
+        }
+        if (dc_mask) {
+            int dcr[4] = {dcl[0], dcl[1], dcl[2], dcl[3]};
+            hadamard2x2(dcr);
+            const int f = cblk == 0 ? dcr[0] : (cblk == 1 ? dcr[1] : (cblk == 2 ? dcr[2] : dcr[3]));
+            mydc = ((f * K.dc_ls) << K.dc_q6) >> 5;
+        }
+    } else if (valid) {   // ChromaDCLevel keeps its old content (rdo.c:2653: not entered)
+        const uint2 v = *reinterpret_cast<const uint2*>(st.chroma_dc_level[plane]);
+        dcl[0] = (int)(int16_t)(v.x & 0xffffu); dcl[1] = (int)v.x >> 16; dcl[2] = (int)(int16_t)(v.y & 0xffffu); dcl[3] = (int)v.y >> 16;
+    }
+    Rows4 rec = pv;
+    if (mydc != 0 || ((ac_mask >> cblk) & 1)) {   // AC levels (possibly the stale ones) are used whenever the DC is non-zero (transf.c:236)
+        const int e0 = (int)(int16_t)(lvw[0] & 0xffffu), e1 = (int)lvw[0] >> 16, e2 = (int)(int16_t)(lvw[1] & 0xffffu), e3 = (int)lvw[1] >> 16;
+        const int e4 = (int)(int16_t)(lvw[2] & 0xffffu), e5 = (int)lvw[2] >> 16, e6 = (int)(int16_t)(lvw[3] & 0xffffu), e7 = (int)lvw[3] >> 16;
+        const int e8 = (int)(int16_t)(lvw[4] & 0xffffu), e9 = (int)lvw[4] >> 16, e10 = (int)(int16_t)(lvw[5] & 0xffffu), e11 = (int)lvw[5] >> 16;
+        const int e12 = (int)(int16_t)(lvw[6] & 0xffffu), e13 = (int)lvw[6] >> 16, e14 = (int)(int16_t)(lvw[7] & 0xffffu);
+        int c[16] = {mydc, e0, e4, e5, e1, e3, e6, e11, e2, e7, e10, e12, e8, e9, e13, e14};
+        fast_dequant_inverse(c, K.chroma, /*keep_dc*/ true);
+        rec = fast_recon_clip(pv, c);
+    }
+    uint2 Pq[4] = {make_uint2(lvw[0], lvw[1]), make_uint2(lvw[2], lvw[3]), make_uint2(lvw[4], lvw[5]), make_uint2(lvw[6], lvw[7])};
+    if (valid && res_nz) {   // state: the same fields, carried to the next picture of the layer (unchanged when the residual is zero)
+        uint2* sp = reinterpret_cast<uint2*>(st.chroma_ac_level[plane][cblk]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sp[k] = Pq[k];
+    }
+    transpose4_u2(Pq, lane);
+    if (valid) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t*>(r + off + (size_t)y * Wc) = rec.r[y];
+        uint2* o = reinterpret_cast<uint2*>(coeffs[mb].chroma_ac_level[plane][0]) + cblk;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k * 4] = Pq[k];
+        if (cblk == 0) {
+            const uint2 d = make_uint2(pair16(dcl[0], dcl[1]), pair16(dcl[2], dcl[3]));
+            *reinterpret_cast<uint2*>(coeffs[mb].chroma_dc_level[plane]) = d;
+            *reinterpret_cast<uint2*>(st.chroma_dc_level[plane]) = d;
+            coeffs[mb].cbp_chroma_dc4x4[plane] = (uint8_t)dc_mask;
+            coeffs[mb].cbp_chroma_ac4x4[plane] = (uint8_t)ac_mask;
+        }
+    }
 }
 
 // ---------------- SAD / SATD of every 4x4 block of two planes -------------------------------------------------------
@@ -504,9 +696,10 @@ static int launch_svc(bool bl, const uint8_t* d_src_y, const uint8_t* d_src_u, c
     SvcPlanes P;
     P.src_y = d_src_y; P.src_u = d_src_u; P.src_v = d_src_v; P.ref_y = d_ref_y; P.ref_u = d_ref_u; P.ref_v = d_ref_v;
     P.rec_y = d_recon_y; P.rec_u = d_recon_u; P.rec_v = d_recon_v; P.W = width; P.H = height;
-    const dim3 grid((nmb * 32 + 127) / 128, n_pics);
-    if (bl) k_svc_inter_recon<true><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, nullptr, d_state, d_coeffs, frame_stride);
-    else k_svc_inter_recon<false><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, d_motion, d_state, d_coeffs, frame_stride);
+    const int luma_ctas = (nmb * 16 + 127) / 128, chroma_ctas = (nmb * 8 + 127) / 128;
+    const dim3 grid(luma_ctas + chroma_ctas, n_pics);
+    if (bl) k_svc_inter_recon<true><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, nullptr, d_state, d_coeffs, frame_stride, luma_ctas);
+    else k_svc_inter_recon<false><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, d_motion, d_state, d_coeffs, frame_stride, luma_ctas);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
