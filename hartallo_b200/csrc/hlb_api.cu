@@ -334,7 +334,7 @@ int hlb200_tq_recon(hlb200_ctx_t* c, int qp, int chroma_qp_index_offset, const u
     const uint8_t* hp[3] = {pred_y, pred_u, pred_v};
     uint8_t* hr[3] = {recon_y, recon_u, recon_v};
     for (int p = 0; p < 3; ++p) if ((rc = h2d(c, c->d_pred[p], hp[p], plane_bytes(c, p)))) return rc;
-    if ((rc = hlb200_dev_tq_recon(c->d_src[0], c->d_src[1], c->d_src[2], c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, qp, chroma_qp_index_offset,
+    if ((rc = hlb200_dev_tq_recon(c->d_src_cur[0], c->d_src_cur[1], c->d_src_cur[2], c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, qp, chroma_qp_index_offset,
                                   (hlb200_mb_coeffs_t*)c->d_scratch, c->d_tmp[0], c->d_tmp[1], c->d_tmp[2], c->stream)))
         return rc;
     if ((rc = d2h(c, coeffs, c->d_scratch, sizeof(hlb200_mb_coeffs_t) * c->nmb))) return rc;
@@ -350,7 +350,7 @@ int hlb200_sad4x4(hlb200_ctx_t* c, const uint8_t* pred_y, int use_satd, int32_t*
     int rc = ensure_scratch(c, nb * sizeof(int32_t));
     if (rc) return rc;
     if ((rc = h2d(c, c->d_pred[0], pred_y, plane_bytes(c, 0)))) return rc;
-    if ((rc = hlb200_dev_sad4x4(c->d_src[0], c->d_pred[0], c->width, c->height, use_satd, (int32_t*)c->d_scratch, c->stream))) return rc;
+    if ((rc = hlb200_dev_sad4x4(c->d_src_cur[0], c->d_pred[0], c->width, c->height, use_satd, (int32_t*)c->d_scratch, c->stream))) return rc;
     if ((rc = d2h(c, out_per_blk, c->d_scratch, nb * sizeof(int32_t)))) return rc;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
     return HLB200_OK;
@@ -362,7 +362,7 @@ int hlb200_homogeneity8x8(hlb200_ctx_t* c, int32_t* out_per_blk)
     const size_t nb = (size_t)(c->width >> 3) * (c->height >> 3);
     int rc = ensure_scratch(c, nb * sizeof(int32_t));
     if (rc) return rc;
-    if ((rc = hlb200_dev_homogeneity8x8(c->d_src[0], c->width, c->height, (int32_t*)c->d_scratch, c->stream))) return rc;
+    if ((rc = hlb200_dev_homogeneity8x8(c->d_src_cur[0], c->width, c->height, (int32_t*)c->d_scratch, c->stream))) return rc;
     if ((rc = d2h(c, out_per_blk, c->d_scratch, nb * sizeof(int32_t)))) return rc;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
     return HLB200_OK;
@@ -384,7 +384,7 @@ int hlb200_me_cost(hlb200_ctx_t* c, int ref_slot, int qp, const hlb200_me_cand_t
     hlb200_me_cand_t* d_c = (hlb200_me_cand_t*)c->d_scratch;
     hlb200_me_cost_t* d_o = (hlb200_me_cost_t*)((char*)c->d_scratch + in_pad);
     if ((rc = h2d(c, d_c, cands, in_b))) return rc;
-    if ((rc = launch_me_cost(c->d_src[0], c->d_slot[ref_slot][0], c->width, c->height, qp, d_c, n, d_o, c->stream))) return rc;
+    if ((rc = launch_me_cost(c->d_src_cur[0], c->d_slot[ref_slot][0], c->width, c->height, qp, d_c, n, d_o, c->stream))) return rc;
     if ((rc = d2h(c, out, d_o, out_b))) return rc;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
     return HLB200_OK;

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, i
 #pragma unroll
             for (int y = 0; y < 4; ++y) pv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(P.ref_y + off + (size_t)y * W)) : 0u;
         } else {
-            const SvcPredSrc ps = svc_pred_src(motion, mb, mbw);
+            const SvcPredSrc ps = svc_pred_src(motion, mb, mbw, nmb);
             const SvcPart g = svc_part_of(ps.m->part_mode, ps.m->sub_mode, bx, by);
             const int mvx = ps.m->mv[g.part][g.sub][0], mvy = ps.m->mv[g.part][g.sub][1];
             // the origin clip applies to the PARTITION origin (pred_inter.c:395-396)
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, i
 #pragma unroll
         for (int y = 0; y < 4; ++y) pv.r[y] = valid ? __ldg(reinterpret_cast<const uint32_t*>(refp - po + off + (size_t)y * Wc)) : 0u;
     } else {
-        const SvcPredSrc ps = svc_pred_src(motion, mb, mbw);
+        const SvcPredSrc ps = svc_pred_src(motion, mb, mbw, nmb);
         mb_intra = ps.inherited;
 #pragma unroll 1
         for (int y = 0; y < 4; ++y) {

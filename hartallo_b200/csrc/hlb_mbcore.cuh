@@ -966,7 +966,9 @@ HLB_HD void fin_rect(const MbWork& w, int x, int y, int& part, int& sub, int& ox
 HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    if (lane < 16) {
+    // lanes 0..31: chroma (one round of a warp, its two dependent reference fetches per lane in flight together with everyone else's); lanes 32..47: luma
+    if (lane >= 32 && lane < 48) {
+        lane -= 32;
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
         int p, s, ox, oy;
         fin_rect(w, bx, by, p, s, ox, oy);
@@ -985,8 +987,8 @@ HLB_FN void phase_pred_inter(MbWork& w, const FrameCtx& f, int lane)
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) ((uint32_t*)w.pred_y)[((by + r) * 16 + bx) >> 2] = o.r[r];
-    } else if (lane < 16 + 32) {   // four chroma samples per lane (plane, row, half row): two sample pairs, each with the vector of its own (sub-)partition
-        const int g = lane - 16, c = g >> 4, py = (g >> 1) & 7, px = (g & 1) * 4;
+    } else if (lane < 32) {   // four chroma samples per lane (plane, row, half row): two sample pairs, each with the vector of its own (sub-)partition
+        const int g = lane, c = g >> 4, py = (g >> 1) & 7, px = (g & 1) * 4;
         const int Wc = f.W >> 1, Hc = f.H >> 1;
         uint8_t sm[4] = {(uint8_t)w.fin_sub[0], (uint8_t)w.fin_sub[1], (uint8_t)w.fin_sub[2], (uint8_t)w.fin_sub[3]};
         uint32_t out = 0;
@@ -1171,13 +1173,13 @@ HLB_FN void phase_load(MbWork& w, const FrameCtx& f, int lane)
         ((uint32_t*)w.src_c[c])[i & 15] = HLB_LDG((const uint32_t*)(f.src[1 + c] + (w.mby * 8 + r) * Wc + w.mbx * 8) + q);
     }
 }
-// arg0 bit 0: luma, bit 1: chroma
+// arg0 bit 0: luma, bit 1: chroma, bit 2: the luma reconstruction IS the prediction (P_Skip: no separate copy into rec_y)
 HLB_FN void phase_store(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane < 64 && (w.arg0 & 1)) {
         const int r = lane >> 2, q = lane & 3;
-        ((uint32_t*)(f.cur[0] + (w.mby * 16 + r) * f.W + w.mbx * 16))[q] = ((const uint32_t*)w.rec_y)[lane];
+        ((uint32_t*)(f.cur[0] + (w.mby * 16 + r) * f.W + w.mbx * 16))[q] = (w.arg0 & 4) ? ((const uint32_t*)w.pred_y)[lane] : ((const uint32_t*)w.rec_y)[lane];
     } else if (lane >= 64 && lane < 96 && (w.arg0 & 2)) {
         const int i = lane - 64, c = i >> 4, r = (i >> 1) & 7, q = i & 1, Wc = f.W >> 1;
         ((uint32_t*)(f.cur[1 + c] + (w.mby * 8 + r) * Wc + w.mbx * 8))[q] = ((const uint32_t*)w.rec_c[c])[i & 15];
@@ -1538,10 +1540,9 @@ HLB_FN void mb_encode_p(X& x, MbWork& w, const FrameCtx& f)
     }
     int kind, cbp_luma = 0, cbp_chroma = 0, cbp = 0, mb_type;
     if (b_pskip) {
-        // luma = prediction; chroma already reconstructed by the zero check
-        w.luma_skip_residual = 1;
-        x.run(CMD_RECON_LUMA, 16);
-        w.arg0 = 3; x.run(CMD_STORE, 96);
+        // luma = prediction (_hl_codec_264_rdo_mb_reconstruct_luma_pskip); chroma already reconstructed by the zero check.  Nothing reads rec_y / luma_level /
+        // blk_coded of a P_Skip macroblock afterwards (mb_commit writes no levels for it), so the samples go straight from the prediction to the picture.
+        w.arg0 = 7; x.run(CMD_STORE, 96);
         w.cbp_luma4x4 = 0;
         kind = MBK_PSKIP; mb_type = 5;
     } else {

@@ -133,12 +133,13 @@ HLB_HD void svc_load_pred4x4(const uint8_t* plane, int off, int pitch, uint8_t p
 // the 2x2 chroma DC quantisation (rdo.c:2660).  The host marks such a macroblock in hlb200_mb_motion_t::pad: pad[0] bit 0, pad[1..2] = address of the
 // macroblock whose prediction it inherits (traced: tag 10 of oracle/ref_driver.c; tests/test_svc_inter.py::test_stale_prediction_model).
 struct SvcPredSrc { int mbx, mby; const hlb200_mb_motion_t* m; bool inherited; };
-HLB_HD SvcPredSrc svc_pred_src(const hlb200_mb_motion_t* pic_motion, int mb, int mbw)
+HLB_HD SvcPredSrc svc_pred_src(const hlb200_mb_motion_t* pic_motion, int mb, int mbw, int nmb = 0x7fffffff)
 {
     SvcPredSrc s;
     const hlb200_mb_motion_t* m = pic_motion + mb;
     s.inherited = (m->pad[0] & 1) != 0;
-    const int from = s.inherited ? ((int)m->pad[1] | ((int)m->pad[2] << 8)) : mb;
+    int from = s.inherited ? ((int)m->pad[1] | ((int)m->pad[2] << 8)) : mb;
+    if (from >= nmb) { from = mb; s.inherited = false; }   // a 16-bit address outside the picture: caller error, never read out of bounds
     s.m = pic_motion + from; s.mbx = from % mbw; s.mby = from / mbw;
     return s;
 }
