@@ -1200,7 +1200,6 @@ HLB_HD int cmd_phases(int cmd)
     case CMD_TILE_FIX: return 2;
     case CMD_CHROMA: return 3;
     case CMD_I16_EVAL: return 2;
-    case CMD_I16_RATE: return 2;
     case CMD_I4_EVAL: return 2;
     default: return 1;
     }
@@ -1223,7 +1222,7 @@ HLB_FN void cmd_phase(MbWork& w, const FrameCtx& f, int cmd, int phase, int lane
         break;
     case CMD_STORE: phase_store(w, f, lane); break;
     case CMD_I16_EVAL: i16_phase(w, f, phase, lane); break;
-    case CMD_I16_RATE: i16_phase(w, f, phase + 2, lane); break;
+    case CMD_I16_RATE: i16_phase(w, f, 2, lane); break;
     case CMD_I16_RECON: i16_recon_phase(w, f, lane); break;
     case CMD_I4_EVAL: i4_phase(w, f, phase, lane); break;
     case CMD_I4_COMMIT: i4_commit_phase(w, f, lane); break;

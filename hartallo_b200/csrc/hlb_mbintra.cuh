@@ -71,109 +71,81 @@ struct I16Shared { I16Params q; };
 HLB_FN void i16_phase(MbWork& w, const FrameCtx& f, int phase, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    if (phase == 0) {
+    if (phase == 0) {   // prediction, residual, transform, AC quantisation (intra offset), CAVLC info of the AC list: packed formulation of hlb_fast.cuh
         if (lane >= 64) return;
         const int m = lane >> 4, blk = lane & 15;
         if (!w.t_mode_ok[m]) return;
         const int bx = blk_x(blk), by = blk_y(blk);
         I16Params q;
         q.dc = w.t_dcbits[0]; q.a = w.t_dcbits[1]; q.b = w.t_dcbits[2]; q.c = w.t_dcbits[3];  // parameters parked by the master
-        int res[16], lv[16];
+        Rows4 sv, pv;
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r) {
+            pv.r[r] = (uint32_t)i16_pred_px(m, w.p33, q, bx, by + r) | ((uint32_t)i16_pred_px(m, w.p33, q, bx + 1, by + r) << 8) |
+                      ((uint32_t)i16_pred_px(m, w.p33, q, bx + 2, by + r) << 16) | ((uint32_t)i16_pred_px(m, w.p33, q, bx + 3, by + r) << 24);
+            ((uint32_t*)w.t_pred[m])[((by + r) * 16 + bx) >> 2] = pv.r[r];
+            sv.r[r] = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2];
+        }
+        QuantK qi = f.qk;
+        qi.f_pos = (1 << qi.qbits) / 3; qi.f_neg = (1 << qi.qbits) - 1 - qi.f_pos;
+        int c[16];
+        fast_fwd_transform(sv, pv, c);
+        w.t_dcw[m][blk] = c[0];
+        fast_quant(c, qi);
+        uint32_t any = 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int pv = i16_pred_px(m, w.p33, q, bx + c, by + r);
-                w.t_pred[m][(by + r) * 16 + bx + c] = (uint8_t)pv;
-                res[r * 4 + c] = (int)w.src_y[(by + r) * 16 + bx + c] - pv;
-            }
-        fwd_transform4x4(res);
-        w.t_dcw[m][blk] = res[0];
-        quant4x4_ac(res, f.qp, true);
-        zigzag4x4(res, lv);
-        bool nz = false;
-        int l16[16];
+        for (int i = 0; i < 16; ++i) any |= (uint32_t)c[i];   // the block counts as non-zero when ANY of the 16 quantised values is (rdo.c:1640), the DC position included
+        // AC list = zig-zag positions 1..15 (0 1 4 8 5 2 3 6 9 12 13 10 7 11 14 15), element 15 = 0
+        int l16[16] = {c[1], c[4], c[8], c[5], c[2], c[3], c[6], c[9], c[12], c[13], c[10], c[7], c[11], c[14], c[15], 0};
+        uint32_t* acw = (uint32_t*)w.t_ac[m][blk];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) nz |= (lv[i] != 0);
-#pragma unroll
-        for (int i = 0; i < 15; ++i) { l16[i] = lv[i + 1]; w.t_ac[m][blk][i] = (int16_t)lv[i + 1]; }
-        l16[15] = 0; w.t_ac[m][blk][15] = 0;
-        const CavlcInfo ci = cavlc_block_info(l16, 16, false);
-        w.t_nz[m][blk] = nz ? 1 : 0; w.t_tc[m][blk] = ci.total_coeff; w.t_t1[m][blk] = ci.trailing_ones; w.t_sc[m][blk] = ci.single_ctr; w.t_bits[m][blk] = ci.bits_rest;
-    } else if (phase == 1) {  // luma DC of each mode: Hadamard (>>1), quantisation, scan (rdo.c:1667-1670)
+        for (int i = 0; i < 8; ++i) acw[i] = pack16(l16[2 * i], l16[2 * i + 1]);
+        const CavlcInfo ci = cavlc_block_info16(l16, level_mask16(l16));
+        w.t_nz[m][blk] = any ? 1 : 0; w.t_tc[m][blk] = ci.total_coeff; w.t_t1[m][blk] = ci.trailing_ones; w.t_sc[m][blk] = ci.single_ctr; w.t_bits[m][blk] = ci.bits_rest;
+    } else if (phase == 1) {  // luma DC of each mode: Hadamard (>>1), quantisation, scan (rdo.c:1667-1670); then its de-scaled form for the reconstruction (8.5.10, transf.c:498)
         if (lane >= 4 || !w.t_mode_ok[lane]) return;
         const int m = lane;
         int d[16], lv[16];
+#pragma unroll
         for (int blk = 0; blk < 16; ++blk) d[(blk_y(blk) >> 2) * 4 + (blk_x(blk) >> 2)] = w.t_dcw[m][blk];
         hadamard4x4(d);
-        for (int i = 0; i < 16; ++i) d[i] >>= 1;
-        quant_dc(d, 16, f.qp, true);
+        const int qb1 = f.qk.qbits + 1, f2 = ((1 << f.qk.qbits) / 3) << 1, mf = f.qk.mf[0];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int v = d[i] >> 1, z = (iabs(v) * mf + f2) >> qb1; d[i] = v >= 0 ? z : -z; }
         zigzag4x4(d, lv);
-        for (int i = 0; i < 16; ++i) w.t_dc[m][i] = (int16_t)lv[i];
-    } else if (phase == 2) {  // serial: rate with the evolving nC state, single-coefficient elimination, DC token (rdo.c:1617-1679)
-        if (lane != 0) return;
-        for (int m = 0; m < 4; ++m) {
-            if (!w.t_mode_ok[m]) continue;
-            int sctr = 0, cbp = 0, bits = 0;
-            for (int blk = 0; blk < 16; ++blk) {
-                if (!w.t_nz[m][blk]) continue;
-                const int nC = luma_nc(w, w.tc, blk);
-                bits += w.t_bits[m][blk] + coeff_token_len(nC, w.t_tc[m][blk], w.t_t1[m][blk]);
-                w.tc[blk] = w.t_tc[m][blk];
-                cbp |= 1 << blk;
-                if (w.t_tc[m][blk] > 0) w.last_sctr = w.t_sc[m][blk];
-                else if (w.last_sctr < 0) { w.need_prev_sctr = 1; w.last_sctr = w.arg1; }  // chain value of the raster predecessor (residual.c:882 is skipped when TotalCoeffs == 0)
-                sctr += w.last_sctr;
-            }
-            if (cbp && sctr < 6) cbp = 0;
-            if (cbp) {
-                int l16[16];
-                for (int i = 0; i < 16; ++i) l16[i] = w.t_dc[m][i];
-                const CavlcInfo ci = cavlc_block_info(l16, 16, false);
-                const int nC = luma_nc(w, w.tc, 0);
-                bits += ci.bits_rest + coeff_token_len(nC, ci.total_coeff, ci.trailing_ones);
-                w.tc[0] = ci.total_coeff;
-                if (ci.total_coeff > 0) w.last_sctr = ci.single_ctr;
-            }
-            w.t_cbp[m] = cbp; w.t_rate[m] = bits;
-        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ((uint32_t*)w.t_dc[m])[i] = pack16(lv[2 * i], lv[2 * i + 1]);
+        hadamard4x4(d);   // d still holds the quantised values in raster order
+        const int q6 = f.qk.qbits - 15, ls = f.qk.dq_shift ? f.qk.dq_mul[0] : (f.qk.dq_mul[0] >> (q6 - 4));   // LevelScale(QP % 6, 0, 0)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w.t_dcw[m][k] = q6 >= 6 ? ((d[k] * ls) << (q6 - 6)) : ((d[k] * ls + (1 << (5 - q6))) >> (6 - q6));   // by raster position of the 4x4 block
     } else {  // reconstruction + distortion per block (rdo.c:1683-1760)
         if (lane >= 64) return;
         const int m = lane >> 4, blk = lane & 15;
         if (!w.t_mode_ok[m]) return;
         const int bx = blk_x(blk), by = blk_y(blk);
-        int r4[16];
+        Rows4 sv, pv;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r4[i] = 0;
+        for (int r = 0; r < 4; ++r) { pv.r[r] = ((const uint32_t*)w.t_pred[m])[((by + r) * 16 + bx) >> 2]; sv.r[r] = ((const uint32_t*)w.src_y)[((by + r) * 16 + bx) >> 2]; }
+        Rows4 rec = pv;
         if (w.t_cbp[m]) {
-            // 8.5.10 (transf.c:498): every lane recomputes the 16 de-scaled DC values of its mode (cheap, avoids a phase)
-            int c[16], l16[16];
-            for (int i = 0; i < 16; ++i) l16[i] = w.t_dc[m][i];
-            inv_zigzag4x4(l16, c);
-            hadamard4x4(c);
-            const int ls = 16 * kNormAdjust[f.qp % 6][0], q6 = f.qp / 6;
-            const int k = (by >> 2) * 4 + (bx >> 2);
-            const int dcv = f.qp >= 36 ? ((c[k] * ls) << (q6 - 6)) : ((c[k] * ls + (1 << (5 - q6))) >> (6 - q6));
-            bool any = dcv != 0;
-            l16[0] = dcv;
+            const int dcv = w.t_dcw[m][(by >> 2) * 4 + (bx >> 2)];
+            const int16_t* e = w.t_ac[m][blk];
+            int c[16] = {dcv, e[0], e[4], e[5], e[1], e[3], e[6], e[11], e[2], e[7], e[10], e[12], e[8], e[9], e[13], e[14]};   // zig-zag list back to raster positions
+            uint32_t any = 0;
 #pragma unroll
-            for (int i = 1; i < 16; ++i) { l16[i] = w.t_ac[m][blk][i - 1]; any |= (l16[i] != 0); }
+            for (int i = 0; i < 16; ++i) any |= (uint32_t)c[i];
             if (any) {
-                inv_zigzag4x4(l16, r4);
-                dequant4x4(r4, f.qp, true);
-                inv_transform4x4(r4);
+                fast_dequant_inverse(c, f.qk, /*keep_dc*/ true);
+                rec = fast_recon_clip(pv, c);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) ((uint32_t*)w.t_pred[m])[((by + r) * 16 + bx) >> 2] = rec.r[r];   // becomes the reconstruction of mode m
             }
         }
-        int dist = 0;
+        uint32_t dist = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int u = clip255((int)w.t_pred[m][(by + r) * 16 + bx + c] + r4[r * 4 + c]);
-                w.t_pred[m][(by + r) * 16 + bx + c] = (uint8_t)u;   // becomes the reconstruction of mode m
-                dist += iabs((int)w.src_y[(by + r) * 16 + bx + c] - u);
-            }
-        w.t_dist[m][blk] = dist;
+        for (int r = 0; r < 4; ++r) dist = p_sad4(sv.r[r], rec.r[r], dist);
+        w.t_dist[m][blk] = (int)dist;
     }
 }
 HLB_FN void i16_recon_phase(MbWork& w, const FrameCtx& f, int lane)
@@ -289,7 +261,51 @@ HLB_FN int mb_encode_intra(X& x, MbWork& w, const FrameCtx& f, double& intra_cos
         }
         if (need) w.arg1 = x.prev_sctr(w.mb);
     }
-    x.run(CMD_I16_RATE, 64);
+    // Rate with the evolving nC state, single-coefficient elimination, DC token (rdo.c:1617-1679).  The four modes follow each other (a mode leaves its TotalCoeff
+    // behind for the next one); inside a mode the blocks go over the lanes: a block's nC reads its left / upper neighbours, which precede it, so "the state when
+    // block b is reached" is the state after every non-zero block of the mode has been written -- written first, read after one barrier.
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {
+        if (!w.t_mode_ok[m]) continue;
+#pragma unroll 1
+        for (int blk = x.lane(); blk < 16; blk += x.nlanes())
+            if (w.t_nz[m][blk]) w.tc[blk] = w.t_tc[m][blk];
+        x.sync();
+        int bits = 0, cbp = 0;
+#pragma unroll 1
+        for (int blk = x.lane(); blk < 16; blk += x.nlanes())
+            if (w.t_nz[m][blk]) { bits += w.t_bits[m][blk] + coeff_token_len(luma_nc(w, w.tc, blk), w.t_tc[m][blk], w.t_t1[m][blk]); cbp |= 1 << blk; }
+        bits = x.reduce_add(bits); cbp = x.reduce_add(cbp);
+        // the Single_ctr chain is a scan over the blocks in order: every lane walks it (16 short steps on shared memory)
+        int sctr = 0, last = w.last_sctr, need_prev = 0;
+#pragma unroll 1
+        for (int blk = 0; blk < 16; ++blk) {
+            if (!w.t_nz[m][blk]) continue;
+            if (w.t_tc[m][blk] > 0) last = w.t_sc[m][blk];
+            else if (last < 0) { need_prev = 1; last = w.arg1; }   // chain value of the raster predecessor (residual.c:882 is skipped when TotalCoeffs == 0)
+            sctr += last;
+        }
+        if (cbp && sctr < 6) cbp = 0;
+        int tc0 = -1;
+        if (cbp) {
+            int l16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) l16[i] = w.t_dc[m][i];
+            const CavlcInfo ci = cavlc_block_info16(l16, level_mask16(l16));
+            bits += ci.bits_rest + coeff_token_len(luma_nc(w, w.tc, 0), ci.total_coeff, ci.trailing_ones);
+            tc0 = ci.total_coeff;
+            if (ci.total_coeff > 0) last = ci.single_ctr;
+        }
+        x.sync();
+        if (x.lane() == 0) {
+            w.last_sctr = last;
+            if (need_prev) w.need_prev_sctr = 1;
+            if (tc0 >= 0) w.tc[0] = (uint8_t)tc0;
+            w.t_cbp[m] = cbp; w.t_rate[m] = bits;
+        }
+        x.sync();
+    }
+    x.run(CMD_I16_RATE, 64);   // reconstruction + distortion of every (mode, block)
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) w.stat_intra += w.t_mode_ok[m] ? 16u : 0u;
     double best16 = DBL_MAX;
