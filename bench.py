@@ -421,6 +421,20 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
                 "encode_fps": e2e["encode_fps"]}
         if all_inter:
             line["all_inter"] = all_inter
+        if world == 1 and not args.no_all_inter:
+            # BASELINE.json configs[3]: three spatial layers QCIF -> CIF -> 4CIF, ONE stream through the drop-in (base layer: slice kernel; enhancement layers: the SVC
+            # kernels; inter-layer derivation still on the host) beside the all-CPU reference on the same input; the byte streams must be equal
+            enc_b, enc_r = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder"), os.path.join(ROOT, "oracle", "_ref", "hl_ref_driver")
+            if os.path.exists(enc_b) and os.path.exists(enc_r):
+                a = ["--layers", "3", "--size", "176", "144", "--frames", "6", "--gen", "g1"]
+                ro = subprocess.run([enc_r] + a + ["--out", "/tmp/hlb200_svc_ref.264"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                bo = subprocess.run([enc_b] + a + ["--out", "/tmp/hlb200_svc_b200.264"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, HLB200_DEVICE=str(local)))
+                if ro.returncode == 0 and bo.returncode == 0:
+                    rj, bj = json.loads(ro.stdout.strip().splitlines()[-1]), json.loads(bo.stdout.strip().splitlines()[-1])
+                    line["svc_layers"] = {"config": "QCIF -> CIF -> 4CIF (BASELINE.json configs[3]), 1 stream, 6 access units of 3 layers, QP 31",
+                                          "ms_per_p_access_unit": bj["ms_p_frames"] / max(bj["p_frames"], 1), "reference_ms_per_p_access_unit": rj["ms_p_frames"] / max(rj["p_frames"], 1),
+                                          "bitstream_bytes": bj["bytes"], "bitstream_equal": bool(bj["md5"] == rj["md5"] and bj["bytes"] == rj["bytes"]),
+                                          "note": "single stream: the layers of one access unit follow each other (the enhancement layers read the layer below), the device is mostly idle"}
         if world == 1 and not args.no_hbm_kernels:
             # the stateless whole-picture kernels (interpolation, transform-quantisation-reconstruction, the SVC base-mode kernels): HBM rooflines at 128 pictures per launch
             torch.cuda.empty_cache()
