@@ -190,7 +190,10 @@ int hlb200_frame_upload(hlb200_ctx_t* c, const uint8_t* y, const uint8_t* u, con
     const uint8_t* h[3] = {y, u, v};
     for (int p = 0; p < 3; ++p) {
         const int w = p ? c->width >> 1 : c->width, hh = p ? c->height >> 1 : c->height, st = p ? stride_c : stride_y;
-        HLB_CUDA(cudaMemcpy2DAsync(c->d_src[p], w, h[p], st, w, hh, cudaMemcpyHostToDevice, c->stream));
+        // tight planes go as ONE linear copy: a copy-engine DMA that overlaps a running slice kernel (the pitched form was observed not to, with every SM held by
+        // the persistent kernel -- 32 ms of idle device per 256-stream launch)
+        if (st == w) HLB_CUDA(cudaMemcpyAsync(c->d_src[p], h[p], (size_t)w * hh, cudaMemcpyHostToDevice, c->stream));
+        else HLB_CUDA(cudaMemcpy2DAsync(c->d_src[p], w, h[p], st, w, hh, cudaMemcpyHostToDevice, c->stream));
         c->d_src_cur[p] = c->d_src[p];
     }
     return HLB200_OK;

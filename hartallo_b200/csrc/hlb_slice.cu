@@ -741,6 +741,10 @@ int hlb200_slice_bits_batch_async(hlb200_ctx_t** ctxs, const int32_t* slice_type
     HLB_CUDA(cudaGetLastError());
     if (!c0->ev_done) HLB_CUDA(cudaEventCreateWithFlags(&c0->ev_done, cudaEventDisableTiming));
     HLB_CUDA(cudaEventRecord(c0->ev_done, st));
+    // The next batch launch of the device waits for these three short kernels too: the persistent slice kernel fills every SM (registers and shared memory at
+    // their limits), so serialisation kernels that become runnable together with it would only get their CTAs placed when it drains -- and the downloads
+    // behind them would wait a whole launch (measured through hl_codec_encode with two groups of 256 streams in flight).
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < HLB_MAX_DEVICES && g_batch_done[dev]) HLB_CUDA(cudaEventRecord(g_batch_done[dev], st)); }
     for (int i = 1; i < n; ++i)
         if (ctxs[i]->stream != st) HLB_CUDA(cudaStreamWaitEvent(ctxs[i]->stream, c0->ev_done, 0));
     return HLB200_OK;

@@ -153,7 +153,7 @@ int main(int argc, char** argv)
     const char* out_path = NULL;
     const struct hl_codec_plugin_def_s* plugin = NULL;
     stream_t* st;
-    double t0 = 0, t1, t_first = 0;
+    double t0 = 0, t1, t_first = 0, t_submit = 0, t_finish = 0, t_flush = 0, t_finish_first = 0, ta;
     size_t bytes_timed = 0, bytes_at_t0 = 0;
     char md5[33];
     HL_ERROR_T err;
@@ -232,18 +232,26 @@ int main(int argc, char** argv)
             if (f == 1 + warm && g == 0) {   /* the timed region starts (and ends) with the pipeline drained: exactly `timed` pictures per stream lie inside it */
                 for (i = 0; i < streams && !failed; ++i)
                     if (st[i].state == ST_SUBMITTED) failed |= resume(&st[i]) != 0;
-                t0 = now_ms(); bytes_at_t0 = 0;
+                t0 = now_ms(); bytes_at_t0 = 0; t_submit = t_finish = t_flush = t_finish_first = 0;
                 for (i = 0; i < streams; ++i) bytes_at_t0 += st[i].out_n;
             }
             if (f > 0) {   /* finish picture f-1 of the group: every hook downloads its slice data, the reference completes the NAL unit */
-                for (i = a; i < b && !failed; ++i)
+                ta = now_ms();
+                for (i = a; i < b && !failed; ++i) {
+                    const double tb = now_ms();
                     if (st[i].state == ST_SUBMITTED) failed |= resume(&st[i]) != 0;
+                    if (i == a) t_finish_first += now_ms() - tb;   /* the first download of a group waits for the group's launch */
+                }
+                t_finish += now_ms() - ta;
                 for (i = a; i < b && !failed; ++i)
                     if (st[i].state != ST_FRAME_DONE) { fprintf(stderr, "stream %d did not finish picture %d (state %d)\n", i, f - 1, st[i].state); failed = 1; }
             }
             if (f < g_frames) {   /* submit picture f of the group, one launch for all of them */
+                ta = now_ms();
                 for (i = a; i < b && !failed; ++i) failed |= resume(&st[i]) != 0;
+                t_submit += now_ms() - ta; ta = now_ms();
                 if (!failed && hlb200_glue_batch_pending() > 0 && (err = (HL_ERROR_T)hlb200_glue_batch_flush())) { fprintf(stderr, "batch launch failed: %d (%s)\n", (int)err, hlb200_last_error()); failed = 1; }
+                t_flush += now_ms() - ta;
             }
         }
     }
@@ -260,9 +268,10 @@ int main(int argc, char** argv)
         const double ms = t1 - t0;
         if (same) for (i = 1; i < streams; ++i) all_equal &= st[i].out_n == st[0].out_n && !memcmp(st[i].out, st[0].out, st[0].out_n);
         printf("{\"streams\": %d, \"width\": %d, \"height\": %d, \"frames\": %d, \"timed_pictures_per_stream\": %d, \"groups\": %d, \"ms_timed\": %.3f, \"ms_total\": %.3f, "
-               "\"encode_fps\": %.2f, \"fps_per_stream\": %.3f, \"mb_per_s\": %.1f, \"bitstream_bytes_timed\": %zu, \"bytes\": %zu, \"md5\": \"%s\", \"same_content\": %d, \"all_streams_equal\": %s}\n",
+               "\"encode_fps\": %.2f, \"fps_per_stream\": %.3f, \"mb_per_s\": %.1f, \"bitstream_bytes_timed\": %zu, \"bytes\": %zu, \"md5\": \"%s\", \"same_content\": %d, \"all_streams_equal\": %s, "
+               "\"host_ms\": {\"submit\": %.1f, \"launch\": %.1f, \"finish\": %.1f, \"finish_first_of_group\": %.1f}}\n",
                streams, g_w, g_h, g_frames, timed, groups, ms, t1 - t_first, 1e3 * timed * streams / ms, 1e3 * timed / ms, 1e3 * (double)timed * streams * mbs / ms, bytes_timed,
-               st[0].out_n, md5, same, same ? (all_equal ? "true" : "false") : "null");
+               st[0].out_n, md5, same, same ? (all_equal ? "true" : "false") : "null", t_submit, t_flush, t_finish, t_finish_first);
         if (same && !all_equal) return 3;
     }
     return 0;
