@@ -196,7 +196,7 @@ def measure_int_peak(torch, hl, lib, dev, stream, sp):
     return best
 
 
-NCU_DRAM_BYTES_PER_MB = 11363   # k_slice_encode_warp, profiles/r02j (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its macroblocks)
+NCU_DRAM_BYTES_PER_MB = 11790   # k_slice_encode_warp, profiles/r02w_ncu_slice_warp.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its macroblocks)
 MULTI = os.path.join(ROOT, "oracle", "_ref", "hl_b200_multi")       # the reference's host code + host/hlb200_glue.c (batch mode) + libhl_b200.so: many streams through hl_codec_encode
 BENCH_GOLDEN = os.path.join(ROOT, "tests", "golden", "encoder_1080p_bench.json")
 
@@ -341,7 +341,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
     variant = int(lib.hlb200_slice_last_variant())
     roof = {"kernel": "k_slice_encode_warp" if variant else "k_slice_encode", "variant": "one warp per macroblock" if variant else "one CTA per macroblock", "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Gop/s", "frac": ach / int_peak,
             # DRAM bytes of the kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture, scaled to this launch
-            "traffic": int(NCU_DRAM_BYTES_PER_MB * S * NMB), "traffic_unit": "bytes per launch (ncu capture profiles/r02j, scaled by macroblocks)", "ms": kms,
+            "traffic": int(NCU_DRAM_BYTES_PER_MB * S * NMB), "traffic_unit": "bytes per launch (ncu capture profiles/r02w_ncu_slice_warp.md, scaled by macroblocks)", "ms": kms,
             "ms_kind": "mean of the timed launches (the three serialisation kernels of a step are included: < 1 % of it)",
             "peak_kind": "measured live (hlb200_dev_int_alu_probe: dependency-free IADD3/LOP3)", "algorithmic_ops_per_launch": ops,
             "per_mb": {"me_candidates": cands / (S * NMB), "me_trials": trials / (S * NMB), "intra_trials": intra / (S * NMB), "int_ops": ops / (S * NMB)},
