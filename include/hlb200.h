@@ -13,8 +13,12 @@
  *                               hl_codec_264_rdo_mb_guess_best_inter_pred_avc source/h264/hl_codec_264_rdo.c:678,
  *                               hl_codec_264_rdo_mb_guess_best_intra_pred_avc rdo.c:99,
  *                               hl_codec_264_me_ds_mb_find_best_cost          source/h264/hl_codec_264_me_ds.c:104);
- *                              the CAVLC serialisation (_hl_codec_264_mb_write_no_pcm, source/h264/hl_codec_264_mb.c:543)
- *                              stays on the host and consumes hlb200_mb_record_t.
+ *                              with hlb200_slice_params_t::me_early_term_flag the homogeneous-block mode mask of rdo.c:889-935, with ::deblock_flag the
+ *                              loop filter hl_codec_264_deblock_avc source/h264/hl_codec_264_deblock.c:192 over the finished picture (slice.c:1897)
+ *   hlb200_slice_bits_*        slice_data() of the pictures just encoded, written on the device: _hl_codec_264_mb_write_no_pcm
+ *                              source/h264/hl_codec_264_mb.c:543-900, hl_codec_264_residual_write residual.c:903-1094, cavlc.c:652-836,
+ *                              mb_skip_run slice.c:1840-1868.  (hlb200_records_download hands the decision records to a host writer instead:
+ *                              streams with SVC layers, whose inter-layer derivation reads them on the host.)
  *   hlb200_interp_luma/chroma  hl_codec_264_interpol_luma  source/h264/hl_codec_264_pred_inter.c:339,
  *                              hl_codec_264_interpol_chroma_cpp pred_inter.c:888 (whole-frame batch, one MV set per MB)
  *   hlb200_tq_recon            _hl_codec_264_rdo_mb_reconstruct_inter rdo.c:2274 (residual part :2428-2478) and
@@ -24,12 +28,20 @@
  *   hlb200_dev_svc_resample_intra_batch  _hl_codec_264_decode_svc_resample_intra_colour_comps decode_svc.c:2864 (Intra_Base resampling, I pictures)
  *   hlb200_dev_svc_bl_recon_batch     hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301 (I_BL macroblocks: residual coding + reconstruction
  *                              against the host-resampled base layer)
- *   hlb200_sad4x4/satd4x4      hl_math_sad4x4_u8 source/hl_math.c:239, hl_math_satd4x4_u8 hl_math.c:283 (whole-frame batch)
+ *   hlb200_sad4x4              hl_math_sad4x4_u8 source/hl_math.c:239, hl_math_satd4x4_u8 hl_math.c:283, hl_math_ssd4x4_u8 hl_math.c:360 (whole-frame batch)
+ *   hlb200_homogeneity8x8      hl_math_homogeneousity8x8_u8 hl_math.c:470 (whole-frame batch)
  *   hlb200_me_cost             hl_codec_264_me_ds_mb_compute_cost_mode me_ds.c:527 (batch of independent candidates)
  *
  * Ownership: device memory belongs to the stream context; host buffers are caller-owned.  One CUDA stream per
- * context; no global mutable state, so -- unlike the reference (rdo.c:97 `static double last_best_intra_cost`) --
- * many contexts may live in one process.
+ * context.  Unlike the reference (rdo.c:97 `static double last_best_intra_cost`) many contexts may live in one process; the
+ * library's process-wide state is read-mostly (resident-CTA counts and one launch-ordering event per device, the kernel-variant
+ * override) plus a thread-local error string.
+ *
+ * ORDERING RULE of the batch entry points (hlb200_slice_encode_batch_async, hlb200_slice_bits_batch_async): the kernels run on the
+ * stream of ctxs[0].  Work queued earlier on the other contexts' streams (uploads) is made a dependency of the launch, and everything
+ * queued later on them (downloads, the next upload) waits for it -- events, no host synchronisation.  Batch launches of one device run
+ * back to back in submission order.  A context must stay alive until the launches that covered it have completed (it may own their
+ * scheduler storage); hlb200_stream_destroy synchronises its stream first.
  */
 #ifndef HLB200_H_
 #define HLB200_H_
