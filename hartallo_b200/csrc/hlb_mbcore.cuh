@@ -584,10 +584,11 @@ HLB_HD int part_blk(const MbWork& w, int k) { return blk_idx_from_xy(w.part_ox +
 HLB_HD void me_scan_block(MbWork& w, int k, int n, bool keep_eff)
 {
     const int blk = part_blk(w, k);
+    int e = w.tc[blk], last = -1;
+#ifdef HLB_SCAN_UNROLLED
     uint32_t v[HLB_MAXC];
 #pragma unroll
     for (int c = 0; c < HLB_MAXC; ++c) v[c] = c < n ? w.r_val[c][blk] : 0u;   // independent loads, then the serial "last non-zero wins" in registers
-    int e = w.tc[blk], last = -1;
 #pragma unroll
     for (int c = 0; c < HLB_MAXC; ++c) {
         const int tcv = (int)((v[c] >> 22) & 31u);
@@ -597,6 +598,20 @@ HLB_HD void me_scan_block(MbWork& w, int k, int n, bool keep_eff)
         }
         if (keep_eff && c < n) w.eff[c][blk] = (uint8_t)e;
     }
+#else
+    // rolled over the step's candidates (n <= 9, often 4-5 after pruning): the kernel is instruction-fetch bound, the nine unrolled copies cost more than the
+    // shared-memory latency they hide
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        const uint32_t v = w.r_val[c][blk];
+        const int tcv = (int)((v >> 22) & 31u);
+        if (tcv) {
+            e = tcv;
+            last = ((c + 1) << 12) | ((tcv == 1 && ((v >> 27) & 3u) == 1) ? (int)((v >> 29) & 3u) : 9);
+        }
+        if (keep_eff) w.eff[c][blk] = (uint8_t)e;
+    }
+#endif
     w.tc[blk] = (uint8_t)e;
     if (last >= 0) HLB_ATOMIC_MAX(&w.step_last, last | (k << 8));
 }
