@@ -318,12 +318,16 @@ HLB_FN void derive_mvp(const MbWork& w, const FrameCtx& f, int part, int sub, in
 }
 
 // 8.4.1.1 (utils.c:709-748); only ever called with the 16x16 geometry
+// 8.4.1.1: the P_Skip vector is zero when A or B is unavailable or is a zero vector on reference 0, else the 16x16 predictor on reference 0
+HLB_HD bool pskip_mv_is_zero(const MbWork& w, const FrameCtx& f)
+{
+    const NbMotion A = nb_motion_at(w, f, -1, 0, 0, 0), B = nb_motion_at(w, f, 0, -1, 0, 0);
+    return !A.avail || !B.avail || (A.ref == 0 && A.mvx == 0 && A.mvy == 0) || (B.ref == 0 && B.mvx == 0 && B.mvy == 0);
+}
 HLB_FN void derive_pskip_mv(const MbWork& w, const FrameCtx& f, int& mx, int& my)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
-    NbMotion A = nb_motion_at(w, f, -1, 0, 0, 0);
-    NbMotion B = nb_motion_at(w, f, 0, -1, 0, 0);
-    if (!A.avail || !B.avail || (A.ref == 0 && A.mvx == 0 && A.mvy == 0) || (B.ref == 0 && B.mvx == 0 && B.mvy == 0)) { mx = my = 0; return; }
+    if (pskip_mv_is_zero(w, f)) { mx = my = 0; return; }
     derive_mvp(w, f, 0, 0, 0, mx, my);
 }
 
@@ -778,8 +782,8 @@ HLB_FN int me_search_begin(X& x, MbWork& w, const FrameCtx& f, int mode)
     x.sync();
     if (mode == 0 && w.ref == 0) {  // PSkip probe (me_ds.c:229-261)
         int sx, sy, px, py;
-        derive_pskip_mv(w, f, sx, sy);
-        derive_mvp(w, f, 0, 0, w.ref, px, py);
+        derive_mvp(w, f, 0, 0, 0, px, py);   // w.ref == 0: the predictor the P_Skip derivation would compute itself
+        if (pskip_mv_is_zero(w, f)) sx = sy = 0; else { sx = px; sy = py; }
         if (px == sx && py == sy) {
             x.sync();
             if (x.lane() == 0) { set_part(w, mode, 0, 0); w.cand_mv[0] = mv_pack(px, py); }
@@ -932,26 +936,55 @@ HLB_FN void me_pskip_tail(X& x, MbWork& w, const FrameCtx& f)
     const int px = w.best_mv[0][0][0], py = w.best_mv[0][0][1], R = f.me_range;
     x.sync();
     if (x.lane() == 0) {
-        int n = 0;
         w.mvp[0][0][0] = (int16_t)px; w.mvp[0][0][1] = (int16_t)py;
         w.mv_cur[0][0][0] = (int16_t)px; w.mv_cur[0][0][1] = (int16_t)py;
         set_part(w, 0, 0, 0);
-        w.tail_mv[n++] = mv_pack(px, py);
-        if (px != 0 || py != 0) w.tail_mv[n++] = 0;
-        for (int shift = 2; shift >= 0; --shift) {
-            // centres: integer and half-pel stage around (mvp >> 2), quarter-pel stage around mvp; window = centre +- me_range
-            const int cx = shift ? px >> 2 : px, cy = shift ? py >> 2 : py, count = shift == 1 ? 5 : 9;
-            for (int i = 0; i < count; ++i) {
-                const int dx = kDsp[shift][i][0], dy = kDsp[shift][i][1];
-                if (dx >= -R && dx <= R && dy >= -R && dy <= R) w.tail_mv[n++] = mv_pack((cx + dx) * (1 << shift), (cy + dy) * (1 << shift));
+    }
+    // The candidates the full search would visit, in its order: the predictor, (0,0) when that is another vector, then the integer, half and quarter
+    // patterns -- centres: integer and half-pel stage around (mvp >> 2), quarter-pel stage around mvp; window = centre +- me_range.  One slot per
+    // lane (25 slots), compacted in slot order.
+    int n = 0, iops = 0;
+    {
+#if defined(__CUDA_ARCH__)
+        const int j0 = x.lane(), j1 = j0 + 1;
+#else
+        const int j0 = 0, j1 = 25;
+#endif
+        uint32_t okmask = 0, mymv = 0;
+        bool myok = false;
+        for (int j = j0; j < j1 && j < 25; ++j) {
+            bool ok;
+            uint32_t mv;
+            if (j == 0) { ok = true; mv = mv_pack(px, py); }
+            else if (j == 1) { ok = px != 0 || py != 0; mv = 0; }
+            else {
+                const int k = j - 2, shift = k < 9 ? 2 : (k < 14 ? 1 : 0), i = k < 9 ? k : (k < 14 ? k - 9 : k - 14);
+                const int cx = shift ? px >> 2 : px, cy = shift ? py >> 2 : py, dx = kDsp[shift][i][0], dy = kDsp[shift][i][1];
+                ok = dx >= -R && dx <= R && dy >= -R && dy <= R;
+                mv = mv_pack((cx + dx) * (1 << shift), (cy + dy) * (1 << shift));
             }
+            if (ok) {
+                const int xf = mv_x(mv) & 3, yf = mv_y(mv) & 3;
+                iops += (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
+#if !defined(__CUDA_ARCH__)
+                w.tail_mv[n] = mv;
+#endif
+                ++n;
+            }
+            myok = ok; mymv = mv;
         }
+#if defined(__CUDA_ARCH__)
+        okmask = __ballot_sync(0xffffffffu, myok && x.lane() < 25);
+        if (myok && x.lane() < 25) w.tail_mv[hlb_popc(okmask & ((1u << x.lane()) - 1u))] = mymv;
+        n = hlb_popc(okmask);
+        if (x.lane() >= 25) iops = 0;
+#else
+        (void)okmask; (void)mymv; (void)myok;
+#endif
+    }
+    iops = x.reduce_add(iops);
+    if (x.lane() == 0) {
         w.tail_n = n;
-        int iops = 0;
-        for (int c = 0; c < n; ++c) {
-            const int xf = mv_x(w.tail_mv[c]) & 3, yf = mv_y(w.tail_mv[c]) & 3;
-            iops += (xf == 0 && yf == 0) ? 0 : ((xf == 0 || yf == 0) ? (((xf | yf) == 2) ? 176 : 208) : (((xf & 1) && (yf & 1)) ? 352 : 880));
-        }
         w.stat_trials += (unsigned)(n << 4); w.stat_cands += (unsigned)n; w.stat_interp += (unsigned)(iops << 4);
     }
     x.sync();
