@@ -34,7 +34,8 @@ def test_device_cavlc_fuzz_cpu():
 
 @pytest.mark.skipif(not os.path.exists(MULTI_CPU), reason="oracle/_ref/hl_multi_check only exists where the reference tree is available")
 @pytest.mark.parametrize("args", [["--size", "176", "144", "--frames", "4", "--qp", "31", "--me-range", "16", "--gen", "g1"],
-                                  ["--size", "96", "64", "--frames", "5", "--qp", "26", "--me-range", "32", "--gen", "g2", "--seed", "3"]])
+                                  ["--size", "96", "64", "--frames", "5", "--qp", "26", "--me-range", "32", "--gen", "g2", "--seed", "3"],
+                                  ["--size", "96", "80", "--frames", "4", "--qp", "30", "--me-range", "16", "--gen", "g2", "--seed", "8", "--defaults"]])   # deblocking + early termination
 def test_multi_stream_batch_cpu(args):
     """five codec instances (coroutines) encoding the same sequence in batch mode, two alternating groups: five identical bitstreams, equal to the reference's"""
     ref = _json([REF] + args)
@@ -44,12 +45,13 @@ def test_multi_stream_batch_cpu(args):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(MULTI_GPU), reason="oracle/_ref/hl_b200_multi not built (needs the reference tree at build time)")
-@pytest.mark.parametrize("name,streams", [("g1_cif_10", 6), ("g2_qcif", 9), ("g1_1080p_q31", 3)])
+@pytest.mark.parametrize("name,streams", [("g1_cif_10", 6), ("g2_qcif", 9), ("g1_1080p_q31", 3), ("g2_qcif_deblock", 7), ("g1_1080p_defaults", 3)])
 def test_multi_stream_drop_in(name, streams):
     """many streams through hl_codec_encode with ONE device launch per picture (encode + device-side CAVLC): every stream's bitstream equals the reference's"""
     g = np.load(os.path.join(GOLD, "encoder_%s.npz" % name))
     w, h, frames, qp, me_range, seed = (int(v) for v in g["config"])
+    early, deblock = (int(g["flags"][0]), int(g["flags"][1])) if "flags" in g.files else (0, 0)
     args = ["--size", str(w), str(h), "--frames", str(frames), "--qp", str(qp), "--me-range", str(me_range), "--gen", str(g["gen"]), "--seed", str(seed), "--streams", str(streams),
-            "--same-content"]
+            "--same-content", "--early-term", str(early), "--deblock", str(deblock)]
     got = _json([MULTI_GPU] + args)
     assert got["all_streams_equal"] is True and got["md5"] == str(g["bitstream_md5"]), (got, str(g["bitstream_md5"]))
