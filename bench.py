@@ -196,7 +196,7 @@ def measure_int_peak(torch, hl, lib, dev, stream, sp):
     return best
 
 
-NCU_DRAM_BYTES_PER_MB = 11790   # k_slice_encode_warp, profiles/r02w_ncu_slice_warp.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its macroblocks)
+NCU_DRAM_BYTES_PER_MB = 11696   # k_slice_encode_warp, profiles/r02w_ncu_slice_warp.md (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its macroblocks)
 MULTI = os.path.join(ROOT, "oracle", "_ref", "hl_b200_multi")       # the reference's host code + host/hlb200_glue.c (batch mode) + libhl_b200.so: many streams through hl_codec_encode
 BENCH_GOLDEN = os.path.join(ROOT, "tests", "golden", "encoder_1080p_bench.json")
 
