@@ -194,6 +194,7 @@ struct MbWork {
     // one evaluation step
     int c_begin, c_end;        // candidates evaluated by the current CMD_ME_EVAL
     int part_ox, part_oy, part_w, part_h;
+    int part_mask;                     // luma4x4BlkIdx bits of the blocks inside the current partition (set_part)
     int counts_only;           // the step's trials need TotalCoeff / TrailingOnes / Single_ctr only (me_step)
     uint32_t cand_mv[HLB_MAXC];        // candidate vectors of the step: (uint16)mvx | (uint16)mvy << 16
     uint8_t cand_pat[HLB_MAXC];        // their pattern indices
@@ -220,7 +221,7 @@ struct MbWork {
     int cbp_ac[2], cbp_dc[2];
     int mb_is_intra;
     int32_t c_dccoef[2][4];
-    uint8_t c_acnz[2][4], c_sc[2][4], c_tc[2][4], c_resnz[2][4];
+    alignas(4) uint8_t c_acnz[2][4], c_sc[2][4], c_tc[2][4], c_resnz[2][4];   // c_acnz rows are read as words
     // ---- intra ----
     int i16_mode, i16_cbp4x4, i4_cbp4x4, intra_chroma_mode;
     int16_t i16_dc[16];
@@ -575,11 +576,7 @@ HLB_FN void me_phase_trial(MbWork& w, const FrameCtx& f, int lane)
     }
     w.r_val[c][blk] = val;
 }
-HLB_HD bool blk_in_part(const MbWork& w, int blk)
-{
-    const int x = blk_x(blk), y = blk_y(blk);
-    return x >= w.part_ox && x < w.part_ox + w.part_w && y >= w.part_oy && y < w.part_oy + w.part_h;
-}
+HLB_HD bool blk_in_part(const MbWork& w, int blk) { return (w.part_mask >> blk) & 1; }   // set_part: kPartMask
 // block k (raster index inside the current partition = evaluation order) -> luma4x4BlkIdx
 HLB_HD int part_blk(const MbWork& w, int k) { return blk_idx_from_xy(w.part_ox + ((k & ((1 << w.bw_log2) - 1)) << 2), w.part_oy + ((k >> w.bw_log2) << 2)); }
 // per block OF THE PARTITION: TotalCoeffsLuma[blk] as every candidate of the step sees / leaves it, in evaluation order (residual.c:796-806: only non-zero
@@ -605,16 +602,18 @@ HLB_HD void me_scan_block(MbWork& w, int k, int n, bool keep_eff)
 #else
     // rolled over the step's candidates (n <= 9, often 4-5 after pruning): the kernel is instruction-fetch bound, the nine unrolled copies cost more than the
     // shared-memory latency they hide
+    uint32_t lastv = 0;
+    int lastc = -1;
+    const uint32_t* rv = &w.r_val[0][blk];
+    uint8_t* ef = &w.eff[0][blk];
 #pragma unroll 1
-    for (int c = 0; c < n; ++c) {
-        const uint32_t v = w.r_val[c][blk];
+    for (int c = 0; c < n; ++c, rv += 16, ef += 16) {
+        const uint32_t v = *rv;
         const int tcv = (int)((v >> 22) & 31u);
-        if (tcv) {
-            e = tcv;
-            last = ((c + 1) << 12) | ((tcv == 1 && ((v >> 27) & 3u) == 1) ? (int)((v >> 29) & 3u) : 9);
-        }
-        if (keep_eff) w.eff[c][blk] = (uint8_t)e;
+        if (tcv) { e = tcv; lastc = c; lastv = v; }
+        if (keep_eff) *ef = (uint8_t)e;
     }
+    if (lastc >= 0) last = ((lastc + 1) << 12) | ((e == 1 && ((lastv >> 27) & 3u) == 1) ? (int)((lastv >> 29) & 3u) : 9);
 #endif
     w.tc[blk] = (uint8_t)e;
     if (last >= 0) HLB_ATOMIC_MAX(&w.step_last, last | (k << 8));
@@ -684,9 +683,19 @@ HLB_TABLE static const uint16_t kPrune[3][9] = {{0x1B0, 0x1F8, 0x03F, 0x1B6, 0x0
                                                 {0x1D0, 0x130, 0x1DA, 0x0B4, 0x000, 0x05A, 0x0B7, 0x05F, 0x017}};
 HLB_TABLE static const uint8_t kHeaderBits[7] = {3, 5, 5, 11, 19, 19, 27};
 
+// luma4x4BlkIdx bits of the 4x4 blocks inside partition (mode, part, sub) -- mode_rect() tabulated
+HLB_TABLE static const uint16_t kPartMask[7][4][4] = {
+    {{0xFFFF, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}},
+    {{0x00FF, 0x0000, 0x0000, 0x0000}, {0xFF00, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}},
+    {{0x0F0F, 0x0000, 0x0000, 0x0000}, {0xF0F0, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}, {0x0000, 0x0000, 0x0000, 0x0000}},
+    {{0x000F, 0x0000, 0x0000, 0x0000}, {0x00F0, 0x0000, 0x0000, 0x0000}, {0x0F00, 0x0000, 0x0000, 0x0000}, {0xF000, 0x0000, 0x0000, 0x0000}},
+    {{0x0003, 0x000C, 0x0000, 0x0000}, {0x0030, 0x00C0, 0x0000, 0x0000}, {0x0300, 0x0C00, 0x0000, 0x0000}, {0x3000, 0xC000, 0x0000, 0x0000}},
+    {{0x0005, 0x000A, 0x0000, 0x0000}, {0x0050, 0x00A0, 0x0000, 0x0000}, {0x0500, 0x0A00, 0x0000, 0x0000}, {0x5000, 0xA000, 0x0000, 0x0000}},
+    {{0x0001, 0x0002, 0x0004, 0x0008}, {0x0010, 0x0020, 0x0040, 0x0080}, {0x0100, 0x0200, 0x0400, 0x0800}, {0x1000, 0x2000, 0x4000, 0x8000}}};
 HLB_HD void set_part(MbWork& w, int mode, int p, int s)
 {
     mode_rect(mode, p, s, w.part_ox, w.part_oy, w.part_w, w.part_h);
+    w.part_mask = kPartMask[mode][p][s];
     w.bw_log2 = w.part_w == 16 ? 2 : (w.part_w == 8 ? 1 : 0);
     w.nblk_log2 = w.bw_log2 + (w.part_h == 16 ? 2 : (w.part_h == 8 ? 1 : 0));
 }
@@ -1137,49 +1146,49 @@ HLB_FN void phase_chroma_serial(MbWork& w, const FrameCtx& f, int lane)
 {
     HLB_IN_SHARED(w); HLB_IN_SHARED(f);
     if (lane != 0) return;
-    // one lane, once per macroblock: every loop stays rolled -- the footprint in the instruction cache matters more than the trip counts
-    int single[2] = {0, 0}, totc[2] = {0, 0};
-    w.cbp_ac[0] = w.cbp_ac[1] = w.cbp_dc[0] = w.cbp_dc[1] = 0;
+    // one lane, once per macroblock: loops stay rolled and the common case (no AC level anywhere) skips the elimination walk -- the footprint in the instruction
+    // cache and the executed instructions matter more than the trip counts.  c_acnz / c_dccoef are only ever non-zero for blocks with a residual.
+    int cbp_ac[2] = {0, 0};
+    if ((*(const uint32_t*)w.c_acnz[0] | *(const uint32_t*)w.c_acnz[1]) != 0) {
+        int single[2] = {0, 0}, totc[2] = {0, 0};
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < 4; ++b)
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            if (w.c_resnz[c][b]) {
-                if (w.c_acnz[c][b]) w.cbp_ac[c] |= 1 << b;
-                if (w.c_dccoef[c][b]) w.cbp_dc[c] |= 1 << b;
+            for (int c = 0; c < 2; ++c) {   // block-major, plane-minor: the order the Single_ctr chain is written in (rdo.c:2599-2625)
+                if (w.c_acnz[c][b]) cbp_ac[c] |= 1 << b;
+                if (single[c] < 7 && ((cbp_ac[c] >> b) & 1)) {
+                    single[c] += w.c_sc[c][b]; totc[c] += w.c_tc[c][b];
+                    w.tc_cac[c][b] = w.c_tc[c][b];
+                    w.last_sctr = w.c_sc[c][b];
+                }
             }
-            if (single[c] < 7 && ((w.cbp_ac[c] >> b) & 1)) {
-                single[c] += w.c_sc[c][b]; totc[c] += w.c_tc[c][b];
-                w.tc_cac[c][b] = w.c_tc[c][b];
-                w.last_sctr = w.c_sc[c][b];
-            }
-        }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c)
-        if (single[c] < 7 && totc[c] == 1) w.cbp_ac[c] = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (single[c] < 7 && totc[c] == 1) cbp_ac[c] = 0;
+    }
+    w.cbp_ac[0] = cbp_ac[0]; w.cbp_ac[1] = cbp_ac[1];
     // 2x2 DC: Hadamard, quantisation with the macroblock's own rounding offset (quant.c:150-189: qbits + 1, 2f, MF(0,0)), de-quantisation (transf.c:612:
     // ((f * LevelScale(QPC % 6, 0, 0)) << (QPC / 6)) >> 5, with QuantK::dq_mul[0] = LevelScale << (QPC / 6 - 4) once QPC >= 24)
     const int qb1 = f.qkc.qbits + 1, f2 = ((1 << f.qkc.qbits) / (w.mb_is_intra ? 3 : 6)) << 1, mf = f.qkc.mf[0], q6 = f.qkc.qbits - 15;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-        int d[4] = {0, 0, 0, 0};
-        if (w.cbp_dc[c]) {
-            int h[4] = {w.c_dccoef[c][0], w.c_dccoef[c][1], w.c_dccoef[c][2], w.c_dccoef[c][3]};
+        int h[4] = {w.c_dccoef[c][0], w.c_dccoef[c][1], w.c_dccoef[c][2], w.c_dccoef[c][3]};
+        int d[4] = {0, 0, 0, 0}, mask = 0;
+        if ((h[0] | h[1] | h[2] | h[3]) != 0) {
             hadamard2x2(h);
-            int mask = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int z = (iabs(h[k]) * mf + f2) >> qb1;
                 h[k] = h[k] >= 0 ? z : -z;
                 w.chroma_dc[c][k] = (int16_t)h[k]; mask |= (h[k] != 0) << k;
             }
-            w.cbp_dc[c] = mask;
             if (mask) {
                 hadamard2x2(h);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { const int v = h[k] * f.qkc.dq_mul[0]; d[k] = q6 >= 4 ? v >> 1 : (v << q6) >> 5; }
             }
         }
+        w.cbp_dc[c] = mask;
         // de-quantised DC per block, parked in c_dccoef for the reconstruction lanes
 #pragma unroll
         for (int k = 0; k < 4; ++k) w.c_dccoef[c][k] = d[k];
