@@ -153,7 +153,7 @@ int hlb200_stream_destroy(hlb200_ctx_t* c)
         cudaFree(c->d_src[p]); cudaFree(c->d_pred[p]); cudaFree(c->d_tmp[p]);
         for (int s = 0; s < c->nslots; ++s) cudaFree(c->d_slot[s][p]);
     }
-    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_svc_state); cudaFree(c->d_tmaps); cudaFree(c->d_sched); cudaFree(c->d_scratch);
+    cudaFree(c->d_records); cudaFree(c->d_mbstate); cudaFree(c->d_svc_state); cudaFree(c->d_svc_had_parts); cudaFree(c->d_tmaps); cudaFree(c->d_sched); cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_jobs) cudaFreeHost(c->h_jobs);
     cudaFree(c->d_bits); cudaFree(c->d_bits_jobs); cudaFree(c->d_dbk_bs);
@@ -229,6 +229,7 @@ int hlb200_state_reset(hlb200_ctx_t* c)
 {
     if (!c) return HLB200_ERR_INVALID_PARAMETER;
     if (c->d_svc_state) HLB_CUDA(cudaMemsetAsync(c->d_svc_state, 0, sizeof(hlb200_svc_mb_state_t) * c->nmb, c->stream));
+    if (c->d_svc_had_parts) HLB_CUDA(cudaMemsetAsync(c->d_svc_had_parts, 0, c->nmb, c->stream));
     return slice_reset_state(c);
 }
 
@@ -264,6 +265,56 @@ int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp
     }
     if (rc) return rc;
     if ((rc = d2h(c, out_coeffs, d_coeffs, cbytes))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+// A P picture of an SVC enhancement layer with the inter-layer motion derivation on the device as well (second half): the caller hands over the reference
+// layer's macroblock fields instead of a motion field derived macroblock by macroblock on the host (rdo.c:1318-1346 -> utils.c:1225, :1498); k_svc_derive /
+// k_svc_derive_inherit build the field in the context's scratch, k_svc_inter_recon codes the picture with it.  Same results as hlb200_svc_layer_picture with the host's field.
+int hlb200_svc_layer_picture_derived(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp, int chroma_qp_index_offset, const hlb200_svc_base_mb_t* base,
+                                     const hlb200_svc_layer_geom_t* geom, hlb200_mb_motion_t* out_motion, int32_t* out_status, hlb200_mb_coeffs_t* out_coeffs)
+{
+    if (!c || ref_slot < 0 || ref_slot >= c->nslots || cur_slot < 0 || cur_slot >= c->nslots || cur_slot == ref_slot || !out_coeffs || !out_status || !base || !geom || qp < 0 || qp > 51 ||
+        geom->ref_width < 16 || geom->ref_height < 16 || (geom->ref_width & 15) || (geom->ref_height & 15) || geom->ref_width > 16384 || geom->ref_height > 16384)
+        return HLB200_ERR_INVALID_PARAMETER;
+    const size_t nref = (size_t)(geom->ref_width >> 4) * (geom->ref_height >> 4);
+    const size_t mbytes = (sizeof(hlb200_mb_motion_t) * c->nmb + 255) & ~(size_t)255, cbytes = (sizeof(hlb200_mb_coeffs_t) * c->nmb + 255) & ~(size_t)255;
+    const size_t bbytes = (sizeof(hlb200_svc_base_mb_t) * nref + 255) & ~(size_t)255, kbytes = ((size_t)c->nmb + 255) & ~(size_t)255;
+    int rc = ensure_scratch(c, mbytes + cbytes + bbytes + kbytes + 256);
+    if (rc) return rc;
+    if (!c->d_svc_state) {
+        HLB_CUDA(cudaMalloc(&c->d_svc_state, sizeof(hlb200_svc_mb_state_t) * c->nmb));
+        HLB_CUDA(cudaMemsetAsync(c->d_svc_state, 0, sizeof(hlb200_svc_mb_state_t) * c->nmb, c->stream));
+    }
+    if (!c->d_svc_had_parts) {
+        HLB_CUDA(cudaMalloc((void**)&c->d_svc_had_parts, c->nmb));
+        HLB_CUDA(cudaMemsetAsync(c->d_svc_had_parts, 0, c->nmb, c->stream));
+    }
+    char* s = (char*)c->d_scratch;
+    hlb200_mb_motion_t* d_motion = (hlb200_mb_motion_t*)s;
+    hlb200_mb_coeffs_t* d_coeffs = (hlb200_mb_coeffs_t*)(s + mbytes);
+    hlb200_svc_base_mb_t* d_base = (hlb200_svc_base_mb_t*)(s + mbytes + cbytes);
+    uint8_t* d_kind = (uint8_t*)(s + mbytes + cbytes + bbytes);
+    int32_t* d_status = (int32_t*)(s + mbytes + cbytes + bbytes + kbytes);
+    if ((rc = h2d(c, d_base, base, sizeof(hlb200_svc_base_mb_t) * nref))) return rc;
+    HLB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), c->stream));
+    if ((rc = svc_derive_launch(d_base, geom, c->width, c->height, 1, c->d_svc_had_parts, d_motion, d_kind, d_status, c->stream))) return rc;
+    // the status decides whether the picture may be coded at all: one small read-back before the big kernel (a refused picture must not touch the layer's state)
+    int32_t st = 0;
+    if ((rc = d2h(c, &st, d_status, sizeof(st)))) return rc;
+    if (out_motion && (rc = d2h(c, out_motion, d_motion, sizeof(hlb200_mb_motion_t) * c->nmb))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    *out_status = st;
+    if (st) {
+        snprintf(g_err, sizeof(g_err), "hlb200: the derived motion of this enhancement-layer picture has no reproduced reference behaviour (HLB200_SVC_DERIVE_* status %d)", (int)st);
+        return HLB200_ERR_NOT_IMPLEMENTED;
+    }
+    if ((rc = hlb200_dev_svc_inter_recon_batch(c->d_src_cur[0], c->d_src_cur[1], c->d_src_cur[2], c->d_slot[ref_slot][0], c->d_slot[ref_slot][1], c->d_slot[ref_slot][2],
+                                               c->width, c->height, 1, 0, qp, chroma_qp_index_offset, d_motion, (hlb200_svc_mb_state_t*)c->d_svc_state, d_coeffs,
+                                               c->d_slot[cur_slot][0], c->d_slot[cur_slot][1], c->d_slot[cur_slot][2], c->stream)))
+        return rc;
+    if ((rc = d2h(c, out_coeffs, d_coeffs, sizeof(hlb200_mb_coeffs_t) * c->nmb))) return rc;
     HLB_CUDA(cudaStreamSynchronize(c->stream));
     return HLB200_OK;
 }

@@ -63,6 +63,10 @@ inline int host_chroma_qp(int qp_y, int offset)
 
 }  // namespace hlb
 
+// hlb_batch.cu: the two launches of the SVC inter-layer motion derivation (d_kind = n_pics x macroblocks bytes of scratch)
+extern "C" int svc_derive_launch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics, uint8_t* d_had_parts,
+                                 hlb200_mb_motion_t* d_motion, uint8_t* d_kind, int32_t* d_status, cudaStream_t stream);
+
 // context (opaque to C callers)
 struct hlb200_ctx {
     int width, height, mbw, mbh, nmb;
@@ -80,6 +84,7 @@ struct hlb200_ctx {
     void* d_mbstate;                            // per-MB state carried across MBs and frames
     void* d_tmaps;                              // CUtensorMap[nslots] (device): 2D tile descriptors of the frame stores' luma planes for the slice kernel's TMA loads
     void* d_svc_state;                          // hlb200_svc_mb_state_t[nmb] when the context is an SVC enhancement layer (allocated on first use)
+    uint8_t* d_svc_had_parts;                   // SVC enhancement layer with the motion derivation on the device: one byte per macroblock carried from picture to picture (hlb_svc_derive.cuh)
     void* d_sched; size_t sched_bytes;          // job descriptors + ready-queue scheduler words (hlb_slice.cu)
     void* h_jobs; int h_jobs_cap;               // pinned staging of the job descriptors
     int* last_sched;                            // scheduler words of the last launch (watchdog status)

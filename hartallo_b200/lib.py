@@ -17,6 +17,10 @@ MB_MOTION = np.dtype([("part_mode", "u1"), ("sub_mode", "u1", (4,)), ("ref_idx",
 MB_COEFFS = np.dtype([("luma_level", "<i2", (16, 16)), ("chroma_dc_level", "<i2", (2, 4)), ("chroma_ac_level", "<i2", (2, 4, 16)),
                       ("cbp_luma4x4", "<u2"), ("cbp_chroma_dc4x4", "u1", (2,)), ("cbp_chroma_ac4x4", "u1", (2,)), ("pad", "u1", (2,))])
 SVC_STATE = np.dtype([("chroma_ac_level", "<i2", (2, 4, 16)), ("chroma_dc_level", "<i2", (2, 4))])   # hlb200_svc_mb_state_t
+SVC_BASE_MB = np.dtype([("flags", "u1"), ("part_w", "u1"), ("part_h", "u1"), ("sub_w", "u1", (4,)), ("sub_h", "u1", (4,)), ("pred_flag", "i1", (4,)), ("ref_idx", "i1", (4,)),
+                        ("pad", "u1"), ("mv", "<i2", (4, 4, 2))])   # hlb200_svc_base_mb_t
+SVC_GEOM = np.dtype([("ref_width", "<i4"), ("ref_height", "<i4"), ("scaled_width", "<i4"), ("scaled_height", "<i4"), ("left_offset", "<i4"), ("top_offset", "<i4"),
+                     ("level_idc", "<i4"), ("restricted", "<i4"), ("cropping_change", "<i4")])   # hlb200_svc_layer_geom_t
 ME_CAND = np.dtype([("mb_x", "<i2"), ("mb_y", "<i2"), ("part_x", "u1"), ("part_y", "u1"), ("part_w", "u1"), ("part_h", "u1"), ("mv_x", "<i2"), ("mv_y", "<i2")])
 ME_COST = np.dtype([("dist", "<i4"), ("bits_rest", "<i4"), ("single_ctr", "<i4"), ("cbp_luma4x4", "<u2"), ("total_coeff", "u1", (16,)),
                     ("trailing_ones", "u1", (16,)), ("pad", "<u2")])
@@ -64,6 +68,8 @@ def load():
         "hlb200_dev_svc_inter_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp, vp],
         "hlb200_svc_layer_picture": [vp, ip, ip, ip, ip, vp, vp, vp, vp, vp],
         "hlb200_svc_layer_picture_resampled": [vp, ip, ip, ip, vp, vp, vp, ip, ip, ip, vp],
+        "hlb200_dev_svc_derive_motion_batch": [vp, vp, ip, ip, ip, vp, vp, vp, vp],
+        "hlb200_svc_layer_picture_derived": [vp, ip, ip, ip, ip, vp, vp, vp, C.POINTER(C.c_int32), vp],
         "hlb200_dev_svc_resample_intra_batch": [vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, C.c_size_t, C.c_size_t, ip, vp],
         "hlb200_dev_svc_bl_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp],
         "hlb200_dev_me_cost": [vp, vp, ip, ip, ip, vp, ip, vp, vp], "hlb200_dev_int_alu_probe": [ip, ip, vp, vp, C.POINTER(C.c_uint64)],
@@ -166,6 +172,17 @@ class Stream:
             rc = self.lib.hlb200_svc_layer_picture(self.ctx, ref_slot, cur_slot, qp, chroma_qp_index_offset, ptr(m), None, None, None, ptr(coeffs))
         check(rc, "svc_layer_picture")
         return coeffs, self.download_slot(cur_slot)
+
+    def svc_layer_picture_derived(self, qp, base, geom, ref_slot=0, cur_slot=1, chroma_qp_index_offset=0):
+        """a P picture of an SVC enhancement layer, inter-layer motion derivation on the device too: base = the reference layer's macroblock fields (SVC_BASE_MB),
+        geom = SVC_GEOM[1]; returns (coefficients, reconstruction, derived motion, status bits); a refused picture (status != 0) returns (None, None, motion, status)"""
+        coeffs, motion, st = np.zeros(self.nmb, MB_COEFFS), np.zeros(self.nmb, MB_MOTION), C.c_int32(0)
+        b, g = np.ascontiguousarray(base), np.ascontiguousarray(geom)
+        rc = self.lib.hlb200_svc_layer_picture_derived(self.ctx, ref_slot, cur_slot, qp, chroma_qp_index_offset, ptr(b), ptr(g), ptr(motion), C.byref(st), ptr(coeffs))
+        if rc == 7 and st.value:
+            return None, None, motion, st.value
+        check(rc, "svc_layer_picture_derived")
+        return coeffs, self.download_slot(cur_slot), motion, 0
 
     def svc_layer_picture_resampled(self, qp, ref_layer_yuv, ref_w, ref_h, cur_slot=1, chroma_qp_index_offset=0, level_idc=0):
         """an I picture of an SVC enhancement layer, Intra_Base resampling on the device too: ref_layer_yuv = the reference layer's reconstruction (tight Y|U|V)"""

@@ -202,10 +202,15 @@ static HL_ERROR_T glue_check_settings(const hl_codec_264_t* p_codec)
 
 /* ================================================================================================================================
  * SVC enhancement layers (currDQId > 0).  The reference does no search there (base_mode_flag = 1 for every macroblock): what it computes per
- * macroblock is (a) the inter-layer derivation of partitions / vectors (P) or the resampling of the base reconstruction (I) -- host code, serial,
- * reads the reference layer only -- and (b) prediction + residual coding + reconstruction, hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 /
- * ..._intra_pred_svc rdo.c:301.  (b) is independent per macroblock, so the hook runs (a) for the whole picture first, hands the picture to the device
- * in ONE call (hlb200_svc_layer_picture) and lets the reference's own loop serialise the result.
+ * macroblock is (a) the inter-layer derivation of partitions / vectors (P; utils.c:1225 + :1498) or the resampling of the base reconstruction (I;
+ * decode_svc.c:2864) -- both read the reference layer only -- and (b) prediction + residual coding + reconstruction,
+ * hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 / ..._intra_pred_svc rdo.c:301.  All of it is independent per macroblock, so the hook hands the
+ * WHOLE picture to the device in ONE call -- hlb200_svc_layer_picture_derived (P: derivation kernel + fused prediction / residual kernel, from the
+ * reference layer's macroblock fields) or hlb200_svc_layer_picture_resampled (I: resampling kernel + residual kernel, from the reference layer's
+ * reconstruction) -- and then lets the reference's own loop serialise the result.  Inside that loop the wrapped guess functions still call the reference's
+ * derivation for each macroblock: the reference's writer and the NEXT layer's derivation read the macroblock object's syntax fields (mb_type, sub_mb_type,
+ * refIdx, mv, flags), which is bookkeeping the north star leaves on the host; no sample and no level depends on it, and the device's field is cross-checked
+ * against it macroblock by macroblock (glue_svc_apply).
  * ================================================================================================================================ */
 #include "hartallo/h264/hl_codec_264_utils.h"
 #include "hartallo/h264/hl_codec_264_sps.h"
@@ -214,9 +219,10 @@ static HL_ERROR_T glue_check_settings(const hl_codec_264_t* p_codec)
 typedef struct glue_svc_layer_s {
     hlb200_ctx_t* ctx;
     int w, h, nmb;
-    hlb200_mb_motion_t* motion;
+    hlb200_mb_motion_t* motion;   /* the motion field the device derived for the picture (read back for the cross-check in glue_svc_apply) */
     hlb200_mb_coeffs_t* coeffs;
     uint8_t* rec;            /* tight Y|U|V */
+    hlb200_svc_base_mb_t* base; int nbase;   /* the reference layer's macroblock fields, as uploaded for the derivation */
 } glue_svc_layer_t;
 static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
 static glue_svc_layer_t* g_svc_active = NULL;
@@ -280,7 +286,9 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     const size_t ysz = (size_t)W * H, csz = (size_t)Wc * Hc;
     glue_svc_layer_t* L;
     HL_ERROR_T err;
-    int rc, qp = -1, last_with_parts = -1, dev_rs = 0, level_idc = 0;
+    int rc, qp = -1, dev_rs = 0, level_idc = 0;
+    int32_t status = 0;
+    hlb200_svc_layer_geom_t geom;
     uint32_t addr;
 
     if (li <= 0 || li >= GLUE_SVC_MAX_LAYERS || (p_codec->layers.currDQId & 15) || p_esd->i_mb_start != 0 || p_esd->i_mb_end != (int32_t)hdr->PicSizeInMbs) {
@@ -313,7 +321,7 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     L = &g_svc[li];
     if (!L->ctx || L->w != W || L->h != H) {
         const char* dev = getenv("HLB200_DEVICE");
-        if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; }
+        if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); free(L->base); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; L->base = NULL; L->nbase = 0; }
         if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
         if ((rc = hlb200_stream_create(W, H, 1, &L->ctx))) return glue_fail("hlb200_stream_create", rc);
         L->w = W; L->h = H; L->nmb = mbw * (H >> 4);
@@ -325,42 +333,49 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
             return HL_ERROR_OUTOFMEMMORY;
         }
     }
-    /* (a) host, serial: inferred motion (P) or resampled base-layer prediction (I) of every macroblock */
-    memset(L->motion, 0, sizeof(hlb200_mb_motion_t) * (size_t)L->nmb);
-    for (addr = 0; addr < (uint32_t)L->nmb; ++addr) {
+    /* (a) what the device needs besides the pictures.  I pictures: nothing (the resampling runs there).  P pictures: the reference layer's macroblock fields the
+     * inter-layer derivation reads (utils.c:1701, mb.h:313-339, utils.c:1807-1834), copied verbatim from the reference layer's macroblock objects -- 84 bytes per
+     * reference-layer macroblock; the derivation itself (utils.c:1225 + :1498 per macroblock) runs on the device (hlb_svc_derive.cuh).  The QP is the slice's: the
+     * prologue of macroblock 0 computes it exactly as the reference's loop will (per-macroblock QP needs rate control, which glue_check_settings refuses). */
+    {
         hl_codec_264_mb_t* p_mb;
-        if ((err = glue_svc_loop_prologue(p_codec, p_esd, addr, &p_mb))) return err;
-        if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;
-        if (qp < 0) qp = p_mb->QPy;
-        if (p_mb->QPy != qp) { HL_DEBUG_ERROR("hlb200: per-macroblock QP is not supported"); return HL_ERROR_NOT_IMPLEMENTED; }
-        if (!intra) {
-            hlb200_mb_motion_t* m = &L->motion[addr];
-            const int n = p_mb->NumMbPart, pw = p_mb->MbPartWidth, ph = p_mb->MbPartHeight;
-            const int mode = (n == 1 && pw == 16 && ph == 16) ? 0 : (n == 2 && pw == 16 && ph == 8) ? 1 : (n == 2 && pw == 8 && ph == 16) ? 2 : (n == 4 && pw == 8 && ph == 8) ? 3 : -1;
-            int p, ok = mode >= 0;
-            for (p = 0; ok && p < n; ++p) ok = p_mb->NumSubMbPart[p] >= 1 && p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == 0 && p_mb->partWidth[p][0] == pw && p_mb->partHeight[p][0] == ph;
-            if (!ok && getenv("HLB200_GLUE_DEBUG"))
-                fprintf(stderr, "hlb200 glue: layer %d mb %u: NumMbPart %d %dx%d NumSubMbPart %d %d %d %d predFlagL0 %d %d %d %d refIdxL0 %d %d %d %d e_type %d\n", li, addr, n, pw, ph,
-                        p_mb->NumSubMbPart[0], p_mb->NumSubMbPart[1], p_mb->NumSubMbPart[2], p_mb->NumSubMbPart[3], p_mb->predFlagL0[0], p_mb->predFlagL0[1], p_mb->predFlagL0[2],
-                        p_mb->predFlagL0[3], p_mb->refIdxL0[0], p_mb->refIdxL0[1], p_mb->refIdxL0[2], p_mb->refIdxL0[3], (int)p_mb->e_type);
-            if (ok) {
-                m->part_mode = (uint8_t)mode;
-                for (p = 0; p < n; ++p) { m->mv[p][0][0] = (int16_t)p_mb->mvL0[p][0].x; m->mv[p][0][1] = (int16_t)p_mb->mvL0[p][0].y; }
-                last_with_parts = (int)addr;
-            }
-            else if (n == 1 && p_mb->NumSubMbPart[0] == 0 && last_with_parts >= 0 && last_with_parts < 65536) {
-                /* base macroblock intra: no partition, the reference's prediction loops do not run and it codes the macroblock against what its scratch blocks
-                 * still hold = the prediction of the last macroblock that had partitions; the device does the same (hlb_svc.cuh: SvcPredSrc) */
-                m->pad[0] = 1; m->pad[1] = (uint8_t)(last_with_parts & 255); m->pad[2] = (uint8_t)(last_with_parts >> 8);
-            }
-            else {
-                /* A macroblock without partitions that precedes every macroblock with partitions of its picture: the reference codes it against scratch memory an
-                 * EARLIER picture left (after a layer's I picture: the I_BL function's int32 temporaries, rdo.c:1304-1312 / rdo.c:344-349 / hl_memory.h:226-241).
-                 * Not reproduced on the device, and never handed to the reference's CPU function: the picture is refused. */
-                HL_DEBUG_ERROR("hlb200: layer %d macroblock %u has no partition and no earlier macroblock of the picture to inherit a prediction from: not implemented by the device path", li, addr);
-                return HL_ERROR_NOT_IMPLEMENTED;
+        if ((err = glue_svc_loop_prologue(p_codec, p_esd, 0, &p_mb))) return err;
+        qp = p_mb->QPy;
+    }
+    if (!intra) {
+        const hl_codec_264_layer_t* rl = pc_layer->pc_ref;
+        const hl_codec_264_layer_t* top = p_codec->layers.p_list[(p_codec->layers.currDQId >> 4) << 4];
+        const uint32_t nref = (pc_layer->RefLayerPicWidthInSamplesL >> 4) * (pc_layer->RefLayerPicHeightInSamplesL >> 4);
+        if (!rl || rl == pc_layer || !top || !top->pc_slice_hdr || rl->u_list_macroblocks_count < nref || hdr->field_pic_flag || hdr->MbaffFrameFlag || pc_layer->RefLayerMbaffFrameFlag ||
+            pc_layer->RefLayerFieldPicFlag || !IsSliceHeaderEP(hdr)) {
+            HL_DEBUG_ERROR("hlb200: the inter-layer motion derivation of this picture (field / MBAFF coding, B slices or a missing reference layer) is not implemented by the device path");
+            return HL_ERROR_NOT_IMPLEMENTED;
+        }
+        if (L->nbase < (int)nref) {
+            free(L->base);
+            if (!(L->base = (hlb200_svc_base_mb_t*)calloc(nref, sizeof(hlb200_svc_base_mb_t)))) { L->nbase = 0; return HL_ERROR_OUTOFMEMMORY; }
+            L->nbase = (int)nref;
+        }
+        for (addr = 0; addr < nref; ++addr) {
+            const hl_codec_264_mb_t* b = rl->pp_list_macroblocks[addr];
+            hlb200_svc_base_mb_t* o = &L->base[addr];
+            int p, q;
+            memset(o, 0, sizeof(*o));
+            if (!b) { HL_DEBUG_ERROR("hlb200: reference-layer macroblock %u does not exist", addr); return HL_ERROR_INVALID_STATE; }
+            o->flags = (uint8_t)(((HL_CODEC_264_MB_TYPE_IS_I_PCM(b) || HL_CODEC_264_MB_TYPE_IS_I_16X16(b) || HL_CODEC_264_MB_TYPE_IS_I_8X8(b) || HL_CODEC_264_MB_TYPE_IS_I_4X4(b) || HL_CODEC_264_MB_TYPE_IS_I_BL(b)) ? 1 : 0) |
+                                 (HL_CODEC_264_MB_TYPE_IS_INTRA(b) ? 2 : 0) | ((b->e_type == HL_CODEC_264_MB_TYPE_P_8X8 || b->e_type == HL_CODEC_264_MB_TYPE_P_8X8REF0) ? 4 : 0));
+            o->part_w = (uint8_t)b->MbPartWidth; o->part_h = (uint8_t)b->MbPartHeight;
+            for (p = 0; p < 4; ++p) {
+                o->sub_w[p] = (uint8_t)b->SubMbPartWidth[p]; o->sub_h[p] = (uint8_t)b->SubMbPartHeight[p];
+                o->pred_flag[p] = (int8_t)b->predFlagL0[p]; o->ref_idx[p] = (int8_t)b->refIdxL0[p];
+                for (q = 0; q < 4; ++q) { o->mv[p][q][0] = (int16_t)b->mvL0[p][q].x; o->mv[p][q][1] = (int16_t)b->mvL0[p][q].y; }
             }
         }
+        geom.ref_width = (int32_t)pc_layer->RefLayerPicWidthInSamplesL; geom.ref_height = (int32_t)pc_layer->RefLayerPicHeightInSamplesL;
+        geom.scaled_width = (int32_t)hdr->ext.svc.ScaledRefLayerPicWidthInSamplesL; geom.scaled_height = (int32_t)hdr->ext.svc.ScaledRefLayerPicHeightInSamplesL;
+        geom.left_offset = (int32_t)hdr->ext.svc.ScaledRefLayerLeftOffset; geom.top_offset = (int32_t)hdr->ext.svc.ScaledRefLayerTopOffset;
+        geom.level_idc = (int32_t)top->pc_slice_hdr->pc_pps->pc_sps->level_idc;
+        geom.restricted = (int32_t)pc_layer->RestrictedSpatialResolutionChangeFlag; geom.cropping_change = (int32_t)pc_layer->CroppingChangeFlag;
     }
     /* (b) device: one call for the picture */
     if ((rc = hlb200_frame_upload(L->ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, Wc))) return glue_fail("hlb200_frame_upload", rc);
@@ -375,7 +390,15 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
         const hl_codec_264_pict_t* ref = pc_layer->pobj_poc->RefPicList0[0] ? pc_layer->pobj_poc->RefPicList0[0]->p_pict : NULL;
         if (!ref) return HL_ERROR_INVALID_STATE;
         if ((rc = hlb200_slot_upload(L->ctx, 0, ref->pc_data_y, ref->pc_data_u, ref->pc_data_v))) return glue_fail("hlb200_slot_upload", rc);
-        rc = hlb200_svc_layer_picture(L->ctx, 0, 1, qp, hdr->pc_pps->chroma_qp_index_offset, L->motion, NULL, NULL, NULL, L->coeffs);
+        rc = hlb200_svc_layer_picture_derived(L->ctx, 0, 1, qp, hdr->pc_pps->chroma_qp_index_offset, L->base, &geom, L->motion, &status, L->coeffs);
+        if (rc == HLB200_ERR_NOT_IMPLEMENTED) {
+            /* status bits (hlb200.h HLB200_SVC_DERIVE_*): partitions the fused kernel is not pinned for, a macroblock whose base macroblock is intra while its object still holds
+             * partitions of an earlier picture, or one with no earlier macroblock of the picture to inherit a prediction from -- after a layer's I picture the reference codes
+             * those against scratch memory of the I_BL function (rdo.c:1304-1312 / rdo.c:344-349 / hl_memory.h:226-241).  Not reproduced, never handed to the reference's CPU
+             * function: the picture is refused. */
+            HL_DEBUG_ERROR("hlb200: layer %d: the derived motion of this picture is outside what the device path reproduces (status bits %d): not implemented", li, (int)status);
+            return HL_ERROR_NOT_IMPLEMENTED;
+        }
     }
     if (rc) return glue_fail("hlb200_svc_layer_picture", rc);
     if ((rc = hlb200_slot_download(L->ctx, 1, L->rec, L->rec + ysz, L->rec + ysz + csz))) return glue_fail("hlb200_slot_download", rc);
@@ -396,7 +419,24 @@ static HL_ERROR_T glue_svc_apply(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_code
     HL_ERROR_T err;
     int b, i, k, y, i8;
     if (p_mb->u_addr >= (uint32_t)L->nmb) return HL_ERROR_INVALID_STATE;
-    if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;   /* the fields later layers / pictures derive from */
+    if ((err = glue_svc_derive(p_mb, p_codec, intra))) return err;   /* the syntax fields the writer serialises and later layers / pictures derive from */
+    if (!intra) {
+        /* the device coded the macroblock with ITS derivation of the same reference-layer fields: both must agree, or the stream would silently diverge */
+        const hlb200_mb_motion_t* m = &L->motion[p_mb->u_addr];
+        static const int N[4] = { 1, 2, 2, 4 }, PW[4] = { 16, 16, 8, 8 }, PH[4] = { 16, 8, 16, 8 };
+        int p, same;
+        if (m->pad[0] & 1) same = p_mb->predFlagL0[0] == 0 && HL_CODEC_264_MB_TYPE_IS_I_BL(p_mb);
+        else {
+            same = m->part_mode < 4 && p_mb->NumMbPart == N[m->part_mode] && p_mb->MbPartWidth == PW[m->part_mode] && p_mb->MbPartHeight == PH[m->part_mode];
+            for (p = 0; same && p < N[m->part_mode]; ++p)
+                same = p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == m->ref_idx[p] && p_mb->mvL0[p][0].x == m->mv[p][0][0] && p_mb->mvL0[p][0].y == m->mv[p][0][1] &&
+                       p_mb->partWidth[p][0] == PW[m->part_mode] && p_mb->partHeight[p][0] == PH[m->part_mode];
+        }
+        if (!same) {
+            HL_DEBUG_ERROR("hlb200: macroblock %u: the motion derived on the device differs from the reference's derivation", p_mb->u_addr);
+            return HL_ERROR_INVALID_STATE;
+        }
+    }
     c = &L->coeffs[p_mb->u_addr];
     p_mb->CodedBlockPatternLuma4x4 = c->cbp_luma4x4;
     for (b = 0; b < 16; ++b) for (i = 0; i < 16; ++i) p_mb->LumaLevel[b][i] = c->luma_level[b][i];

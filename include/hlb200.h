@@ -25,6 +25,8 @@
  *                              _hl_codec_264_rdo_mb_reconstruct_chroma rdo.c:2502 (whole-frame batch)
  *   hlb200_dev_svc_inter_recon_batch  hl_codec_264_rdo_mb_guess_best_inter_pred_svc rdo.c:1273 (SVC enhancement layer, base-mode inter
  *                              macroblocks: prediction + residual coding + reconstruction fused, whole-picture batch)
+ *   hlb200_dev_svc_derive_motion_batch   hl_codec_264_utils_derivation_process_initialisation_svc utils.c:1225 + ..._for_mv_comps_and_ref_indices_svc utils.c:1498
+ *                                        (inter-layer motion derivation, P pictures with base_mode_flag = 1)
  *   hlb200_dev_svc_resample_intra_batch  _hl_codec_264_decode_svc_resample_intra_colour_comps decode_svc.c:2864 (Intra_Base resampling, I pictures)
  *   hlb200_dev_svc_bl_recon_batch     hl_codec_264_rdo_mb_guess_best_intra_pred_svc rdo.c:301 (I_BL macroblocks: residual coding + reconstruction
  *                              against the host-resampled base layer)
@@ -150,6 +152,33 @@ typedef struct hlb200_svc_mb_state {
     int16_t chroma_dc_level[2][4];
 } hlb200_svc_mb_state_t;
 
+/* What the SVC inter-layer motion derivation reads of one REFERENCE-LAYER macroblock: the fields of hl_codec_264_mb_t that utils.c:1701 (intra test),
+ * mb.h:313-339 (partition indices of a luma location) and utils.c:1807-1834 (predFlagL0 / refIdxL0 / mvL0) touch, copied verbatim -- stale values included, the
+ * reference's macroblock objects are never reset (utils.c:73-89). */
+typedef struct hlb200_svc_base_mb {
+    uint8_t flags;                /* bit 0: e_type is I_PCM / I_16X16 / I_8X8 / I_4X4 / I_BL (utils.c:1701); bit 1: HL_CODEC_264_MB_TYPE_IS_INTRA (flags_type, mb.h:322);
+                                     bit 2: e_type is P_8X8 / P_8X8REF0 (mb.h:329) */
+    uint8_t part_w, part_h;       /* MbPartWidth, MbPartHeight */
+    uint8_t sub_w[4], sub_h[4];   /* SubMbPartWidth, SubMbPartHeight */
+    int8_t pred_flag[4];          /* predFlagL0 */
+    int8_t ref_idx[4];            /* refIdxL0 */
+    uint8_t pad;
+    int16_t mv[4][4][2];          /* mvL0 */
+} hlb200_svc_base_mb_t;
+
+/* Geometry of one enhancement-layer picture relative to its reference layer (layer.c:104-157, slice header SVC extension) */
+typedef struct hlb200_svc_layer_geom {
+    int32_t ref_width, ref_height;         /* RefLayerPicWidthInSamplesL / RefLayerPicHeightInSamplesL */
+    int32_t scaled_width, scaled_height;   /* ScaledRefLayerPicWidthInSamplesL / ScaledRefLayerPicHeightInSamplesL */
+    int32_t left_offset, top_offset;       /* ScaledRefLayerLeftOffset / ScaledRefLayerTopOffset */
+    int32_t level_idc;                     /* of the SPS utils.c:989 reads */
+    int32_t restricted;                    /* RestrictedSpatialResolutionChangeFlag (layer.c:143); 0 is refused */
+    int32_t cropping_change;               /* CroppingChangeFlag (layer.c:104); 1 is refused */
+} hlb200_svc_layer_geom_t;
+
+/* status bits of a derived picture (hlb200_dev_svc_derive_motion_batch); any bit = the picture has no reproduced reference behaviour */
+enum { HLB200_SVC_DERIVE_BAD_REF = 1, HLB200_SVC_DERIVE_UNSUPPORTED = 2, HLB200_SVC_DERIVE_STALE_PARTS = 4, HLB200_SVC_DERIVE_NO_PRED_SOURCE = 8 };
+
 /* One independent ME candidate for hlb200_me_cost (me_ds.c:527): partition rectangle inside MB (mb_x, mb_y) */
 typedef struct hlb200_me_cand {
     int16_t mb_x, mb_y;     /* macroblock coordinates */
@@ -212,6 +241,14 @@ HLB200_API int hlb200_slice_last_variant(void);   /* variant the most recent sli
  * carries from picture to picture lives in the context (hlb200_state_reset clears it). ---- */
 HLB200_API int hlb200_svc_layer_picture(hlb200_ctx_t* ctx, int ref_slot, int cur_slot, int qp, int chroma_qp_index_offset, const hlb200_mb_motion_t* motion,
                                         const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v, hlb200_mb_coeffs_t* out_coeffs);
+/* The P picture of an enhancement layer with the inter-layer motion derivation on the device as well (second half; replaces the per-macroblock calls of
+ * hl_codec_264_utils_derivation_process_initialisation_svc utils.c:1225 + ..._for_mv_comps_and_ref_indices_svc utils.c:1498 that rdo.c:1318-1346 makes before it predicts):
+ * `base` = the reference layer's macroblock fields (host array, (ref_width / 16) x (ref_height / 16) entries).  k_svc_derive turns them into the layer's motion field on the
+ * device, k_svc_inter_recon codes the picture with it.  out_motion (optional) receives the derived field, *out_status the HLB200_SVC_DERIVE_* bits; when any is set the
+ * call returns HLB200_ERR_NOT_IMPLEMENTED and cur_slot / out_coeffs hold nothing usable.  The context keeps, per macroblock, whether an earlier picture left partitions
+ * in the reference's macroblock object (hlb200_state_reset clears it). */
+HLB200_API int hlb200_svc_layer_picture_derived(hlb200_ctx_t* ctx, int ref_slot, int cur_slot, int qp, int chroma_qp_index_offset, const hlb200_svc_base_mb_t* base,
+                                                const hlb200_svc_layer_geom_t* geom, hlb200_mb_motion_t* out_motion, int32_t* out_status, hlb200_mb_coeffs_t* out_coeffs);
 /* The same for an I picture with the Intra_Base resampling on the device too (hlb200_dev_svc_resample_intra_batch below; decode_svc.c:2864-3200): the caller passes
  * the reference layer's reconstruction (host planes, ref_width x ref_height) instead of full-size prediction planes.  Restrictions of that entry point apply
  * (no cropping offsets, the reference's chroma phases, no power-of-two reference dimension when level_idc > 30): HLB200_ERR_INVALID_PARAMETER otherwise. */
@@ -260,6 +297,15 @@ HLB200_API int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const ui
                                                 const uint8_t* d_ref_v, int width, int height, int n_pics, size_t frame_stride, int qp, int chroma_qp_index_offset,
                                                 const hlb200_mb_motion_t* d_motion, hlb200_svc_mb_state_t* d_state, hlb200_mb_coeffs_t* d_coeffs,
                                                 uint8_t* d_recon_y, uint8_t* d_recon_u, uint8_t* d_recon_v, void* cuda_stream);
+/* Inter-layer motion derivation for enhancement-layer P pictures with base_mode_flag = 1 -- hl_codec_264_utils_derivation_process_initialisation_svc
+ * utils.c:1225 (G.8.6.1.1 utils.c:1677, G.8.6.1.2 utils.c:1779, G.8.6.1.3 utils.c:1986) and ..._for_mv_comps_and_ref_indices_svc utils.c:1498 (G.8.4.1), with the
+ * reference-layer lookups of utils.c:966-1059 / mb.h:313-339: d_base = n_pics x reference-layer macroblocks, d_motion = n_pics x (width / 16) x (height / 16) derived
+ * macroblocks (partition layout, refIdxL0, mvL0; macroblocks whose base macroblock is intra carry the address of the macroblock whose prediction they inherit in pad[],
+ * as hlb200_dev_svc_inter_recon_batch reads it), d_had_parts = one byte per derived macroblock carried from picture to picture of a layer (zero for a new layer),
+ * d_status = one int32 per picture, HLB200_SVC_DERIVE_* bits OR-ed in (the caller zeroes it).  Frame macroblocks, RestrictedSpatialResolutionChangeFlag = 1,
+ * CroppingChangeFlag = 0; anything else returns HLB200_ERR_NOT_IMPLEMENTED. */
+HLB200_API int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics,
+                                                  uint8_t* d_had_parts, hlb200_mb_motion_t* d_motion, int32_t* d_status, void* cuda_stream);
 /* I_BL macroblocks (enhancement-layer I pictures) -- hl_codec_264_rdo_mb_guess_best_intra_pred_svc, rdo.c:301-461: the prediction is the base-layer reconstruction
  * resampled by the host (G.8.6.2.1, _hl_codec_264_decode_svc_resample_intra_colour_comps, source/h264/hl_codec_264_decode_svc.c:216) and arrives as
  * planes; residual coding and reconstruction are those of the base-mode inter macroblock above (rdo.c:387-446). */

@@ -621,3 +621,146 @@ HLO_API void hlo_svc_resample_intra_yuv(const uint8_t* ref_yuv, int refW, int re
     hlo_svc_resample_intra_plane(ref_yuv + refW * refH, refW >> 1, refH >> 1, W >> 1, H >> 1, 1, level_idc, out_yuv + W * H);
     hlo_svc_resample_intra_plane(ref_yuv + refW * refH + rc, refW >> 1, refH >> 1, W >> 1, H >> 1, 1, level_idc, out_yuv + W * H + oc);
 }
+
+/* --- SVC inter-layer motion derivation for an enhancement-layer P macroblock with base_mode_flag = 1 -------------------------------------------
+ * What rdo.c:1318-1346 has computed before it predicts: hl_codec_264_utils_derivation_process_initialisation_svc (utils.c:1225) followed by
+ * hl_codec_264_utils_derivation_process_for_mv_comps_and_ref_indices_svc (utils.c:1498).  Restated clause by clause with the reference's own intermediate arrays
+ * (refLayerPartIdc, tempRefIdxPredL0, mvILPredL0, refIdxILPredL0), for frame macroblocks, EP slices, RestrictedSpatialResolutionChangeFlag = 1 and
+ * CroppingChangeFlag = 0 -- the case the reference can be run on here (layers of equal or doubled size).  PINNED by tests/test_svc_derive.py against the
+ * reference's trace (oracle/ref_driver.c tags 11 and 6: tests/golden/svc_derive.npz and, in the build container, live runs).
+ * base records: 53 int32 per reference-layer macroblock in the order of tag 11 (intra by e_type, flags_type intra, e_type P_8X8 / P_8X8REF0, MbPartWidth, MbPartHeight,
+ * SubMbPartWidth[4], SubMbPartHeight[4], predFlagL0[4], refIdxL0[4], mvL0[4][4][2]).
+ * out16: [0] intraILPredFlag, [1] NumMbPart, [2] MbPartWidth, [3] MbPartHeight, [4..7] NumSubMbPart, [8..11] SubMbPartWidth, [12..15] SubMbPartHeight (entries of the
+ * partitions that exist); ref_idx4 = refIdxL0[4]; mv32 = mvL0[4][4][2].
+ * Returns 0, or -1 when a block maps outside the reference layer / onto an object the reference would divide by zero on / intra and inter blocks mix. */
+static int svc_il_floor_div(int a, int b) { return a / b; }   /* operands are non-negative wherever the reference divides */
+HLO_API int hlo_svc_derive_mb(const int32_t* base, int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int mb_x, int mb_y,
+                              int32_t* out16, int32_t* ref_idx4, int32_t* mv32)
+{
+    const int ref_mbw = ref_w >> 4, nref = ref_mbw * (ref_h >> 4);
+    /* utils.c:988-993 (G-7..G-10) */
+    const int shiftX = level_idc <= 30 ? 16 : 31 - svc_ceil_log2(ref_w), shiftY = level_idc <= 30 ? 16 : 31 - svc_ceil_log2(ref_h);
+    const int scaleX = (int)((((long long)ref_w << shiftX) + (scaled_w >> 1)) / scaled_w), scaleY = (int)((((long long)ref_h << shiftY) + (scaled_h >> 1)) / scaled_h);
+    int refLayerPartIdc[4][4], tempRefIdxPredL0[4][4], mvILPredL0[4][4][2], refIdxILPredL0[2][2];
+    int x, y, intraILPredFlag = 1, any_intra = 0, i;
+    memset(out16, 0, 16 * sizeof(int32_t)); memset(ref_idx4, 0, 4 * sizeof(int32_t)); memset(mv32, 0, 32 * sizeof(int32_t));
+    /* G.8.6.1.1, utils.c:1690-1711 */
+    for (y = 0; y < 4; ++y)
+        for (x = 0; x < 4; ++x) {
+            const int xP = (x << 2) + 1, yP = (y << 2) + 1;
+            /* G.6.1, utils.c:995-1003 (frame macroblock in a frame picture: yC = yM + yP) */
+            const int xC = mb_x * 16 + xP, yC = mb_y * 16 + yP;
+            int xRef = (int)(((unsigned)(xC - off_x) * (unsigned)scaleX + (1u << (shiftX - 1)))) >> shiftX;
+            int yRef = (int)(((unsigned)(yC - off_y) * (unsigned)scaleY + (1u << (shiftY - 1)))) >> shiftY;
+            int addr, xB, yB, mbPartIdx, subMbPartIdx;
+            const int32_t* b;
+            if (xRef > ref_w - 1) xRef = ref_w - 1;
+            if (yRef > ref_h - 1) yRef = ref_h - 1;
+            if (xRef < 0 || yRef < 0) return -1;
+            addr = (yRef >> 4) * ref_mbw + (xRef >> 4);   /* (G-15) */
+            if (addr >= nref) return -1;
+            xB = xRef & 15; yB = yRef & 15;
+            b = base + 53 * addr;
+            if (b[0]) { refLayerPartIdc[y][x] = -1; any_intra = 1; continue; }   /* utils.c:1701-1703 */
+            /* G.6.4 -> 6.4.12.4 as mb.h:313-339 */
+            if (b[1]) mbPartIdx = 0;
+            else {
+                if (b[3] <= 0 || b[4] <= 0) return -1;
+                mbPartIdx = svc_il_floor_div(16, b[3]) * svc_il_floor_div(yB, b[4]) + svc_il_floor_div(xB, b[3]);
+            }
+            if (mbPartIdx > 3) return -1;
+            if (!b[2]) subMbPartIdx = 0;
+            else {
+                const int sw = b[5 + mbPartIdx], sh = b[9 + mbPartIdx];
+                if (sw <= 0 || sh <= 0) return -1;
+                subMbPartIdx = svc_il_floor_div(8, sw) * svc_il_floor_div(yB % 8, sh) + svc_il_floor_div(xB % 8, sw);
+            }
+            if (subMbPartIdx > 3) return -1;
+            refLayerPartIdc[y][x] = (addr << 4) + (mbPartIdx << 2) + subMbPartIdx;   /* (G-209) */
+            intraILPredFlag = 0;
+        }
+    if (intraILPredFlag) {   /* utils.c:1272-1287: I_BL, G.8.4.1 then clears the motion (utils.c:1510-1528) */
+        out16[0] = 1; out16[1] = 1; out16[2] = out16[3] = 16;
+        for (i = 0; i < 4; ++i) ref_idx4[i] = -1;
+        return 0;
+    }
+    if (any_intra) return -1;   /* would need the replacement steps of the unrestricted case (G-210..G-215) */
+    /* G.8.6.1.2, utils.c:1793-1880 */
+    {
+        const int mvScaleX = (int)((((long long)scaled_w << 16) + (ref_w >> 1)) / ref_w), mvScaleY = (int)((((long long)scaled_h << 16) + (ref_h >> 1)) / ref_h);   /* (G-232), (G-233) */
+        for (y = 0; y < 4; ++y)
+            for (x = 0; x < 4; ++x) {
+                const int idc = refLayerPartIdc[y][x], refMbAddr = idc >> 4, refMbPartIdx = (idc & 15) >> 2, refSubMbPartIdx = idc & 3;   /* (G-219)..(G-221) */
+                const int32_t* b = base + 53 * refMbAddr;
+                if (b[13 + refMbPartIdx] == 0) { tempRefIdxPredL0[y][x] = -1; mvILPredL0[y][x][0] = mvILPredL0[y][x][1] = 0; }   /* (G-216)..(G-218) */
+                else {
+                    const int32_t* mv = b + 21 + (refMbPartIdx * 4 + refSubMbPartIdx) * 2;
+                    tempRefIdxPredL0[y][x] = b[17 + refMbPartIdx];                 /* (G-222) */
+                    mvILPredL0[y][x][0] = (mv[0] * mvScaleX + 32768) >> 16;        /* (G-234), (G-242) */
+                    mvILPredL0[y][x][1] = (mv[1] * mvScaleY + 32768) >> 16;        /* (G-235), (G-243) */
+                }
+            }
+        for (y = 0; y < 2; ++y) for (x = 0; x < 2; ++x) refIdxILPredL0[y][x] = tempRefIdxPredL0[y << 1][x << 1];   /* utils.c:1888; the rest is skipped when restricted */
+    }
+    /* G.8.6.1.3, utils.c:2006-2122 (EP: one list) */
+    {
+        int partitionSize = 3, c, yy, xx;
+        const int (*r)[2] = refIdxILPredL0;
+#define MV_EQ(Y, X, Y0, X0) (mvILPredL0[Y][X][0] == mvILPredL0[Y0][X0][0] && mvILPredL0[Y][X][1] == mvILPredL0[Y0][X0][1])
+        c = r[0][0] == r[0][1] && r[0][0] == r[1][0] && r[0][0] == r[1][1];
+        for (yy = 0; yy < 4 && c; ++yy) for (xx = 0; xx < 4; ++xx) if (!MV_EQ(yy, xx, 0, 0)) { c = 0; break; }
+        if (c) partitionSize = 0;
+        else {
+            c = r[0][0] == r[0][1] && r[1][0] == r[1][1];
+            for (yy = 0; yy < 2 && c; ++yy) for (xx = 0; xx < 4; ++xx) if (!MV_EQ(yy, xx, 0, 0)) { c = 0; break; }
+            for (yy = 2; yy < 4 && c; ++yy) for (xx = 0; xx < 4; ++xx) if (!MV_EQ(yy, xx, 2, 0)) { c = 0; break; }
+            if (c) partitionSize = 1;
+            else {
+                c = r[0][0] == r[1][0] && r[0][1] == r[1][1];
+                for (yy = 0; yy < 4 && c; ++yy) for (xx = 0; xx < 2; ++xx) if (!MV_EQ(yy, xx, 0, 0)) { c = 0; break; }
+                for (yy = 0; yy < 4 && c; ++yy) for (xx = 2; xx < 4; ++xx) if (!MV_EQ(yy, xx, 0, 2)) { c = 0; break; }
+                if (c) partitionSize = 2;
+            }
+        }
+        /* Table G-7 (EP) -> hl_codec_264_mb_set_mb_type, mb.c:117-126 */
+        {
+            static const int N[4] = { 1, 2, 2, 4 }, W[4] = { 16, 16, 8, 8 }, H[4] = { 16, 8, 16, 8 };
+            int subSize[4] = { 3, 0, 0, 0 };   /* utils.c:2145: `subPartitionSize[4] = { 4X4 }` leaves elements 1..3 at enum value 0 = 8X8 */
+            int p, s;
+            out16[1] = N[partitionSize]; out16[2] = W[partitionSize]; out16[3] = H[partitionSize];
+            if (partitionSize == 3) {   /* utils.c:2143-2186, Table G-8 -> hl_codec_264_mb_set_sub_mb_type, mb.c:175-186 */
+                static const int SN[4] = { 1, 2, 2, 4 }, SW[4] = { 8, 8, 4, 4 }, SH[4] = { 8, 4, 8, 4 };
+                for (p = 0; p < 4; ++p) {
+                    const int xO = (p & 1) << 1, yO = (p >> 1) << 1;
+                    if (MV_EQ(yO, xO + 1, yO, xO) && MV_EQ(yO + 1, xO, yO, xO) && MV_EQ(yO + 1, xO + 1, yO, xO)) subSize[p] = 0;
+                    else if (MV_EQ(yO, xO + 1, yO, xO) && MV_EQ(yO + 1, xO + 1, yO + 1, xO)) subSize[p] = 1;
+                    else if (MV_EQ(yO + 1, xO, yO, xO) && MV_EQ(yO + 1, xO + 1, yO, xO + 1)) subSize[p] = 2;
+                    out16[4 + p] = SN[subSize[p]]; out16[8 + p] = SW[subSize[p]]; out16[12 + p] = SH[subSize[p]];
+                }
+            }
+            else for (p = 0; p < N[partitionSize]; ++p) { out16[4 + p] = 1; out16[8 + p] = W[partitionSize]; out16[12 + p] = H[partitionSize]; }   /* mb.c:234-243 */
+            /* G.8.4.1, utils.c:1533-1545 and :1606-1633 */
+            for (p = 0; p < out16[1]; ++p) {
+                /* 6.4.2.1: upper-left sample of the macroblock partition, raster order inside the 16x16 */
+                const int xP = (p % (16 / out16[2])) * out16[2], yP = (p / (16 / out16[2])) * out16[3];
+                for (s = 0; s < out16[4 + p]; ++s) {
+                    int xS = 0, yS = 0;
+                    if (partitionSize == 3) { xS = (s % (8 / out16[8 + p])) * out16[8 + p]; yS = (s / (8 / out16[8 + p])) * out16[12 + p]; }   /* 6.4.2.2, mb.h:283-300 */
+                    if (s == 0) ref_idx4[p] = refIdxILPredL0[(yP + yS) >> 3][(xP + xS) >> 3];   /* (G-94) */
+                    mv32[(p * 4 + s) * 2] = mvILPredL0[(yP + yS) >> 2][(xP + xS) >> 2][0];       /* (G-93), (G-96) */
+                    mv32[(p * 4 + s) * 2 + 1] = mvILPredL0[(yP + yS) >> 2][(xP + xS) >> 2][1];
+                }
+            }
+        }
+#undef MV_EQ
+    }
+    return 0;
+}
+/* whole picture: out = nmb x (16 + 4 + 32) int32 {out16, refIdxL0[4], mvL0[4][4][2]}; bad[] receives 1 where hlo_svc_derive_mb failed */
+HLO_API void hlo_svc_derive_picture(const int32_t* base, int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int width, int height,
+                                    int32_t* out, uint8_t* bad)
+{
+    const int mbw = width >> 4, nmb = mbw * (height >> 4);
+    int a;
+    for (a = 0; a < nmb; ++a) bad[a] = hlo_svc_derive_mb(base, ref_w, ref_h, scaled_w, scaled_h, off_x, off_y, level_idc, a % mbw, a / mbw, out + 52 * a, out + 52 * a + 16, out + 52 * a + 20) != 0;
+}

@@ -40,6 +40,8 @@
 #include "hartallo/h264/hl_codec_264_me.h"
 #include "hartallo/h264/hl_codec_264_me_ds.h"
 #include "hartallo/h264/hl_codec_264_macros.h"
+#include "hartallo/h264/hl_codec_264_pps.h"
+#include "hartallo/h264/hl_codec_264_sps.h"
 
 static FILE* g_trace = NULL;       /* int32 record stream */
 static FILE* g_recon = NULL;       /* raw recon planes, frame after frame */
@@ -292,6 +294,43 @@ HL_ERROR_T __wrap_hl_codec_264_rdo_mb_guess_best_inter_pred_svc(hl_codec_264_mb_
             put_planes((const uint8_t*)in->data_ptr[0], (const uint8_t*)in->data_ptr[1], (const uint8_t*)in->data_ptr[2], W, H);
             put_planes(fs->p_pict->pc_data_y, fs->p_pict->pc_data_u, fs->p_pict->pc_data_v, W, H);
             g_svc_last_frame = g_frame_idx; g_svc_last_dqid = dq;
+            /* tag 11 (once per enhancement-layer P picture, after its tag 7): what the inter-layer motion derivation (utils.c:966-2439) reads --
+             * [11, n, frame, DQId, RefLayerPicWidthInSamplesL, RefLayerPicHeightInSamplesL, ScaledRefLayerPicWidthInSamplesL, ScaledRefLayerPicHeightInSamplesL,
+             *  ScaledRefLayerLeftOffset, ScaledRefLayerTopOffset, level_idc (utils.c:989), RestrictedSpatialResolutionChangeFlag, CroppingChangeFlag,
+             *  SpatialResolutionChangeFlag, number of reference-layer macroblocks, then per reference-layer macroblock 53 words: intra by e_type (utils.c:1701),
+             *  HL_CODEC_264_MB_TYPE_IS_INTRA (flags_type, mb.h:322), e_type is P_8X8 / P_8X8REF0 (mb.h:329), MbPartWidth, MbPartHeight, SubMbPartWidth[4],
+             *  SubMbPartHeight[4], predFlagL0[4], refIdxL0[4], mvL0[4][4][2]]; the reference layer's macroblock objects do not change while this picture is coded */
+            if (pc_layer->pc_ref && pc_layer->pc_slice_hdr) {
+                const hl_codec_264_layer_t* rl = pc_layer->pc_ref;
+                const hl_codec_264_nal_slice_header_t* sh = pc_layer->pc_slice_hdr;
+                const int nref = (int)rl->u_list_macroblocks_count;
+                int32_t h11[15]; int a;
+                h11[0] = 11; h11[1] = 15 + 53 * nref; h11[2] = g_frame_idx; h11[3] = dq;
+                h11[4] = (int32_t)pc_layer->RefLayerPicWidthInSamplesL; h11[5] = (int32_t)pc_layer->RefLayerPicHeightInSamplesL;
+                h11[6] = (int32_t)sh->ext.svc.ScaledRefLayerPicWidthInSamplesL; h11[7] = (int32_t)sh->ext.svc.ScaledRefLayerPicHeightInSamplesL;
+                h11[8] = (int32_t)sh->ext.svc.ScaledRefLayerLeftOffset; h11[9] = (int32_t)sh->ext.svc.ScaledRefLayerTopOffset;
+                h11[10] = (int32_t)p_codec->layers.p_list[(p_codec->layers.currDQId >> 4) << 4]->pc_slice_hdr->pc_pps->pc_sps->level_idc;
+                h11[11] = (int32_t)pc_layer->RestrictedSpatialResolutionChangeFlag; h11[12] = (int32_t)pc_layer->CroppingChangeFlag;
+                h11[13] = (int32_t)pc_layer->SpatialResolutionChangeFlag; h11[14] = nref;
+                put32(h11, 15);
+                for (a = 0; a < nref; ++a) {
+                    const hl_codec_264_mb_t* b = rl->pp_list_macroblocks[a];
+                    int32_t w[53]; int q = 0;
+                    memset(w, 0, sizeof(w));
+                    if (b) {
+                        w[q++] = (HL_CODEC_264_MB_TYPE_IS_I_PCM(b) || HL_CODEC_264_MB_TYPE_IS_I_16X16(b) || HL_CODEC_264_MB_TYPE_IS_I_8X8(b) || HL_CODEC_264_MB_TYPE_IS_I_4X4(b) || HL_CODEC_264_MB_TYPE_IS_I_BL(b)) ? 1 : 0;
+                        w[q++] = HL_CODEC_264_MB_TYPE_IS_INTRA(b) ? 1 : 0;
+                        w[q++] = (b->e_type == HL_CODEC_264_MB_TYPE_P_8X8 || b->e_type == HL_CODEC_264_MB_TYPE_P_8X8REF0) ? 1 : 0;
+                        w[q++] = b->MbPartWidth; w[q++] = b->MbPartHeight;
+                        for (i = 0; i < 4; ++i) w[q++] = b->SubMbPartWidth[i];
+                        for (i = 0; i < 4; ++i) w[q++] = b->SubMbPartHeight[i];
+                        for (i = 0; i < 4; ++i) w[q++] = b->predFlagL0[i];
+                        for (i = 0; i < 4; ++i) w[q++] = b->refIdxL0[i];
+                        for (i = 0; i < 4; ++i) for (j = 0; j < 4; ++j) { w[q++] = b->mvL0[i][j].x; w[q++] = b->mvL0[i][j].y; }
+                    }
+                    put32(w, 53);
+                }
+            }
         }
         r[k++] = 6; r[k++] = 0; r[k++] = g_frame_idx; r[k++] = dq; r[k++] = (int32_t)p_mb->u_addr; r[k++] = p_mb->QPy; r[k++] = p_mb->QPc[0]; r[k++] = p_mb->QPc[1];
         r[k++] = p_mb->NumMbPart; r[k++] = p_mb->MbPartWidth; r[k++] = p_mb->MbPartHeight;

@@ -200,3 +200,207 @@ def compare_picture(p, coeffs, rec_yuv, state_out=None, what=""):
             assert np.array_equal(state_out[a]["chroma_ac_level"], e["chroma_ac_level"]) and np.array_equal(state_out[a]["chroma_dc_level"], e["chroma_dc_level"]), a
         n += 1
     return n
+
+
+# ---- inter-layer motion derivation (second half): tag 11 of oracle/ref_driver.c = what the derivation reads, tag 6 = what it produced -----------------
+SVC_BASE_MB = np.dtype([("flags", "u1"), ("part_w", "u1"), ("part_h", "u1"), ("sub_w", "u1", (4,)), ("sub_h", "u1", (4,)), ("pred_flag", "i1", (4,)), ("ref_idx", "i1", (4,)),
+                        ("pad", "u1"), ("mv", "<i2", (4, 4, 2))])   # hlb200_svc_base_mb_t
+SVC_GEOM = np.dtype([("ref_width", "<i4"), ("ref_height", "<i4"), ("scaled_width", "<i4"), ("scaled_height", "<i4"), ("left_offset", "<i4"), ("top_offset", "<i4"),
+                     ("level_idc", "<i4"), ("restricted", "<i4"), ("cropping_change", "<i4")])   # hlb200_svc_layer_geom_t
+E_TYPE_I_BL = 426   # HL_CODEC_264_MB_TYPE_SVC_I_BL (hl_codec_264_defs.h:474)
+DERIVE_BAD_REF, DERIVE_UNSUPPORTED, DERIVE_STALE_PARTS, DERIVE_NO_PRED_SOURCE = 1, 2, 4, 8
+
+
+def base_mbs_from_words(w):
+    """(n, 53) int32 words of a tag-11 record -> SVC_BASE_MB array"""
+    b = np.zeros(len(w), SVC_BASE_MB)
+    b["flags"] = (w[:, 0] != 0) * 1 + (w[:, 1] != 0) * 2 + (w[:, 2] != 0) * 4
+    b["part_w"], b["part_h"] = w[:, 3], w[:, 4]
+    b["sub_w"], b["sub_h"], b["pred_flag"], b["ref_idx"] = w[:, 5:9], w[:, 9:13], w[:, 13:17], w[:, 17:21]
+    b["mv"] = w[:, 21:53].reshape(-1, 4, 4, 2)
+    return b
+
+
+def derive_pictures_from_trace(path):
+    """one dict per enhancement-layer P picture, in coding order: geom / base = the derivation's inputs (tag 11); kind (0 inter, 1 base macroblock intra), part_mode,
+    sub_mode, ref_idx, mv, nparts, nsub = what the reference derived per macroblock (tag 6: NumMbPart, MbPartWidth/Height, SubMbPartWidth/Height, refIdxL0, mvL0; only the
+    entries below NumMbPart / NumSubMbPart are meaningful, the macroblock objects are never reset); stale_parts = NumSubMbPart[0] the object held (tag 6, unchanged by an
+    intra derivation); motion / valid = the glue's view of it (pictures_from_trace)"""
+    t = reftrace.parse(path)
+    glue_view = {(p["frame"], p["dqid"]): p for p in pictures_from_trace(path)}
+    out = []
+    for r in t.get(11, []):
+        key = (int(r[2]), int(r[3]))
+        gv = glue_view[key]
+        nmb = len(gv["valid"])
+        g = np.zeros(1, SVC_GEOM)
+        for i, f in enumerate(SVC_GEOM.names):
+            g[f] = int(r[4 + i]) if f != "cropping_change" else int(r[12])
+        g["restricted"] = int(r[11])
+        nref = int(r[14])
+        d = dict(frame=key[0], dqid=key[1], w=gv["w"], h=gv["h"], geom=g, spatial_change=int(r[13]), base=base_mbs_from_words(r[15:15 + 53 * nref].reshape(nref, 53)),
+                 kind=np.zeros(nmb, np.uint8), part_mode=np.zeros(nmb, np.uint8), sub_mode=np.zeros((nmb, 4), np.uint8), ref_idx=np.zeros((nmb, 4), np.int8),
+                 mv=np.zeros((nmb, 4, 4, 2), np.int16), nparts=np.zeros(nmb, np.uint8), nsub=np.zeros((nmb, 4), np.uint8), stale_parts=np.zeros(nmb, np.uint8),
+                 motion=gv["motion"], valid=gv["valid"])
+        out.append(d)
+    by_key = {(d["frame"], d["dqid"]): d for d in out}
+    for r in t.get(6, []):
+        d = by_key.get((int(r[2]), int(r[3])))
+        if d is None:
+            continue
+        a = int(r[4])
+        nparts, pw, ph = int(r[8]), int(r[9]), int(r[10])
+        nsub, sw, sh, ridx, mv = r[11:15], r[15:19], r[19:23], r[27:31], r[31:63].reshape(4, 4, 2)
+        e_type = int(r[63 + 7 + 256 + 8 + 128 + 384 + 128])
+        if e_type == E_TYPE_I_BL:
+            d["kind"][a] = 1
+            d["stale_parts"][a] = int(nsub[0])
+            continue
+        mode = {(1, 16, 16): 0, (2, 16, 8): 1, (2, 8, 16): 2, (4, 8, 8): 3}[(nparts, pw, ph)]
+        d["part_mode"][a], d["nparts"][a] = mode, nparts
+        for p in range(nparts):
+            d["ref_idx"][a, p] = int(ridx[p])
+            d["nsub"][a, p] = int(nsub[p])
+            if mode == 3:
+                d["sub_mode"][a, p] = {(8, 8): 0, (8, 4): 1, (4, 8): 2, (4, 4): 3}[(int(sw[p]), int(sh[p]))]
+            d["mv"][a, p, :int(nsub[p])] = mv[p, :int(nsub[p])]
+    return out
+
+
+def compare_derived(d, motion, status, what=""):
+    """motion (MB_MOTION per macroblock) / status bits of an implementation of the derivation against the reference's picture `d`.  Every inter macroblock: partition layout,
+    refIdxL0 and mvL0 of every (sub-)partition; every macroblock the glue codes (valid): the inherited-prediction marker; the status bits = the reasons the glue refuses"""
+    n = 0
+    for a in range(len(d["kind"])):
+        m = motion[a]
+        tag = "%s frame %d dqid %d macroblock %d" % (what, d["frame"], d["dqid"], a)
+        if d["kind"][a] == 0:
+            assert int(m["part_mode"]) == int(d["part_mode"][a]), tag + ": part_mode %d, reference %d" % (m["part_mode"], d["part_mode"][a])
+            for p in range(int(d["nparts"][a])):
+                assert int(m["ref_idx"][p]) == int(d["ref_idx"][a, p]), tag + ": refIdxL0[%d]" % p
+                if d["part_mode"][a] == 3:
+                    assert int(m["sub_mode"][p]) == int(d["sub_mode"][a, p]), tag + ": sub_mode[%d]" % p
+                ns = int(d["nsub"][a, p])
+                assert np.array_equal(m["mv"][p, :ns], d["mv"][a, p, :ns]), tag + ": mvL0[%d] %s, reference %s" % (p, m["mv"][p, :ns].tolist(), d["mv"][a, p, :ns].tolist())
+            assert not (int(m["pad"][0]) & 1), tag
+        if d["valid"][a]:
+            g = d["motion"][a]
+            assert np.array_equal(m["pad"], g["pad"]), tag + ": inherited-prediction marker %s, glue %s" % (m["pad"].tolist(), g["pad"].tolist())
+            if not (int(g["pad"][0]) & 1):
+                assert int(m["part_mode"]) == int(g["part_mode"]) and all(np.array_equal(m["mv"][p, 0], g["mv"][p, 0]) for p in range(4 if g["part_mode"] == 3 else (1 if g["part_mode"] == 0 else 2))), tag
+        n += 1
+    expect = 0
+    inter_ok = (d["kind"] == 0) & np.array([all(int(d["ref_idx"][a, p]) == 0 and int(d["sub_mode"][a, p]) == 0 for p in range(int(d["nparts"][a]))) for a in range(len(d["kind"]))])
+    if ((d["kind"] == 0) & ~inter_ok).any():
+        expect |= DERIVE_UNSUPPORTED
+    if ((d["kind"] == 1) & (d["stale_parts"] != 0)).any():
+        expect |= DERIVE_STALE_PARTS
+    first_ok = np.nonzero(inter_ok)[0]
+    intra = np.nonzero(d["kind"] == 1)[0]
+    if len(intra) and (not len(first_ok) or intra[0] < first_ok[0]):
+        expect |= DERIVE_NO_PRED_SOURCE
+    assert status == expect, "%s frame %d dqid %d: status %d, expected %d" % (what, d["frame"], d["dqid"], status, expect)
+    return n
+
+
+DERIVE_GOLDEN = os.path.join(ROOT, "tests", "golden", "svc_derive.npz")
+
+
+def load_derive_golden(path=DERIVE_GOLDEN):
+    """pictures of tests/golden/svc_derive.npz (made by tests/golden/make_golden_svc_derive.py) in coding order; pictures of one stream share the name prefix"""
+    z = np.load(path)
+    out = []
+    for tag in z["index"]:
+        tag = str(tag)
+        w, h, frame, dqid, sc = (int(v) for v in z[tag + ".meta"])
+        p = dict(name=tag, stream=tag.rsplit(".", 1)[0], w=w, h=h, frame=frame, dqid=dqid, spatial_change=sc)
+        for k, dt in (("geom", SVC_GEOM), ("base", SVC_BASE_MB), ("motion", MB_MOTION)):
+            p[k] = z[tag + "." + k].view(dt).reshape(-1)
+        for k in ("kind", "part_mode", "sub_mode", "ref_idx", "mv", "nparts", "nsub", "stale_parts", "valid"):
+            p[k] = z[tag + "." + k]
+        out.append(p)
+    return out
+
+
+def base_words(base):
+    """SVC_BASE_MB array -> (n, 53) int32 words in the order of trace tag 11 (what oracle/hl_oracle.c: hlo_svc_derive_mb reads)"""
+    w = np.zeros((len(base), 53), np.int32)
+    f = base["flags"].astype(np.int32)
+    w[:, 0], w[:, 1], w[:, 2] = f & 1, (f >> 1) & 1, (f >> 2) & 1
+    w[:, 3], w[:, 4] = base["part_w"], base["part_h"]
+    w[:, 5:9], w[:, 9:13], w[:, 13:17], w[:, 17:21] = base["sub_w"], base["sub_h"], base["pred_flag"], base["ref_idx"]
+    w[:, 21:53] = base["mv"].reshape(len(base), 32)
+    return w
+
+
+def oracle_derive(olib, base, geom, w, h):
+    """the oracle's derivation of a picture -> (MB_MOTION array in the C-ABI's layout incl. inherited-prediction markers, kind, status bits); had_parts is the caller's"""
+    import ctypes as C
+    g = geom[0]
+    nmb = (w // 16) * (h // 16)
+    bw = np.ascontiguousarray(base_words(base))
+    out, bad = np.zeros((nmb, 52), np.int32), np.zeros(nmb, np.uint8)
+    olib.hlo_svc_derive_picture(bw.ctypes.data_as(C.c_void_p), int(g["ref_width"]), int(g["ref_height"]), int(g["scaled_width"]), int(g["scaled_height"]), int(g["left_offset"]),
+                                int(g["top_offset"]), int(g["level_idc"]), w, h, out.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p))
+    return out, bad
+
+
+def motion_from_oracle(out, bad, had_parts):
+    """oracle records -> (MB_MOTION array, status bits) with the classification / inheritance rules of host/hlb200_glue.c (restated here in numpy, not shared with the device)"""
+    nmb = len(out)
+    m, status, kind = np.zeros(nmb, MB_MOTION), 0, np.zeros(nmb, np.uint8)
+    for a in range(nmb):
+        o = out[a]
+        if bad[a]:
+            status |= DERIVE_BAD_REF; kind[a] = 2
+            continue
+        if o[0]:
+            kind[a] = 1
+            if had_parts[a]:
+                status |= DERIVE_STALE_PARTS
+            continue
+        n, pw, ph = int(o[1]), int(o[2]), int(o[3])
+        mode = {(1, 16, 16): 0, (2, 16, 8): 1, (2, 8, 16): 2, (4, 8, 8): 3}[(n, pw, ph)]
+        m[a]["part_mode"] = mode
+        sup = True
+        for p in range(n):
+            ns = int(o[4 + p])
+            m[a]["ref_idx"][p] = int(o[16 + p])
+            if mode == 3:
+                m[a]["sub_mode"][p] = {(8, 8): 0, (8, 4): 1, (4, 8): 2, (4, 4): 3}[(int(o[8 + p]), int(o[12 + p]))]
+            m[a]["mv"][p, :ns] = o[20:52].reshape(4, 4, 2)[p, :ns]
+            sup = sup and int(o[16 + p]) == 0 and m[a]["sub_mode"][p] == 0
+        had_parts[a] = 1
+        if not sup:
+            status |= DERIVE_UNSUPPORTED; kind[a] = 2
+    last = -1
+    for a in range(nmb):
+        if kind[a] == 0:
+            last = a
+        elif kind[a] == 1:
+            if last < 0 or last >= 65536:
+                status |= DERIVE_NO_PRED_SOURCE
+            else:
+                m[a]["pad"] = (1, last & 255, last >> 8)
+    return m, status
+
+
+def random_base_field(rng, ref_w, ref_h, intra_frac=0.1, zero_mv_frac=0.3):
+    """random reference-layer macroblock fields with every partition layout, intra macroblocks, unused partitions (predFlagL0 = 0) and non-zero reference indices"""
+    n = (ref_w // 16) * (ref_h // 16)
+    b = np.zeros(n, SVC_BASE_MB)
+    mode = rng.integers(0, 4, n)
+    b["part_w"], b["part_h"] = np.array([16, 16, 8, 8])[mode], np.array([16, 8, 16, 8])[mode]
+    sm = rng.integers(0, 4, (n, 4))
+    b["sub_w"], b["sub_h"] = np.array([8, 8, 4, 4])[sm], np.array([8, 4, 8, 4])[sm]
+    b["sub_w"][mode != 3], b["sub_h"][mode != 3] = b["part_w"][mode != 3, None], b["part_h"][mode != 3, None]
+    b["flags"] = (mode == 3) * 4
+    b["pred_flag"] = (rng.random((n, 4)) > 0.05)
+    b["ref_idx"] = np.where(rng.random((n, 4)) > 0.1, 0, rng.integers(0, 3, (n, 4)))
+    mv = rng.integers(-64, 65, (n, 4, 4, 2))
+    same = rng.random(n) < zero_mv_frac          # macroblocks whose partitions all move alike (they merge to larger partitions in the enhancement layer)
+    mv[same] = mv[same][:, :1, :1, :]
+    b["mv"] = mv
+    intra = rng.random(n) < intra_frac
+    b["flags"][intra] = np.where(rng.random(int(intra.sum())) < 0.5, 3, 2)   # Intra16x16 (recognised by e_type) or Intra4x4 of a P picture (flags_type only: motion is derived from it)
+    return b

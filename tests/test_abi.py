@@ -30,15 +30,16 @@ def test_exports_every_declared_symbol():
 
 def test_struct_layouts_match_c():
     lib = _lib()
-    src = '#include "hlb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(hlb200_mb_motion_t),' \
+    src = '#include "hlb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(hlb200_mb_motion_t),' \
           'sizeof(hlb200_mb_coeffs_t),sizeof(hlb200_me_cand_t),sizeof(hlb200_me_cost_t),sizeof(hlb200_mb_record_t),sizeof(hlb200_slice_params_t),' \
           'offsetof(hlb200_mb_record_t,mv),offsetof(hlb200_mb_record_t,luma_level),sizeof(hlb200_svc_mb_state_t),' \
-          'offsetof(hlb200_svc_mb_state_t,chroma_dc_level));return 0;}'
+          'offsetof(hlb200_svc_mb_state_t,chroma_dc_level),sizeof(hlb200_svc_base_mb_t),offsetof(hlb200_svc_base_mb_t,mv),sizeof(hlb200_svc_layer_geom_t));return 0;}'
     exe = "/tmp/hlb200_sizes"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     got = [int(v) for v in subprocess.check_output([exe]).split()]
     want = [lib.MB_MOTION.itemsize, lib.MB_COEFFS.itemsize, lib.ME_CAND.itemsize, lib.ME_COST.itemsize, lib.MB_RECORD.itemsize, ctypes.sizeof(lib.SliceParams),
-            lib.MB_RECORD.fields["mv"][1], lib.MB_RECORD.fields["luma_level"][1], lib.SVC_STATE.itemsize, lib.SVC_STATE.fields["chroma_dc_level"][1]]
+            lib.MB_RECORD.fields["mv"][1], lib.MB_RECORD.fields["luma_level"][1], lib.SVC_STATE.itemsize, lib.SVC_STATE.fields["chroma_dc_level"][1],
+            lib.SVC_BASE_MB.itemsize, lib.SVC_BASE_MB.fields["mv"][1], lib.SVC_GEOM.itemsize]
     assert got == want
 
 
@@ -87,6 +88,9 @@ def test_argument_errors_are_reported_not_executed():
     assert l.hlb200_dev_svc_inter_recon_batch(1, 1, 1, 1, 1, 1, 64, 40, 1, 0, 31, 0, 1, 1, 1, 1, 1, 1, None) == inv      # height not a multiple of 16
     assert l.hlb200_svc_layer_picture(None, 0, 1, 31, 0, 1, None, None, None, 1) == inv                                  # no layer context
     assert l.hlb200_dev_svc_bl_recon_batch(1, 1, 1, 1, 1, 1, 64, 48, 0, 0, 31, 0, 1, 1, 1, 1, 1, None) == inv            # no pictures
+    assert l.hlb200_dev_svc_derive_motion_batch(1, None, 64, 48, 1, 1, 1, 1, None) == inv                                # no geometry
+    assert l.hlb200_dev_svc_derive_motion_batch(1, 1, 64, 40, 1, 1, 1, 1, None) == inv                                   # height not a multiple of 16
+    assert l.hlb200_svc_layer_picture_derived(None, 0, 1, 31, 0, 1, 1, None, None, 1) == inv                             # no layer context
     assert l.hlb200_slice_encode_batch_async(None, None, 1) == inv
     assert l.hlb200_frame_set_device(None, 1, 1, 1) == inv
     prev = l.hlb200_slice_set_variant(1)

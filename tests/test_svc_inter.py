@@ -403,7 +403,7 @@ def _run_expect_refusal(exe, args, needle):
 @pytest.mark.parametrize("args,needle", [
     (["--size", "48", "48", "--layers", "2", "--frames", "2", "--deblock", "1"], "deblock_flag"),   # inter-layer deblocking (deblock.c:175-186) is not reproduced
     (["--size", "48", "16", "--layers", "3", "--frames", "2", "--gen", "g2", "--seed", "1865", "--qp", "22"], "Intra_Base"),   # 12-macroblock enhancement I picture (layer.c:202)
-    (["--size", "48", "48", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "21", "--qp", "30"], "no partition"),    # coded against an earlier picture's scratch memory
+    (["--size", "48", "48", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "21", "--qp", "30"], "status bits 8"),   # HLB200_SVC_DERIVE_NO_PRED_SOURCE: coded against an earlier picture's scratch memory
 ])
 def test_glue_refuses_what_it_does_not_reproduce(args, needle):
     """No silent divergence and no CPU fallback: deblocking of streams with SVC layers, enhancement-layer I pictures too small for the reference's own window

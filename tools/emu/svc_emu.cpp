@@ -50,3 +50,23 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_resample_plane(con
         for (int x = 0; x < W; ++x) out[y * W + x] = hlb::svc_resample_px(ref, refW, refH, ax, ay, x, y, chroma != 0);
     return HLB200_OK;
 }
+
+// CPU run of the inter-layer motion derivation (hlb_svc_derive.cuh, the body of k_svc_derive / k_svc_derive_inherit): one picture, host pointers.  Same meaning of the
+// arguments as hlb200_dev_svc_derive_motion_batch; returns the HLB200_SVC_DERIVE_* status bits in *status.
+#include "../../hartallo_b200/csrc/hlb_svc_derive.cuh"
+extern "C" __attribute__((visibility("default"))) int svc_emu_derive_motion(const hlb200_svc_base_mb_t* base, const hlb200_svc_layer_geom_t* geom, int width, int height,
+                                                                            uint8_t* had_parts, hlb200_mb_motion_t* motion, int32_t* status)
+{
+    if (!base || !geom || !had_parts || !motion || !status || width < 16 || height < 16 || (width & 15) || (height & 15)) return HLB200_ERR_INVALID_PARAMETER;
+    if (!geom->restricted || geom->cropping_change) return HLB200_ERR_NOT_IMPLEMENTED;
+    hlb::SvcDeriveGeom g;
+    if (!hlb::svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, g)) return HLB200_ERR_NOT_IMPLEMENTED;
+    const int mbw = width >> 4, nmb = mbw * (height >> 4);
+    uint8_t* kind = new uint8_t[nmb];
+    int st = 0;
+    for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass1(base, g, mb, mbw, had_parts, motion, kind);
+    for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass2(mb, kind, motion);
+    delete[] kind;
+    *status = st;
+    return HLB200_OK;
+}

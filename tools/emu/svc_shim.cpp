@@ -25,6 +25,7 @@ struct hlb200_ctx {
     uint8_t* src;
     uint8_t* slot[HLB200_MAX_REFS + 1];
     hlb200_svc_mb_state_t* state;
+    uint8_t* had_parts;   /* hlb200_svc_layer_picture_derived: carried per macroblock from picture to picture */
 #ifdef SVC_SHIM_WITH_SLICE
     hlb::MbState* mbstate;
     hlb::MbWork* work;
@@ -57,7 +58,7 @@ API int hlb200_stream_create(int w, int h, int max_refs, hlb200_ctx_t** out)
 }
 API int hlb200_stream_destroy(hlb200_ctx_t* c)
 {
-    free(c->src); free(c->state);
+    free(c->src); free(c->state); free(c->had_parts);
     for (int s = 0; s < c->nslots; ++s) free(c->slot[s]);
 #ifdef SVC_SHIM_WITH_SLICE
     free(c->mbstate); free(c->work); free(c->rec); free(c->bits);
@@ -198,6 +199,19 @@ API int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, in
     if (ref_slot < 0) { ry = pred_y; ru = pred_u; rv = pred_v; }
     else { ry = c->slot[ref_slot]; ru = ry + ysz; rv = ru + csz; }
     return svc_emu_recon_batch(ref_slot < 0, s, s + ysz, s + ysz + csz, ry, ru, rv, c->w, c->h, 1, 0, qp, off, motion, c->state, out, o, o + ysz, o + ysz + csz);
+}
+extern "C" int svc_emu_derive_motion(const hlb200_svc_base_mb_t* base, const hlb200_svc_layer_geom_t* geom, int width, int height, uint8_t* had_parts, hlb200_mb_motion_t* motion,
+                                     int32_t* status);
+API int hlb200_svc_layer_picture_derived(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp, int off, const hlb200_svc_base_mb_t* base, const hlb200_svc_layer_geom_t* geom,
+                                         hlb200_mb_motion_t* out_motion, int32_t* out_status, hlb200_mb_coeffs_t* out)
+{
+    if (!c->had_parts) c->had_parts = (uint8_t*)calloc((size_t)c->nmb, 1);
+    std::vector<hlb200_mb_motion_t> m((size_t)c->nmb);
+    int rc = svc_emu_derive_motion(base, geom, c->w, c->h, c->had_parts, m.data(), out_status);
+    if (rc) return rc;
+    if (out_motion) memcpy(out_motion, m.data(), sizeof(hlb200_mb_motion_t) * (size_t)c->nmb);
+    if (*out_status) return HLB200_ERR_NOT_IMPLEMENTED;
+    return hlb200_svc_layer_picture(c, ref_slot, cur_slot, qp, off, m.data(), nullptr, nullptr, nullptr, out);
 }
 extern "C" int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma, int level_idc);
 API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* c, int cur_slot, int qp, int off, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v, int rw, int rh,
