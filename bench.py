@@ -423,7 +423,7 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
             line["all_inter"] = all_inter
         if world == 1 and not args.no_all_inter:
             # BASELINE.json configs[3]: three spatial layers QCIF -> CIF -> 4CIF, ONE stream through the drop-in (base layer: slice kernel; enhancement layers: the SVC
-            # kernels; inter-layer derivation still on the host) beside the all-CPU reference on the same input; the byte streams must be equal
+            # kernels incl. the inter-layer motion derivation, k_svc_derive) beside the all-CPU reference on the same input; the byte streams must be equal
             enc_b, enc_r = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder"), os.path.join(ROOT, "oracle", "_ref", "hl_ref_driver")
             if os.path.exists(enc_b) and os.path.exists(enc_r):
                 a = ["--layers", "3", "--size", "176", "144", "--frames", "6", "--gen", "g1"]

@@ -280,8 +280,8 @@ int hlb200_svc_layer_picture_derived(hlb200_ctx_t* c, int ref_slot, int cur_slot
         return HLB200_ERR_INVALID_PARAMETER;
     const size_t nref = (size_t)(geom->ref_width >> 4) * (geom->ref_height >> 4);
     const size_t mbytes = (sizeof(hlb200_mb_motion_t) * c->nmb + 255) & ~(size_t)255, cbytes = (sizeof(hlb200_mb_coeffs_t) * c->nmb + 255) & ~(size_t)255;
-    const size_t bbytes = (sizeof(hlb200_svc_base_mb_t) * nref + 255) & ~(size_t)255, kbytes = ((size_t)c->nmb + 255) & ~(size_t)255;
-    int rc = ensure_scratch(c, mbytes + cbytes + bbytes + kbytes + 256);
+    const size_t bbytes = (sizeof(hlb200_svc_base_mb_t) * nref + 255) & ~(size_t)255;
+    int rc = ensure_scratch(c, mbytes + cbytes + bbytes + 256);
     if (rc) return rc;
     if (!c->d_svc_state) {
         HLB_CUDA(cudaMalloc(&c->d_svc_state, sizeof(hlb200_svc_mb_state_t) * c->nmb));
@@ -295,11 +295,10 @@ int hlb200_svc_layer_picture_derived(hlb200_ctx_t* c, int ref_slot, int cur_slot
     hlb200_mb_motion_t* d_motion = (hlb200_mb_motion_t*)s;
     hlb200_mb_coeffs_t* d_coeffs = (hlb200_mb_coeffs_t*)(s + mbytes);
     hlb200_svc_base_mb_t* d_base = (hlb200_svc_base_mb_t*)(s + mbytes + cbytes);
-    uint8_t* d_kind = (uint8_t*)(s + mbytes + cbytes + bbytes);
-    int32_t* d_status = (int32_t*)(s + mbytes + cbytes + bbytes + kbytes);
+    int32_t* d_status = (int32_t*)(s + mbytes + cbytes + bbytes);
     if ((rc = h2d(c, d_base, base, sizeof(hlb200_svc_base_mb_t) * nref))) return rc;
     HLB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), c->stream));
-    if ((rc = svc_derive_launch(d_base, geom, c->width, c->height, 1, c->d_svc_had_parts, d_motion, d_kind, d_status, c->stream))) return rc;
+    if ((rc = hlb200_dev_svc_derive_motion_batch(d_base, geom, c->width, c->height, 1, c->d_svc_had_parts, d_motion, d_status, c->stream))) return rc;
     // the status decides whether the picture may be coded at all: one small read-back before the big kernel (a refused picture must not touch the layer's state)
     int32_t st = 0;
     if ((rc = d2h(c, &st, d_status, sizeof(st)))) return rc;

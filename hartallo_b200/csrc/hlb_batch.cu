@@ -724,28 +724,27 @@ int hlb200_dev_svc_bl_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u
 // One thread per enhancement-layer macroblock, blockIdx.y = picture.  The reference layer's records are 84 bytes per macroblock and four (dyadic) enhancement macroblocks
 // read the same one: served by L1/L2, the kernel is a few microseconds per 1080p picture.  Pass 2 resolves the macroblocks that inherit a prediction (base macroblock
 // intra) by walking back over the kinds pass 1 wrote; it is a second launch because the walk crosses CTAs.
-__global__ void __launch_bounds__(128) k_svc_derive(const hlb200_svc_base_mb_t* __restrict__ base, SvcDeriveGeom g, int mbw, int nmb, uint8_t* __restrict__ had_parts,
-                                                    hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ kind, int32_t* __restrict__ status)
+__global__ void __launch_bounds__(128) k_svc_derive(const hlb200_svc_base_mb_t* __restrict__ base, SvcDeriveGeom g, int mbw, int nmb, uint8_t* __restrict__ flags,
+                                                    hlb200_mb_motion_t* __restrict__ motion, int32_t* __restrict__ status)
 {
     const int mb = blockIdx.x * blockDim.x + threadIdx.x;
     if (mb >= nmb) return;
     const size_t pic = blockIdx.y;
-    const int st = svc_derive_pass1(base + pic * g.nref, g, mb, mbw, had_parts + pic * nmb, motion + pic * nmb, kind + pic * nmb);
+    const int st = svc_derive_pass1(base + pic * g.nref, g, mb, mbw, flags + pic * nmb, motion + pic * nmb);
     if (st) atomicOr(status + pic, st);
 }
-__global__ void __launch_bounds__(128) k_svc_derive_inherit(int nmb, const uint8_t* __restrict__ kind, hlb200_mb_motion_t* __restrict__ motion, int32_t* __restrict__ status)
+__global__ void __launch_bounds__(128) k_svc_derive_inherit(int nmb, const uint8_t* __restrict__ flags, hlb200_mb_motion_t* __restrict__ motion, int32_t* __restrict__ status)
 {
     const int mb = blockIdx.x * blockDim.x + threadIdx.x;
     if (mb >= nmb) return;
     const size_t pic = blockIdx.y;
-    const int st = svc_derive_pass2(mb, kind + pic * nmb, motion + pic * nmb);
+    const int st = svc_derive_pass2(mb, flags + pic * nmb, motion + pic * nmb);
     if (st) atomicOr(status + pic, st);
 }
-// d_kind: n_pics x macroblocks bytes of scratch (kinds of pass 1)
-int svc_derive_launch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics, uint8_t* d_had_parts,
-                      hlb200_mb_motion_t* d_motion, uint8_t* d_kind, int32_t* d_status, cudaStream_t stream)
+int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics, uint8_t* d_had_parts,
+                                       hlb200_mb_motion_t* d_motion, int32_t* d_status, void* cuda_stream)
 {
-    if (!d_base || !geom || !d_had_parts || !d_motion || !d_kind || !d_status || width < 16 || height < 16 || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535)
+    if (!d_base || !geom || !d_had_parts || !d_motion || !d_status || width < 16 || height < 16 || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535)
         return HLB200_ERR_INVALID_PARAMETER;
     SvcDeriveGeom g;
     if (!geom->restricted || geom->cropping_change ||
@@ -755,23 +754,10 @@ int svc_derive_launch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer
     }
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
     const dim3 grid((nmb + 127) / 128, n_pics);
-    k_svc_derive<<<grid, 128, 0, stream>>>(d_base, g, mbw, nmb, d_had_parts, d_motion, d_kind, d_status);
-    k_svc_derive_inherit<<<grid, 128, 0, stream>>>(nmb, d_kind, d_motion, d_status);
+    k_svc_derive<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(d_base, g, mbw, nmb, d_had_parts, d_motion, d_status);
+    k_svc_derive_inherit<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(nmb, d_had_parts, d_motion, d_status);
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
-}
-
-int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics, uint8_t* d_had_parts,
-                                       hlb200_mb_motion_t* d_motion, int32_t* d_status, void* cuda_stream)
-{
-    if (!d_base || !geom || !d_had_parts || !d_motion || !d_status || width < 16 || height < 16 || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535)
-        return HLB200_ERR_INVALID_PARAMETER;
-    const cudaStream_t stream = (cudaStream_t)cuda_stream;
-    uint8_t* d_kind = nullptr;
-    HLB_CUDA(cudaMallocAsync((void**)&d_kind, (size_t)n_pics * (width >> 4) * (height >> 4), stream));
-    const int rc = svc_derive_launch(d_base, geom, width, height, n_pics, d_had_parts, d_motion, d_kind, d_status, stream);
-    HLB_CUDA(cudaFreeAsync(d_kind, stream));
-    return rc;
 }
 
 // Intra_Base resampling (hlb_svc.cuh: svc_resample_px): one thread = four horizontally adjacent output samples of one plane, stored as one word;

@@ -63,10 +63,6 @@ inline int host_chroma_qp(int qp_y, int offset)
 
 }  // namespace hlb
 
-// hlb_batch.cu: the two launches of the SVC inter-layer motion derivation (d_kind = n_pics x macroblocks bytes of scratch)
-extern "C" int svc_derive_launch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics, uint8_t* d_had_parts,
-                                 hlb200_mb_motion_t* d_motion, uint8_t* d_kind, int32_t* d_status, cudaStream_t stream);
-
 // context (opaque to C callers)
 struct hlb200_ctx {
     int width, height, mbw, mbh, nmb;

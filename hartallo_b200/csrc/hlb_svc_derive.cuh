@@ -68,7 +68,7 @@ HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const Sv
 #pragma unroll
         for (int s = 0; s < 4; ++s) out.mv[p][s][0] = out.mv[p][s][1] = 0;
     // G.8.6.1.1 over the sixteen 4x4 blocks: luma location (4x + 1, 4y + 1) (utils.c:1692-1695) -> reference-layer sample (G-11..G-14) -> macroblock (G-15) -> partition
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < 16; ++b) {
         const int x = b & 3, y = b >> 2;
         const int xC = mbx * 16 + 4 * x + 1, yC = mby * 16 + 4 * y + 1;
@@ -139,11 +139,15 @@ HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const Sv
     }
     // G.8.4.1 with base_mode_flag = 1 (utils.c:1606-1621): a partition takes the predictors at its upper-left sample
     const int nparts = mode == 0 ? 1 : (mode == 3 ? 4 : 2);
-    for (int p = 0; p < nparts; ++p) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (p >= nparts) break;
         const int xP = mode == 2 ? p * 8 : (mode == 3 ? (p & 1) * 8 : 0), yP = mode == 1 ? p * 8 : (mode == 3 ? (p >> 1) * 8 : 0);
         const int sm = mode == 3 ? out.sub_mode[p] : 0, nsub = sm == 0 ? 1 : (sm == 3 ? 4 : 2);
         out.ref_idx[p] = (int8_t)tref[((yP >> 3) << 3) | ((xP >> 3) << 1)];
-        for (int s = 0; s < nsub; ++s) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s >= nsub) break;
             const int xS = sm == 2 ? s * 4 : (sm == 3 ? (s & 1) * 4 : 0), yS = sm == 1 ? s * 4 : (sm == 3 ? (s >> 1) * 4 : 0);
             const int b = (((yP + yS) >> 2) << 2) | ((xP + xS) >> 2);
             out.mv[p][s][0] = (int16_t)mvx[b]; out.mv[p][s][1] = (int16_t)mvy[b];
@@ -162,29 +166,31 @@ HLB_HD bool svc_derive_supported(const hlb200_mb_motion_t& m)
 }
 
 // Pass 1 of a picture, one call per macroblock: derive, classify, keep the "object holds partitions" flag of the layer's macroblock (NumSubMbPart[0] of the reference's
-// persistent macroblock object: written by every inter derivation, mb.c:137-207 / :209-244, never by an intra one).  kind[mb]: 0 inter, 1 intra (resolved by pass 2).
-HLB_HD int svc_derive_pass1(const hlb200_svc_base_mb_t* __restrict__ base, const SvcDeriveGeom& g, int mb, int mbw, uint8_t* had_parts, hlb200_mb_motion_t* motion, uint8_t* kind)
+// persistent macroblock object: written by every inter derivation, mb.c:137-207 / :209-244, never by an intra one).  flags[mb]: bit 0 = that carried flag, bits 1-2 = kind of the
+// macroblock in THIS picture (0 inter, 1 base macroblock intra: resolved by pass 2, 2 not reproduced) -- pass 2 only reads them, so the walk needs no other scratch.
+HLB_HD int svc_derive_pass1(const hlb200_svc_base_mb_t* __restrict__ base, const SvcDeriveGeom& g, int mb, int mbw, uint8_t* flags, hlb200_mb_motion_t* motion)
 {
     hlb200_mb_motion_t m;
     const int r = svc_derive_mb(base, g, mb % mbw, mb / mbw, m);
-    int status = 0;
-    if (r < 0) { status = SVC_DERIVE_BAD_REF; kind[mb] = 2; }
-    else if (r == 1) { kind[mb] = 1; if (had_parts[mb]) status = SVC_DERIVE_STALE_PARTS; }
+    int status = 0, had = flags[mb] & 1, kind;
+    if (r < 0) { status = SVC_DERIVE_BAD_REF; kind = 2; }
+    else if (r == 1) { kind = 1; if (had) status = SVC_DERIVE_STALE_PARTS; }
     else {
-        had_parts[mb] = 1;
-        if (svc_derive_supported(m)) kind[mb] = 0;
-        else { kind[mb] = 2; status = SVC_DERIVE_UNSUPPORTED; }
+        had = 1;
+        if (svc_derive_supported(m)) kind = 0;
+        else { kind = 2; status = SVC_DERIVE_UNSUPPORTED; }
     }
+    flags[mb] = (uint8_t)(had | (kind << 1));
     motion[mb] = m;
     return status;
 }
 // Pass 2: a macroblock whose base macroblock is intra inherits the prediction of the last macroblock before it (raster order) that has partitions
 // (hlb_svc.cuh: SvcPredSrc; host/hlb200_glue.c did this serially while it derived)
-HLB_HD int svc_derive_pass2(int mb, const uint8_t* kind, hlb200_mb_motion_t* motion)
+HLB_HD int svc_derive_pass2(int mb, const uint8_t* flags, hlb200_mb_motion_t* motion)
 {
-    if (kind[mb] != 1) return 0;
+    if ((flags[mb] >> 1) != 1) return 0;
     int a = mb - 1;
-    while (a >= 0 && kind[a] != 0) --a;
+    while (a >= 0 && (flags[a] >> 1) != 0) --a;
     if (a < 0 || a >= 65536) return SVC_DERIVE_NO_PRED_SOURCE;
     motion[mb].pad[0] = 1; motion[mb].pad[1] = (uint8_t)(a & 255); motion[mb].pad[2] = (uint8_t)(a >> 8);
     return 0;

@@ -301,7 +301,8 @@ HLB200_API int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const ui
  * utils.c:1225 (G.8.6.1.1 utils.c:1677, G.8.6.1.2 utils.c:1779, G.8.6.1.3 utils.c:1986) and ..._for_mv_comps_and_ref_indices_svc utils.c:1498 (G.8.4.1), with the
  * reference-layer lookups of utils.c:966-1059 / mb.h:313-339: d_base = n_pics x reference-layer macroblocks, d_motion = n_pics x (width / 16) x (height / 16) derived
  * macroblocks (partition layout, refIdxL0, mvL0; macroblocks whose base macroblock is intra carry the address of the macroblock whose prediction they inherit in pad[],
- * as hlb200_dev_svc_inter_recon_batch reads it), d_had_parts = one byte per derived macroblock carried from picture to picture of a layer (zero for a new layer),
+ * as hlb200_dev_svc_inter_recon_batch reads it), d_had_parts = one byte per derived macroblock carried from picture to picture of a layer (zero for a new layer; bit 0 = the reference's
+ * macroblock object holds partitions of an earlier picture, bits 1-2 = scratch of the last call),
  * d_status = one int32 per picture, HLB200_SVC_DERIVE_* bits OR-ed in (the caller zeroes it).  Frame macroblocks, RestrictedSpatialResolutionChangeFlag = 1,
  * CroppingChangeFlag = 0; anything else returns HLB200_ERR_NOT_IMPLEMENTED. */
 HLB200_API int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics,

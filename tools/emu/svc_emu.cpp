@@ -62,11 +62,9 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_derive_motion(cons
     hlb::SvcDeriveGeom g;
     if (!hlb::svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, g)) return HLB200_ERR_NOT_IMPLEMENTED;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    uint8_t* kind = new uint8_t[nmb];
     int st = 0;
-    for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass1(base, g, mb, mbw, had_parts, motion, kind);
-    for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass2(mb, kind, motion);
-    delete[] kind;
+    for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass1(base, g, mb, mbw, had_parts, motion);
+    for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass2(mb, had_parts, motion);
     *status = st;
     return HLB200_OK;
 }

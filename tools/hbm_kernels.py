@@ -48,6 +48,17 @@ for n in [int(a) for a in (sys.argv[1:] or ["1", "8", "32", "128"])]:
     }
     # algorithmic bytes per macroblock; resampling: 96 B of the reference layer read + 384 B of prediction written
     alg = {"interp_luma": 512, "interp_chroma": 256, "tq_recon": 1920, "svc_inter_recon": 1920, "svc_resample_intra": 480}
+    # inter-layer motion derivation (dyadic: a (W/2 x H/2) reference layer): 84 B of reference-layer fields per FOUR macroblocks read, 80 B of motion + 2 B of flags written per macroblock
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import svc_util
+    rngd = np.random.default_rng(5)
+    dbase = torch.from_numpy(np.concatenate([svc_util.random_base_field(rngd, W // 2, H // 2, intra_frac=0.02)] * n).view(np.uint8).copy()).to(dev)
+    dgeom = np.zeros(1, hl.SVC_GEOM)
+    dgeom["ref_width"], dgeom["ref_height"], dgeom["scaled_width"], dgeom["scaled_height"], dgeom["level_idc"], dgeom["restricted"] = W // 2, H // 2, W, H, 40, 1
+    dmotion = torch.zeros(n * nmb * hl.MB_MOTION.itemsize, dtype=torch.uint8, device=dev)
+    dhad, dstatus = torch.zeros(n * nmb, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.int32, device=dev)
+    ks["svc_derive_motion"] = lambda: lib.hlb200_dev_svc_derive_motion_batch(dbase.data_ptr(), dgeom.ctypes.data, W, H, n, dhad.data_ptr(), dmotion.data_ptr(), dstatus.data_ptr(), sp)
+    alg["svc_derive_motion"] = 103
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {"pictures_per_launch": n, "peak_gbs": PEAK, "peak_kind": PEAK_KIND, "kernels": {}}
     for name, k in ks.items():
