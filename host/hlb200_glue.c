@@ -223,6 +223,7 @@ typedef struct glue_svc_layer_s {
     hlb200_mb_coeffs_t* coeffs;
     uint8_t* rec;            /* tight Y|U|V */
     hlb200_svc_base_mb_t* base; int nbase;   /* the reference layer's macroblock fields, as uploaded for the derivation */
+    const void* fs_of_slot[2];               /* host frame store whose picture lives in each of the layer context's two device slots (reconstructions stay resident) */
 } glue_svc_layer_t;
 static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
 static glue_svc_layer_t* g_svc_active = NULL;
@@ -286,7 +287,7 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     const size_t ysz = (size_t)W * H, csz = (size_t)Wc * Hc;
     glue_svc_layer_t* L;
     HL_ERROR_T err;
-    int rc, qp = -1, dev_rs = 0, level_idc = 0;
+    int rc, qp = -1, dev_rs = 0, level_idc = 0, ref_slot = 0, cur_slot = 1;
     int32_t status = 0;
     hlb200_svc_layer_geom_t geom;
     uint32_t addr;
@@ -324,7 +325,7 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
         if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); free(L->base); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; L->base = NULL; L->nbase = 0; }
         if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
         if ((rc = hlb200_stream_create(W, H, 1, &L->ctx))) return glue_fail("hlb200_stream_create", rc);
-        L->w = W; L->h = H; L->nmb = mbw * (H >> 4);
+        L->w = W; L->h = H; L->nmb = mbw * (H >> 4); L->fs_of_slot[0] = L->fs_of_slot[1] = NULL;
         L->motion = (hlb200_mb_motion_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_motion_t));
         L->coeffs = (hlb200_mb_coeffs_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_coeffs_t));
         L->rec = (uint8_t*)malloc(ysz + 2 * csz);
@@ -379,18 +380,31 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     }
     /* (b) device: one call for the picture */
     if ((rc = hlb200_frame_upload(L->ctx, frame->data_ptr[0], frame->data_ptr[1], frame->data_ptr[2], W, Wc))) return glue_fail("hlb200_frame_upload", rc);
+    /* the layer's two device slots hold its last reconstructions; the picture being coded goes to the one that does not hold the reference */
+    {
+        const void* ref_fs = intra ? NULL : (const void*)pc_layer->pobj_poc->RefPicList0[0];
+        ref_slot = (ref_fs && L->fs_of_slot[1] == ref_fs) ? 1 : 0;
+        cur_slot = ref_slot ^ 1;
+        if (!intra) {
+            const hl_codec_264_pict_t* ref = ref_fs ? pc_layer->pobj_poc->RefPicList0[0]->p_pict : NULL;
+            if (!ref) return HL_ERROR_INVALID_STATE;
+            /* normally the reference is the picture this context reconstructed last time and is still resident; otherwise (a reordered list, a picture this context did not
+             * produce) it travels from the host DPB */
+            if (L->fs_of_slot[ref_slot] != ref_fs) {
+                if ((rc = hlb200_slot_upload(L->ctx, ref_slot, ref->pc_data_y, ref->pc_data_u, ref->pc_data_v))) return glue_fail("hlb200_slot_upload", rc);
+                L->fs_of_slot[ref_slot] = ref_fs;
+            }
+        }
+        if (L->fs_of_slot[ref_slot] == (const void*)pc_layer->pc_fs_curr) L->fs_of_slot[ref_slot] = NULL;   /* the host recycles the reference's frame store for this picture */
+        L->fs_of_slot[cur_slot] = NULL;
+    }
     if (intra) {
         const hl_codec_264_pict_t* rp = pc_layer->pc_ref->pc_fs_curr->p_pict;   /* what decode_svc.c:2970 reads: the reference layer's reconstruction of this access unit */
-        rc = hlb200_svc_layer_picture_resampled(L->ctx, 1, qp, hdr->pc_pps->chroma_qp_index_offset, rp->pc_data_y, rp->pc_data_u, rp->pc_data_v,
+        rc = hlb200_svc_layer_picture_resampled(L->ctx, cur_slot, qp, hdr->pc_pps->chroma_qp_index_offset, rp->pc_data_y, rp->pc_data_u, rp->pc_data_v,
                                                 (int)pc_layer->RefLayerPicWidthInSamplesL, (int)pc_layer->RefLayerPicHeightInSamplesL, level_idc, L->coeffs);
     }
     else {
-        /* the layer's reference picture travels from the host DPB (the picture this context reconstructed last time; kept as an upload so that a layer whose
-         * reference list was reordered by the host still predicts from what the reference would) */
-        const hl_codec_264_pict_t* ref = pc_layer->pobj_poc->RefPicList0[0] ? pc_layer->pobj_poc->RefPicList0[0]->p_pict : NULL;
-        if (!ref) return HL_ERROR_INVALID_STATE;
-        if ((rc = hlb200_slot_upload(L->ctx, 0, ref->pc_data_y, ref->pc_data_u, ref->pc_data_v))) return glue_fail("hlb200_slot_upload", rc);
-        rc = hlb200_svc_layer_picture_derived(L->ctx, 0, 1, qp, hdr->pc_pps->chroma_qp_index_offset, L->base, &geom, L->motion, &status, L->coeffs);
+        rc = hlb200_svc_layer_picture_derived(L->ctx, ref_slot, cur_slot, qp, hdr->pc_pps->chroma_qp_index_offset, L->base, &geom, L->motion, &status, L->coeffs);
         if (rc == HLB200_ERR_NOT_IMPLEMENTED) {
             /* status bits (hlb200.h HLB200_SVC_DERIVE_*): partitions the fused kernel is not pinned for, a macroblock whose base macroblock is intra while its object still holds
              * partitions of an earlier picture, or one with no earlier macroblock of the picture to inherit a prediction from -- after a layer's I picture the reference codes
@@ -401,7 +415,8 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
         }
     }
     if (rc) return glue_fail("hlb200_svc_layer_picture", rc);
-    if ((rc = hlb200_slot_download(L->ctx, 1, L->rec, L->rec + ysz, L->rec + ysz + csz))) return glue_fail("hlb200_slot_download", rc);
+    if ((rc = hlb200_slot_download(L->ctx, cur_slot, L->rec, L->rec + ysz, L->rec + ysz + csz))) return glue_fail("hlb200_slot_download", rc);
+    L->fs_of_slot[cur_slot] = (const void*)pc_layer->pc_fs_curr;   /* the host's loop copies L->rec into this frame store (glue_svc_apply): same samples on both sides */
     /* the reference's own loop: same prologue again, the wrapped guess functions copy the device's results, the real writer serialises them */
     g_svc_active = L; g_svc_intra = intra;
     err = __real_hl_codec_264_nal_slice_data_encode(p_codec, p_esd);
