@@ -126,6 +126,7 @@ int hlb200_stream_create(int width, int height, int max_refs, hlb200_ctx_t** out
     *out = c;
     HLB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    HLB_CUDA(cudaGetDevice(&c->device));
     for (int p = 0; p < 3; ++p) {
         HLB_CUDA(cudaMalloc(&c->d_src[p], plane_bytes(c, p)));
         c->d_src_cur[p] = c->d_src[p];
@@ -338,6 +339,51 @@ int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* c, int cur_slot, int qp, in
     hlb200_mb_coeffs_t* d_coeffs = (hlb200_mb_coeffs_t*)c->d_scratch;
     uint8_t* d_ref = (uint8_t*)c->d_scratch + cbytes;
     if ((rc = h2d(c, d_ref, ref_y, rys)) || (rc = h2d(c, d_ref + rys, ref_u, rcs)) || (rc = h2d(c, d_ref + rys + rcs, ref_v, rcs))) return rc;
+    if ((rc = hlb200_dev_svc_resample_intra_batch(d_ref, d_ref + rys, d_ref + rys + rcs, ref_width, ref_height, c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, 1, 0, 0,
+                                                  level_idc, c->stream)))
+        return rc;
+    if ((rc = hlb200_dev_svc_bl_recon_batch(c->d_src_cur[0], c->d_src_cur[1], c->d_src_cur[2], c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, 1, 0, qp,
+                                            chroma_qp_index_offset, (hlb200_svc_mb_state_t*)c->d_svc_state, d_coeffs, c->d_slot[cur_slot][0], c->d_slot[cur_slot][1],
+                                            c->d_slot[cur_slot][2], c->stream)))
+        return rc;
+    if ((rc = d2h(c, out_coeffs, d_coeffs, sizeof(hlb200_mb_coeffs_t) * c->nmb))) return rc;
+    HLB_CUDA(cudaStreamSynchronize(c->stream));
+    return HLB200_OK;
+}
+
+// The same with the reference layer's reconstruction taken from ANOTHER CONTEXT's frame store instead of host planes (the per-access-unit hand-off between the
+// layers of an SVC stream): the lower layer's context may live on another GPU, the planes then travel GPU to GPU (cudaMemcpyPeerAsync over NVLink; without peer access the
+// runtime stages the copy itself).  The calling thread's current device must be ctx's.
+int hlb200_svc_layer_picture_resampled_from(hlb200_ctx_t* c, int cur_slot, int qp, int chroma_qp_index_offset, hlb200_ctx_t* rc_ctx, int ref_ctx_slot, int level_idc,
+                                            hlb200_mb_coeffs_t* out_coeffs)
+{
+    if (!c || !rc_ctx || rc_ctx == c || cur_slot < 0 || cur_slot >= c->nslots || ref_ctx_slot < 0 || ref_ctx_slot >= rc_ctx->nslots || !out_coeffs || qp < 0 || qp > 51 ||
+        rc_ctx->width > c->width || rc_ctx->height > c->height)
+        return HLB200_ERR_INVALID_PARAMETER;
+    const int ref_width = rc_ctx->width, ref_height = rc_ctx->height;
+    const size_t cbytes = (sizeof(hlb200_mb_coeffs_t) * c->nmb + 255) & ~(size_t)255, rys = (size_t)ref_width * ref_height, rcs = rys >> 2;
+    int rc = ensure_scratch(c, cbytes + rys + 2 * rcs);
+    if (rc) return rc;
+    if (!c->d_svc_state) {
+        HLB_CUDA(cudaMalloc(&c->d_svc_state, sizeof(hlb200_svc_mb_state_t) * c->nmb));
+        HLB_CUDA(cudaMemsetAsync(c->d_svc_state, 0, sizeof(hlb200_svc_mb_state_t) * c->nmb, c->stream));
+    }
+    hlb200_mb_coeffs_t* d_coeffs = (hlb200_mb_coeffs_t*)c->d_scratch;
+    uint8_t* d_ref = (uint8_t*)c->d_scratch + cbytes;
+    // the lower layer's picture is complete once its stream has drained (its own picture call synchronised already; this also covers asynchronous producers)
+    {
+        int cur = 0;
+        HLB_CUDA(cudaGetDevice(&cur));
+        if (cur != rc_ctx->device) HLB_CUDA(cudaSetDevice(rc_ctx->device));
+        const cudaError_t e = cudaStreamSynchronize(rc_ctx->stream);
+        if (cur != rc_ctx->device) HLB_CUDA(cudaSetDevice(cur));
+        HLB_CUDA(e);
+    }
+    const size_t off[3] = {0, rys, rys + rcs}, bytes[3] = {rys, rcs, rcs};
+    for (int p = 0; p < 3; ++p) {
+        if (rc_ctx->device == c->device) HLB_CUDA(cudaMemcpyAsync(d_ref + off[p], rc_ctx->d_slot[ref_ctx_slot][p], bytes[p], cudaMemcpyDeviceToDevice, c->stream));
+        else HLB_CUDA(cudaMemcpyPeerAsync(d_ref + off[p], c->device, rc_ctx->d_slot[ref_ctx_slot][p], rc_ctx->device, bytes[p], c->stream));
+    }
     if ((rc = hlb200_dev_svc_resample_intra_batch(d_ref, d_ref + rys, d_ref + rys + rcs, ref_width, ref_height, c->d_pred[0], c->d_pred[1], c->d_pred[2], c->width, c->height, 1, 0, 0,
                                                   level_idc, c->stream)))
         return rc;

@@ -91,4 +91,5 @@ struct hlb200_ctx {
     void* d_bits_jobs; void* h_bits_jobs; int bits_jobs_cap; cudaEvent_t ev_bits;   // owner of a serialisation batch: job descriptors
     void* d_dbk_bs;                             // deblocking: 32 boundary-strength bytes per macroblock (allocated on first use, hlb_deblock.cuh)
     int frame_count;
+    int device;                                 // CUDA device the context's memory and stream live on (the device current when hlb200_stream_create ran)
 };

@@ -68,6 +68,7 @@ def load():
         "hlb200_dev_svc_inter_recon_batch": [vp, vp, vp, vp, vp, vp, ip, ip, ip, C.c_size_t, ip, ip, vp, vp, vp, vp, vp, vp, vp],
         "hlb200_svc_layer_picture": [vp, ip, ip, ip, ip, vp, vp, vp, vp, vp],
         "hlb200_svc_layer_picture_resampled": [vp, ip, ip, ip, vp, vp, vp, ip, ip, ip, vp],
+        "hlb200_svc_layer_picture_resampled_from": [vp, ip, ip, ip, vp, ip, ip, vp],
         "hlb200_dev_svc_derive_motion_batch": [vp, vp, ip, ip, ip, vp, vp, vp, vp],
         "hlb200_svc_layer_picture_derived": [vp, ip, ip, ip, ip, vp, vp, vp, C.POINTER(C.c_int32), vp],
         "hlb200_dev_svc_resample_intra_batch": [vp, vp, vp, ip, ip, vp, vp, vp, ip, ip, ip, C.c_size_t, C.c_size_t, ip, vp],
@@ -192,6 +193,13 @@ class Stream:
         ry, ru, rv = np.ascontiguousarray(r[:ys]), np.ascontiguousarray(r[ys:ys + cs]), np.ascontiguousarray(r[ys + cs:ys + 2 * cs])
         check(self.lib.hlb200_svc_layer_picture_resampled(self.ctx, cur_slot, qp, chroma_qp_index_offset, ptr(ry), ptr(ru), ptr(rv), ref_w, ref_h, level_idc, ptr(coeffs)),
               "svc_layer_picture_resampled")
+        return coeffs, self.download_slot(cur_slot)
+
+    def svc_layer_picture_resampled_from(self, qp, ref_stream, ref_stream_slot, cur_slot=1, chroma_qp_index_offset=0, level_idc=0):
+        """the same with the reference layer's reconstruction taken from frame store ref_stream_slot of another Stream (same or another GPU)"""
+        coeffs = np.zeros(self.nmb, MB_COEFFS)
+        check(self.lib.hlb200_svc_layer_picture_resampled_from(self.ctx, cur_slot, qp, chroma_qp_index_offset, ref_stream.ctx, ref_stream_slot, level_idc, ptr(coeffs)),
+              "svc_layer_picture_resampled_from")
         return coeffs, self.download_slot(cur_slot)
 
     def sad4x4(self, pred_y, satd=False):

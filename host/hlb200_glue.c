@@ -90,6 +90,29 @@ int hlb200_glue_batch_flush(void)
     return rc;
 }
 
+/* Which GPU a layer's context lives on: HLB200_SVC_DEVICES = comma-separated device ordinals, layer 0 first (the layers of an SVC stream sharded over GPUs,
+ * "0,1,2" = one layer per GPU); layers beyond the list, and streams without the variable, use HLB200_DEVICE (default 0).  The host code is single-threaded: the device
+ * of the context about to be used is made current before every group of library calls. */
+static int g_dev_cur = -1;
+static int glue_layer_device(int li)
+{
+    const char* list = getenv("HLB200_SVC_DEVICES");
+    const char* one = getenv("HLB200_DEVICE");
+    int i;
+    for (i = 0; list && *list; ++i) {
+        if (i == li) return atoi(list);
+        list = strchr(list, ',');
+        if (list) ++list;
+    }
+    return one ? atoi(one) : 0;
+}
+static int glue_use_device(int dev)
+{
+    int rc = 0;
+    if (dev != g_dev_cur && !(rc = hlb200_init(dev))) g_dev_cur = dev;
+    return rc;
+}
+
 static HL_ERROR_T glue_fail(const char* what, int rc)
 {
     HL_DEBUG_ERROR("hlb200: %s failed (%d): %s", what, rc, hlb200_last_error());
@@ -223,6 +246,7 @@ typedef struct glue_svc_layer_s {
     hlb200_mb_coeffs_t* coeffs;
     uint8_t* rec;            /* tight Y|U|V */
     hlb200_svc_base_mb_t* base; int nbase;   /* the reference layer's macroblock fields, as uploaded for the derivation */
+    int dev;                                 /* GPU of this layer's context (glue_layer_device) */
     const void* fs_of_slot[2];               /* host frame store whose picture lives in each of the layer context's two device slots (reconstructions stay resident) */
 } glue_svc_layer_t;
 static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
@@ -320,11 +344,11 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
         level_idc = (int)top->pc_slice_hdr->pc_pps->pc_sps->level_idc;
     }
     L = &g_svc[li];
-    if (!L->ctx || L->w != W || L->h != H) {
-        const char* dev = getenv("HLB200_DEVICE");
-        if (L->ctx) { hlb200_stream_destroy(L->ctx); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); free(L->base); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; L->base = NULL; L->nbase = 0; }
-        if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
+    if ((rc = glue_use_device(glue_layer_device(li)))) return glue_fail("hlb200_init", rc);
+    if (!L->ctx || L->w != W || L->h != H || L->dev != g_dev_cur) {
+        if (L->ctx) { const int now = g_dev_cur; if (glue_use_device(L->dev) == 0) hlb200_stream_destroy(L->ctx); glue_use_device(now); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); free(L->base); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; L->base = NULL; L->nbase = 0; }
         if ((rc = hlb200_stream_create(W, H, 1, &L->ctx))) return glue_fail("hlb200_stream_create", rc);
+        L->dev = g_dev_cur;
         L->w = W; L->h = H; L->nmb = mbw * (H >> 4); L->fs_of_slot[0] = L->fs_of_slot[1] = NULL;
         L->motion = (hlb200_mb_motion_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_motion_t));
         L->coeffs = (hlb200_mb_coeffs_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_coeffs_t));
@@ -400,6 +424,22 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     }
     if (intra) {
         const hl_codec_264_pict_t* rp = pc_layer->pc_ref->pc_fs_curr->p_pict;   /* what decode_svc.c:2970 reads: the reference layer's reconstruction of this access unit */
+        /* that picture was reconstructed by the reference layer's own device context a moment ago and is still resident there (same samples as the host copy: the glue
+         * itself wrote the host copy from it): hand it over device to device -- GPU to GPU when the layers live on different ones -- instead of uploading the host copy */
+        const int li_ref = (int)(pc_layer->pc_ref->DQId >> 4);
+        const void* rfs = (const void*)pc_layer->pc_ref->pc_fs_curr;
+        hlb200_ctx_t* rctx = NULL;
+        int rslot = -1, k;
+        if (li_ref == 0) {
+            const glue_stream_t* gb = glue_stream_of(p_codec, 0);
+            for (k = 0; gb && gb->ctx && k < gb->nslots; ++k) if (gb->fs_of_slot[k] == rfs && gb->w == (int)pc_layer->RefLayerPicWidthInSamplesL && gb->h == (int)pc_layer->RefLayerPicHeightInSamplesL) { rctx = gb->ctx; rslot = k; }
+        }
+        else if (li_ref > 0 && li_ref < li && g_svc[li_ref].ctx && g_svc[li_ref].w == (int)pc_layer->RefLayerPicWidthInSamplesL && g_svc[li_ref].h == (int)pc_layer->RefLayerPicHeightInSamplesL) {
+            for (k = 0; k < 2; ++k) if (g_svc[li_ref].fs_of_slot[k] == rfs) { rctx = g_svc[li_ref].ctx; rslot = k; }
+        }
+        if (rctx && !getenv("HLB200_SVC_HOST_HANDOFF"))
+            rc = hlb200_svc_layer_picture_resampled_from(L->ctx, cur_slot, qp, hdr->pc_pps->chroma_qp_index_offset, rctx, rslot, level_idc, L->coeffs);
+        else
         rc = hlb200_svc_layer_picture_resampled(L->ctx, cur_slot, qp, hdr->pc_pps->chroma_qp_index_offset, rp->pc_data_y, rp->pc_data_u, rp->pc_data_v,
                                                 (int)pc_layer->RefLayerPicWidthInSamplesL, (int)pc_layer->RefLayerPicHeightInSamplesL, level_idc, L->coeffs);
     }
@@ -512,13 +552,12 @@ HL_ERROR_T __wrap_hl_codec_264_nal_slice_data_encode(hl_codec_264_t* p_codec, hl
         return HL_ERROR_NOT_IMPLEMENTED;
     }
     if (!(g = glue_stream_of(p_codec, 1))) { HL_DEBUG_ERROR("hlb200: too many codec instances"); return HL_ERROR_OUTOFCAPACITY; }
+    if ((rc = glue_use_device(glue_layer_device(0)))) return glue_fail("hlb200_init", rc);
     if (!g->ctx || g->w != W || g->h != H) {
-        const char* dev = getenv("HLB200_DEVICE");
         int refs = (int)p_codec->pc_base->max_ref_frame;
         if (refs < 1) refs = 1;
         if (refs > HLB200_MAX_REFS) refs = HLB200_MAX_REFS;
         if (g->ctx) { hlb200_stream_destroy(g->ctx); g->ctx = NULL; free(g->rec); free(g->bits); g->rec = NULL; g->bits = NULL; }
-        if ((rc = hlb200_init(dev ? atoi(dev) : 0))) return glue_fail("hlb200_init", rc);
         if ((rc = hlb200_stream_create(W, H, refs, &g->ctx))) return glue_fail("hlb200_stream_create", rc);
         g->w = W; g->h = H; g->nmb = (W >> 4) * (H >> 4); g->nslots = refs + 1;
         memset(g->fs_of_slot, 0, sizeof(g->fs_of_slot));

@@ -256,6 +256,11 @@ HLB200_API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* ctx, int cur_slo
                                                   const uint8_t* ref_v, int ref_width, int ref_height, int level_idc, hlb200_mb_coeffs_t* out_coeffs);
 
 /* ---- whole-frame batch kernels, host buffers (copies inside) ---- */
+/* ... and with the reference layer's reconstruction read from frame store `ref_ctx_slot` of the lower layer's context `ref_ctx` (its width x height are the reference
+ * layer's), on the same GPU or another one: the hand-off between the layers of an access unit stays on the device(s) -- cudaMemcpyPeerAsync between GPUs.
+ * Replaces the same call sites as hlb200_svc_layer_picture_resampled (rdo.c:363-377 -> decode_svc.c:2864). */
+HLB200_API int hlb200_svc_layer_picture_resampled_from(hlb200_ctx_t* ctx, int cur_slot, int qp, int chroma_qp_index_offset, hlb200_ctx_t* ref_ctx, int ref_ctx_slot,
+                                                       int level_idc, hlb200_mb_coeffs_t* out_coeffs);
 HLB200_API int hlb200_interp_luma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_y);
 HLB200_API int hlb200_interp_chroma(hlb200_ctx_t* ctx, int ref_slot, const hlb200_mb_motion_t* motion, uint8_t* pred_u, uint8_t* pred_v);
 HLB200_API int hlb200_tq_recon(hlb200_ctx_t* ctx, int qp, int chroma_qp_index_offset, const uint8_t* pred_y, const uint8_t* pred_u, const uint8_t* pred_v,

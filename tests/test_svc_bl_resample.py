@@ -167,3 +167,30 @@ def test_gpu_layer_picture_resampled_vs_golden():
     assert coef.tobytes() == coef2.tobytes() and np.array_equal(rec, rec2)
     assert svc_util.compare_picture(p, coef, rec, None, "GPU resampled layer picture") == (w // 16) * (h // 16)
     st.close(); st2.close()
+
+
+@pytest.mark.gpu
+def test_gpu_layer_picture_resampled_from_another_context():
+    """hlb200_svc_layer_picture_resampled_from: the reference layer's reconstruction is read from a frame store of the lower layer's device context (the hand-off
+    between the layers of an access unit) -- same coefficients and reconstruction as the host-buffer entry point; with a second GPU in the box the lower
+    layer's context lives there and the planes travel GPU to GPU (cudaMemcpyPeerAsync)"""
+    from hartallo_b200 import lib as hl
+    lib = hl.load()
+    base, (rw, rh), pred, (w, h) = golden_pair()
+    p = [q for q in svc_util.load_golden() if q["name"] == "g2_3layer.1"][0]
+    st = hl.Stream(w, h, 1)
+    st.upload_frame(p["src"])
+    coef, rec = st.svc_layer_picture_resampled(p["qp"], base, rw, rh)
+    for ref_dev in range(min(2, lib.hlb200_device_count())):
+        low = hl.Stream(rw, rh, 1, device=ref_dev)      # hlb200_init(ref_dev): the lower layer's context on that GPU
+        low.upload_slot(1, base)
+        hl.check(lib.hlb200_init(0), "hlb200_init")     # back to the enhancement layer's GPU
+        up = hl.Stream(w, h, 1)
+        up.upload_frame(p["src"])
+        coef2, rec2 = up.svc_layer_picture_resampled_from(p["qp"], low, 1)
+        assert coef.tobytes() == coef2.tobytes() and np.array_equal(rec, rec2), ref_dev
+        up.close()
+        hl.check(lib.hlb200_init(ref_dev), "hlb200_init")
+        low.close()
+        hl.check(lib.hlb200_init(0), "hlb200_init")
+    st.close()

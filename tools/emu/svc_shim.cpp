@@ -200,6 +200,14 @@ API int hlb200_svc_layer_picture(hlb200_ctx_t* c, int ref_slot, int cur_slot, in
     else { ry = c->slot[ref_slot]; ru = ry + ysz; rv = ru + csz; }
     return svc_emu_recon_batch(ref_slot < 0, s, s + ysz, s + ysz + csz, ry, ru, rv, c->w, c->h, 1, 0, qp, off, motion, c->state, out, o, o + ysz, o + ysz + csz);
 }
+API int hlb200_svc_layer_picture_resampled(hlb200_ctx_t* c, int cur_slot, int qp, int off, const uint8_t* ref_y, const uint8_t* ref_u, const uint8_t* ref_v, int rw, int rh,
+                                           int level_idc, hlb200_mb_coeffs_t* out);
+API int hlb200_svc_layer_picture_resampled_from(hlb200_ctx_t* c, int cur_slot, int qp, int off, hlb200_ctx_t* r, int rslot, int level_idc, hlb200_mb_coeffs_t* out)
+{
+    const size_t rys = (size_t)r->w * r->h, rcs = rys >> 2;
+    const uint8_t* p = r->slot[rslot];
+    return hlb200_svc_layer_picture_resampled(c, cur_slot, qp, off, p, p + rys, p + rys + rcs, r->w, r->h, level_idc, out);
+}
 extern "C" int svc_emu_derive_motion(const hlb200_svc_base_mb_t* base, const hlb200_svc_layer_geom_t* geom, int width, int height, uint8_t* had_parts, hlb200_mb_motion_t* motion,
                                      int32_t* status);
 API int hlb200_svc_layer_picture_derived(hlb200_ctx_t* c, int ref_slot, int cur_slot, int qp, int off, const hlb200_svc_base_mb_t* base, const hlb200_svc_layer_geom_t* geom,
