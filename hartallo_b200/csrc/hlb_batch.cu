@@ -150,7 +150,10 @@ __device__ __forceinline__ void transpose4_u2(uint2 P[4], int lane)
         if (o2) P[j] = rcv; else P[j + 2] = rcv;
     }
 }
-__global__ void __launch_bounds__(128, 10) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
+#ifndef HLB_TQ_MINB
+#define HLB_TQ_MINB 12   // 40 registers (40 bytes spilled): 48 resident warps instead of 40 -- 0.4935 -> 0.519 of the HBM peak at 128 pictures per launch (profiles/r02v_tq_variants.log; 16 blocks: 0.463)
+#endif
+__global__ void __launch_bounds__(128, HLB_TQ_MINB) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
                                                   const uint8_t* __restrict__ pred_y, const uint8_t* __restrict__ pred_u, const uint8_t* __restrict__ pred_v,
                                                   int W, int H, int mbw, int nmb, int qp, int qpc, hlb200_mb_coeffs_t* __restrict__ coeffs,
                                                   uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride, int luma_ctas)

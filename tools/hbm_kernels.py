@@ -61,7 +61,10 @@ for n in [int(a) for a in (sys.argv[1:] or ["1", "8", "32", "128"])]:
     alg["svc_derive_motion"] = 103
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {"pictures_per_launch": n, "peak_gbs": PEAK, "peak_kind": PEAK_KIND, "kernels": {}}
+    only = os.environ.get("HBM_ONLY")   # restrict the table to one kernel (A/B runs of build variants selected with HLB200_LIB)
     for name, k in ks.items():
+        if only and name != only:
+            continue
         for _ in range(3):
             hl.check(k(), name)
         ts = []

@@ -1,2 +1,7 @@
-python tools/hbm_kernels.py 128 2>&1 | tail -1
-python -m pytest tests/test_codec_264_transf.py tests/test_batch_pictures.py -x -q -m gpu 2>&1 | tail -2
+mkdir -p gpurun_out
+: > gpurun_out/r02v_tq_variants.log
+for L in "" hartallo_b200/variants/tq12.so hartallo_b200/variants/tq16.so ""; do
+  echo "lib=$L" >> gpurun_out/r02v_tq_variants.log
+  HLB200_LIB=${L:+$PWD/$L} HBM_ONLY=tq_recon python tools/hbm_kernels.py 128 >> gpurun_out/r02v_tq_variants.log 2>&1
+done
+grep -o "lib=.*\|\"tq_recon\": {[^}]*}" gpurun_out/r02v_tq_variants.log
