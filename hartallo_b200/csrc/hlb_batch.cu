@@ -38,7 +38,10 @@ __device__ __forceinline__ void load_win9(const uint8_t* __restrict__ plane, int
 // (a warp stores 32 adjacent words of each of its four output rows; the 9x9 window of an interior block is read straight from the plane as aligned 32-bit
 // words through the read-only path and funnel-shifted into place, the prediction is formed by the packed formulation of hlb_fast.cuh).
 // blockIdx.y = picture of a batch: the planes of consecutive pictures lie `stride` bytes apart, their motion fields nmb entries apart
-__global__ void __launch_bounds__(256) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
+#ifndef HLB_IL_MINB
+#define HLB_IL_MINB 5   // 48 registers: +5 % (profiles/r02v2_variants.log)
+#endif
+__global__ void __launch_bounds__(256, HLB_IL_MINB) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
                                                      const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred, size_t stride)
 {
     const int bw = W >> 2, t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,8 +308,11 @@ __global__ void __launch_bounds__(128, HLB_TQ_MINB) k_tq_recon(const uint8_t* __
 // picture (ChromaACLevel of blocks without residual, ChromaDCLevel of planes without DC) travels in / out through `state`.  The formulation checked against the
 // reference's trace on the CPU is the per-lane one of hlb_svc.cuh (tools/emu/svc_emu.cpp); this kernel is checked against the oracle and the golden
 // fixtures on the GPU (tests/test_svc_inter.py).  Round 1's kernel (one warp per macroblock on hlb_svc.cuh's phases) measured 0.056 of the HBM peak.
+#ifndef HLB_SVC_MINB
+#define HLB_SVC_MINB 10   // 48 registers: +1.4 %
+#endif
 template <bool BL>
-__global__ void __launch_bounds__(128) k_svc_inter_recon(SvcPlanes P, int mbw, int nmb, int qp, int qpc, const hlb200_mb_motion_t* __restrict__ motion,
+__global__ void __launch_bounds__(128, HLB_SVC_MINB) k_svc_inter_recon(SvcPlanes P, int mbw, int nmb, int qp, int qpc, const hlb200_mb_motion_t* __restrict__ motion,
                                                          hlb200_svc_mb_state_t* __restrict__ state, hlb200_mb_coeffs_t* __restrict__ coeffs, size_t stride, int luma_ctas)
 {
     __shared__ TqConst K;
@@ -765,7 +771,10 @@ int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const
 
 // Intra_Base resampling (hlb_svc.cuh: svc_resample_px): one thread = four horizontally adjacent output samples of one plane, stored as one word;
 // blockIdx.y = picture, blockIdx.z = plane (Y, Cb, Cr).  Reads of the (four times smaller) reference plane go through the read-only path.
-__global__ void __launch_bounds__(256) k_svc_resample_intra(const uint8_t* __restrict__ ref_y, const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int refW,
+#ifndef HLB_RS_MINB
+#define HLB_RS_MINB 6   // 40 registers: +1.3 %
+#endif
+__global__ void __launch_bounds__(256, HLB_RS_MINB) k_svc_resample_intra(const uint8_t* __restrict__ ref_y, const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int refW,
                                                             int refH, uint8_t* __restrict__ out_y, uint8_t* __restrict__ out_u, uint8_t* __restrict__ out_v, int W, int H,
                                                             size_t ref_frame_stride, size_t frame_stride, int level_idc)
 {
