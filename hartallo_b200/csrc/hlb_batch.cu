@@ -756,8 +756,8 @@ int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const
     if (!d_base || !geom || !d_had_parts || !d_motion || !d_status || width < 16 || height < 16 || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535)
         return HLB200_ERR_INVALID_PARAMETER;
     SvcDeriveGeom g;
-    if (!geom->restricted || geom->cropping_change ||
-        !svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, g)) {
+    if (geom->cropping_change ||
+        !svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, geom->restricted, g)) {
         snprintf(g_err, sizeof(g_err), "hlb200: inter-layer motion derivation outside the restricted spatial-resolution-change case (or an overflowing precision) is not implemented");
         return HLB200_ERR_NOT_IMPLEMENTED;
     }

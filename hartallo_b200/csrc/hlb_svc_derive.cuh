@@ -7,8 +7,8 @@
 //   G.8.4.1         refIdxL0 / mvL0 of every (sub-)macroblock partition           utils.c:1498-1650
 // as one thread per enhancement-layer macroblock over a compact copy of the reference layer's macroblock fields (hlb200_svc_base_mb_t), so that a layer
 // picture needs nothing from the host but those records.  Scope = what the reference can be run on here: frame macroblocks, P (EP) slices,
-// RestrictedSpatialResolutionChangeFlag = 1 (layer.c:143: same size or dyadic, macroblock-aligned offsets), CroppingChangeFlag = 0; the merging steps of the
-// unrestricted case (G-210..G-215, G-244..G-261) are not built and such pictures are refused by the callers.  The functions are HLB_HD: under nvcc the body of
+// CroppingChangeFlag = 0; both the restricted case (layer.c:143: same size or dyadic, macroblock-aligned offsets) and the general one with its replacement /
+// merging steps (G-210..G-215, G-244..G-261), pinned against live runs of the reference with layers scaled 3:2.  The functions are HLB_HD: under nvcc the body of
 // k_svc_derive (hlb_batch.cu), as plain C++ the CPU run of tools/emu/svc_emu.cpp that the CPU tier checks against the reference's trace (tag 11 / tag 6).
 #pragma once
 #include "../../include/hlb200.h"
@@ -23,12 +23,14 @@ struct SvcDeriveGeom {
     int shift_x, shift_y;              // (G-7), (G-8)
     int scale_x, scale_y;              // (G-9), (G-10): position scaling
     int mv_scale_x, mv_scale_y;        // (G-232), (G-233) with dSW = dSH = 0 (CroppingChangeFlag = 0)
+    int restricted;                    // RestrictedSpatialResolutionChangeFlag (layer.c:143): 0 = the replacement / merging steps of the general case run
 };
 // ceil(log2(v)), host side (utils.c:990-991 go through HL_MATH_CEIL(HL_MATH_LOG2()))
 inline int svc_derive_ceil_log2(int v) { int n = 0; while ((1 << n) < v) ++n; return n; }
 // false when the reference itself has no defined result: level_idc > 30 with a power-of-two reference dimension overflows `refW << shiftX` (as svc_rs_precision_ok)
-inline bool svc_derive_geom(int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, SvcDeriveGeom& g)
+inline bool svc_derive_geom(int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int restricted, SvcDeriveGeom& g)
 {
+    g.restricted = restricted != 0;
     if (ref_w < 16 || ref_h < 16 || (ref_w & 15) || (ref_h & 15) || scaled_w < 1 || scaled_h < 1 || ref_w > 16384 || ref_h > 16384 || scaled_w > 16384 || scaled_h > 16384) return false;
     if (level_idc > 30 && (!(ref_w & (ref_w - 1)) || !(ref_h & (ref_h - 1)))) return false;
     g.ref_w = ref_w; g.ref_h = ref_h; g.ref_mbw = ref_w >> 4; g.nref = (ref_w >> 4) * (ref_h >> 4);
@@ -46,7 +48,7 @@ inline bool svc_derive_geom(int ref_w, int ref_h, int scaled_w, int scaled_h, in
 enum {
     SVC_DERIVE_BAD_REF = 1,        // a 4x4 block maps outside the reference layer, onto a macroblock object the reference would divide by zero on, or intra and inter
                                    // reference macroblocks mix inside one macroblock (cannot happen at the restricted ratios with aligned offsets)
-    SVC_DERIVE_UNSUPPORTED = 2,    // partitions the fused kernel is not pinned for: sub-macroblock partitions below 8x8, refIdxL0 != 0, predFlagL0 = 0 (glue: `ok`)
+    SVC_DERIVE_UNSUPPORTED = 2,    // a partition the fused kernel is not pinned for: refIdxL0 != 0 or predFlagL0 = 0 (the layer contexts hold ONE reference picture)
     SVC_DERIVE_STALE_PARTS = 4,    // base macroblock intra but the macroblock object still holds partitions of an earlier picture (NumSubMbPart[0] != 0): the reference predicts
                                    // from RefPicList0[-1]
     SVC_DERIVE_NO_PRED_SOURCE = 8  // base macroblock intra and no earlier macroblock of the picture has partitions (the reference codes it against scratch memory of an earlier picture)
@@ -59,6 +61,7 @@ HLB_HD int svc_derive_sar(int v, int s) { return v >> s; }   // arithmetic, as g
 HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const SvcDeriveGeom& g, int mbx, int mby, hlb200_mb_motion_t& out)
 {
     int tref[16], mvx[16], mvy[16], n_intra = 0;
+    unsigned intra = 0;   // bit b: refLayerPartIdc of 4x4 block b is -1 (reference-layer macroblock intra)
     out.part_mode = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { out.sub_mode[i] = 0; out.ref_idx[i] = 0; }
@@ -80,7 +83,7 @@ HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const Sv
         const int addr = (yr >> 4) * g.ref_mbw + (xr >> 4);
         if (addr >= g.nref) return -1;
         const hlb200_svc_base_mb_t& B = base[addr];
-        if (B.flags & 1) { ++n_intra; tref[b] = -1; mvx[b] = mvy[b] = 0; continue; }   // refLayerPartIdc = -1 (utils.c:1701-1703)
+        if (B.flags & 1) { ++n_intra; intra |= 1u << b; tref[b] = -1; mvx[b] = mvy[b] = 0; continue; }   // refLayerPartIdc = -1 (utils.c:1701-1703)
         const int xB = xr & 15, yB = yr & 15;
         // 6.4.12.4 as mb.h:313-339 evaluates it on the reference layer's macroblock object
         int p = 0, s = 0;
@@ -103,9 +106,94 @@ HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const Sv
         }
     }
     if (n_intra == 16) return 1;
-    if (n_intra) return -1;
-    // refIdxILPredL0 of an 8x8 block = that of its upper-left 4x4 block (utils.c:1888; nothing is merged in the restricted case)
-    const int r00 = tref[0], r01 = tref[2], r10 = tref[8], r11 = tref[10];
+    if (n_intra && g.restricted) return -1;
+    int r00, r01, r10, r11;
+    if (!g.restricted) {
+        // ---- the general case (RestrictedSpatialResolutionChangeFlag = 0), statement by statement as the reference executes it ----
+        // (1) intra 4x4 blocks take the partition of a neighbour inside their 8x8 block, utils.c:1713-1741.  Copying refLayerPartIdc = copying what follows from it
+        // (reference index, scaled vector).  Two things differ from G.8.6.1.1 and are reproduced: procI4x4Blk is NOT reset between the 8x8 blocks, and the first test reads
+        // `refLayerPartIdc[yO + yS][xO + 1] == -1` (fixed column, equality) where the clause has `[xO + 1 - xS] != -1`.
+#define SVC_CP(dst, src) do { tref[dst] = tref[src]; mvx[dst] = mvx[src]; mvy[dst] = mvy[src]; intra = (intra & ~(1u << (dst))) | (((intra >> (src)) & 1u) << (dst)); } while (0)
+        unsigned proc4 = 0;   // procI4x4Blk[yS][xS] at bit yS * 2 + xS
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int xO = (q & 1) << 1, yO = (q >> 1) << 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xS = k & 1, yS = k >> 1, b = (yO + yS) * 4 + xO + xS;
+                if (!((intra >> b) & 1)) continue;
+                proc4 |= 1u << k;
+                const int bh = (yO + yS) * 4 + xO + 1 - xS, bv = (yO + 1 - yS) * 4 + xO + xS, bd = (yO + 1 - yS) * 4 + xO + 1 - xS;
+                if (!((proc4 >> (yS * 2 + 1 - xS)) & 1) && ((intra >> ((yO + yS) * 4 + xO + 1)) & 1)) SVC_CP(b, bh);          // (G-210) as coded
+                else if (!((proc4 >> ((1 - yS) * 2 + xS)) & 1) && !((intra >> bv) & 1)) SVC_CP(b, bv);                          // (G-211)
+                else if (!((proc4 >> ((1 - yS) * 2 + 1 - xS)) & 1) && !((intra >> bd) & 1)) SVC_CP(b, bd);                      // (G-212)
+            }
+        }
+        // (2) 8x8 blocks whose upper-left 4x4 block is still intra take a neighbouring 8x8 block's columns / rows / corner, utils.c:1743-1774
+        unsigned proc8 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int xP = q & 1, yP = q >> 1;
+            if (!((intra >> ((yP << 1) * 4 + (xP << 1))) & 1)) continue;
+            proc8 |= 1u << q;
+            int mode = 0;
+            if (!((proc8 >> (yP * 2 + 1 - xP)) & 1) && !((intra >> ((yP << 1) * 4 + 2 - xP)) & 1)) mode = 1;                      // (G-213)
+            else if (!((proc8 >> ((1 - yP) * 2 + xP)) & 1) && !((intra >> ((2 - yP) * 4 + (xP << 1))) & 1)) mode = 2;               // (G-214)
+            else if (!((proc8 >> ((1 - yP) * 2 + 1 - xP)) & 1) && !((intra >> ((2 - yP) * 4 + 2 - xP)) & 1)) mode = 3;              // (G-215)
+            if (!mode) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xS = k & 1, yS = k >> 1, b = ((yP << 1) + yS) * 4 + (xP << 1) + xS;
+                const int src = mode == 1 ? ((yP << 1) + yS) * 4 + 2 - xP : (mode == 2 ? (2 - yP) * 4 + (xP << 1) + xS : (2 - yP) * 4 + 2 - xP);
+                SVC_CP(b, src);
+            }
+        }
+#undef SVC_CP
+        if (intra) return -1;   // the reference would index its macroblock list with -1 (utils.c:1797-1803)
+        // (3) reference index of an 8x8 block = smallest non-negative one of its 4x4 blocks, vectors of blocks with another index replaced, utils.c:1888-1912.  The
+        // minimum is taken while the four blocks are walked, so a block is compared with the minimum SO FAR (the clause takes the minimum first).
+        int rq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int xP = q & 1, yP = q >> 1;
+            int r = tref[(yP << 1) * 4 + (xP << 1)];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xS = k & 1, yS = k >> 1, b = (2 * yP + yS) * 4 + 2 * xP + xS, t = tref[b];
+                r = (r >= 0 && t >= 0) ? (r < t ? r : t) : (r > t ? r : t);   // HL_MATH_MIN_POSITIVE (G-245)
+                if (t != r) {
+                    const int bh = (2 * yP + yS) * 4 + 2 * xP + 1 - xS, bv = (2 * yP + 1 - yS) * 4 + 2 * xP + xS, bd = (2 * yP + 1 - yS) * 4 + 2 * xP + 1 - xS;
+                    const int src = tref[bh] == r ? bh : (tref[bv] == r ? bv : bd);   // (G-246) / (G-247) / (G-248)
+                    mvx[b] = mvx[src]; mvy[b] = mvy[src];
+                }
+            }
+            rq[q] = r;
+        }
+        r00 = rq[0]; r01 = rq[1]; r10 = rq[2]; r11 = rq[3];
+        // (4) vectors of an 8x8 block that differ by at most one quarter sample are merged, utils.c:1916-1979 (EP: list 0 only)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int b0 = ((q >> 1) << 3) | ((q & 1) << 1), b1 = b0 + 1, b2 = b0 + 4, b3 = b0 + 5;
+#define SVC_D(a, c) ((mvx[a] > mvx[c] ? mvx[a] - mvx[c] : mvx[c] - mvx[a]) + (mvy[a] > mvy[c] ? mvy[a] - mvy[c] : mvy[c] - mvy[a]))
+            const bool d01 = SVC_D(b0, b1) <= 1, d02 = SVC_D(b0, b2) <= 1, d03 = SVC_D(b0, b3) <= 1, d23 = SVC_D(b2, b3) <= 1, d13 = SVC_D(b1, b3) <= 1;
+#undef SVC_D
+            if (d01 && d02 && d03) {
+                const int ax = svc_derive_sar(mvx[b0] + mvx[b1] + mvx[b2] + mvx[b3] + 2, 2), ay = svc_derive_sar(mvy[b0] + mvy[b1] + mvy[b2] + mvy[b3] + 2, 2);   // (G-252)
+                mvx[b0] = mvx[b1] = mvx[b2] = mvx[b3] = ax; mvy[b0] = mvy[b1] = mvy[b2] = mvy[b3] = ay;
+            } else if (d01 && d23) {
+                const int ax = svc_derive_sar(mvx[b0] + mvx[b1] + 1, 1), ay = svc_derive_sar(mvy[b0] + mvy[b1] + 1, 1);   // (G-253)
+                const int bx = svc_derive_sar(mvx[b2] + mvx[b3] + 1, 1), by = svc_derive_sar(mvy[b2] + mvy[b3] + 1, 1);   // (G-254)
+                mvx[b0] = mvx[b1] = ax; mvy[b0] = mvy[b1] = ay; mvx[b2] = mvx[b3] = bx; mvy[b2] = mvy[b3] = by;
+            } else if (d02 && d13) {
+                const int ax = svc_derive_sar(mvx[b0] + mvx[b2] + 1, 1), ay = svc_derive_sar(mvy[b0] + mvy[b2] + 1, 1);   // (G-255)
+                const int bx = svc_derive_sar(mvx[b1] + mvx[b3] + 1, 1), by = svc_derive_sar(mvy[b1] + mvy[b3] + 1, 1);   // (G-256)
+                mvx[b0] = mvx[b2] = ax; mvy[b0] = mvy[b2] = ay; mvx[b1] = mvx[b3] = bx; mvy[b1] = mvy[b3] = by;
+            }
+        }
+    } else {
+        // refIdxILPredL0 of an 8x8 block = that of its upper-left 4x4 block (utils.c:1888; nothing is merged in the restricted case)
+        r00 = tref[0]; r01 = tref[2]; r10 = tref[8]; r11 = tref[10];
+    }
     // G.8.6.1.3: partition size from equal reference indices and equal vectors, tested in the reference's order (utils.c:2006-2122)
     bool same_all = true, same_top = true, same_bot = true, same_left = true, same_right = true;
 #pragma unroll
@@ -144,7 +232,8 @@ HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const Sv
         if (p >= nparts) break;
         const int xP = mode == 2 ? p * 8 : (mode == 3 ? (p & 1) * 8 : 0), yP = mode == 1 ? p * 8 : (mode == 3 ? (p >> 1) * 8 : 0);
         const int sm = mode == 3 ? out.sub_mode[p] : 0, nsub = sm == 0 ? 1 : (sm == 3 ? 4 : 2);
-        out.ref_idx[p] = (int8_t)tref[((yP >> 3) << 3) | ((xP >> 3) << 1)];
+        const int qi = ((yP >> 3) << 1) | (xP >> 3);
+        out.ref_idx[p] = (int8_t)(qi == 0 ? r00 : (qi == 1 ? r01 : (qi == 2 ? r10 : r11)));
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             if (s >= nsub) break;
@@ -156,12 +245,13 @@ HLB_HD int svc_derive_mb(const hlb200_svc_base_mb_t* __restrict__ base, const Sv
     return 0;
 }
 
-// is the derived macroblock one the fused prediction + residual kernel is pinned for (host/hlb200_glue.c: `ok`)?
+// is the derived macroblock one the fused prediction + residual kernel is pinned for?  Every partition layout down to 4x4 sub-macroblock partitions (the general case
+// produces them), as long as every partition predicts from RefPicList0[0] (refIdxL0 = 0, which includes predFlagL0 = 1): the layer contexts hold one reference picture.
 HLB_HD bool svc_derive_supported(const hlb200_mb_motion_t& m)
 {
     const int nparts = m.part_mode == 0 ? 1 : (m.part_mode == 3 ? 4 : 2);
     for (int p = 0; p < nparts; ++p)
-        if (m.ref_idx[p] != 0 || (m.part_mode == 3 && m.sub_mode[p] != 0)) return false;
+        if (m.ref_idx[p] != 0) return false;
     return true;
 }
 

@@ -478,14 +478,17 @@ static HL_ERROR_T glue_svc_apply(hl_codec_264_mb_t* p_mb, hl_codec_264_t* p_code
     if (!intra) {
         /* the device coded the macroblock with ITS derivation of the same reference-layer fields: both must agree, or the stream would silently diverge */
         const hlb200_mb_motion_t* m = &L->motion[p_mb->u_addr];
-        static const int N[4] = { 1, 2, 2, 4 }, PW[4] = { 16, 16, 8, 8 }, PH[4] = { 16, 8, 16, 8 };
-        int p, same;
+        static const int N[4] = { 1, 2, 2, 4 }, PW[4] = { 16, 16, 8, 8 }, PH[4] = { 16, 8, 16, 8 }, SN[4] = { 1, 2, 2, 4 }, SW[4] = { 8, 8, 4, 4 }, SH[4] = { 8, 4, 8, 4 };
+        int p, q, same;
         if (m->pad[0] & 1) same = p_mb->predFlagL0[0] == 0 && HL_CODEC_264_MB_TYPE_IS_I_BL(p_mb);
         else {
             same = m->part_mode < 4 && p_mb->NumMbPart == N[m->part_mode] && p_mb->MbPartWidth == PW[m->part_mode] && p_mb->MbPartHeight == PH[m->part_mode];
-            for (p = 0; same && p < N[m->part_mode]; ++p)
-                same = p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == m->ref_idx[p] && p_mb->mvL0[p][0].x == m->mv[p][0][0] && p_mb->mvL0[p][0].y == m->mv[p][0][1] &&
-                       p_mb->partWidth[p][0] == PW[m->part_mode] && p_mb->partHeight[p][0] == PH[m->part_mode];
+            for (p = 0; same && p < N[m->part_mode]; ++p) {
+                const int sm = m->part_mode == 3 ? (m->sub_mode[p] & 3) : 0, ns = m->part_mode == 3 ? SN[sm] : 1;
+                const int w = m->part_mode == 3 ? SW[sm] : PW[m->part_mode], h = m->part_mode == 3 ? SH[sm] : PH[m->part_mode];
+                same = p_mb->predFlagL0[p] == 1 && p_mb->refIdxL0[p] == m->ref_idx[p] && p_mb->NumSubMbPart[p] == ns && p_mb->partWidth[p][0] == w && p_mb->partHeight[p][0] == h;
+                for (q = 0; same && q < ns; ++q) same = p_mb->mvL0[p][q].x == m->mv[p][q][0] && p_mb->mvL0[p][q].y == m->mv[p][q][1];
+            }
         }
         if (!same) {
             HL_DEBUG_ERROR("hlb200: macroblock %u: the motion derived on the device differs from the reference's derivation", p_mb->u_addr);

@@ -625,8 +625,8 @@ HLO_API void hlo_svc_resample_intra_yuv(const uint8_t* ref_yuv, int refW, int re
 /* --- SVC inter-layer motion derivation for an enhancement-layer P macroblock with base_mode_flag = 1 -------------------------------------------
  * What rdo.c:1318-1346 has computed before it predicts: hl_codec_264_utils_derivation_process_initialisation_svc (utils.c:1225) followed by
  * hl_codec_264_utils_derivation_process_for_mv_comps_and_ref_indices_svc (utils.c:1498).  Restated clause by clause with the reference's own intermediate arrays
- * (refLayerPartIdc, tempRefIdxPredL0, mvILPredL0, refIdxILPredL0), for frame macroblocks, EP slices, RestrictedSpatialResolutionChangeFlag = 1 and
- * CroppingChangeFlag = 0 -- the case the reference can be run on here (layers of equal or doubled size).  PINNED by tests/test_svc_derive.py against the
+ * (refLayerPartIdc, tempRefIdxPredL0, mvILPredL0, refIdxILPredL0), for frame macroblocks, EP slices and CroppingChangeFlag = 0: the restricted case (layers of equal
+ * or doubled size) and the general one (run live with layers scaled 3:2, oracle/ref_driver.c --scale).  PINNED by tests/test_svc_derive.py against the
  * reference's trace (oracle/ref_driver.c tags 11 and 6: tests/golden/svc_derive.npz and, in the build container, live runs).
  * base records: 53 int32 per reference-layer macroblock in the order of tag 11 (intra by e_type, flags_type intra, e_type P_8X8 / P_8X8REF0, MbPartWidth, MbPartHeight,
  * SubMbPartWidth[4], SubMbPartHeight[4], predFlagL0[4], refIdxL0[4], mvL0[4][4][2]).
@@ -634,7 +634,7 @@ HLO_API void hlo_svc_resample_intra_yuv(const uint8_t* ref_yuv, int refW, int re
  * partitions that exist); ref_idx4 = refIdxL0[4]; mv32 = mvL0[4][4][2].
  * Returns 0, or -1 when a block maps outside the reference layer / onto an object the reference would divide by zero on / intra and inter blocks mix. */
 static int svc_il_floor_div(int a, int b) { return a / b; }   /* operands are non-negative wherever the reference divides */
-HLO_API int hlo_svc_derive_mb(const int32_t* base, int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int mb_x, int mb_y,
+HLO_API int hlo_svc_derive_mb(const int32_t* base, int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int restricted, int mb_x, int mb_y,
                               int32_t* out16, int32_t* ref_idx4, int32_t* mv32)
 {
     const int ref_mbw = ref_w >> 4, nref = ref_mbw * (ref_h >> 4);
@@ -684,7 +684,40 @@ HLO_API int hlo_svc_derive_mb(const int32_t* base, int ref_w, int ref_h, int sca
         for (i = 0; i < 4; ++i) ref_idx4[i] = -1;
         return 0;
     }
-    if (any_intra) return -1;   /* would need the replacement steps of the unrestricted case (G-210..G-215) */
+    if (any_intra && restricted) return -1;   /* cannot happen with aligned layers of equal or doubled size */
+    if (!restricted) {
+        /* utils.c:1713-1774, transcribed with its two departures from G.8.6.1.1: procI4x4Blk lives across the four 8x8 blocks, and the first 4x4 test reads column xO + 1 with `== -1` */
+        int procI4x4Blk[2][2] = {{0, 0}, {0, 0}}, procI8x8Blk[2][2] = {{0, 0}, {0, 0}};
+        int xP, yP, xS, yS;
+        int (*idc)[4] = refLayerPartIdc;
+        for (yP = 0; yP < 2; ++yP)
+            for (xP = 0; xP < 2; ++xP) {
+                const int xO = xP << 1, yO = yP << 1;
+                for (yS = 0; yS < 2; ++yS)
+                    for (xS = 0; xS < 2; ++xS)
+                        if (idc[yO + yS][xO + xS] == -1) {
+                            procI4x4Blk[yS][xS] = 1;
+                            if (procI4x4Blk[yS][1 - xS] == 0 && idc[yO + yS][xO + 1] == -1) idc[yO + yS][xO + xS] = idc[yO + yS][xO + 1 - xS];
+                            else if (procI4x4Blk[1 - yS][xS] == 0 && idc[yO + 1 - yS][xO + xS] != -1) idc[yO + yS][xO + xS] = idc[yO + 1 - yS][xO + xS];
+                            else if (procI4x4Blk[1 - yS][1 - xS] == 0 && idc[yO + 1 - yS][xO + 1 - xS] != -1) idc[yO + yS][xO + xS] = idc[yO + 1 - yS][xO + 1 - xS];
+                        }
+            }
+        for (yP = 0; yP < 2; ++yP)
+            for (xP = 0; xP < 2; ++xP)
+                if (idc[yP << 1][xP << 1] == -1) {
+                    procI8x8Blk[yP][xP] = 1;
+                    if (procI8x8Blk[yP][1 - xP] == 0 && idc[yP << 1][2 - xP] != -1) {
+                        for (yS = 0; yS < 2; ++yS) for (xS = 0; xS < 2; ++xS) idc[(yP << 1) + yS][(xP << 1) + xS] = idc[(yP << 1) + yS][2 - xP];
+                    }
+                    else if (procI8x8Blk[1 - yP][xP] == 0 && idc[2 - yP][xP << 1] != -1) {
+                        for (yS = 0; yS < 2; ++yS) for (xS = 0; xS < 2; ++xS) idc[(yP << 1) + yS][(xP << 1) + xS] = idc[2 - yP][(xP << 1) + xS];
+                    }
+                    else if (procI8x8Blk[1 - yP][1 - xP] == 0 && idc[2 - yP][2 - xP] != -1) {
+                        for (yS = 0; yS < 2; ++yS) for (xS = 0; xS < 2; ++xS) idc[(yP << 1) + yS][(xP << 1) + xS] = idc[2 - yP][2 - xP];
+                    }
+                }
+        for (y = 0; y < 4; ++y) for (x = 0; x < 4; ++x) if (idc[y][x] == -1) return -1;   /* utils.c:1797 would index the macroblock list with -1 */
+    }
     /* G.8.6.1.2, utils.c:1793-1880 */
     {
         const int mvScaleX = (int)((((long long)scaled_w << 16) + (ref_w >> 1)) / ref_w), mvScaleY = (int)((((long long)scaled_h << 16) + (ref_h >> 1)) / ref_h);   /* (G-232), (G-233) */
@@ -701,6 +734,42 @@ HLO_API int hlo_svc_derive_mb(const int32_t* base, int ref_w, int ref_h, int sca
                 }
             }
         for (y = 0; y < 2; ++y) for (x = 0; x < 2; ++x) refIdxILPredL0[y][x] = tempRefIdxPredL0[y << 1][x << 1];   /* utils.c:1888; the rest is skipped when restricted */
+        if (!restricted) {
+            int yP, xP, yS, xS, k;
+            /* utils.c:1889-1912: the minimum (G-244) is updated INSIDE the walk over the four blocks, each block is compared with the value reached so far */
+            for (yP = 0; yP < 2; ++yP)
+                for (xP = 0; xP < 2; ++xP)
+                    for (yS = 0; yS < 2; ++yS)
+                        for (xS = 0; xS < 2; ++xS) {
+                            const int t = tempRefIdxPredL0[2 * yP + yS][2 * xP + xS];
+                            int* r = &refIdxILPredL0[yP][xP];
+                            *r = (*r >= 0 && t >= 0) ? (*r < t ? *r : t) : (*r > t ? *r : t);   /* HL_MATH_MIN_POSITIVE, hl_math.h:28 */
+                            if (t != *r) {
+                                int sy, sx;
+                                if (tempRefIdxPredL0[2 * yP + yS][2 * xP + 1 - xS] == *r) { sy = 2 * yP + yS; sx = 2 * xP + 1 - xS; }            /* (G-246) */
+                                else if (tempRefIdxPredL0[2 * yP + 1 - yS][2 * xP + xS] == *r) { sy = 2 * yP + 1 - yS; sx = 2 * xP + xS; }       /* (G-247) */
+                                else { sy = 2 * yP + 1 - yS; sx = 2 * xP + 1 - xS; }                                                             /* (G-248) */
+                                for (k = 0; k < 2; ++k) mvILPredL0[2 * yP + yS][2 * xP + xS][k] = mvILPredL0[sy][sx][k];
+                            }
+                        }
+            /* utils.c:1916-1979 (maxX = 0 in EP slices): (G-251)..(G-261) */
+            for (yP = 0; yP < 2; ++yP)
+                for (xP = 0; xP < 2; ++xP) {
+                    const int xO = xP << 1, yO = yP << 1;
+                    int (*a)[2] = &mvILPredL0[yO][xO], (*b)[2] = &mvILPredL0[yO][xO + 1], (*c)[2] = &mvILPredL0[yO + 1][xO], (*d)[2] = &mvILPredL0[yO + 1][xO + 1];
+#define MVD(p, q) (abs((*p)[0] - (*q)[0]) + abs((*p)[1] - (*q)[1]))
+                    if (MVD(a, b) <= 1 && MVD(a, c) <= 1 && MVD(a, d) <= 1) {
+                        for (k = 0; k < 2; ++k) { const int v = ((*a)[k] + (*b)[k] + (*c)[k] + (*d)[k] + 2) >> 2; (*a)[k] = (*b)[k] = (*c)[k] = (*d)[k] = v; }
+                    }
+                    else if (MVD(a, b) <= 1 && MVD(c, d) <= 1) {
+                        for (k = 0; k < 2; ++k) { const int v = ((*a)[k] + (*b)[k] + 1) >> 1, w = ((*c)[k] + (*d)[k] + 1) >> 1; (*a)[k] = (*b)[k] = v; (*c)[k] = (*d)[k] = w; }
+                    }
+                    else if (MVD(a, c) <= 1 && MVD(b, d) <= 1) {
+                        for (k = 0; k < 2; ++k) { const int v = ((*a)[k] + (*c)[k] + 1) >> 1, w = ((*b)[k] + (*d)[k] + 1) >> 1; (*a)[k] = (*c)[k] = v; (*b)[k] = (*d)[k] = w; }
+                    }
+#undef MVD
+                }
+        }
     }
     /* G.8.6.1.3, utils.c:2006-2122 (EP: one list) */
     {
@@ -757,10 +826,10 @@ HLO_API int hlo_svc_derive_mb(const int32_t* base, int ref_w, int ref_h, int sca
     return 0;
 }
 /* whole picture: out = nmb x (16 + 4 + 32) int32 {out16, refIdxL0[4], mvL0[4][4][2]}; bad[] receives 1 where hlo_svc_derive_mb failed */
-HLO_API void hlo_svc_derive_picture(const int32_t* base, int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int width, int height,
+HLO_API void hlo_svc_derive_picture(const int32_t* base, int ref_w, int ref_h, int scaled_w, int scaled_h, int off_x, int off_y, int level_idc, int restricted, int width, int height,
                                     int32_t* out, uint8_t* bad)
 {
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
     int a;
-    for (a = 0; a < nmb; ++a) bad[a] = hlo_svc_derive_mb(base, ref_w, ref_h, scaled_w, scaled_h, off_x, off_y, level_idc, a % mbw, a / mbw, out + 52 * a, out + 52 * a + 16, out + 52 * a + 20) != 0;
+    for (a = 0; a < nmb; ++a) bad[a] = hlo_svc_derive_mb(base, ref_w, ref_h, scaled_w, scaled_h, off_x, off_y, level_idc, restricted, a % mbw, a / mbw, out + 52 * a, out + 52 * a + 16, out + 52 * a + 20) != 0;
 }

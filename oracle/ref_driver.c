@@ -515,6 +515,10 @@ static void md5_hex(const uint8_t* p, size_t n, char out[33])
     out[32] = 0;
 }
 
+/* size of spatial layer l: doubled per layer as source/test_encoder.c:150-202 does, or scaled by --scale n d per layer */
+static int g_scale_n = 2, g_scale_d = 1;
+static int layer_dim(int base, int l) { int v = base, k; for (k = 0; k < l; ++k) v = v * g_scale_n / g_scale_d; return v; }
+
 int main(int argc, char** argv)
 {
     int w = 352, h = 288, frames = 3, qp = 31, me_range = 16, refs = 1, gen = 1, gop = 400, early = 0, deblock = 0, defaults = 0, layers = 1, l, i;
@@ -537,6 +541,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--refs") && i + 1 < argc) refs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gop") && i + 1 < argc) gop = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--layers") && i + 1 < argc) layers = atoi(argv[++i]);   /* SVC spatial layers: layer l is (w << l) x (h << l), source/test_encoder.c:150-202 */
+        else if (!strcmp(argv[i], "--scale") && i + 2 < argc) { g_scale_n = atoi(argv[++i]); g_scale_d = atoi(argv[++i]); }   /* layer l is (w, h) * (n / d)^l instead of doubled: 3 2 = extended spatial scalability */
         else if (!strcmp(argv[i], "--early-term") && i + 1 < argc) early = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--deblock") && i + 1 < argc) deblock = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--defaults")) defaults = 1;   /* keep what hl_codec_create sets for deblock_flag / me_early_term_flag (both 1, hl_types.h:67,69) */
@@ -555,7 +560,9 @@ int main(int argc, char** argv)
     if ((w & 15) || (h & 15)) { fprintf(stderr, "W and H must be multiples of 16 (hl_codec_264.c:428-439)\n"); return 2; }
     g_width = w; g_height = h;
     if (layers < 1 || layers > 3) layers = 1;
-    frame_bytes = (size_t)(w << (layers - 1)) * (h << (layers - 1)) * 3 / 2;   /* largest layer */
+    if (g_scale_n < g_scale_d || g_scale_d < 1) { fprintf(stderr, "--scale n d needs n >= d >= 1\n"); return 2; }
+    for (l = 0; l < layers; ++l) if ((layer_dim(w, l) & 15) || (layer_dim(h, l) & 15)) { fprintf(stderr, "layer %d is %d x %d: not whole macroblocks\n", l, layer_dim(w, l), layer_dim(h, l)); return 2; }
+    frame_bytes = (size_t)layer_dim(w, layers - 1) * layer_dim(h, layers - 1) * 3 / 2;   /* largest layer */
     yuv = (uint8_t*)malloc(frame_bytes);
     stream_cap = frame_bytes * (size_t)(frames + 1) + 65536; stream = (uint8_t*)malloc(stream_cap);
     if (in_path && !(fin = fopen(in_path, "rb"))) { perror(in_path); return 2; }
@@ -592,11 +599,11 @@ int main(int argc, char** argv)
 
     if (layers > 1)
         for (l = 0; l < layers; ++l)
-            if ((err = hl_codec_add_layer(codec, (uint32_t)(w << l), (uint32_t)(h << l), 0, 0))) { fprintf(stderr, "add_layer %d failed: %d\n", l, err); return 1; }
+            if ((err = hl_codec_add_layer(codec, (uint32_t)layer_dim(w, l), (uint32_t)layer_dim(h, l), 0, 0))) { fprintf(stderr, "add_layer %d failed: %d\n", l, err); return 1; }
     for (i = 0; i < frames; ++i) {
         for (l = 0; l < layers; ++l) {   /* one hl_codec_encode per layer per access unit (test_encoder.c:174-202) */
             double t0, t1;
-            const int lw = w << l, lh = h << l;
+            const int lw = layer_dim(w, l), lh = layer_dim(h, l);
             const size_t lbytes = (size_t)lw * lh * 3 / 2;
             if (fin) { if (fread(yuv, 1, lbytes, fin) != lbytes) goto done; }
             else if (gen == 1) gen_g1(yuv, lw, lh, i);

@@ -19,6 +19,11 @@ CONFIGS = {
     # inter commit (host/hlb200_glue.c: glue_apply); both differed through the whole glue before that was reproduced
     "g2_i4_in_p_2layer": ["--size", "64", "64", "--layers", "2", "--frames", "4", "--gen", "g2", "--seed", "8931", "--qp", "29"],
     "g2_3layer_48_q34": ["--size", "48", "48", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "22", "--qp", "34"],   # smallest layers the drop-in accepts (36 macroblocks at the dyadic ratio)
+    # extended spatial scalability: every layer 1.5 times the one below (ref_driver --scale 3 2) -- the general case of the inter-layer derivation, enhancement
+    # macroblocks with sub-macroblock partitions, non-dyadic Intra_Base resampling
+    "g2_ess_3layer": ["--size", "128", "192", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "6302", "--qp", "35", "--scale", "3", "2"],
+    "g1_ess_3layer": ["--size", "256", "128", "--layers", "3", "--frames", "4", "--gen", "g1", "--seed", "6426", "--qp", "25", "--scale", "3", "2"],
+    "g2_ess_2layer": ["--size", "128", "64", "--layers", "2", "--frames", "2", "--gen", "g2", "--seed", "6675", "--qp", "23", "--scale", "3", "2"],
 }
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "svc_bitstream.json")
 

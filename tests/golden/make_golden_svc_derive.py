@@ -14,6 +14,8 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "svc_derive.npz")
 CONFIGS = S.CONFIGS + [
     ("g2_3layer_64", ["--size", "64", "64", "--layers", "3", "--frames", "5", "--gen", "g2", "--seed", "998", "--qp", "38"]),     # first P picture refused (no prediction source)
     ("g1_2layer_112", ["--size", "112", "32", "--layers", "2", "--frames", "3", "--gen", "g1", "--seed", "1899", "--qp", "46"]),
+    ("g2_ess_3to2", ["--size", "128", "64", "--layers", "2", "--frames", "4", "--gen", "g2", "--seed", "11", "--qp", "30", "--scale", "3", "2"]),   # general case: layers scaled 3:2
+    ("g1_ess_3layer", ["--size", "64", "128", "--layers", "3", "--frames", "3", "--gen", "g1", "--seed", "5", "--qp", "26", "--scale", "3", "2"]),
     ("g1_3layer_80", ["--size", "80", "64", "--layers", "3", "--frames", "3", "--gen", "g1", "--seed", "5", "--qp", "31"]),
 ]
 KEYS = ("geom", "base", "kind", "part_mode", "sub_mode", "ref_idx", "mv", "nparts", "nsub", "stale_parts", "motion", "valid")

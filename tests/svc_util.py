@@ -62,7 +62,13 @@ def pictures_from_trace(path):
         mode = {(1, 16, 16): 0, (2, 16, 8): 1, (2, 8, 16): 2, (4, 8, 8): 3}.get((nparts, pw, ph), -1)
         # macroblocks the reference predicts from real motion; the others (base macroblock intra: no partition, predFlagL0 = 0) are coded by the
         # reference against the prediction of an earlier macroblock: mark_inherited() below
-        ok = mode >= 0 and all(int(nsub[i]) >= 1 and int(pflag[i]) == 1 and int(ridx[i]) == 0 and int(pwh[i, 0]) == pw and int(pwh[i, 1]) == ph for i in range(nparts))
+        sw, sh = r[15:19], r[19:23]
+        SUB = {(8, 8): (0, 1), (8, 4): (1, 2), (4, 8): (2, 2), (4, 4): (3, 4)}   # (SubMbPartWidth, SubMbPartHeight) -> (sub_mode, NumSubMbPart)
+        ok = mode >= 0 and all(int(nsub[i]) >= 1 and int(pflag[i]) == 1 and int(ridx[i]) == 0 for i in range(nparts))
+        if ok and mode == 3:    # P_8x8: sub-macroblock partitions of every shape (the general, non-dyadic case produces them); partWidth/Height[i][0] = the sub-partition's
+            ok = all(SUB.get((int(sw[i]), int(sh[i])), (0, -1))[1] == int(nsub[i]) and int(pwh[i, 0]) == int(sw[i]) and int(pwh[i, 1]) == int(sh[i]) for i in range(4))
+        elif ok:
+            ok = all(int(pwh[i, 0]) == pw and int(pwh[i, 1]) == ph for i in range(nparts))
         ok = ok and e_type in (301, 302, 303, 304)
         p["valid"][a] = 1 if ok else 0
         p["kind"] = 0
@@ -70,7 +76,10 @@ def pictures_from_trace(path):
             m = p["motion"][a]
             m["part_mode"] = mode
             for i in range(nparts):
-                m["mv"][i, 0] = mv[i, 0]
+                ns = int(nsub[i]) if mode == 3 else 1
+                if mode == 3:
+                    m["sub_mode"][i] = SUB[(int(sw[i]), int(sh[i]))][0]
+                m["mv"][i, :ns] = mv[i, :ns]
         p["seen"] += 1
     stale = {(int(r[2]), int(r[3]), int(r[4])): r[5:5 + 384].copy() for r in t.get(10, [])}
     out = []
@@ -271,6 +280,7 @@ def compare_derived(d, motion, status, what=""):
     """motion (MB_MOTION per macroblock) / status bits of an implementation of the derivation against the reference's picture `d`.  Every inter macroblock: partition layout,
     refIdxL0 and mvL0 of every (sub-)partition; every macroblock the glue codes (valid): the inherited-prediction marker; the status bits = the reasons the glue refuses"""
     n = 0
+    inter_ok = (d["kind"] == 0) & np.array([all(int(d["ref_idx"][a, p]) == 0 for p in range(int(d["nparts"][a]))) for a in range(len(d["kind"]))])
     for a in range(len(d["kind"])):
         m = motion[a]
         tag = "%s frame %d dqid %d macroblock %d" % (what, d["frame"], d["dqid"], a)
@@ -283,14 +293,15 @@ def compare_derived(d, motion, status, what=""):
                 ns = int(d["nsub"][a, p])
                 assert np.array_equal(m["mv"][p, :ns], d["mv"][a, p, :ns]), tag + ": mvL0[%d] %s, reference %s" % (p, m["mv"][p, :ns].tolist(), d["mv"][a, p, :ns].tolist())
             assert not (int(m["pad"][0]) & 1), tag
-        if d["valid"][a]:
+        # the glue's view (pictures_from_trace / mark_inherited) is only defined for macroblocks it would code: inter ones inside its pinned set and intra-base ones;
+        # an inter macroblock outside the set (sub-macroblock partitions in the general case) makes the glue refuse the picture
+        if d["valid"][a] and (d["kind"][a] == 1 or inter_ok[a]) and not ((d["kind"] == 0) & ~inter_ok)[:a].any():
             g = d["motion"][a]
             assert np.array_equal(m["pad"], g["pad"]), tag + ": inherited-prediction marker %s, glue %s" % (m["pad"].tolist(), g["pad"].tolist())
             if not (int(g["pad"][0]) & 1):
-                assert int(m["part_mode"]) == int(g["part_mode"]) and all(np.array_equal(m["mv"][p, 0], g["mv"][p, 0]) for p in range(4 if g["part_mode"] == 3 else (1 if g["part_mode"] == 0 else 2))), tag
+                assert int(m["part_mode"]) == int(g["part_mode"]) and np.array_equal(m["sub_mode"], g["sub_mode"]) and np.array_equal(m["mv"], g["mv"]), tag
         n += 1
     expect = 0
-    inter_ok = (d["kind"] == 0) & np.array([all(int(d["ref_idx"][a, p]) == 0 and int(d["sub_mode"][a, p]) == 0 for p in range(int(d["nparts"][a]))) for a in range(len(d["kind"]))])
     if ((d["kind"] == 0) & ~inter_ok).any():
         expect |= DERIVE_UNSUPPORTED
     if ((d["kind"] == 1) & (d["stale_parts"] != 0)).any():
@@ -341,7 +352,7 @@ def oracle_derive(olib, base, geom, w, h):
     bw = np.ascontiguousarray(base_words(base))
     out, bad = np.zeros((nmb, 52), np.int32), np.zeros(nmb, np.uint8)
     olib.hlo_svc_derive_picture(bw.ctypes.data_as(C.c_void_p), int(g["ref_width"]), int(g["ref_height"]), int(g["scaled_width"]), int(g["scaled_height"]), int(g["left_offset"]),
-                                int(g["top_offset"]), int(g["level_idc"]), w, h, out.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p))
+                                int(g["top_offset"]), int(g["level_idc"]), int(g["restricted"]), w, h, out.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p))
     return out, bad
 
 
@@ -369,7 +380,7 @@ def motion_from_oracle(out, bad, had_parts):
             if mode == 3:
                 m[a]["sub_mode"][p] = {(8, 8): 0, (8, 4): 1, (4, 8): 2, (4, 4): 3}[(int(o[8 + p]), int(o[12 + p]))]
             m[a]["mv"][p, :ns] = o[20:52].reshape(4, 4, 2)[p, :ns]
-            sup = sup and int(o[16 + p]) == 0 and m[a]["sub_mode"][p] == 0
+            sup = sup and int(o[16 + p]) == 0
         had_parts[a] = 1
         if not sup:
             status |= DERIVE_UNSUPPORTED; kind[a] = 2

@@ -28,7 +28,7 @@ VP = C.c_void_p
 def _oracle():
     o = load_oracle()
     o.hlo_svc_derive_picture.restype = None
-    o.hlo_svc_derive_picture.argtypes = [VP] + [C.c_int] * 9 + [VP, VP]
+    o.hlo_svc_derive_picture.argtypes = [VP] + [C.c_int] * 10 + [VP, VP]
     return o
 
 
@@ -80,19 +80,23 @@ def _check_pictures(pics, derive, what):
 
 
 def make_geom(ref_w, ref_h, w, h, level_idc=10):
+    """RestrictedSpatialResolutionChangeFlag as layer.c:143 sets it for layers without offsets: equal or doubled size in each direction"""
     g = np.zeros(1, S.SVC_GEOM)
-    g["ref_width"], g["ref_height"], g["scaled_width"], g["scaled_height"], g["level_idc"], g["restricted"] = ref_w, ref_h, w, h, level_idc, 1
+    g["ref_width"], g["ref_height"], g["scaled_width"], g["scaled_height"], g["level_idc"] = ref_w, ref_h, w, h, level_idc
+    g["restricted"] = int(w in (ref_w, 2 * ref_w) and h in (ref_h, 2 * ref_h))
     return g
 
 
 # ------------------------------------------------------------------ CPU tier ------------------------------------------------------------------
 def test_golden_fixture_shape():
     pics = S.load_derive_golden()
-    assert len(pics) == 23
+    assert len(pics) == 30
     assert {p["dqid"] for p in pics} == {16, 32}                                  # first and second enhancement layer
     assert sum(int((p["kind"] == 1).sum()) for p in pics) >= 30                   # macroblocks whose base macroblock is intra
     assert {int(v) for p in pics for v in np.unique(p["part_mode"][p["kind"] == 0])} == {0, 1, 2, 3}
-    assert all(int(p["geom"]["restricted"][0]) == 1 and int(p["geom"]["cropping_change"][0]) == 0 for p in pics)
+    assert all(int(p["geom"]["cropping_change"][0]) == 0 for p in pics)
+    assert sum(int(p["geom"]["restricted"][0]) == 0 for p in pics) == 7           # layers scaled 3:2: the general case with its replacement / merging steps
+    assert any(int(p["sub_mode"].max()) > 0 for p in pics if int(p["geom"]["restricted"][0]) == 0)
 
 
 def test_oracle_vs_golden():
@@ -119,7 +123,8 @@ def test_live_reference(tmp_path):
         assert _check_pictures(pics, emu_derive, "device source on the CPU")[0] > 0
 
 
-@pytest.mark.parametrize("ref_size,size,level_idc", [((64, 48), (128, 96), 10), ((64, 48), (64, 48), 10), ((80, 32), (160, 32), 10), ((48, 80), (48, 160), 31), ((176, 144), (352, 288), 40)])
+@pytest.mark.parametrize("ref_size,size,level_idc", [((64, 48), (128, 96), 10), ((64, 48), (64, 48), 10), ((80, 32), (160, 32), 10), ((48, 80), (48, 160), 31), ((176, 144), (352, 288), 40),
+                                                     ((64, 64), (96, 96), 10), ((160, 96), (240, 144), 40), ((96, 64), (128, 80), 10), ((64, 32), (96, 64), 10)])
 def test_device_source_vs_oracle_random(ref_size, size, level_idc):
     """random reference-layer fields: the two restatements agree macroblock by macroblock, over three pictures of a layer (carried 'object holds partitions' flags)"""
     o = _oracle()
@@ -136,16 +141,16 @@ def test_device_source_vs_oracle_random(ref_size, size, level_idc):
         assert np.array_equal(mo.view(np.uint8), me.view(np.uint8)), np.nonzero((mo.view(np.uint8).reshape(len(mo), -1) != me.view(np.uint8).reshape(len(me), -1)).any(axis=1))[0][:8]
         assert np.array_equal(had_o, had_e & 1)
         seen |= {int(v) for v in np.unique(mo["part_mode"])} | {10 + int(v) for v in np.unique(mo["sub_mode"])}
-    if size == ref_size:
-        assert {0, 1, 2, 3, 11, 12} <= seen      # equal size: sub-macroblock partitions survive
+    if size == ref_size or not int(g["restricted"][0]):
+        assert {0, 3} <= seen and seen & {11, 12, 13}      # equal size / general case: sub-macroblock partitions appear
     else:
         assert {0, 3} <= seen
 
 
 def test_refusals():
-    """geometry outside the restricted case is refused, not approximated"""
+    """geometry the derivation is not pinned for is refused, not approximated"""
     base = S.random_base_field(np.random.default_rng(1), 64, 48)
-    for field, value in (("restricted", 0), ("cropping_change", 1)):
+    for field, value in (("cropping_change", 1),):
         g = make_geom(64, 48, 128, 96)
         g[field] = value
         mot, st = np.zeros(48, S.MB_MOTION), C.c_int32(0)
@@ -187,7 +192,7 @@ def test_gpu_vs_golden():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ref_size,size", [((960, 544), (1920, 1088)), ((1920, 1088), (1920, 1088)), ((176, 144), (352, 288))])
+@pytest.mark.parametrize("ref_size,size", [((960, 544), (1920, 1088)), ((1920, 1088), (1920, 1088)), ((176, 144), (352, 288)), ((1280, 704), (1920, 1056))])
 def test_gpu_vs_oracle_random_batch(ref_size, size):
     """full-size random fields, eight pictures in one launch, two launches (the carried flags of picture k feed picture k of the next launch)"""
     import torch

@@ -38,6 +38,11 @@ for case in range(first, first + n_cases):
     w, h = int(rng.integers(1, 9 if layers == 2 else 6)) * 16, int(rng.integers(1, 8 if layers == 2 else 5)) * 16
     frames, qp, gen, seed = int(rng.integers(2, 6)), int(rng.integers(16, 52)), str(rng.choice(["g1", "g2"])), int(rng.integers(1, 10000))
     args = ["--size", str(w), str(h), "--layers", str(layers), "--frames", str(frames), "--gen", gen, "--seed", str(seed), "--qp", str(qp)]
+    if os.environ.get("FUZZ_SCALE"):   # e.g. "3 2": every layer 1.5 times the one below (extended spatial scalability: the general case of the derivation)
+        n, d = (int(v) for v in os.environ["FUZZ_SCALE"].split())
+        unit = 16 * d ** (layers - 1)
+        w, h = int(rng.integers(1, 5)) * unit, int(rng.integers(1, 4)) * unit
+        args = ["--size", str(w), str(h), "--layers", str(layers), "--frames", str(frames), "--gen", gen, "--seed", str(seed), "--qp", str(qp), "--scale", str(n), str(d)]
     tr = "/tmp/fuzz_derive_%d.trace" % case
     try:
         subprocess.run([rt.DRIVER] + args + ["--trace", tr, "--no-levels"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)

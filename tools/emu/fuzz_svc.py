@@ -36,6 +36,11 @@ for case in range(first, first + n_cases):
     gen = str(rng.choice(["g1", "g2"]))
     seed = int(rng.integers(1, 10000))
     args = ["--size", str(w), str(h), "--layers", str(layers), "--frames", str(frames), "--gen", gen, "--seed", str(seed), "--qp", str(qp)]
+    if os.environ.get("FUZZ_SCALE"):   # e.g. "3 2": every layer 1.5 times the one below (extended spatial scalability: sub-macroblock partitions, the general derivation case)
+        sn, sd = (int(v) for v in os.environ["FUZZ_SCALE"].split())
+        unit = 16 * sd ** (layers - 1)
+        w, h = int(rng.integers(1, 5)) * unit, int(rng.integers(1, 4)) * unit
+        args = ["--size", str(w), str(h), "--layers", str(layers), "--frames", str(frames), "--gen", gen, "--seed", str(seed), "--qp", str(qp), "--scale", str(sn), str(sd)]
     tr = "/tmp/fuzz_svc_%d.trace" % case
     try:
         out = subprocess.run([rt.DRIVER] + args + ["--trace", tr], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)

@@ -58,9 +58,9 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_derive_motion(cons
                                                                             uint8_t* had_parts, hlb200_mb_motion_t* motion, int32_t* status)
 {
     if (!base || !geom || !had_parts || !motion || !status || width < 16 || height < 16 || (width & 15) || (height & 15)) return HLB200_ERR_INVALID_PARAMETER;
-    if (!geom->restricted || geom->cropping_change) return HLB200_ERR_NOT_IMPLEMENTED;
+    if (geom->cropping_change) return HLB200_ERR_NOT_IMPLEMENTED;
     hlb::SvcDeriveGeom g;
-    if (!hlb::svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, g)) return HLB200_ERR_NOT_IMPLEMENTED;
+    if (!hlb::svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, geom->restricted, g)) return HLB200_ERR_NOT_IMPLEMENTED;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
     int st = 0;
     for (int mb = 0; mb < nmb; ++mb) st |= hlb::svc_derive_pass1(base, g, mb, mbw, had_parts, motion);
