@@ -758,7 +758,7 @@ int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const
     SvcDeriveGeom g;
     if (geom->cropping_change ||
         !svc_derive_geom(geom->ref_width, geom->ref_height, geom->scaled_width, geom->scaled_height, geom->left_offset, geom->top_offset, geom->level_idc, geom->restricted, g)) {
-        snprintf(g_err, sizeof(g_err), "hlb200: inter-layer motion derivation outside the restricted spatial-resolution-change case (or an overflowing precision) is not implemented");
+        snprintf(g_err, sizeof(g_err), "hlb200: inter-layer motion derivation with CroppingChangeFlag = 1 (or a fixed-point precision the reference itself overflows) is not implemented");
         return HLB200_ERR_NOT_IMPLEMENTED;
     }
     const int mbw = width >> 4, nmb = mbw * (height >> 4);

@@ -172,7 +172,7 @@ typedef struct hlb200_svc_layer_geom {
     int32_t scaled_width, scaled_height;   /* ScaledRefLayerPicWidthInSamplesL / ScaledRefLayerPicHeightInSamplesL */
     int32_t left_offset, top_offset;       /* ScaledRefLayerLeftOffset / ScaledRefLayerTopOffset */
     int32_t level_idc;                     /* of the SPS utils.c:989 reads */
-    int32_t restricted;                    /* RestrictedSpatialResolutionChangeFlag (layer.c:143); 0 is refused */
+    int32_t restricted;                    /* RestrictedSpatialResolutionChangeFlag (layer.c:143); 0 = the general case with its replacement / merging steps */
     int32_t cropping_change;               /* CroppingChangeFlag (layer.c:104); 1 is refused */
 } hlb200_svc_layer_geom_t;
 
@@ -308,8 +308,8 @@ HLB200_API int hlb200_dev_svc_inter_recon_batch(const uint8_t* d_src_y, const ui
  * macroblocks (partition layout, refIdxL0, mvL0; macroblocks whose base macroblock is intra carry the address of the macroblock whose prediction they inherit in pad[],
  * as hlb200_dev_svc_inter_recon_batch reads it), d_had_parts = one byte per derived macroblock carried from picture to picture of a layer (zero for a new layer; bit 0 = the reference's
  * macroblock object holds partitions of an earlier picture, bits 1-2 = scratch of the last call),
- * d_status = one int32 per picture, HLB200_SVC_DERIVE_* bits OR-ed in (the caller zeroes it).  Frame macroblocks, RestrictedSpatialResolutionChangeFlag = 1,
- * CroppingChangeFlag = 0; anything else returns HLB200_ERR_NOT_IMPLEMENTED. */
+ * d_status = one int32 per picture, HLB200_SVC_DERIVE_* bits OR-ed in (the caller zeroes it).  Frame macroblocks, EP slices, CroppingChangeFlag = 0 (1 returns
+ * HLB200_ERR_NOT_IMPLEMENTED); RestrictedSpatialResolutionChangeFlag 1 and 0. */
 HLB200_API int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const hlb200_svc_layer_geom_t* geom, int width, int height, int n_pics,
                                                   uint8_t* d_had_parts, hlb200_mb_motion_t* d_motion, int32_t* d_status, void* cuda_stream);
 /* I_BL macroblocks (enhancement-layer I pictures) -- hl_codec_264_rdo_mb_guess_best_intra_pred_svc, rdo.c:301-461: the prediction is the base-layer reconstruction
