@@ -47,8 +47,13 @@ __global__ void __launch_bounds__(256, HLB_IL_MINB) k_interp_luma(const uint8_t*
     const int bw = W >> 2, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bw * (H >> 2)) return;
     ref += blockIdx.y * stride; pred += blockIdx.y * stride; motion += (size_t)blockIdx.y * nmb;
+#ifdef HLB_IL_RASTER   // blocks in picture raster order: a warp = one row of 32 blocks = a strip of 8 macroblocks (whole sectors per store, but up to 8 x 4 partitions per warp)
     const int gy4 = t / bw, gx = (t - gy4 * bw) << 2, gy = gy4 << 2;
     const int mbx = gx >> 4, mby = gy >> 4, bx = gx & 15, by = gy & 15;
+#else                  // blocks in macroblock order (luma4x4BlkIdx inside): a warp = two macroblocks, so it meets the fractional classes of two macroblocks' partitions only
+    const int mb = t >> 4, b4 = t & 15, mbx = mb % mbw, mby = mb / mbw, bx = blk_x(b4), by = blk_y(b4);
+    const int gx = mbx * 16 + bx, gy = mby * 16 + by;
+#endif
     const hlb200_mb_motion_t* m = motion + mby * mbw + mbx;
     const PartGeom g = part_of(m->part_mode, m->sub_mode, bx, by);
     const int mvx = m->mv[g.part][g.sub][0], mvy = m->mv[g.part][g.sub][1];
