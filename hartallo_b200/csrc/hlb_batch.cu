@@ -779,24 +779,34 @@ int hlb200_dev_svc_derive_motion_batch(const hlb200_svc_base_mb_t* d_base, const
 #ifndef HLB_RS_MINB
 #define HLB_RS_MINB 6   // 40 registers: +1.3 %
 #endif
-__global__ void __launch_bounds__(256, HLB_RS_MINB) k_svc_resample_intra(const uint8_t* __restrict__ ref_y, const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int refW,
-                                                            int refH, uint8_t* __restrict__ out_y, uint8_t* __restrict__ out_u, uint8_t* __restrict__ out_v, int W, int H,
-                                                            size_t ref_frame_stride, size_t frame_stride, int level_idc)
+// One launch per kind of plane (CHROMA = false: the luma planes of all pictures, true: their Cb and Cr planes): block = 64 x 4 threads = 256 x 4 output samples,
+// blockIdx.x / .y walk the plane, blockIdx.z = picture (luma) or picture * 2 + plane (chroma) -- no index division anywhere, no empty chroma blocks.
+extern "C++" {
+template <bool CHROMA>
+__global__ void __launch_bounds__(256, HLB_RS_MINB) k_svc_resample_intra(const uint8_t* __restrict__ ref_a, const uint8_t* __restrict__ ref_b, int rw, int rh, uint8_t* __restrict__ out_a,
+                                                                         uint8_t* __restrict__ out_b, int w, int h, size_t ref_frame_stride, size_t frame_stride, SvcRsAxis ax, SvcRsAxis ay)
 {
-    const int plane = blockIdx.z, chroma = plane != 0;
-    const int w = W >> chroma, h = H >> chroma, rw = refW >> chroma, rh = refH >> chroma, wq = w >> 2;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= wq * h) return;
-    const int y = t / wq, x0 = (t - y * wq) * 4;
-    const uint8_t* ref = (plane == 0 ? ref_y : (plane == 1 ? ref_u : ref_v)) + (size_t)blockIdx.y * ref_frame_stride;
-    uint8_t* out = (plane == 0 ? out_y : (plane == 1 ? out_u : out_v)) + (size_t)blockIdx.y * frame_stride;
-    const SvcRsAxis ax = svc_rs_axis(rw, w, level_idc), ay = svc_rs_axis(rh, h, level_idc);
-    uint32_t word = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) word |= (uint32_t)svc_resample_px(ref, rw, rh, ax, ay, x0 + i, y, chroma != 0) << (8 * i);
-    *reinterpret_cast<uint32_t*>(out + (size_t)y * w + x0) = word;
+    const int x0 = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y;
+    if (x0 >= w || y >= h) return;
+    const int pic = CHROMA ? blockIdx.z >> 1 : blockIdx.z, second = CHROMA ? (blockIdx.z & 1) : 0;
+    const uint8_t* ref = (second ? ref_b : ref_a) + (size_t)pic * ref_frame_stride;
+    uint8_t* out = (second ? out_b : out_a) + (size_t)pic * frame_stride;
+    *reinterpret_cast<uint32_t*>(out + (size_t)y * w + x0) = svc_resample_row4(ref, rw, rh, ax, ay, x0, y, CHROMA);
 }
+}   // extern "C++"
 
+// host twin of svc_rs_axis (hlb_svc.cuh; the device functions are not callable from host code)
+static SvcRsAxis host_rs_axis(int refDim, int scaledDim, int level_idc)
+{
+    SvcRsAxis a;
+    int lg = 0;
+    while ((1 << lg) < refDim) ++lg;
+    const int shift = level_idc <= 30 ? 16 : 31 - lg;
+    a.scale = ((refDim << shift) + (scaledDim >> 1)) / scaledDim;
+    a.add = (((refDim * 2) << (shift - 2)) + (scaledDim >> 1)) / scaledDim + (1 << (shift - 5));
+    a.shift4 = shift - 4;
+    return a;
+}
 static bool rs_ok(int dim, int level_idc) { return level_idc <= 30 || (dim & (dim - 1)) != 0; }   // host twin of svc_rs_precision_ok
 int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d_ref_u, const uint8_t* d_ref_v, int ref_width, int ref_height, uint8_t* d_pred_y,
                                         uint8_t* d_pred_u, uint8_t* d_pred_v, int width, int height, int n_pics, size_t ref_frame_stride, size_t frame_stride, int level_idc,
@@ -806,11 +816,21 @@ int hlb200_dev_svc_resample_intra_batch(const uint8_t* d_ref_y, const uint8_t* d
     // reference's int32 `refDim << shift` overflows: no reference behaviour there, refused
     if (!d_ref_y || !d_ref_u || !d_ref_v || !d_pred_y || !d_pred_u || !d_pred_v || ref_width < 16 || ref_height < 16 || (ref_width & 15) || (ref_height & 15) || width < ref_width ||
         height < ref_height || (width & 15) || (height & 15) || width > 8 * ref_width || height > 8 * ref_height || width > 8192 || height > 8192 || n_pics < 1 || n_pics > 65535 ||
-        level_idc < 0 || !rs_ok(ref_width, level_idc) || !rs_ok(ref_height, level_idc) || !rs_ok(ref_width >> 1, level_idc) || !rs_ok(ref_height >> 1, level_idc) || (frame_stride & 3) || (((uintptr_t)d_pred_y | (uintptr_t)d_pred_u | (uintptr_t)d_pred_v) & 3))
+        (ref_frame_stride & 3) || (((uintptr_t)d_ref_y | (uintptr_t)d_ref_u | (uintptr_t)d_ref_v) & 3) || level_idc < 0 || !rs_ok(ref_width, level_idc) || !rs_ok(ref_height, level_idc) || !rs_ok(ref_width >> 1, level_idc) || !rs_ok(ref_height >> 1, level_idc) || (frame_stride & 3) || (((uintptr_t)d_pred_y | (uintptr_t)d_pred_u | (uintptr_t)d_pred_v) & 3))
         return HLB200_ERR_INVALID_PARAMETER;
-    const int words = (width >> 2) * height;
-    k_svc_resample_intra<<<dim3((words + 255) / 256, n_pics, 3), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, d_ref_u, d_ref_v, ref_width, ref_height, d_pred_y, d_pred_u, d_pred_v,
-                                                                                                      width, height, ref_frame_stride, frame_stride, level_idc);
+    // per-launch constants ((G-43)..(G-48) hold two integer divisions per axis): computed once on the host
+    const SvcRsAxis lx = host_rs_axis(ref_width, width, level_idc), ly = host_rs_axis(ref_height, height, level_idc);
+    const SvcRsAxis cx = host_rs_axis(ref_width >> 1, width >> 1, level_idc), cy = host_rs_axis(ref_height >> 1, height >> 1, level_idc);
+    const dim3 blk(64, 4);
+    for (int p0 = 0; p0 < n_pics; p0 += 32767) {   // gridDim.z <= 65535
+        const int np = n_pics - p0 < 32767 ? n_pics - p0 : 32767;
+        const size_t ro = (size_t)p0 * ref_frame_stride, oo = (size_t)p0 * frame_stride;
+        k_svc_resample_intra<false><<<dim3((width / 4 + 63) / 64, (height + 3) / 4, np), blk, 0, (cudaStream_t)cuda_stream>>>(d_ref_y + ro, d_ref_y + ro, ref_width, ref_height, d_pred_y + oo,
+                                                                                                                        d_pred_y + oo, width, height, ref_frame_stride, frame_stride, lx, ly);
+        k_svc_resample_intra<true><<<dim3((width / 8 + 63) / 64, (height / 2 + 3) / 4, 2 * np), blk, 0, (cudaStream_t)cuda_stream>>>(d_ref_u + ro, d_ref_v + ro, ref_width >> 1, ref_height >> 1,
+                                                                                                                               d_pred_u + oo, d_pred_v + oo, width >> 1, height >> 1,
+                                                                                                                               ref_frame_stride, frame_stride, cx, cy);
+    }
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }

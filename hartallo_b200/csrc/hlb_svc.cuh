@@ -18,6 +18,7 @@
 #pragma once
 #include "../../include/hlb200.h"
 #include "hlb_prims.cuh"
+#include "hlb_fast.cuh"   // packed-byte primitives (funnel shift, byte dot product, saturating pack) for svc_resample_row4
 
 namespace hlb {
 
@@ -388,6 +389,55 @@ HLB_HD uint8_t svc_resample_px(const uint8_t* ref, int refW, int refH, const Svc
         for (int j = 0; j < 4; ++j) v += svc_rs_luma_tap(fx, j) * t[j];
     }
     return (uint8_t)clip255((v + 512) >> 10);
+}
+
+// Four horizontally adjacent output samples (x0 .. x0 + 3, x0 a multiple of 4) of row y as one word -- what a thread of k_svc_resample_intra stores.  The two passes
+// of the reference ((G-301) vertical, (G-305) horizontal) carry no rounding between them, so the filter is the exact 2-D sum  sum_k fy[k] sum_j fx[j] s[k][j]  and
+// the inner (horizontal) sum is a byte dot product: the row's samples xs .. xs + 7 are fetched ONCE as three aligned words and shifted into an 8-byte window, each
+// output takes its four bytes from it by a funnel shift (its reference column differs from the first output's by at most 3 when the layer is not smaller than the
+// reference layer) and multiplies them with its packed taps (Table G-9 rows / the two-tap chroma weights).  12 word loads per thread instead of 64 byte loads with
+// per-sample clamps.  Threads whose window would leave the row (picture edges) and layers that shrink take the per-sample form; the rows are clamped as the reference
+// clamps them.  Same results as four svc_resample_px calls (tests/test_svc_bl_resample.py runs this form on the CPU against the oracle).
+HLB_HD uint32_t svc_resample_row4(const uint8_t* ref, int refW, int refH, const SvcRsAxis& ax, const SvcRsAxis& ay, int x0, int y, bool chroma)
+{
+    const int y16 = svc_rs_ref16(y, ay), yr = y16 >> 4, yp = y16 & 15;
+    int xr[4];
+    uint32_t fx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x16 = svc_rs_ref16(x0 + i, ax), xp = x16 & 15;
+        xr[i] = x16 >> 4;
+        fx[i] = chroma ? (uint32_t)(32 - 2 * xp) | ((uint32_t)(2 * xp) << 8) : kSvcRsLuma[xp];
+    }
+    const int xs = xr[0] - (chroma ? 0 : 1), xa = xs & ~3;
+    const int d1 = xr[1] - xr[0], d2 = xr[2] - xr[0], d3 = xr[3] - xr[0];
+    const bool fast = xs >= 0 && xa + 12 <= refW && (unsigned)d1 <= 3u && (unsigned)d2 <= 3u && (unsigned)d3 <= 3u;
+    if (!fast) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) word |= (uint32_t)svc_resample_px(ref, refW, refH, ax, ay, x0 + i, y, chroma) << (8 * i);
+        return word;
+    }
+    // the vertical taps as four plain integers (chroma: the two-tap weights, rows yr and yr + 1; luma: Table G-9 row yp, rows yr - 1 .. yr + 2)
+    const uint32_t fyl = kSvcRsLuma[yp], sh = (uint32_t)(xs & 3) * 8, s1 = (uint32_t)d1 * 8, s2 = (uint32_t)d2 * 8, s3 = (uint32_t)d3 * 8;
+    const int fy0 = chroma ? 0 : svc_rs_luma_tap(fyl, 0), fy1 = chroma ? 32 - 2 * yp : svc_rs_luma_tap(fyl, 1), fy2 = chroma ? 2 * yp : svc_rs_luma_tap(fyl, 2),
+              fy3 = chroma ? 0 : svc_rs_luma_tap(fyl, 3);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(ref + xa);   // row r of the window starts refW / 4 words further (plane widths are multiples of 8)
+    const int pitch4 = refW >> 2, r0 = yr - 1;
+    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int fyk = k == 0 ? fy0 : (k == 1 ? fy1 : (k == 2 ? fy2 : fy3));
+        if (chroma && (k == 0 || k == 3)) continue;
+        const uint32_t* q = base + clip3(0, refH - 1, r0 + k) * pitch4;
+        const uint32_t w0 = HLB_LDG(q), w1 = HLB_LDG(q + 1), w2 = HLB_LDG(q + 2);
+        const uint32_t lo = p_shf_r(w0, w1, sh), hi = p_shf_r(w1, w2, sh);   // samples xs .. xs + 7 of the row
+        acc0 += fyk * p_dp4a_us(lo, fx[0], 0);
+        acc1 += fyk * p_dp4a_us(p_shf_r(lo, hi, s1), fx[1], 0);
+        acc2 += fyk * p_dp4a_us(p_shf_r(lo, hi, s2), fx[2], 0);
+        acc3 += fyk * p_dp4a_us(p_shf_r(lo, hi, s3), fx[3], 0);
+    }
+    return pack4_sat((acc0 + 512) >> 10, (acc1 + 512) >> 10, (acc2 + 512) >> 10, (acc3 + 512) >> 10);
 }
 
 }  // namespace hlb

@@ -46,8 +46,12 @@ extern "C" __attribute__((visibility("default"))) int svc_emu_recon_batch(int bl
 extern "C" __attribute__((visibility("default"))) int svc_emu_resample_plane(const uint8_t* ref, int refW, int refH, uint8_t* out, int W, int H, int chroma, int level_idc)
 {
     const hlb::SvcRsAxis ax = hlb::svc_rs_axis(refW, W, level_idc), ay = hlb::svc_rs_axis(refH, H, level_idc);
+    // the form the kernel's threads run: four samples per call (svc_resample_row4), which itself falls back to the per-sample form at the picture edges
     for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) out[y * W + x] = hlb::svc_resample_px(ref, refW, refH, ax, ay, x, y, chroma != 0);
+        for (int x = 0; x < W; x += 4) {
+            const uint32_t w = hlb::svc_resample_row4(ref, refW, refH, ax, ay, x, y, chroma != 0);
+            for (int i = 0; i < 4; ++i) out[y * W + x + i] = (uint8_t)(w >> (8 * i));
+        }
     return HLB200_OK;
 }
 
