@@ -42,7 +42,7 @@ __device__ __forceinline__ void load_win9(const uint8_t* __restrict__ plane, int
 #define HLB_IL_MINB 5   // 48 registers: +5 % (profiles/r02v2_variants.log)
 #endif
 __global__ void __launch_bounds__(256, HLB_IL_MINB) k_interp_luma(const uint8_t* __restrict__ ref, int W, int H, int mbw, int nmb,
-                                                     const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred, size_t stride)
+                                                     const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred, size_t stride, uint32_t rcp_mbw)
 {
     const int bw = W >> 2, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bw * (H >> 2)) return;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256, HLB_IL_MINB) k_interp_luma(const uint8_t*
     const int gy4 = t / bw, gx = (t - gy4 * bw) << 2, gy = gy4 << 2;
     const int mbx = gx >> 4, mby = gy >> 4, bx = gx & 15, by = gy & 15;
 #else                  // blocks in macroblock order (luma4x4BlkIdx inside): a warp = two macroblocks, so it meets the fractional classes of two macroblocks' partitions only
-    const int mb = t >> 4, b4 = t & 15, mbx = mb % mbw, mby = mb / mbw, bx = blk_x(b4), by = blk_y(b4);
+    const int mb = t >> 4, b4 = t & 15, mby = div_rcp(mb, mbw, rcp_mbw), mbx = mb - mby * mbw, bx = blk_x(b4), by = blk_y(b4);
     const int gx = mbx * 16 + bx, gy = mby * 16 + by;
 #endif
     const hlb200_mb_motion_t* m = motion + mby * mbw + mbx;
@@ -89,12 +89,12 @@ __global__ void __launch_bounds__(256, HLB_IL_MINB) k_interp_luma(const uint8_t*
 // do not run the two variants one after the other (the first packed version did: 360 warp instructions per thread, 17 of 32 lanes active on average).
 // The sample pairs come from fast_chroma_two (hlb_fast.cuh).
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
-                                                       const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride)
+                                                       const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride, uint32_t rcp_sw)
 {
     const int Wc = W >> 1, Hc = H >> 1, sw = Wc >> 2, per_plane = sw * Hc;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * per_plane) return;
-    const int plane = t >= per_plane, s = t - plane * per_plane, cy = s / sw, cx = (s - cy * sw) << 2;
+    const int plane = t >= per_plane, s = t - plane * per_plane, cy = div_rcp(s, sw, rcp_sw), cx = (s - cy * sw) << 2;
     const uint8_t* rp = (plane ? ref_v : ref_u) + blockIdx.y * stride;
     uint8_t* dst = (plane ? pred_v : pred_u) + blockIdx.y * stride + (size_t)cy * Wc + cx;
     const hlb200_mb_motion_t* m = motion + (size_t)blockIdx.y * nmb + (cy >> 3) * mbw + (cx >> 3);
@@ -164,7 +164,7 @@ __device__ __forceinline__ void transpose4_u2(uint2 P[4], int lane)
 __global__ void __launch_bounds__(128, HLB_TQ_MINB) k_tq_recon(const uint8_t* __restrict__ src_y, const uint8_t* __restrict__ src_u, const uint8_t* __restrict__ src_v,
                                                   const uint8_t* __restrict__ pred_y, const uint8_t* __restrict__ pred_u, const uint8_t* __restrict__ pred_v,
                                                   int W, int H, int mbw, int nmb, int qp, int qpc, hlb200_mb_coeffs_t* __restrict__ coeffs,
-                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride, int luma_ctas)
+                                                  uint8_t* __restrict__ rec_y, uint8_t* __restrict__ rec_u, uint8_t* __restrict__ rec_v, size_t stride, int luma_ctas, uint32_t rcp_mbw)
 {
     __shared__ TqConst K;
     if (threadIdx.x < 2) quantk_device(threadIdx.x ? K.chroma : K.luma, threadIdx.x ? qpc : qp, threadIdx.x != 0);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, HLB_TQ_MINB) k_tq_recon(const uint8_t* __
         // ---------------- luma: t = macroblock * 16 + luma4x4BlkIdx ----------------
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
         const bool valid = t < nmb * 16;
-        const int mb = valid ? t >> 4 : 0, b = t & 15, mbx = mb % mbw, mby = mb / mbw;
+        const int mb = valid ? t >> 4 : 0, b = t & 15, mby = div_rcp(mb, mbw, rcp_mbw), mbx = mb - mby * mbw;
         const size_t off = po + (size_t)(mby * 16 + blk_y(b)) * W + mbx * 16 + blk_x(b);
         Rows4 sv, pv;
         bool res_nz = false;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(128, HLB_TQ_MINB) k_tq_recon(const uint8_t* __
     // ---------------- chroma: t = macroblock * 8 + plane * 4 + block (raster) ----------------
     const int t = ((int)blockIdx.x - luma_ctas) * blockDim.x + threadIdx.x;
     const bool valid = t < nmb * 8;
-    const int mb = valid ? t >> 3 : 0, plane = (t >> 2) & 1, cblk = t & 3, mbx = mb % mbw, mby = mb / mbw, Wc = W >> 1;
+    const int mb = valid ? t >> 3 : 0, plane = (t >> 2) & 1, cblk = t & 3, mby = div_rcp(mb, mbw, rcp_mbw), mbx = mb - mby * mbw, Wc = W >> 1;
     const size_t off = po + (size_t)(mby * 8 + (cblk >> 1) * 4) * Wc + mbx * 8 + (cblk & 1) * 4;
     const uint8_t* s = plane ? src_v : src_u;
     const uint8_t* p = plane ? pred_v : pred_u;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128, HLB_TQ_MINB) k_tq_recon(const uint8_t* __
 #endif
 template <bool BL>
 __global__ void __launch_bounds__(128, HLB_SVC_MINB) k_svc_inter_recon(SvcPlanes P, int mbw, int nmb, int qp, int qpc, const hlb200_mb_motion_t* __restrict__ motion,
-                                                         hlb200_svc_mb_state_t* __restrict__ state, hlb200_mb_coeffs_t* __restrict__ coeffs, size_t stride, int luma_ctas)
+                                                         hlb200_svc_mb_state_t* __restrict__ state, hlb200_mb_coeffs_t* __restrict__ coeffs, size_t stride, int luma_ctas, uint32_t rcp_mbw)
 {
     __shared__ TqConst K;
     if (threadIdx.x < 2) quantk_device(threadIdx.x ? K.chroma : K.luma, threadIdx.x ? qpc : qp, true);   // luma too takes the intra offset here (rdo.c:1468)
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128, HLB_SVC_MINB) k_svc_inter_recon(SvcPlanes
         // ---------------- luma: t = macroblock * 16 + luma4x4BlkIdx ----------------
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
         const bool valid = t < nmb * 16;
-        const int mb = valid ? t >> 4 : 0, b = t & 15, mbx = mb % mbw, mby = mb / mbw, bx = blk_x(b), by = blk_y(b);
+        const int mb = valid ? t >> 4 : 0, b = t & 15, mby = div_rcp(mb, mbw, rcp_mbw), mbx = mb - mby * mbw, bx = blk_x(b), by = blk_y(b);
         const size_t off = po + (size_t)(mby * 16 + by) * W + mbx * 16 + bx;
         Rows4 sv, pv;
         if (BL) {
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(128, HLB_SVC_MINB) k_svc_inter_recon(SvcPlanes
     // ---------------- chroma: t = macroblock * 8 + plane * 4 + block (raster) ----------------
     const int t = ((int)blockIdx.x - luma_ctas) * blockDim.x + threadIdx.x;
     const bool valid = t < nmb * 8;
-    const int mb = valid ? t >> 3 : 0, plane = (t >> 2) & 1, cblk = t & 3, mbx = mb % mbw, mby = mb / mbw, Wc = W >> 1, Hc = H >> 1;
+    const int mb = valid ? t >> 3 : 0, plane = (t >> 2) & 1, cblk = t & 3, mby = div_rcp(mb, mbw, rcp_mbw), mbx = mb - mby * mbw, Wc = W >> 1, Hc = H >> 1;
     const int bx = (cblk & 1) * 4, by = (cblk >> 1) * 4;
     const size_t off = po + (size_t)(mby * 8 + by) * Wc + mbx * 8 + bx;
     const uint8_t* s = plane ? P.src_v : P.src_u;
@@ -654,7 +654,7 @@ int hlb200_dev_interp_luma_batch(const uint8_t* d_ref_y, int width, int height, 
 {
     if (!d_ref_y || !d_motion || !d_pred_y || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_interp_luma<<<dim3((nmb * 16 + 127) / 128, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, width, height, mbw, nmb, d_motion, d_pred_y, frame_stride);
+    k_interp_luma<<<dim3((nmb * 16 + 127) / 128, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_ref_y, width, height, mbw, nmb, d_motion, d_pred_y, frame_stride, host_rcp32(mbw, width, height));
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
@@ -668,7 +668,7 @@ int hlb200_dev_interp_chroma_batch(const uint8_t* d_ref_u, const uint8_t* d_ref_
 {
     if (!d_ref_u || !d_ref_v || !d_motion || !d_pred_u || !d_pred_v || (width & 15) || (height & 15) || n_pics < 1 || n_pics > 65535) return HLB200_ERR_INVALID_PARAMETER;
     const int mbw = width >> 4, nmb = mbw * (height >> 4);
-    k_interp_chroma<<<dim3((nmb * 32 + 255) / 256, n_pics), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v, frame_stride);
+    k_interp_chroma<<<dim3((nmb * 32 + 255) / 256, n_pics), 256, 0, (cudaStream_t)cuda_stream>>>(d_ref_u, d_ref_v, width, height, mbw, nmb, d_motion, d_pred_u, d_pred_v, frame_stride, host_rcp32(width >> 3, width, height));
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
@@ -688,7 +688,7 @@ int hlb200_dev_tq_recon_batch(const uint8_t* d_src_y, const uint8_t* d_src_u, co
     const int luma_ctas = (nmb * 16 + 127) / 128, chroma_ctas = (nmb * 8 + 127) / 128;
     k_tq_recon<<<dim3(luma_ctas + chroma_ctas, n_pics), 128, 0, (cudaStream_t)cuda_stream>>>(d_src_y, d_src_u, d_src_v, d_pred_y, d_pred_u, d_pred_v, width, height, mbw, nmb, qp,
                                                                                              host_chroma_qp(qp, chroma_qp_index_offset), d_coeffs, d_recon_y, d_recon_u, d_recon_v,
-                                                                                             frame_stride, luma_ctas);
+                                                                                             frame_stride, luma_ctas, host_rcp32(mbw, width, height));
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }
@@ -713,8 +713,8 @@ static int launch_svc(bool bl, const uint8_t* d_src_y, const uint8_t* d_src_u, c
     P.rec_y = d_recon_y; P.rec_u = d_recon_u; P.rec_v = d_recon_v; P.W = width; P.H = height;
     const int luma_ctas = (nmb * 16 + 127) / 128, chroma_ctas = (nmb * 8 + 127) / 128;
     const dim3 grid(luma_ctas + chroma_ctas, n_pics);
-    if (bl) k_svc_inter_recon<true><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, nullptr, d_state, d_coeffs, frame_stride, luma_ctas);
-    else k_svc_inter_recon<false><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, d_motion, d_state, d_coeffs, frame_stride, luma_ctas);
+    if (bl) k_svc_inter_recon<true><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, nullptr, d_state, d_coeffs, frame_stride, luma_ctas, host_rcp32(mbw, width, height));
+    else k_svc_inter_recon<false><<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(P, mbw, nmb, qp, qpc, d_motion, d_state, d_coeffs, frame_stride, luma_ctas, host_rcp32(mbw, width, height));
     HLB_CUDA(cudaGetLastError());
     return HLB200_OK;
 }

@@ -50,6 +50,12 @@ HLB_HD PartGeom part_of(int part_mode, const uint8_t sub_mode[4], int bx, int by
     return g;
 }
 
+// Index division by a per-launch constant (macroblocks per row, words per row) as ONE multiply-high: rcp = ceil(2^32 / d) gives the exact quotient while
+// n * (rcp * d - 2^32) < 2^32, which holds for every index of a plane up to 8192 x 8192 (n < 2^22, d <= 1024); 0 = "d is 1", 1 = "use the divider" (larger planes).
+// The generic 32-bit division costs ~25 instructions per thread, which showed up as 4-6 % of the whole-picture kernels (profiles/r02v5_*).
+inline uint32_t host_rcp32(int d, int w, int h) { return d <= 1 ? 0u : ((w > 8192 || h > 8192) ? 1u : (uint32_t)((0x100000000ull + (unsigned)d - 1) / (unsigned)d)); }
+__device__ __forceinline__ int div_rcp(int n, int d, uint32_t rcp) { return rcp > 1u ? (int)__umulhi((uint32_t)n, rcp) : (rcp ? n / d : n); }
+
 // chroma QP (8.5.8; source/h264/hl_codec_264_mb.c:375-418)
 HLB_HD int chroma_qp(int qp_y, int offset) { return kQpc[clip3(0, 51, qp_y + offset)]; }
 // host-side twin (the device tables are not readable from host code)
