@@ -247,6 +247,7 @@ typedef struct glue_svc_layer_s {
     uint8_t* rec;            /* tight Y|U|V */
     hlb200_svc_base_mb_t* base; int nbase;   /* the reference layer's macroblock fields, as uploaded for the derivation */
     int dev;                                 /* GPU of this layer's context (glue_layer_device) */
+    const void* codec;                       /* the hl_codec_264_t this layer context belongs to: another instance gets a fresh context (carried state, resident pictures) */
     const void* fs_of_slot[2];               /* host frame store whose picture lives in each of the layer context's two device slots (reconstructions stay resident) */
 } glue_svc_layer_t;
 static glue_svc_layer_t g_svc[GLUE_SVC_MAX_LAYERS];
@@ -345,10 +346,10 @@ static HL_ERROR_T glue_svc_slice(hl_codec_264_t* p_codec, hl_codec_264_encode_sl
     }
     L = &g_svc[li];
     if ((rc = glue_use_device(glue_layer_device(li)))) return glue_fail("hlb200_init", rc);
-    if (!L->ctx || L->w != W || L->h != H || L->dev != g_dev_cur) {
+    if (!L->ctx || L->w != W || L->h != H || L->dev != g_dev_cur || L->codec != (const void*)p_codec) {
         if (L->ctx) { const int now = g_dev_cur; if (glue_use_device(L->dev) == 0) hlb200_stream_destroy(L->ctx); glue_use_device(now); L->ctx = NULL; free(L->motion); free(L->coeffs); free(L->rec); free(L->base); L->motion = NULL; L->coeffs = NULL; L->rec = NULL; L->base = NULL; L->nbase = 0; }
         if ((rc = hlb200_stream_create(W, H, 1, &L->ctx))) return glue_fail("hlb200_stream_create", rc);
-        L->dev = g_dev_cur;
+        L->dev = g_dev_cur; L->codec = (const void*)p_codec;
         L->w = W; L->h = H; L->nmb = mbw * (H >> 4); L->fs_of_slot[0] = L->fs_of_slot[1] = NULL;
         L->motion = (hlb200_mb_motion_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_motion_t));
         L->coeffs = (hlb200_mb_coeffs_t*)calloc((size_t)L->nmb, sizeof(hlb200_mb_coeffs_t));
