@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(256, HLB_IL_MINB) k_interp_luma(const uint8_t*
 // (8 luma samples wide: one motion vector unless the macroblock is split into 4-wide sub-partitions, then two).  Written as ONE control flow for both cases:
 // every thread forms its two sample pairs from their own vectors (equal in the common case), so warps that straddle macroblocks of different partition layouts
 // do not run the two variants one after the other (the first packed version did: 360 warp instructions per thread, 17 of 32 lanes active on average).
-// The sample pairs come from fast_chroma_two (hlb_fast.cuh).
+// The sample pairs come from fast_chroma_two (hlb_fast.cuh).  Measured again at the end of round 2 (profiles/r02v8_chroma_four_dropped.log): a second path that fetches the
+// two rows once for the four samples when both halves share a vector executes fewer instructions per thread (8 loads -> 4) but made the kernel 17 % SLOWER (0.141 -> 0.117
+// of the HBM peak) -- the test field mixes layouts inside a warp and both paths run.
 __global__ void __launch_bounds__(256) k_interp_chroma(const uint8_t* __restrict__ ref_u, const uint8_t* __restrict__ ref_v, int W, int H, int mbw, int nmb,
                                                        const hlb200_mb_motion_t* __restrict__ motion, uint8_t* __restrict__ pred_u, uint8_t* __restrict__ pred_v, size_t stride, uint32_t rcp_sw)
 {
