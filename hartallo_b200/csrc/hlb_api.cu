@@ -300,7 +300,8 @@ int hlb200_svc_layer_picture_derived(hlb200_ctx_t* c, int ref_slot, int cur_slot
     if ((rc = h2d(c, d_base, base, sizeof(hlb200_svc_base_mb_t) * nref))) return rc;
     HLB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), c->stream));
     if ((rc = hlb200_dev_svc_derive_motion_batch(d_base, geom, c->width, c->height, 1, c->d_svc_had_parts, d_motion, d_status, c->stream))) return rc;
-    // the status decides whether the picture may be coded at all: one small read-back before the big kernel (a refused picture must not touch the layer's state)
+    // the status decides whether the picture may be coded at all: one small read-back before the big kernel (a refused picture leaves the frame stores and the carried
+    // chroma levels alone; the per-macroblock flags are those after its derivation, as the reference's macroblock objects would be)
     int32_t st = 0;
     if ((rc = d2h(c, &st, d_status, sizeof(st)))) return rc;
     if (out_motion && (rc = d2h(c, out_motion, d_motion, sizeof(hlb200_mb_motion_t) * c->nmb))) return rc;
