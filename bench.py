@@ -435,6 +435,24 @@ def slice_workload(args, rank, world, local, dev, torch, dist, hl, lib, synth, s
                                           "ms_per_p_access_unit": bj["ms_p_frames"] / max(bj["p_frames"], 1), "reference_ms_per_p_access_unit": rj["ms_p_frames"] / max(rj["p_frames"], 1),
                                           "bitstream_bytes": bj["bytes"], "bitstream_equal": bool(bj["md5"] == rj["md5"] and bj["bytes"] == rj["bytes"]),
                                           "note": "single stream: the layers of one access unit follow each other (the enhancement layers read the layer below), the device is mostly idle"}
+        if world >= 3 and not args.no_all_inter:
+            # the same three layers with ONE LAYER PER GPU: layer k's context on GPU k, the I-picture hand-off GPU to GPU.  The ranks have
+            # finished their timed region; the byte stream must equal the all-CPU reference's.  (No speed-up is expected: the reference's API codes the layers of an access
+            # unit one after the other)
+            enc_b, enc_r = os.path.join(ROOT, "oracle", "_ref", "hl_b200_encoder"), os.path.join(ROOT, "oracle", "_ref", "hl_ref_driver")
+            if os.path.exists(enc_b) and os.path.exists(enc_r):
+                a = ["--layers", "3", "--size", "176", "144", "--frames", "6", "--gen", "g1"]
+                try:
+                    ro = subprocess.run([enc_r] + a, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+                    bo = subprocess.run([enc_b] + a, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120, env=dict(os.environ, HLB200_SVC_DEVICES="0,1,2"))
+                    if ro.returncode == 0 and bo.returncode == 0:
+                        rj, bj = json.loads(ro.stdout.strip().splitlines()[-1]), json.loads(bo.stdout.strip().splitlines()[-1])
+                        line["svc_layers_over_gpus"] = {"config": "QCIF -> CIF -> 4CIF (BASELINE.json configs[3]), 1 stream, layer k on GPU k (HLB200_SVC_DEVICES=0,1,2)",
+                                                        "ms_per_p_access_unit": bj["ms_p_frames"] / max(bj["p_frames"], 1),
+                                                        "reference_ms_per_p_access_unit": rj["ms_p_frames"] / max(rj["p_frames"], 1), "bitstream_bytes": bj["bytes"],
+                                                        "bitstream_equal": bool(bj["md5"] == rj["md5"] and bj["bytes"] == rj["bytes"])}
+                except Exception as ex:   # reported, never fatal for the throughput line
+                    line["svc_layers_over_gpus"] = {"error": str(ex)[:200]}
         if world == 1 and not args.no_hbm_kernels:
             # the stateless whole-picture kernels (interpolation, transform-quantisation-reconstruction, the SVC base-mode kernels): HBM rooflines at 128 pictures per launch
             torch.cuda.empty_cache()
