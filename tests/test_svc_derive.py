@@ -114,7 +114,10 @@ def test_device_source_vs_golden():
 def test_live_reference(tmp_path):
     o = _oracle()
     for name, args in [("g2_3layer", ["--size", "48", "32", "--layers", "3", "--frames", "4", "--gen", "g2", "--seed", "77", "--qp", "33"]),
-                       ("g1_2layer", ["--size", "96", "64", "--layers", "2", "--frames", "3", "--gen", "g1", "--seed", "4", "--qp", "28"])]:
+                       ("g1_2layer", ["--size", "96", "64", "--layers", "2", "--frames", "3", "--gen", "g1", "--seed", "4", "--qp", "28"]),
+                       # layers scaled 3:2 (ref_driver --scale): the general case of G.8.6.1 with its replacement / merging steps, sub-macroblock partitions
+                       ("g2_ess", ["--size", "64", "192", "--layers", "3", "--frames", "3", "--gen", "g2", "--seed", "5147", "--qp", "44", "--scale", "3", "2"]),
+                       ("g1_ess", ["--size", "128", "64", "--layers", "2", "--frames", "4", "--gen", "g1", "--seed", "9", "--qp", "27", "--scale", "3", "2"])]:
         tr = str(tmp_path / (name + ".trace"))
         S.run_driver_svc(args + ["--no-levels"], tr)
         pics = S.derive_pictures_from_trace(tr)
